@@ -1,0 +1,191 @@
+/*
+ * thetis_b200 -- C ABI of the B200-native explicit P1DG shallow-water stepper.
+ *
+ * This is the drop-in boundary for ONE hot path of thetisproject/thetis: the
+ * explicit SSPRK33 step of `ShallowWaterEquations` on P1DG-P1DG triangles, the
+ * explicit 2-D tracer advection and `VertexBasedP1DGLimiter`.  The reference has
+ * no FFI of its own (it is pure Python on Firedrake); each entry point below
+ * names the reference interface whose work it replaces (paths relative to the
+ * thetis repository).  The Python class that mirrors
+ * `thetis.timeintegrator.TimeIntegrator` binds these with ctypes
+ * (thetis_b200/_lib.py); INTEGRATION.md shows the stub a Thetis maintainer adds.
+ *
+ * Conventions: extern "C"; every function returns 0 on success or a negative
+ * tb_status; no exceptions, no ownership transfer.  Mesh/coefficient arrays
+ * handed to tb_create / tb_set_* are HOST pointers read once at set-up.  All
+ * bulk state pointers (u_in, u_out, ...) are caller-owned DEVICE pointers
+ * (e.g. torch.Tensor.data_ptr()).  `stream` is a cudaStream_t passed as void*;
+ * nothing synchronises the stream unless stated.
+ *
+ * Device state layout ("cell records"): for local cell c, 9 doubles
+ *   [u0x u0y u1x u1y u2x u2y eta0 eta1 eta2]      (nodes in the cell's CCW order)
+ * in an array of tb_state_len() doubles: owned cells padded to a multiple of
+ * the patch size, followed by ghost cells (multi-GPU halo).
+ */
+#ifndef THETIS_B200_H
+#define THETIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tb_ctx tb_ctx;
+
+typedef enum {
+    TB_OK = 0,
+    TB_ERR_ARG = -1,        /* invalid argument */
+    TB_ERR_CUDA = -2,       /* CUDA runtime error (see tb_last_error) */
+    TB_ERR_UNSUPPORTED = -3,/* configuration outside the accelerated path */
+    TB_ERR_STATE = -4       /* call order / missing data */
+} tb_status;
+
+/* Mesh connectivity, HOST arrays, read once (what the adaptor extracts from
+ * Firedrake's mesh.coordinates / cell_node_map / exterior_facets; see
+ * SURVEY.md 8b).  Cells must be counter-clockwise. */
+typedef struct {
+    int64_t n_cells;        /* owned + ghost cells                               */
+    int64_t n_owned;        /* cells [0, n_owned) are advanced; the rest are ghosts */
+    int64_t n_vertices;     /* geometric vertices                                */
+    int64_t n_bfacets;      /* exterior facets                                   */
+    const double  *coords;  /* [n_vertices*2]                                    */
+    const int32_t *cells;   /* [n_cells*3] geometric vertex ids                  */
+    const int32_t *nbr;     /* [n_cells*3] neighbour across local facet i (opposite
+                               vertex i), or -(1+k) for exterior facet k; for
+                               ghost cells entries may be INT32_MIN (unknown)    */
+    const int8_t  *nbr_lf;  /* [n_cells*3] local facet number inside the neighbour */
+    const int32_t *bf_marker;/* [n_bfacets] boundary marker id                    */
+    const int32_t *topo;    /* [n_vertices] topological vertex id (periodic meshes;
+                               may be NULL = identity); used by the limiter      */
+} tb_mesh;
+
+/* Scalar options: `ModelOptions2d` flags consumed on this path
+ * (thetis/options.py:596-611,712,871-881) and thetis/physical_constants.py. */
+typedef enum {
+    TB_OPT_G_GRAV = 0,                 /* physical_constants['g_grav']            */
+    TB_OPT_RHO0 = 1,                   /* physical_constants['rho0']              */
+    TB_OPT_NONLINEAR = 2,              /* use_nonlinear_equations                 */
+    TB_OPT_LAX_FRIEDRICHS = 3,         /* use_lax_friedrichs_velocity             */
+    TB_OPT_LF_SCALING = 4,             /* lax_friedrichs_velocity_scaling_factor  */
+    TB_OPT_NORM_SMOOTHER = 5,          /* norm_smoother                           */
+    TB_OPT_WETTING_DRYING = 6,         /* use_wetting_and_drying                  */
+    TB_OPT_WD_ALPHA = 7,               /* wetting_and_drying_alpha (constant)     */
+    TB_OPT_LF_TRACER = 8,              /* use_lax_friedrichs_tracer               */
+    TB_OPT_LF_TRACER_SCALING = 9,      /* lax_friedrichs_tracer_scaling_factor    */
+    TB_OPT_TRACER_VEL_FACTOR = 10      /* tracer_advective_velocity_factor        */
+} tb_option;
+
+/* Coefficient fields: the `fields` dict of solver2d.py:546-558 plus bathymetry. */
+typedef enum {
+    TB_F_BATHYMETRY = 0,       /* DepthExpression.bathymetry_2d (utility.py:965)  */
+    TB_F_CORIOLIS = 1,         /* 'coriolis'                                      */
+    TB_F_MANNING = 2,          /* 'manning_drag_coefficient'                      */
+    TB_F_QUAD_DRAG = 3,        /* 'quadratic_drag_coefficient'                    */
+    TB_F_LINEAR_DRAG = 4,      /* 'linear_drag_coefficient'                       */
+    TB_F_WIND_STRESS = 5,      /* 'wind_stress' (2 components)                    */
+    TB_F_ATM_PRESSURE = 6,     /* 'atmospheric_pressure'                          */
+    TB_F_MOMENTUM_SOURCE = 7,  /* 'momentum_source' (2 components)                */
+    TB_F_VOLUME_SOURCE = 8,    /* 'volume_source'                                 */
+    TB_F_TRACER_SOURCE = 9,    /* 'source-<label>' of the tracer equation         */
+    TB_F_COUNT = 10
+} tb_field;
+
+/* Boundary tags (shallowwater_eq.py:243-267); a marker's opcode is the OR of
+ * the tags present.  0 = closed (land) boundary. */
+enum { TB_BC_ELEV = 1, TB_BC_UV = 2, TB_BC_UN = 4, TB_BC_FLUX = 8, TB_BC_VALUE = 16 };
+
+/* ---- lifetime ---------------------------------------------------------- */
+int tb_create(tb_ctx **out, const tb_mesh *mesh, int device);
+int tb_destroy(tb_ctx *ctx);
+const char *tb_last_error(const tb_ctx *ctx);   /* ctx may be NULL: create errors */
+int tb_version(void);
+
+/* ---- sizes ------------------------------------------------------------- */
+int64_t tb_state_len(const tb_ctx *ctx);        /* doubles in an SWE state array    */
+int64_t tb_tracer_len(const tb_ctx *ctx);       /* doubles in a tracer array (3/cell) */
+int64_t tb_patch_size(const tb_ctx *ctx);
+int64_t tb_n_patches(const tb_ctx *ctx);
+
+/* ---- options / coefficients / boundary conditions ---------------------- */
+int tb_set_option(tb_ctx *ctx, int option, double value);
+/* constant coefficient (Firedrake `Constant`); ncomp = 1 or 2 */
+int tb_set_field_const(tb_ctx *ctx, int field, const double *value, int ncomp);
+/* P1 coefficient given at the geometric vertices, HOST [n_vertices*ncomp] */
+int tb_set_field_vertex(tb_ctx *ctx, int field, const double *values, int ncomp);
+int tb_clear_field(tb_ctx *ctx, int field);     /* field = None                     */
+/* Boundary condition of one marker for equation eq (0 = shallow water,
+ * 1 = tracer): opcode = OR of TB_BC_*, consts = {elev, uv_x, uv_y, un, flux, value}.
+ * replaces ShallowWaterTerm.get_bnd_functions (shallowwater_eq.py:232-272)
+ * and TracerTerm.get_bnd_functions (tracer_eq_2d.py:78-115) */
+int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const double consts[6]);
+/* Spatially varying datum for one tag of one marker: HOST values at the two
+ * nodes of every exterior facet of the mesh, [n_bfacets*2*ncomp] (entries of
+ * other markers ignored).  Copied asynchronously on `stream`. */
+int tb_set_bc_array(tb_ctx *ctx, int eq, int marker, int tag, const double *values,
+                    int ncomp, void *stream);
+int tb_set_boundary_length(tb_ctx *ctx, int marker, double length); /* utility.py:821-832 */
+
+/* Cell quadrature for the non-polynomial cell integrands (Manning drag, wind
+ * stress / H, wetting-drying): n <= 12 points, barycentric lam[n*3], weights
+ * summing to 1.  Default: the 6-point degree-3 Strang-Fix rule (the reference
+ * asks for degree 2p+1 = 3, shallowwater_eq.py:225-230; FIAT's default rule for
+ * that degree is version dependent). */
+int tb_set_cell_quadrature(tb_ctx *ctx, int n, const double *lam, const double *w);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* One Shu-Osher stage of ERKGenericShuOsher.solve_stage (rungekutta.py:929-946)
+ * fused with the residual assembly (shallowwater_eq.py:886-890), the P1DG mass
+ * solve (rungekutta.py:921-924) and the stage update:
+ *      u_out = a0*u0 + a1*u_in + b_dt * M^-1 R(u_in)
+ * u0 may be NULL when a0 == 0.  u_out must not alias u_in. */
+int tb_swe_stage(tb_ctx *ctx, double a0, double a1, double b_dt,
+                 const double *u_in, const double *u0, double *u_out, void *stream);
+/* Parity hook: k = M^-1 R(u)  (the `tendency` of rungekutta.py:940 for dt = 1) */
+int tb_swe_tendency(tb_ctx *ctx, const double *u, double *k_out, void *stream);
+/* Same for TracerEquation2D (tracer_eq_2d.py:147-193, 293-298) with the frozen
+ * SWE state `swe_state` providing uv_2d / elev_2d (solver2d.py:580-598). */
+int tb_tracer_stage(tb_ctx *ctx, double a0, double a1, double b_dt,
+                    const double *c_in, const double *c0, double *c_out,
+                    const double *swe_state, void *stream);
+/* VertexBasedP1DGLimiter.apply (limiter.py:182-198), in place. */
+int tb_limiter_apply(tb_ctx *ctx, double *c, void *stream);
+
+/* ---- layout conversion & diagnostics ----------------------------------- */
+/* Thetis' mixed Function layout <-> cell records.  uv: [n_nodes*2] interleaved,
+ * eta: [n_nodes]; node_map: DEVICE int32 [n_cells*3] giving, for local cell c and
+ * CCW local node a, the index of that dof in the Thetis arrays (cell_node_map
+ * composed with the renumbering).  All pointers are device pointers. */
+int tb_state_from_fields(tb_ctx *ctx, const double *uv, const double *eta,
+                         const int32_t *node_map, double *state, void *stream);
+int tb_state_to_fields(tb_ctx *ctx, const double *state, const int32_t *node_map,
+                       double *uv, double *eta, void *stream);
+int tb_tracer_from_field(tb_ctx *ctx, const double *q, const int32_t *node_map,
+                         double *c, void *stream);
+int tb_tracer_to_field(tb_ctx *ctx, const double *c, const int32_t *node_map,
+                       double *q, void *stream);
+/* out[0] = int eta^2 dx, out[1] = int |u|^2 dx, out[2] = int eta dx over owned
+ * cells (print_state norms, solver2d.py:955-956; VolumeConservation2DCallback).
+ * `out` is a DEVICE pointer to 4 doubles. */
+int tb_swe_integrals(tb_ctx *ctx, const double *state, double *out, void *stream);
+
+/* ---- multi-GPU halo (one-deep element halo) -------------- */
+/* Gather the records of `n` cells listed in DEVICE idx into a contiguous
+ * buffer / scatter them back; used to pack the per-peer send buffers that
+ * torch.distributed (NCCL) exchanges once per RK stage. */
+int tb_gather_cells(tb_ctx *ctx, const double *state, const int32_t *idx, int64_t n,
+                    int rec_len, double *buf, void *stream);
+int tb_scatter_cells(tb_ctx *ctx, const double *buf, const int32_t *idx, int64_t n,
+                     int rec_len, double *state, void *stream);
+/* Restrict the next tb_swe_stage / tb_tracer_stage launches to patches
+ * [first, first+count) (interior / partition-boundary split for overlap).
+ * count < 0 resets to all patches. */
+int tb_set_patch_range(tb_ctx *ctx, int64_t first, int64_t count);
+
+/* launches issued by this library so far (bench.py's gpu_launches) */
+int64_t tb_launch_count(const tb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THETIS_B200_H */

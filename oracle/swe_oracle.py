@@ -1,0 +1,718 @@
+"""
+CPU ORACLE -- TEST INFRASTRUCTURE ONLY.  NOT A PRODUCT PATH.
+
+Plain numpy restatement of the reference's explicit P1DG shallow-water path.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference arm
+may import this module; `thetis_b200/` never does.
+
+What is restated (all paths relative to /root/reference):
+
+* thetis/shallowwater_eq.py:335-393   ExternalPressureGradientTerm (dg branch)
+* thetis/shallowwater_eq.py:396-450   HUDivTerm (by-parts branch)
+* thetis/shallowwater_eq.py:453-510   HorizontalAdvectionTerm (+ Lax-Friedrichs)
+* thetis/shallowwater_eq.py:619-663   CoriolisTerm, WindStressTerm, AtmosphericPressureTerm
+* thetis/shallowwater_eq.py:666-701   QuadraticDragTerm (constant / Manning)
+* thetis/shallowwater_eq.py:728-740   LinearDragTerm
+* thetis/shallowwater_eq.py:794-831   MomentumSourceTerm, ContinuitySourceTerm
+* thetis/shallowwater_eq.py:232-296   get_bnd_functions / impose_dynamic_bnd
+* thetis/utility.py:936-996           DepthExpression
+* thetis/equation.py:99-105           mass term
+* thetis/rungekutta.py:13-87,326-347,870-952  Shu-Osher SSPRK33
+* thetis/tracer_eq_2d.py:78-193,281-298       tracer advection + source
+* thetis/limiter.py:48-198 + firedrake.VertexBasedLimiter (recalled)
+
+The arithmetic itself lives in Firedrake/TSFC/PyOP2/PETSc, which is NOT under
+/root/reference and is unpinned upstream (CI image
+firedrakeproject/firedrake-vanilla-default:dev-main).  It cannot be imported
+here, so this oracle restates the *published weak forms* with the same
+quadrature the reference requests (`degree=2p+1=3`, shallowwater_eq.py:225-230):
+2-point Gauss-Legendre on facets and a 6-point degree-3 rule in cells.
+
+PARITY STATUS: pinned against the reference's own known-answer criteria
+(tests/test_oracle_kat.py: Shu-Osher coefficients produced by executing
+rungekutta.py:13-87 itself, ODE convergence slope, eta-norm 6251.2574, standing
+wave thresholds, limiter invariants, tracer conservation, atmospheric-pressure
+and Rossby-soliton criteria).  There are no stored field dumps in the
+reference for this path, so field-level parity vs Firedrake itself is
+"pinned through those criteria only"; explicit wetting-drying is
+"parity unpinned" (not a reference code path).
+
+Deliberately written differently from the CUDA kernels: every form is
+evaluated by quadrature with tabulated basis functions, interior facets are
+visited once with '+'/'-' restrictions exactly like UFL, and the mass system
+is *solved* (batched LU) instead of using a closed-form inverse.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+FACET_NODES = np.array([[1, 2], [2, 0], [0, 1]], dtype=np.int64)
+
+# ---------------------------------------------------------------- quadrature
+# facet: 2-point Gauss-Legendre on [0, 1] (degree 3)
+_GS = np.array([0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)])
+_GW = np.array([0.5, 0.5])
+
+
+def cell_quadrature(name="strang_fix6"):
+    """
+    Degree-3 cell rules in barycentric coordinates; weights sum to 1 (multiply
+    by the cell area).  FIAT's default degree-3 triangle rule differs between
+    FIAT versions; it only matters for non-polynomial
+    integrands (Manning drag, wind stress / H, wetting-drying depth).
+    """
+    if name == "strang_fix6":
+        a, b, c = 0.659027622374092, 0.231933368553031, 0.109039009072877
+        pts = np.array([[a, b, c], [a, c, b], [b, a, c], [b, c, a], [c, a, b], [c, b, a]])
+        # FIAT lists reference coordinates (x, y); barycentric = (1-x-y, x, y)
+        lam = np.stack([1.0 - pts[:, 0] - pts[:, 1], pts[:, 0], pts[:, 1]], axis=1)
+        w = np.full(6, 1.0 / 6.0)
+        return lam, w
+    if name == "dunavant6":      # degree 4, 6 points
+        a1, w1 = 0.445948490915965, 0.223381589678011
+        a2, w2 = 0.091576213509771, 0.109951743655322
+        lam = np.array([[1 - 2 * a1, a1, a1], [a1, 1 - 2 * a1, a1], [a1, a1, 1 - 2 * a1],
+                        [1 - 2 * a2, a2, a2], [a2, 1 - 2 * a2, a2], [a2, a2, 1 - 2 * a2]])
+        w = np.array([w1, w1, w1, w2, w2, w2])
+        return lam, w / w.sum()
+    if name == "collapsed_gauss4":   # FIAT 'canonical' 2x2 collapsed Gauss-Jacobi
+        # Gauss-Legendre (2 pts) in eta1, Gauss-Jacobi(1,0) (2 pts) in eta2
+        g = np.array([-1.0, 1.0]) / np.sqrt(3.0)
+        gw = np.array([1.0, 1.0])
+        # Gauss-Jacobi alpha=1, beta=0 two-point rule on [-1, 1]
+        j = np.array([-0.6898979485566356, 0.2898979485566356])
+        # weights of GJ(1,0) n=2: solve moments  int (1-x) dx = 2, int (1-x) x dx = -2/3
+        A = np.array([[1.0, 1.0], [j[0], j[1]]])
+        jw = np.linalg.solve(A, np.array([2.0, -2.0 / 3.0]))
+        lam, w = [], []
+        for a_, wa in zip(g, gw):
+            for b_, wb in zip(j, jw):
+                x = 0.25 * (1 + a_) * (1 - b_)
+                y = 0.5 * (1 + b_)
+                lam.append([1 - x - y, x, y])
+                w.append(wa * wb * 0.125)
+        lam = np.array(lam)
+        w = np.array(w)
+        return lam, w / w.sum()
+    raise ValueError(name)
+
+
+# ------------------------------------------------------- Shu-Osher (restated)
+def butcher_to_shuosher_form(a, b):
+    """Restates thetis/rungekutta.py:13-87 (explicit branch only)."""
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    butcher = np.vstack((a, b))
+    if np.diag(a).any():
+        raise NotImplementedError("implicit tableaux are out of scope")
+    aa = butcher[1:, :]
+    be_0 = np.diag(np.diag(aa))
+    n = aa.shape[0]
+    al_0 = np.eye(n) - be_0 @ np.linalg.inv(aa)
+    alpha = np.zeros((n + 1, n + 1))
+    alpha[1:, 1:] = al_0
+    alpha[:, 0] = 1.0 - alpha.sum(axis=1)
+    beta = np.zeros((n + 1, n + 1))
+    beta[1:, :-1] = be_0
+    alpha[np.abs(alpha) < 1e-13] = 0.0
+    beta[np.abs(beta) < 1e-13] = 0.0
+    return alpha, beta
+
+
+SSPRK33_A = [[0, 0, 0], [1.0, 0, 0], [0.25, 0.25, 0]]      # rungekutta.py:342-344
+SSPRK33_B = [1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0]              # :345
+SSPRK33_C = [0, 1.0, 0.5]                                  # :346
+
+
+class _Geom:
+    """Per-cell affine geometry from vertex coordinates."""
+
+    def __init__(self, coords, cells):
+        x = coords[cells]                                   # (nt, 3, 2)
+        self.x = x
+        d1 = x[:, 1] - x[:, 0]
+        d2 = x[:, 2] - x[:, 0]
+        self.area = 0.5 * (d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0])
+        assert np.all(self.area > 0)
+        p = x[:, FACET_NODES[:, 0]]
+        q = x[:, FACET_NODES[:, 1]]
+        e = q - p
+        self.flen = np.hypot(e[..., 0], e[..., 1])          # (nt, 3)
+        self.fnormal = np.stack([e[..., 1], -e[..., 0]], -1) / self.flen[..., None]   # unit outward
+        # grad phi_a = - N_a |e_a| / (2 A)
+        self.grad = -self.fnormal * (self.flen / (2.0 * self.area[:, None]))[..., None]  # (nt, 3, 2)
+
+
+def _nodal(val, nt, ncomp=None):
+    """Broadcast a constant or nodal array to a P1DG nodal array."""
+    if ncomp is None:
+        out = np.empty((nt, 3))
+        out[...] = np.asarray(val, dtype=float) if np.ndim(val) else float(val)
+        return out
+    out = np.empty((nt, 3, ncomp))
+    out[...] = np.asarray(val, dtype=float)
+    return out
+
+
+class SWEOracle:
+    """
+    Explicit residual of `ShallowWaterEquations` on P1DG-P1DG triangles.
+
+    State layout: uv (nt, 3, 2), eta (nt, 3) -- nodal values per cell in the
+    cell's local vertex order.
+
+    :arg mesh: object with coords, cells (CCW), nbr, nbr_lf, bf_cell, bf_lf, bf_marker
+    :arg bathymetry: constant or nodal (nt, 3)
+    :kwarg options: dict with use_nonlinear_equations, use_lax_friedrichs_velocity,
+        use_wetting_and_drying, wetting_and_drying_alpha, norm_smoother
+    :kwarg fields: dict like solver2d.py:546-558 (values: None, constants, nodal arrays)
+    :kwarg bnd_conditions: {marker: {'elev'|'uv'|'un'|'flux'|'drag': value}}
+    """
+
+    def __init__(self, mesh, bathymetry, options=None, fields=None, bnd_conditions=None,
+                 g_grav=9.81, rho0=1000.0, cell_rule="strang_fix6"):
+        self.mesh = mesh
+        self.nt = mesh.cells.shape[0]
+        self.geom = _Geom(mesh.coords, mesh.cells)
+        self.bath = _nodal(bathymetry, self.nt)
+        o = dict(use_nonlinear_equations=True, use_lax_friedrichs_velocity=True,
+                 use_wetting_and_drying=False, wetting_and_drying_alpha=0.5,
+                 norm_smoother=0.0)
+        o.update(options or {})
+        self.options = o
+        self.fields = dict(fields or {})
+        self.bnd = dict(bnd_conditions or {})
+        self.g = float(g_grav)
+        self.rho0 = float(rho0)
+        self.lam, self.qw = cell_quadrature(cell_rule)
+        c, f, n, g = mesh.interior_facets()
+        self.if_p, self.if_fp, self.if_m, self.if_fm = (np.asarray(c, np.int64), np.asarray(f, np.int64),
+                                                        np.asarray(n, np.int64), np.asarray(g, np.int64))
+        self.boundary_len = mesh.boundary_length()
+        # mass matrix per cell (equation.py:99-105): M_ab = int phi_a phi_b
+        lam, w = self.lam, self.qw
+        mref = np.einsum("q,qa,qb->ab", w, lam, lam)
+        self.mass = self.geom.area[:, None, None] * mref[None]
+
+    # ------------------------------------------------------------ depth (utility.py:975-996)
+    def wd_bathymetry_displacement(self, b, eta):
+        if self.options["use_wetting_and_drying"]:
+            H = b + eta
+            al = self.options["wetting_and_drying_alpha"]
+            return 0.5 * (np.sqrt(H ** 2 + np.asarray(al) ** 2) - H)
+        return 0.0
+
+    def total_depth(self, b, eta):
+        if self.options["use_nonlinear_equations"]:
+            return b + eta + self.wd_bathymetry_displacement(b, eta)
+        return b + 0.0 * eta
+
+    # ------------------------------------------------------------ helpers
+    def _field(self, name, ncomp=None):
+        v = self.fields.get(name)
+        if v is None:
+            return None
+        return _nodal(v, self.nt, ncomp)
+
+    @staticmethod
+    def _at_cell_q(nodal, lam):
+        """nodal (nt,3[,k]) -> values at quadrature points (nt, nq[,k])"""
+        return np.einsum("qa,ca...->cq...", lam, nodal)
+
+    @staticmethod
+    def _facet_trace(nodal, cells, lf, s, reverse=False):
+        """
+        Trace of a P1DG nodal field on local facet `lf` of `cells` at facet
+        parameters s (ngp,) measured from the facet's first node (or from its
+        second node if reverse).  Returns (nf, ngp[,k]).
+        """
+        n0 = FACET_NODES[lf, 0]
+        n1 = FACET_NODES[lf, 1]
+        if reverse:
+            n0, n1 = n1, n0
+        v0 = nodal[cells, n0]
+        v1 = nodal[cells, n1]
+        if v0.ndim == 1:
+            return v0[:, None] * (1 - s)[None, :] + v1[:, None] * s[None, :]
+        return v0[:, None, :] * (1 - s)[None, :, None] + v1[:, None, :] * s[None, :, None]
+
+    def _bc_value(self, val, cells, lf, ncomp=None):
+        """Evaluate a boundary datum (constant or nodal DG array) at the facet Gauss points."""
+        if isinstance(val, np.ndarray) and val.ndim >= 2 and val.shape[0] == self.nt:
+            return self._facet_trace(val, cells, lf, _GS)
+        nf = cells.shape[0]
+        if ncomp is None:
+            return np.full((nf, _GS.shape[0]), float(val))
+        out = np.empty((nf, _GS.shape[0], ncomp))
+        out[...] = np.asarray(val, dtype=float)
+        return out
+
+    def get_bnd_functions(self, eta_in, uv_in, marker, funcs, b, normal):
+        """shallowwater_eq.py:232-272; everything evaluated at facet Gauss points."""
+        bnd_len = self.boundary_len[marker]
+        cells, lf = self._bf_sel[marker]
+        eta_ext = uv_ext = None
+        if 'elev' in funcs and 'uv' in funcs:
+            eta_ext = self._bc_value(funcs['elev'], cells, lf)
+            uv_ext = self._bc_value(funcs['uv'], cells, lf, 2)
+        elif 'elev' in funcs and 'un' in funcs:
+            eta_ext = self._bc_value(funcs['elev'], cells, lf)
+            uv_ext = self._bc_value(funcs['un'], cells, lf)[..., None] * normal
+        elif 'elev' in funcs and 'flux' in funcs:
+            eta_ext = self._bc_value(funcs['elev'], cells, lf)
+            h_ext = self.total_depth(b, eta_ext)
+            area = h_ext * bnd_len
+            uv_ext = (self._bc_value(funcs['flux'], cells, lf) / area)[..., None] * normal
+        elif 'elev' in funcs:
+            eta_ext = self._bc_value(funcs['elev'], cells, lf)
+            uv_ext = uv_in
+        elif 'uv' in funcs:
+            eta_ext = eta_in
+            uv_ext = self._bc_value(funcs['uv'], cells, lf, 2)
+        elif 'un' in funcs:
+            eta_ext = eta_in
+            uv_ext = self._bc_value(funcs['un'], cells, lf)[..., None] * normal
+        elif 'flux' in funcs:
+            eta_ext = eta_in
+            h_ext = self.total_depth(b, eta_ext)
+            area = h_ext * bnd_len
+            uv_ext = (self._bc_value(funcs['flux'], cells, lf) / area)[..., None] * normal
+        if eta_ext is None or uv_ext is None:
+            raise Exception('Unsupported bnd type, one of "elev", "uv", "un", or "flux" must be defined')
+        return eta_ext, uv_ext
+
+    @staticmethod
+    def impose_dynamic_bnd(funcs, marker):
+        """shallowwater_eq.py:274-296"""
+        open_tags = ['elev', 'uv', 'un', 'flux']
+        all_tags = open_tags + ['drag']
+        if funcs is None:
+            return False
+        for k in funcs.keys():
+            if k not in all_tags:
+                raise Exception(f'Invalid boundary tag "{k}" specified on boundary {marker}')
+            if k in open_tags:
+                return True
+        return False
+
+    # ------------------------------------------------------------ residual
+    def residual(self, uv, eta):
+        """
+        Sum over all terms of `-f` tested against every basis function:
+        returns (Ru (nt,3,2), Re (nt,3)) such that  M d(u,eta)/dt = (Ru, Re).
+        In the explicit integrator solution_old == solution and
+        fields_old == fields (rungekutta.py:901-904).
+        """
+        nt, g, geo = self.nt, self.g, self.geom
+        o = self.options
+        lam, qw = self.lam, self.qw
+        nonlin = o["use_nonlinear_equations"]
+        Ru = np.zeros((nt, 3, 2))
+        Re = np.zeros((nt, 3))
+        A = geo.area
+        grad = geo.grad                                   # (nt, 3, 2)
+        wq = A[:, None] * qw[None, :]                     # (nt, nq)
+        phi = lam                                         # (nq, 3)
+
+        # ---- cell integrals
+        u_q = self._at_cell_q(uv, lam)                    # (nt, nq, 2)
+        eta_q = self._at_cell_q(eta, lam)
+        b_q = self._at_cell_q(self.bath, lam)
+        H_q = self.total_depth(b_q, eta_q)
+        # ExternalPressureGradient: f = -g*eta*div(psi) dx ; R = -f
+        Ru += g * np.einsum("cq,cq,cai->cai", wq, eta_q, grad)
+        # HUDiv: f = -inner(grad(phi), H*uv) dx
+        Re += np.einsum("cq,cqi,cai->ca", wq, H_q[..., None] * u_q, grad)
+        if nonlin:
+            # HorizontalAdvection: f = -inner(div(outer(psi, uv_old)), uv) dx
+            divu = np.einsum("cai,cai->c", grad, uv)      # constant per cell
+            gu = np.einsum("cai,cqi->cqa", grad, u_q)     # grad(phi_a).u at q
+            coef = gu + phi[None, :, :] * divu[:, None, None]       # (nt, nq, 3)
+            Ru += np.einsum("cq,cqa,cqi->cai", wq, coef, u_q)
+        cor = self._field("coriolis")
+        if cor is not None:
+            f_q = self._at_cell_q(cor, lam)
+            # f = coriolis*(-uv[1]*psi[0] + uv[0]*psi[1]) dx ; R = -f
+            Ru[..., 0] += np.einsum("cq,cq,qa->ca", wq, f_q * u_q[..., 1], phi)
+            Ru[..., 1] -= np.einsum("cq,cq,qa->ca", wq, f_q * u_q[..., 0], phi)
+        wind = self._field("wind_stress", 2)
+        if wind is not None:
+            t_q = self._at_cell_q(wind, lam)
+            Ru += np.einsum("cq,cqi,qa->cai", wq, t_q / H_q[..., None] / self.rho0, phi)
+        pa = self._field("atmospheric_pressure")
+        if pa is not None:
+            gp = np.einsum("ca,cai->ci", pa, grad)
+            Ru -= np.einsum("cq,ci,qa->cai", wq, gp / self.rho0, phi)
+        mann = self._field("manning_drag_coefficient")
+        cd = self._field("quadratic_drag_coefficient")
+        if self.fields.get("nikuradse_bed_roughness") is not None:
+            raise NotImplementedError("nikuradse_bed_roughness is not on the accelerated path")
+        cd_q = None
+        if mann is not None:
+            if cd is not None:
+                raise Exception('Cannot set both dimensionless and Manning drag parameter')
+            cd_q = g * self._at_cell_q(mann, lam) ** 2 / H_q ** (1. / 3.)
+        elif cd is not None:
+            cd_q = self._at_cell_q(cd, lam)
+        if cd_q is not None:
+            eps = float(o["norm_smoother"])
+            mag = np.sqrt(u_q[..., 0] ** 2 + u_q[..., 1] ** 2 + eps ** 2)
+            Ru -= np.einsum("cq,cq,cqi,qa->cai", wq, cd_q * mag / H_q, u_q, phi)
+        lin = self._field("linear_drag_coefficient")
+        if lin is not None:
+            Ru -= np.einsum("cq,cq,cqi,qa->cai", wq, self._at_cell_q(lin, lam), u_q, phi)
+        ms = self._field("momentum_source", 2)
+        if ms is not None:
+            Ru += np.einsum("cq,cqi,qa->cai", wq, self._at_cell_q(ms, lam), phi)
+        vs = self._field("volume_source")
+        if vs is not None:
+            Re += np.einsum("cq,cq,qa->ca", wq, self._at_cell_q(vs, lam), phi)
+        if self.fields.get("viscosity_h") is not None:
+            raise NotImplementedError("horizontal viscosity is not on the accelerated path")
+
+        # ---- interior facets ('+' = if_p, '-' = if_m), 2-point Gauss
+        cp, fp, cm, fm = self.if_p, self.if_fp, self.if_m, self.if_fm
+        if cp.size:
+            s = _GS
+            n_p = geo.fnormal[cp, fp][:, None, :]         # (nf, 1, 2)
+            n_m = -n_p
+            flen = geo.flen[cp, fp]
+            wf = flen[:, None] * _GW[None, :]             # (nf, ngp)
+            up = self._facet_trace(uv, cp, fp, s)
+            um = self._facet_trace(uv, cm, fm, s, reverse=True)
+            ep = self._facet_trace(eta, cp, fp, s)
+            em = self._facet_trace(eta, cm, fm, s, reverse=True)
+            bp = self._facet_trace(self.bath, cp, fp, s)
+            bm = self._facet_trace(self.bath, cm, fm, s, reverse=True)
+            Hp = self.total_depth(bp, ep)
+            Hm = self.total_depth(bm, em)
+            # test functions: '+' nodes (n0: 1-s, n1: s); '-' nodes reversed
+            php = np.stack([1 - s, s], -1)                # (ngp, 2) for nodes FACET_NODES[fp]
+            nodes_p = FACET_NODES[fp]                     # (nf, 2)
+            nodes_m = FACET_NODES[fm][:, ::-1]            # matching order
+            h_av = 0.5 * (Hp + Hm)
+            # --- PG: head_star = avg(head) + sqrt(avg(H)/g)*jump(uv, n)
+            jump_un = np.einsum("fqi,fqi->fq", up, np.broadcast_to(n_p, up.shape)) \
+                + np.einsum("fqi,fqi->fq", um, np.broadcast_to(n_m, um.shape))
+            head_star = 0.5 * (ep + em) + np.sqrt(h_av / g) * jump_un
+            # f += g*head_star*jump(psi, n) dS
+            fu_p = g * head_star[..., None] * n_p         # tested with phi on '+'
+            fu_m = g * head_star[..., None] * n_m
+            # --- HUDiv: uv_rie = avg(uv) + sqrt(g/h)*jump(eta, n); hu_star = h*uv_rie
+            jump_eta_n = ep[..., None] * n_p + em[..., None] * n_m
+            uv_rie = 0.5 * (up + um) + np.sqrt(g / h_av)[..., None] * jump_eta_n
+            hu_star = h_av[..., None] * uv_rie
+            fe_p = np.einsum("fqi,fqi->fq", hu_star, np.broadcast_to(n_p, hu_star.shape))
+            fe_m = np.einsum("fqi,fqi->fq", hu_star, np.broadcast_to(n_m, hu_star.shape))
+            if nonlin:
+                uv_avg = 0.5 * (up + um)
+                un_av = np.einsum("fqi,fqi->fq", uv_avg, np.broadcast_to(n_m, uv_avg.shape))
+                # inner(uv_avg, jump(outer(psi, uv_old), n))
+                fu_p = fu_p + uv_avg * np.einsum("fqi,fqi->fq", up, np.broadcast_to(n_p, up.shape))[..., None]
+                fu_m = fu_m + uv_avg * np.einsum("fqi,fqi->fq", um, np.broadcast_to(n_m, um.shape))[..., None]
+                if o["use_lax_friedrichs_velocity"]:
+                    sig = float(self.fields.get("lax_friedrichs_velocity_scaling_factor", 1.0))
+                    gamma = 0.5 * np.abs(un_av) * sig
+                    ju = up - um
+                    fu_p = fu_p + gamma[..., None] * ju
+                    fu_m = fu_m - gamma[..., None] * ju
+            # scatter: R -= int f * phi
+            for k in range(2):
+                np.subtract.at(Ru, (cp, nodes_p[:, k]), np.einsum("fq,fqi,q->fi", wf, fu_p, php[:, k]))
+                np.subtract.at(Ru, (cm, nodes_m[:, k]), np.einsum("fq,fqi,q->fi", wf, fu_m, php[:, k]))
+                np.subtract.at(Re, (cp, nodes_p[:, k]), np.einsum("fq,fq,q->f", wf, fe_p, php[:, k]))
+                np.subtract.at(Re, (cm, nodes_m[:, k]), np.einsum("fq,fq,q->f", wf, fe_m, php[:, k]))
+
+        # ---- exterior facets, one integral per marker
+        mesh = self.mesh
+        self._bf_sel = {}
+        for marker in sorted(set(int(m) for m in np.unique(mesh.bf_marker))):
+            sel = mesh.bf_marker == marker
+            cells = mesh.bf_cell[sel].astype(np.int64)
+            lf = mesh.bf_lf[sel].astype(np.int64)
+            self._bf_sel[marker] = (cells, lf)
+            funcs = self.bnd.get(marker)
+            s = _GS
+            n = geo.fnormal[cells, lf][:, None, :]
+            nb = np.broadcast_to(n, (cells.shape[0], s.shape[0], 2))
+            wf = geo.flen[cells, lf][:, None] * _GW[None, :]
+            u = self._facet_trace(uv, cells, lf, s)
+            e = self._facet_trace(eta, cells, lf, s)
+            b = self._facet_trace(self.bath, cells, lf, s)
+            H = self.total_depth(b, e)
+            nodes = FACET_NODES[lf]
+            php = np.stack([1 - s, s], -1)
+            fu = np.zeros_like(u)
+            fe = np.zeros_like(e)
+            if self.impose_dynamic_bnd(funcs, marker):
+                eta_ext, uv_ext = self.get_bnd_functions(e, u, marker, funcs, b, nb)
+                # PG (shallowwater_eq.py:370-375)
+                un_jump = np.einsum("fqi,fqi->fq", u - uv_ext, nb)
+                eta_rie = 0.5 * (e + eta_ext) + np.sqrt(H / g) * un_jump
+                fu = fu + g * eta_rie[..., None] * nb
+                # HUDiv (:431-442)
+                H_ext = self.total_depth(b, eta_ext)
+                h_av = 0.5 * (H + H_ext)
+                eta_jump = e - eta_ext
+                un_rie = 0.5 * np.einsum("fqi,fqi->fq", u + uv_ext, nb) + np.sqrt(g / h_av) * eta_jump
+                eta_rie2 = 0.5 * (e + eta_ext) + np.sqrt(h_av / g) * un_jump
+                h_rie = self.total_depth(b, eta_rie2)
+                fe = fe + h_rie * un_rie
+                if nonlin:
+                    # advection (:498-509)
+                    un_rie_a = 0.5 * np.einsum("fqi,fqi->fq", u + uv_ext, nb) + np.sqrt(g / H) * eta_jump
+                    uv_av = 0.5 * (uv_ext + u)
+                    fu = fu + un_rie_a[..., None] * uv_av
+            else:
+                # land boundary (:376-381)
+                un_jump = np.einsum("fqi,fqi->fq", u, nb)
+                head_rie = e + np.sqrt(H / g) * un_jump
+                fu = fu + g * head_rie[..., None] * nb
+                if nonlin and o["use_lax_friedrichs_velocity"]:
+                    # mirror velocity (:489-497)
+                    sig = float(self.fields.get("lax_friedrichs_velocity_scaling_factor", 1.0))
+                    uv_ext = u - 2 * un_jump[..., None] * nb
+                    gamma = 0.5 * np.abs(un_jump) * sig
+                    fu = fu + gamma[..., None] * (u - uv_ext)
+            if funcs is not None and 'drag' in funcs:
+                raise NotImplementedError("BoundaryDragTerm is not on the accelerated path")
+            for k in range(2):
+                np.subtract.at(Ru, (cells, nodes[:, k]), np.einsum("fq,fqi,q->fi", wf, fu, php[:, k]))
+                np.subtract.at(Re, (cells, nodes[:, k]), np.einsum("fq,fq,q->f", wf, fe, php[:, k]))
+        return Ru, Re
+
+    # ------------------------------------------------------------ mass solve
+    def solve_mass(self, Ru, Re):
+        """`M k = R` (rungekutta.py:921-924; PETSc cg/bjacobi/ilu is an exact block solve)."""
+        ku = np.linalg.solve(self.mass, Ru)
+        ke = np.linalg.solve(self.mass, Re[..., None])[..., 0]
+        return ku, ke
+
+    def tendency(self, uv, eta, dt=1.0):
+        Ru, Re = self.residual(uv, eta)
+        return self.solve_mass(dt * Ru, dt * Re)
+
+
+class ShuOsherStepper:
+    """
+    `ERKGenericShuOsher` (rungekutta.py:870-952) over any object exposing
+    ``tendency(*state, dt) -> tuple of arrays``.  ``state`` is a list of arrays
+    updated in place (like `solution.assign`).
+    """
+
+    def __init__(self, rhs, state, dt, a=SSPRK33_A, b=SSPRK33_B, c=SSPRK33_C):
+        self.rhs = rhs
+        self.state = state
+        self.dt = float(dt)
+        self.a = np.array(a, dtype=float)
+        self.b = np.array(b, dtype=float)
+        self.c = np.array(c, dtype=float)
+        self.n_stages = len(self.b)
+        self.alpha, self.beta = butcher_to_shuosher_form(self.a, self.b)
+        self.stage_sol = [[np.zeros_like(s) for s in state] for _ in range(self.n_stages)]
+        self.cfl_coeff = 1.0
+
+    def set_dt(self, dt):
+        self.dt = float(dt)
+
+    def solve_stage(self, i, t, update_forcings=None):
+        if update_forcings is not None:
+            update_forcings(t + self.c[i] * self.dt)
+        if i == 0:
+            for d, s in zip(self.stage_sol[0], self.state):
+                d[...] = s
+        k = self.rhs.tendency(*self.state, dt=self.dt)
+        for j, s in enumerate(self.state):
+            new = self.beta[i + 1][i] * k[j]
+            for jj in range(i + 1):
+                if self.alpha[i + 1][jj] != 0.0:
+                    new = new + self.alpha[i + 1][jj] * self.stage_sol[jj][j]
+            s[...] = new
+        if i < self.n_stages - 1:
+            for d, s in zip(self.stage_sol[i + 1], self.state):
+                d[...] = s
+
+    def advance(self, t, update_forcings=None):
+        for i in range(self.n_stages):
+            self.solve_stage(i, t, update_forcings)
+
+
+class TracerOracle:
+    """
+    Non-conservative 2-D tracer advection + source on P1DG
+    (tracer_eq_2d.py:124-193, 281-298).  ``uv`` (nt,3,2) and ``elev`` (nt,3)
+    are the live SWE fields (frozen during the tracer stages,
+    coupled_timeintegrator_2d.py:99-101).
+    """
+
+    def __init__(self, swe: SWEOracle, bnd_conditions=None, fields=None, options=None):
+        self.swe = swe
+        self.mesh = swe.mesh
+        self.nt = swe.nt
+        self.geom = swe.geom
+        self.bnd = dict(bnd_conditions or {})
+        self.fields = dict(fields or {})
+        o = dict(use_lax_friedrichs_tracer=False)
+        o.update(options or {})
+        self.options = o
+        self.uv = None
+        self.elev = None
+        self.mass = swe.mass
+
+    def set_velocity(self, uv, elev):
+        self.uv, self.elev = uv, elev
+
+    def residual(self, c):
+        swe, geo, nt = self.swe, self.geom, self.nt
+        lam, qw = swe.lam, swe.qw
+        corr = float(self.fields.get("tracer_advective_velocity_factor", 1.0))
+        uv = corr * self.uv
+        R = np.zeros((nt, 3))
+        wq = geo.area[:, None] * qw[None, :]
+        grad = geo.grad
+        u_q = swe._at_cell_q(uv, lam)
+        c_q = swe._at_cell_q(c, lam)
+        divu = np.einsum("cai,cai->c", grad, uv)
+        # f = -(Dx(uv[0]*test,0)*c + Dx(uv[1]*test,1)*c) dx ; R = -f
+        gu = np.einsum("cai,cqi->cqa", grad, u_q)
+        coef = gu + lam[None] * divu[:, None, None]
+        R += np.einsum("cq,cqa,cq->ca", wq, coef, c_q)
+        src = self.fields.get("source")
+        if src is not None:
+            R += np.einsum("cq,cq,qa->ca", wq, swe._at_cell_q(_nodal(src, nt), lam), lam)
+        # interior facets
+        cp, fp, cm, fm = swe.if_p, swe.if_fp, swe.if_m, swe.if_fm
+        s = _GS
+        php = np.stack([1 - s, s], -1)
+        if cp.size:
+            n_p = np.broadcast_to(geo.fnormal[cp, fp][:, None, :], (cp.shape[0], 2, 2))
+            n_m = -n_p
+            wf = geo.flen[cp, fp][:, None] * _GW[None, :]
+            up = swe._facet_trace(uv, cp, fp, s)
+            um = swe._facet_trace(uv, cm, fm, s, reverse=True)
+            c_p = swe._facet_trace(c, cp, fp, s)
+            c_m = swe._facet_trace(c, cm, fm, s, reverse=True)
+            uv_av = 0.5 * (up + um)
+            un_av = np.einsum("fqi,fqi->fq", uv_av, n_m)
+            sg = 0.5 * (np.sign(un_av) + 1.0)
+            c_up = c_m * sg + c_p * (1 - sg)
+            f_p = c_up * np.einsum("fqi,fqi->fq", up, n_p)
+            f_m = c_up * np.einsum("fqi,fqi->fq", um, n_m)
+            if self.options["use_lax_friedrichs_tracer"]:
+                lf = float(self.fields.get("lax_friedrichs_tracer_scaling_factor", 1.0))
+                gamma = 0.5 * np.abs(un_av) * lf
+                f_p = f_p + gamma * (c_p - c_m)
+                f_m = f_m - gamma * (c_p - c_m)
+            nodes_p = FACET_NODES[fp]
+            nodes_m = FACET_NODES[fm][:, ::-1]
+            for k in range(2):
+                np.subtract.at(R, (cp, nodes_p[:, k]), np.einsum("fq,fq,q->f", wf, f_p, php[:, k]))
+                np.subtract.at(R, (cm, nodes_m[:, k]), np.einsum("fq,fq,q->f", wf, f_m, php[:, k]))
+        # exterior facets
+        mesh = self.mesh
+        for marker in sorted(set(int(m) for m in np.unique(mesh.bf_marker))):
+            sel = mesh.bf_marker == marker
+            cells = mesh.bf_cell[sel].astype(np.int64)
+            lf = mesh.bf_lf[sel].astype(np.int64)
+            funcs = self.bnd.get(marker)
+            n = np.broadcast_to(geo.fnormal[cells, lf][:, None, :], (cells.shape[0], 2, 2))
+            wf = geo.flen[cells, lf][:, None] * _GW[None, :]
+            u = swe._facet_trace(uv, cells, lf, s)
+            cin = swe._facet_trace(c, cells, lf, s)
+            if funcs is not None:
+                swe._bf_sel = getattr(swe, "_bf_sel", {})
+                swe._bf_sel[marker] = (cells, lf)
+                c_ext = swe._bc_value(funcs['value'], cells, lf) if 'value' in funcs else cin
+                if 'uv' in funcs:
+                    uv_ext = corr * swe._bc_value(funcs['uv'], cells, lf, 2)
+                elif 'flux' in funcs:
+                    e_in = swe._facet_trace(self.elev, cells, lf, s)
+                    e_ext = swe._bc_value(funcs['elev'], cells, lf) if 'elev' in funcs else e_in
+                    b = swe._facet_trace(swe.bath, cells, lf, s)
+                    h_ext = swe.total_depth(b, e_ext)
+                    area = h_ext * swe.boundary_len[marker]
+                    uv_ext = (corr * swe._bc_value(funcs['flux'], cells, lf) / area)[..., None] * n
+                elif 'un' in funcs:
+                    uv_ext = swe._bc_value(funcs['un'], cells, lf)[..., None] * n
+                else:
+                    uv_ext = u
+                uv_av = 0.5 * (u + uv_ext)
+                un_av = np.einsum("fqi,fqi->fq", uv_av, n)
+                sg = 0.5 * (np.sign(un_av) + 1.0)
+                c_up = cin * sg + c_ext * (1 - sg)
+                f = c_up * un_av
+            else:
+                f = cin * np.einsum("fqi,fqi->fq", u, n)
+            nodes = FACET_NODES[lf]
+            for k in range(2):
+                np.subtract.at(R, (cells, nodes[:, k]), np.einsum("fq,fq,q->f", wf, f, php[:, k]))
+        return R
+
+    def tendency(self, c, dt=1.0):
+        R = self.residual(c)
+        return (np.linalg.solve(self.mass, (dt * R)[..., None])[..., 0],)
+
+
+def vertex_based_limiter(mesh, q):
+    """
+    `VertexBasedP1DGLimiter.apply` for a scalar P1DG field on a 2-D mesh
+    (limiter.py:100-145,182-198 + Firedrake's VertexBasedLimiter kernels,
+    recalled): returns the limited nodal array (nt, 3).
+    """
+    q = np.array(q, dtype=float)
+    nt = q.shape[0]
+    tv = mesh.topo[mesh.cells]                             # topological vertex of each node
+    nv = int(mesh.topo.max()) + 1
+    # centroids: P0 projection = mean of the nodal values (limiter.py:90-97)
+    qbar = q.mean(axis=1)
+    qmax = np.full(nv, -1.0e10)
+    qmin = np.full(nv, 1.0e10)
+    for a in range(3):
+        np.maximum.at(qmax, tv[:, a], qbar)
+        np.minimum.at(qmin, tv[:, a], qbar)
+    # boundary facets: arithmetic mean of the facet's nodal values (limiter.py:123-145)
+    bc = mesh.bf_cell.astype(np.int64)
+    bl = mesh.bf_lf.astype(np.int64)
+    n0 = FACET_NODES[bl, 0]
+    n1 = FACET_NODES[bl, 1]
+    face_mean = (q[bc, n0] + q[bc, n1]) / 2
+    for nn in (n0, n1):
+        np.maximum.at(qmax, tv[bc, nn], face_mean)
+        np.minimum.at(qmin, tv[bc, nn], face_mean)
+    # limit
+    alpha = np.ones(nt)
+    for a in range(3):
+        qa = q[:, a]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a1 = np.minimum(alpha, np.minimum(1.0, (qmax[tv[:, a]] - qbar) / (qa - qbar)))
+            a2 = np.minimum(alpha, np.minimum(1.0, (qbar - qmin[tv[:, a]]) / (qbar - qa)))
+        alpha = np.where(qa > qbar, a1, np.where(qa < qbar, a2, alpha))
+    return qbar[:, None] + alpha[:, None] * (q - qbar[:, None])
+
+
+# ------------------------------------------------------------------ utilities
+def l2_norm(mesh, nodal, lam_w=None):
+    """sqrt(int f^2 dx) of a P1DG nodal field (scalar (nt,3) or vector (nt,3,k))."""
+    geo = _Geom(mesh.coords, mesh.cells)
+    mref = (np.ones((3, 3)) + np.eye(3)) / 12.0
+    if nodal.ndim == 2:
+        v = np.einsum("ca,ab,cb->c", nodal, mref, nodal)
+    else:
+        v = np.einsum("cai,ab,cbi->c", nodal, mref, nodal)
+    return float(np.sqrt((geo.area * v).sum()))
+
+
+def interpolate(mesh, fn):
+    """P1DG nodal interpolation of fn(x, y) -> (nt, 3[,k])."""
+    x = mesh.coords[mesh.cells]
+    return np.asarray(fn(x[..., 0], x[..., 1]))
+
+
+def l2_error(mesh, nodal, fn, degree_rule="dunavant6"):
+    """L2 error of a P1DG field against an analytic function (quadrature)."""
+    lam, w = cell_quadrature(degree_rule)
+    geo = _Geom(mesh.coords, mesh.cells)
+    xq = np.einsum("qa,cai->cqi", lam, geo.x)
+    vq = np.einsum("qa,ca->cq", lam, nodal)
+    ex = fn(xq[..., 0], xq[..., 1])
+    return float(np.sqrt((geo.area[:, None] * w[None] * (vq - ex) ** 2).sum()))

@@ -1,0 +1,190 @@
+"""
+GPU parity: M^-1 R(u) from the CUDA stage kernel (through the C-ABI) against the
+numpy oracle on the same seeded inputs.  fp64; tolerance: 1e-12 relative to the
+max-norm of the tendency for polynomial integrands, 1e-11 where sqrt/cbrt/division
+order differs (nonlinear depth, Manning).
+"""
+import numpy as np
+import pytest
+
+from thetis_b200.mesh import (rectangle_mesh, periodic_rectangle_mesh, delaunay_mesh, read_gmsh, sfc_renumber,
+                              FACET_NODES)
+from oracle.swe_oracle import SWEOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _state(mesh, seed, amp_u=0.5, amp_e=0.3):
+    rng = np.random.default_rng(seed)
+    x = mesh.coords[mesh.cells]
+    L = np.ptp(mesh.coords, axis=0).max()
+    k = 2 * np.pi / L
+    u = amp_u * np.sin(k * x[..., 0] + 0.3) * np.cos(k * x[..., 1]) + 0.05 * rng.standard_normal(x.shape[:2])
+    v = -amp_u * np.cos(2 * k * x[..., 0]) * np.sin(k * x[..., 1] + 0.1) + 0.05 * rng.standard_normal(x.shape[:2])
+    e = amp_e * np.cos(k * x[..., 0]) * np.sin(k * x[..., 1]) + 0.02 * rng.standard_normal(x.shape[:2])
+    return np.stack([u, v], -1), e
+
+
+def _vertex_field(mesh, fn):
+    return fn(mesh.coords[:, 0], mesh.coords[:, 1])
+
+
+def _run(mesh, bath_v, options, fields_v, bnd, g=9.81, tol=1e-12, seed=0, bc_arrays=None):
+    """fields_v: dict name -> None | const | per-vertex array; bnd: {marker: {tag: const}}"""
+    import thetis_b200._lib as L
+    from thetis_b200.engine import Engine
+    uv, eta = _state(mesh, seed)
+    cells = mesh.cells
+    to_nodal = lambda a: a[cells] if (isinstance(a, np.ndarray) and a.shape[0] == mesh.n_vertices) else a
+    ofields = {k: to_nodal(v) for k, v in fields_v.items() if v is not None}
+    obnd = {}
+    for m, d in bnd.items():
+        obnd[m] = dict(d)
+    if bc_arrays:
+        # per-exterior-facet nodal arrays -> oracle wants DG nodal arrays (nt,3[,2])
+        for (m, tag), arr in bc_arrays.items():
+            full = np.zeros((mesh.n_cells, 3) + arr.shape[2:])
+            for side in range(2):
+                full[mesh.bf_cell, FACET_NODES[mesh.bf_lf, side]] = arr[:, side]
+            obnd.setdefault(m, {})[tag] = full
+    orc = SWEOracle(mesh, to_nodal(bath_v), options=options, fields=ofields, bnd_conditions=obnd, g_grav=g)
+    ku, ke = orc.tendency(uv, eta)
+
+    eng = Engine(mesh)
+    eng.set_option(L.OPT_G_GRAV, g)
+    eng.set_option(L.OPT_NONLINEAR, options.get("use_nonlinear_equations", True))
+    eng.set_option(L.OPT_LAX_FRIEDRICHS, options.get("use_lax_friedrichs_velocity", True))
+    eng.set_option(L.OPT_NORM_SMOOTHER, options.get("norm_smoother", 0.0))
+    eng.set_option(L.OPT_WETTING_DRYING, options.get("use_wetting_and_drying", False))
+    eng.set_option(L.OPT_WD_ALPHA, options.get("wetting_and_drying_alpha", 0.5))
+    eng.set_option(L.OPT_LF_SCALING, fields_v.get("lax_friedrichs_velocity_scaling_factor", 1.0))
+    eng.set_field(L.F_BATHYMETRY, bath_v)
+    names = {"coriolis": L.F_CORIOLIS, "manning_drag_coefficient": L.F_MANNING,
+             "quadratic_drag_coefficient": L.F_QUAD_DRAG, "linear_drag_coefficient": L.F_LINEAR_DRAG,
+             "wind_stress": L.F_WIND_STRESS, "atmospheric_pressure": L.F_ATM_PRESSURE,
+             "momentum_source": L.F_MOMENTUM_SOURCE, "volume_source": L.F_VOLUME_SOURCE}
+    for k, fid in names.items():
+        if fields_v.get(k) is not None:
+            eng.set_field(fid, fields_v[k])
+    tags = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX}
+    for m, d in obnd.items():
+        op = 0
+        consts = np.zeros(6)
+        for tag, val in d.items():
+            op |= tags[tag]
+            if not (isinstance(val, np.ndarray) and val.ndim >= 2):
+                if tag == "elev": consts[0] = val
+                if tag == "uv": consts[1:3] = val
+                if tag == "un": consts[3] = val
+                if tag == "flux": consts[4] = val
+        eng.set_bc(0, m, op, consts)
+    if bc_arrays:
+        for (m, tag), arr in bc_arrays.items():
+            eng.set_bc_array(0, m, tags[tag], arr)
+    st = eng.upload_nodal(uv, eta)
+    k = eng.new_state()
+    eng.swe_tendency(st, k)
+    gu, ge = eng.download_nodal(k)
+    su = np.abs(ku).max()
+    se = np.abs(ke).max()
+    eu = np.abs(gu - ku).max() / su
+    ee = np.abs(ge - ke).max() / se
+    assert eu < tol and ee < tol, (eu, ee)
+    return eu, ee
+
+
+def test_linear_constant_depth_closed():
+    mesh = sfc_renumber(rectangle_mesh(24, 20, 1000.0, 800.0))
+    _run(mesh, 50.0, dict(use_nonlinear_equations=False), {}, {})
+
+
+def test_linear_variable_depth_small_ragged():
+    # 2 x 3 cells x 2 = 12 triangles: a single ragged patch
+    mesh = rectangle_mesh(2, 3, 10.0, 10.0)
+    b = _vertex_field(mesh, lambda x, y: 5.0 + 0.1 * x + 0.05 * y)
+    _run(mesh, b, dict(use_nonlinear_equations=False), {}, {})
+
+
+def test_nonlinear_lf_closed_channel():
+    mesh = sfc_renumber(rectangle_mesh(40, 25, 40e3, 2e3))
+    _run(mesh, 20.0, {}, {}, {}, tol=1e-11)
+
+
+def test_nonlinear_no_lf():
+    mesh = sfc_renumber(rectangle_mesh(17, 9, 300.0, 200.0, diagonal="right"))
+    b = _vertex_field(mesh, lambda x, y: 10 + 2 * np.sin(x / 50.0))
+    _run(mesh, b, dict(use_lax_friedrichs_velocity=False), {}, {}, tol=1e-11)
+
+
+def test_periodic_coriolis_uv_bc():
+    # Rossby-soliton style set-up (test/swe2d/test_rossby_wave.py): g=1, h=1, f=y, 'uv' BCs
+    mesh = sfc_renumber(periodic_rectangle_mesh(48, 24, 48.0, 24.0, origin=(-24.0, -12.0)))
+    f = _vertex_field(mesh, lambda x, y: y)
+    bnd = {m: {"uv": (0.0, 0.0)} for m in mesh.unique_markers()}
+    _run(mesh, 1.0, {}, {"coriolis": f}, bnd, g=1.0, tol=1e-11)
+
+
+def test_unstructured_stommel_terms():
+    # stommel2d style: linear, coriolis beta-plane, wind stress, linear drag
+    mesh = sfc_renumber(delaunay_mesh(3000, 1e6, 1e6, seed=0))
+    f = _vertex_field(mesh, lambda x, y: 1e-4 + 2e-11 * y)
+    tau = np.stack([0.1 * np.sin(np.pi * (mesh.coords[:, 1] / 1e6 - 0.5)), 0 * mesh.coords[:, 1]], -1)
+    _run(mesh, 1000.0, dict(use_nonlinear_equations=False),
+         {"coriolis": f, "wind_stress": tau, "linear_drag_coefficient": 1e-6}, {})
+
+
+def test_manning_atm_pressure_sources_nonlinear():
+    mesh = sfc_renumber(rectangle_mesh(16, 16, 10e3, 10e3))
+    X, Y = mesh.coords[:, 0], mesh.coords[:, 1]
+    b = 5.0 + 1.0 * np.cos(np.pi * X / 10e3)
+    pa = 2.0 * 9.81 * 1000.0 * np.cos(np.pi * X / 10e3) * np.cos(np.pi * Y / 10e3)
+    ms = np.stack([1e-4 * np.sin(X / 3e3), 2e-4 * np.cos(Y / 2e3)], -1)
+    vs = 1e-4 * np.sin((X + Y) / 4e3)
+    _run(mesh, b, dict(norm_smoother=0.01),
+         {"manning_drag_coefficient": 0.03 + 0 * X, "atmospheric_pressure": pa, "momentum_source": ms,
+          "volume_source": vs, "coriolis": 1.2e-4, "wind_stress": (0.05, -0.02)}, {}, tol=1e-11)
+
+
+def test_quadratic_drag_const_linear_drag_field():
+    mesh = sfc_renumber(rectangle_mesh(10, 12, 1e3, 1e3))
+    X = mesh.coords[:, 0]
+    _run(mesh, 8.0, {}, {"quadratic_drag_coefficient": 2.5e-3, "linear_drag_coefficient": 1e-3 * (1 + X / 1e3)},
+         {}, tol=1e-11)
+
+
+@pytest.mark.parametrize("bc", [
+    {"elev": 0.3, "uv": (0.2, -0.1)},
+    {"elev": 0.3, "un": 0.15},
+    {"elev": -0.2, "flux": 500.0},
+    {"elev": 0.25},
+    {"uv": (0.1, 0.3)},
+    {"un": -0.2},
+    {"flux": -300.0},
+])
+@pytest.mark.parametrize("nonlinear", [True, False])
+def test_open_boundary_opcodes(bc, nonlinear):
+    mesh = sfc_renumber(rectangle_mesh(12, 10, 600.0, 500.0))
+    b = _vertex_field(mesh, lambda x, y: 12 + 0.004 * x)
+    bnd = {1: bc, 2: {"elev": 0.1}, 3: bc}
+    _run(mesh, b, dict(use_nonlinear_equations=nonlinear), {}, bnd, tol=1e-11)
+
+
+def test_open_boundary_arrays_north_sea():
+    # tidal elevation Function on marker 100 + uv Constant (demos/demo_2d_north_sea.py), Manning + Coriolis
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "mini_tagged.msh")
+    mesh = sfc_renumber(read_gmsh(path))
+    rng = np.random.default_rng(3)
+    elev = 0.5 + 0.1 * rng.standard_normal((mesh.n_bfacets, 2))
+    X, Y = mesh.coords[:, 0], mesh.coords[:, 1]
+    b = 30.0 + 5 * np.sin(X / 7.0) * np.cos(Y / 5.0)
+    _run(mesh, b, {}, {"manning_drag_coefficient": 0.03, "coriolis": 1e-4 + 1e-6 * Y},
+         {100: {"elev": 0.0, "uv": (0.0, 0.0)}}, tol=1e-11, bc_arrays={(100, "elev"): elev})
+
+
+def test_wetting_drying_residual():
+    mesh = sfc_renumber(rectangle_mesh(14, 6, 14e3, 1.2e3))
+    X = mesh.coords[:, 0]
+    b = 3.0 - 5.0 * X / 14e3          # dries out: negative bathymetry on the right
+    _run(mesh, b, dict(use_wetting_and_drying=True, wetting_and_drying_alpha=0.4),
+         {"manning_drag_coefficient": 0.02}, {1: {"elev": 0.5}}, tol=1e-10)

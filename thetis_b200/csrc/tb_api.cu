@@ -1,0 +1,792 @@
+// C-ABI glue: context, patch construction (native host runtime), option / coefficient /
+// boundary-condition tables, kernel launches.  See include/thetis_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include "tb_internal.h"
+
+#define TB_BC_PRESENT 32
+
+static thread_local std::string g_create_error;
+
+struct FieldStore {
+    int mode = 0;            // 0 none, 1 const, 2 vertex
+    int ncomp = 1;
+    double v[2] = {0, 0};
+    std::vector<double> vert;   // [nv*ncomp]
+    int col = -1;
+};
+
+struct BcHost {
+    std::vector<TbBcSlot> slots;   // per marker slot
+};
+
+struct tb_ctx {
+    int device = 0;
+    std::string err;
+    // mesh (host copies)
+    long long n_cells = 0, n_owned = 0, n_vertices = 0, n_bfacets = 0, n_tvert = 0;
+    std::vector<double> coords;
+    std::vector<int32_t> cells, nbr, bf_marker, topo;
+    std::vector<int8_t> nbr_lf;
+    long long n_patches = 0, n_owned_pad = 0;
+    // patch tables (host)
+    int NV = 0, NH = 0;
+    std::vector<int32_t> patch_vglob;   // [n_patches*NV] global vertex of each patch-local vertex (-1 pad)
+    std::vector<uint16_t> patch_cv;     // [n_patches*TB_P*3]
+    std::vector<int32_t> patch_cn;      // [n_patches*TB_P*3]
+    std::vector<int32_t> halo_ids;      // [n_patches*NH]
+    std::vector<int32_t> halo_cnt;
+    // device
+    unsigned char *d_sblk = nullptr;
+    size_t sblk_bytes = 0;
+    int32_t *d_halo_ids = nullptr, *d_halo_cnt = nullptr;
+    int32_t *d_bf_slot = nullptr;
+    double *d_ext[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // elev, uv, un, flux, value (swe)
+    double *d_ext_tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *d_area = nullptr;
+    std::vector<double> h_stage;        // pinned staging? (plain host vector; copies are small)
+    double *h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+    // layout
+    TbPatchLayout pl{};
+    bool layout_dirty = true;
+    int ncol = 3;
+    // options
+    double g = 9.81, rho0 = 1000.0, lf_sigma = 1.0, norm_smoother = 0.0, wd_alpha = 0.5;
+    int nonlinear = 1, lf_on = 1, wd_on = 0;
+    int lf_tracer = 0;
+    double lf_tracer_sigma = 1.0, tracer_vel_factor = 1.0;
+    FieldStore fields[TB_F_COUNT];
+    // bcs: eq 0 swe, 1 tracer
+    std::vector<int> slot_marker;       // slot -> marker
+    std::vector<int32_t> bf_slot;       // [n_bfacets]
+    TbBcSlot bc[2][TB_MAX_SLOTS];
+    // quadrature
+    int nquad = 0;
+    // patch range
+    long long range_first = 0, range_count = -1;
+    long long launches = 0;
+    // limiter
+    bool lim_ready = false;
+    TbLimiterData lim{};
+    long long *d_v2c_ptr = nullptr, *d_v2b_ptr = nullptr;
+    int *d_v2c_idx = nullptr, *d_v2b_idx = nullptr, *d_cell_tv = nullptr;
+    double *d_qmin = nullptr, *d_qmax = nullptr;
+};
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                            \
+            return TB_ERR_CUDA;                                                                        \
+        }                                                                                              \
+    } while (0)
+
+static int fail(tb_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+// ------------------------------------------------------------------ patch construction
+static int build_patches(tb_ctx *ctx) {
+    const long long no = ctx->n_owned;
+    const long long np = (no + TB_P - 1) / TB_P;
+    ctx->n_patches = np;
+    ctx->n_owned_pad = np * TB_P;
+    // ghosts (cells >= n_owned) live after the padded owned block: cell id g -> g - n_owned + n_owned_pad
+    auto dev_cell = [&](long long c) -> long long { return c < no ? c : c - no + ctx->n_owned_pad; };
+    std::vector<int32_t> vstamp(ctx->n_vertices, -1), vlocal(ctx->n_vertices, 0);
+    std::vector<int32_t> cstamp(ctx->n_cells, -1), clocal(ctx->n_cells, 0);
+    std::vector<std::vector<int32_t>> pv(np), ph(np);
+    int NV = 0, NH = 0;
+    for (long long p = 0; p < np; ++p) {
+        const long long c0 = p * TB_P, c1 = std::min(no, c0 + TB_P);
+        auto &vl = pv[p];
+        auto &hl = ph[p];
+        for (long long c = c0; c < c1; ++c) {
+            for (int a = 0; a < 3; ++a) {
+                const int32_t gv = ctx->cells[c * 3 + a];
+                if (gv < 0 || gv >= ctx->n_vertices) return fail(ctx, TB_ERR_ARG, "cell vertex id out of range");
+                if (vstamp[gv] != p) {
+                    vstamp[gv] = (int32_t)p;
+                    vlocal[gv] = (int32_t)vl.size();
+                    vl.push_back(gv);
+                }
+                const int32_t nb = ctx->nbr[c * 3 + a];
+                if (nb >= 0) {
+                    if (nb >= ctx->n_cells) return fail(ctx, TB_ERR_ARG, "neighbour id out of range");
+                    if ((nb < c0 || nb >= c1) && cstamp[nb] != p) {
+                        cstamp[nb] = (int32_t)p;
+                        clocal[nb] = (int32_t)hl.size();
+                        hl.push_back(nb);
+                    }
+                } else if (nb == std::numeric_limits<int32_t>::min()) {
+                    return fail(ctx, TB_ERR_ARG, "owned cell with unknown neighbour");
+                } else if (-(long long)nb - 1 >= ctx->n_bfacets) {
+                    return fail(ctx, TB_ERR_ARG, "exterior facet id out of range");
+                }
+            }
+        }
+        NV = std::max(NV, (int)vl.size());
+        NH = std::max(NH, (int)hl.size());
+    }
+    NV = (NV + 1) & ~1;
+    NH = (NH + 1) & ~1;
+    if (NV > 65535) return fail(ctx, TB_ERR_UNSUPPORTED, "patch vertex table too large");
+    ctx->NV = NV;
+    ctx->NH = NH;
+    ctx->patch_vglob.assign((size_t)np * NV, -1);
+    ctx->patch_cv.assign((size_t)np * TB_P * 3, 0);
+    ctx->patch_cn.assign((size_t)np * TB_P * 3, 0);
+    ctx->halo_ids.assign((size_t)np * std::max(NH, 1), 0);
+    ctx->halo_cnt.assign(np, 0);
+    // second pass: local ids (recompute stamps per patch)
+    std::fill(vstamp.begin(), vstamp.end(), -1);
+    std::fill(cstamp.begin(), cstamp.end(), -1);
+    for (long long p = 0; p < np; ++p) {
+        const long long c0 = p * TB_P, c1 = std::min(no, c0 + TB_P);
+        const auto &vl = pv[p];
+        const auto &hl = ph[p];
+        for (size_t k = 0; k < vl.size(); ++k) {
+            vstamp[vl[k]] = (int32_t)p;
+            vlocal[vl[k]] = (int32_t)k;
+            ctx->patch_vglob[(size_t)p * NV + k] = vl[k];
+        }
+        for (size_t k = 0; k < hl.size(); ++k) {
+            cstamp[hl[k]] = (int32_t)p;
+            clocal[hl[k]] = (int32_t)k;
+            ctx->halo_ids[(size_t)p * NH + k] = (int32_t)dev_cell(hl[k]);
+        }
+        ctx->halo_cnt[p] = (int32_t)hl.size();
+        for (long long c = c0; c < c1; ++c) {
+            const size_t o = ((size_t)p * TB_P + (c - c0)) * 3;
+            for (int a = 0; a < 3; ++a) {
+                ctx->patch_cv[o + a] = (uint16_t)vlocal[ctx->cells[c * 3 + a]];
+                const int32_t nb = ctx->nbr[c * 3 + a];
+                if (nb >= 0) {
+                    const int li = (nb >= c0 && nb < c1) ? (int)(nb - c0) : TB_P + clocal[nb];
+                    ctx->patch_cn[o + a] = li * 4 + (int)ctx->nbr_lf[c * 3 + a];
+                } else {
+                    ctx->patch_cn[o + a] = nb;
+                }
+            }
+        }
+    }
+    return TB_OK;
+}
+
+static int upload_layout(tb_ctx *ctx) {
+    // assign columns
+    int ncol = 3;
+    ctx->fields[TB_F_BATHYMETRY].col = 2;
+    for (int f = 1; f < TB_F_COUNT; ++f) {
+        FieldStore &fs = ctx->fields[f];
+        fs.col = -1;
+        if (fs.mode == 2) {
+            fs.col = ncol;
+            ncol += fs.ncomp;
+        }
+    }
+    ctx->ncol = ncol;
+    const int NV = ctx->NV;
+    const long long np = ctx->n_patches;
+    const size_t off_cv = (size_t)ncol * NV * sizeof(double);
+    const size_t off_cn = off_cv + (size_t)TB_P * 3 * sizeof(uint16_t);
+    const size_t stride = off_cn + (size_t)TB_P * 3 * sizeof(int32_t);
+    std::vector<unsigned char> host((size_t)np * stride, 0);
+    const FieldStore &bath = ctx->fields[TB_F_BATHYMETRY];
+    if (bath.mode == 0) return fail(ctx, TB_ERR_STATE, "bathymetry not set");
+    for (long long p = 0; p < np; ++p) {
+        unsigned char *blk = host.data() + (size_t)p * stride;
+        double *cols = reinterpret_cast<double *>(blk);
+        for (int k = 0; k < NV; ++k) {
+            int gv = ctx->patch_vglob[(size_t)p * NV + k];
+            if (gv < 0) gv = ctx->patch_vglob[(size_t)p * NV];   // pad with a valid vertex
+            if (gv < 0) continue;
+            cols[k] = ctx->coords[2 * (size_t)gv];
+            cols[NV + k] = ctx->coords[2 * (size_t)gv + 1];
+            cols[2 * NV + k] = bath.mode == 2 ? bath.vert[gv] : bath.v[0];
+            for (int f = 1; f < TB_F_COUNT; ++f) {
+                const FieldStore &fs = ctx->fields[f];
+                if (fs.mode != 2) continue;
+                for (int cpt = 0; cpt < fs.ncomp; ++cpt)
+                    cols[(size_t)(fs.col + cpt) * NV + k] = fs.vert[(size_t)gv * fs.ncomp + cpt];
+            }
+        }
+        memcpy(blk + off_cv, ctx->patch_cv.data() + (size_t)p * TB_P * 3, (size_t)TB_P * 3 * sizeof(uint16_t));
+        memcpy(blk + off_cn, ctx->patch_cn.data() + (size_t)p * TB_P * 3, (size_t)TB_P * 3 * sizeof(int32_t));
+    }
+    if (host.size() != ctx->sblk_bytes) {
+        if (ctx->d_sblk) cudaFree(ctx->d_sblk);
+        ctx->d_sblk = nullptr;
+        CK(cudaMalloc(&ctx->d_sblk, std::max<size_t>(host.size(), 16)));
+        ctx->sblk_bytes = host.size();
+    }
+    // the blocks may be in use by kernels already queued: order the copy after them
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(ctx->d_sblk, host.data(), host.size(), cudaMemcpyHostToDevice));
+    ctx->pl.sblk = ctx->d_sblk;
+    ctx->pl.stride = (long long)stride;
+    ctx->pl.NV = NV;
+    ctx->pl.NH = ctx->NH;
+    ctx->pl.ncol = ncol;
+    ctx->pl.off_cv = (int)off_cv;
+    ctx->pl.off_cn = (int)off_cn;
+    ctx->pl.halo_ids = ctx->d_halo_ids;
+    ctx->pl.halo_cnt = ctx->d_halo_cnt;
+    ctx->layout_dirty = false;
+    return TB_OK;
+}
+
+static void default_quadrature(tb_ctx *ctx) {
+    // Strang-Fix 6-point degree-3 rule (FIAT's classic default for degree 3)
+    const double a = 0.659027622374092, b = 0.231933368553031, c = 0.109039009072877;
+    const double xy[6][2] = {{a, b}, {a, c}, {b, a}, {b, c}, {c, a}, {c, b}};
+    double lam[6][3], w[6];
+    for (int i = 0; i < 6; ++i) {
+        lam[i][0] = 1.0 - xy[i][0] - xy[i][1];
+        lam[i][1] = xy[i][0];
+        lam[i][2] = xy[i][1];
+        w[i] = 1.0 / 6.0;
+    }
+    tb_set_quadrature(6, &lam[0][0], w);
+    ctx->nquad = 6;
+}
+
+// ------------------------------------------------------------------ lifetime
+extern "C" int tb_version(void) { return 100; }
+
+extern "C" const char *tb_last_error(const tb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int tb_create(tb_ctx **out, const tb_mesh *m, int device) {
+    if (!out || !m) return fail(nullptr, TB_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (m->n_cells <= 0 || m->n_owned <= 0 || m->n_owned > m->n_cells || m->n_vertices <= 0 || !m->coords ||
+        !m->cells || !m->nbr || !m->nbr_lf || (m->n_bfacets > 0 && !m->bf_marker))
+        return fail(nullptr, TB_ERR_ARG, "invalid mesh description");
+    if (m->n_cells > (1ll << 29)) return fail(nullptr, TB_ERR_UNSUPPORTED, "too many cells for 32-bit patch tables");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TB_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, TB_ERR_ARG, "bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, TB_ERR_CUDA, cudaGetErrorString(e));
+    tb_ctx *ctx = new (std::nothrow) tb_ctx();
+    if (!ctx) return fail(nullptr, TB_ERR_STATE, "out of host memory");
+    ctx->device = device;
+    ctx->n_cells = m->n_cells;
+    ctx->n_owned = m->n_owned;
+    ctx->n_vertices = m->n_vertices;
+    ctx->n_bfacets = m->n_bfacets;
+    ctx->coords.assign(m->coords, m->coords + 2 * m->n_vertices);
+    ctx->cells.assign(m->cells, m->cells + 3 * m->n_cells);
+    ctx->nbr.assign(m->nbr, m->nbr + 3 * m->n_cells);
+    ctx->nbr_lf.assign(m->nbr_lf, m->nbr_lf + 3 * m->n_cells);
+    if (m->n_bfacets) ctx->bf_marker.assign(m->bf_marker, m->bf_marker + m->n_bfacets);
+    ctx->topo.resize(m->n_vertices);
+    for (long long v = 0; v < m->n_vertices; ++v) ctx->topo[v] = m->topo ? m->topo[v] : (int32_t)v;
+    ctx->n_tvert = 0;
+    for (long long v = 0; v < m->n_vertices; ++v) ctx->n_tvert = std::max<long long>(ctx->n_tvert, ctx->topo[v] + 1);
+    // geometry sanity: CCW cells
+    std::vector<double> area(m->n_owned);
+    for (long long c = 0; c < m->n_owned; ++c) {
+        const double *p0 = &ctx->coords[2 * (size_t)ctx->cells[3 * c]];
+        const double *p1 = &ctx->coords[2 * (size_t)ctx->cells[3 * c + 1]];
+        const double *p2 = &ctx->coords[2 * (size_t)ctx->cells[3 * c + 2]];
+        const double a2 = (p1[0] - p0[0]) * (p2[1] - p0[1]) - (p1[1] - p0[1]) * (p2[0] - p0[0]);
+        if (!(a2 > 0)) {
+            delete ctx;
+            return fail(nullptr, TB_ERR_ARG, "cells must be counter-clockwise with positive area");
+        }
+        area[c] = 0.5 * a2;
+    }
+    int rc = build_patches(ctx);
+    if (rc != TB_OK) {
+        g_create_error = ctx->err;
+        delete ctx;
+        return rc;
+    }
+    // boundary marker slots
+    ctx->bf_slot.resize(m->n_bfacets);
+    for (long long k = 0; k < m->n_bfacets; ++k) {
+        const int mk = ctx->bf_marker[k];
+        int s = -1;
+        for (size_t j = 0; j < ctx->slot_marker.size(); ++j)
+            if (ctx->slot_marker[j] == mk) s = (int)j;
+        if (s < 0) {
+            if (ctx->slot_marker.size() >= TB_MAX_SLOTS) {
+                delete ctx;
+                return fail(nullptr, TB_ERR_UNSUPPORTED, "more than 16 distinct boundary markers");
+            }
+            s = (int)ctx->slot_marker.size();
+            ctx->slot_marker.push_back(mk);
+        }
+        ctx->bf_slot[k] = s;
+    }
+    memset(ctx->bc, 0, sizeof(ctx->bc));
+    for (int eq = 0; eq < 2; ++eq)
+        for (size_t j = 0; j < ctx->slot_marker.size(); ++j) {
+            ctx->bc[eq][j].marker = ctx->slot_marker[j];
+            ctx->bc[eq][j].bnd_len = 1.0;
+        }
+#define CKC(call)                                                              \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) {                                              \
+            g_create_error = std::string(#call) + ": " + cudaGetErrorString(e__); \
+            tb_destroy(ctx);                                                   \
+            return TB_ERR_CUDA;                                                \
+        }                                                                      \
+    } while (0)
+    CKC(tb_kernels_init());
+    CKC(cudaMalloc(&ctx->d_halo_ids, sizeof(int32_t) * std::max<size_t>(ctx->halo_ids.size(), 4)));
+    CKC(cudaMemcpy(ctx->d_halo_ids, ctx->halo_ids.data(), sizeof(int32_t) * ctx->halo_ids.size(),
+                   cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&ctx->d_halo_cnt, sizeof(int32_t) * ctx->n_patches));
+    CKC(cudaMemcpy(ctx->d_halo_cnt, ctx->halo_cnt.data(), sizeof(int32_t) * ctx->n_patches, cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&ctx->d_bf_slot, sizeof(int32_t) * std::max<long long>(m->n_bfacets, 4)));
+    if (m->n_bfacets)
+        CKC(cudaMemcpy(ctx->d_bf_slot, ctx->bf_slot.data(), sizeof(int32_t) * m->n_bfacets, cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&ctx->d_area, sizeof(double) * m->n_owned));
+    CKC(cudaMemcpy(ctx->d_area, area.data(), sizeof(double) * m->n_owned, cudaMemcpyHostToDevice));
+    default_quadrature(ctx);
+    *out = ctx;
+    return TB_OK;
+}
+
+extern "C" int tb_destroy(tb_ctx *ctx) {
+    if (!ctx) return TB_OK;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_sblk);
+    cudaFree(ctx->d_halo_ids);
+    cudaFree(ctx->d_halo_cnt);
+    cudaFree(ctx->d_bf_slot);
+    cudaFree(ctx->d_area);
+    for (int k = 0; k < 5; ++k) {
+        cudaFree(ctx->d_ext[k]);
+        cudaFree(ctx->d_ext_tr[k]);
+    }
+    cudaFree(ctx->d_v2c_ptr);
+    cudaFree(ctx->d_v2b_ptr);
+    cudaFree(ctx->d_v2c_idx);
+    cudaFree(ctx->d_v2b_idx);
+    cudaFree(ctx->d_cell_tv);
+    cudaFree(ctx->d_qmin);
+    cudaFree(ctx->d_qmax);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx;
+    return TB_OK;
+}
+
+// ------------------------------------------------------------------ sizes
+extern "C" int64_t tb_state_len(const tb_ctx *ctx) {
+    return ctx ? (ctx->n_owned_pad + (ctx->n_cells - ctx->n_owned)) * 9 : 0;
+}
+extern "C" int64_t tb_tracer_len(const tb_ctx *ctx) {
+    return ctx ? (ctx->n_owned_pad + (ctx->n_cells - ctx->n_owned)) * 3 : 0;
+}
+extern "C" int64_t tb_patch_size(const tb_ctx *) { return TB_P; }
+extern "C" int64_t tb_n_patches(const tb_ctx *ctx) { return ctx ? ctx->n_patches : 0; }
+extern "C" int64_t tb_launch_count(const tb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------ options
+extern "C" int tb_set_option(tb_ctx *ctx, int option, double value) {
+    if (!ctx) return TB_ERR_ARG;
+    switch (option) {
+        case TB_OPT_G_GRAV: ctx->g = value; break;
+        case TB_OPT_RHO0: ctx->rho0 = value; break;
+        case TB_OPT_NONLINEAR: ctx->nonlinear = value != 0.0; break;
+        case TB_OPT_LAX_FRIEDRICHS: ctx->lf_on = value != 0.0; break;
+        case TB_OPT_LF_SCALING: ctx->lf_sigma = value; break;
+        case TB_OPT_NORM_SMOOTHER: ctx->norm_smoother = value; break;
+        case TB_OPT_WETTING_DRYING: ctx->wd_on = value != 0.0; break;
+        case TB_OPT_WD_ALPHA: ctx->wd_alpha = value; break;
+        case TB_OPT_LF_TRACER: ctx->lf_tracer = value != 0.0; break;
+        case TB_OPT_LF_TRACER_SCALING: ctx->lf_tracer_sigma = value; break;
+        case TB_OPT_TRACER_VEL_FACTOR: ctx->tracer_vel_factor = value; break;
+        default: return fail(ctx, TB_ERR_ARG, "unknown option");
+    }
+    return TB_OK;
+}
+
+static int field_ncomp(int field) { return (field == TB_F_WIND_STRESS || field == TB_F_MOMENTUM_SOURCE) ? 2 : 1; }
+
+extern "C" int tb_set_field_const(tb_ctx *ctx, int field, const double *value, int ncomp) {
+    if (!ctx || !value || field < 0 || field >= TB_F_COUNT) return fail(ctx, TB_ERR_ARG, "bad field");
+    if (ncomp != field_ncomp(field)) return fail(ctx, TB_ERR_ARG, "wrong number of components");
+    FieldStore &fs = ctx->fields[field];
+    if (fs.mode == 2 || field == TB_F_BATHYMETRY) ctx->layout_dirty = true;
+    fs.mode = 1;
+    fs.ncomp = ncomp;
+    fs.v[0] = value[0];
+    fs.v[1] = ncomp > 1 ? value[1] : 0.0;
+    fs.vert.clear();
+    return TB_OK;
+}
+
+extern "C" int tb_set_field_vertex(tb_ctx *ctx, int field, const double *values, int ncomp) {
+    if (!ctx || !values || field < 0 || field >= TB_F_COUNT) return fail(ctx, TB_ERR_ARG, "bad field");
+    if (ncomp != field_ncomp(field)) return fail(ctx, TB_ERR_ARG, "wrong number of components");
+    FieldStore &fs = ctx->fields[field];
+    fs.mode = 2;
+    fs.ncomp = ncomp;
+    fs.vert.assign(values, values + (size_t)ctx->n_vertices * ncomp);
+    ctx->layout_dirty = true;
+    return TB_OK;
+}
+
+extern "C" int tb_clear_field(tb_ctx *ctx, int field) {
+    if (!ctx || field < 0 || field >= TB_F_COUNT) return fail(ctx, TB_ERR_ARG, "bad field");
+    FieldStore &fs = ctx->fields[field];
+    if (fs.mode == 2) ctx->layout_dirty = true;
+    fs.mode = 0;
+    fs.vert.clear();
+    return TB_OK;
+}
+
+static int find_slot(tb_ctx *ctx, int marker) {
+    for (size_t j = 0; j < ctx->slot_marker.size(); ++j)
+        if (ctx->slot_marker[j] == marker) return (int)j;
+    return -1;
+}
+
+extern "C" int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const double consts[6]) {
+    if (!ctx || eq < 0 || eq > 1) return fail(ctx, TB_ERR_ARG, "bad equation id");
+    const int s = find_slot(ctx, marker);
+    if (s < 0) return TB_OK;   // marker not present on this (sub)mesh: nothing to do (reference loops over mesh markers)
+    if (opcode & ~(TB_BC_ELEV | TB_BC_UV | TB_BC_UN | TB_BC_FLUX | TB_BC_VALUE))
+        return fail(ctx, TB_ERR_ARG, "invalid boundary tag");
+    TbBcSlot &b = ctx->bc[eq][s];
+    b.opcode = opcode | TB_BC_PRESENT;
+    b.arr_mask = 0;
+    if (consts) {
+        b.elev = consts[0]; b.uvx = consts[1]; b.uvy = consts[2];
+        b.un = consts[3]; b.flux = consts[4]; b.value = consts[5];
+    }
+    return TB_OK;
+}
+
+extern "C" int tb_set_boundary_length(tb_ctx *ctx, int marker, double length) {
+    if (!ctx) return TB_ERR_ARG;
+    const int s = find_slot(ctx, marker);
+    if (s < 0) return TB_OK;
+    ctx->bc[0][s].bnd_len = length;
+    ctx->bc[1][s].bnd_len = length;
+    return TB_OK;
+}
+
+extern "C" int tb_set_bc_array(tb_ctx *ctx, int eq, int marker, int tag, const double *values, int ncomp,
+                               void *stream) {
+    if (!ctx || eq < 0 || eq > 1 || !values) return fail(ctx, TB_ERR_ARG, "bad argument");
+    const int s = find_slot(ctx, marker);
+    if (s < 0) return TB_OK;
+    int k;
+    switch (tag) {
+        case TB_BC_ELEV: k = 0; break;
+        case TB_BC_UV: k = 1; break;
+        case TB_BC_UN: k = 2; break;
+        case TB_BC_FLUX: k = 3; break;
+        case TB_BC_VALUE: k = 4; break;
+        default: return fail(ctx, TB_ERR_ARG, "invalid boundary tag");
+    }
+    const int nc = (tag == TB_BC_UV) ? 2 : 1;
+    if (ncomp != nc) return fail(ctx, TB_ERR_ARG, "wrong number of components");
+    if (!(ctx->bc[eq][s].opcode & tag)) return fail(ctx, TB_ERR_STATE, "tag not declared with tb_set_bc");
+    double **slot_arr = eq == 0 ? ctx->d_ext : ctx->d_ext_tr;
+    const size_t n = (size_t)ctx->n_bfacets * 2 * nc;
+    if (!slot_arr[k]) {
+        CK(cudaMalloc(&slot_arr[k], sizeof(double) * std::max<size_t>(n, 2)));
+        CK(cudaMemset(slot_arr[k], 0, sizeof(double) * std::max<size_t>(n, 2)));
+    }
+    // stage only this marker's entries through pinned memory so several markers can hold arrays
+    if (ctx->h_pinned_bytes < n * sizeof(double)) {
+        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        ctx->h_pinned = nullptr;
+        CK(cudaMallocHost(&ctx->h_pinned, n * sizeof(double)));
+        ctx->h_pinned_bytes = n * sizeof(double);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    // the pinned buffer may still be in flight from the previous call on this stream
+    CK(cudaStreamSynchronize(st));
+    const size_t w = 2 * (size_t)nc;
+    // copy contiguous runs of facets belonging to this marker
+    long long k0 = -1;
+    for (long long f = 0; f <= ctx->n_bfacets; ++f) {
+        const bool mine = f < ctx->n_bfacets && ctx->bf_slot[f] == s;
+        if (mine && k0 < 0) k0 = f;
+        if (!mine && k0 >= 0) {
+            memcpy(ctx->h_pinned + k0 * w, values + k0 * w, sizeof(double) * w * (f - k0));
+            CK(cudaMemcpyAsync(slot_arr[k] + k0 * w, ctx->h_pinned + k0 * w, sizeof(double) * w * (f - k0),
+                               cudaMemcpyHostToDevice, st));
+            k0 = -1;
+        }
+    }
+    ctx->bc[eq][s].arr_mask |= tag;
+    return TB_OK;
+}
+
+// ------------------------------------------------------------------ hot path
+static void fill_coef(const FieldStore &fs, TbCoef &c) {
+    c.mode = fs.mode;
+    c.col = fs.col;
+    c.v0 = fs.v[0];
+    c.v1 = fs.v[1];
+}
+
+static void fill_bc(tb_ctx *ctx, int eq, TbBcTable &t) {
+    t.n_slots = (int)ctx->slot_marker.size();
+    t.bf_slot = ctx->d_bf_slot;
+    double **a = eq == 0 ? ctx->d_ext : ctx->d_ext_tr;
+    t.ext_elev = a[0];
+    t.ext_uv = a[1];
+    t.ext_un = a[2];
+    t.ext_flux = a[3];
+    t.ext_value = a[4];
+    memcpy(t.slots, ctx->bc[eq], sizeof(TbBcSlot) * TB_MAX_SLOTS);
+}
+
+static void patch_range(tb_ctx *ctx, long long &first, long long &count) {
+    first = 0;
+    count = ctx->n_patches;
+    if (ctx->range_count >= 0) {
+        first = std::min(ctx->range_first, ctx->n_patches);
+        count = std::min(ctx->range_count, ctx->n_patches - first);
+    }
+}
+
+extern "C" int tb_swe_stage(tb_ctx *ctx, double a0, double a1, double b_dt, const double *u_in, const double *u0,
+                            double *u_out, void *stream) {
+    if (!ctx || !u_in || !u_out) return fail(ctx, TB_ERR_ARG, "null state pointer");
+    if (u_in == u_out) return fail(ctx, TB_ERR_ARG, "u_out must not alias u_in");
+    if (a0 != 0.0 && !u0) return fail(ctx, TB_ERR_ARG, "u0 required when a0 != 0");
+    if (ctx->fields[TB_F_MANNING].mode && ctx->fields[TB_F_QUAD_DRAG].mode)
+        return fail(ctx, TB_ERR_ARG, "Cannot set both dimensionless and Manning drag parameter");
+    if (ctx->layout_dirty) {
+        int rc = upload_layout(ctx);
+        if (rc != TB_OK) return rc;
+    }
+    TbSweParams p;
+    memset(&p, 0, sizeof(p));
+    p.u_in = u_in;
+    p.u0 = (a0 != 0.0) ? u0 : nullptr;
+    p.u_out = u_out;
+    p.pl = ctx->pl;
+    p.n_owned = (int)ctx->n_owned;
+    p.a0 = a0;
+    p.a1 = a1;
+    p.bdt = b_dt;
+    p.g = ctx->g;
+    p.rho0 = ctx->rho0;
+    p.lf_sigma = ctx->lf_sigma;
+    p.eps2 = ctx->norm_smoother * ctx->norm_smoother;
+    p.wd_alpha2 = ctx->wd_alpha * ctx->wd_alpha;
+    p.lf_on = ctx->lf_on;
+    p.wd_on = ctx->wd_on && ctx->nonlinear;
+    fill_coef(ctx->fields[TB_F_CORIOLIS], p.cor);
+    fill_coef(ctx->fields[TB_F_MANNING], p.man);
+    fill_coef(ctx->fields[TB_F_QUAD_DRAG], p.cd);
+    fill_coef(ctx->fields[TB_F_LINEAR_DRAG], p.lin);
+    fill_coef(ctx->fields[TB_F_WIND_STRESS], p.wind);
+    fill_coef(ctx->fields[TB_F_ATM_PRESSURE], p.pa);
+    fill_coef(ctx->fields[TB_F_MOMENTUM_SOURCE], p.msrc);
+    fill_coef(ctx->fields[TB_F_VOLUME_SOURCE], p.vsrc);
+    p.use_quad = (p.man.mode || p.cd.mode || p.wind.mode || p.wd_on) ? 1 : 0;
+    p.nquad = ctx->nquad;
+    fill_bc(ctx, 0, p.bc);
+    long long first, count;
+    patch_range(ctx, first, count);
+    p.patch_first = (int)first;
+    const size_t smem = tb_swe_smem_bytes(ctx->pl);
+    if (smem > 200 * 1024) return fail(ctx, TB_ERR_UNSUPPORTED, "patch halo too large for shared memory");
+    CK(tb_launch_swe_stage(p, ctx->nonlinear != 0, (int)count, smem, (cudaStream_t)stream));
+    ctx->launches += count > 0 ? 1 : 0;
+    return TB_OK;
+}
+
+extern "C" int tb_swe_tendency(tb_ctx *ctx, const double *u, double *k_out, void *stream) {
+    return tb_swe_stage(ctx, 0.0, 0.0, 1.0, u, nullptr, k_out, stream);
+}
+
+extern "C" int tb_tracer_stage(tb_ctx *ctx, double a0, double a1, double b_dt, const double *c_in, const double *c0,
+                               double *c_out, const double *swe_state, void *stream) {
+    if (!ctx || !c_in || !c_out || !swe_state) return fail(ctx, TB_ERR_ARG, "null state pointer");
+    if (c_in == c_out) return fail(ctx, TB_ERR_ARG, "c_out must not alias c_in");
+    if (a0 != 0.0 && !c0) return fail(ctx, TB_ERR_ARG, "c0 required when a0 != 0");
+    if (ctx->layout_dirty) {
+        int rc = upload_layout(ctx);
+        if (rc != TB_OK) return rc;
+    }
+    TbTracerParams p;
+    memset(&p, 0, sizeof(p));
+    p.c_in = c_in;
+    p.c0 = (a0 != 0.0) ? c0 : nullptr;
+    p.c_out = c_out;
+    p.swe = swe_state;
+    p.pl = ctx->pl;
+    p.n_owned = (int)ctx->n_owned;
+    p.a0 = a0;
+    p.a1 = a1;
+    p.bdt = b_dt;
+    p.corr = ctx->tracer_vel_factor;
+    p.lf_sigma = ctx->lf_tracer_sigma;
+    p.lf_on = ctx->lf_tracer;
+    p.nonlin = ctx->nonlinear;
+    p.wd_on = ctx->wd_on && ctx->nonlinear;
+    p.wd_alpha2 = ctx->wd_alpha * ctx->wd_alpha;
+    fill_coef(ctx->fields[TB_F_TRACER_SOURCE], p.src);
+    fill_bc(ctx, 1, p.bc);
+    long long first, count;
+    patch_range(ctx, first, count);
+    p.patch_first = (int)first;
+    const size_t smem = tb_tracer_smem_bytes(ctx->pl);
+    if (smem > 200 * 1024) return fail(ctx, TB_ERR_UNSUPPORTED, "patch halo too large for shared memory");
+    CK(tb_launch_tracer_stage(p, (int)count, smem, (cudaStream_t)stream));
+    ctx->launches += count > 0 ? 1 : 0;
+    return TB_OK;
+}
+
+static int limiter_setup(tb_ctx *ctx) {
+    const long long nc = ctx->n_cells, no = ctx->n_owned, nt = ctx->n_tvert;
+    auto dev_cell = [&](long long c) -> long long { return c < no ? c : c - no + ctx->n_owned_pad; };
+    std::vector<long long> cnt(nt + 1, 0);
+    std::vector<int> cell_tv((size_t)(ctx->n_owned_pad + (nc - no)) * 3, 0);
+    for (long long c = 0; c < nc; ++c)
+        for (int a = 0; a < 3; ++a) {
+            const int tv = ctx->topo[ctx->cells[3 * c + a]];
+            cnt[tv + 1]++;
+            cell_tv[(size_t)dev_cell(c) * 3 + a] = tv;
+        }
+    std::vector<long long> ptr(nt + 1, 0);
+    for (long long v = 0; v < nt; ++v) ptr[v + 1] = ptr[v] + cnt[v + 1];
+    std::vector<int> idx(ptr[nt]);
+    std::vector<long long> fillp(ptr.begin(), ptr.end() - 1);
+    for (long long c = 0; c < nc; ++c)
+        for (int a = 0; a < 3; ++a) idx[fillp[ctx->topo[ctx->cells[3 * c + a]]]++] = (int)dev_cell(c);
+    // exterior facets per vertex
+    std::vector<long long> bcnt(nt + 1, 0);
+    for (long long c = 0; c < nc; ++c)
+        for (int f = 0; f < 3; ++f) {
+            const int32_t nb = ctx->nbr[3 * c + f];
+            if (nb < 0 && nb != std::numeric_limits<int32_t>::min()) {
+                bcnt[ctx->topo[ctx->cells[3 * c + (f + 1) % 3]] + 1]++;
+                bcnt[ctx->topo[ctx->cells[3 * c + (f + 2) % 3]] + 1]++;
+            }
+        }
+    std::vector<long long> bptr(nt + 1, 0);
+    for (long long v = 0; v < nt; ++v) bptr[v + 1] = bptr[v] + bcnt[v + 1];
+    std::vector<int> bidx(std::max<long long>(bptr[nt], 1));
+    std::vector<long long> bfill(bptr.begin(), bptr.end() - 1);
+    for (long long c = 0; c < nc; ++c)
+        for (int f = 0; f < 3; ++f) {
+            const int32_t nb = ctx->nbr[3 * c + f];
+            if (nb < 0 && nb != std::numeric_limits<int32_t>::min()) {
+                const int code = (int)dev_cell(c) * 4 + f;
+                bidx[bfill[ctx->topo[ctx->cells[3 * c + (f + 1) % 3]]]++] = code;
+                bidx[bfill[ctx->topo[ctx->cells[3 * c + (f + 2) % 3]]]++] = code;
+            }
+        }
+    CK(cudaMalloc(&ctx->d_v2c_ptr, sizeof(long long) * (nt + 1)));
+    CK(cudaMemcpy(ctx->d_v2c_ptr, ptr.data(), sizeof(long long) * (nt + 1), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->d_v2c_idx, sizeof(int) * std::max<size_t>(idx.size(), 1)));
+    CK(cudaMemcpy(ctx->d_v2c_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->d_v2b_ptr, sizeof(long long) * (nt + 1)));
+    CK(cudaMemcpy(ctx->d_v2b_ptr, bptr.data(), sizeof(long long) * (nt + 1), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->d_v2b_idx, sizeof(int) * bidx.size()));
+    CK(cudaMemcpy(ctx->d_v2b_idx, bidx.data(), sizeof(int) * bidx.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->d_cell_tv, sizeof(int) * cell_tv.size()));
+    CK(cudaMemcpy(ctx->d_cell_tv, cell_tv.data(), sizeof(int) * cell_tv.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->d_qmin, sizeof(double) * nt));
+    CK(cudaMalloc(&ctx->d_qmax, sizeof(double) * nt));
+    ctx->lim.n_owned = no;
+    ctx->lim.n_cells = nc;
+    ctx->lim.n_tvert = nt;
+    ctx->lim.v2c_ptr = ctx->d_v2c_ptr;
+    ctx->lim.v2c_idx = ctx->d_v2c_idx;
+    ctx->lim.v2b_ptr = ctx->d_v2b_ptr;
+    ctx->lim.v2b_idx = ctx->d_v2b_idx;
+    ctx->lim.cell_tv = ctx->d_cell_tv;
+    ctx->lim.qmin = ctx->d_qmin;
+    ctx->lim.qmax = ctx->d_qmax;
+    ctx->lim_ready = true;
+    return TB_OK;
+}
+
+extern "C" int tb_limiter_apply(tb_ctx *ctx, double *c, void *stream) {
+    if (!ctx || !c) return fail(ctx, TB_ERR_ARG, "null pointer");
+    if (!ctx->lim_ready) {
+        int rc = limiter_setup(ctx);
+        if (rc != TB_OK) return rc;
+    }
+    CK(tb_launch_limiter(ctx->lim, c, (cudaStream_t)stream));
+    ctx->launches += 2;
+    return TB_OK;
+}
+
+// ------------------------------------------------------------------ layout conversion & diagnostics
+extern "C" int tb_state_from_fields(tb_ctx *ctx, const double *uv, const double *eta, const int32_t *node_map,
+                                    double *state, void *stream) {
+    if (!ctx || !uv || !eta || !node_map || !state) return fail(ctx, TB_ERR_ARG, "null pointer");
+    CK(tb_launch_state_from_fields(uv, eta, node_map, state, ctx->n_owned, (cudaStream_t)stream));
+    ctx->launches++;
+    return TB_OK;
+}
+extern "C" int tb_state_to_fields(tb_ctx *ctx, const double *state, const int32_t *node_map, double *uv, double *eta,
+                                  void *stream) {
+    if (!ctx || !uv || !eta || !node_map || !state) return fail(ctx, TB_ERR_ARG, "null pointer");
+    CK(tb_launch_state_to_fields(state, node_map, uv, eta, ctx->n_owned, (cudaStream_t)stream));
+    ctx->launches++;
+    return TB_OK;
+}
+extern "C" int tb_tracer_from_field(tb_ctx *ctx, const double *q, const int32_t *node_map, double *c, void *stream) {
+    if (!ctx || !q || !node_map || !c) return fail(ctx, TB_ERR_ARG, "null pointer");
+    CK(tb_launch_tracer_from_field(q, node_map, c, ctx->n_owned, (cudaStream_t)stream));
+    ctx->launches++;
+    return TB_OK;
+}
+extern "C" int tb_tracer_to_field(tb_ctx *ctx, const double *c, const int32_t *node_map, double *q, void *stream) {
+    if (!ctx || !q || !node_map || !c) return fail(ctx, TB_ERR_ARG, "null pointer");
+    CK(tb_launch_tracer_to_field(c, node_map, q, ctx->n_owned, (cudaStream_t)stream));
+    ctx->launches++;
+    return TB_OK;
+}
+extern "C" int tb_swe_integrals(tb_ctx *ctx, const double *state, double *out, void *stream) {
+    if (!ctx || !state || !out) return fail(ctx, TB_ERR_ARG, "null pointer");
+    CK(tb_launch_swe_integrals(state, ctx->d_area, ctx->n_owned, out, (cudaStream_t)stream));
+    ctx->launches += 2;
+    return TB_OK;
+}
+extern "C" int tb_gather_cells(tb_ctx *ctx, const double *state, const int32_t *idx, int64_t n, int rec_len,
+                               double *buf, void *stream) {
+    if (!ctx || (n > 0 && (!state || !idx || !buf))) return fail(ctx, TB_ERR_ARG, "null pointer");
+    CK(tb_launch_gather_cells(state, idx, n, rec_len, buf, (cudaStream_t)stream));
+    ctx->launches += n > 0;
+    return TB_OK;
+}
+extern "C" int tb_scatter_cells(tb_ctx *ctx, const double *buf, const int32_t *idx, int64_t n, int rec_len,
+                                double *state, void *stream) {
+    if (!ctx || (n > 0 && (!state || !idx || !buf))) return fail(ctx, TB_ERR_ARG, "null pointer");
+    CK(tb_launch_scatter_cells(buf, idx, n, rec_len, state, (cudaStream_t)stream));
+    ctx->launches += n > 0;
+    return TB_OK;
+}
+extern "C" int tb_set_patch_range(tb_ctx *ctx, int64_t first, int64_t count) {
+    if (!ctx) return TB_ERR_ARG;
+    ctx->range_first = first;
+    ctx->range_count = count;
+    return TB_OK;
+}
+
+extern "C" int tb_set_cell_quadrature(tb_ctx *ctx, int n, const double *lam, const double *w) {
+    if (!ctx || !lam || !w || n < 1 || n > TB_MAX_QUAD) return fail(ctx, TB_ERR_ARG, "bad quadrature rule");
+    CK(cudaDeviceSynchronize());
+    CK(tb_set_quadrature(n, lam, w));
+    ctx->nquad = n;
+    return TB_OK;
+}

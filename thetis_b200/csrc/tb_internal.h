@@ -1,0 +1,116 @@
+// Internal structures shared by the kernels and the C-ABI glue (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/thetis_b200.h"
+
+#define TB_P 128            // cells per patch == threads per CTA (one thread per cell)
+#define TB_MAX_SLOTS 16     // distinct boundary markers
+#define TB_MAX_QUAD 12      // max cell quadrature points
+
+// coefficient descriptor: mode 0 = None, 1 = Constant, 2 = P1 vertex column(s)
+struct TbCoef {
+    int mode;
+    int col;
+    double v0, v1;
+};
+
+struct TbBcSlot {
+    int marker;
+    int opcode;      // OR of TB_BC_*
+    int arr_mask;    // tags whose datum is a per-facet-node array instead of a constant
+    int pad;
+    double elev, uvx, uvy, un, flux, value;
+    double bnd_len;
+};
+
+struct TbBcTable {
+    int n_slots;
+    int pad;
+    const int *bf_slot;          // [n_bfacets] slot of each exterior facet
+    const double *ext_elev;      // [n_bfacets*2]
+    const double *ext_uv;        // [n_bfacets*4]
+    const double *ext_un;        // [n_bfacets*2]
+    const double *ext_flux;      // [n_bfacets*2]
+    const double *ext_value;     // [n_bfacets*2]
+    TbBcSlot slots[TB_MAX_SLOTS];
+};
+
+// static per-patch block (one TMA bulk copy):
+//   double col[ncol][NV]   vertex columns: 0 = x, 1 = y, 2 = bathymetry, then optional fields
+//   uint16 cv[TB_P][3]     local vertex ids
+//   int32  cn[TB_P][3]     >= 0: (smem cell index)*4 + local facet in neighbour;  < 0: -(1 + exterior facet)
+struct TbPatchLayout {
+    const unsigned char *sblk;
+    long long stride;
+    int NV, NH, ncol;
+    int off_cv, off_cn;
+    const int *halo_ids;         // [n_patches*NH] cell ids of off-patch facet neighbours
+    const int *halo_cnt;         // [n_patches]
+};
+
+struct TbSweParams {
+    const double *u_in;
+    const double *u0;
+    double *u_out;
+    TbPatchLayout pl;
+    int n_owned;
+    int patch_first;
+    double a0, a1, bdt;
+    double g, rho0, lf_sigma, eps2, wd_alpha2;
+    int lf_on, wd_on, use_quad, nquad;
+    TbCoef cor, man, cd, lin, wind, pa, msrc, vsrc;
+    TbBcTable bc;
+};
+
+struct TbTracerParams {
+    const double *c_in;
+    const double *c0;
+    double *c_out;
+    const double *swe;           // frozen SWE state (cell records)
+    TbPatchLayout pl;
+    int n_owned;
+    int patch_first;
+    double a0, a1, bdt;
+    double corr, lf_sigma;
+    int lf_on, nonlin, wd_on, pad;
+    double wd_alpha2;
+    TbCoef src;
+    TbBcTable bc;
+};
+
+// kernel launchers (tb_kernels.cu)
+cudaError_t tb_launch_swe_stage(const TbSweParams &p, bool nonlinear, int n_patches, size_t smem, cudaStream_t s);
+cudaError_t tb_launch_tracer_stage(const TbTracerParams &p, int n_patches, size_t smem, cudaStream_t s);
+cudaError_t tb_set_quadrature(int n, const double *lam, const double *w);
+size_t tb_swe_smem_bytes(const TbPatchLayout &pl);
+size_t tb_tracer_smem_bytes(const TbPatchLayout &pl);
+cudaError_t tb_kernels_init();
+
+cudaError_t tb_launch_state_from_fields(const double *uv, const double *eta, const int32_t *node_map,
+                                        double *state, long long n_cells, cudaStream_t s);
+cudaError_t tb_launch_state_to_fields(const double *state, const int32_t *node_map, double *uv, double *eta,
+                                      long long n_cells, cudaStream_t s);
+cudaError_t tb_launch_tracer_from_field(const double *q, const int32_t *node_map, double *c, long long n_cells,
+                                        cudaStream_t s);
+cudaError_t tb_launch_tracer_to_field(const double *c, const int32_t *node_map, double *q, long long n_cells,
+                                      cudaStream_t s);
+cudaError_t tb_launch_gather_cells(const double *state, const int32_t *idx, long long n, int rec, double *buf,
+                                   cudaStream_t s);
+cudaError_t tb_launch_scatter_cells(const double *buf, const int32_t *idx, long long n, int rec, double *state,
+                                    cudaStream_t s);
+cudaError_t tb_launch_swe_integrals(const double *state, const double *area, long long n_owned, double *out,
+                                    cudaStream_t s);
+// limiter: vertex bounds via deterministic CSR gather, then per-cell clamp
+struct TbLimiterData {
+    long long n_owned, n_cells, n_tvert;
+    const long long *v2c_ptr;    // [n_tvert+1]
+    const int *v2c_idx;          // cells around each topological vertex
+    const long long *v2b_ptr;    // [n_tvert+1]
+    const int *v2b_idx;          // exterior facets touching each topological vertex: cell*4 + local facet
+    const int *cell_tv;          // [n_cells*3] topological vertex of each cell node
+    double *qmin, *qmax;         // [n_tvert]
+};
+cudaError_t tb_launch_limiter(const TbLimiterData &d, double *c, cudaStream_t s);

@@ -1,0 +1,680 @@
+// Hand-written sm_100a kernels for the explicit P1DG shallow-water path.
+//
+// One CTA = one patch of TB_P SFC-consecutive cells, one thread per cell.
+//   * the patch's cell records (9 doubles/cell), its previous-step records (u0)
+//     and its static block (vertex columns + local connectivity) arrive in
+//     shared memory by TMA bulk copies (cp.async.bulk + mbarrier);
+//   * records of the off-patch facet neighbours (the patch halo) are gathered
+//     by all threads while the bulk copies are in flight;
+//   * each thread evaluates the volume terms and the three facets of its cell
+//     (every interior facet is evaluated from both sides: no atomics, results
+//     bit-identical regardless of the partition), applies the closed-form
+//     P1 mass inverse and the Shu-Osher update, and the patch is written back
+//     with one TMA bulk store.
+//
+// Arithmetic follows thetis/shallowwater_eq.py (line refs at each term).
+#include "tb_internal.h"
+
+// ------------------------------------------------------------------ constants
+__constant__ double c_qlam[TB_MAX_QUAD][3];
+__constant__ double c_qw[TB_MAX_QUAD];
+
+// 2-point Gauss-Legendre on [0,1]
+#define TB_XI1 0.21132486540518711775
+#define TB_XI2 0.78867513459481288225
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// TMA 1-D bulk copy shared -> global
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------ small helpers
+// DepthExpression.get_total_depth for the nonlinear case (utility.py:975-996):
+// hl = bathymetry + eta at the evaluation point
+__device__ __forceinline__ double wd_depth(double hl, int wd_on, double alpha2) {
+    if (wd_on) return 0.5 * (hl + sqrt(hl * hl + alpha2));
+    return hl;
+}
+
+struct BcExt {
+    double eta, ux, uy;
+};
+
+// External state of an open boundary at one Gauss point
+// (ShallowWaterTerm.get_bnd_functions, shallowwater_eq.py:232-272).
+// e_in, ux_in, uy_in: interior traces; (nxs, nys) = normal*len; il = 1/len;
+// elev/uv/un/flux: boundary data already interpolated to the point.
+template <bool NONLIN>
+__device__ __forceinline__ BcExt bc_external(int op, double e_in, double ux_in, double uy_in, double bpt, double elev,
+                                             double uvx, double uvy, double un, double flux, double bnd_len, double nxs,
+                                             double nys, double il, int wd_on, double alpha2) {
+    BcExt r;
+    const double nx = nxs * il, ny = nys * il;
+    if ((op & TB_BC_ELEV) && (op & TB_BC_UV)) {
+        r.eta = elev; r.ux = uvx; r.uy = uvy;
+    } else if ((op & TB_BC_ELEV) && (op & TB_BC_UN)) {
+        r.eta = elev; r.ux = un * nx; r.uy = un * ny;
+    } else if ((op & TB_BC_ELEV) && (op & TB_BC_FLUX)) {
+        r.eta = elev;
+        const double h_ext = NONLIN ? wd_depth(bpt + elev, wd_on, alpha2) : bpt;
+        const double s = flux / (h_ext * bnd_len);
+        r.ux = s * nx; r.uy = s * ny;
+    } else if (op & TB_BC_ELEV) {
+        r.eta = elev; r.ux = ux_in; r.uy = uy_in;
+    } else if (op & TB_BC_UV) {
+        r.eta = e_in; r.ux = uvx; r.uy = uvy;
+    } else if (op & TB_BC_UN) {
+        r.eta = e_in; r.ux = un * nx; r.uy = un * ny;
+    } else {  // TB_BC_FLUX
+        r.eta = e_in;
+        const double h_ext = NONLIN ? wd_depth(bpt + e_in, wd_on, alpha2) : bpt;
+        const double s = flux / (h_ext * bnd_len);
+        r.ux = s * nx; r.uy = s * ny;
+    }
+    return r;
+}
+
+__device__ __forceinline__ double coef_at(const TbCoef &c, const double *cols, int NV, int v, int comp = 0) {
+    if (c.mode == 2) return cols[(size_t)(c.col + comp) * NV + v];
+    return comp == 0 ? c.v0 : c.v1;
+}
+
+// ------------------------------------------------------------------ SWE stage kernel
+template <bool NONLIN>
+__global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__ TbSweParams prm) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    double *S = reinterpret_cast<double *>(smem + 16);              // [(TB_P+NH)][9] stage state (own + halo)
+    double *O = S + (size_t)(TB_P + prm.pl.NH) * 9;                 // [TB_P][9] u0 in, result out
+    unsigned char *blk = reinterpret_cast<unsigned char *>(O + TB_P * 9);
+
+    const int tid = threadIdx.x;
+    const int patch = prm.patch_first + blockIdx.x;
+    const long long cell0 = (long long)patch * TB_P;
+    const int NV = prm.pl.NV;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t sb = (uint32_t)prm.pl.stride;
+        const uint32_t rec = TB_P * 9 * sizeof(double);
+        mbar_expect_tx(bar, rec + sb + (prm.u0 ? rec : 0u));
+        bulk_g2s(S, prm.u_in + cell0 * 9, rec, bar);
+        bulk_g2s(blk, prm.pl.sblk + (long long)patch * prm.pl.stride, sb, bar);
+        if (prm.u0) bulk_g2s(O, prm.u0 + cell0 * 9, rec, bar);
+    }
+    // patch halo: records of off-patch facet neighbours, gathered while the bulk copies fly
+    {
+        const int nh = __ldg(prm.pl.halo_cnt + patch);
+        const int *hid = prm.pl.halo_ids + (long long)patch * prm.pl.NH;
+        for (int i = tid; i < nh * 9; i += TB_P) {
+            const int h = i / 9, k = i - h * 9;
+            S[(TB_P + h) * 9 + k] = __ldg(prm.u_in + (long long)__ldg(hid + h) * 9 + k);
+        }
+    }
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    const bool active = (cell0 + tid) < prm.n_owned;
+    double res[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) res[k] = 0.0;
+
+    if (active) {
+        const double *cols = reinterpret_cast<const double *>(blk);
+        const uint16_t *cv = reinterpret_cast<const uint16_t *>(blk + prm.pl.off_cv) + tid * 3;
+        const int *cn = reinterpret_cast<const int *>(blk + prm.pl.off_cn) + tid * 3;
+        const double *my = S + tid * 9;
+        const double g = prm.g;
+        const int wd_on = prm.wd_on;
+        const double a2 = prm.wd_alpha2;
+
+        double ux[3], uy[3], et[3], x[3], y[3], b[3];
+        int v[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            ux[a] = my[2 * a];
+            uy[a] = my[2 * a + 1];
+            et[a] = my[6 + a];
+            v[a] = cv[a];
+            x[a] = cols[v[a]];
+            y[a] = cols[NV + v[a]];
+            b[a] = cols[2 * NV + v[a]];
+        }
+        // scaled outward normals N_i = |e_i| n_i of facet i (opposite vertex i); A*grad(phi_i) = -N_i/2
+        double Nx[3], Ny[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int p = (i + 1) % 3, q = (i + 2) % 3;
+            Nx[i] = y[q] - y[p];
+            Ny[i] = x[p] - x[q];
+        }
+        const double twoA = (x[1] - x[0]) * (y[2] - y[0]) - (y[1] - y[0]) * (x[2] - x[0]);
+
+        double Rux[3] = {0, 0, 0}, Ruy[3] = {0, 0, 0}, Re[3] = {0, 0, 0};
+
+        // ---------------- volume terms (closed-form P1 integrals) ----------------
+        const double sux = ux[0] + ux[1] + ux[2], suy = uy[0] + uy[1] + uy[2];
+        const double se = et[0] + et[1] + et[2];
+        {
+            // ExternalPressureGradientTerm cell part (shallowwater_eq.py:361): +g*eta*div(psi)
+            const double c = -g * se * (1.0 / 6.0);   // g * (se/3) * (-N/2)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                Rux[a] += c * Nx[a];
+                Ruy[a] += c * Ny[a];
+            }
+        }
+        if (!(NONLIN && wd_on)) {
+            // HUDivTerm cell part (:422): +grad(phi).(H u);  int H u = A/12 sum_b H_b (u_b + su)
+            double Wx = 0, Wy = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double H = NONLIN ? (b[a] + et[a]) : b[a];
+                Wx += H * (ux[a] + sux);
+                Wy += H * (uy[a] + suy);
+            }
+            Wx *= (-1.0 / 24.0);
+            Wy *= (-1.0 / 24.0);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) Re[a] += Nx[a] * Wx + Ny[a] * Wy;
+        }
+        if (NONLIN) {
+            // HorizontalAdvectionTerm cell part (:478): +div(outer(psi,u)).u
+            double Gu[3];   // (A grad phi_b).u_b  (own node)
+            double D = 0;
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb) {
+                Gu[bb] = -0.5 * (Nx[bb] * ux[bb] + Ny[bb] * uy[bb]);
+                D += Gu[bb];
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                double sx = D * (ux[a] + sux), sy = D * (uy[a] + suy);
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb) {
+                    const double gab = -0.5 * (Nx[a] * ux[bb] + Ny[a] * uy[bb]);   // (A grad phi_a).u_b
+                    sx += gab * (ux[bb] + sux);
+                    sy += gab * (uy[bb] + suy);
+                }
+                Rux[a] += sx * (1.0 / 12.0);
+                Ruy[a] += sy * (1.0 / 12.0);
+            }
+        }
+        const double A = 0.5 * twoA;
+        if (prm.cor.mode) {
+            // CoriolisTerm (:632-633): R_x += int f u_y phi, R_y -= int f u_x phi
+            double f[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) f[a] = coef_at(prm.cor, cols, NV, v[a]);
+            const double F = f[0] + f[1] + f[2];
+            const double fux_ = f[0] * ux[0] + f[1] * ux[1] + f[2] * ux[2];
+            const double fuy_ = f[0] * uy[0] + f[1] * uy[1] + f[2] * uy[2];
+            const double c = A * (1.0 / 60.0);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double ix = F * sux + f[a] * sux + fux_ + F * ux[a] + 2.0 * f[a] * ux[a];
+                const double iy = F * suy + f[a] * suy + fuy_ + F * uy[a] + 2.0 * f[a] * uy[a];
+                Rux[a] += c * iy;
+                Ruy[a] -= c * ix;
+            }
+        }
+        if (prm.lin.mode) {
+            // LinearDragTerm (:734-740): -C u
+            double f[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) f[a] = coef_at(prm.lin, cols, NV, v[a]);
+            const double F = f[0] + f[1] + f[2];
+            const double fux_ = f[0] * ux[0] + f[1] * ux[1] + f[2] * ux[2];
+            const double fuy_ = f[0] * uy[0] + f[1] * uy[1] + f[2] * uy[2];
+            const double c = A * (1.0 / 60.0);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                Rux[a] -= c * (F * sux + f[a] * sux + fux_ + F * ux[a] + 2.0 * f[a] * ux[a]);
+                Ruy[a] -= c * (F * suy + f[a] * suy + fuy_ + F * uy[a] + 2.0 * f[a] * uy[a]);
+            }
+        }
+        if (prm.pa.mode == 2) {
+            // AtmosphericPressureTerm (:658-663): -grad(p_a)/rho0;  A*grad p = -1/2 sum_a p_a N_a
+            double gx = 0, gy = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double pa = coef_at(prm.pa, cols, NV, v[a]);
+                gx += pa * Nx[a];
+                gy += pa * Ny[a];
+            }
+            const double c = (1.0 / 6.0) / prm.rho0;   // -( -1/2 ) * (1/3)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                Rux[a] += c * gx;
+                Ruy[a] += c * gy;
+            }
+        }
+        if (prm.msrc.mode) {
+            // MomentumSourceTerm (:805-811)
+            double fx[3], fy[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                fx[a] = coef_at(prm.msrc, cols, NV, v[a], 0);
+                fy[a] = coef_at(prm.msrc, cols, NV, v[a], 1);
+            }
+            const double sx = fx[0] + fx[1] + fx[2], sy = fy[0] + fy[1] + fy[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                Rux[a] += A * (1.0 / 12.0) * (fx[a] + sx);
+                Ruy[a] += A * (1.0 / 12.0) * (fy[a] + sy);
+            }
+        }
+        if (prm.vsrc.mode) {
+            // ContinuitySourceTerm (:824-831)
+            double f[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) f[a] = coef_at(prm.vsrc, cols, NV, v[a]);
+            const double s = f[0] + f[1] + f[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) Re[a] += A * (1.0 / 12.0) * (f[a] + s);
+        }
+        if (prm.use_quad) {
+            // non-polynomial cell integrands by the degree-3 cell rule:
+            // QuadraticDragTerm (:679-701), WindStressTerm (:643-649), wetting-drying HUDiv volume term
+            double mu[3] = {0, 0, 0}, cdn[3] = {0, 0, 0}, wx[3] = {0, 0, 0}, wy[3] = {0, 0, 0};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (prm.man.mode) mu[a] = coef_at(prm.man, cols, NV, v[a]);
+                if (prm.cd.mode) cdn[a] = coef_at(prm.cd, cols, NV, v[a]);
+                if (prm.wind.mode) {
+                    wx[a] = coef_at(prm.wind, cols, NV, v[a], 0);
+                    wy[a] = coef_at(prm.wind, cols, NV, v[a], 1);
+                }
+            }
+            const double irho = 1.0 / prm.rho0;
+            for (int qd = 0; qd < prm.nquad; ++qd) {
+                const double l0 = c_qlam[qd][0], l1 = c_qlam[qd][1], l2 = c_qlam[qd][2];
+                const double w = c_qw[qd] * A;
+                const double uq = l0 * ux[0] + l1 * ux[1] + l2 * ux[2];
+                const double vq = l0 * uy[0] + l1 * uy[1] + l2 * uy[2];
+                const double bq = l0 * b[0] + l1 * b[1] + l2 * b[2];
+                double Hq = bq;
+                if (NONLIN) Hq = wd_depth(bq + l0 * et[0] + l1 * et[1] + l2 * et[2], wd_on, a2);
+                double sx = 0, sy = 0;   // momentum source density at the point
+                if (prm.man.mode || prm.cd.mode) {
+                    double cdq;
+                    if (prm.man.mode) {
+                        const double m = l0 * mu[0] + l1 * mu[1] + l2 * mu[2];
+                        cdq = g * m * m * rcbrt(Hq);              // g mu^2 / H^(1/3)
+                    } else {
+                        cdq = l0 * cdn[0] + l1 * cdn[1] + l2 * cdn[2];
+                    }
+                    const double k = cdq * sqrt(uq * uq + vq * vq + prm.eps2) / Hq;
+                    sx -= k * uq;
+                    sy -= k * vq;
+                }
+                if (prm.wind.mode) {
+                    const double k = irho / Hq;
+                    sx += k * (l0 * wx[0] + l1 * wx[1] + l2 * wx[2]);
+                    sy += k * (l0 * wy[0] + l1 * wy[1] + l2 * wy[2]);
+                }
+                sx *= w;
+                sy *= w;
+                Rux[0] += l0 * sx; Rux[1] += l1 * sx; Rux[2] += l2 * sx;
+                Ruy[0] += l0 * sy; Ruy[1] += l1 * sy; Ruy[2] += l2 * sy;
+                if (NONLIN && wd_on) {
+                    // grad(phi_a).(H u) * w*A  with A grad(phi_a) = -N_a/2
+                    const double hx = -0.5 * c_qw[qd] * Hq * uq, hy = -0.5 * c_qw[qd] * Hq * vq;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) Re[a] += Nx[a] * hx + Ny[a] * hy;
+                }
+            }
+        }
+
+        // ---------------- facet terms, 2-point Gauss per facet ----------------
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int p = (i + 1) % 3, q = (i + 2) % 3;
+            const double nxs = Nx[i], nys = Ny[i];
+            const double len2 = nxs * nxs + nys * nys;
+            const double il = rsqrt(len2);
+            const double len = len2 * il;
+            const int code = cn[i];
+            // flux accumulators tested against phi_p and phi_q
+            double Fpx = 0, Fpy = 0, Fpe = 0, Fqx = 0, Fqy = 0, Fqe = 0;
+            if (code >= 0) {
+                const int lf = code & 3;
+                const double *nr = S + (code >> 2) * 9;
+                const int np_ = (lf + 2) % 3, nq_ = (lf + 1) % 3;   // neighbour nodes matching p and q
+                const double uNxp = nr[2 * np_], uNyp = nr[2 * np_ + 1], eNp = nr[6 + np_];
+                const double uNxq = nr[2 * nq_], uNyq = nr[2 * nq_ + 1], eNq = nr[6 + nq_];
+#pragma unroll
+                for (int gp = 0; gp < 2; ++gp) {
+                    const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
+                    const double uKx = wp_ * ux[p] + wq_ * ux[q], uKy = wp_ * uy[p] + wq_ * uy[q];
+                    const double eK = wp_ * et[p] + wq_ * et[q];
+                    const double uNx = wp_ * uNxp + wq_ * uNxq, uNy = wp_ * uNyp + wq_ * uNyq;
+                    const double eN = wp_ * eNp + wq_ * eNq;
+                    const double bg = wp_ * b[p] + wq_ * b[q];
+                    double hbar;
+                    if (NONLIN) hbar = 0.5 * (wd_depth(bg + eK, wd_on, a2) + wd_depth(bg + eN, wd_on, a2));
+                    else hbar = bg;
+                    const double c = sqrt(g * hbar);
+                    const double dux = uKx - uNx, duy = uKy - uNy;
+                    const double dun = dux * nxs + duy * nys;
+                    // PG (:363-366): g*(avg(eta) + sqrt(h/g)*jump(u,n)) n
+                    const double t = 0.5 * g * (eK + eN) + c * dun * il;
+                    double fx = t * nxs, fy = t * nys;
+                    // HUDiv (:424-427): h*(avg(u) + sqrt(g/h)*jump(eta,n)).n
+                    const double usx = uKx + uNx, usy = uKy + uNy;
+                    const double usN = usx * nxs + usy * nys;
+                    const double fe = 0.5 * hbar * usN + c * (eK - eN) * len;
+                    if (NONLIN) {
+                        // advection (:480-488): avg(u) (u_K.n) + gamma (u_K - u_N)
+                        const double uKN = uKx * nxs + uKy * nys;
+                        fx += 0.5 * usx * uKN;
+                        fy += 0.5 * usy * uKN;
+                        if (prm.lf_on) {
+                            const double gam = 0.25 * fabs(usN) * prm.lf_sigma;
+                            fx += gam * dux;
+                            fy += gam * duy;
+                        }
+                    }
+                    Fpx += wp_ * fx; Fpy += wp_ * fy; Fpe += wp_ * fe;
+                    Fqx += wq_ * fx; Fqy += wq_ * fy; Fqe += wq_ * fe;
+                }
+            } else {
+                const int gb = -(code + 1);
+                const int slot = __ldg(prm.bc.bf_slot + gb);
+                const TbBcSlot &bs = prm.bc.slots[slot];
+                const int op = bs.opcode;
+#pragma unroll
+                for (int gp = 0; gp < 2; ++gp) {
+                    const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
+                    const double uKx = wp_ * ux[p] + wq_ * ux[q], uKy = wp_ * uy[p] + wq_ * uy[q];
+                    const double eK = wp_ * et[p] + wq_ * et[q];
+                    const double bg = wp_ * b[p] + wq_ * b[q];
+                    const double HK = NONLIN ? wd_depth(bg + eK, wd_on, a2) : bg;
+                    const double uKN = uKx * nxs + uKy * nys;
+                    double fx, fy, fe = 0.0;
+                    if ((op & (TB_BC_ELEV | TB_BC_UV | TB_BC_UN | TB_BC_FLUX)) == 0) {
+                        // land boundary (:376-381), mirror-velocity Lax-Friedrichs (:489-497)
+                        const double c = sqrt(g * HK);
+                        double t = g * eK + c * uKN * il;
+                        if (NONLIN && prm.lf_on) t += prm.lf_sigma * fabs(uKN) * uKN * il * il;
+                        fx = t * nxs;
+                        fy = t * nys;
+                    } else {
+                        double elev = bs.elev, uvx = bs.uvx, uvy = bs.uvy, un = bs.un, flux = bs.flux;
+                        if (bs.arr_mask & TB_BC_ELEV)
+                            elev = wp_ * __ldg(prm.bc.ext_elev + 2 * gb) + wq_ * __ldg(prm.bc.ext_elev + 2 * gb + 1);
+                        if (bs.arr_mask & TB_BC_UV) {
+                            uvx = wp_ * __ldg(prm.bc.ext_uv + 4 * gb) + wq_ * __ldg(prm.bc.ext_uv + 4 * gb + 2);
+                            uvy = wp_ * __ldg(prm.bc.ext_uv + 4 * gb + 1) + wq_ * __ldg(prm.bc.ext_uv + 4 * gb + 3);
+                        }
+                        if (bs.arr_mask & TB_BC_UN)
+                            un = wp_ * __ldg(prm.bc.ext_un + 2 * gb) + wq_ * __ldg(prm.bc.ext_un + 2 * gb + 1);
+                        if (bs.arr_mask & TB_BC_FLUX)
+                            flux = wp_ * __ldg(prm.bc.ext_flux + 2 * gb) + wq_ * __ldg(prm.bc.ext_flux + 2 * gb + 1);
+                        const BcExt ex = bc_external<NONLIN>(op, eK, uKx, uKy, bg, elev, uvx, uvy, un, flux, bs.bnd_len,
+                                                             nxs, nys, il, wd_on, a2);
+                        // PG (:370-375)
+                        const double dun = (uKx - ex.ux) * nxs + (uKy - ex.uy) * nys;   // un_jump*len
+                        const double cK = sqrt(g * HK);
+                        const double t = 0.5 * g * (eK + ex.eta) + cK * dun * il;
+                        fx = t * nxs;
+                        fy = t * nys;
+                        // HUDiv (:431-442)
+                        const double Hext = NONLIN ? wd_depth(bg + ex.eta, wd_on, a2) : bg;
+                        const double hav = 0.5 * (HK + Hext);
+                        const double cav = sqrt(g * hav);
+                        const double usx = uKx + ex.ux, usy = uKy + ex.uy;
+                        const double usN = usx * nxs + usy * nys;
+                        const double ejump = eK - ex.eta;
+                        const double un_rie_len = 0.5 * usN + (cav / hav) * ejump * len;
+                        const double eta_rie = 0.5 * (eK + ex.eta) + (cav / g) * dun * il;
+                        const double h_rie = NONLIN ? wd_depth(bg + eta_rie, wd_on, a2) : bg;
+                        fe = h_rie * un_rie_len;
+                        if (NONLIN) {
+                            // advection (:498-509)
+                            const double un_a_len = 0.5 * usN + (cK / HK) * ejump * len;
+                            fx += 0.5 * usx * un_a_len;
+                            fy += 0.5 * usy * un_a_len;
+                        }
+                    }
+                    Fpx += wp_ * fx; Fpy += wp_ * fy; Fpe += wp_ * fe;
+                    Fqx += wq_ * fx; Fqy += wq_ * fy; Fqe += wq_ * fe;
+                }
+            }
+            Rux[p] -= 0.5 * Fpx; Ruy[p] -= 0.5 * Fpy; Re[p] -= 0.5 * Fpe;
+            Rux[q] -= 0.5 * Fqx; Ruy[q] -= 0.5 * Fqy; Re[q] -= 0.5 * Fqe;
+        }
+
+        // ---------------- P1 mass inverse (equation.py:99-105) and Shu-Osher update ----------------
+        // M_K^-1 = (3/A)(4 I - 1 1^T)
+        const double mi = 6.0 / twoA * prm.bdt;
+        const double sRx = Rux[0] + Rux[1] + Rux[2], sRy = Ruy[0] + Ruy[1] + Ruy[2], sRe = Re[0] + Re[1] + Re[2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            res[2 * a] = prm.a1 * ux[a] + mi * (4.0 * Rux[a] - sRx);
+            res[2 * a + 1] = prm.a1 * uy[a] + mi * (4.0 * Ruy[a] - sRy);
+            res[6 + a] = prm.a1 * et[a] + mi * (4.0 * Re[a] - sRe);
+        }
+        if (prm.u0) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) res[k] += prm.a0 * O[tid * 9 + k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) O[tid * 9 + k] = res[k];
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        bulk_s2g(prm.u_out + cell0 * 9, O, TB_P * 9 * sizeof(double));
+        bulk_commit_wait_read();
+    }
+}
+
+size_t tb_swe_smem_bytes(const TbPatchLayout &pl) {
+    return 16 + (size_t)(TB_P + pl.NH) * 72 + (size_t)TB_P * 72 + (size_t)pl.stride;
+}
+
+cudaError_t tb_kernels_init() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(swe_stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(swe_stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return e;
+}
+
+cudaError_t tb_launch_swe_stage(const TbSweParams &p, bool nonlinear, int n_patches, size_t smem, cudaStream_t s) {
+    if (n_patches <= 0) return cudaSuccess;
+    if (nonlinear)
+        swe_stage_kernel<true><<<n_patches, TB_P, smem, s>>>(p);
+    else
+        swe_stage_kernel<false><<<n_patches, TB_P, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t tb_set_quadrature(int n, const double *lam, const double *w) {
+    cudaError_t e = cudaMemcpyToSymbol(c_qlam, lam, sizeof(double) * 3 * n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_qw, w, sizeof(double) * n);
+}
+
+// ------------------------------------------------------------------ layout conversion
+__global__ void state_from_fields_kernel(const double *__restrict__ uv, const double *__restrict__ eta,
+                                         const int32_t *__restrict__ node_map, double *__restrict__ state,
+                                         long long n_cells) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (cell, node)
+    if (i >= n_cells * 3) return;
+    const long long c = i / 3;
+    const int a = (int)(i - c * 3);
+    const long long nd = node_map[i];
+    state[c * 9 + 2 * a] = uv[2 * nd];
+    state[c * 9 + 2 * a + 1] = uv[2 * nd + 1];
+    state[c * 9 + 6 + a] = eta[nd];
+}
+__global__ void state_to_fields_kernel(const double *__restrict__ state, const int32_t *__restrict__ node_map,
+                                       double *__restrict__ uv, double *__restrict__ eta, long long n_cells) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells * 3) return;
+    const long long c = i / 3;
+    const int a = (int)(i - c * 3);
+    const long long nd = node_map[i];
+    uv[2 * nd] = state[c * 9 + 2 * a];
+    uv[2 * nd + 1] = state[c * 9 + 2 * a + 1];
+    eta[nd] = state[c * 9 + 6 + a];
+}
+__global__ void tracer_from_field_kernel(const double *__restrict__ q, const int32_t *__restrict__ node_map,
+                                         double *__restrict__ c, long long n3) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) c[i] = q[node_map[i]];
+}
+__global__ void tracer_to_field_kernel(const double *__restrict__ c, const int32_t *__restrict__ node_map,
+                                       double *__restrict__ q, long long n3) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) q[node_map[i]] = c[i];
+}
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+cudaError_t tb_launch_state_from_fields(const double *uv, const double *eta, const int32_t *node_map, double *state,
+                                        long long n_cells, cudaStream_t s) {
+    if (n_cells) state_from_fields_kernel<<<nblk(n_cells * 3, 256), 256, 0, s>>>(uv, eta, node_map, state, n_cells);
+    return cudaGetLastError();
+}
+cudaError_t tb_launch_state_to_fields(const double *state, const int32_t *node_map, double *uv, double *eta,
+                                      long long n_cells, cudaStream_t s) {
+    if (n_cells) state_to_fields_kernel<<<nblk(n_cells * 3, 256), 256, 0, s>>>(state, node_map, uv, eta, n_cells);
+    return cudaGetLastError();
+}
+cudaError_t tb_launch_tracer_from_field(const double *q, const int32_t *node_map, double *c, long long n_cells,
+                                        cudaStream_t s) {
+    if (n_cells) tracer_from_field_kernel<<<nblk(n_cells * 3, 256), 256, 0, s>>>(q, node_map, c, n_cells * 3);
+    return cudaGetLastError();
+}
+cudaError_t tb_launch_tracer_to_field(const double *c, const int32_t *node_map, double *q, long long n_cells,
+                                      cudaStream_t s) {
+    if (n_cells) tracer_to_field_kernel<<<nblk(n_cells * 3, 256), 256, 0, s>>>(c, node_map, q, n_cells * 3);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ halo pack / unpack
+__global__ void gather_cells_kernel(const double *__restrict__ state, const int32_t *__restrict__ idx, long long n,
+                                    int rec, double *__restrict__ buf) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * rec) return;
+    const long long h = i / rec;
+    const int k = (int)(i - h * rec);
+    buf[i] = state[(long long)idx[h] * rec + k];
+}
+__global__ void scatter_cells_kernel(const double *__restrict__ buf, const int32_t *__restrict__ idx, long long n,
+                                     int rec, double *__restrict__ state) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * rec) return;
+    const long long h = i / rec;
+    const int k = (int)(i - h * rec);
+    state[(long long)idx[h] * rec + k] = buf[i];
+}
+cudaError_t tb_launch_gather_cells(const double *state, const int32_t *idx, long long n, int rec, double *buf,
+                                   cudaStream_t s) {
+    if (n) gather_cells_kernel<<<nblk(n * rec, 256), 256, 0, s>>>(state, idx, n, rec, buf);
+    return cudaGetLastError();
+}
+cudaError_t tb_launch_scatter_cells(const double *buf, const int32_t *idx, long long n, int rec, double *state,
+                                    cudaStream_t s) {
+    if (n) scatter_cells_kernel<<<nblk(n * rec, 256), 256, 0, s>>>(buf, idx, n, rec, state);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ diagnostics
+// out[0] = int eta^2, out[1] = int |u|^2, out[2] = int eta  (deterministic two-pass reduction)
+__global__ void swe_integrals_partial(const double *__restrict__ state, const double *__restrict__ area,
+                                      long long n_owned, double *__restrict__ partial) {
+    __shared__ double sh[3][8];
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_owned;
+         c += (long long)gridDim.x * blockDim.x) {
+        const double *r = state + c * 9;
+        const double A = area[c];
+        // int f g = A/12 (sum_a f_a g_a + (sum f)(sum g))
+        const double se = r[6] + r[7] + r[8];
+        const double sx = r[0] + r[2] + r[4], sy = r[1] + r[3] + r[5];
+        a0 += A * (1.0 / 12.0) * (r[6] * r[6] + r[7] * r[7] + r[8] * r[8] + se * se);
+        a1 += A * (1.0 / 12.0) *
+              (r[0] * r[0] + r[2] * r[2] + r[4] * r[4] + sx * sx + r[1] * r[1] + r[3] * r[3] + r[5] * r[5] + sy * sy);
+        a2 += A * (1.0 / 3.0) * se;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_down_sync(0xffffffffu, a0, o);
+        a1 += __shfl_down_sync(0xffffffffu, a1, o);
+        a2 += __shfl_down_sync(0xffffffffu, a2, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = a0; sh[1][w] = a1; sh[2][w] = a2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += sh[threadIdx.x][k];
+        partial[blockIdx.x * 3 + threadIdx.x] = s;
+    }
+}
+__global__ void swe_integrals_final(const double *__restrict__ partial, int nb, double *__restrict__ out) {
+    if (threadIdx.x < 3) {
+        double s = 0;
+        for (int k = 0; k < nb; ++k) s += partial[k * 3 + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+}
+static double *g_partial = nullptr;
+cudaError_t tb_launch_swe_integrals(const double *state, const double *area, long long n_owned, double *out,
+                                    cudaStream_t s) {
+    const int nb = 296;
+    if (!g_partial) {
+        cudaError_t e = cudaMalloc(&g_partial, sizeof(double) * 3 * nb);
+        if (e != cudaSuccess) return e;
+    }
+    swe_integrals_partial<<<nb, 256, 0, s>>>(state, area, n_owned, g_partial);
+    swe_integrals_final<<<1, 32, 0, s>>>(g_partial, nb, out);
+    return cudaGetLastError();
+}

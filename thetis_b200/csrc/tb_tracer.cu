@@ -1,0 +1,313 @@
+// Explicit 2-D tracer advection stage (tracer_eq_2d.py:147-193, 293-298) and
+// VertexBasedP1DGLimiter (limiter.py:48-198) as sm_100a kernels.
+// Same patch / TMA staging scheme as the SWE stage kernel (tb_kernels.cu).
+#include "tb_internal.h"
+
+#define TB_XI1 0.21132486540518711775
+#define TB_XI2 0.78867513459481288225
+#define TB_BC_PRESENT 32   // marker has a (possibly empty) dict in bnd_conditions
+
+__device__ __forceinline__ uint32_t t_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void t_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void t_mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(t_smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void t_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     t_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(t_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void t_bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(t_smem_u32(src)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constant__ TbTracerParams prm) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    double *S = reinterpret_cast<double *>(smem + 16);            // SWE records [(TB_P+NH)][9]
+    double *C = S + (size_t)(TB_P + prm.pl.NH) * 9;               // tracer [(TB_P+NH)][3]
+    double *O = C + (size_t)(TB_P + prm.pl.NH) * 3;               // [TB_P][3]  (+pad to 16 B)
+    unsigned char *blk = reinterpret_cast<unsigned char *>(O + TB_P * 3);
+
+    const int tid = threadIdx.x;
+    const int patch = prm.patch_first + blockIdx.x;
+    const long long cell0 = (long long)patch * TB_P;
+    const int NV = prm.pl.NV;
+
+    if (tid == 0) t_mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t sb = (uint32_t)prm.pl.stride;
+        const uint32_t rec9 = TB_P * 9 * sizeof(double), rec3 = TB_P * 3 * sizeof(double);
+        t_mbar_expect_tx(bar, rec9 + rec3 + sb + (prm.c0 ? rec3 : 0u));
+        t_bulk_g2s(S, prm.swe + cell0 * 9, rec9, bar);
+        t_bulk_g2s(C, prm.c_in + cell0 * 3, rec3, bar);
+        t_bulk_g2s(blk, prm.pl.sblk + (long long)patch * prm.pl.stride, sb, bar);
+        if (prm.c0) t_bulk_g2s(O, prm.c0 + cell0 * 3, rec3, bar);
+    }
+    {
+        const int nh = __ldg(prm.pl.halo_cnt + patch);
+        const int *hid = prm.pl.halo_ids + (long long)patch * prm.pl.NH;
+        for (int i = tid; i < nh * 12; i += TB_P) {
+            const int h = i / 12, k = i - h * 12;
+            const long long gc = __ldg(hid + h);
+            if (k < 9) S[(TB_P + h) * 9 + k] = __ldg(prm.swe + gc * 9 + k);
+            else C[(TB_P + h) * 3 + (k - 9)] = __ldg(prm.c_in + gc * 3 + (k - 9));
+        }
+    }
+    t_mbar_wait(bar, 0);
+    __syncthreads();
+
+    const bool active = (cell0 + tid) < prm.n_owned;
+    double res[3] = {0, 0, 0};
+    if (active) {
+        const double *cols = reinterpret_cast<const double *>(blk);
+        const uint16_t *cv = reinterpret_cast<const uint16_t *>(blk + prm.pl.off_cv) + tid * 3;
+        const int *cn = reinterpret_cast<const int *>(blk + prm.pl.off_cn) + tid * 3;
+        const double *my = S + tid * 9;
+        const double corr = prm.corr;
+        double ux[3], uy[3], et[3], c[3], x[3], y[3], b[3];
+        int v[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            ux[a] = corr * my[2 * a];
+            uy[a] = corr * my[2 * a + 1];
+            et[a] = my[6 + a];
+            c[a] = C[tid * 3 + a];
+            v[a] = cv[a];
+            x[a] = cols[v[a]];
+            y[a] = cols[NV + v[a]];
+            b[a] = cols[2 * NV + v[a]];
+        }
+        double Nx[3], Ny[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int p = (i + 1) % 3, q = (i + 2) % 3;
+            Nx[i] = y[q] - y[p];
+            Ny[i] = x[p] - x[q];
+        }
+        const double twoA = (x[1] - x[0]) * (y[2] - y[0]) - (y[1] - y[0]) * (x[2] - x[0]);
+        double R[3] = {0, 0, 0};
+        const double sc = c[0] + c[1] + c[2];
+        {
+            // cell part (:159-160): + c div(u phi_a)
+            double D = 0;
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb) D += -0.5 * (Nx[bb] * ux[bb] + Ny[bb] * uy[bb]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                double s = D * (c[a] + sc);
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) s += -0.5 * (Nx[a] * ux[cc] + Ny[a] * uy[cc]) * (c[cc] + sc);
+                R[a] += s * (1.0 / 12.0);
+            }
+        }
+        if (prm.src.mode) {
+            // SourceTerm (:293-298)
+            double f[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                f[a] = prm.src.mode == 2 ? cols[(size_t)prm.src.col * NV + v[a]] : prm.src.v0;
+            const double s = f[0] + f[1] + f[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) R[a] += 0.5 * twoA * (1.0 / 12.0) * (f[a] + s);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int p = (i + 1) % 3, q = (i + 2) % 3;
+            const double nxs = Nx[i], nys = Ny[i];
+            const int code = cn[i];
+            double Fp = 0, Fq = 0;
+            if (code >= 0) {
+                const int lf = code & 3;
+                const int ni = code >> 2;
+                const double *nr = S + ni * 9;
+                const double *nc = C + ni * 3;
+                const int np_ = (lf + 2) % 3, nq_ = (lf + 1) % 3;
+                const double uNxp = corr * nr[2 * np_], uNyp = corr * nr[2 * np_ + 1], cNp = nc[np_];
+                const double uNxq = corr * nr[2 * nq_], uNyq = corr * nr[2 * nq_ + 1], cNq = nc[nq_];
+#pragma unroll
+                for (int gp = 0; gp < 2; ++gp) {
+                    const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
+                    const double uKx = wp_ * ux[p] + wq_ * ux[q], uKy = wp_ * uy[p] + wq_ * uy[q];
+                    const double uNx = wp_ * uNxp + wq_ * uNxq, uNy = wp_ * uNyp + wq_ * uNyq;
+                    const double cK = wp_ * c[p] + wq_ * c[q], cN = wp_ * cNp + wq_ * cNq;
+                    const double unav = 0.5 * ((uKx + uNx) * nxs + (uKy + uNy) * nys);   // avg(u).n * len (own outward n)
+                    // upwind value (:164-168); sign(0) = 0 gives the mean
+                    const double cup = unav > 0.0 ? cK : (unav < 0.0 ? cN : 0.5 * (cK + cN));
+                    double f = cup * (uKx * nxs + uKy * nys);                              // own velocity trace (:170-171)
+                    if (prm.lf_on) f += 0.5 * fabs(unav) * prm.lf_sigma * (cK - cN);     // (:173-175)
+                    Fp += wp_ * f;
+                    Fq += wq_ * f;
+                }
+            } else {
+                const int gb = -(code + 1);
+                const int slot = __ldg(prm.bc.bf_slot + gb);
+                const TbBcSlot &bs = prm.bc.slots[slot];
+                const int op = bs.opcode;
+                const double len2 = nxs * nxs + nys * nys;
+                const double il = rsqrt(len2);
+#pragma unroll
+                for (int gp = 0; gp < 2; ++gp) {
+                    const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
+                    const double uKx = wp_ * ux[p] + wq_ * ux[q], uKy = wp_ * uy[p] + wq_ * uy[q];
+                    const double cK = wp_ * c[p] + wq_ * c[q];
+                    double f;
+                    if (!(op & TB_BC_PRESENT)) {
+                        f = cK * (uKx * nxs + uKy * nys);                                 // closed (:189-191)
+                    } else {
+                        // TracerTerm.get_bnd_functions (:78-115)
+                        double cext = cK, uex = uKx, uey = uKy;
+                        if (op & TB_BC_VALUE) {
+                            cext = bs.value;
+                            if (bs.arr_mask & TB_BC_VALUE)
+                                cext = wp_ * __ldg(prm.bc.ext_value + 2 * gb) + wq_ * __ldg(prm.bc.ext_value + 2 * gb + 1);
+                        }
+                        if (op & TB_BC_UV) {
+                            double uvx = bs.uvx, uvy = bs.uvy;
+                            if (bs.arr_mask & TB_BC_UV) {
+                                uvx = wp_ * __ldg(prm.bc.ext_uv + 4 * gb) + wq_ * __ldg(prm.bc.ext_uv + 4 * gb + 2);
+                                uvy = wp_ * __ldg(prm.bc.ext_uv + 4 * gb + 1) + wq_ * __ldg(prm.bc.ext_uv + 4 * gb + 3);
+                            }
+                            uex = corr * uvx;
+                            uey = corr * uvy;
+                        } else if (op & TB_BC_FLUX) {
+                            double flux = bs.flux;
+                            if (bs.arr_mask & TB_BC_FLUX)
+                                flux = wp_ * __ldg(prm.bc.ext_flux + 2 * gb) + wq_ * __ldg(prm.bc.ext_flux + 2 * gb + 1);
+                            double eext = wp_ * et[p] + wq_ * et[q];
+                            if (op & TB_BC_ELEV) {
+                                eext = bs.elev;
+                                if (bs.arr_mask & TB_BC_ELEV)
+                                    eext = wp_ * __ldg(prm.bc.ext_elev + 2 * gb) + wq_ * __ldg(prm.bc.ext_elev + 2 * gb + 1);
+                            }
+                            const double bg = wp_ * b[p] + wq_ * b[q];
+                            double hext = bg;
+                            if (prm.nonlin) {
+                                hext = bg + eext;
+                                if (prm.wd_on) hext = 0.5 * (hext + sqrt(hext * hext + prm.wd_alpha2));
+                            }
+                            const double s = corr * flux / (hext * bs.bnd_len);
+                            uex = s * nxs * il;
+                            uey = s * nys * il;
+                        } else if (op & TB_BC_UN) {
+                            double un = bs.un;
+                            if (bs.arr_mask & TB_BC_UN)
+                                un = wp_ * __ldg(prm.bc.ext_un + 2 * gb) + wq_ * __ldg(prm.bc.ext_un + 2 * gb + 1);
+                            uex = un * nxs * il;
+                            uey = un * nys * il;
+                        }
+                        const double unav = 0.5 * ((uKx + uex) * nxs + (uKy + uey) * nys);
+                        const double cup = unav > 0.0 ? cK : (unav < 0.0 ? cext : 0.5 * (cK + cext));
+                        f = cup * unav;                                                    // (:181-188)
+                    }
+                    Fp += wp_ * f;
+                    Fq += wq_ * f;
+                }
+            }
+            R[p] -= 0.5 * Fp;
+            R[q] -= 0.5 * Fq;
+        }
+        const double mi = 6.0 / twoA * prm.bdt;
+        const double sR = R[0] + R[1] + R[2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) res[a] = prm.a1 * c[a] + mi * (4.0 * R[a] - sR);
+        if (prm.c0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) res[a] += prm.a0 * O[tid * 3 + a];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) O[tid * 3 + a] = res[a];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) t_bulk_s2g(prm.c_out + cell0 * 3, O, TB_P * 3 * sizeof(double));
+}
+
+size_t tb_tracer_smem_bytes(const TbPatchLayout &pl) {
+    return 16 + (size_t)(TB_P + pl.NH) * 96 + (size_t)TB_P * 24 + (size_t)pl.stride;
+}
+
+cudaError_t tb_launch_tracer_stage(const TbTracerParams &p, int n_patches, size_t smem, cudaStream_t s) {
+    static bool init = false;
+    if (!init) {
+        cudaError_t e =
+            cudaFuncSetAttribute(tracer_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        init = true;
+    }
+    if (n_patches <= 0) return cudaSuccess;
+    tracer_stage_kernel<<<n_patches, TB_P, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ limiter
+// (i) vertex bounds: max/min over the centroids of the cells around each vertex plus the means of the
+// exterior facets touching it; deterministic gather over CSR lists (no atomics).
+__global__ void limiter_bounds_kernel(TbLimiterData d, const double *__restrict__ c) {
+    long long vtx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vtx >= d.n_tvert) return;
+    double qmax = -1.0e10, qmin = 1.0e10;   // firedrake VertexBasedLimiter.compute_bounds initial values
+    for (long long k = d.v2c_ptr[vtx]; k < d.v2c_ptr[vtx + 1]; ++k) {
+        const double *r = c + (long long)d.v2c_idx[k] * 3;
+        // P0 projection of a P1 field = mean of nodal values (limiter.py:90-97)
+        const double qb = (r[0] + r[1] + r[2]) / 3.0;
+        qmax = fmax(qmax, qb);
+        qmin = fmin(qmin, qb);
+    }
+    for (long long k = d.v2b_ptr[vtx]; k < d.v2b_ptr[vtx + 1]; ++k) {
+        const int code = d.v2b_idx[k];
+        const double *r = c + (long long)(code >> 2) * 3;
+        const int lf = code & 3;
+        const double fm = (r[(lf + 1) % 3] + r[(lf + 2) % 3]) / 2;   // limiter.py:123-137
+        qmax = fmax(qmax, fm);
+        qmin = fmin(qmin, fm);
+    }
+    d.qmax[vtx] = qmax;
+    d.qmin[vtx] = qmin;
+}
+// (ii) per-cell clamp (firedrake VertexBasedLimiter._limit_kernel)
+__global__ void limiter_apply_kernel(TbLimiterData d, double *__restrict__ c) {
+    long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= d.n_owned) return;
+    double q[3] = {c[cell * 3], c[cell * 3 + 1], c[cell * 3 + 2]};
+    const double qavg = (q[0] + q[1] + q[2]) / 3.0;
+    double alpha = 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int tv = d.cell_tv[cell * 3 + i];
+        if (q[i] > qavg)
+            alpha = fmin(alpha, fmin(1.0, (d.qmax[tv] - qavg) / (q[i] - qavg)));
+        else if (q[i] < qavg)
+            alpha = fmin(alpha, fmin(1.0, (qavg - d.qmin[tv]) / (qavg - q[i])));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) c[cell * 3 + i] = qavg + alpha * (q[i] - qavg);
+}
+cudaError_t tb_launch_limiter(const TbLimiterData &d, double *c, cudaStream_t s) {
+    if (d.n_tvert) limiter_bounds_kernel<<<(unsigned)((d.n_tvert + 255) / 256), 256, 0, s>>>(d, c);
+    if (d.n_owned) limiter_apply_kernel<<<(unsigned)((d.n_owned + 255) / 256), 256, 0, s>>>(d, c);
+    return cudaGetLastError();
+}
