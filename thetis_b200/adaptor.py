@@ -1,0 +1,213 @@
+"""
+Adaptor between Firedrake-shaped objects (real Firedrake or thetis_b200.shim)
+and the arrays the CUDA library consumes.  Read once at set-up; never on the
+hot path.
+
+Everything here relies only on attribute names that the reference itself uses
+on Firedrake objects (SURVEY.md 8b lists the evidence for each one):
+`Function.dat.data(_ro)`, `Function.function_space()`,
+`FunctionSpace.cell_node_map().values`, `FunctionSpace.ufl_element().family()/
+.degree()`, `mesh.coordinates`, `mesh.exterior_facets.unique_markers`,
+`Constant.values()`, `float(Constant)`.
+
+The Firedrake branch of `extract_mesh` cannot be exercised in this environment
+(Firedrake is not installed); the shim branch is what the tests
+run.  Both produce the same `Mesh2D`.
+"""
+from __future__ import annotations
+
+import weakref
+
+import numpy as np
+
+from .mesh import Mesh2D, FACET_NODES, sfc_renumber
+
+__all__ = ["MeshAdaptor", "is_constant", "is_function", "constant_value", "get_adaptor"]
+
+
+def is_function(x):
+    return hasattr(x, "function_space") and hasattr(x, "dat") or hasattr(x, "subfunctions") and hasattr(x, "function_space")
+
+
+def is_constant(x):
+    if isinstance(x, (int, float, np.integer, np.floating)):
+        return True
+    if isinstance(x, (tuple, list)) and all(isinstance(v, (int, float, np.integer, np.floating)) for v in x):
+        return True
+    if isinstance(x, np.ndarray) and x.ndim <= 1 and x.size <= 3:
+        return True
+    return hasattr(x, "values") and callable(x.values) and not hasattr(x, "dat")
+
+
+def constant_value(x):
+    """Current value of a Constant-like object as a 1-D float array (read live, like the UFL forms do)."""
+    if hasattr(x, "values") and callable(x.values):
+        return np.atleast_1d(np.asarray(x.values(), dtype=np.float64))
+    return np.atleast_1d(np.asarray(x, dtype=np.float64))
+
+
+def _family(fs):
+    el = fs.ufl_element()
+    fam = el.family()
+    # firedrake VectorElement wraps a scalar element
+    sub = getattr(el, "sub_elements", None)
+    if fam in ("Discontinuous Lagrange", "DG", "DP", "DQ"):
+        return "DG"
+    if fam in ("Lagrange", "CG", "P", "Q"):
+        return "CG"
+    if sub:
+        return _family_of_name(sub[0].family())
+    return fam
+
+
+def _family_of_name(fam):
+    if fam in ("Discontinuous Lagrange", "DG", "DP"):
+        return "DG"
+    if fam in ("Lagrange", "CG", "P"):
+        return "CG"
+    return fam
+
+
+def _mesh2d_from_firedrake(mesh):
+    """
+    Build a `Mesh2D` from a real Firedrake mesh.  UNTESTED HERE (no Firedrake);
+    written against the attribute names listed in SURVEY.md 8b.
+    """
+    import firedrake as fd  # noqa: F401  (ImportError if absent, by design)
+    coords_f = mesh.coordinates
+    cfs = coords_f.function_space()
+    ncell = mesh.cell_set.size                                 # owned cells
+    cmap = np.asarray(cfs.cell_node_map().values[:ncell], dtype=np.int64)
+    xy = np.asarray(coords_f.dat.data_ro_with_halos, dtype=np.float64)
+    used = np.unique(cmap)
+    remap = np.full(xy.shape[0], -1, dtype=np.int64)
+    remap[used] = np.arange(used.shape[0])
+    coords = xy[used][:, :2]
+    cells = remap[cmap].astype(np.int32)
+    p1 = fd.FunctionSpace(mesh, "CG", 1)
+    tmap = np.asarray(p1.cell_node_map().values[:ncell], dtype=np.int64)
+    topo = np.zeros(coords.shape[0], dtype=np.int64)
+    topo[cells.reshape(-1)] = tmap.reshape(-1)
+    _, topo = np.unique(topo, return_inverse=True)
+    m = Mesh2D(coords=coords, cells=cells, topo=topo.astype(np.int32),
+               periodic=_family(cfs) == "DG")
+    a = m.cell_area()
+    swap = a < 0
+    m.make_ccw()
+    # exterior facet markers by topological edge
+    ef = mesh.exterior_facets
+    fcell = np.asarray(ef.facet_cell).reshape(-1)
+    flocal = np.asarray(ef.local_facet_dat.data_ro).reshape(-1)
+    markers = np.asarray(ef.markers).reshape(-1)
+    em = {}
+    for c, lf, mk in zip(fcell, flocal, markers):
+        if c >= ncell:
+            continue
+        a_, b_ = tmap[c, FACET_NODES[lf, 0]], tmap[c, FACET_NODES[lf, 1]]
+        ta, tb = int(topo[remap[cmap[c, FACET_NODES[lf, 0]]]]), int(topo[remap[cmap[c, FACET_NODES[lf, 1]]]])
+        em[(min(ta, tb), max(ta, tb))] = int(mk)
+        del a_, b_
+    m.build_connectivity(edge_markers=em)
+    m.cell_perm = np.arange(m.n_cells, dtype=np.int64)
+    return m, swap
+
+
+class MeshAdaptor:
+    """
+    One per mesh object: the SFC-renumbered `Mesh2D` the device uses plus the
+    maps back to the caller's numbering.
+    """
+
+    def __init__(self, mesh_obj, renumber=True):
+        tm = getattr(mesh_obj, "topology_mesh", None)
+        if isinstance(mesh_obj, Mesh2D):
+            base, swap = mesh_obj, np.zeros(mesh_obj.n_cells, dtype=bool)
+        elif isinstance(tm, Mesh2D):
+            base, swap = tm, np.zeros(tm.n_cells, dtype=bool)
+        else:
+            base, swap = _mesh2d_from_firedrake(mesh_obj)
+        self.mesh_obj_ref = weakref.ref(mesh_obj) if not isinstance(mesh_obj, Mesh2D) else (lambda: mesh_obj)
+        self.base = base
+        self.swap = swap
+        if renumber and not base.meta.get("sfc"):
+            self.mesh = sfc_renumber(base)
+            self.perm = np.argsort(np.argsort(self.mesh.cell_perm))  # placeholder, fixed below
+            # cell_perm composes with earlier renumberings of `base`; we need new -> base order
+            base_perm = base.cell_perm if base.cell_perm is not None else np.arange(base.n_cells)
+            inv = np.empty(base.n_cells, dtype=np.int64)
+            inv[base_perm] = np.arange(base.n_cells)
+            self.perm = inv[self.mesh.cell_perm]
+        else:
+            self.mesh = base
+            self.perm = np.arange(base.n_cells, dtype=np.int64)
+        self.engine = None
+        bl = getattr(mesh_obj, "boundary_len", None)
+        self.boundary_len = dict(bl) if bl is not None else self.mesh.boundary_length()
+
+    # ------------------------------------------------------------ node maps
+    def _cell_nodes(self, fs):
+        cm = np.asarray(fs.cell_node_map().values)[: self.base.n_cells].astype(np.int64)
+        if cm.shape[1] != 3:
+            raise NotImplementedError("only P1 / P1DG spaces are supported on the accelerated path")
+        if self.swap.any():
+            cm = cm.copy()
+            cm[self.swap, 1], cm[self.swap, 2] = cm[self.swap, 2].copy(), cm[self.swap, 1].copy()
+        return cm[self.perm]
+
+    def dg_node_map(self, fs):
+        """(nt, 3) int32: dof of device cell c / CCW local node a in a P1DG space."""
+        if _family(fs) != "DG" or fs.ufl_element().degree() != 1:
+            raise NotImplementedError("solution must live in a P1DG space (element_family 'dg-dg', degree 1)")
+        return np.ascontiguousarray(self._cell_nodes(fs), dtype=np.int32)
+
+    def nodal_values(self, func):
+        """(nt, 3[,k]) values of a P1/P1DG Function at the device cells' nodes."""
+        fs = func.function_space()
+        data = np.asarray(func.dat.data_ro)
+        return data[self._cell_nodes(fs)]
+
+    def vertex_values(self, func):
+        """
+        Values of a P1 (CG, or continuous DG) Function at the device mesh's
+        geometric vertices.  Discontinuous coefficients are outside the
+        accelerated path.
+        """
+        nodal = self.nodal_values(func)
+        vert = np.zeros((self.mesh.n_vertices,) + nodal.shape[2:])
+        vert[self.mesh.cells] = nodal
+        err = np.abs(vert[self.mesh.cells] - nodal).max() if nodal.size else 0.0
+        scale = max(np.abs(nodal).max() if nodal.size else 0.0, 1e-300)
+        if err > 1e-10 * scale:
+            raise NotImplementedError("discontinuous coefficient fields are not supported on the accelerated path")
+        return vert
+
+    def bfacet_values(self, func):
+        """(nb, 2[,k]) values of a P1/P1DG Function at the two nodes of every exterior facet."""
+        fs = func.function_space()
+        cache = self.__dict__.setdefault("_bf_nodes", {})
+        idx = cache.get(id(fs))
+        if idx is None:
+            cn = self._cell_nodes(fs)
+            m = self.mesh
+            idx = np.stack([cn[m.bf_cell, FACET_NODES[m.bf_lf, 0]], cn[m.bf_cell, FACET_NODES[m.bf_lf, 1]]], axis=1)
+            cache[id(fs)] = idx
+            self.__dict__.setdefault("_bf_keep", []).append(fs)     # keep the key object alive
+        return np.asarray(func.dat.data_ro)[idx]
+
+
+_ADAPTORS = weakref.WeakKeyDictionary()
+_ADAPTORS_STRONG = {}
+
+
+def get_adaptor(mesh_obj, renumber=True):
+    try:
+        ad = _ADAPTORS.get(mesh_obj)
+        if ad is None:
+            ad = MeshAdaptor(mesh_obj, renumber=renumber)
+            _ADAPTORS[mesh_obj] = ad
+        return ad
+    except TypeError:      # unhashable / not weak-referenceable
+        key = id(mesh_obj)
+        if key not in _ADAPTORS_STRONG:
+            _ADAPTORS_STRONG[key] = MeshAdaptor(mesh_obj, renumber=renumber)
+        return _ADAPTORS_STRONG[key]

@@ -49,8 +49,12 @@ struct tb_ctx {
     double *d_ext_tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_area = nullptr;
     std::vector<double> h_stage;        // pinned staging? (plain host vector; copies are small)
-    double *h_pinned = nullptr;
-    size_t h_pinned_bytes = 0;
+    // ring of pinned staging buffers for boundary data uploads (no stream stall in steady state)
+    static const int NSTAGE = 8;
+    double *h_pinned[NSTAGE] = {nullptr};
+    size_t h_pinned_bytes[NSTAGE] = {0};
+    cudaEvent_t h_event[NSTAGE] = {nullptr};
+    int h_next = 0;
     // layout
     TbPatchLayout pl{};
     bool layout_dirty = true;
@@ -380,7 +384,10 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_cell_tv);
     cudaFree(ctx->d_qmin);
     cudaFree(ctx->d_qmax);
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int k = 0; k < tb_ctx::NSTAGE; ++k) {
+        if (ctx->h_pinned[k]) cudaFreeHost(ctx->h_pinned[k]);
+        if (ctx->h_event[k]) cudaEventDestroy(ctx->h_event[k]);
+    }
     delete ctx;
     return TB_OK;
 }
@@ -506,15 +513,18 @@ extern "C" int tb_set_bc_array(tb_ctx *ctx, int eq, int marker, int tag, const d
         CK(cudaMemset(slot_arr[k], 0, sizeof(double) * std::max<size_t>(n, 2)));
     }
     // stage only this marker's entries through pinned memory so several markers can hold arrays
-    if (ctx->h_pinned_bytes < n * sizeof(double)) {
-        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-        ctx->h_pinned = nullptr;
-        CK(cudaMallocHost(&ctx->h_pinned, n * sizeof(double)));
-        ctx->h_pinned_bytes = n * sizeof(double);
+    const int slot = ctx->h_next;
+    ctx->h_next = (ctx->h_next + 1) % tb_ctx::NSTAGE;
+    if (!ctx->h_event[slot]) CK(cudaEventCreateWithFlags(&ctx->h_event[slot], cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(ctx->h_event[slot]));      // copy issued NSTAGE calls ago has finished
+    if (ctx->h_pinned_bytes[slot] < n * sizeof(double)) {
+        if (ctx->h_pinned[slot]) cudaFreeHost(ctx->h_pinned[slot]);
+        ctx->h_pinned[slot] = nullptr;
+        CK(cudaMallocHost(&ctx->h_pinned[slot], n * sizeof(double)));
+        ctx->h_pinned_bytes[slot] = n * sizeof(double);
     }
+    double *hp = ctx->h_pinned[slot];
     cudaStream_t st = (cudaStream_t)stream;
-    // the pinned buffer may still be in flight from the previous call on this stream
-    CK(cudaStreamSynchronize(st));
     const size_t w = 2 * (size_t)nc;
     // copy contiguous runs of facets belonging to this marker
     long long k0 = -1;
@@ -522,12 +532,13 @@ extern "C" int tb_set_bc_array(tb_ctx *ctx, int eq, int marker, int tag, const d
         const bool mine = f < ctx->n_bfacets && ctx->bf_slot[f] == s;
         if (mine && k0 < 0) k0 = f;
         if (!mine && k0 >= 0) {
-            memcpy(ctx->h_pinned + k0 * w, values + k0 * w, sizeof(double) * w * (f - k0));
-            CK(cudaMemcpyAsync(slot_arr[k] + k0 * w, ctx->h_pinned + k0 * w, sizeof(double) * w * (f - k0),
+            memcpy(hp + k0 * w, values + k0 * w, sizeof(double) * w * (f - k0));
+            CK(cudaMemcpyAsync(slot_arr[k] + k0 * w, hp + k0 * w, sizeof(double) * w * (f - k0),
                                cudaMemcpyHostToDevice, st));
             k0 = -1;
         }
     }
+    CK(cudaEventRecord(ctx->h_event[slot], st));
     ctx->bc[eq][s].arr_mask |= tag;
     return TB_OK;
 }

@@ -29,7 +29,7 @@ from dataclasses import dataclass, field
 __all__ = [
     "Mesh2D", "rectangle_mesh", "unit_square_mesh", "periodic_rectangle_mesh",
     "read_gmsh", "refine_uniform", "delaunay_mesh", "hilbert_index",
-    "sfc_renumber", "FACET_NODES",
+    "sfc_renumber", "FACET_NODES", "load_npz_mesh",
 ]
 
 # local facet i = edge opposite local vertex i; its two nodes in CCW order
@@ -558,8 +558,12 @@ def sfc_renumber(mesh, perm=None):
     vinv[vorder] = np.arange(vorder.shape[0])
     new = Mesh2D(coords=mesh.coords[vorder], cells=vinv[cells].astype(np.int32),
                  topo=None, periodic=mesh.periodic)
-    _, t = np.unique(mesh.topo[vorder], return_inverse=True)
-    new.topo = t.astype(np.int32)
+    # topological ids renumbered by first occurrence: identity for non-periodic meshes
+    told = mesh.topo[vorder]
+    _, first_t, t = np.unique(told, return_index=True, return_inverse=True)
+    rank = np.empty(first_t.shape[0], dtype=np.int64)
+    rank[np.argsort(first_t, kind="stable")] = np.arange(first_t.shape[0])
+    new.topo = rank[t].astype(np.int32)
     nbr = mesh.nbr[perm].astype(np.int64)
     pos = nbr >= 0
     nbr[pos] = inv[nbr[pos]]
@@ -574,3 +578,16 @@ def sfc_renumber(mesh, perm=None):
     new.meta["sfc"] = True
     new.meta["vertex_perm"] = vorder
     return new
+
+
+def load_npz_mesh(path):
+    """Mesh stored as arrays (coords, cells, bnd_edges, bnd_tags); see tests/golden/make_north_sea_fixture.py."""
+    d = np.load(path)
+    m = Mesh2D(coords=d["coords"].astype(np.float64), cells=d["cells"].astype(np.int32),
+               topo=np.arange(d["coords"].shape[0], dtype=np.int32))
+    m.make_ccw()
+    em = {(int(min(a, b)), int(max(a, b))): int(t) for (a, b), t in zip(d["bnd_edges"], d["bnd_tags"])}
+    m.build_connectivity(edge_markers=em)
+    m.cell_perm = np.arange(m.n_cells, dtype=np.int64)
+    m.meta.update(kind="npz", path=str(path))
+    return m

@@ -1,0 +1,354 @@
+"""
+Domain decomposition for the explicit P1DG path.
+
+The reference distributes the mesh inside Firedrake/PETSc (DMPlex overlap 1, PyOP2
+halo exchanges in every assemble).  Here: the SFC-ordered cell range is cut into
+`world` contiguous chunks, each rank owns one chunk plus a one-deep halo of ghost
+cells (facet neighbours owned by other ranks, appended after the owned cells and
+grouped by owner).  Once per RK stage every rank packs the records of the owned
+cells its peers need (tb_gather_cells) and one all-to-all over NCCL/NVLink drops
+them straight into the peers' ghost regions (the ghost block of a peer is
+contiguous, so the receive side needs no unpack).
+
+Cells are evaluated from their own side only, so the result of an owned cell does
+not depend on who owns its neighbours: an N-GPU run is bit-identical to the 1-GPU run.
+
+Also holds the two bench drivers (`SingleSWE`, `PartitionedSWE`) that bench.py,
+the GPU tests and __graft_entry__.smoke() share.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .mesh import Mesh2D, FACET_NODES
+
+__all__ = ["LocalPart", "partition_mesh", "SingleSWE", "PartitionedSWE", "exchange_halo"]
+
+INT32_MIN = np.iinfo(np.int32).min
+
+
+class LocalPart:
+    """One rank's share of a partitioned mesh (numpy only)."""
+
+    def __init__(self, rank, world, mesh, owned_global, ghost_global, ghost_owner, send_lists):
+        self.rank, self.world = rank, world
+        self.owned_global = owned_global            # (n_owned,) global cell ids, ascending
+        self.ghost_global = ghost_global            # (n_ghost,) grouped by owner rank, ascending inside a group
+        self.ghost_owner = ghost_owner              # (n_ghost,)
+        self.send_lists = send_lists                # {peer: local owned cell ids the peer needs, in the peer's ghost order}
+        self.n_owned = owned_global.shape[0]
+        self.n_ghost = ghost_global.shape[0]
+        self.recv_counts = np.array([(ghost_owner == p).sum() for p in range(world)], dtype=np.int64)
+        self.send_counts = np.array([send_lists[p].shape[0] if p in send_lists else 0 for p in range(world)], dtype=np.int64)
+        self.mesh = mesh                            # local Mesh2D: owned cells first, then ghosts
+
+
+def partition_mesh(mesh: Mesh2D, world: int):
+    """
+    Cut the (SFC-ordered) mesh into `world` contiguous chunks with a one-deep facet halo.
+    Deterministic: every rank computes the same partition from the same global mesh.
+    Returns a list of `LocalPart`.
+    """
+    nt = mesh.n_cells
+    bounds = np.linspace(0, nt, world + 1).astype(np.int64)
+    # align chunk boundaries to the patch size so that patches never straddle ranks
+    owner = np.zeros(nt, dtype=np.int32)
+    for r in range(world):
+        owner[bounds[r]:bounds[r + 1]] = r
+    parts = []
+    ghosts_of = []
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        nb = mesh.nbr[lo:hi]
+        ext = nb[(nb >= 0) & ((nb < lo) | (nb >= hi))]
+        g = np.unique(ext)
+        go = owner[g]
+        order = np.lexsort((g, go))
+        ghosts_of.append((g[order].astype(np.int64), go[order].astype(np.int32)))
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        owned = np.arange(lo, hi, dtype=np.int64)
+        gg, go = ghosts_of[r]
+        # what I must send to peer p = peer p's ghosts that I own, in p's ghost order
+        send = {}
+        for p in range(world):
+            if p == r:
+                continue
+            pg, po = ghosts_of[p]
+            mine = pg[po == r]
+            if mine.size:
+                send[p] = (mine - lo).astype(np.int64)
+        # local mesh
+        glob = np.concatenate([owned, gg])
+        g2l = {}
+        loc_of = np.full(nt, -1, dtype=np.int64)
+        loc_of[glob] = np.arange(glob.shape[0])
+        cells_g = mesh.cells[glob]
+        vused, vinv = np.unique(cells_g.reshape(-1), return_inverse=True)
+        cells_l = vinv.reshape(-1, 3).astype(np.int32)
+        coords_l = mesh.coords[vused]
+        topo_l = mesh.topo[vused]
+        _, topo_l = np.unique(topo_l, return_inverse=True)
+        nbr_g = mesh.nbr[glob].astype(np.int64)
+        nbr_l = np.full(nbr_g.shape, INT32_MIN, dtype=np.int64)
+        n_own = owned.shape[0]
+        own_rows = np.arange(glob.shape[0]) < n_own
+        pos = (nbr_g >= 0) & own_rows[:, None]
+        nbr_l[pos] = loc_of[nbr_g[pos]]
+        assert np.all(nbr_l[pos] >= 0)
+        # exterior facets of owned cells, renumbered locally
+        bsel = (nbr_g < 0) & own_rows[:, None]
+        gb = -(nbr_g[bsel] + 1)
+        ub, binv = np.unique(gb, return_inverse=True)
+        nbr_l[bsel] = -(1 + binv)
+        m = Mesh2D(coords=coords_l, cells=cells_l, topo=topo_l.astype(np.int32), periodic=mesh.periodic)
+        m.nbr = nbr_l.astype(np.int32)
+        m.nbr_lf = mesh.nbr_lf[glob].copy()
+        m.bf_cell = loc_of[mesh.bf_cell[ub]].astype(np.int32)
+        m.bf_lf = mesh.bf_lf[ub].copy()
+        m.bf_marker = mesh.bf_marker[ub].copy()
+        m.meta = dict(mesh.meta)
+        m.meta.update(global_bfacets=ub, global_vertices=vused, global_boundary_len=mesh.boundary_length())
+        del g2l
+        parts.append(LocalPart(r, world, m, owned, gg, go, send))
+    return parts
+
+
+def exchange_halo(part: LocalPart, sendbuf, recv_view, group=None):
+    """
+    One halo exchange with torch.distributed: sendbuf = packed records grouped by peer,
+    recv_view = the ghost block (grouped by owner).  Works with NCCL (GPU) and gloo (CPU).
+    """
+    import torch.distributed as dist
+    rec = sendbuf.shape[-1] if sendbuf.dim() > 1 else 1
+    ins = [int(c) * rec for c in part.send_counts]
+    outs = [int(c) * rec for c in part.recv_counts]
+    try:
+        dist.all_to_all_single(recv_view.view(-1), sendbuf.view(-1), output_split_sizes=outs, input_split_sizes=ins,
+                               group=group)
+    except (RuntimeError, NotImplementedError):
+        # backends without all-to-all (older gloo): pairwise non-blocking send/recv
+        reqs = []
+        so = np.concatenate([[0], np.cumsum(ins)])
+        ro = np.concatenate([[0], np.cumsum(outs)])
+        sflat, rflat = sendbuf.view(-1), recv_view.view(-1)
+        for p in range(part.world):
+            if p == part.rank:
+                continue
+            if outs[p]:
+                reqs.append(dist.irecv(rflat[ro[p]:ro[p + 1]], src=p, group=group))
+            if ins[p]:
+                reqs.append(dist.isend(sflat[so[p]:so[p + 1]].contiguous(), dst=p, group=group))
+        for q in reqs:
+            q.wait()
+
+
+# ---------------------------------------------------------------------- bench drivers
+def _make_solver(mesh, setup, wd, n_owned=None):
+    """FlowSolver2d mirror configured for the North Sea workload (thetis_b200/workloads.py)."""
+    from . import solver2d
+    from .shim import Function, FunctionSpace, Constant, as_shim_mesh
+    sm = as_shim_mesh(mesh)
+    P1 = FunctionSpace(sm, "CG", 1)
+    bath = Function(P1, name="Bathymetry")
+    bath.dat.data[:] = setup["bath"]
+    s = solver2d.FlowSolver2d(sm, bath)
+    o = s.options
+    o.swe_timestepper_type = "SSPRK33"
+    o.swe_timestepper_options.use_automatic_timestep = False
+    o.timestep = setup["dt"]
+    o.simulation_end_time = 1e30
+    o.simulation_export_time = 1e30
+    o.use_wetting_and_drying = bool(wd)
+    o.wetting_and_drying_alpha = Constant(setup["wd_alpha"])
+    man = Function(P1, name="Manning coefficient")
+    man.dat.data[:] = setup["manning"]
+    cor = Function(P1, name="Coriolis forcing")
+    cor.dat.data[:] = setup["coriolis"]
+    o.manning_drag_coefficient = man
+    o.coriolis_frequency = cor
+    o.horizontal_velocity_scale = Constant(1.5)
+    tide = Function(P1, name="Tidal elevation")
+    s.bnd_functions["shallow_water"] = {100: {"elev": tide, "uv": Constant((0.0, 0.0))}}
+    return s, tide
+
+
+class SingleSWE:
+    """North Sea workload on one GPU through the reference-shaped surface."""
+
+    def __init__(self, mesh, setup, wd=True):
+        import torch
+        from .workloads import M2_PERIOD
+        self.torch = torch
+        self.mesh, self.setup = mesh, setup
+        self.solver, self.tide = _make_solver(mesh, setup, wd)
+        s = self.solver
+        s.create_function_spaces()
+        s.create_equations()
+        uv0 = setup["uv0"]
+        eta0 = setup["eta0"]
+        s.initialize()
+        s.fields.uv_2d.dat.data[:] = uv0.reshape(-1, 2)
+        s.fields.elev_2d.dat.data[:] = eta0.reshape(-1)
+        s.timestepper.initialize(s.fields.solution_2d)
+        self.ts = s.timestepper
+        self.eng = self.ts.engine
+        self.t = 0.0
+        self.dt = setup["dt"]
+        # open-boundary vertices of the P1 tide Function and their phase (host-side forcing, like TPXO in the demo)
+        m = mesh
+        open_f = m.bf_marker == 100
+        nodes = m.cells[m.bf_cell[open_f][:, None], FACET_NODES[m.bf_lf[open_f]]]      # geometric vertices (nb_open, 2)
+        self._tide_nodes = m.topo[nodes].reshape(-1)
+        self._tide_phase = setup["tide_phase"][open_f].reshape(-1)
+        self._omega = 2 * np.pi / M2_PERIOD
+        self._n_open = int(open_f.sum())
+        self._norms = torch.zeros(4, dtype=torch.float64, device=self.eng.device)
+        self._norms_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+        self.update_forcings(0.0)
+        self.ts._push_dynamic()
+
+    def update_forcings(self, t):
+        """user callback of iterate(update_forcings=...): set the tidal elevation Function at time t"""
+        self.tide.dat.data[self._tide_nodes] = np.sin(self._omega * t + self._tide_phase)
+
+    def n_owned(self):
+        return self.mesh.n_cells
+
+    def launches(self):
+        return self.eng.launch_count()
+
+    def stage_launches_per_step(self):
+        return 3
+
+    def step_resident(self):
+        self.ts.advance_device()
+
+    def step_e2e(self):
+        self.ts.advance(self.t, self.update_forcings)
+        self.t += self.dt
+        self.eng.swe_integrals(self.ts.device_state(), self._norms)
+        self._norms_host.copy_(self._norms, non_blocking=True)
+
+    def h2d_bytes_per_step(self):
+        return 3 * self._n_open * 2 * 8
+
+    def d2h_bytes_per_step(self):
+        return 4 * 8
+
+    def state_nodal(self):
+        self.ts._host_stale = True
+        self.ts.sync_to_host()
+        s = self.solver
+        return (s.fields.uv_2d.dat.data_ro.reshape(-1, 3, 2).copy(), s.fields.elev_2d.dat.data_ro.reshape(-1, 3).copy())
+
+
+class PartitionedSWE:
+    """North Sea workload on `world` GPUs: one process per GPU, one halo exchange per RK stage over NCCL."""
+
+    def __init__(self, mesh, setup, rank, world, wd=True):
+        import torch
+        from . import _lib as L
+        from .engine import Engine
+        from .workloads import M2_PERIOD
+        self.torch = torch
+        self.rank, self.world = rank, world
+        self.part = partition_mesh(mesh, world)[rank]
+        p = self.part
+        lm = p.mesh
+        self.eng = eng = Engine(lm, n_owned=p.n_owned)
+        gv = lm.meta["global_vertices"]
+        eng.set_option(L.OPT_NONLINEAR, 1)
+        eng.set_option(L.OPT_LAX_FRIEDRICHS, 1)
+        eng.set_option(L.OPT_WETTING_DRYING, bool(wd))
+        eng.set_option(L.OPT_WD_ALPHA, setup["wd_alpha"])
+        eng.set_field(L.F_BATHYMETRY, setup["bath"][gv])
+        eng.set_field(L.F_MANNING, setup["manning"][gv])
+        eng.set_field(L.F_CORIOLIS, setup["coriolis"][gv])
+        for mk, ln in lm.meta["global_boundary_len"].items():
+            eng.set_boundary_length(mk, ln)
+        eng.set_bc(0, 100, L.BC_ELEV | L.BC_UV, [0, 0, 0, 0, 0, 0])
+        gb = lm.meta["global_bfacets"]
+        self._phase = setup["tide_phase"][gb]
+        self._has_open = bool((lm.bf_marker == 100).any())
+        self._omega = 2 * np.pi / M2_PERIOD
+        self._n_open = int((lm.bf_marker == 100).sum())
+        if self._has_open:
+            eng.set_bc_array(0, 100, L.BC_ELEV, np.sin(self._phase))
+        glob = np.concatenate([p.owned_global, p.ghost_global])
+        uv = setup["uv0"][glob]
+        eta = setup["eta0"][glob]
+        # state: owned (padded) + ghosts
+        A = eng.new_state()
+        dev = eng.device
+        own = eng.upload_nodal(uv[:p.n_owned], eta[:p.n_owned])
+        A.copy_(own)
+        if p.n_ghost:
+            grec = np.concatenate([uv[p.n_owned:].reshape(-1, 6), eta[p.n_owned:]], axis=1)
+            A[eng.n_owned_pad * 9:] = torch.as_tensor(grec.reshape(-1)).to(dev)
+        self.buf = [A, eng.new_state(), eng.new_state()]
+        send_idx = np.concatenate([p.send_lists[q] for q in range(world) if q in p.send_lists]) if p.send_lists else np.zeros(0, np.int64)
+        self.send_idx = torch.as_tensor(send_idx.astype(np.int32)).to(dev)
+        self.sendbuf = torch.zeros((max(int(send_idx.shape[0]), 1), 9), dtype=torch.float64, device=dev)
+        self.n_send = int(send_idx.shape[0])
+        self.dt = setup["dt"]
+        self.t = 0.0
+        self._norms = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._norms_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+        self._L = L
+
+    def _exchange(self, state):
+        eng, p = self.eng, self.part
+        if self.n_send:
+            eng.gather_cells(state, self.send_idx, 9, self.sendbuf)
+        ghost = state[eng.n_owned_pad * 9:].view(-1, 9)
+        exchange_halo(p, self.sendbuf[:self.n_send], ghost)
+
+    def _stage(self, a0, a1, bdt, src, u0, dst):
+        self.eng.swe_stage(a0, a1, bdt, src, u0, dst)
+        self._exchange(dst)
+
+    def _step(self, forcing=None):
+        A, B, C = self.buf
+        dt = self.dt
+        c = (0.0, 1.0, 0.5)
+        if forcing:
+            forcing(self.t + c[0] * dt)
+        self._stage(0.0, 1.0, dt, A, None, B)
+        if forcing:
+            forcing(self.t + c[1] * dt)
+        self._stage(0.75, 0.25, 0.25 * dt, B, A, C)
+        if forcing:
+            forcing(self.t + c[2] * dt)
+        self._stage(1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0 * dt, C, A, A)
+
+    def update_forcings(self, t):
+        if self._has_open:
+            self.eng.set_bc_array(0, 100, self._L.BC_ELEV, np.sin(self._omega * t + self._phase))
+
+    def n_owned(self):
+        return self.part.n_owned
+
+    def launches(self):
+        return self.eng.launch_count()
+
+    def stage_launches_per_step(self):
+        return 3
+
+    def step_resident(self):
+        self._step()
+
+    def step_e2e(self):
+        self._step(self.update_forcings)
+        self.t += self.dt
+        self.eng.swe_integrals(self.buf[0], self._norms)
+        self._norms_host.copy_(self._norms, non_blocking=True)
+
+    def h2d_bytes_per_step(self):
+        return 3 * self._n_open * 2 * 8
+
+    def d2h_bytes_per_step(self):
+        return 4 * 8
+
+    def owned_nodal(self):
+        return self.eng.download_nodal(self.buf[0])

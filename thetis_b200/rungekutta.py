@@ -1,0 +1,474 @@
+"""
+B200 drop-in for `thetis.rungekutta.SSPRK33` (= ERKGenericShuOsher + SSPRK33Abstract,
+/root/reference thetis/rungekutta.py:326-347, 870-956) behind the reference's own
+time-integrator interface (`thetis.timeintegrator.TimeIntegrator`,
+thetis/timeintegrator.py:13-73):
+
+    cls(equation, solution, fields, dt, options, bnd_conditions, terms_to_add='all')
+    .initialize(solution)  .advance(t, update_forcings=None)  .set_dt(dt)
+    .solve_stage(i, t, update_forcings=None)  .n_stages  .cfl_coeff  .name
+
+The per-stage residual assembly, the P1DG mass solve and the Shu-Osher update
+(rungekutta.py:929-946) are ONE CUDA kernel launch (tb_swe_stage /
+tb_tracer_stage); Firedrake/PETSc are not touched on the hot path.  State lives
+on the device; `solution` (host) is refreshed according to ``sync_policy``.
+
+There is no CPU fallback: construction raises if the configuration is outside
+the accelerated path (NotImplementedError) or if the CUDA library is missing.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .adaptor import get_adaptor, is_constant, is_function, constant_value
+from .engine import Engine
+
+__all__ = ["SSPRK33", "ERKGenericShuOsher", "ForwardEuler", "butcher_to_shuosher_form", "CFL_UNCONDITIONALLY_STABLE"]
+
+CFL_UNCONDITIONALLY_STABLE = np.inf
+
+
+def butcher_to_shuosher_form(a, b):
+    """
+    Shu-Osher form of an explicit Butcher tableau; same construction as
+    thetis/rungekutta.py:13-87 (sub-diagonal entries of [a; b] become beta).
+    """
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    if np.diag(a).any():
+        raise NotImplementedError("implicit Runge-Kutta schemes are outside the accelerated path")
+    lower = np.vstack((a, b))[1:, :]
+    n = lower.shape[0]
+    beta_sub = np.diag(np.diag(lower))
+    alpha = np.zeros((n + 1, n + 1))
+    alpha[1:, 1:] = np.eye(n) - beta_sub @ np.linalg.inv(lower)
+    alpha[:, 0] = 1.0 - alpha.sum(axis=1)
+    beta = np.zeros((n + 1, n + 1))
+    beta[1:, :-1] = beta_sub
+    alpha[np.abs(alpha) < 1e-13] = 0.0
+    beta[np.abs(beta) < 1e-13] = 0.0
+    assert np.allclose(alpha.sum(axis=1), 1.0)
+    return alpha, beta
+
+
+_SWE_FIELDS = {
+    "coriolis": L.F_CORIOLIS, "manning_drag_coefficient": L.F_MANNING,
+    "quadratic_drag_coefficient": L.F_QUAD_DRAG, "linear_drag_coefficient": L.F_LINEAR_DRAG,
+    "wind_stress": L.F_WIND_STRESS, "atmospheric_pressure": L.F_ATM_PRESSURE,
+    "momentum_source": L.F_MOMENTUM_SOURCE, "volume_source": L.F_VOLUME_SOURCE,
+}
+_SWE_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX}
+_TRACER_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX, "value": L.BC_VALUE}
+_CONST_SLOT = {"elev": 0, "uv": 1, "un": 3, "flux": 4, "value": 5}
+
+
+def _opt(options, name, default=None):
+    if options is None:
+        return default
+    if isinstance(options, dict):
+        return options.get(name, default)
+    return getattr(options, name, default)
+
+
+def _version(obj):
+    """Cheap change stamp of a Function/Constant (PyOP2 dat_version when available)."""
+    d = getattr(obj, "dat", None)
+    if d is not None:
+        v = getattr(d, "dat_version", None)
+        if v is not None:
+            return ("dat", v)
+        return None          # unknown: always refresh
+    v = getattr(obj, "version", None)
+    return None if v is None else ("const", v)
+
+
+class ERKGenericShuOsher:
+    """
+    Explicit Runge-Kutta integrator in Shu-Osher form on the device.  Only
+    schemes whose stages combine the step's initial state u^(0) and the latest
+    stage are supported (SSPRK33, forward Euler, SSPRK22): the fused kernel
+    computes  u_out = a0*u^(0) + a1*u^(i) + beta*dt*M^-1 R(u^(i)).
+    """
+    a = None
+    b = None
+    c = None
+    cfl_coeff = 1.0
+
+    def __init__(self, equation, solution, fields, dt, options=None, bnd_conditions=None, terms_to_add="all",
+                 sync_policy="every_step"):
+        self.equation = equation
+        self.solution = solution
+        self.fields = fields if fields is not None else {}
+        self.dt = float(dt)
+        self.options = options
+        self.bnd_conditions = bnd_conditions if bnd_conditions is not None else {}
+        self.name = "-".join([self.__class__.__name__, self.equation.__class__.__name__])
+        self.solver_parameters = _opt(options, "solver_parameters", {})   # accepted, unused: the mass solve is exact
+        if terms_to_add not in ("all", ["implicit", "explicit", "source"]) and set(terms_to_add) != {"implicit", "explicit", "source"}:
+            raise NotImplementedError("term subsets are outside the accelerated path")
+        self.a = np.array(self.a, dtype=float)
+        self.b = np.array(self.b, dtype=float)
+        self.c = np.array(self.c, dtype=float)
+        self.n_stages = len(self.b)
+        self.alpha, self.beta = butcher_to_shuosher_form(self.a, self.b)
+        for i in range(self.n_stages):
+            if np.any(self.alpha[i + 1][1:i] != 0.0):
+                raise NotImplementedError("Shu-Osher form uses intermediate stages other than u^(0) and the latest")
+        self.sync_policy = sync_policy          # 'every_step' | 'manual'
+        self._kind = self._equation_kind()
+        mesh_obj = self._function_space().mesh()
+        self.adaptor = get_adaptor(mesh_obj)
+        if self.adaptor.engine is None:
+            self.adaptor.engine = Engine(self.adaptor.mesh)
+        self.engine = self.adaptor.engine
+        self._host_stale = False
+        self._last_host_version = None
+        self._field_versions = {}
+        self._bc_versions = {}
+        self._setup_buffers()
+        self._check_supported()
+        self._push_static()
+        self.initialize(solution)
+
+    # ------------------------------------------------------------------ set-up
+    def _function_space(self):
+        fs = getattr(self.equation, "function_space", None)
+        return fs if fs is not None else self.solution.function_space()
+
+    def _equation_kind(self):
+        n = self.equation.__class__.__name__
+        if n == "ShallowWaterEquations":
+            return "swe"
+        if n == "TracerEquation2D":
+            return "tracer"
+        raise NotImplementedError(f"{n} is outside the accelerated path (ShallowWaterEquations, TracerEquation2D)")
+
+    def _setup_buffers(self):
+        eng, ad = self.engine, self.adaptor
+        dev = eng.device
+        if self._kind == "swe":
+            uv_f, eta_f = self.solution.subfunctions
+            nm_u = ad.dg_node_map(uv_f.function_space())
+            nm_e = ad.dg_node_map(eta_f.function_space())
+            if not np.array_equal(nm_u, nm_e):
+                raise NotImplementedError("velocity and elevation P1DG spaces must share their node numbering")
+            self.node_map = torch.as_tensor(nm_u.reshape(-1)).to(dev)
+            n_nodes = int(np.asarray(eta_f.dat.data_ro).shape[0])
+            self.buf = [eng.new_state() for _ in range(3)]
+            self._d_uv = torch.empty((n_nodes, 2), dtype=torch.float64, device=dev)
+            self._d_eta = torch.empty(n_nodes, dtype=torch.float64, device=dev)
+            self._h_uv = torch.empty((n_nodes, 2), dtype=torch.float64).pin_memory()
+            self._h_eta = torch.empty(n_nodes, dtype=torch.float64).pin_memory()
+            eng.swe_stepper = self
+        else:
+            nm = ad.dg_node_map(self.solution.function_space())
+            self.node_map = torch.as_tensor(nm.reshape(-1)).to(dev)
+            n_nodes = int(np.asarray(self.solution.dat.data_ro).shape[0])
+            self.buf = [eng.new_tracer() for _ in range(3)]
+            self._d_q = torch.empty(n_nodes, dtype=torch.float64, device=dev)
+            self._h_q = torch.empty(n_nodes, dtype=torch.float64).pin_memory()
+            self._own_swe_state = None
+            if not hasattr(eng, "tracer_steppers"):
+                eng.tracer_steppers = {}
+            eng.tracer_steppers[id(self.solution)] = self
+
+    def _check_supported(self):
+        if self._kind == "swe":
+            if self.fields.get("viscosity_h") is not None:
+                raise NotImplementedError("horizontal viscosity is outside the accelerated path")
+            if self.fields.get("nikuradse_bed_roughness") is not None:
+                raise NotImplementedError("nikuradse_bed_roughness is outside the accelerated path")
+            for m, funcs in self.bnd_conditions.items():
+                for k in (funcs or {}):
+                    if k == "drag":
+                        raise NotImplementedError("boundary drag is outside the accelerated path")
+                    if k not in _SWE_TAGS:
+                        raise Exception(f'Invalid boundary tag "{k}" specified on boundary {m}')
+            if getattr(self.equation, "tidal_farms", None):
+                raise NotImplementedError("tidal turbines are outside the accelerated path")
+        else:
+            opts = self.equation.options
+            if _opt(opts, "use_supg_tracer", False):
+                raise NotImplementedError("SUPG is outside the accelerated path")
+            for k, v in self.fields.items():
+                if k.startswith("diffusivity_h") and v is not None:
+                    raise NotImplementedError("tracer diffusion is outside the accelerated path")
+
+    # ------------------------------------------------------------------ configuration upload
+    def _depth(self):
+        return self.equation.depth
+
+    def _push_static(self):
+        """Options, bathymetry and everything else read once at construction."""
+        eng = self.engine
+        depth = self._depth()
+        eqo = self.equation.options
+        eng.set_option(L.OPT_NONLINEAR, bool(depth.use_nonlinear_equations))
+        eng.set_option(L.OPT_WETTING_DRYING, bool(depth.use_wetting_and_drying))
+        if depth.use_wetting_and_drying:
+            al = depth.wetting_and_drying_alpha
+            if not is_constant(al):
+                raise NotImplementedError("spatially varying wetting_and_drying_alpha is outside the accelerated path")
+            eng.set_option(L.OPT_WD_ALPHA, float(constant_value(al)[0]))
+        self._set_field(L.F_BATHYMETRY, depth.bathymetry_2d, "bathymetry")
+        for m, ln in self.adaptor.boundary_len.items():
+            eng.set_boundary_length(m, ln)
+        if self._kind == "swe":
+            eng.set_option(L.OPT_LAX_FRIEDRICHS, bool(_opt(eqo, "use_lax_friedrichs_velocity", True)))
+        else:
+            eng.set_option(L.OPT_LF_TRACER, bool(_opt(eqo, "use_lax_friedrichs_tracer", False)))
+        self._push_dynamic(force=True)
+
+    def _set_field(self, fid, value, key):
+        eng = self.engine
+        if value is None:
+            if self._field_versions.get(key, "unset") != "none":
+                eng.set_field(fid, None)
+                self._field_versions[key] = "none"
+            return
+        if is_constant(value):
+            v = constant_value(value)
+            stamp = ("c",) + tuple(v.tolist())
+            if self._field_versions.get(key) != stamp:
+                eng.set_field(fid, v if v.size > 1 else float(v[0]))
+                self._field_versions[key] = stamp
+            return
+        if is_function(value):
+            ver = _version(value)
+            stamp = ("f", id(value), ver)
+            if ver is None or self._field_versions.get(key) != stamp:
+                eng.set_field(fid, self.adaptor.vertex_values(value))
+                self._field_versions[key] = stamp
+            return
+        raise NotImplementedError(f"coefficient {key!r}: UFL expressions must be interpolated into a P1 Function first")
+
+    def _push_dynamic(self, force=False):
+        """Everything `update_forcings` may have changed: Constants are re-read, Functions re-uploaded if touched."""
+        eng = self.engine
+        if self._kind == "swe":
+            gc = getattr(self.equation, "physical_constants", None)
+            if gc is None:
+                try:
+                    from thetis.physical_constants import physical_constants as gc   # live Thetis install
+                except ImportError:
+                    gc = None
+            if gc is not None:
+                eng.set_option(L.OPT_G_GRAV, float(constant_value(gc["g_grav"])[0]))
+                eng.set_option(L.OPT_RHO0, float(constant_value(gc["rho0"])[0]))
+            eqo = self.equation.options
+            eng.set_option(L.OPT_NORM_SMOOTHER, float(constant_value(_opt(eqo, "norm_smoother", 0.0))[0]))
+            lf = self.fields.get("lax_friedrichs_velocity_scaling_factor")
+            eng.set_option(L.OPT_LF_SCALING, 1.0 if lf is None else float(constant_value(lf)[0]))
+            for name, fid in _SWE_FIELDS.items():
+                self._set_field(fid, self.fields.get(name), name)
+            self._push_bcs(0, _SWE_TAGS)
+        else:
+            lf = self.fields.get("lax_friedrichs_tracer_scaling_factor")
+            eng.set_option(L.OPT_LF_TRACER_SCALING, 1.0 if lf is None else float(constant_value(lf)[0]))
+            cf = self.fields.get("tracer_advective_velocity_factor")
+            if cf is not None and not is_constant(cf):
+                raise NotImplementedError("spatially varying tracer_advective_velocity_factor is outside the accelerated path")
+            eng.set_option(L.OPT_TRACER_VEL_FACTOR, 1.0 if cf is None else float(constant_value(cf)[0]))
+            src = None
+            for k, v in self.fields.items():
+                if k.startswith("source") and v is not None:
+                    src = v
+            self._set_field(L.F_TRACER_SOURCE, src, "tracer_source")
+            self._push_bcs(1, _TRACER_TAGS)
+
+    def _push_bcs(self, eq, tags):
+        eng = self.engine
+        for marker, funcs in self.bnd_conditions.items():
+            if funcs is None:
+                continue
+            op = 0
+            consts = np.zeros(6)
+            arrays = []
+            for tag, val in funcs.items():
+                if tag not in tags:
+                    if eq == 0:
+                        raise Exception(f'Invalid boundary tag "{tag}" specified on boundary {marker}')
+                    continue
+                op |= tags[tag]
+                if is_constant(val):
+                    v = constant_value(val)
+                    s = _CONST_SLOT[tag]
+                    consts[s:s + v.size] = v
+                elif is_function(val):
+                    arrays.append((tag, val))
+                else:
+                    raise NotImplementedError(
+                        f"boundary datum {tag!r} on marker {marker}: UFL expressions must be interpolated into a P1 Function first")
+            stamp = (op,) + tuple(consts.tolist())
+            key = (eq, marker)
+            if self._bc_versions.get(key) != stamp:
+                eng.set_bc(eq, marker, op, consts)
+                self._bc_versions[key] = stamp
+                for tag, _ in arrays:
+                    self._bc_versions.pop((eq, marker, tag), None)
+            for tag, val in arrays:
+                ver = _version(val)
+                akey = (eq, marker, tag)
+                astamp = (id(val), ver)
+                if ver is None or self._bc_versions.get(akey) != astamp:
+                    eng.set_bc_array(eq, marker, tags[tag], self.adaptor.bfacet_values(val))
+                    self._bc_versions[akey] = astamp
+
+    # ------------------------------------------------------------------ host <-> device
+    def _solution_version(self):
+        if self._kind == "swe":
+            return tuple(_version(f) for f in self.solution.subfunctions)
+        return (_version(self.solution),)
+
+    def upload(self):
+        """H2D: host `solution` -> device state (buffer 0)."""
+        eng = self.engine
+        if self._kind == "swe":
+            uv_f, eta_f = self.solution.subfunctions
+            self._h_uv.numpy()[...] = np.asarray(uv_f.dat.data_ro).reshape(-1, 2)
+            self._h_eta.numpy()[...] = np.asarray(eta_f.dat.data_ro)
+            self._d_uv.copy_(self._h_uv, non_blocking=True)
+            self._d_eta.copy_(self._h_eta, non_blocking=True)
+            eng.state_from_fields(self._d_uv, self._d_eta, self.node_map, self.buf[0])
+        else:
+            self._h_q.numpy()[...] = np.asarray(self.solution.dat.data_ro)
+            self._d_q.copy_(self._h_q, non_blocking=True)
+            eng.tracer_from_field(self._d_q, self.node_map, self.buf[0])
+        self._host_stale = False
+        self._last_host_version = self._solution_version()
+
+    def sync_to_host(self):
+        """D2H: device state -> `solution.dat.data` (in place; sub-function views stay valid)."""
+        if not self._host_stale:
+            return
+        eng = self.engine
+        if self._kind == "swe":
+            eng.state_to_fields(self.buf[0], self.node_map, self._d_uv, self._d_eta)
+            self._h_uv.copy_(self._d_uv, non_blocking=True)
+            self._h_eta.copy_(self._d_eta, non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+            uv_f, eta_f = self.solution.subfunctions
+            uv_f.dat.data[...] = self._h_uv.numpy().reshape(np.asarray(uv_f.dat.data_ro).shape)
+            eta_f.dat.data[...] = self._h_eta.numpy()
+        else:
+            eng.tracer_to_field(self.buf[0], self.node_map, self._d_q)
+            self._h_q.copy_(self._d_q, non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+            self.solution.dat.data[...] = self._h_q.numpy()
+        self._host_stale = False
+        self._last_host_version = self._solution_version()
+
+    def device_state(self):
+        """Device tensor holding the current solution (cell records)."""
+        return self.buf[0]
+
+    def mark_device_modified(self):
+        """Another device operator (the limiter) changed buffer 0 in place."""
+        self._host_stale = True
+
+    def _host_changed(self):
+        v = self._solution_version()
+        if any(x is None for x in v):
+            return not self._host_stale and self.sync_policy == "every_step"
+        return v != self._last_host_version
+
+    # ------------------------------------------------------------------ TimeIntegrator API
+    def initialize(self, solution):
+        """Assign initial conditions (timeintegrator.py:33-39): upload `solution` to the device."""
+        if solution is not self.solution and solution is not None:
+            self.solution.assign(solution)
+        self.upload()
+
+    def set_dt(self, dt):
+        """Update time step (timeintegrator.py:70-73)."""
+        self.dt = float(dt)
+
+    def update_solver(self):
+        """Kept for API compatibility (rungekutta.py:913-919): the mass solve is closed-form, nothing to rebuild."""
+        return None
+
+    def _swe_state_for_tracer(self):
+        eng = self.engine
+        sw = eng.swe_stepper
+        uv_f = self.fields.get("uv_2d")
+        if sw is not None and uv_f is not None and any(uv_f is s for s in sw.solution.subfunctions):
+            if not sw._host_stale and sw._host_changed():
+                sw.upload()
+            return sw.device_state()
+        # tracer-only run: velocity / elevation come from host Functions
+        if uv_f is None:
+            raise NotImplementedError("tracer equation without uv_2d is trivial; not on the accelerated path")
+        if self._own_swe_state is None:
+            self._own_swe_state = eng.new_state()
+        el_f = self.fields.get("elev_2d")
+        uvd = torch.as_tensor(np.ascontiguousarray(np.asarray(uv_f.dat.data_ro).reshape(-1, 2))).to(eng.device)
+        if el_f is not None:
+            ed = torch.as_tensor(np.ascontiguousarray(np.asarray(el_f.dat.data_ro))).to(eng.device)
+        else:
+            ed = torch.zeros(uvd.shape[0], dtype=torch.float64, device=eng.device)
+        eng.state_from_fields(uvd, ed, self.node_map, self._own_swe_state)
+        return self._own_swe_state
+
+    def solve_stage(self, i_stage, t, update_forcings=None):
+        """Solve i-th stage and leave it in the device solution (rungekutta.py:929-946)."""
+        if update_forcings is not None:
+            update_forcings(t + self.c[i_stage] * self.dt)
+        if i_stage == 0 and not self._host_stale and self._host_changed():
+            self.upload()                      # the host copy was modified since the last sync
+        self._push_dynamic()
+        self._launch_stage(i_stage)
+
+    def _launch_stage(self, i_stage):
+        """One fused kernel launch: residual + mass inverse + Shu-Osher update of stage i."""
+        eng = self.engine
+        a0 = float(self.alpha[i_stage + 1][0]) if i_stage > 0 else 0.0
+        a1 = float(self.alpha[i_stage + 1][i_stage]) if i_stage > 0 else float(self.alpha[1][0])
+        bdt = float(self.beta[i_stage + 1][i_stage]) * self.dt
+        last = i_stage == self.n_stages - 1
+        A, B, Cb = self.buf
+        # stage buffers rotate A -> B -> C -> ... and the last stage writes back into A (u0 may alias u_out)
+        if i_stage == 0:
+            src, dst = A, B
+        else:
+            src = self._cur
+            dst = A if last else (Cb if src is B else B)
+        self._cur = dst
+        u0 = A if i_stage > 0 else None
+        if self._kind == "swe":
+            eng.swe_stage(a0, a1, bdt, src, u0, dst)
+        else:
+            eng.tracer_stage(a0, a1, bdt, src, u0, dst, self._swe_state_for_tracer())
+        if last:
+            if dst is not A:
+                self.buf[0], self.buf[1] = self.buf[1], self.buf[0]
+            self._host_stale = True
+
+    def advance_device(self):
+        """One step with every input already resident on the device (no forcing refresh, no host sync)."""
+        for i in range(self.n_stages):
+            self._launch_stage(i)
+
+    def advance(self, t, update_forcings=None):
+        """Advances equations for one time step (rungekutta.py:948-952)."""
+        for i in range(self.n_stages):
+            self.solve_stage(i, t, update_forcings)
+        if self.sync_policy == "every_step":
+            self.sync_to_host()
+
+
+class SSPRK33(ERKGenericShuOsher):
+    """3rd order SSP(3,3): tableau of thetis/rungekutta.py:342-347."""
+    a = [[0, 0, 0], [1.0, 0, 0], [0.25, 0.25, 0]]
+    b = [1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0]
+    c = [0, 1.0, 0.5]
+    cfl_coeff = 1.0
+
+
+class ForwardEuler(ERKGenericShuOsher):
+    """Forward Euler through the same stage kernel."""
+    a = [[0]]
+    b = [1.0]
+    c = [0]
+    cfl_coeff = 1.0
