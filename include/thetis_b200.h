@@ -73,7 +73,8 @@ typedef enum {
     TB_OPT_WD_ALPHA = 7,               /* wetting_and_drying_alpha (constant)     */
     TB_OPT_LF_TRACER = 8,              /* use_lax_friedrichs_tracer               */
     TB_OPT_LF_TRACER_SCALING = 9,      /* lax_friedrichs_tracer_scaling_factor    */
-    TB_OPT_TRACER_VEL_FACTOR = 10      /* tracer_advective_velocity_factor        */
+    TB_OPT_TRACER_VEL_FACTOR = 10,     /* tracer_advective_velocity_factor        */
+    TB_OPT_FORCE_GENERIC_KERNEL = 11   /* developer/test switch: bypass the specialised stage kernels */
 } tb_option;
 
 /* Coefficient fields: the `fields` dict of solver2d.py:546-558 plus bathymetry. */

@@ -85,6 +85,12 @@ def _run(mesh, bath_v, options, fields_v, bnd, g=9.81, tol=1e-12, seed=0, bc_arr
     k = eng.new_state()
     eng.swe_tendency(st, k)
     gu, ge = eng.download_nodal(k)
+    # the specialised stage kernels and the generic one must agree to rounding
+    eng.set_option(L.OPT_FORCE_GENERIC_KERNEL, 1)
+    k2 = eng.new_state()
+    eng.swe_tendency(st, k2)
+    gu2, ge2 = eng.download_nodal(k2)
+    assert np.abs(gu2 - gu).max() <= 1e-13 * np.abs(gu).max() and np.abs(ge2 - ge).max() <= 1e-13 * np.abs(ge).max()
     su = np.abs(ku).max()
     se = np.abs(ke).max()
     eu = np.abs(gu - ku).max() / su
@@ -188,3 +194,16 @@ def test_wetting_drying_residual():
     b = 3.0 - 5.0 * X / 14e3          # dries out: negative bathymetry on the right
     _run(mesh, b, dict(use_wetting_and_drying=True, wetting_and_drying_alpha=0.4),
          {"manning_drag_coefficient": 0.02}, {1: {"elev": 0.5}}, tol=1e-10)
+
+
+@pytest.mark.parametrize("wd", [False, True])
+def test_config5_specialised_kernels(wd):
+    """North-Sea physics (Manning + Coriolis + LF + tidal elevation array [+ wetting-drying]): SPEC 2 / SPEC 3 kernels"""
+    import os
+    from thetis_b200.workloads import north_sea_mesh, north_sea_setup, tide_values
+    mesh = north_sea_mesh(k=1)
+    setup = north_sea_setup(mesh, wetting_drying=wd)
+    tv = tide_values(setup, 1234.0)
+    _run(mesh, setup["bath"], dict(use_wetting_and_drying=wd, wetting_and_drying_alpha=0.5),
+         {"manning_drag_coefficient": setup["manning"], "coriolis": setup["coriolis"]},
+         {100: {"elev": 0.0, "uv": (0.0, 0.0)}}, tol=1e-10, bc_arrays={(100, "elev"): tv})

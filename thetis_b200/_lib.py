@@ -10,12 +10,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libthetis_b200.so")
+LIB_PATH = os.environ.get("THETIS_B200_LIB", os.path.join(_HERE, "libthetis_b200.so"))   # override: developer A/B builds
 
 TB_OK = 0
 # tb_option
 OPT_G_GRAV, OPT_RHO0, OPT_NONLINEAR, OPT_LAX_FRIEDRICHS, OPT_LF_SCALING, OPT_NORM_SMOOTHER, \
-    OPT_WETTING_DRYING, OPT_WD_ALPHA, OPT_LF_TRACER, OPT_LF_TRACER_SCALING, OPT_TRACER_VEL_FACTOR = range(11)
+    OPT_WETTING_DRYING, OPT_WD_ALPHA, OPT_LF_TRACER, OPT_LF_TRACER_SCALING, OPT_TRACER_VEL_FACTOR, \
+    OPT_FORCE_GENERIC_KERNEL = range(12)
 # tb_field
 F_BATHYMETRY, F_CORIOLIS, F_MANNING, F_QUAD_DRAG, F_LINEAR_DRAG, F_WIND_STRESS, F_ATM_PRESSURE, \
     F_MOMENTUM_SOURCE, F_VOLUME_SOURCE, F_TRACER_SOURCE = range(10)

@@ -63,6 +63,7 @@ struct tb_ctx {
     double g = 9.81, rho0 = 1000.0, lf_sigma = 1.0, norm_smoother = 0.0, wd_alpha = 0.5;
     int nonlinear = 1, lf_on = 1, wd_on = 0;
     int lf_tracer = 0;
+    int force_generic = 0;
     double lf_tracer_sigma = 1.0, tracer_vel_factor = 1.0;
     FieldStore fields[TB_F_COUNT];
     // bcs: eq 0 swe, 1 tracer
@@ -418,6 +419,7 @@ extern "C" int tb_set_option(tb_ctx *ctx, int option, double value) {
         case TB_OPT_LF_TRACER: ctx->lf_tracer = value != 0.0; break;
         case TB_OPT_LF_TRACER_SCALING: ctx->lf_tracer_sigma = value; break;
         case TB_OPT_TRACER_VEL_FACTOR: ctx->tracer_vel_factor = value; break;
+        case TB_OPT_FORCE_GENERIC_KERNEL: ctx->force_generic = value != 0.0; break;
         default: return fail(ctx, TB_ERR_ARG, "unknown option");
     }
     return TB_OK;
@@ -610,6 +612,7 @@ extern "C" int tb_swe_stage(tb_ctx *ctx, double a0, double a1, double b_dt, cons
     fill_coef(ctx->fields[TB_F_VOLUME_SOURCE], p.vsrc);
     p.use_quad = (p.man.mode || p.cd.mode || p.wind.mode || p.wd_on) ? 1 : 0;
     p.nquad = ctx->nquad;
+    p.force_generic = ctx->force_generic;
     fill_bc(ctx, 0, p.bc);
     long long first, count;
     patch_range(ctx, first, count);

@@ -61,6 +61,7 @@ struct TbSweParams {
     double a0, a1, bdt;
     double g, rho0, lf_sigma, eps2, wd_alpha2;
     int lf_on, wd_on, use_quad, nquad;
+    int force_generic, pad0;      // developer switch: always run the generic (SPEC 0) kernel
     TbCoef cor, man, cd, lin, wind, pa, msrc, vsrc;
     TbBcTable bc;
 };
@@ -85,6 +86,7 @@ struct TbTracerParams {
 cudaError_t tb_launch_swe_stage(const TbSweParams &p, bool nonlinear, int n_patches, size_t smem, cudaStream_t s);
 cudaError_t tb_launch_tracer_stage(const TbTracerParams &p, int n_patches, size_t smem, cudaStream_t s);
 cudaError_t tb_set_quadrature(int n, const double *lam, const double *w);
+int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear);
 size_t tb_swe_smem_bytes(const TbPatchLayout &pl);
 size_t tb_tracer_smem_bytes(const TbPatchLayout &pl);
 cudaError_t tb_kernels_init();

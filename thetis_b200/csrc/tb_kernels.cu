@@ -15,6 +15,10 @@
 // Arithmetic follows thetis/shallowwater_eq.py (line refs at each term).
 #include "tb_internal.h"
 
+#ifndef TB_MINB
+#define TB_MINB 4      // resident CTAs per SM the stage kernel is compiled for (register budget)
+#endif
+
 // ------------------------------------------------------------------ constants
 __constant__ double c_qlam[TB_MAX_QUAD][3];
 __constant__ double c_qw[TB_MAX_QUAD];
@@ -69,11 +73,42 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ------------------------------------------------------------------ fp64 math helpers
+// MUFU seed + two Newton steps, branch-free, ~1 ulp (checked in tests/test_gpu_math.py).  The CUDA library
+// versions of sqrt / division / rcbrt carry slow-path subroutine calls that cost more fp64-pipe and issue
+// slots than the whole facet flux; arguments here are depths, lengths and areas (normal, positive).
+__device__ __forceinline__ double tb_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double xy = x * y;
+    double r = fma(-xy, y, 1.0);
+    y = fma(0.5 * y, r, y);
+    xy = x * y;
+    r = fma(-xy, y, 1.0);
+    return fma(0.5 * y, r, y);
+}
+__device__ __forceinline__ double tb_sqrt(double x) { return x * tb_rsqrt(x); }   // x > 0
+__device__ __forceinline__ double tb_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double r = fma(-x, y, 1.0);
+    y = fma(y, r, y);
+    r = fma(-x, y, 1.0);
+    return fma(y, r, y);
+}
+__device__ __forceinline__ double tb_rcbrt(double x) {   // x^(-1/3), x > 0 within float range
+    double y = (double)rcbrtf((float)x);
+    double r = fma(-x * y, y * y, 1.0);
+    y = fma(y * (1.0 / 3.0), r, y);
+    r = fma(-x * y, y * y, 1.0);
+    return fma(y * (1.0 / 3.0), r, y);
+}
+
 // ------------------------------------------------------------------ small helpers
 // DepthExpression.get_total_depth for the nonlinear case (utility.py:975-996):
 // hl = bathymetry + eta at the evaluation point
 __device__ __forceinline__ double wd_depth(double hl, int wd_on, double alpha2) {
-    if (wd_on) return 0.5 * (hl + sqrt(hl * hl + alpha2));
+    if (wd_on) return 0.5 * (hl + tb_sqrt(hl * hl + alpha2));
     return hl;
 }
 
@@ -98,7 +133,7 @@ __device__ __forceinline__ BcExt bc_external(int op, double e_in, double ux_in, 
     } else if ((op & TB_BC_ELEV) && (op & TB_BC_FLUX)) {
         r.eta = elev;
         const double h_ext = NONLIN ? wd_depth(bpt + elev, wd_on, alpha2) : bpt;
-        const double s = flux / (h_ext * bnd_len);
+        const double s = flux * tb_rcp(h_ext * bnd_len);
         r.ux = s * nx; r.uy = s * ny;
     } else if (op & TB_BC_ELEV) {
         r.eta = elev; r.ux = ux_in; r.uy = uy_in;
@@ -109,7 +144,7 @@ __device__ __forceinline__ BcExt bc_external(int op, double e_in, double ux_in, 
     } else {  // TB_BC_FLUX
         r.eta = e_in;
         const double h_ext = NONLIN ? wd_depth(bpt + e_in, wd_on, alpha2) : bpt;
-        const double s = flux / (h_ext * bnd_len);
+        const double s = flux * tb_rcp(h_ext * bnd_len);
         r.ux = s * nx; r.uy = s * ny;
     }
     return r;
@@ -121,8 +156,76 @@ __device__ __forceinline__ double coef_at(const TbCoef &c, const double *cols, i
 }
 
 // ------------------------------------------------------------------ SWE stage kernel
+// Compile-time specialisations (warp-uniform runtime flags cost issue slots and registers in a kernel whose fp64
+// pipe and issue port are co-critical):
+//   SPEC 0  generic: every optional term behind a runtime flag
+//   SPEC 1  no optional cell terms (BASELINE configs 1 and 2)
+//   SPEC 2  Manning drag + Coriolis, 6-point cell rule (config 5 without wetting-drying)
+//   SPEC 3  SPEC 2 + wetting-drying (config 5)
+template <int SPEC>
+struct StageSpec {
+    static constexpr bool generic = SPEC == 0;
+    static constexpr bool wd = SPEC == 3;
+    static constexpr bool man = SPEC >= 2;
+    static constexpr bool cor = SPEC >= 2;
+};
+
+__device__ __forceinline__ void cp_async8(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// Open-boundary fluxes at one Gauss point (shallowwater_eq.py:370-375, 431-442, 498-509).  Rare (only facets of
+// open markers), kept out of line so that it does not bloat the hot instruction stream.
 template <bool NONLIN>
-__global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__ TbSweParams prm) {
+__device__ __noinline__ void open_boundary_flux(const TbBcTable *bc, int gb, int slot, double wp_, double wq_, double uKx,
+                                                double uKy, double eK, double bg, double HK, double nxs, double nys,
+                                                double il, double len, double g, int wd_on, double a2, double *out) {
+    const TbBcSlot &bs = bc->slots[slot];
+    const int op = bs.opcode;
+    double elev = bs.elev, uvx = bs.uvx, uvy = bs.uvy, un = bs.un, flux = bs.flux;
+    if (bs.arr_mask & TB_BC_ELEV) elev = wp_ * __ldg(bc->ext_elev + 2 * gb) + wq_ * __ldg(bc->ext_elev + 2 * gb + 1);
+    if (bs.arr_mask & TB_BC_UV) {
+        uvx = wp_ * __ldg(bc->ext_uv + 4 * gb) + wq_ * __ldg(bc->ext_uv + 4 * gb + 2);
+        uvy = wp_ * __ldg(bc->ext_uv + 4 * gb + 1) + wq_ * __ldg(bc->ext_uv + 4 * gb + 3);
+    }
+    if (bs.arr_mask & TB_BC_UN) un = wp_ * __ldg(bc->ext_un + 2 * gb) + wq_ * __ldg(bc->ext_un + 2 * gb + 1);
+    if (bs.arr_mask & TB_BC_FLUX) flux = wp_ * __ldg(bc->ext_flux + 2 * gb) + wq_ * __ldg(bc->ext_flux + 2 * gb + 1);
+    const BcExt ex = bc_external<NONLIN>(op, eK, uKx, uKy, bg, elev, uvx, uvy, un, flux, bs.bnd_len, nxs, nys, il, wd_on, a2);
+    const double ig = tb_rcp(g);
+    // PG (:370-375)
+    const double dun = (uKx - ex.ux) * nxs + (uKy - ex.uy) * nys;   // un_jump*len
+    const double cK = tb_sqrt(g * HK);
+    const double t = 0.5 * g * (eK + ex.eta) + cK * dun * il;
+    double fx = t * nxs, fy = t * nys;
+    // HUDiv (:431-442)
+    const double Hext = NONLIN ? wd_depth(bg + ex.eta, wd_on, a2) : bg;
+    const double hav = 0.5 * (HK + Hext);
+    const double cav = tb_sqrt(g * hav);
+    const double usx = uKx + ex.ux, usy = uKy + ex.uy;
+    const double usN = usx * nxs + usy * nys;
+    const double ejump = eK - ex.eta;
+    const double un_rie_len = 0.5 * usN + (cav * tb_rcp(hav)) * ejump * len;
+    const double eta_rie = 0.5 * (eK + ex.eta) + (cav * ig) * dun * il;
+    const double h_rie = NONLIN ? wd_depth(bg + eta_rie, wd_on, a2) : bg;
+    const double fe = h_rie * un_rie_len;
+    if (NONLIN) {
+        // advection (:498-509)
+        const double un_a_len = 0.5 * usN + (cK * tb_rcp(HK)) * ejump * len;
+        fx += 0.5 * usx * un_a_len;
+        fy += 0.5 * usy * un_a_len;
+    }
+    out[0] = fx;
+    out[1] = fy;
+    out[2] = fe;
+}
+
+template <bool NONLIN, int SPEC>
+__global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_constant__ TbSweParams prm) {
+    typedef StageSpec<SPEC> SP;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     double *S = reinterpret_cast<double *>(smem + 16);              // [(TB_P+NH)][9] stage state (own + halo)
@@ -147,14 +250,29 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
         bulk_g2s(blk, prm.pl.sblk + (long long)patch * prm.pl.stride, sb, bar);
         if (prm.u0) bulk_g2s(O, prm.u0 + cell0 * 9, rec, bar);
     }
-    // patch halo: records of off-patch facet neighbours, gathered while the bulk copies fly
+    // patch halo: records of off-patch facet neighbours, copied asynchronously (LDGSTS) while the bulk copies fly.
+    // Element i of the halo block is double (i % 9) of halo cell (i / 9): S[TB_P*9 + i].
     {
-        const int nh = __ldg(prm.pl.halo_cnt + patch);
+        const int nh9 = __ldg(prm.pl.halo_cnt + patch) * 9;
         const int *hid = prm.pl.halo_ids + (long long)patch * prm.pl.NH;
-        for (int i = tid; i < nh * 9; i += TB_P) {
-            const int h = i / 9, k = i - h * 9;
-            S[(TB_P + h) * 9 + k] = __ldg(prm.u_in + (long long)__ldg(hid + h) * 9 + k);
+        double *H = S + TB_P * 9;
+        for (int base = 0; base < nh9; base += 4 * TB_P) {
+            long long gsrc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = base + j * TB_P + tid;
+                if (i < nh9) {
+                    const int h = i / 9;
+                    gsrc[j] = (long long)__ldg(hid + h) * 9 + (i - h * 9);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = base + j * TB_P + tid;
+                if (i < nh9) cp_async8(H + i, prm.u_in + gsrc[j]);
+            }
         }
+        cp_async_wait_all();
     }
     mbar_wait(bar, 0);
     __syncthreads();
@@ -170,7 +288,17 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
         const int *cn = reinterpret_cast<const int *>(blk + prm.pl.off_cn) + tid * 3;
         const double *my = S + tid * 9;
         const double g = prm.g;
-        const int wd_on = prm.wd_on;
+        const int wd_on = SP::generic ? prm.wd_on : (SP::wd ? 1 : 0);
+        const bool lf_on = SP::generic ? (prm.lf_on != 0) : true;
+        const bool has_cor = SP::generic ? (prm.cor.mode != 0) : SP::cor;
+        const bool has_man = SP::generic ? (prm.man.mode != 0) : SP::man;
+        const bool has_cd = SP::generic ? (prm.cd.mode != 0) : false;
+        const bool has_lin = SP::generic ? (prm.lin.mode != 0) : false;
+        const bool has_wind = SP::generic ? (prm.wind.mode != 0) : false;
+        const bool has_pa = SP::generic ? (prm.pa.mode == 2) : false;
+        const bool has_msrc = SP::generic ? (prm.msrc.mode != 0) : false;
+        const bool has_vsrc = SP::generic ? (prm.vsrc.mode != 0) : false;
+        const bool use_quad = SP::generic ? (prm.use_quad != 0) : (SP::man || SP::wd);
         const double a2 = prm.wd_alpha2;
 
         double ux[3], uy[3], et[3], x[3], y[3], b[3];
@@ -200,6 +328,12 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
         // ---------------- volume terms (closed-form P1 integrals) ----------------
         const double sux = ux[0] + ux[1] + ux[2], suy = uy[0] + uy[1] + uy[2];
         const double se = et[0] + et[1] + et[2];
+        double wx[3], wy[3];      // u_b + sum_c u_c
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            wx[a] = ux[a] + sux;
+            wy[a] = uy[a] + suy;
+        }
         {
             // ExternalPressureGradientTerm cell part (shallowwater_eq.py:361): +g*eta*div(psi)
             const double c = -g * se * (1.0 / 6.0);   // g * (se/3) * (-N/2)
@@ -215,8 +349,8 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const double H = NONLIN ? (b[a] + et[a]) : b[a];
-                Wx += H * (ux[a] + sux);
-                Wy += H * (uy[a] + suy);
+                Wx += H * wx[a];
+                Wy += H * wy[a];
             }
             Wx *= (-1.0 / 24.0);
             Wy *= (-1.0 / 24.0);
@@ -225,28 +359,26 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
         }
         if (NONLIN) {
             // HorizontalAdvectionTerm cell part (:478): +div(outer(psi,u)).u
-            double Gu[3];   // (A grad phi_b).u_b  (own node)
-            double D = 0;
+            //   int (grad phi_a . u) u_i = 1/12 sum_j (A grad phi_a)_j T_ji,  T_ji = sum_b u_b,j (u_b,i + su_i)
+            //   int phi_a (div u) u_i   = D/12 (u_a,i + su_i),                D = sum_b (A grad phi_b).u_b
+            double Txx = 0, Txy = 0, Tyx = 0, Tyy = 0, D = 0;
 #pragma unroll
             for (int bb = 0; bb < 3; ++bb) {
-                Gu[bb] = -0.5 * (Nx[bb] * ux[bb] + Ny[bb] * uy[bb]);
-                D += Gu[bb];
+                Txx += ux[bb] * wx[bb];
+                Txy += ux[bb] * wy[bb];
+                Tyx += uy[bb] * wx[bb];
+                Tyy += uy[bb] * wy[bb];
+                D += Nx[bb] * ux[bb] + Ny[bb] * uy[bb];
             }
+            D *= (-1.0 / 24.0);          // (-1/2) * (1/12)
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                double sx = D * (ux[a] + sux), sy = D * (uy[a] + suy);
-#pragma unroll
-                for (int bb = 0; bb < 3; ++bb) {
-                    const double gab = -0.5 * (Nx[a] * ux[bb] + Ny[a] * uy[bb]);   // (A grad phi_a).u_b
-                    sx += gab * (ux[bb] + sux);
-                    sy += gab * (uy[bb] + suy);
-                }
-                Rux[a] += sx * (1.0 / 12.0);
-                Ruy[a] += sy * (1.0 / 12.0);
+                Rux[a] += (-1.0 / 24.0) * (Nx[a] * Txx + Ny[a] * Tyx) + D * wx[a];
+                Ruy[a] += (-1.0 / 24.0) * (Nx[a] * Txy + Ny[a] * Tyy) + D * wy[a];
             }
         }
         const double A = 0.5 * twoA;
-        if (prm.cor.mode) {
+        if (has_cor) {
             // CoriolisTerm (:632-633): R_x += int f u_y phi, R_y -= int f u_x phi
             double f[3];
 #pragma unroll
@@ -255,15 +387,17 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
             const double fux_ = f[0] * ux[0] + f[1] * ux[1] + f[2] * ux[2];
             const double fuy_ = f[0] * uy[0] + f[1] * uy[1] + f[2] * uy[2];
             const double c = A * (1.0 / 60.0);
+            const double bx = F * sux + fux_, by = F * suy + fuy_;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                const double ix = F * sux + f[a] * sux + fux_ + F * ux[a] + 2.0 * f[a] * ux[a];
-                const double iy = F * suy + f[a] * suy + fuy_ + F * uy[a] + 2.0 * f[a] * uy[a];
+                // int f w phi_a = A/60 [F W + f_a W + sum f_b w_b + F w_a + 2 f_a w_a] = A/60 [bx + f_a (W + w_a) + F w_a + f_a w_a]
+                const double ix = bx + f[a] * (wx[a] + ux[a]) + F * ux[a];
+                const double iy = by + f[a] * (wy[a] + uy[a]) + F * uy[a];
                 Rux[a] += c * iy;
                 Ruy[a] -= c * ix;
             }
         }
-        if (prm.lin.mode) {
+        if (has_lin) {
             // LinearDragTerm (:734-740): -C u
             double f[3];
 #pragma unroll
@@ -278,7 +412,7 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
                 Ruy[a] -= c * (F * suy + f[a] * suy + fuy_ + F * uy[a] + 2.0 * f[a] * uy[a]);
             }
         }
-        if (prm.pa.mode == 2) {
+        if (has_pa) {
             // AtmosphericPressureTerm (:658-663): -grad(p_a)/rho0;  A*grad p = -1/2 sum_a p_a N_a
             double gx = 0, gy = 0;
 #pragma unroll
@@ -287,14 +421,14 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
                 gx += pa * Nx[a];
                 gy += pa * Ny[a];
             }
-            const double c = (1.0 / 6.0) / prm.rho0;   // -( -1/2 ) * (1/3)
+            const double c = (1.0 / 6.0) * tb_rcp(prm.rho0);   // -( -1/2 ) * (1/3)
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 Rux[a] += c * gx;
                 Ruy[a] += c * gy;
             }
         }
-        if (prm.msrc.mode) {
+        if (has_msrc) {
             // MomentumSourceTerm (:805-811)
             double fx[3], fy[3];
 #pragma unroll
@@ -309,7 +443,7 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
                 Ruy[a] += A * (1.0 / 12.0) * (fy[a] + sy);
             }
         }
-        if (prm.vsrc.mode) {
+        if (has_vsrc) {
             // ContinuitySourceTerm (:824-831)
             double f[3];
 #pragma unroll
@@ -318,45 +452,53 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
 #pragma unroll
             for (int a = 0; a < 3; ++a) Re[a] += A * (1.0 / 12.0) * (f[a] + s);
         }
-        if (prm.use_quad) {
+        if (use_quad) {
             // non-polynomial cell integrands by the degree-3 cell rule:
             // QuadraticDragTerm (:679-701), WindStressTerm (:643-649), wetting-drying HUDiv volume term
-            double mu[3] = {0, 0, 0}, cdn[3] = {0, 0, 0}, wx[3] = {0, 0, 0}, wy[3] = {0, 0, 0};
+            double mu[3] = {0, 0, 0}, cdn[3] = {0, 0, 0}, twx[3] = {0, 0, 0}, twy[3] = {0, 0, 0};
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                if (prm.man.mode) mu[a] = coef_at(prm.man, cols, NV, v[a]);
-                if (prm.cd.mode) cdn[a] = coef_at(prm.cd, cols, NV, v[a]);
-                if (prm.wind.mode) {
-                    wx[a] = coef_at(prm.wind, cols, NV, v[a], 0);
-                    wy[a] = coef_at(prm.wind, cols, NV, v[a], 1);
+                if (has_man) mu[a] = coef_at(prm.man, cols, NV, v[a]);
+                if (has_cd) cdn[a] = coef_at(prm.cd, cols, NV, v[a]);
+                if (has_wind) {
+                    twx[a] = coef_at(prm.wind, cols, NV, v[a], 0);
+                    twy[a] = coef_at(prm.wind, cols, NV, v[a], 1);
                 }
             }
-            const double irho = 1.0 / prm.rho0;
-            for (int qd = 0; qd < prm.nquad; ++qd) {
+            const double irho = has_wind ? tb_rcp(prm.rho0) : 0.0;
+            double hl[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) hl[a] = NONLIN ? b[a] + et[a] : b[a];
+            const int nq = SP::generic ? prm.nquad : 6;
+#pragma unroll
+            for (int qd = 0; qd < (SP::generic ? TB_MAX_QUAD : 6); ++qd) {
+                if (SP::generic && qd >= nq) break;
                 const double l0 = c_qlam[qd][0], l1 = c_qlam[qd][1], l2 = c_qlam[qd][2];
                 const double w = c_qw[qd] * A;
                 const double uq = l0 * ux[0] + l1 * ux[1] + l2 * ux[2];
                 const double vq = l0 * uy[0] + l1 * uy[1] + l2 * uy[2];
-                const double bq = l0 * b[0] + l1 * b[1] + l2 * b[2];
-                double Hq = bq;
-                if (NONLIN) Hq = wd_depth(bq + l0 * et[0] + l1 * et[1] + l2 * et[2], wd_on, a2);
+                double Hq = l0 * hl[0] + l1 * hl[1] + l2 * hl[2];
+                if (NONLIN) Hq = wd_depth(Hq, wd_on, a2);
                 double sx = 0, sy = 0;   // momentum source density at the point
-                if (prm.man.mode || prm.cd.mode) {
-                    double cdq;
-                    if (prm.man.mode) {
+                if (has_man || has_cd) {
+                    const double s2 = uq * uq + vq * vq + prm.eps2;
+                    const double umag = s2 > 0.0 ? s2 * tb_rsqrt(s2) : 0.0;
+                    double k;
+                    if (has_man) {
                         const double m = l0 * mu[0] + l1 * mu[1] + l2 * mu[2];
-                        cdq = g * m * m * rcbrt(Hq);              // g mu^2 / H^(1/3)
+                        const double r = tb_rcbrt(Hq);             // H^(-1/3)
+                        const double r2 = r * r;
+                        k = g * m * m * (r2 * r2) * umag;          // g mu^2 / H^(1/3) * |u| / H
                     } else {
-                        cdq = l0 * cdn[0] + l1 * cdn[1] + l2 * cdn[2];
+                        k = (l0 * cdn[0] + l1 * cdn[1] + l2 * cdn[2]) * umag * tb_rcp(Hq);
                     }
-                    const double k = cdq * sqrt(uq * uq + vq * vq + prm.eps2) / Hq;
                     sx -= k * uq;
                     sy -= k * vq;
                 }
-                if (prm.wind.mode) {
-                    const double k = irho / Hq;
-                    sx += k * (l0 * wx[0] + l1 * wx[1] + l2 * wx[2]);
-                    sy += k * (l0 * wy[0] + l1 * wy[1] + l2 * wy[2]);
+                if (has_wind) {
+                    const double k = irho * tb_rcp(Hq);
+                    sx += k * (l0 * twx[0] + l1 * twx[1] + l2 * twx[2]);
+                    sy += k * (l0 * twy[0] + l1 * twy[1] + l2 * twy[2]);
                 }
                 sx *= w;
                 sy *= w;
@@ -377,7 +519,7 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
             const int p = (i + 1) % 3, q = (i + 2) % 3;
             const double nxs = Nx[i], nys = Ny[i];
             const double len2 = nxs * nxs + nys * nys;
-            const double il = rsqrt(len2);
+            const double il = tb_rsqrt(len2);
             const double len = len2 * il;
             const int code = cn[i];
             // flux accumulators tested against phi_p and phi_q
@@ -399,7 +541,7 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
                     double hbar;
                     if (NONLIN) hbar = 0.5 * (wd_depth(bg + eK, wd_on, a2) + wd_depth(bg + eN, wd_on, a2));
                     else hbar = bg;
-                    const double c = sqrt(g * hbar);
+                    const double c = tb_sqrt(g * hbar);
                     const double dux = uKx - uNx, duy = uKy - uNy;
                     const double dun = dux * nxs + duy * nys;
                     // PG (:363-366): g*(avg(eta) + sqrt(h/g)*jump(u,n)) n
@@ -414,7 +556,7 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
                         const double uKN = uKx * nxs + uKy * nys;
                         fx += 0.5 * usx * uKN;
                         fy += 0.5 * usy * uKN;
-                        if (prm.lf_on) {
+                        if (lf_on) {
                             const double gam = 0.25 * fabs(usN) * prm.lf_sigma;
                             fx += gam * dux;
                             fy += gam * duy;
@@ -426,64 +568,31 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
             } else {
                 const int gb = -(code + 1);
                 const int slot = __ldg(prm.bc.bf_slot + gb);
-                const TbBcSlot &bs = prm.bc.slots[slot];
-                const int op = bs.opcode;
-#pragma unroll
+                const int op = prm.bc.slots[slot].opcode;
+                const bool closed = (op & (TB_BC_ELEV | TB_BC_UV | TB_BC_UN | TB_BC_FLUX)) == 0;
+#pragma unroll 1
                 for (int gp = 0; gp < 2; ++gp) {
                     const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
                     const double uKx = wp_ * ux[p] + wq_ * ux[q], uKy = wp_ * uy[p] + wq_ * uy[q];
                     const double eK = wp_ * et[p] + wq_ * et[q];
                     const double bg = wp_ * b[p] + wq_ * b[q];
                     const double HK = NONLIN ? wd_depth(bg + eK, wd_on, a2) : bg;
-                    const double uKN = uKx * nxs + uKy * nys;
-                    double fx, fy, fe = 0.0;
-                    if ((op & (TB_BC_ELEV | TB_BC_UV | TB_BC_UN | TB_BC_FLUX)) == 0) {
+                    double fl[3];
+                    if (closed) {
                         // land boundary (:376-381), mirror-velocity Lax-Friedrichs (:489-497)
-                        const double c = sqrt(g * HK);
+                        const double uKN = uKx * nxs + uKy * nys;
+                        const double c = tb_sqrt(g * HK);
                         double t = g * eK + c * uKN * il;
-                        if (NONLIN && prm.lf_on) t += prm.lf_sigma * fabs(uKN) * uKN * il * il;
-                        fx = t * nxs;
-                        fy = t * nys;
+                        if (NONLIN && lf_on) t += prm.lf_sigma * fabs(uKN) * uKN * il * il;
+                        fl[0] = t * nxs;
+                        fl[1] = t * nys;
+                        fl[2] = 0.0;
                     } else {
-                        double elev = bs.elev, uvx = bs.uvx, uvy = bs.uvy, un = bs.un, flux = bs.flux;
-                        if (bs.arr_mask & TB_BC_ELEV)
-                            elev = wp_ * __ldg(prm.bc.ext_elev + 2 * gb) + wq_ * __ldg(prm.bc.ext_elev + 2 * gb + 1);
-                        if (bs.arr_mask & TB_BC_UV) {
-                            uvx = wp_ * __ldg(prm.bc.ext_uv + 4 * gb) + wq_ * __ldg(prm.bc.ext_uv + 4 * gb + 2);
-                            uvy = wp_ * __ldg(prm.bc.ext_uv + 4 * gb + 1) + wq_ * __ldg(prm.bc.ext_uv + 4 * gb + 3);
-                        }
-                        if (bs.arr_mask & TB_BC_UN)
-                            un = wp_ * __ldg(prm.bc.ext_un + 2 * gb) + wq_ * __ldg(prm.bc.ext_un + 2 * gb + 1);
-                        if (bs.arr_mask & TB_BC_FLUX)
-                            flux = wp_ * __ldg(prm.bc.ext_flux + 2 * gb) + wq_ * __ldg(prm.bc.ext_flux + 2 * gb + 1);
-                        const BcExt ex = bc_external<NONLIN>(op, eK, uKx, uKy, bg, elev, uvx, uvy, un, flux, bs.bnd_len,
-                                                             nxs, nys, il, wd_on, a2);
-                        // PG (:370-375)
-                        const double dun = (uKx - ex.ux) * nxs + (uKy - ex.uy) * nys;   // un_jump*len
-                        const double cK = sqrt(g * HK);
-                        const double t = 0.5 * g * (eK + ex.eta) + cK * dun * il;
-                        fx = t * nxs;
-                        fy = t * nys;
-                        // HUDiv (:431-442)
-                        const double Hext = NONLIN ? wd_depth(bg + ex.eta, wd_on, a2) : bg;
-                        const double hav = 0.5 * (HK + Hext);
-                        const double cav = sqrt(g * hav);
-                        const double usx = uKx + ex.ux, usy = uKy + ex.uy;
-                        const double usN = usx * nxs + usy * nys;
-                        const double ejump = eK - ex.eta;
-                        const double un_rie_len = 0.5 * usN + (cav / hav) * ejump * len;
-                        const double eta_rie = 0.5 * (eK + ex.eta) + (cav / g) * dun * il;
-                        const double h_rie = NONLIN ? wd_depth(bg + eta_rie, wd_on, a2) : bg;
-                        fe = h_rie * un_rie_len;
-                        if (NONLIN) {
-                            // advection (:498-509)
-                            const double un_a_len = 0.5 * usN + (cK / HK) * ejump * len;
-                            fx += 0.5 * usx * un_a_len;
-                            fy += 0.5 * usy * un_a_len;
-                        }
+                        open_boundary_flux<NONLIN>(&prm.bc, gb, slot, wp_, wq_, uKx, uKy, eK, bg, HK, nxs, nys, il, len, g,
+                                                   wd_on, a2, fl);
                     }
-                    Fpx += wp_ * fx; Fpy += wp_ * fy; Fpe += wp_ * fe;
-                    Fqx += wq_ * fx; Fqy += wq_ * fy; Fqe += wq_ * fe;
+                    Fpx += wp_ * fl[0]; Fpy += wp_ * fl[1]; Fpe += wp_ * fl[2];
+                    Fqx += wq_ * fl[0]; Fqy += wq_ * fl[1]; Fqe += wq_ * fl[2];
                 }
             }
             Rux[p] -= 0.5 * Fpx; Ruy[p] -= 0.5 * Fpy; Re[p] -= 0.5 * Fpe;
@@ -492,7 +601,7 @@ __global__ void __launch_bounds__(TB_P) swe_stage_kernel(const __grid_constant__
 
         // ---------------- P1 mass inverse (equation.py:99-105) and Shu-Osher update ----------------
         // M_K^-1 = (3/A)(4 I - 1 1^T)
-        const double mi = 6.0 / twoA * prm.bdt;
+        const double mi = 6.0 * tb_rcp(twoA) * prm.bdt;
         const double sRx = Rux[0] + Rux[1] + Rux[2], sRy = Ruy[0] + Ruy[1] + Ruy[2], sRe = Re[0] + Re[1] + Re[2];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -519,20 +628,44 @@ size_t tb_swe_smem_bytes(const TbPatchLayout &pl) {
     return 16 + (size_t)(TB_P + pl.NH) * 72 + (size_t)TB_P * 72 + (size_t)pl.stride;
 }
 
+template <bool NL, int SPEC>
+static cudaError_t stage_attr() {
+    return cudaFuncSetAttribute(swe_stage_kernel<NL, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 cudaError_t tb_kernels_init() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(swe_stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(swe_stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    return e;
+    if ((e = stage_attr<true, 0>()) != cudaSuccess) return e;
+    if ((e = stage_attr<true, 1>()) != cudaSuccess) return e;
+    if ((e = stage_attr<true, 2>()) != cudaSuccess) return e;
+    if ((e = stage_attr<true, 3>()) != cudaSuccess) return e;
+    if ((e = stage_attr<false, 0>()) != cudaSuccess) return e;
+    return stage_attr<false, 1>();
+}
+
+// which specialisation serves this parameter set (0 = generic)
+int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear) {
+    const bool extras = p.cd.mode || p.lin.mode || p.wind.mode || p.pa.mode == 2 || p.msrc.mode || p.vsrc.mode;
+    if (extras) return 0;
+    if (!p.man.mode && !p.cor.mode && !p.wd_on && (!nonlinear || p.lf_on)) return 1;
+    if (nonlinear && p.lf_on && p.man.mode && p.cor.mode && p.nquad == 6) return p.wd_on ? 3 : 2;
+    return 0;
 }
 
 cudaError_t tb_launch_swe_stage(const TbSweParams &p, bool nonlinear, int n_patches, size_t smem, cudaStream_t s) {
     if (n_patches <= 0) return cudaSuccess;
-    if (nonlinear)
-        swe_stage_kernel<true><<<n_patches, TB_P, smem, s>>>(p);
-    else
-        swe_stage_kernel<false><<<n_patches, TB_P, smem, s>>>(p);
+    const int spec = p.force_generic ? 0 : tb_swe_stage_spec(p, nonlinear);
+    if (nonlinear) {
+        switch (spec) {
+            case 1: swe_stage_kernel<true, 1><<<n_patches, TB_P, smem, s>>>(p); break;
+            case 2: swe_stage_kernel<true, 2><<<n_patches, TB_P, smem, s>>>(p); break;
+            case 3: swe_stage_kernel<true, 3><<<n_patches, TB_P, smem, s>>>(p); break;
+            default: swe_stage_kernel<true, 0><<<n_patches, TB_P, smem, s>>>(p); break;
+        }
+    } else {
+        if (spec == 1) swe_stage_kernel<false, 1><<<n_patches, TB_P, smem, s>>>(p);
+        else swe_stage_kernel<false, 0><<<n_patches, TB_P, smem, s>>>(p);
+    }
     return cudaGetLastError();
 }
 
