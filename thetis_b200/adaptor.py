@@ -181,8 +181,11 @@ class MeshAdaptor:
             raise NotImplementedError("discontinuous coefficient fields are not supported on the accelerated path")
         return vert
 
-    def bfacet_values(self, func):
-        """(nb, 2[,k]) values of a P1/P1DG Function at the two nodes of every exterior facet."""
+    def bfacet_values(self, func, marker=None):
+        """
+        (nb, 2[,k]) values of a P1/P1DG Function at the two nodes of every exterior facet.  With ``marker`` only
+        the rows of that marker are evaluated (the rest of the returned, reused, buffer is untouched).
+        """
         fs = func.function_space()
         cache = self.__dict__.setdefault("_bf_nodes", {})
         idx = cache.get(id(fs))
@@ -192,7 +195,18 @@ class MeshAdaptor:
             idx = np.stack([cn[m.bf_cell, FACET_NODES[m.bf_lf, 0]], cn[m.bf_cell, FACET_NODES[m.bf_lf, 1]]], axis=1)
             cache[id(fs)] = idx
             self.__dict__.setdefault("_bf_keep", []).append(fs)     # keep the key object alive
-        return np.asarray(func.dat.data_ro)[idx]
+        data = np.asarray(func.dat.data_ro)
+        if marker is None:
+            return data[idx]
+        key = (id(fs), int(marker))
+        ent = cache.get(key)
+        if ent is None:
+            rows = np.nonzero(self.mesh.bf_marker == marker)[0]
+            ent = (rows, idx[rows], np.zeros(idx.shape + data.shape[1:]))
+            cache[key] = ent
+        rows, ridx, out = ent
+        out[rows] = data[ridx]
+        return out
 
 
 _ADAPTORS = weakref.WeakKeyDictionary()

@@ -55,6 +55,8 @@ struct tb_ctx {
     size_t h_pinned_bytes[NSTAGE] = {0};
     cudaEvent_t h_event[NSTAGE] = {nullptr};
     int h_next = 0;
+    std::vector<double> h_mirror[2][5];
+    std::vector<long long> slot_first, slot_last;
     // layout
     TbPatchLayout pl{};
     bool layout_dirty = true;
@@ -514,32 +516,42 @@ extern "C" int tb_set_bc_array(tb_ctx *ctx, int eq, int marker, int tag, const d
         CK(cudaMalloc(&slot_arr[k], sizeof(double) * std::max<size_t>(n, 2)));
         CK(cudaMemset(slot_arr[k], 0, sizeof(double) * std::max<size_t>(n, 2)));
     }
-    // stage only this marker's entries through pinned memory so several markers can hold arrays
+    // Host mirror of the whole per-tag array: merge this marker's entries, then ship the marker's facet range
+    // [first, last] with ONE async copy from a pinned ring slot (entries of other markers inside the range are
+    // re-sent unchanged from the mirror, so several markers can hold arrays of the same tag).
+    std::vector<double> &mir = ctx->h_mirror[eq][k];
+    if (mir.size() != std::max<size_t>(n, 2)) mir.assign(std::max<size_t>(n, 2), 0.0);
+    const size_t w = 2 * (size_t)nc;
+    long long first = -1, last = -1;
+    if (ctx->slot_first.empty()) {
+        ctx->slot_first.assign(TB_MAX_SLOTS, -1);
+        ctx->slot_last.assign(TB_MAX_SLOTS, -1);
+        for (long long f = 0; f < ctx->n_bfacets; ++f) {
+            const int sl = ctx->bf_slot[f];
+            if (ctx->slot_first[sl] < 0) ctx->slot_first[sl] = f;
+            ctx->slot_last[sl] = f;
+        }
+    }
+    first = ctx->slot_first[s];
+    last = ctx->slot_last[s];
+    if (first < 0) return TB_OK;
+    for (long long f = first; f <= last; ++f)
+        if (ctx->bf_slot[f] == s) memcpy(&mir[f * w], values + f * w, sizeof(double) * w);
     const int slot = ctx->h_next;
     ctx->h_next = (ctx->h_next + 1) % tb_ctx::NSTAGE;
     if (!ctx->h_event[slot]) CK(cudaEventCreateWithFlags(&ctx->h_event[slot], cudaEventDisableTiming));
     else CK(cudaEventSynchronize(ctx->h_event[slot]));      // copy issued NSTAGE calls ago has finished
-    if (ctx->h_pinned_bytes[slot] < n * sizeof(double)) {
+    const size_t bytes = sizeof(double) * w * (size_t)(last - first + 1);
+    if (ctx->h_pinned_bytes[slot] < bytes) {
         if (ctx->h_pinned[slot]) cudaFreeHost(ctx->h_pinned[slot]);
         ctx->h_pinned[slot] = nullptr;
-        CK(cudaMallocHost(&ctx->h_pinned[slot], n * sizeof(double)));
-        ctx->h_pinned_bytes[slot] = n * sizeof(double);
+        CK(cudaMallocHost(&ctx->h_pinned[slot], bytes));
+        ctx->h_pinned_bytes[slot] = bytes;
     }
     double *hp = ctx->h_pinned[slot];
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t w = 2 * (size_t)nc;
-    // copy contiguous runs of facets belonging to this marker
-    long long k0 = -1;
-    for (long long f = 0; f <= ctx->n_bfacets; ++f) {
-        const bool mine = f < ctx->n_bfacets && ctx->bf_slot[f] == s;
-        if (mine && k0 < 0) k0 = f;
-        if (!mine && k0 >= 0) {
-            memcpy(hp + k0 * w, values + k0 * w, sizeof(double) * w * (f - k0));
-            CK(cudaMemcpyAsync(slot_arr[k] + k0 * w, hp + k0 * w, sizeof(double) * w * (f - k0),
-                               cudaMemcpyHostToDevice, st));
-            k0 = -1;
-        }
-    }
+    memcpy(hp, &mir[first * w], bytes);
+    CK(cudaMemcpyAsync(slot_arr[k] + first * w, hp, bytes, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->h_event[slot], st));
     ctx->bc[eq][s].arr_mask |= tag;
     return TB_OK;

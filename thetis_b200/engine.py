@@ -72,6 +72,7 @@ class Engine:
         self.n_owned_pad = self.n_patches * self.patch_size
         for m, ln in mesh.boundary_length().items():
             self.set_boundary_length(m, ln)
+        self._opt_cache = {}
         self.swe_stepper = None      # set by the SWE integrator so tracer integrators can find the live state
         self._identity_map = None
 
@@ -94,7 +95,11 @@ class Engine:
 
     # ------------------------------------------------------------ configuration
     def set_option(self, opt, value):
-        self._ck(self.lib.tb_set_option(self.ctx, opt, float(value)))
+        value = float(value)
+        if self._opt_cache.get(opt) == value:      # options are re-read every stage; only changes reach the library
+            return
+        self._ck(self.lib.tb_set_option(self.ctx, opt, value))
+        self._opt_cache[opt] = value
 
     def set_field(self, field, value):
         """value: None | scalar/sequence (Constant) | ndarray over geometric vertices (nv,) / (nv, 2)."""

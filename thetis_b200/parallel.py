@@ -296,6 +296,9 @@ class PartitionedSWE:
         self._norms = torch.zeros(4, dtype=torch.float64, device=dev)
         self._norms_host = torch.zeros(4, dtype=torch.float64).pin_memory()
         self._L = L
+        from .rungekutta import SSPRK33, butcher_to_shuosher_form
+        self._alpha, self._beta = butcher_to_shuosher_form(SSPRK33.a, SSPRK33.b)
+        self._c = [float(v) for v in SSPRK33.c]
 
     def _exchange(self, state):
         eng, p = self.eng, self.part
@@ -311,16 +314,16 @@ class PartitionedSWE:
     def _step(self, forcing=None):
         A, B, C = self.buf
         dt = self.dt
-        c = (0.0, 1.0, 0.5)
+        al, be, c = self._alpha, self._beta, self._c      # the reference's own Shu-Osher coefficients
         if forcing:
             forcing(self.t + c[0] * dt)
-        self._stage(0.0, 1.0, dt, A, None, B)
+        self._stage(0.0, float(al[1][0]), float(be[1][0]) * dt, A, None, B)
         if forcing:
             forcing(self.t + c[1] * dt)
-        self._stage(0.75, 0.25, 0.25 * dt, B, A, C)
+        self._stage(float(al[2][0]), float(al[2][1]), float(be[2][1]) * dt, B, A, C)
         if forcing:
             forcing(self.t + c[2] * dt)
-        self._stage(1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0 * dt, C, A, A)
+        self._stage(float(al[3][0]), float(al[3][2]), float(be[3][2]) * dt, C, A, A)
 
     def update_forcings(self, t):
         if self._has_open:

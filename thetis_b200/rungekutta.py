@@ -313,7 +313,7 @@ class ERKGenericShuOsher:
                 akey = (eq, marker, tag)
                 astamp = (id(val), ver)
                 if ver is None or self._bc_versions.get(akey) != astamp:
-                    eng.set_bc_array(eq, marker, tags[tag], self.adaptor.bfacet_values(val))
+                    eng.set_bc_array(eq, marker, tags[tag], self.adaptor.bfacet_values(val, marker))
                     self._bc_versions[akey] = astamp
 
     # ------------------------------------------------------------------ host <-> device
