@@ -1,0 +1,183 @@
+"""CPU-only tests of the host side: C-ABI exports, mesh toolkit, shim/adaptor maps, option mirrors, install()."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+
+from thetis_b200 import mesh as M
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- C-ABI
+def test_library_exports_every_declared_symbol():
+    """the shared library must load and export every function include/thetis_b200.h declares (no compute calls)"""
+    from thetis_b200.build import build_library
+    from thetis_b200 import _lib
+    lib_path = build_library()
+    hdr = open(os.path.join(ROOT, "include", "thetis_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(tb_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().tb_version() == 100
+
+
+def test_create_fails_loudly_without_gpu_or_with_bad_mesh():
+    import torch
+    from thetis_b200 import _lib
+    lib = _lib.load()
+    ctx = ctypes.c_void_p()
+    tm = _lib.TbMesh()
+    rc = lib.tb_create(ctypes.byref(ctx), ctypes.byref(tm), 0)
+    assert rc != 0 and not ctx.value
+    assert lib.tb_last_error(None)
+    if not torch.cuda.is_available():
+        from thetis_b200.engine import Engine
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            Engine(M.rectangle_mesh(2, 2, 1.0, 1.0))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "thetis_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in re.sub(r"#.*|//.*", "", src).replace("swe_oracle.py", ""), f
+
+
+# ---------------------------------------------------------------- mesh toolkit
+def test_rectangle_mesh_conventions():
+    m = M.rectangle_mesh(25, 2, 40e3, 2e3)
+    assert m.n_cells == 100 and m.n_vertices == 78 and m.n_bfacets == 54
+    assert m.boundary_length() == {1: 2000.0, 2: 2000.0, 3: 40000.0, 4: 40000.0}
+    assert np.all(m.cell_area() > 0) and abs(m.cell_area().sum() - 8e7) < 1e-6
+    c, f, n, g = m.interior_facets()
+    tv = m.topo[m.cells]
+    assert np.array_equal(tv[c, M.FACET_NODES[f, 0]], tv[n, M.FACET_NODES[g, 1]])     # crosswise node matching
+    assert np.array_equal(tv[c, M.FACET_NODES[f, 1]], tv[n, M.FACET_NODES[g, 0]])
+    assert 3 * m.n_cells == 2 * len(c) + m.n_bfacets
+
+
+def test_periodic_mesh_and_sfc_renumbering_keep_topology():
+    p = M.periodic_rectangle_mesh(8, 4, 8.0, 4.0)
+    assert p.n_topo_vertices == 8 * 5 and p.unique_markers() == [1, 2] and p.n_bfacets == 16
+    s = M.sfc_renumber(p)
+    assert sorted(s.cell_perm.tolist()) == list(range(p.n_cells))
+    assert np.allclose(np.sort(s.cell_area()), np.sort(p.cell_area()))
+    c, f, n, g = s.interior_facets()
+    tv = s.topo[s.cells]
+    assert np.array_equal(tv[c, M.FACET_NODES[f, 0]], tv[n, M.FACET_NODES[g, 1]])
+    q = M.sfc_renumber(M.rectangle_mesh(9, 7, 3.0, 2.0))
+    assert np.array_equal(q.topo, np.arange(q.n_vertices))          # identity for non-periodic meshes
+
+
+def test_gmsh_reader_refinement_and_npz_fixture():
+    g = M.read_gmsh(os.path.join(ROOT, "tests", "golden", "mini_tagged.msh"))
+    assert g.n_cells == 360 and sorted(np.unique(g.bf_marker)) == [100, 200]
+    r = M.refine_uniform(g, 3)
+    assert r.n_cells == 9 * g.n_cells and r.n_bfacets == 3 * g.n_bfacets
+    assert abs(r.cell_area().sum() - g.cell_area().sum()) < 1e-9 * g.cell_area().sum()
+    bl_g, bl_r = g.boundary_length(), r.boundary_length()
+    for k in bl_g:
+        assert abs(bl_g[k] - bl_r[k]) < 1e-9 * bl_g[k]
+    ns = M.load_npz_mesh(os.path.join(ROOT, "tests", "golden", "north_sea_mesh.npz"))
+    assert ns.n_cells == 10920 and ns.n_vertices == 6565                      # demos/north_sea.msh
+    mk, cnt = np.unique(ns.bf_marker, return_counts=True)
+    assert dict(zip(mk.tolist(), cnt.tolist())) == {100: 111, 200: 2169}
+
+
+def test_empty_and_ragged_inputs():
+    with pytest.raises(ValueError):
+        M.periodic_rectangle_mesh(2, 2, 1.0, 1.0)
+    one = M.rectangle_mesh(1, 1, 1.0, 1.0)                                    # 2 triangles: ragged single patch
+    assert one.n_cells == 2 and one.n_bfacets == 4
+
+
+# ---------------------------------------------------------------- shim / adaptor
+def test_adaptor_node_maps_and_vertex_values():
+    from thetis_b200.shim import Function, FunctionSpace, as_shim_mesh
+    from thetis_b200.adaptor import MeshAdaptor
+    base = M.rectangle_mesh(6, 5, 3.0, 2.0)
+    sm = as_shim_mesh(base)
+    ad = MeshAdaptor(sm)
+    assert ad.mesh.meta.get("sfc") and sorted(ad.perm.tolist()) == list(range(base.n_cells))
+    dg = FunctionSpace(sm, "DG", 1)
+    nm = ad.dg_node_map(dg)
+    assert np.array_equal(nm, (3 * ad.perm[:, None] + np.arange(3)).astype(np.int32))
+    cg = Function(FunctionSpace(sm, "CG", 1)).interpolate(lambda x, y: 2 * x - y)
+    vv = ad.vertex_values(cg)
+    assert np.allclose(vv, 2 * ad.mesh.coords[:, 0] - ad.mesh.coords[:, 1])
+    f_dg = Function(dg).interpolate(lambda x, y: x * y)
+    assert np.allclose(ad.vertex_values(f_dg), ad.mesh.coords[:, 0] * ad.mesh.coords[:, 1])
+    shared = np.bincount(base.cells.reshape(-1))[base.cells.reshape(-1)] > 1
+    f_dg.dat.data[np.nonzero(shared)[0][0]] += 1.0                            # make it discontinuous at a shared vertex
+    with pytest.raises(NotImplementedError):
+        ad.vertex_values(f_dg)
+    bv = ad.bfacet_values(cg, marker=1)
+    rows = ad.mesh.bf_marker == 1
+    p = ad.mesh.coords[ad.mesh.cells[ad.mesh.bf_cell[rows], M.FACET_NODES[ad.mesh.bf_lf[rows], 0]]]
+    assert np.allclose(bv[rows, 0], 2 * p[:, 0] - p[:, 1])
+    with pytest.raises(NotImplementedError):
+        ad.dg_node_map(FunctionSpace(sm, "CG", 1))
+
+
+def test_constants_are_read_live():
+    from thetis_b200.shim import Constant
+    from thetis_b200.adaptor import is_constant, constant_value
+    c = Constant(9.81)
+    assert is_constant(c) and float(constant_value(c)[0]) == 9.81
+    c.assign(1.0)
+    assert float(constant_value(c)[0]) == 1.0 and float(c) == 1.0
+    v = Constant((0.0, 0.5))
+    assert constant_value(v).tolist() == [0.0, 0.5] and is_constant((1.0, 2.0)) and not is_constant("elev")
+
+
+def test_options_mirror_defaults_match_reference():
+    """defaults of thetis/options.py:583-733, 838-949 that the path reads"""
+    from thetis_b200.options import ModelOptions2d
+    o = ModelOptions2d()
+    assert o.element_family == "dg-dg" and o.polynomial_degree == 1
+    assert o.use_nonlinear_equations and o.use_lax_friedrichs_velocity and not o.use_lax_friedrichs_tracer
+    assert o.use_limiter_for_tracers and not o.use_wetting_and_drying
+    assert float(o.lax_friedrichs_velocity_scaling_factor) == 1.0 and float(o.norm_smoother) == 0.0
+    assert float(o.horizontal_velocity_scale) == 0.1 and o.cfl_2d == 1.0 and o.timestep == 10.0
+    assert float(o.wetting_and_drying_alpha) == 0.5 and float(o.tracer_advective_velocity_factor) == 1.0
+    assert o.swe_timestepper_options.use_automatic_timestep                     # options.py:26
+    o.add_tracer_2d("tracer_2d", "Depth averaged tracer", "Tracer2d")
+    assert "tracer_2d" in o.tracer and "tracer_2d" in o.tracer_fields
+    with pytest.raises(AttributeError):
+        o.update({"no_such_option": 1})
+
+
+def test_automatic_timestep_rule():
+    """solver2d.py:150-177,214-241: dt = cfl_2d * 0.05 * min P1-projection of h_elem / (sqrt(g max(b,0.05)) + U)"""
+    from thetis_b200 import solver2d
+    from thetis_b200.shim import Function, FunctionSpace, as_shim_mesh
+    sm = as_shim_mesh(M.rectangle_mesh(10, 10, 1000.0, 1000.0))
+    b = Function(FunctionSpace(sm, "CG", 1)).assign(10.0)
+    s = solver2d.FlowSolver2d(sm, b)
+    s.create_function_spaces()
+    s.create_fields()
+    s.set_time_step()
+    h = np.sqrt(0.5 * 100.0 * 100.0)                          # sqrt(cell area), uniform mesh => projection is exact
+    assert abs(s.dt - 0.05 * h / (np.sqrt(9.81 * 10.0) + 0.1)) < 1e-10
+
+
+def test_install_rebinds_reference_attributes():
+    import thetis_b200
+    fake = types.SimpleNamespace(rungekutta=types.SimpleNamespace(SSPRK33=object),
+                                 limiter=types.SimpleNamespace(VertexBasedP1DGLimiter=object))
+    cls = thetis_b200.install(fake, sync_policy="manual")
+    from thetis_b200.rungekutta import SSPRK33
+    from thetis_b200.limiter import VertexBasedP1DGLimiter
+    assert issubclass(fake.rungekutta.SSPRK33, SSPRK33) and cls is fake.rungekutta.SSPRK33
+    assert fake.limiter.VertexBasedP1DGLimiter is VertexBasedP1DGLimiter
+    assert SSPRK33.cfl_coeff == 1.0 and len(SSPRK33.b) == 3

@@ -14,11 +14,17 @@ def install(thetis_module=None, sync_policy="every_step"):
     implementations so that FlowSolver2d.create_timestepper() picks them up (the `steppers` dict is built from
     module attributes at call time, thetis/solver2d.py:662-672).  See INTEGRATION.md.
     """
-    import functools
     from . import rungekutta as rk, limiter as lim
     if thetis_module is None:
         import thetis as thetis_module          # raises ImportError without a Thetis/Firedrake install
-    cls = type("SSPRK33", (rk.SSPRK33,), {"__init__": functools.partialmethod(rk.SSPRK33.__init__, sync_policy=sync_policy)})
+    policy = sync_policy
+
+    class SSPRK33(rk.SSPRK33):
+        def __init__(self, equation, solution, fields, dt, options=None, bnd_conditions=None, terms_to_add="all"):
+            super().__init__(equation, solution, fields, dt, options, bnd_conditions, terms_to_add,
+                             sync_policy=policy)
+
+    cls = SSPRK33
     thetis_module.rungekutta.SSPRK33 = cls
     thetis_module.limiter.VertexBasedP1DGLimiter = lim.VertexBasedP1DGLimiter
     return cls
