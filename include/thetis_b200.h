@@ -183,6 +183,10 @@ int tb_scatter_cells(tb_ctx *ctx, const double *buf, const int32_t *idx, int64_t
  * count < 0 resets to all patches. */
 int tb_set_patch_range(tb_ctx *ctx, int64_t first, int64_t count);
 
+/* Diagnostics: evaluates the kernels' fp64 helpers on DEVICE x[n]: out[0:n] = x^-1/2, out[n:2n] = sqrt(x),
+ * out[2n:3n] = 1/x, out[3n:4n] = x^-1/3 (accuracy is asserted in tests/test_gpu_math.py). */
+int tb_selftest_math(tb_ctx *ctx, const double *x, double *out, int64_t n, void *stream);
+
 /* launches issued by this library so far (bench.py's gpu_launches) */
 int64_t tb_launch_count(const tb_ctx *ctx);
 

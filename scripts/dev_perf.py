@@ -19,7 +19,7 @@ if not a.nosfc:
     m = sfc_renumber(m)
 print("mesh", m.n_cells, "cells", time.time() - t0, "s", flush=True)
 eng = Engine(m)
-print("patches", eng.n_patches, "state MB", eng.state_len * 8 / 1e6, flush=True)
+print("patches", eng.n_patches, "state MB", eng.state_len * 8 / 1e6, "smem", eng.lib.tb_patch_size(eng.ctx), flush=True)
 X, Y = m.coords[:, 0], m.coords[:, 1]
 bath = 40.0 + 30.0 * np.sin(X / 2.0e5) * np.cos(Y / 1.5e5)
 eng.set_field(L.F_BATHYMETRY, bath)

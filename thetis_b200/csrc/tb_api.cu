@@ -809,6 +809,12 @@ extern "C" int tb_set_patch_range(tb_ctx *ctx, int64_t first, int64_t count) {
     return TB_OK;
 }
 
+extern "C" int tb_selftest_math(tb_ctx *ctx, const double *x, double *out, int64_t n, void *stream) {
+    if (!ctx || !x || !out) return fail(ctx, TB_ERR_ARG, "null pointer");
+    CK(tb_launch_test_math(x, out, (int)n, (cudaStream_t)stream));
+    return TB_OK;
+}
+
 extern "C" int tb_set_cell_quadrature(tb_ctx *ctx, int n, const double *lam, const double *w) {
     if (!ctx || !lam || !w || n < 1 || n > TB_MAX_QUAD) return fail(ctx, TB_ERR_ARG, "bad quadrature rule");
     CK(cudaDeviceSynchronize());

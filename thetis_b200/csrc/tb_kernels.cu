@@ -15,6 +15,12 @@
 // Arithmetic follows thetis/shallowwater_eq.py (line refs at each term).
 #include "tb_internal.h"
 
+#ifndef TB_HALO_SPEC
+#define TB_HALO_SPEC 6        // halo elements per thread fetched speculatively (covers NH <= 85)
+#endif
+#ifndef TB_PREFETCH_DIST
+#define TB_PREFETCH_DIST 592   // patches ahead to warm in L2: one wave of 148 SMs x 4 CTAs
+#endif
 #ifndef TB_MINB
 #define TB_MINB 4      // resident CTAs per SM the stage kernel is compiled for (register budget)
 #endif
@@ -74,34 +80,47 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------ fp64 math helpers
-// MUFU seed + two Newton steps, branch-free, ~1 ulp (checked in tests/test_gpu_math.py).  The CUDA library
-// versions of sqrt / division / rcbrt carry slow-path subroutine calls that cost more fp64-pipe and issue
-// slots than the whole facet flux; arguments here are depths, lengths and areas (normal, positive).
+// MUFU / fp32 seed (>= 21 good bits) + ONE third-order (Halley-type) correction: with e = 1 - x*y0^k,
+//   x^(-1/2) = y0 (1 + e/2 + 3e^2/8 + O(e^3)),  x^(-1) = y0 (1 + e + e^2 + O(e^3)),  x^(-1/3) = y0 (1 + e/3 + 2e^2/9 + O(e^3));
+// the dropped e^3 term is < 2^-60, so results are good to ~1 ulp (tests/test_gpu_math.py), branch-free, all FMAs.
+// The CUDA library sqrt / division / rcbrt carry slow-path subroutine calls that cost more fp64-pipe and issue
+// slots than the whole facet flux.  Arguments here are depths, lengths and areas (normal, positive).
 __device__ __forceinline__ double tb_rsqrt(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double xy = x * y;
-    double r = fma(-xy, y, 1.0);
-    y = fma(0.5 * y, r, y);
-    xy = x * y;
-    r = fma(-xy, y, 1.0);
-    return fma(0.5 * y, r, y);
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
 }
-__device__ __forceinline__ double tb_sqrt(double x) { return x * tb_rsqrt(x); }   // x > 0
+__device__ __forceinline__ double tb_sqrt(double x) {   // x > 0
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double g = x * y;
+    const double e = fma(-g, y, 1.0);
+    return fma(g * e, fma(0.375, e, 0.5), g);
+}
 __device__ __forceinline__ double tb_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double r = fma(-x, y, 1.0);
-    y = fma(y, r, y);
-    r = fma(-x, y, 1.0);
-    return fma(y, r, y);
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
 }
 __device__ __forceinline__ double tb_rcbrt(double x) {   // x^(-1/3), x > 0 within float range
-    double y = (double)rcbrtf((float)x);
-    double r = fma(-x * y, y * y, 1.0);
-    y = fma(y * (1.0 / 3.0), r, y);
-    r = fma(-x * y, y * y, 1.0);
-    return fma(y * (1.0 / 3.0), r, y);
+    const double y = (double)rcbrtf((float)x);
+    const double e = fma(-(x * y), y * y, 1.0);
+    return fma(y * e, fma(2.0 / 9.0, e, 1.0 / 3.0), y);
+}
+
+__global__ void test_math_kernel(const double *x, double *out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = tb_rsqrt(x[i]);
+    out[n + i] = tb_sqrt(x[i]);
+    out[2 * n + i] = tb_rcp(x[i]);
+    out[3 * n + i] = tb_rcbrt(x[i]);
+}
+cudaError_t tb_launch_test_math(const double *x, double *out, int n, cudaStream_t s) {
+    if (n > 0) test_math_kernel<<<(n + 255) / 256, 256, 0, s>>>(x, out, n);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ small helpers
@@ -173,6 +192,9 @@ struct StageSpec {
 __device__ __forceinline__ void cp_async8(void *sdst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -237,45 +259,54 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
     const long long cell0 = (long long)patch * TB_P;
     const int NV = prm.pl.NV;
 
+    // Speculative, mutually independent global loads first (one DRAM latency instead of a chain of three): the halo
+    // count and the ids this thread will need (rows of halo_ids are padded to NH valid entries).
+    const int *hid = prm.pl.halo_ids + (long long)patch * prm.pl.NH;
+    const int NH9 = prm.pl.NH * 9;
+    int hcell[TB_HALO_SPEC];
+#pragma unroll
+    for (int j = 0; j < TB_HALO_SPEC; ++j) {
+        const int i = j * TB_P + tid;
+        hcell[j] = (i < NH9) ? __ldg(hid + i / 9) : 0;
+    }
+    const int nh9 = __ldg(prm.pl.halo_cnt + patch) * 9;
+
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
         const uint32_t sb = (uint32_t)prm.pl.stride;
         const uint32_t rec = TB_P * 9 * sizeof(double);
         mbar_expect_tx(bar, rec + sb + (prm.u0 ? rec : 0u));
         bulk_g2s(S, prm.u_in + cell0 * 9, rec, bar);
         bulk_g2s(blk, prm.pl.sblk + (long long)patch * prm.pl.stride, sb, bar);
         if (prm.u0) bulk_g2s(O, prm.u0 + cell0 * 9, rec, bar);
+    } else if (tid == 32) {
+        // warm L2 for the patch that will run on this SM slot one wave later
+        const int pf = patch + TB_PREFETCH_DIST;
+        if (pf < prm.patch_first + (int)gridDim.x) {
+            const uint32_t rec = TB_P * 9 * sizeof(double);
+            bulk_prefetch_l2(prm.u_in + (long long)pf * TB_P * 9, rec);
+            bulk_prefetch_l2(prm.pl.sblk + (long long)pf * prm.pl.stride, (uint32_t)prm.pl.stride);
+            if (prm.u0) bulk_prefetch_l2(prm.u0 + (long long)pf * TB_P * 9, rec);
+        }
     }
     // patch halo: records of off-patch facet neighbours, copied asynchronously (LDGSTS) while the bulk copies fly.
     // Element i of the halo block is double (i % 9) of halo cell (i / 9): S[TB_P*9 + i].
     {
-        const int nh9 = __ldg(prm.pl.halo_cnt + patch) * 9;
-        const int *hid = prm.pl.halo_ids + (long long)patch * prm.pl.NH;
         double *H = S + TB_P * 9;
-        for (int base = 0; base < nh9; base += 4 * TB_P) {
-            long long gsrc[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = base + j * TB_P + tid;
-                if (i < nh9) {
-                    const int h = i / 9;
-                    gsrc[j] = (long long)__ldg(hid + h) * 9 + (i - h * 9);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = base + j * TB_P + tid;
-                if (i < nh9) cp_async8(H + i, prm.u_in + gsrc[j]);
-            }
+        for (int j = 0; j < TB_HALO_SPEC; ++j) {
+            const int i = j * TB_P + tid;
+            if (i < nh9) cp_async8(H + i, prm.u_in + ((long long)hcell[j] * 9 + (i - (i / 9) * 9)));
+        }
+        for (int i = TB_HALO_SPEC * TB_P + tid; i < nh9; i += TB_P) {      // very large halos only
+            const int h = i / 9;
+            cp_async8(H + i, prm.u_in + ((long long)__ldg(hid + h) * 9 + (i - h * 9)));
         }
         cp_async_wait_all();
     }
-    mbar_wait(bar, 0);
-    __syncthreads();
+    __syncthreads();          // mbarrier initialised (thread 0) before anybody waits on it; halo copies landed
+    mbar_wait(bar, 0);        // every thread observes the TMA completion itself: no second barrier needed
 
     const bool active = (cell0 + tid) < prm.n_owned;
     double res[9];
@@ -529,15 +560,18 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                 const double *nr = S + (code >> 2) * 9;
                 const int np_ = (lf + 2) % 3, nq_ = (lf + 1) % 3;   // neighbour nodes matching p and q
                 const double uNxp = nr[2 * np_], uNyp = nr[2 * np_ + 1], eNp = nr[6 + np_];
-                const double uNxq = nr[2 * nq_], uNyq = nr[2 * nq_ + 1], eNq = nr[6 + nq_];
+                // nodal differences along the facet: trace(xi) = v_p + xi (v_q - v_p)
+                const double dKx = ux[q] - ux[p], dKy = uy[q] - uy[p], dKe = et[q] - et[p], dKb = b[q] - b[p];
+                const double dNx = nr[2 * nq_] - uNxp, dNy = nr[2 * nq_ + 1] - uNyp, dNe = nr[6 + nq_] - eNp;
 #pragma unroll
                 for (int gp = 0; gp < 2; ++gp) {
-                    const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
-                    const double uKx = wp_ * ux[p] + wq_ * ux[q], uKy = wp_ * uy[p] + wq_ * uy[q];
-                    const double eK = wp_ * et[p] + wq_ * et[q];
-                    const double uNx = wp_ * uNxp + wq_ * uNxq, uNy = wp_ * uNyp + wq_ * uNyq;
-                    const double eN = wp_ * eNp + wq_ * eNq;
-                    const double bg = wp_ * b[p] + wq_ * b[q];
+                    const double xi = gp ? TB_XI2 : TB_XI1;
+                    const double hq_ = 0.5 * xi, hp_ = 0.5 - hq_;      // Gauss weight 1/2 folded into the test functions
+                    const double uKx = fma(xi, dKx, ux[p]), uKy = fma(xi, dKy, uy[p]);
+                    const double eK = fma(xi, dKe, et[p]);
+                    const double uNx = fma(xi, dNx, uNxp), uNy = fma(xi, dNy, uNyp);
+                    const double eN = fma(xi, dNe, eNp);
+                    const double bg = fma(xi, dKb, b[p]);
                     double hbar;
                     if (NONLIN) hbar = 0.5 * (wd_depth(bg + eK, wd_on, a2) + wd_depth(bg + eN, wd_on, a2));
                     else hbar = bg;
@@ -562,8 +596,8 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                             fy += gam * duy;
                         }
                     }
-                    Fpx += wp_ * fx; Fpy += wp_ * fy; Fpe += wp_ * fe;
-                    Fqx += wq_ * fx; Fqy += wq_ * fy; Fqe += wq_ * fe;
+                    Fpx += hp_ * fx; Fpy += hp_ * fy; Fpe += hp_ * fe;
+                    Fqx += hq_ * fx; Fqy += hq_ * fy; Fqe += hq_ * fe;
                 }
             } else {
                 const int gb = -(code + 1);
@@ -591,12 +625,12 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                         open_boundary_flux<NONLIN>(&prm.bc, gb, slot, wp_, wq_, uKx, uKy, eK, bg, HK, nxs, nys, il, len, g,
                                                    wd_on, a2, fl);
                     }
-                    Fpx += wp_ * fl[0]; Fpy += wp_ * fl[1]; Fpe += wp_ * fl[2];
-                    Fqx += wq_ * fl[0]; Fqy += wq_ * fl[1]; Fqe += wq_ * fl[2];
+                    Fpx += 0.5 * wp_ * fl[0]; Fpy += 0.5 * wp_ * fl[1]; Fpe += 0.5 * wp_ * fl[2];
+                    Fqx += 0.5 * wq_ * fl[0]; Fqy += 0.5 * wq_ * fl[1]; Fqe += 0.5 * wq_ * fl[2];
                 }
             }
-            Rux[p] -= 0.5 * Fpx; Ruy[p] -= 0.5 * Fpy; Re[p] -= 0.5 * Fpe;
-            Rux[q] -= 0.5 * Fqx; Ruy[q] -= 0.5 * Fqy; Re[q] -= 0.5 * Fqe;
+            Rux[p] -= Fpx; Ruy[p] -= Fpy; Re[p] -= Fpe;
+            Rux[q] -= Fqx; Ruy[q] -= Fqy; Re[q] -= Fqe;
         }
 
         // ---------------- P1 mass inverse (equation.py:99-105) and Shu-Osher update ----------------
