@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "symm"], help="multi-GPU halo transport")
     return ap.parse_args()
 
 
@@ -178,7 +179,7 @@ def main():
 
     if world > 1:
         from thetis_b200.parallel import PartitionedSWE
-        run = PartitionedSWE(mesh, setup, rank, world, wd=wd)
+        run = PartitionedSWE(mesh, setup, rank, world, wd=wd, transport=a.transport)
     else:
         from thetis_b200.parallel import SingleSWE
         run = SingleSWE(mesh, setup, wd=wd)
@@ -282,7 +283,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "triangles": int(n_tri_global), "dofs": int(9 * n_tri_global),
                        "dt": dt, "l2": "state arrays (3 x %.0f MB) larger than L2; no flush" % (n_tri_global * 72 / 1e6),
-                       "parallelism": f"domain decomposition x{world}" if world > 1 else "single GPU"},
+                       "parallelism": (f"domain decomposition x{world}, halo transport {run.transport}" if world > 1 else "single GPU")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "stage_kernel_launches": int(stage_launches),
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

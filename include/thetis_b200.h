@@ -178,6 +178,10 @@ int tb_gather_cells(tb_ctx *ctx, const double *state, const int32_t *idx, int64_
                     int rec_len, double *buf, void *stream);
 int tb_scatter_cells(tb_ctx *ctx, const double *buf, const int32_t *idx, int64_t n,
                      int rec_len, double *state, void *stream);
+/* Peer push over NVLink: record of cell idx[h] is stored to the address dst_ptrs[h] (DEVICE array of device
+ * pointers into peer GPUs' ghost blocks, e.g. from torch symmetric memory).  Replaces pack + all-to-all. */
+int tb_push_cells(tb_ctx *ctx, const double *state, const int32_t *idx, const uint64_t *dst_ptrs, int64_t n,
+                  int rec_len, void *stream);
 /* Restrict the next tb_swe_stage / tb_tracer_stage launches to patches
  * [first, first+count) (interior / partition-boundary split for overlap).
  * count < 0 resets to all patches. */

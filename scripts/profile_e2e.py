@@ -1,0 +1,24 @@
+"""cProfile of the e2e step loop (host overhead of the reference-shaped API)."""
+import os, sys, cProfile, pstats, time
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import torch
+from thetis_b200.workloads import north_sea_mesh, north_sea_setup
+from thetis_b200.parallel import SingleSWE
+k = int(sys.argv[1]) if len(sys.argv) > 1 else 19
+mesh = north_sea_mesh(k)
+setup = north_sea_setup(mesh)
+run = SingleSWE(mesh, setup)
+for _ in range(5):
+    run.step_e2e()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(100):
+    run.step_e2e()
+pr.disable()
+t_host = time.perf_counter() - t0
+torch.cuda.synchronize()
+t_all = time.perf_counter() - t0
+print(f"host issue time {t_host*10:.3f} ms/step; incl. GPU drain {t_all*10:.3f} ms/step")
+pstats.Stats(pr).sort_stats("cumulative").print_stats(22)

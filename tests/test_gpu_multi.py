@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, k, nsteps, out):
+def _worker(rank, world, port, k, nsteps, transport, out):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -32,7 +32,8 @@ def _worker(rank, world, port, k, nsteps, out):
         from thetis_b200.parallel import PartitionedSWE
         mesh = north_sea_mesh(k)
         setup = north_sea_setup(mesh, wetting_drying=True)
-        run = PartitionedSWE(mesh, setup, rank, world, wd=True)
+        run = PartitionedSWE(mesh, setup, rank, world, wd=True, transport=transport)
+        assert run.transport == transport
         for _ in range(nsteps):
             run.step_e2e()
         torch.cuda.synchronize()
@@ -42,8 +43,9 @@ def _worker(rank, world, port, k, nsteps, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["nccl", "symm"])
 @pytest.mark.parametrize("world", [2])
-def test_partitioned_run_is_bit_identical(world):
+def test_partitioned_run_is_bit_identical(world, transport):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
@@ -51,7 +53,7 @@ def test_partitioned_run_is_bit_identical(world):
     k, nsteps = 2, 4
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), k, nsteps, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), k, nsteps, transport, out), nprocs=world, join=True)
     from thetis_b200.workloads import north_sea_mesh, north_sea_setup
     from thetis_b200.parallel import SingleSWE
     mesh = north_sea_mesh(k)

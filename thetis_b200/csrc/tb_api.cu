@@ -44,7 +44,10 @@ struct tb_ctx {
     unsigned char *d_sblk = nullptr;
     size_t sblk_bytes = 0;
     int32_t *d_halo_ids = nullptr, *d_halo_cnt = nullptr;
-    int32_t *d_bf_slot = nullptr;
+    int32_t *d_bf_slot = nullptr, *d_bf_row = nullptr;
+    std::vector<int32_t> bf_row;                 // compact row of each exterior facet (grouped by slot)
+    std::vector<std::vector<int32_t>> slot_rows; // exterior facets of each slot, ascending
+    std::vector<long long> slot_row0;            // first compact row of each slot
     double *d_ext[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // elev, uv, un, flux, value (swe)
     double *d_ext_tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_area = nullptr;
@@ -55,8 +58,6 @@ struct tb_ctx {
     size_t h_pinned_bytes[NSTAGE] = {0};
     cudaEvent_t h_event[NSTAGE] = {nullptr};
     int h_next = 0;
-    std::vector<double> h_mirror[2][5];
-    std::vector<long long> slot_first, slot_last;
     // layout
     TbPatchLayout pl{};
     bool layout_dirty = true;
@@ -337,6 +338,15 @@ extern "C" int tb_create(tb_ctx **out, const tb_mesh *m, int device) {
         }
         ctx->bf_slot[k] = s;
     }
+    ctx->slot_rows.assign(TB_MAX_SLOTS, {});
+    for (long long k = 0; k < m->n_bfacets; ++k) ctx->slot_rows[ctx->bf_slot[k]].push_back((int32_t)k);
+    ctx->slot_row0.assign(TB_MAX_SLOTS + 1, 0);
+    ctx->bf_row.assign(m->n_bfacets, 0);
+    for (int sl = 0; sl < TB_MAX_SLOTS; ++sl) {
+        ctx->slot_row0[sl + 1] = ctx->slot_row0[sl] + (long long)ctx->slot_rows[sl].size();
+        for (size_t j = 0; j < ctx->slot_rows[sl].size(); ++j)
+            ctx->bf_row[ctx->slot_rows[sl][j]] = (int32_t)(ctx->slot_row0[sl] + (long long)j);
+    }
     memset(ctx->bc, 0, sizeof(ctx->bc));
     for (int eq = 0; eq < 2; ++eq)
         for (size_t j = 0; j < ctx->slot_marker.size(); ++j) {
@@ -361,6 +371,9 @@ extern "C" int tb_create(tb_ctx **out, const tb_mesh *m, int device) {
     CKC(cudaMalloc(&ctx->d_bf_slot, sizeof(int32_t) * std::max<long long>(m->n_bfacets, 4)));
     if (m->n_bfacets)
         CKC(cudaMemcpy(ctx->d_bf_slot, ctx->bf_slot.data(), sizeof(int32_t) * m->n_bfacets, cudaMemcpyHostToDevice));
+    CKC(cudaMalloc(&ctx->d_bf_row, sizeof(int32_t) * std::max<long long>(m->n_bfacets, 4)));
+    if (m->n_bfacets)
+        CKC(cudaMemcpy(ctx->d_bf_row, ctx->bf_row.data(), sizeof(int32_t) * m->n_bfacets, cudaMemcpyHostToDevice));
     CKC(cudaMalloc(&ctx->d_area, sizeof(double) * m->n_owned));
     CKC(cudaMemcpy(ctx->d_area, area.data(), sizeof(double) * m->n_owned, cudaMemcpyHostToDevice));
     default_quadrature(ctx);
@@ -375,6 +388,7 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_halo_ids);
     cudaFree(ctx->d_halo_cnt);
     cudaFree(ctx->d_bf_slot);
+    cudaFree(ctx->d_bf_row);
     cudaFree(ctx->d_area);
     for (int k = 0; k < 5; ++k) {
         cudaFree(ctx->d_ext[k]);
@@ -516,32 +530,16 @@ extern "C" int tb_set_bc_array(tb_ctx *ctx, int eq, int marker, int tag, const d
         CK(cudaMalloc(&slot_arr[k], sizeof(double) * std::max<size_t>(n, 2)));
         CK(cudaMemset(slot_arr[k], 0, sizeof(double) * std::max<size_t>(n, 2)));
     }
-    // Host mirror of the whole per-tag array: merge this marker's entries, then ship the marker's facet range
-    // [first, last] with ONE async copy from a pinned ring slot (entries of other markers inside the range are
-    // re-sent unchanged from the mirror, so several markers can hold arrays of the same tag).
-    std::vector<double> &mir = ctx->h_mirror[eq][k];
-    if (mir.size() != std::max<size_t>(n, 2)) mir.assign(std::max<size_t>(n, 2), 0.0);
+    // The device arrays are compact: rows grouped by marker slot (bf_row), so one marker's data is one contiguous
+    // block: gather its rows from the caller's full-size array into a pinned ring slot, one async copy.
     const size_t w = 2 * (size_t)nc;
-    long long first = -1, last = -1;
-    if (ctx->slot_first.empty()) {
-        ctx->slot_first.assign(TB_MAX_SLOTS, -1);
-        ctx->slot_last.assign(TB_MAX_SLOTS, -1);
-        for (long long f = 0; f < ctx->n_bfacets; ++f) {
-            const int sl = ctx->bf_slot[f];
-            if (ctx->slot_first[sl] < 0) ctx->slot_first[sl] = f;
-            ctx->slot_last[sl] = f;
-        }
-    }
-    first = ctx->slot_first[s];
-    last = ctx->slot_last[s];
-    if (first < 0) return TB_OK;
-    for (long long f = first; f <= last; ++f)
-        if (ctx->bf_slot[f] == s) memcpy(&mir[f * w], values + f * w, sizeof(double) * w);
+    const std::vector<int32_t> &rows = ctx->slot_rows[s];
+    if (rows.empty()) return TB_OK;
     const int slot = ctx->h_next;
     ctx->h_next = (ctx->h_next + 1) % tb_ctx::NSTAGE;
     if (!ctx->h_event[slot]) CK(cudaEventCreateWithFlags(&ctx->h_event[slot], cudaEventDisableTiming));
     else CK(cudaEventSynchronize(ctx->h_event[slot]));      // copy issued NSTAGE calls ago has finished
-    const size_t bytes = sizeof(double) * w * (size_t)(last - first + 1);
+    const size_t bytes = sizeof(double) * w * rows.size();
     if (ctx->h_pinned_bytes[slot] < bytes) {
         if (ctx->h_pinned[slot]) cudaFreeHost(ctx->h_pinned[slot]);
         ctx->h_pinned[slot] = nullptr;
@@ -550,8 +548,15 @@ extern "C" int tb_set_bc_array(tb_ctx *ctx, int eq, int marker, int tag, const d
     }
     double *hp = ctx->h_pinned[slot];
     cudaStream_t st = (cudaStream_t)stream;
-    memcpy(hp, &mir[first * w], bytes);
-    CK(cudaMemcpyAsync(slot_arr[k] + first * w, hp, bytes, cudaMemcpyHostToDevice, st));
+    if (w == 2) {
+        for (size_t j = 0; j < rows.size(); ++j) {
+            hp[2 * j] = values[2 * (size_t)rows[j]];
+            hp[2 * j + 1] = values[2 * (size_t)rows[j] + 1];
+        }
+    } else {
+        for (size_t j = 0; j < rows.size(); ++j) memcpy(hp + j * w, values + (size_t)rows[j] * w, sizeof(double) * w);
+    }
+    CK(cudaMemcpyAsync(slot_arr[k] + ctx->slot_row0[s] * w, hp, bytes, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->h_event[slot], st));
     ctx->bc[eq][s].arr_mask |= tag;
     return TB_OK;
@@ -568,6 +573,7 @@ static void fill_coef(const FieldStore &fs, TbCoef &c) {
 static void fill_bc(tb_ctx *ctx, int eq, TbBcTable &t) {
     t.n_slots = (int)ctx->slot_marker.size();
     t.bf_slot = ctx->d_bf_slot;
+    t.bf_row = ctx->d_bf_row;
     double **a = eq == 0 ? ctx->d_ext : ctx->d_ext_tr;
     t.ext_elev = a[0];
     t.ext_uv = a[1];
@@ -799,6 +805,14 @@ extern "C" int tb_scatter_cells(tb_ctx *ctx, const double *buf, const int32_t *i
                                 double *state, void *stream) {
     if (!ctx || (n > 0 && (!state || !idx || !buf))) return fail(ctx, TB_ERR_ARG, "null pointer");
     CK(tb_launch_scatter_cells(buf, idx, n, rec_len, state, (cudaStream_t)stream));
+    ctx->launches += n > 0;
+    return TB_OK;
+}
+extern "C" int tb_push_cells(tb_ctx *ctx, const double *state, const int32_t *idx, const uint64_t *dst_ptrs, int64_t n,
+                             int rec_len, void *stream) {
+    if (!ctx || (n > 0 && (!state || !idx || !dst_ptrs))) return fail(ctx, TB_ERR_ARG, "null pointer");
+    CK(tb_launch_push_cells(state, idx, reinterpret_cast<const unsigned long long *>(dst_ptrs), n, rec_len,
+                            (cudaStream_t)stream));
     ctx->launches += n > 0;
     return TB_OK;
 }

@@ -30,7 +30,8 @@ struct TbBcTable {
     int n_slots;
     int pad;
     const int *bf_slot;          // [n_bfacets] slot of each exterior facet
-    const double *ext_elev;      // [n_bfacets*2]
+    const int *bf_row;           // [n_bfacets] row of the facet in the compact per-tag arrays (grouped by slot)
+    const double *ext_elev;      // [n_bfacets*2], indexed by bf_row
     const double *ext_uv;        // [n_bfacets*4]
     const double *ext_un;        // [n_bfacets*2]
     const double *ext_flux;      // [n_bfacets*2]
@@ -104,6 +105,8 @@ cudaError_t tb_launch_gather_cells(const double *state, const int32_t *idx, long
                                    cudaStream_t s);
 cudaError_t tb_launch_scatter_cells(const double *buf, const int32_t *idx, long long n, int rec, double *state,
                                     cudaStream_t s);
+cudaError_t tb_launch_push_cells(const double *state, const int32_t *idx, const unsigned long long *dst, long long n,
+                                 int rec, cudaStream_t s);
 cudaError_t tb_launch_swe_integrals(const double *state, const double *area, long long n_owned, double *out,
                                     cudaStream_t s);
 // limiter: vertex bounds via deterministic CSR gather, then per-cell clamp

@@ -208,14 +208,15 @@ __device__ __noinline__ void open_boundary_flux(const TbBcTable *bc, int gb, int
                                                 double il, double len, double g, int wd_on, double a2, double *out) {
     const TbBcSlot &bs = bc->slots[slot];
     const int op = bs.opcode;
+    const int row = bs.arr_mask ? __ldg(bc->bf_row + gb) : 0;
     double elev = bs.elev, uvx = bs.uvx, uvy = bs.uvy, un = bs.un, flux = bs.flux;
-    if (bs.arr_mask & TB_BC_ELEV) elev = wp_ * __ldg(bc->ext_elev + 2 * gb) + wq_ * __ldg(bc->ext_elev + 2 * gb + 1);
+    if (bs.arr_mask & TB_BC_ELEV) elev = wp_ * __ldg(bc->ext_elev + 2 * row) + wq_ * __ldg(bc->ext_elev + 2 * row + 1);
     if (bs.arr_mask & TB_BC_UV) {
-        uvx = wp_ * __ldg(bc->ext_uv + 4 * gb) + wq_ * __ldg(bc->ext_uv + 4 * gb + 2);
-        uvy = wp_ * __ldg(bc->ext_uv + 4 * gb + 1) + wq_ * __ldg(bc->ext_uv + 4 * gb + 3);
+        uvx = wp_ * __ldg(bc->ext_uv + 4 * row) + wq_ * __ldg(bc->ext_uv + 4 * row + 2);
+        uvy = wp_ * __ldg(bc->ext_uv + 4 * row + 1) + wq_ * __ldg(bc->ext_uv + 4 * row + 3);
     }
-    if (bs.arr_mask & TB_BC_UN) un = wp_ * __ldg(bc->ext_un + 2 * gb) + wq_ * __ldg(bc->ext_un + 2 * gb + 1);
-    if (bs.arr_mask & TB_BC_FLUX) flux = wp_ * __ldg(bc->ext_flux + 2 * gb) + wq_ * __ldg(bc->ext_flux + 2 * gb + 1);
+    if (bs.arr_mask & TB_BC_UN) un = wp_ * __ldg(bc->ext_un + 2 * row) + wq_ * __ldg(bc->ext_un + 2 * row + 1);
+    if (bs.arr_mask & TB_BC_FLUX) flux = wp_ * __ldg(bc->ext_flux + 2 * row) + wq_ * __ldg(bc->ext_flux + 2 * row + 1);
     const BcExt ex = bc_external<NONLIN>(op, eK, uKx, uKy, bg, elev, uvx, uvy, un, flux, bs.bnd_len, nxs, nys, il, wd_on, a2);
     const double ig = tb_rcp(g);
     // PG (:370-375)
@@ -572,29 +573,43 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                     const double uNx = fma(xi, dNx, uNxp), uNy = fma(xi, dNy, uNyp);
                     const double eN = fma(xi, dNe, eNp);
                     const double bg = fma(xi, dKb, b[p]);
-                    double hbar;
-                    if (NONLIN) hbar = 0.5 * (wd_depth(bg + eK, wd_on, a2) + wd_depth(bg + eN, wd_on, a2));
-                    else hbar = bg;
-                    const double c = tb_sqrt(g * hbar);
+                    // everything below is written in FMA-minimal form (no reassociation is left to the compiler)
+                    const double esum = eK + eN, ediff = eK - eN;
+                    double gh, hh;           // g*hbar and hbar/2, hbar = avg(total depth)
+                    if (NONLIN && wd_on) {
+                        const double hlK = bg + eK, hlN = bg + eN;
+                        const double sig = (hlK + hlN) + (tb_sqrt(fma(hlK, hlK, a2)) + tb_sqrt(fma(hlN, hlN, a2)));   // 4*hbar
+                        gh = (0.25 * g) * sig;
+                        hh = 0.125 * sig;
+                    } else {
+                        const double hbar = NONLIN ? fma(0.5, esum, bg) : bg;
+                        gh = g * hbar;
+                        hh = 0.5 * hbar;
+                    }
+                    const double c = tb_sqrt(gh);
                     const double dux = uKx - uNx, duy = uKy - uNy;
-                    const double dun = dux * nxs + duy * nys;
-                    // PG (:363-366): g*(avg(eta) + sqrt(h/g)*jump(u,n)) n
-                    const double t = 0.5 * g * (eK + eN) + c * dun * il;
-                    double fx = t * nxs, fy = t * nys;
-                    // HUDiv (:424-427): h*(avg(u) + sqrt(g/h)*jump(eta,n)).n
                     const double usx = uKx + uNx, usy = uKy + uNy;
-                    const double usN = usx * nxs + usy * nys;
-                    const double fe = 0.5 * hbar * usN + c * (eK - eN) * len;
+                    const double dun = fma(dux, nxs, duy * nys);
+                    const double usN = fma(usx, nxs, usy * nys);
+                    // PG (:363-366): g*(avg(eta) + sqrt(h/g)*jump(u,n)) n
+                    const double t = fma(c * il, dun, (0.5 * g) * esum);
+                    // HUDiv (:424-427): h*(avg(u) + sqrt(g/h)*jump(eta,n)).n
+                    const double fe = fma(c * len, ediff, hh * usN);
+                    double fx, fy;
                     if (NONLIN) {
-                        // advection (:480-488): avg(u) (u_K.n) + gamma (u_K - u_N)
-                        const double uKN = uKx * nxs + uKy * nys;
-                        fx += 0.5 * usx * uKN;
-                        fy += 0.5 * usy * uKN;
+                        // advection (:480-488): avg(u) (u_K.n) + gamma (u_K - u_N);  u_K.N = (us.N + du.N)/2
+                        const double hu = 0.25 * (usN + dun);
                         if (lf_on) {
-                            const double gam = 0.25 * fabs(usN) * prm.lf_sigma;
-                            fx += gam * dux;
-                            fy += gam * duy;
+                            const double gam = (0.25 * prm.lf_sigma) * fabs(usN);
+                            fx = fma(t, nxs, fma(hu, usx, gam * dux));
+                            fy = fma(t, nys, fma(hu, usy, gam * duy));
+                        } else {
+                            fx = fma(t, nxs, hu * usx);
+                            fy = fma(t, nys, hu * usy);
                         }
+                    } else {
+                        fx = t * nxs;
+                        fy = t * nys;
                     }
                     Fpx += hp_ * fx; Fpy += hp_ * fy; Fpe += hp_ * fe;
                     Fqx += hq_ * fx; Fqy += hq_ * fy; Fqe += hq_ * fe;
@@ -782,6 +797,20 @@ __global__ void scatter_cells_kernel(const double *__restrict__ buf, const int32
     const long long h = i / rec;
     const int k = (int)(i - h * rec);
     state[(long long)idx[h] * rec + k] = buf[i];
+}
+// peer push: record h goes straight to dst[h] (a pointer into a peer GPU's ghost block, NVLink P2P store)
+__global__ void push_cells_kernel(const double *__restrict__ state, const int32_t *__restrict__ idx,
+                                  const unsigned long long *__restrict__ dst, long long n, int rec) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * rec) return;
+    const long long h = i / rec;
+    const int k = (int)(i - h * rec);
+    reinterpret_cast<double *>(dst[h])[k] = state[(long long)idx[h] * rec + k];
+}
+cudaError_t tb_launch_push_cells(const double *state, const int32_t *idx, const unsigned long long *dst, long long n,
+                                 int rec, cudaStream_t s) {
+    if (n) push_cells_kernel<<<nblk(n * rec, 256), 256, 0, s>>>(state, idx, dst, n, rec);
+    return cudaGetLastError();
 }
 cudaError_t tb_launch_gather_cells(const double *state, const int32_t *idx, long long n, int rec, double *buf,
                                    cudaStream_t s) {

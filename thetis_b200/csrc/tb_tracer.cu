@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
                 const int slot = __ldg(prm.bc.bf_slot + gb);
                 const TbBcSlot &bs = prm.bc.slots[slot];
                 const int op = bs.opcode;
+                const int row = bs.arr_mask ? __ldg(prm.bc.bf_row + gb) : 0;
                 const double len2 = nxs * nxs + nys * nys;
                 const double il = rsqrt(len2);
 #pragma unroll
@@ -183,25 +184,25 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
                         if (op & TB_BC_VALUE) {
                             cext = bs.value;
                             if (bs.arr_mask & TB_BC_VALUE)
-                                cext = wp_ * __ldg(prm.bc.ext_value + 2 * gb) + wq_ * __ldg(prm.bc.ext_value + 2 * gb + 1);
+                                cext = wp_ * __ldg(prm.bc.ext_value + 2 * row) + wq_ * __ldg(prm.bc.ext_value + 2 * row + 1);
                         }
                         if (op & TB_BC_UV) {
                             double uvx = bs.uvx, uvy = bs.uvy;
                             if (bs.arr_mask & TB_BC_UV) {
-                                uvx = wp_ * __ldg(prm.bc.ext_uv + 4 * gb) + wq_ * __ldg(prm.bc.ext_uv + 4 * gb + 2);
-                                uvy = wp_ * __ldg(prm.bc.ext_uv + 4 * gb + 1) + wq_ * __ldg(prm.bc.ext_uv + 4 * gb + 3);
+                                uvx = wp_ * __ldg(prm.bc.ext_uv + 4 * row) + wq_ * __ldg(prm.bc.ext_uv + 4 * row + 2);
+                                uvy = wp_ * __ldg(prm.bc.ext_uv + 4 * row + 1) + wq_ * __ldg(prm.bc.ext_uv + 4 * row + 3);
                             }
                             uex = corr * uvx;
                             uey = corr * uvy;
                         } else if (op & TB_BC_FLUX) {
                             double flux = bs.flux;
                             if (bs.arr_mask & TB_BC_FLUX)
-                                flux = wp_ * __ldg(prm.bc.ext_flux + 2 * gb) + wq_ * __ldg(prm.bc.ext_flux + 2 * gb + 1);
+                                flux = wp_ * __ldg(prm.bc.ext_flux + 2 * row) + wq_ * __ldg(prm.bc.ext_flux + 2 * row + 1);
                             double eext = wp_ * et[p] + wq_ * et[q];
                             if (op & TB_BC_ELEV) {
                                 eext = bs.elev;
                                 if (bs.arr_mask & TB_BC_ELEV)
-                                    eext = wp_ * __ldg(prm.bc.ext_elev + 2 * gb) + wq_ * __ldg(prm.bc.ext_elev + 2 * gb + 1);
+                                    eext = wp_ * __ldg(prm.bc.ext_elev + 2 * row) + wq_ * __ldg(prm.bc.ext_elev + 2 * row + 1);
                             }
                             const double bg = wp_ * b[p] + wq_ * b[q];
                             double hext = bg;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
                         } else if (op & TB_BC_UN) {
                             double un = bs.un;
                             if (bs.arr_mask & TB_BC_UN)
-                                un = wp_ * __ldg(prm.bc.ext_un + 2 * gb) + wq_ * __ldg(prm.bc.ext_un + 2 * gb + 1);
+                                un = wp_ * __ldg(prm.bc.ext_un + 2 * row) + wq_ * __ldg(prm.bc.ext_un + 2 * row + 1);
                             uex = un * nxs * il;
                             uey = un * nys * il;
                         }

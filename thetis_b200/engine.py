@@ -164,6 +164,10 @@ class Engine:
         self._ck(self.lib.tb_scatter_cells(self.ctx, _ptr(buf), _ptr(idx), int(idx.numel()), rec_len, _ptr(state),
                                            self.stream))
 
+    def push_cells(self, state, idx, dst_ptrs, rec_len):
+        self._ck(self.lib.tb_push_cells(self.ctx, _ptr(state), _ptr(idx), _ptr(dst_ptrs), int(idx.numel()), rec_len,
+                                        self.stream))
+
     # ------------------------------------------------------------ layout conversion
     def identity_node_map(self):
         if self._identity_map is None:

@@ -246,14 +246,21 @@ class SingleSWE:
 class PartitionedSWE:
     """North Sea workload on `world` GPUs: one process per GPU, one halo exchange per RK stage over NCCL."""
 
-    def __init__(self, mesh, setup, rank, world, wd=True):
+    def __init__(self, mesh, setup, rank, world, wd=True, transport="auto"):
+        """
+        transport: 'nccl'  pack + NCCL all-to-all into the ghost block;
+                   'symm'  state buffers in torch symmetric memory, send cells stored straight into the peers'
+                           ghost blocks over NVLink (tb_push_cells) + one device-side barrier per stage;
+                   'auto'  'symm' when symmetric memory can be set up, else 'nccl'.
+        """
         import torch
         from . import _lib as L
         from .engine import Engine
         from .workloads import M2_PERIOD
         self.torch = torch
         self.rank, self.world = rank, world
-        self.part = partition_mesh(mesh, world)[rank]
+        parts = partition_mesh(mesh, world)
+        self.part = parts[rank]
         p = self.part
         lm = p.mesh
         self.eng = eng = Engine(lm, n_owned=p.n_owned)
@@ -279,15 +286,26 @@ class PartitionedSWE:
         uv = setup["uv0"][glob]
         eta = setup["eta0"][glob]
         # state: owned (padded) + ghosts
-        A = eng.new_state()
         dev = eng.device
+        send_idx = np.concatenate([p.send_lists[q] for q in range(world) if q in p.send_lists]) if p.send_lists else np.zeros(0, np.int64)
+        self.transport = "nccl"
+        self._symm = None
+        if transport in ("auto", "symm"):
+            try:
+                self._setup_symmetric(parts, send_idx)
+                self.transport = "symm"
+            except Exception as exc:            # noqa: BLE001  (fall back to NCCL all-to-all, same results)
+                if transport == "symm":
+                    raise
+                self._symm_error = repr(exc)
+        if self.transport == "nccl":
+            self.buf = [eng.new_state(), eng.new_state(), eng.new_state()]
+        A = self.buf[0]
         own = eng.upload_nodal(uv[:p.n_owned], eta[:p.n_owned])
-        A.copy_(own)
+        A[:own.numel()].copy_(own)
         if p.n_ghost:
             grec = np.concatenate([uv[p.n_owned:].reshape(-1, 6), eta[p.n_owned:]], axis=1)
-            A[eng.n_owned_pad * 9:] = torch.as_tensor(grec.reshape(-1)).to(dev)
-        self.buf = [A, eng.new_state(), eng.new_state()]
-        send_idx = np.concatenate([p.send_lists[q] for q in range(world) if q in p.send_lists]) if p.send_lists else np.zeros(0, np.int64)
+            A[eng.n_owned_pad * 9:eng.n_owned_pad * 9 + grec.size] = torch.as_tensor(grec.reshape(-1)).to(dev)
         self.send_idx = torch.as_tensor(send_idx.astype(np.int32)).to(dev)
         self.sendbuf = torch.zeros((max(int(send_idx.shape[0]), 1), 9), dtype=torch.float64, device=dev)
         self.n_send = int(send_idx.shape[0])
@@ -300,8 +318,45 @@ class PartitionedSWE:
         self._alpha, self._beta = butcher_to_shuosher_form(SSPRK33.a, SSPRK33.b)
         self._c = [float(v) for v in SSPRK33.c]
 
+    def _setup_symmetric(self, parts, send_idx):
+        """State buffers in symmetric memory; per buffer the peer addresses every send cell must be stored to."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        eng, p, world, rank = self.eng, self.part, self.world, self.rank
+        P = eng.patch_size
+        pads = [((q.n_owned + P - 1) // P) * P for q in parts]
+        lens = [(pads[r] + parts[r].n_ghost) * 9 for r in range(world)]
+        L = (max(lens) + 31) // 32 * 32                 # same size on every rank; 256-B aligned sub-buffers (TMA)
+        t = symm_mem.empty(3 * L, dtype=torch.float64, device=eng.device)
+        t.zero_()
+        hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+        self._symm = (t, hdl)
+        self.buf = [t[i * L:i * L + eng.state_len] for i in range(3)]
+        ptrs = [int(x) for x in hdl.buffer_ptrs]
+        dst = np.zeros((3, max(send_idx.shape[0], 1)), dtype=np.uint64)
+        e = 0
+        for q in range(world):
+            if q not in p.send_lists:
+                continue
+            n = p.send_lists[q].shape[0]
+            # my cells sit in q's ghost block after the ghosts owned by lower ranks, in q's ghost order
+            first = int((parts[q].ghost_owner < rank).sum())
+            slot = pads[q] + first + np.arange(n, dtype=np.int64)
+            for b in range(3):
+                dst[b, e:e + n] = np.uint64(ptrs[q]) + ((b * L + slot * 9) * 8).astype(np.uint64)
+            e += n
+        self._dst_ptrs = [torch.as_tensor(dst[b].view(np.int64)).to(eng.device) for b in range(3)]
+        self._buf_index = {self.buf[b].data_ptr(): b for b in range(3)}
+
     def _exchange(self, state):
         eng, p = self.eng, self.part
+        if self.transport == "symm":
+            b = self._buf_index[state.data_ptr()]
+            if self.n_send:
+                eng.push_cells(state, self.send_idx, self._dst_ptrs[b], 9)
+            self._symm[1].barrier(channel=0)        # every rank's stores have landed before anyone reads its ghosts
+            return
         if self.n_send:
             eng.gather_cells(state, self.send_idx, 9, self.sendbuf)
         ghost = state[eng.n_owned_pad * 9:].view(-1, 9)
@@ -327,7 +382,12 @@ class PartitionedSWE:
 
     def update_forcings(self, t):
         if self._has_open:
-            self.eng.set_bc_array(0, 100, self._L.BC_ELEV, np.sin(self._omega * t + self._phase))
+            if not hasattr(self, "_tide_buf"):
+                self._open_rows = np.nonzero(self.part.mesh.bf_marker == 100)[0]
+                self._open_phase = self._phase[self._open_rows]
+                self._tide_buf = np.zeros_like(self._phase)
+            self._tide_buf[self._open_rows] = np.sin(self._omega * t + self._open_phase)
+            self.eng.set_bc_array(0, 100, self._L.BC_ELEV, self._tide_buf)
 
     def n_owned(self):
         return self.part.n_owned
