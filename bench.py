@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: do not overlap the halo push with interior patches")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the resident step in a CUDA graph")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "symm"], help="multi-GPU halo transport")
     return ap.parse_args()
 
@@ -179,7 +181,7 @@ def main():
 
     if world > 1:
         from thetis_b200.parallel import PartitionedSWE
-        run = PartitionedSWE(mesh, setup, rank, world, wd=wd, transport=a.transport)
+        run = PartitionedSWE(mesh, setup, rank, world, wd=wd, transport=a.transport, overlap=not a.no_overlap)
     else:
         from thetis_b200.parallel import SingleSWE
         run = SingleSWE(mesh, setup, wd=wd)
@@ -190,6 +192,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing
+    if not a.no_graph and hasattr(run, "enable_graph"):
+        run.enable_graph()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -226,6 +230,8 @@ def main():
     # ---------------- end-to-end through the reference-facing API
     e2e = None
     if not a.no_e2e:
+        if not a.no_graph and hasattr(run, "enable_stage_graphs"):
+            run.enable_stage_graphs()
         for _ in range(max(a.warmup, 3)):
             run.step_e2e()
         barrier()
@@ -242,9 +248,7 @@ def main():
         e2e = {"value": 9.0 * n_tri_global * a.steps / (ms2 * 1e-3) / 1e6, "unit": "M dof-updates/s",
                "h2d_bytes_per_step": int(run.h2d_bytes_per_step()), "d2h_bytes_per_step": int(run.d2h_bytes_per_step()),
                "ms_per_step": ms2 / a.steps,
-               "path": "FlowSolver2d mirror -> SSPRK33.advance(t, update_forcings): tidal elevation Function updated on "
-                       "the host every stage (H2D from pinned memory), print_state norms reduced on device and read "
-                       "back every step"}
+               "path": run.e2e_path()}
 
     if rank != 0:
         if world > 1:
@@ -283,7 +287,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "triangles": int(n_tri_global), "dofs": int(9 * n_tri_global),
                        "dt": dt, "l2": "state arrays (3 x %.0f MB) larger than L2; no flush" % (n_tri_global * 72 / 1e6),
-                       "parallelism": (f"domain decomposition x{world}, halo transport {run.transport}" if world > 1 else "single GPU")},
+                       "parallelism": (f"domain decomposition x{world}, halo transport {run.transport}, overlap {run.overlap}, "
+                                       f"cuda graph {hasattr(run, '_graph')}" if world > 1 else "single GPU")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "stage_kernel_launches": int(stage_launches),
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -191,6 +191,10 @@ int tb_set_patch_range(tb_ctx *ctx, int64_t first, int64_t count);
  * out[2n:3n] = 1/x, out[3n:4n] = x^-1/3 (accuracy is asserted in tests/test_gpu_math.py). */
 int tb_selftest_math(tb_ctx *ctx, const double *x, double *out, int64_t n, void *stream);
 
+/* Same with an explicit DEVICE list of patch ids (n > 0), e.g. the patches that hold cells a peer needs first,
+ * then the rest while the halo is in flight.  n == 0 resets to all patches.  SWE stage only. */
+int tb_set_patch_list(tb_ctx *ctx, const int32_t *list, int64_t n);
+
 /* launches issued by this library so far (bench.py's gpu_launches) */
 int64_t tb_launch_count(const tb_ctx *ctx);
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "tb_scatter_cells": (_I, [_P, _P, _P, _L, _I, _P, _P]),
     "tb_push_cells": (_I, [_P, _P, _P, _P, _L, _I, _P]),
     "tb_set_patch_range": (_I, [_P, _L, _L]),
+    "tb_set_patch_list": (_I, [_P, _P, _L]),
     "tb_launch_count": (_L, [_P]),
     "tb_selftest_math": (_I, [_P, _P, _P, _L, _P]),
 }

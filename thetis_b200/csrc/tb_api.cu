@@ -77,6 +77,8 @@ struct tb_ctx {
     int nquad = 0;
     // patch range
     long long range_first = 0, range_count = -1;
+    const int32_t *patch_list = nullptr;
+    long long patch_list_n = 0;
     long long launches = 0;
     // limiter
     bool lim_ready = false;
@@ -635,6 +637,11 @@ extern "C" int tb_swe_stage(tb_ctx *ctx, double a0, double a1, double b_dt, cons
     long long first, count;
     patch_range(ctx, first, count);
     p.patch_first = (int)first;
+    if (ctx->patch_list) {
+        p.patch_list = ctx->patch_list;
+        p.patch_first = 0;
+        count = ctx->patch_list_n;
+    }
     const size_t smem = tb_swe_smem_bytes(ctx->pl);
     if (smem > 200 * 1024) return fail(ctx, TB_ERR_UNSUPPORTED, "patch halo too large for shared memory");
     CK(tb_launch_swe_stage(p, ctx->nonlinear != 0, (int)count, smem, (cudaStream_t)stream));
@@ -820,6 +827,14 @@ extern "C" int tb_set_patch_range(tb_ctx *ctx, int64_t first, int64_t count) {
     if (!ctx) return TB_ERR_ARG;
     ctx->range_first = first;
     ctx->range_count = count;
+    ctx->patch_list = nullptr;
+    ctx->patch_list_n = 0;
+    return TB_OK;
+}
+extern "C" int tb_set_patch_list(tb_ctx *ctx, const int32_t *list, int64_t n) {
+    if (!ctx || (n > 0 && !list) || n > ctx->n_patches) return fail(ctx, TB_ERR_ARG, "bad patch list");
+    ctx->patch_list = n > 0 ? list : nullptr;
+    ctx->patch_list_n = n > 0 ? n : 0;
     return TB_OK;
 }
 

@@ -57,6 +57,7 @@ struct TbSweParams {
     const double *u0;
     double *u_out;
     TbPatchLayout pl;
+    const int *patch_list;       // optional: patch of CTA b is patch_list[b] (boundary / interior split), else patch_first + b
     int n_owned;
     int patch_first;
     double a0, a1, bdt;

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
     unsigned char *blk = reinterpret_cast<unsigned char *>(O + TB_P * 9);
 
     const int tid = threadIdx.x;
-    const int patch = prm.patch_first + blockIdx.x;
+    const int patch = prm.patch_list ? __ldg(prm.patch_list + blockIdx.x) : prm.patch_first + (int)blockIdx.x;
     const long long cell0 = (long long)patch * TB_P;
     const int NV = prm.pl.NV;
 
@@ -283,8 +283,9 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         if (prm.u0) bulk_g2s(O, prm.u0 + cell0 * 9, rec, bar);
     } else if (tid == 32) {
         // warm L2 for the patch that will run on this SM slot one wave later
-        const int pf = patch + TB_PREFETCH_DIST;
-        if (pf < prm.patch_first + (int)gridDim.x) {
+        const int pb = (int)blockIdx.x + TB_PREFETCH_DIST;
+        if (pb < (int)gridDim.x) {
+            const int pf = prm.patch_list ? __ldg(prm.patch_list + pb) : prm.patch_first + pb;
             const uint32_t rec = TB_P * 9 * sizeof(double);
             bulk_prefetch_l2(prm.u_in + (long long)pf * TB_P * 9, rec);
             bulk_prefetch_l2(prm.pl.sblk + (long long)pf * prm.pl.stride, (uint32_t)prm.pl.stride);

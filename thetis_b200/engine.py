@@ -139,6 +139,13 @@ class Engine:
     def set_patch_range(self, first=0, count=-1):
         self._ck(self.lib.tb_set_patch_range(self.ctx, int(first), int(count)))
 
+    def set_patch_list(self, lst=None):
+        """lst: device int32 tensor of patch ids for the next SWE stage launches, or None for all patches."""
+        if lst is None:
+            self._ck(self.lib.tb_set_patch_list(self.ctx, None, 0))
+        else:
+            self._ck(self.lib.tb_set_patch_list(self.ctx, _ptr(lst), int(lst.numel())))
+
     # ------------------------------------------------------------ hot path
     def swe_stage(self, a0, a1, b_dt, u_in, u0, u_out):
         self._ck(self.lib.tb_swe_stage(self.ctx, a0, a1, b_dt, _ptr(u_in), _ptr(u0), _ptr(u_out), self.stream))
