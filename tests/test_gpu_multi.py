@@ -37,8 +37,11 @@ def _worker(rank, world, port, k, nsteps, transport, out):
         assert run.overlap
         for _ in range(nsteps - 2):
             run.step_e2e()
-        # the last two steps replay the CUDA graph of the resident step (forcing frozen at its last value on both sides)
-        run.enable_graph() if transport == "symm" else run._step()
+        # the last two steps: one plain resident step, one replay of its CUDA graph (forcing frozen on both sides)
+        if transport == "symm":
+            run.enable_graph()            # runs one warm-up step, then captures
+        else:
+            run.step_resident()
         run.step_resident()
         torch.cuda.synchronize()
         uv, eta = run.owned_nodal()
@@ -74,3 +77,76 @@ def test_partitioned_run_is_bit_identical(world, transport):
         de = np.abs(eta - eta1[owned]).max()
         assert du == 0.0 and de == 0.0, (r, du, de, np.abs(uv1).max(), int((np.abs(uv - uv1[owned]).max(axis=(1, 2)) > 0).sum()))
     assert np.isfinite(uv1).all() and np.abs(eta1).max() > 0
+
+
+def _worker_coupled(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from thetis_b200.parallel import distribute_mesh
+        mesh = _coupled_mesh()
+        sm = distribute_mesh(mesh, rank, world, halo="vertex")
+        lm = sm.topology_mesh
+        s = _coupled_solver(sm)
+        s.iterate()
+        n = sm.halo_plan.part.n_owned
+        out[rank] = (lm.meta["global_cells"][:n].copy(),
+                     s.fields.uv_2d.dat.data_ro.reshape(-1, 3, 2)[:n].copy(),
+                     s.fields.elev_2d.dat.data_ro.reshape(-1, 3)[:n].copy(),
+                     s.fields.tracer_2d.dat.data_ro.reshape(-1, 3)[:n].copy(), s.last_norms)
+    finally:
+        dist.destroy_process_group()
+
+
+def _coupled_mesh():
+    from thetis_b200.mesh import rectangle_mesh, sfc_renumber
+    return sfc_renumber(rectangle_mesh(36, 16, 18e3, 8e3))
+
+
+def _coupled_solver(mesh_obj):
+    """BASELINE config 4 style: SWE + tracer + limiter (same set-up on 1 GPU and on the distributed mesh)"""
+    from thetis_b200 import solver2d
+    from thetis_b200.shim import Function, FunctionSpace, Constant, as_shim_mesh, ShimMesh
+    sm = mesh_obj if isinstance(mesh_obj, ShimMesh) else as_shim_mesh(mesh_obj)
+    lx = 18e3
+    b = Function(FunctionSpace(sm, "CG", 1)).interpolate(lambda x, y: 10.0 + 2.0 * np.cos(2 * np.pi * x / lx))
+    s = solver2d.FlowSolver2d(sm, b)
+    o = s.options
+    o.swe_timestepper_options.use_automatic_timestep = False
+    o.tracer_timestepper_options.use_automatic_timestep = False
+    o.timestep = 2.5
+    o.simulation_end_time = 2.5 * 30
+    o.simulation_export_time = 2.5 * 10
+    o.add_tracer_2d("tracer_2d", "Depth averaged tracer", "Tracer2d")
+    o.use_limiter_for_tracers = True
+    s.bnd_functions["shallow_water"] = {1: {"elev": Constant(0.2), "uv": Constant((0.05, 0.0))}}
+    s.bnd_functions["tracer"] = {1: {"value": Constant(4.0)}}
+    s.assign_initial_conditions(elev=lambda x, y: 0.5 * np.cos(np.pi * x / lx),
+                                tracer=lambda x, y: 4.5 + 2.0 * ((np.abs(x - lx / 2) < 3e3) & (np.abs(y - 4e3) < 2e3)))
+    return s
+
+
+def test_coupled_tracer_limiter_distributed_is_bit_identical():
+    """SWE -> tracer -> limiter on 2 GPUs (vertex halo for the limiter bounds) == the 1-GPU run, bit for bit"""
+    import torch
+    import torch.multiprocessing as mp
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_coupled, args=(world, _free_port(), out), nprocs=world, join=True)
+    s = _coupled_solver(_coupled_mesh())
+    s.iterate()
+    uv1 = s.fields.uv_2d.dat.data_ro.reshape(-1, 3, 2)
+    e1 = s.fields.elev_2d.dat.data_ro.reshape(-1, 3)
+    c1 = s.fields.tracer_2d.dat.data_ro.reshape(-1, 3)
+    assert np.abs(c1 - 4.5).max() > 0.5 and c1.max() <= 6.5 + 1e-9 and c1.min() >= 4.0 - 1e-9
+    for r in range(world):
+        cells, uv, e, c, norms = out[r]
+        assert np.array_equal(uv, uv1[cells]) and np.array_equal(e, e1[cells]) and np.array_equal(c, c1[cells])
+        assert abs(norms[0] - s.last_norms[0]) <= 1e-12 * s.last_norms[0]      # all-reduced print_state norms

@@ -141,8 +141,22 @@ class MeshAdaptor:
             self.mesh = base
             self.perm = np.arange(base.n_cells, dtype=np.int64)
         self.engine = None
+        # distributed run: the mesh object carries this rank's HaloPlan (thetis_b200.parallel.distribute_mesh)
+        self.halo = getattr(mesh_obj, "halo_plan", None)
+        self.n_owned = self.halo.part.n_owned if self.halo is not None else self.mesh.n_cells
         bl = getattr(mesh_obj, "boundary_len", None)
         self.boundary_len = dict(bl) if bl is not None else self.mesh.boundary_length()
+
+    def get_engine(self):
+        """The device context of this mesh (created on first use; shared by every integrator / limiter on it)."""
+        if self.engine is None:
+            from .engine import Engine
+            self.engine = Engine(self.mesh, n_owned=self.n_owned)
+            if self.halo is not None:
+                self.halo.attach(self.engine)
+                for mk, ln in self.boundary_len.items():
+                    self.engine.set_boundary_length(mk, ln)
+        return self.engine
 
     # ------------------------------------------------------------ node maps
     def _cell_nodes(self, fs):

@@ -24,9 +24,8 @@ class VertexBasedP1DGLimiter:
             raise NotImplementedError("vector fields are limited component-wise only on extruded meshes (out of scope)")
         self.P1DG = p1dg_space
         self.adaptor = get_adaptor(p1dg_space.mesh())
-        if self.adaptor.engine is None:
-            self.adaptor.engine = Engine(self.adaptor.mesh)
-        self.engine = self.adaptor.engine
+        self.engine = self.adaptor.get_engine()
+        self.halo = self.adaptor.halo
         self.node_map = None
 
     def apply(self, field):
@@ -39,10 +38,14 @@ class VertexBasedP1DGLimiter:
             if not st._host_stale and st._host_changed():
                 st.upload()
             eng.limiter_apply(st.device_state())
+            if self.halo is not None:
+                self.halo.exchange(st.device_state())      # limited ghost values for the next step
             st.mark_device_modified()
             if st.sync_policy == "every_step":
                 st.sync_to_host()
             return
+        if self.halo is not None:
+            raise NotImplementedError("distributed limiter needs the field to be owned by a B200 tracer integrator")
         if self.node_map is None:
             self.node_map = torch.as_tensor(self.adaptor.dg_node_map(self.P1DG).reshape(-1)).to(eng.device)
         q = torch.as_tensor(np.ascontiguousarray(np.asarray(field.dat.data_ro, dtype=np.float64))).to(eng.device)

@@ -43,28 +43,43 @@ class LocalPart:
         self.mesh = mesh                            # local Mesh2D: owned cells first, then ghosts
 
 
-def partition_mesh(mesh: Mesh2D, world: int):
+def partition_mesh(mesh: Mesh2D, world: int, halo: str = "facet"):
     """
-    Cut the (SFC-ordered) mesh into `world` contiguous chunks with a one-deep facet halo.
+    Cut the (SFC-ordered) mesh into `world` contiguous chunks with a one-deep halo of ghost cells:
+    ``halo='facet'`` = facet neighbours (enough for the SWE / tracer stage kernels),
+    ``halo='vertex'`` = every cell sharing a vertex with an owned cell (needed by the vertex-based limiter,
+    thetis/limiter.py:100-145: bounds are over all cells around a vertex).
     Deterministic: every rank computes the same partition from the same global mesh.
     Returns a list of `LocalPart`.
     """
     nt = mesh.n_cells
     bounds = np.linspace(0, nt, world + 1).astype(np.int64)
-    # align chunk boundaries to the patch size so that patches never straddle ranks
     owner = np.zeros(nt, dtype=np.int32)
     for r in range(world):
         owner[bounds[r]:bounds[r + 1]] = r
+    if halo == "vertex":
+        v2c_ptr, v2c_idx = mesh.vertex_to_cell_csr()
+        tv = mesh.topo[mesh.cells]
     parts = []
     ghosts_of = []
     for r in range(world):
         lo, hi = bounds[r], bounds[r + 1]
-        nb = mesh.nbr[lo:hi]
-        ext = nb[(nb >= 0) & ((nb < lo) | (nb >= hi))]
-        g = np.unique(ext)
+        if halo == "vertex":
+            verts = np.unique(tv[lo:hi].reshape(-1))
+            cnt = v2c_ptr[verts + 1] - v2c_ptr[verts]
+            starts = np.repeat(v2c_ptr[verts], cnt)
+            offs = np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+            cand = v2c_idx[starts + offs]
+            g = np.unique(cand[(cand < lo) | (cand >= hi)])
+        elif halo == "facet":
+            nb = mesh.nbr[lo:hi]
+            g = np.unique(nb[(nb >= 0) & ((nb < lo) | (nb >= hi))])
+        else:
+            raise ValueError(halo)
         go = owner[g]
         order = np.lexsort((g, go))
         ghosts_of.append((g[order].astype(np.int64), go[order].astype(np.int32)))
+    blen = mesh.boundary_length()
     for r in range(world):
         lo, hi = bounds[r], bounds[r + 1]
         owned = np.arange(lo, hi, dtype=np.int64)
@@ -78,26 +93,25 @@ def partition_mesh(mesh: Mesh2D, world: int):
             mine = pg[po == r]
             if mine.size:
                 send[p] = (mine - lo).astype(np.int64)
-        # local mesh
+        # local mesh: owned cells first, then ghosts (grouped by owner)
         glob = np.concatenate([owned, gg])
-        g2l = {}
         loc_of = np.full(nt, -1, dtype=np.int64)
         loc_of[glob] = np.arange(glob.shape[0])
         cells_g = mesh.cells[glob]
         vused, vinv = np.unique(cells_g.reshape(-1), return_inverse=True)
         cells_l = vinv.reshape(-1, 3).astype(np.int32)
         coords_l = mesh.coords[vused]
-        topo_l = mesh.topo[vused]
-        _, topo_l = np.unique(topo_l, return_inverse=True)
+        _, topo_l = np.unique(mesh.topo[vused], return_inverse=True)
         nbr_g = mesh.nbr[glob].astype(np.int64)
-        nbr_l = np.full(nbr_g.shape, INT32_MIN, dtype=np.int64)
+        nbr_l = np.full(nbr_g.shape, INT32_MIN, dtype=np.int64)       # unknown: neighbour not on this rank
+        pos = nbr_g >= 0
+        present = np.zeros_like(pos)
+        present[pos] = loc_of[nbr_g[pos]] >= 0
+        nbr_l[present] = loc_of[nbr_g[present]]
         n_own = owned.shape[0]
-        own_rows = np.arange(glob.shape[0]) < n_own
-        pos = (nbr_g >= 0) & own_rows[:, None]
-        nbr_l[pos] = loc_of[nbr_g[pos]]
-        assert np.all(nbr_l[pos] >= 0)
-        # exterior facets of owned cells, renumbered locally
-        bsel = (nbr_g < 0) & own_rows[:, None]
+        assert np.all(present[:n_own][pos[:n_own]]), "facet neighbours of owned cells must be local"
+        # exterior facets of every local cell (ghosts included: the limiter needs their facet means), renumbered
+        bsel = nbr_g < 0
         gb = -(nbr_g[bsel] + 1)
         ub, binv = np.unique(gb, return_inverse=True)
         nbr_l[bsel] = -(1 + binv)
@@ -108,8 +122,8 @@ def partition_mesh(mesh: Mesh2D, world: int):
         m.bf_lf = mesh.bf_lf[ub].copy()
         m.bf_marker = mesh.bf_marker[ub].copy()
         m.meta = dict(mesh.meta)
-        m.meta.update(global_bfacets=ub, global_vertices=vused, global_boundary_len=mesh.boundary_length())
-        del g2l
+        m.meta.update(global_bfacets=ub, global_vertices=vused, global_boundary_len=blen, global_cells=glob,
+                      n_owned=int(n_own), halo=halo, sfc=True)
         parts.append(LocalPart(r, world, m, owned, gg, go, send))
     return parts
 
@@ -143,12 +157,181 @@ def exchange_halo(part: LocalPart, sendbuf, recv_view, group=None):
             q.wait()
 
 
+class HaloPlan:
+    """
+    Per-rank halo machinery shared by the integrators and the limiter of a distributed run:
+    buffer allocation (symmetric memory when available), the per-stage exchange, and the
+    boundary-first / interior-overlapped launch of the SWE stage kernel.
+    """
+
+    def __init__(self, parts, rank, transport="auto", overlap=True):
+        self.parts = parts
+        self.part = parts[rank]
+        self.rank, self.world = rank, len(parts)
+        self.requested_transport = transport
+        self.want_overlap = overlap
+        self.transport = None
+        self.engine = None
+        self.overlap = False
+        self._groups = {}          # rec_len -> dict(L, tensor, handle, bufs, dst_ptrs)
+        self._buf_info = {}        # data_ptr -> (rec_len, buffer index)
+        self._sendbuf = {}
+
+    # ------------------------------------------------------------ set-up (needs the engine: patch size, device)
+    def attach(self, engine):
+        if self.engine is not None:
+            return
+        import torch
+        self.torch = torch
+        self.engine = engine
+        p = self.part
+        send_idx = np.concatenate([p.send_lists[q] for q in range(self.world) if q in p.send_lists]) \
+            if p.send_lists else np.zeros(0, np.int64)
+        self.n_send = int(send_idx.shape[0])
+        self.send_idx = torch.as_tensor(send_idx.astype(np.int32)).to(engine.device)
+        self._send_idx_np = send_idx
+        P = engine.patch_size
+        self._pads = [((q.n_owned + P - 1) // P) * P for q in self.parts]
+        self.transport = "nccl"
+        if self.requested_transport in ("auto", "symm"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem   # noqa: F401
+                self._symm_mem = symm_mem
+                self._probe = self._alloc_symmetric(1, 1)       # fails early if symmetric memory is unusable
+                self.transport = "symm"
+            except Exception as exc:                            # noqa: BLE001
+                if self.requested_transport == "symm":
+                    raise
+                self.symm_error = repr(exc)
+        if self.want_overlap and self.n_send:
+            bp = np.unique(send_idx // P)
+            mask = np.zeros(engine.n_patches, dtype=bool)
+            mask[bp] = True
+            self._plist_b = torch.as_tensor(np.nonzero(mask)[0].astype(np.int32)).to(engine.device)
+            self._plist_i = torch.as_tensor(np.nonzero(~mask)[0].astype(np.int32)).to(engine.device)
+            self._comm_stream = torch.cuda.Stream(device=engine.device)
+            self._ev_b = torch.cuda.Event()
+            self._ev_x = torch.cuda.Event()
+            self.overlap = self._plist_b.numel() > 0 and self._plist_i.numel() > 0
+
+    def _alloc_symmetric(self, rec, nbuf):
+        import torch.distributed as dist
+        torch, eng = self.torch, self.engine
+        lens = [(self._pads[r] + self.parts[r].n_ghost) * rec for r in range(self.world)]
+        L = (max(lens) + 31) // 32 * 32                 # same size on every rank; 256-B aligned sub-buffers (TMA)
+        t = self._symm_mem.empty(nbuf * L, dtype=torch.float64, device=eng.device)
+        t.zero_()
+        hdl = self._symm_mem.rendezvous(t, dist.group.WORLD)
+        return L, t, hdl
+
+    def alloc(self, rec, nbuf=3):
+        """`nbuf` state arrays of record length `rec` (9 = SWE, 3 = tracer) whose ghost blocks peers can write."""
+        torch, eng, p = self.torch, self.engine, self.part
+        n_local = (eng.n_owned_pad + p.n_ghost) * rec
+        if self.transport != "symm":
+            bufs = [torch.zeros(n_local, dtype=torch.float64, device=eng.device) for _ in range(nbuf)]
+            for b, t in enumerate(bufs):
+                self._buf_info[t.data_ptr()] = (rec, None, b)
+            if rec not in self._sendbuf:
+                self._sendbuf[rec] = torch.zeros((max(self.n_send, 1), rec), dtype=torch.float64, device=eng.device)
+            return bufs
+        L, t, hdl = self._alloc_symmetric(rec, nbuf)
+        bufs = [t[b * L:b * L + n_local] for b in range(nbuf)]
+        ptrs = [int(x) for x in hdl.buffer_ptrs]
+        dst = np.zeros((nbuf, max(self.n_send, 1)), dtype=np.uint64)
+        e = 0
+        for q in range(self.world):
+            if q not in p.send_lists:
+                continue
+            n = p.send_lists[q].shape[0]
+            # my cells sit in q's ghost block after the ghosts owned by lower ranks, in q's ghost order
+            first = int((self.parts[q].ghost_owner < self.rank).sum())
+            slot = self._pads[q] + first + np.arange(n, dtype=np.int64)
+            for b in range(nbuf):
+                dst[b, e:e + n] = np.uint64(ptrs[q]) + ((b * L + slot * rec) * 8).astype(np.uint64)
+            e += n
+        grp = dict(L=L, tensor=t, handle=hdl,
+                   dst_ptrs=[torch.as_tensor(dst[b].view(np.int64)).to(eng.device) for b in range(nbuf)])
+        gid = len(self._groups)
+        self._groups[gid] = grp
+        for b, bt in enumerate(bufs):
+            self._buf_info[bt.data_ptr()] = (rec, gid, b)
+        return bufs
+
+    # ------------------------------------------------------------ per-stage exchange
+    def exchange(self, state):
+        """Make the ghost block of `state` current on every rank (stream ordered on the current stream)."""
+        eng, p = self.engine, self.part
+        rec, gid, b = self._buf_info[state.data_ptr()]
+        if self.transport == "symm":
+            grp = self._groups[gid]
+            if self.n_send:
+                eng.push_cells(state, self.send_idx, grp["dst_ptrs"][b], rec)
+            grp["handle"].barrier(channel=0)        # every rank's stores have landed before anyone reads its ghosts
+            return
+        sb = self._sendbuf[rec]
+        if self.n_send:
+            eng.gather_cells(state, self.send_idx, rec, sb)
+        g0 = eng.n_owned_pad * rec
+        ghost = state[g0:g0 + p.n_ghost * rec].view(-1, rec)
+        exchange_halo(p, sb[:self.n_send], ghost)
+
+    def swe_stage(self, a0, a1, bdt, src, u0, dst):
+        """Stage kernel + halo exchange of its output; boundary patches first so the exchange overlaps the rest."""
+        eng, torch = self.engine, self.torch
+        if not self.overlap:
+            eng.swe_stage(a0, a1, bdt, src, u0, dst)
+            self.exchange(dst)
+            return
+        main = torch.cuda.current_stream(eng.device)
+        eng.set_patch_list(self._plist_b)
+        eng.swe_stage(a0, a1, bdt, src, u0, dst)                 # partition-boundary patches
+        self._ev_b.record(main)
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(self._ev_b)
+            self.exchange(dst)                                    # push + barrier while the interior computes
+            self._ev_x.record(self._comm_stream)
+        eng.set_patch_list(self._plist_i)
+        eng.swe_stage(a0, a1, bdt, src, u0, dst)                 # interior patches
+        eng.set_patch_list(None)
+        main.wait_event(self._ev_x)                              # ghosts of dst are complete before the next stage
+
+    def kernels_per_swe_stage(self):
+        return (2 if self.overlap else 1) + (1 if self.n_send else 0)
+
+    def allreduce_sum(self, t):
+        import torch.distributed as dist
+        dist.all_reduce(t)
+        return t
+
+
+def distribute_mesh(mesh: Mesh2D, rank=None, world=None, halo="vertex", transport="auto", overlap=True):
+    """
+    This rank's share of `mesh` as a shim mesh (owned cells first, then ghosts) carrying a `HaloPlan`; the
+    integrators, the limiter and FlowSolver2d pick the plan up from the mesh.  Analogue of Firedrake distributing a
+    mesh over COMM_WORLD; rank / world default to torch.distributed's.
+    """
+    import torch.distributed as dist
+    from .shim import ShimMesh
+    if rank is None:
+        rank = dist.get_rank()
+    if world is None:
+        world = dist.get_world_size()
+    parts = partition_mesh(mesh, world, halo=halo)
+    lm = parts[rank].mesh
+    sm = ShimMesh(lm)
+    sm.boundary_len = dict(lm.meta["global_boundary_len"])     # boundary lengths are global sums (utility.py:821-832)
+    sm.halo_plan = HaloPlan(parts, rank, transport=transport, overlap=overlap)
+    sm.global_mesh = mesh
+    return sm
+
+
 # ---------------------------------------------------------------------- bench drivers
 def _make_solver(mesh, setup, wd, n_owned=None):
     """FlowSolver2d mirror configured for the North Sea workload (thetis_b200/workloads.py)."""
     from . import solver2d
-    from .shim import Function, FunctionSpace, Constant, as_shim_mesh
-    sm = as_shim_mesh(mesh)
+    from .shim import Function, FunctionSpace, Constant, ShimMesh, as_shim_mesh
+    sm = mesh if isinstance(mesh, ShimMesh) else as_shim_mesh(mesh)
     P1 = FunctionSpace(sm, "CG", 1)
     bath = Function(P1, name="Bathymetry")
     bath.dat.data[:] = setup["bath"]
@@ -180,8 +363,9 @@ class SingleSWE:
         import torch
         from .workloads import M2_PERIOD
         self.torch = torch
-        self.mesh, self.setup = mesh, setup
         self.solver, self.tide = _make_solver(mesh, setup, wd)
+        mesh = self.solver.mesh2d.topology_mesh          # local Mesh2D (whole mesh on one GPU)
+        self.mesh, self.setup = mesh, setup
         s = self.solver
         s.create_function_spaces()
         s.create_equations()
@@ -215,17 +399,50 @@ class SingleSWE:
     def n_owned(self):
         return self.mesh.n_cells
 
-    def launches(self):
-        return self.eng.launch_count()
-
     def stage_launches_per_step(self):
         return 3
 
+    def launches_per_step(self):
+        return 3
+
+    def enable_graph(self):
+        """Capture one resident step (3 fused stage launches + halo traffic) in a CUDA graph."""
+        torch = self.torch
+        self.ts.advance_device()                 # warm-up outside capture (lazy uploads)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.ts.advance_device()
+        self._graph = g
+
+    def enable_stage_graphs(self):
+        """One CUDA graph per RK stage for the e2e path: the host-side forcing refresh stays between the launches."""
+        torch, ts = self.torch, self.ts
+        ts.advance_device()
+        torch.cuda.synchronize()
+        self._stage_graphs = []
+        for i in range(ts.n_stages):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ts._launch_stage(i)
+            self._stage_graphs.append(g)
+        ts.stage_graphs = self._stage_graphs     # SSPRK33.solve_stage replays them instead of re-launching
+
+    def launches(self):
+        return self.eng.launch_count() + getattr(self, "_replays", 0) * self.launches_per_step()
+
     def step_resident(self):
-        self.ts.advance_device()
+        g = getattr(self, "_graph", None)
+        if g is not None:
+            g.replay()
+            self._replays = getattr(self, "_replays", 0) + 1
+        else:
+            self.ts.advance_device()
 
     def step_e2e(self):
         self.ts.advance(self.t, self.update_forcings)
+        if getattr(self.ts, "stage_graphs", None):
+            self._replays = getattr(self, "_replays", 0) + 1
         self.t += self.dt
         self.eng.swe_integrals(self.ts.device_state(), self._norms)
         self._norms_host.copy_(self._norms, non_blocking=True)
@@ -248,262 +465,48 @@ class SingleSWE:
         return (s.fields.uv_2d.dat.data_ro.reshape(-1, 3, 2).copy(), s.fields.elev_2d.dat.data_ro.reshape(-1, 3).copy())
 
 
-class PartitionedSWE:
-    """North Sea workload on `world` GPUs: one process per GPU, one halo exchange per RK stage over NCCL."""
+def localize_setup(setup, lm):
+    """Restrict the global workload arrays (thetis_b200.workloads.north_sea_setup) to a rank's local mesh."""
+    gv, gc, gb = lm.meta["global_vertices"], lm.meta["global_cells"], lm.meta["global_bfacets"]
+    out = dict(setup)
+    for k in ("bath", "coriolis", "manning"):
+        out[k] = setup[k][gv]
+    for k in ("eta0", "uv0"):
+        out[k] = setup[k][gc]
+    out["tide_phase"] = setup["tide_phase"][gb]
+    return out
 
-    def __init__(self, mesh, setup, rank, world, wd=True, transport="auto", overlap=True):
-        """
-        transport: 'nccl'  pack + NCCL all-to-all into the ghost block;
-                   'symm'  state buffers in torch symmetric memory, send cells stored straight into the peers'
-                           ghost blocks over NVLink (tb_push_cells) + one device-side barrier per stage;
-                   'auto'  'symm' when symmetric memory can be set up, else 'nccl'.
-        """
-        import torch
-        from . import _lib as L
-        from .engine import Engine
-        from .workloads import M2_PERIOD
-        self.torch = torch
+
+class PartitionedSWE(SingleSWE):
+    """
+    North Sea workload on `world` GPUs through the SAME reference-shaped surface as `SingleSWE` (FlowSolver2d mirror
+    -> SSPRK33): the mesh is distributed with `distribute_mesh`, the integrator picks the rank's HaloPlan up from it
+    and exchanges the one-deep halo once per RK stage.
+    """
+
+    def __init__(self, mesh, setup, rank, world, wd=True, transport="auto", overlap=True, halo="facet"):
         self.rank, self.world = rank, world
-        parts = partition_mesh(mesh, world)
-        self.part = parts[rank]
-        p = self.part
-        lm = p.mesh
-        self.eng = eng = Engine(lm, n_owned=p.n_owned)
-        gv = lm.meta["global_vertices"]
-        eng.set_option(L.OPT_NONLINEAR, 1)
-        eng.set_option(L.OPT_LAX_FRIEDRICHS, 1)
-        eng.set_option(L.OPT_WETTING_DRYING, bool(wd))
-        eng.set_option(L.OPT_WD_ALPHA, setup["wd_alpha"])
-        eng.set_field(L.F_BATHYMETRY, setup["bath"][gv])
-        eng.set_field(L.F_MANNING, setup["manning"][gv])
-        eng.set_field(L.F_CORIOLIS, setup["coriolis"][gv])
-        for mk, ln in lm.meta["global_boundary_len"].items():
-            eng.set_boundary_length(mk, ln)
-        eng.set_bc(0, 100, L.BC_ELEV | L.BC_UV, [0, 0, 0, 0, 0, 0])
-        gb = lm.meta["global_bfacets"]
-        self._phase = setup["tide_phase"][gb]
-        self._has_open = bool((lm.bf_marker == 100).any())
-        self._omega = 2 * np.pi / M2_PERIOD
-        self._n_open = int((lm.bf_marker == 100).sum())
-        if self._has_open:
-            eng.set_bc_array(0, 100, L.BC_ELEV, np.sin(self._phase))
-        glob = np.concatenate([p.owned_global, p.ghost_global])
-        uv = setup["uv0"][glob]
-        eta = setup["eta0"][glob]
-        # state: owned (padded) + ghosts
-        dev = eng.device
-        send_idx = np.concatenate([p.send_lists[q] for q in range(world) if q in p.send_lists]) if p.send_lists else np.zeros(0, np.int64)
-        self.transport = "nccl"
-        self._symm = None
-        if transport in ("auto", "symm"):
-            try:
-                self._setup_symmetric(parts, send_idx)
-                self.transport = "symm"
-            except Exception as exc:            # noqa: BLE001  (fall back to NCCL all-to-all, same results)
-                if transport == "symm":
-                    raise
-                self._symm_error = repr(exc)
-        if self.transport == "nccl":
-            self.buf = [eng.new_state(), eng.new_state(), eng.new_state()]
-        A = self.buf[0]
-        own = eng.upload_nodal(uv[:p.n_owned], eta[:p.n_owned])
-        A[:own.numel()].copy_(own)
-        if p.n_ghost:
-            grec = np.concatenate([uv[p.n_owned:].reshape(-1, 6), eta[p.n_owned:]], axis=1)
-            A[eng.n_owned_pad * 9:eng.n_owned_pad * 9 + grec.size] = torch.as_tensor(grec.reshape(-1)).to(dev)
-        self.send_idx = torch.as_tensor(send_idx.astype(np.int32)).to(dev)
-        self.sendbuf = torch.zeros((max(int(send_idx.shape[0]), 1), 9), dtype=torch.float64, device=dev)
-        self.n_send = int(send_idx.shape[0])
-        self.dt = setup["dt"]
-        self.t = 0.0
-        self._norms = torch.zeros(4, dtype=torch.float64, device=dev)
-        self._norms_host = torch.zeros(4, dtype=torch.float64).pin_memory()
-        self._L = L
-        from .rungekutta import SSPRK33, butcher_to_shuosher_form
-        self._alpha, self._beta = butcher_to_shuosher_form(SSPRK33.a, SSPRK33.b)
-        self._c = [float(v) for v in SSPRK33.c]
-        self.overlap = False
-        if overlap:
-            self._setup_overlap()
-
-    def _setup_symmetric(self, parts, send_idx):
-        """State buffers in symmetric memory; per buffer the peer addresses every send cell must be stored to."""
-        import torch
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
-        eng, p, world, rank = self.eng, self.part, self.world, self.rank
-        P = eng.patch_size
-        pads = [((q.n_owned + P - 1) // P) * P for q in parts]
-        lens = [(pads[r] + parts[r].n_ghost) * 9 for r in range(world)]
-        L = (max(lens) + 31) // 32 * 32                 # same size on every rank; 256-B aligned sub-buffers (TMA)
-        t = symm_mem.empty(3 * L, dtype=torch.float64, device=eng.device)
-        t.zero_()
-        hdl = symm_mem.rendezvous(t, dist.group.WORLD)
-        self._symm = (t, hdl)
-        self.buf = [t[i * L:i * L + eng.state_len] for i in range(3)]
-        ptrs = [int(x) for x in hdl.buffer_ptrs]
-        dst = np.zeros((3, max(send_idx.shape[0], 1)), dtype=np.uint64)
-        e = 0
-        for q in range(world):
-            if q not in p.send_lists:
-                continue
-            n = p.send_lists[q].shape[0]
-            # my cells sit in q's ghost block after the ghosts owned by lower ranks, in q's ghost order
-            first = int((parts[q].ghost_owner < rank).sum())
-            slot = pads[q] + first + np.arange(n, dtype=np.int64)
-            for b in range(3):
-                dst[b, e:e + n] = np.uint64(ptrs[q]) + ((b * L + slot * 9) * 8).astype(np.uint64)
-            e += n
-        self._dst_ptrs = [torch.as_tensor(dst[b].view(np.int64)).to(eng.device) for b in range(3)]
-        self._buf_index = {self.buf[b].data_ptr(): b for b in range(3)}
-
-    def _exchange(self, state):
-        eng, p = self.eng, self.part
-        if self.transport == "symm":
-            b = self._buf_index[state.data_ptr()]
-            if self.n_send:
-                eng.push_cells(state, self.send_idx, self._dst_ptrs[b], 9)
-            self._symm[1].barrier(channel=0)        # every rank's stores have landed before anyone reads its ghosts
-            return
-        if self.n_send:
-            eng.gather_cells(state, self.send_idx, 9, self.sendbuf)
-        ghost = state[eng.n_owned_pad * 9:eng.n_owned_pad * 9 + p.n_ghost * 9].view(-1, 9)
-        exchange_halo(p, self.sendbuf[:self.n_send], ghost)
-
-    def _setup_overlap(self):
-        """Patches holding cells a peer needs run first; their halo push overlaps the remaining patches."""
-        torch = self.torch
-        eng = self.eng
-        P = eng.patch_size
-        bp = np.unique(self.send_idx.cpu().numpy().astype(np.int64) // P) if self.n_send else np.zeros(0, np.int64)
-        mask = np.zeros(eng.n_patches, dtype=bool)
-        mask[bp] = True
-        self._plist_b = torch.as_tensor(np.nonzero(mask)[0].astype(np.int32)).to(eng.device)
-        self._plist_i = torch.as_tensor(np.nonzero(~mask)[0].astype(np.int32)).to(eng.device)
-        self._comm_stream = torch.cuda.Stream(device=eng.device)
-        self._ev_b = torch.cuda.Event()
-        self._ev_x = torch.cuda.Event()
-        self.overlap = self._plist_b.numel() > 0 and self._plist_i.numel() > 0
-
-    def _stage(self, a0, a1, bdt, src, u0, dst):
-        eng, torch = self.eng, self.torch
-        if not getattr(self, "overlap", False):
-            eng.swe_stage(a0, a1, bdt, src, u0, dst)
-            self._exchange(dst)
-            return
-        main = torch.cuda.current_stream(eng.device)
-        eng.set_patch_list(self._plist_b)
-        eng.swe_stage(a0, a1, bdt, src, u0, dst)                 # partition-boundary patches
-        self._ev_b.record(main)
-        with torch.cuda.stream(self._comm_stream):
-            self._comm_stream.wait_event(self._ev_b)
-            self._exchange(dst)                                   # push + barrier while the interior computes
-            self._ev_x.record(self._comm_stream)
-        eng.set_patch_list(self._plist_i)
-        eng.swe_stage(a0, a1, bdt, src, u0, dst)                 # interior patches
-        eng.set_patch_list(None)
-        main.wait_event(self._ev_x)                              # ghosts of dst are complete before the next stage
-
-    def _step(self, forcing=None):
-        A, B, C = self.buf
-        dt = self.dt
-        al, be, c = self._alpha, self._beta, self._c      # the reference's own Shu-Osher coefficients
-        if forcing:
-            forcing(self.t + c[0] * dt)
-        self._stage(0.0, float(al[1][0]), float(be[1][0]) * dt, A, None, B)
-        if forcing:
-            forcing(self.t + c[1] * dt)
-        self._stage(float(al[2][0]), float(al[2][1]), float(be[2][1]) * dt, B, A, C)
-        if forcing:
-            forcing(self.t + c[2] * dt)
-        self._stage(float(al[3][0]), float(al[3][2]), float(be[3][2]) * dt, C, A, A)
-
-    def enable_graph(self):
-        """Capture one whole resident step (3 stages incl. halo traffic) in a CUDA graph: at 8 GPUs a stage is ~45 us
-        of GPU work, less than what the Python launch path costs."""
-        torch = self.torch
-        self._step()                                             # warm-up outside capture (lazy uploads, allocations)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._step()
-        self._graph = g
-        self._graph_launches = self.launches_per_step()
-
-    def launches_per_step(self):
-        per_stage = (2 if getattr(self, "overlap", False) else 1) + (1 if self.n_send else 0) + \
-            (0 if self.transport == "symm" else 0)
-        return 3 * per_stage
-
-    def update_forcings(self, t):
-        if self._has_open:
-            if not hasattr(self, "_tide_buf"):
-                self._open_rows = np.nonzero(self.part.mesh.bf_marker == 100)[0]
-                self._open_phase = self._phase[self._open_rows]
-                self._tide_buf = np.zeros_like(self._phase)
-            self._tide_buf[self._open_rows] = np.sin(self._omega * t + self._open_phase)
-            self.eng.set_bc_array(0, 100, self._L.BC_ELEV, self._tide_buf)
+        sm = distribute_mesh(mesh, rank, world, halo=halo, transport=transport, overlap=overlap)
+        self.part = sm.halo_plan.part
+        super().__init__(sm, localize_setup(setup, self.part.mesh), wd=wd)
+        self.plan = sm.halo_plan
+        self.transport = self.plan.transport
+        self.overlap = self.plan.overlap
 
     def n_owned(self):
         return self.part.n_owned
 
-    def launches(self):
-        return self.eng.launch_count() + getattr(self, "_replays", 0) * getattr(self, "_graph_launches", 0)
-
     def stage_launches_per_step(self):
-        return 6 if getattr(self, "overlap", False) else 3
+        return 3 * (2 if self.plan.overlap else 1)
 
-    def step_resident(self):
-        g = getattr(self, "_graph", None)
-        if g is not None:
-            g.replay()
-            self._replays = getattr(self, "_replays", 0) + 1
-        else:
-            self._step()
-
-    def enable_stage_graphs(self):
-        """One CUDA graph per RK stage (kernels + halo traffic); the host-side forcing upload stays between them."""
-        torch = self.torch
-        A, B, C = self.buf
-        dt = self.dt
-        al, be = self._alpha, self._beta
-        args = [(0.0, float(al[1][0]), float(be[1][0]) * dt, A, None, B),
-                (float(al[2][0]), float(al[2][1]), float(be[2][1]) * dt, B, A, C),
-                (float(al[3][0]), float(al[3][2]), float(be[3][2]) * dt, C, A, A)]
-        self._step()
-        torch.cuda.synchronize()
-        self._stage_graphs = []
-        for a in args:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._stage(*a)
-            self._stage_graphs.append(g)
-        # graph capture ran each stage once more on real data: harmless for the bench (state stays finite), and
-        # tests that need exact step counts use _step() directly
-
-    def step_e2e(self):
-        sg = getattr(self, "_stage_graphs", None)
-        if sg is None:
-            self._step(self.update_forcings)
-        else:
-            for i in range(3):
-                self.update_forcings(self.t + self._c[i] * self.dt)     # host forcing -> H2D, stream ordered
-                sg[i].replay()
-            self._replays_stage = getattr(self, "_replays_stage", 0) + 1
-        self.t += self.dt
-        self.eng.swe_integrals(self.buf[0], self._norms)
-        self._norms_host.copy_(self._norms, non_blocking=True)
+    def launches_per_step(self):
+        return 3 * self.plan.kernels_per_swe_stage()
 
     def e2e_path(self):
-        return ("PartitionedSWE driver -> C-ABI (tb_swe_stage + tb_push_cells, one CUDA graph per RK stage): tidal "
-                "elevation computed on the host every stage and copied H2D from pinned memory (tb_set_bc_array), "
-                "print_state integrals reduced on the device and read back every step")
-
-    def h2d_bytes_per_step(self):
-        return 3 * self._n_open * 2 * 8
-
-    def d2h_bytes_per_step(self):
-        return 4 * 8
+        return ("distribute_mesh -> " + SingleSWE.e2e_path(self) + "; one halo exchange per RK stage ("
+                + self.plan.transport + ")")
 
     def owned_nodal(self):
-        return self.eng.download_nodal(self.buf[0])
+        uv, eta = self.state_nodal()
+        n = self.part.n_owned
+        return uv[:n], eta[:n]

@@ -120,9 +120,8 @@ class ERKGenericShuOsher:
         self._kind = self._equation_kind()
         mesh_obj = self._function_space().mesh()
         self.adaptor = get_adaptor(mesh_obj)
-        if self.adaptor.engine is None:
-            self.adaptor.engine = Engine(self.adaptor.mesh)
-        self.engine = self.adaptor.engine
+        self.engine = self.adaptor.get_engine()
+        self.halo = self.adaptor.halo          # None on a single GPU
         self._host_stale = False
         self._last_host_version = None
         self._field_versions = {}
@@ -156,7 +155,7 @@ class ERKGenericShuOsher:
                 raise NotImplementedError("velocity and elevation P1DG spaces must share their node numbering")
             self.node_map = torch.as_tensor(nm_u.reshape(-1)).to(dev)
             n_nodes = int(np.asarray(eta_f.dat.data_ro).shape[0])
-            self.buf = [eng.new_state() for _ in range(3)]
+            self.buf = self.halo.alloc(9) if self.halo is not None else [eng.new_state() for _ in range(3)]
             self._d_uv = torch.empty((n_nodes, 2), dtype=torch.float64, device=dev)
             self._d_eta = torch.empty(n_nodes, dtype=torch.float64, device=dev)
             self._h_uv = torch.empty((n_nodes, 2), dtype=torch.float64).pin_memory()
@@ -166,7 +165,7 @@ class ERKGenericShuOsher:
             nm = ad.dg_node_map(self.solution.function_space())
             self.node_map = torch.as_tensor(nm.reshape(-1)).to(dev)
             n_nodes = int(np.asarray(self.solution.dat.data_ro).shape[0])
-            self.buf = [eng.new_tracer() for _ in range(3)]
+            self.buf = self.halo.alloc(3) if self.halo is not None else [eng.new_tracer() for _ in range(3)]
             self._d_q = torch.empty(n_nodes, dtype=torch.float64, device=dev)
             self._h_q = torch.empty(n_nodes, dtype=torch.float64).pin_memory()
             self._own_swe_state = None
@@ -336,6 +335,8 @@ class ERKGenericShuOsher:
             self._h_q.numpy()[...] = np.asarray(self.solution.dat.data_ro)
             self._d_q.copy_(self._h_q, non_blocking=True)
             eng.tracer_from_field(self._d_q, self.node_map, self.buf[0])
+        if self.halo is not None:
+            self.halo.exchange(self.buf[0])        # ghost records come from their owners, not from the host copy
         self._host_stale = False
         self._last_host_version = self._solution_version()
 
@@ -401,7 +402,7 @@ class ERKGenericShuOsher:
         if uv_f is None:
             raise NotImplementedError("tracer equation without uv_2d is trivial; not on the accelerated path")
         if self._own_swe_state is None:
-            self._own_swe_state = eng.new_state()
+            self._own_swe_state = self.halo.alloc(9, nbuf=1)[0] if self.halo is not None else eng.new_state()
         el_f = self.fields.get("elev_2d")
         uvd = torch.as_tensor(np.ascontiguousarray(np.asarray(uv_f.dat.data_ro).reshape(-1, 2))).to(eng.device)
         if el_f is not None:
@@ -409,6 +410,8 @@ class ERKGenericShuOsher:
         else:
             ed = torch.zeros(uvd.shape[0], dtype=torch.float64, device=eng.device)
         eng.state_from_fields(uvd, ed, self.node_map, self._own_swe_state)
+        if self.halo is not None:
+            self.halo.exchange(self._own_swe_state)
         return self._own_swe_state
 
     def solve_stage(self, i_stage, t, update_forcings=None):
@@ -418,7 +421,13 @@ class ERKGenericShuOsher:
         if i_stage == 0 and not self._host_stale and self._host_changed():
             self.upload()                      # the host copy was modified since the last sync
         self._push_dynamic()
-        self._launch_stage(i_stage)
+        graphs = getattr(self, "stage_graphs", None)
+        if graphs:
+            graphs[i_stage].replay()           # same launches, captured once (the forcing arrays are read at replay time)
+            if i_stage == self.n_stages - 1:
+                self._host_stale = True
+        else:
+            self._launch_stage(i_stage)
 
     def _launch_stage(self, i_stage):
         """One fused kernel launch: residual + mass inverse + Shu-Osher update of stage i."""
@@ -437,9 +446,14 @@ class ERKGenericShuOsher:
         self._cur = dst
         u0 = A if i_stage > 0 else None
         if self._kind == "swe":
-            eng.swe_stage(a0, a1, bdt, src, u0, dst)
+            if self.halo is not None:
+                self.halo.swe_stage(a0, a1, bdt, src, u0, dst)        # + one halo exchange per stage
+            else:
+                eng.swe_stage(a0, a1, bdt, src, u0, dst)
         else:
             eng.tracer_stage(a0, a1, bdt, src, u0, dst, self._swe_state_for_tracer())
+            if self.halo is not None:
+                self.halo.exchange(dst)
         if last:
             if dst is not A:
                 self.buf[0], self.buf[1] = self.buf[1], self.buf[0]

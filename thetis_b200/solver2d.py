@@ -333,6 +333,8 @@ class FlowSolver2d:
         if sw is not None:
             out = torch.zeros(4, dtype=torch.float64, device=sw.engine.device)
             sw.engine.swe_integrals(sw.device_state(), out)
+            if sw.halo is not None:
+                sw.halo.allreduce_sum(out)          # norms are global (Firedrake's norm() reduces over the communicator)
             o = out.cpu().numpy()
             entries += [("eta norm", float(np.sqrt(o[0])), "14.4f"), ("u norm", float(np.sqrt(o[1])), "14.4f")]
             self.last_norms = (float(np.sqrt(o[0])), float(np.sqrt(o[1])))
