@@ -103,10 +103,8 @@ def _mesh2d_from_firedrake(mesh):
     for c, lf, mk in zip(fcell, flocal, markers):
         if c >= ncell:
             continue
-        a_, b_ = tmap[c, FACET_NODES[lf, 0]], tmap[c, FACET_NODES[lf, 1]]
         ta, tb = int(topo[remap[cmap[c, FACET_NODES[lf, 0]]]]), int(topo[remap[cmap[c, FACET_NODES[lf, 1]]]])
         em[(min(ta, tb), max(ta, tb))] = int(mk)
-        del a_, b_
     m.build_connectivity(edge_markers=em)
     m.cell_perm = np.arange(m.n_cells, dtype=np.int64)
     return m, swap
@@ -131,7 +129,6 @@ class MeshAdaptor:
         self.swap = swap
         if renumber and not base.meta.get("sfc"):
             self.mesh = sfc_renumber(base)
-            self.perm = np.argsort(np.argsort(self.mesh.cell_perm))  # placeholder, fixed below
             # cell_perm composes with earlier renumberings of `base`; we need new -> base order
             base_perm = base.cell_perm if base.cell_perm is not None else np.arange(base.n_cells)
             inv = np.empty(base.n_cells, dtype=np.int64)

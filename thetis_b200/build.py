@@ -15,7 +15,7 @@ HEADERS = [os.path.join(CSRC, "tb_internal.h"),
            os.path.join(HERE, "..", "include", "thetis_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false" if False else "-Xptxas=-v",
+    "-Xcompiler", "-fPIC", "-shared", "-Xptxas=-v",
 ]
 
 

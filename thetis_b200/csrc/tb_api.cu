@@ -20,10 +20,6 @@ struct FieldStore {
     int col = -1;
 };
 
-struct BcHost {
-    std::vector<TbBcSlot> slots;   // per marker slot
-};
-
 struct tb_ctx {
     int device = 0;
     std::string err;
@@ -51,7 +47,6 @@ struct tb_ctx {
     double *d_ext[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // elev, uv, un, flux, value (swe)
     double *d_ext_tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_area = nullptr;
-    std::vector<double> h_stage;        // pinned staging? (plain host vector; copies are small)
     // ring of pinned staging buffers for boundary data uploads (no stream stall in steady state)
     static const int NSTAGE = 8;
     double *h_pinned[NSTAGE] = {nullptr};

@@ -313,7 +313,6 @@ def read_gmsh(path):
     """
     with open(path, "r") as fh:
         lines = fh.read().split("\n")
-    it = iter(range(len(lines)))
     nodes = None
     tris, edges, etags = [], [], []
     i = 0
@@ -345,7 +344,6 @@ def read_gmsh(path):
             i += 2 + n
         else:
             i += 1
-    del it
     ids, xy = nodes
     remap = np.full(int(ids.max()) + 1, -1, dtype=np.int64)
     remap[ids] = np.arange(ids.shape[0])
