@@ -74,7 +74,12 @@ typedef enum {
     TB_OPT_LF_TRACER = 8,              /* use_lax_friedrichs_tracer               */
     TB_OPT_LF_TRACER_SCALING = 9,      /* lax_friedrichs_tracer_scaling_factor    */
     TB_OPT_TRACER_VEL_FACTOR = 10,     /* tracer_advective_velocity_factor        */
-    TB_OPT_FORCE_GENERIC_KERNEL = 11   /* developer/test switch: bypass the specialised stage kernels */
+    TB_OPT_FORCE_GENERIC_KERNEL = 11,  /* developer/test switch: bypass the specialised stage kernels */
+    TB_OPT_SIPG_FACTOR = 12,           /* sipg_factor (options.py:730; shallowwater_eq.py:558)      */
+    TB_OPT_SIPG_FACTOR_TRACER = 13,    /* sipg_factor_tracer (options.py:732; tracer_eq_2d.py:235)  */
+    TB_OPT_GRAD_DIV_VISCOSITY = 14,    /* use_grad_div_viscosity_term (options.py:597)              */
+    TB_OPT_GRAD_DEPTH_VISCOSITY = 15,  /* use_grad_depth_viscosity_term (options.py:602), default on */
+    TB_OPT_TRACER_CONSERVATIVE = 16    /* tracer use_conservative_form (options.py:543; tracer_eq_2d.py:323-437) */
 } tb_option;
 
 /* Coefficient fields: the `fields` dict of solver2d.py:546-558 plus bathymetry. */
@@ -89,12 +94,15 @@ typedef enum {
     TB_F_MOMENTUM_SOURCE = 7,  /* 'momentum_source' (2 components)                */
     TB_F_VOLUME_SOURCE = 8,    /* 'volume_source'                                 */
     TB_F_TRACER_SOURCE = 9,    /* 'source-<label>' of the tracer equation         */
-    TB_F_COUNT = 10
+    TB_F_VISCOSITY = 10,       /* 'viscosity_h' (HorizontalViscosityTerm, shallowwater_eq.py:554-616) */
+    TB_F_DIFFUSIVITY = 11,     /* 'diffusivity_h-<label>' (HorizontalDiffusionTerm, tracer_eq_2d.py:226-278) */
+    TB_F_COUNT = 12
 } tb_field;
 
 /* Boundary tags (shallowwater_eq.py:243-267); a marker's opcode is the OR of
  * the tags present.  0 = closed (land) boundary. */
-enum { TB_BC_ELEV = 1, TB_BC_UV = 2, TB_BC_UN = 4, TB_BC_FLUX = 8, TB_BC_VALUE = 16 };
+enum { TB_BC_ELEV = 1, TB_BC_UV = 2, TB_BC_UN = 4, TB_BC_FLUX = 8, TB_BC_VALUE = 16,
+       TB_BC_DIFF_FLUX = 64 /* tracer 'diff_flux' (tracer_eq_2d.py:264-265); 32 is reserved */ };
 
 /* ---- lifetime ---------------------------------------------------------- */
 int tb_create(tb_ctx **out, const tb_mesh *mesh, int device);
@@ -116,10 +124,10 @@ int tb_set_field_const(tb_ctx *ctx, int field, const double *value, int ncomp);
 int tb_set_field_vertex(tb_ctx *ctx, int field, const double *values, int ncomp);
 int tb_clear_field(tb_ctx *ctx, int field);     /* field = None                     */
 /* Boundary condition of one marker for equation eq (0 = shallow water,
- * 1 = tracer): opcode = OR of TB_BC_*, consts = {elev, uv_x, uv_y, un, flux, value}.
+ * 1 = tracer): opcode = OR of TB_BC_*, consts = {elev, uv_x, uv_y, un, flux, value, diff_flux, reserved}.
  * replaces ShallowWaterTerm.get_bnd_functions (shallowwater_eq.py:232-272)
  * and TracerTerm.get_bnd_functions (tracer_eq_2d.py:78-115) */
-int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const double consts[6]);
+int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const double consts[8]);
 /* Spatially varying datum for one tag of one marker: HOST values at the two
  * nodes of every exterior facet of the mesh, [n_bfacets*2*ncomp] (entries of
  * other markers ignored).  Copied asynchronously on `stream`. */
@@ -169,6 +177,16 @@ int tb_tracer_to_field(tb_ctx *ctx, const double *c, const int32_t *node_map,
  * cells (print_state norms, solver2d.py:955-956; VolumeConservation2DCallback).
  * `out` is a DEVICE pointer to 4 doubles. */
 int tb_swe_integrals(tb_ctx *ctx, const double *state, double *out, void *stream);
+/* Tracer diagnostics reduced on the device (callback.py:369-392,448-484): out[0] = int c dx
+ * (ConservativeTracerMassConservation2DCallback), out[1] = int H c dx with H = total depth of `swe_state`
+ * (TracerMassConservation2DCallback / comp_tracer_mass_2d), out[2] = min c, out[3] = max c
+ * (TracerOvershootCallBack).  `out`: DEVICE pointer to 4 doubles.  tb_swe_integrals' out[3] is
+ * int (eta + bathymetry) dx (VolumeConservation2DCallback / comp_volume_2d). */
+int tb_tracer_integrals(tb_ctx *ctx, const double *c, const double *swe_state, double *out, void *stream);
+/* out = sum_j w[j]*x[j], j < n <= 6, over `len` doubles (len even): the stage combinations of the Butcher-form
+ * integrators (ERKGeneric.update_solution / get_final_solution, rungekutta.py:816-852).  x: HOST array of n
+ * DEVICE pointers, w: HOST weights.  out may alias any x[j]. */
+int tb_lincomb(tb_ctx *ctx, int n, const double *const *x, const double *w, double *out, int64_t len, void *stream);
 
 /* ---- multi-GPU halo (one-deep element halo) -------------- */
 /* Gather the records of `n` cells listed in DEVICE idx into a contiguous

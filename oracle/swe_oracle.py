@@ -13,12 +13,16 @@ What is restated (all paths relative to /root/reference):
 * thetis/shallowwater_eq.py:619-663   CoriolisTerm, WindStressTerm, AtmosphericPressureTerm
 * thetis/shallowwater_eq.py:666-701   QuadraticDragTerm (constant / Manning)
 * thetis/shallowwater_eq.py:728-740   LinearDragTerm
+* thetis/shallowwater_eq.py:513-616   HorizontalViscosityTerm (SIPG; grad-div and grad-depth variants)
 * thetis/shallowwater_eq.py:794-831   MomentumSourceTerm, ContinuitySourceTerm
 * thetis/shallowwater_eq.py:232-296   get_bnd_functions / impose_dynamic_bnd
 * thetis/utility.py:936-996           DepthExpression
 * thetis/equation.py:99-105           mass term
 * thetis/rungekutta.py:13-87,326-347,870-952  Shu-Osher SSPRK33
 * thetis/tracer_eq_2d.py:78-193,281-298       tracer advection + source
+* thetis/tracer_eq_2d.py:196-278              HorizontalDiffusionTerm (SIPG)
+* thetis/conservative_tracer_eq_2d.py:57-137  conservative tracer advection + source
+* thetis/rungekutta.py:762-867                ERKGeneric (Butcher form)
 * thetis/limiter.py:48-198 + firedrake.VertexBasedLimiter (recalled)
 
 The arithmetic itself lives in Firedrake/TSFC/PyOP2/PETSc, which is NOT under
@@ -177,7 +181,8 @@ class SWEOracle:
         self.bath = _nodal(bathymetry, self.nt)
         o = dict(use_nonlinear_equations=True, use_lax_friedrichs_velocity=True,
                  use_wetting_and_drying=False, wetting_and_drying_alpha=0.5,
-                 norm_smoother=0.0)
+                 norm_smoother=0.0, use_grad_div_viscosity_term=False,
+                 use_grad_depth_viscosity_term=True, sipg_factor=1.0)
         o.update(options or {})
         self.options = o
         self.fields = dict(fields or {})
@@ -367,8 +372,29 @@ class SWEOracle:
         vs = self._field("volume_source")
         if vs is not None:
             Re += np.einsum("cq,cq,qa->ca", wq, self._at_cell_q(vs, lam), phi)
-        if self.fields.get("viscosity_h") is not None:
-            raise NotImplementedError("horizontal viscosity is not on the accelerated path")
+        nu = self._field("viscosity_h")
+        graddiv = bool(o["use_grad_div_viscosity_term"])
+        if nu is not None:
+            # HorizontalViscosityTerm cell part (shallowwater_eq.py:554-573, 611-614)
+            G = np.einsum("cai,caj->cij", uv, grad)              # grad(uv)[i, j] = d u_i / d x_j, constant per cell
+            S = G + np.swapaxes(G, 1, 2) if graddiv else G       # stress / nu
+            nu_q = self._at_cell_q(nu, lam)
+            # f = inner(grad(psi), stress) dx ; R = -f
+            Ru -= np.einsum("cq,cq,caj,cij->cai", wq, nu_q, grad, S)
+            if o["use_grad_depth_viscosity_term"]:
+                # f += -dot(psi, dot(grad(total_h)/total_h, stress)) dx
+                if nonlin:
+                    ghl = np.einsum("ca,caj->cj", self.bath + eta, grad)          # grad(b + eta)
+                    gH = np.broadcast_to(ghl[:, None, :], (nt, lam.shape[0], 2))
+                    if o["use_wetting_and_drying"]:
+                        hl_q = b_q + eta_q
+                        al = np.asarray(o["wetting_and_drying_alpha"])
+                        gH = gH * (0.5 * (1.0 + hl_q / np.sqrt(hl_q ** 2 + al ** 2)))[..., None]
+                else:
+                    gb = np.einsum("ca,caj->cj", self.bath, grad)
+                    gH = np.broadcast_to(gb[:, None, :], (nt, lam.shape[0], 2))
+                w_q = np.einsum("cqi,cq,cij->cqj", gH / H_q[..., None], nu_q, S)
+                Ru += np.einsum("cq,cqj,qa->caj", wq, w_q, phi)
 
         # ---- interior facets ('+' = if_p, '-' = if_m), 2-point Gauss
         cp, fp, cm, fm = self.if_p, self.if_fp, self.if_m, self.if_fm
@@ -416,6 +442,28 @@ class SWEOracle:
                     ju = up - um
                     fu_p = fu_p + gamma[..., None] * ju
                     fu_m = fu_m - gamma[..., None] * ju
+            if nu is not None:
+                # SIPG interior-facet terms (shallowwater_eq.py:575-590)
+                sipg = float(o["sipg_factor"])
+                cp_el = 3.0                                       # (p+1)(p+2)/2 for p = 1 triangles
+                sig_p = sipg * cp_el * flen / A[cp]               # sigma = sipg*cp / (CellVolume/FacetArea)
+                sig_m = sipg * cp_el * flen / A[cm]
+                sig_max = np.maximum(sig_p, sig_m)[:, None]
+                nu_p = self._facet_trace(nu, cp, fp, s)
+                nu_m = self._facet_trace(nu, cm, fm, s, reverse=True)
+                nu_av = 0.5 * (nu_p + nu_m)
+                npb = np.broadcast_to(n_p, up.shape)
+                J = np.einsum("fqi,fqj->fqij", up - um, npb)      # tensor_jump(uv, n)
+                SJ = nu_av[..., None, None] * (J + np.swapaxes(J, 2, 3) if graddiv else J)
+                avS = 0.5 * (nu_p[..., None, None] * S[cp][:, None] + nu_m[..., None, None] * S[cm][:, None])
+                # + sigma_max*inner(tensor_jump(psi, n), stress_jump) - inner(tensor_jump(psi, n), avg(stress))
+                t13 = np.einsum("fqij,fqj->fqi", sig_max[..., None, None] * SJ - avS, npb)
+                fu_p = fu_p + t13
+                fu_m = fu_m - t13
+                # - inner(avg(grad(psi)), stress_jump): touches all three nodes of each side
+                SJint = np.einsum("fq,fqij->fij", wf, SJ)
+                np.add.at(Ru, cp, 0.5 * np.einsum("faj,fij->fai", grad[cp], SJint))
+                np.add.at(Ru, cm, 0.5 * np.einsum("faj,fij->fai", grad[cm], SJint))
             # scatter: R -= int f * phi
             for k in range(2):
                 np.subtract.at(Ru, (cp, nodes_p[:, k]), np.einsum("fq,fqi,q->fi", wf, fu_p, php[:, k]))
@@ -474,6 +522,26 @@ class SWEOracle:
                     uv_ext = u - 2 * un_jump[..., None] * nb
                     gamma = 0.5 * np.abs(un_jump) * sig
                     fu = fu + gamma[..., None] * (u - uv_ext)
+            if nu is not None and self.impose_dynamic_bnd(funcs, marker):
+                # Dirichlet bcs of the viscosity term (shallowwater_eq.py:592-609)
+                delta = None
+                if 'un' in funcs:
+                    un_ext = self._bc_value(funcs['un'], cells, lf)
+                    delta = (np.einsum("fqi,fqi->fq", u, nb) - un_ext)[..., None] * nb
+                else:
+                    eta_ext, uv_ext = self.get_bnd_functions(e, u, marker, funcs, b, nb)
+                    if uv_ext is not u:
+                        delta = u - uv_ext
+                if delta is not None:
+                    sipg = float(o["sipg_factor"])
+                    sig = (sipg * 3.0 * geo.flen[cells, lf] / A[cells])[:, None]
+                    nu_b = self._facet_trace(nu, cells, lf, s)
+                    Jb = np.einsum("fqi,fqj->fqij", delta, nb)
+                    SJb = nu_b[..., None, None] * (Jb + np.swapaxes(Jb, 2, 3) if graddiv else Jb)
+                    Sb = nu_b[..., None, None] * S[cells][:, None]
+                    fu = fu + np.einsum("fqij,fqj->fqi", sig[..., None, None] * SJb - Sb, nb)
+                    SJint = np.einsum("fq,fqij->fij", wf, SJb)
+                    np.add.at(Ru, cells, np.einsum("faj,fij->fai", grad[cells], SJint))
             if funcs is not None and 'drag' in funcs:
                 raise NotImplementedError("BoundaryDragTerm is not on the accelerated path")
             for k in range(2):
@@ -537,12 +605,73 @@ class ShuOsherStepper:
             self.solve_stage(i, t, update_forcings)
 
 
+class ButcherStepper:
+    """
+    `ERKGeneric` (rungekutta.py:762-867): explicit Runge-Kutta in Butcher form.
+    Stage i: solution = solution_old + sum_j a[i][j]*k_j (update_solution, :816-828), forcings at t + c_i*dt and
+    k_i = dt*M^-1 R(solution) (solve_tendency, :831-838); after the last stage
+    solution = solution_old + sum_j b[j]*k_j (get_final_solution, :841-852).
+    """
+
+    def __init__(self, rhs, state, dt, a, b, c, cfl_coeff=1.0):
+        self.rhs = rhs
+        self.state = state
+        self.dt = float(dt)
+        self.a = [list(map(float, row)) for row in a]
+        self.b = list(map(float, b))
+        self.c = list(map(float, c))
+        self.n_stages = len(self.b)
+        self.cfl_coeff = cfl_coeff
+        self.solution_old = [np.array(s, copy=True) for s in state]
+        self.tendency = [None] * self.n_stages
+
+    def set_dt(self, dt):
+        self.dt = float(dt)
+
+    def solve_stage(self, i, t, update_forcings=None):
+        for j, s in enumerate(self.state):
+            new = self.solution_old[j].copy()
+            for jj in range(i):
+                if self.a[i][jj] != 0.0:
+                    new = new + self.a[i][jj] * self.tendency[jj][j]
+            s[...] = new
+        if update_forcings is not None:
+            update_forcings(t + self.c[i] * self.dt)
+        self.tendency[i] = self.rhs.tendency(*self.state, dt=self.dt)
+
+    def advance(self, t, update_forcings=None):
+        for i in range(self.n_stages):
+            self.solve_stage(i, t, update_forcings)
+        for j, s in enumerate(self.state):
+            new = self.solution_old[j].copy()
+            for jj in range(self.n_stages):
+                if self.b[jj] != 0.0:
+                    new = new + self.b[jj] * self.tendency[jj][j]
+            s[...] = new
+            self.solution_old[j][...] = new
+
+
+ERK_TABLEAUX = {
+    # name: (a, b, c, cfl_coeff)   rungekutta.py:142-149, 350-392
+    "ERKEuler": ([[0]], [1.0], [0], 1.0),
+    "ERKLSPUM2": ([[0, 0, 0], [5.0 / 6.0, 0, 0], [11.0 / 24.0, 11.0 / 24.0, 0]],
+                  [24.0 / 55.0, 1.0 / 5.0, 4.0 / 11.0], [0, 5.0 / 6.0, 11.0 / 12.0], 1.2),
+    "ERKLPUM2": ([[0, 0, 0], [0.5, 0, 0], [0.5, 0.5, 0]], [1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0], [0, 0.5, 1.0], 2.0),
+    "ERKMidpoint": ([[0.0, 0.0], [0.5, 0.0]], [0.0, 1.0], [0.0, 0.5], 1.0),
+}
+
+
 class TracerOracle:
     """
-    Non-conservative 2-D tracer advection + source on P1DG
-    (tracer_eq_2d.py:124-193, 281-298).  ``uv`` (nt,3,2) and ``elev`` (nt,3)
-    are the live SWE fields (frozen during the tracer stages,
-    coupled_timeintegrator_2d.py:99-101).
+    2-D tracer advection + SIPG diffusion + source on P1DG, non-conservative
+    (tracer_eq_2d.py:124-298) or conservative form (``use_conservative_form``,
+    tracer_eq_2d.py:323-437: the unknown is the depth-integrated tracer).
+    ``uv`` (nt,3,2) and ``elev`` (nt,3) are the live SWE fields (frozen during
+    the tracer stages, coupled_timeintegrator_2d.py:99-101).
+
+    fields: 'source', 'diffusivity_h' (constant or nodal (nt,3)),
+    'tracer_advective_velocity_factor', 'lax_friedrichs_tracer_scaling_factor'.
+    bnd tags: 'value', 'uv', 'un', 'flux', 'elev', 'diff_flux'.
     """
 
     def __init__(self, swe: SWEOracle, bnd_conditions=None, fields=None, options=None):
@@ -552,7 +681,7 @@ class TracerOracle:
         self.geom = swe.geom
         self.bnd = dict(bnd_conditions or {})
         self.fields = dict(fields or {})
-        o = dict(use_lax_friedrichs_tracer=False)
+        o = dict(use_lax_friedrichs_tracer=False, use_conservative_form=False, sipg_factor_tracer=1.0)
         o.update(options or {})
         self.options = o
         self.uv = None
@@ -570,16 +699,31 @@ class TracerOracle:
         R = np.zeros((nt, 3))
         wq = geo.area[:, None] * qw[None, :]
         grad = geo.grad
+        cons = bool(self.options["use_conservative_form"])
         u_q = swe._at_cell_q(uv, lam)
         c_q = swe._at_cell_q(c, lam)
-        divu = np.einsum("cai,cai->c", grad, uv)
-        # f = -(Dx(uv[0]*test,0)*c + Dx(uv[1]*test,1)*c) dx ; R = -f
         gu = np.einsum("cai,cqi->cqa", grad, u_q)
-        coef = gu + lam[None] * divu[:, None, None]
-        R += np.einsum("cq,cqa,cq->ca", wq, coef, c_q)
+        if cons:
+            # f = -(Dx(test,0)*uv[0]*c + Dx(test,1)*uv[1]*c) dx (tracer_eq_2d.py:356-357) ; R = -f
+            R += np.einsum("cq,cqa,cq->ca", wq, gu, c_q)
+        else:
+            divu = np.einsum("cai,cai->c", grad, uv)
+            # f = -(Dx(uv[0]*test,0)*c + Dx(uv[1]*test,1)*c) dx ; R = -f
+            coef = gu + lam[None] * divu[:, None, None]
+            R += np.einsum("cq,cqa,cq->ca", wq, coef, c_q)
         src = self.fields.get("source")
         if src is not None:
-            R += np.einsum("cq,cq,qa->ca", wq, swe._at_cell_q(_nodal(src, nt), lam), lam)
+            s_q = swe._at_cell_q(_nodal(src, nt), lam)
+            if cons:
+                # ConservativeSourceTerm (:429-437): H*source
+                s_q = s_q * swe.total_depth(swe._at_cell_q(swe.bath, lam), swe._at_cell_q(self.elev, lam))
+            R += np.einsum("cq,cq,qa->ca", wq, s_q, lam)
+        mu = self.fields.get("diffusivity_h")
+        if mu is not None:
+            mu = _nodal(mu, nt)
+            gc = np.einsum("ca,caj->cj", c, grad)                 # grad(c), constant per cell
+            # HorizontalDiffusionTerm cell part (:238): f = inner(grad(test), mu*grad(c)) dx
+            R -= np.einsum("cq,cq,caj,cj->ca", wq, swe._at_cell_q(mu, lam), grad, gc)
         # interior facets
         cp, fp, cm, fm = swe.if_p, swe.if_fp, swe.if_m, swe.if_fm
         s = _GS
@@ -595,14 +739,37 @@ class TracerOracle:
             uv_av = 0.5 * (up + um)
             un_av = np.einsum("fqi,fqi->fq", uv_av, n_m)
             sg = 0.5 * (np.sign(un_av) + 1.0)
-            c_up = c_m * sg + c_p * (1 - sg)
-            f_p = c_up * np.einsum("fqi,fqi->fq", up, n_p)
-            f_m = c_up * np.einsum("fqi,fqi->fq", um, n_m)
+            if cons:
+                # flux_up = c('-')*uv('-')*s + c('+')*uv('+')*(1-s)   (:364-367)
+                flux_up = (c_m * sg)[..., None] * um + (c_p * (1 - sg))[..., None] * up
+                f_p = np.einsum("fqi,fqi->fq", flux_up, n_p)
+                f_m = np.einsum("fqi,fqi->fq", flux_up, n_m)
+            else:
+                c_up = c_m * sg + c_p * (1 - sg)
+                f_p = c_up * np.einsum("fqi,fqi->fq", up, n_p)
+                f_m = c_up * np.einsum("fqi,fqi->fq", um, n_m)
             if self.options["use_lax_friedrichs_tracer"]:
                 lf = float(self.fields.get("lax_friedrichs_tracer_scaling_factor", 1.0))
                 gamma = 0.5 * np.abs(un_av) * lf
                 f_p = f_p + gamma * (c_p - c_m)
                 f_m = f_m - gamma * (c_p - c_m)
+            if mu is not None:
+                # SIPG interior-facet terms (:240-258)
+                sipg = float(self.options["sipg_factor_tracer"])
+                flen = geo.flen[cp, fp]
+                sig_max = np.maximum(sipg * 3.0 * flen / geo.area[cp], sipg * 3.0 * flen / geo.area[cm])[:, None]
+                mu_p = swe._facet_trace(mu, cp, fp, s)
+                mu_m = swe._facet_trace(mu, cm, fm, s, reverse=True)
+                dc = c_p - c_m                                    # jump(c, n) = dc * n('+')
+                av_flux = 0.5 * (mu_p[..., None] * gc[cp][:, None, :] + mu_m[..., None] * gc[cm][:, None, :])
+                t = sig_max * 0.5 * (mu_p + mu_m) * dc - np.einsum("fqi,fqi->fq", av_flux, n_p)
+                f_p = f_p + t
+                f_m = f_m - t
+                # -inner(avg(mu*grad(test)), jump(c, n)): all three nodes of each side
+                gn_p = np.einsum("faj,fj->fa", grad[cp], n_p[:, 0, :])
+                gn_m = np.einsum("faj,fj->fa", grad[cm], n_p[:, 0, :])
+                np.add.at(R, cp, 0.5 * gn_p * np.einsum("fq,fq->f", wf, mu_p * dc)[:, None])
+                np.add.at(R, cm, 0.5 * gn_m * np.einsum("fq,fq->f", wf, mu_m * dc)[:, None])
             nodes_p = FACET_NODES[fp]
             nodes_m = FACET_NODES[fm][:, ::-1]
             for k in range(2):
@@ -639,8 +806,27 @@ class TracerOracle:
                 uv_av = 0.5 * (u + uv_ext)
                 un_av = np.einsum("fqi,fqi->fq", uv_av, n)
                 sg = 0.5 * (np.sign(un_av) + 1.0)
-                c_up = cin * sg + c_ext * (1 - sg)
-                f = c_up * un_av
+                if cons:
+                    # flux_up = c_in*uv*s + c_ext*uv_ext*(1-s)   (:391-394)
+                    f = np.einsum("fqi,fqi->fq", (cin * sg)[..., None] * u + (c_ext * (1 - sg))[..., None] * uv_ext, n)
+                else:
+                    c_up = cin * sg + c_ext * (1 - sg)
+                    f = c_up * un_av
+                if mu is not None:
+                    mu_b = swe._facet_trace(mu, cells, lf, s)
+                    if 'diff_flux' in funcs:
+                        # f += -test*diff_flux ds   (:264-265)
+                        f = f - swe._bc_value(funcs['diff_flux'], cells, lf)
+                    else:
+                        # f += -test*dot(mu*grad(c_up), n) ds  (:267-272); grad(c_ext) = 0 for a Constant 'value',
+                        # d(sign)/dx = 0 in UFL
+                        if 'value' in funcs:
+                            if isinstance(funcs['value'], np.ndarray) and np.ndim(funcs['value']) >= 2:
+                                raise NotImplementedError("diffusive boundary flux with a spatially varying 'value'")
+                            wgt = sg
+                        else:
+                            wgt = np.ones_like(sg)
+                        f = f - wgt * mu_b * np.einsum("fj,fqj->fq", gc[cells], n)
             else:
                 f = cin * np.einsum("fqi,fqi->fq", u, n)
             nodes = FACET_NODES[lf]

@@ -37,6 +37,11 @@ for name in ("SSPRK33Abstract", "ForwardEulerAbstract"):
     alpha, beta = ns["butcher_to_shuosher_form"](a, b)
     out[name] = {"a": a.tolist(), "b": b.tolist(), "c": list(map(float, t["c"])), "cfl_coeff": float(t["cfl_coeff"]),
                  "alpha": alpha.tolist(), "beta": beta.tolist()}
+# explicit Butcher-form tableaux stepped by ERKGeneric (thetis/rungekutta.py:350-392, 959-980): the numbers only
+for name in ("ERKLSPUM2Abstract", "ERKLPUM2Abstract", "ERKMidpointAbstract"):
+    t = tableaux[name]
+    out[name] = {"a": numpy.array(t["a"], dtype=float).tolist(), "b": list(map(float, t["b"])),
+                 "c": list(map(float, t["c"])), "cfl_coeff": float(t["cfl_coeff"])}
 path = os.path.join(os.path.dirname(__file__), "shuosher_ssprk33.json")
 json.dump(out, open(path, "w"), indent=1)
 print(path)

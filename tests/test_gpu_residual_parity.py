@@ -58,11 +58,15 @@ def _run(mesh, bath_v, options, fields_v, bnd, g=9.81, tol=1e-12, seed=0, bc_arr
     eng.set_option(L.OPT_WETTING_DRYING, options.get("use_wetting_and_drying", False))
     eng.set_option(L.OPT_WD_ALPHA, options.get("wetting_and_drying_alpha", 0.5))
     eng.set_option(L.OPT_LF_SCALING, fields_v.get("lax_friedrichs_velocity_scaling_factor", 1.0))
+    eng.set_option(L.OPT_SIPG_FACTOR, options.get("sipg_factor", 1.0))
+    eng.set_option(L.OPT_GRAD_DIV_VISCOSITY, options.get("use_grad_div_viscosity_term", False))
+    eng.set_option(L.OPT_GRAD_DEPTH_VISCOSITY, options.get("use_grad_depth_viscosity_term", True))
     eng.set_field(L.F_BATHYMETRY, bath_v)
     names = {"coriolis": L.F_CORIOLIS, "manning_drag_coefficient": L.F_MANNING,
              "quadratic_drag_coefficient": L.F_QUAD_DRAG, "linear_drag_coefficient": L.F_LINEAR_DRAG,
              "wind_stress": L.F_WIND_STRESS, "atmospheric_pressure": L.F_ATM_PRESSURE,
-             "momentum_source": L.F_MOMENTUM_SOURCE, "volume_source": L.F_VOLUME_SOURCE}
+             "momentum_source": L.F_MOMENTUM_SOURCE, "volume_source": L.F_VOLUME_SOURCE,
+             "viscosity_h": L.F_VISCOSITY}
     for k, fid in names.items():
         if fields_v.get(k) is not None:
             eng.set_field(fid, fields_v[k])
@@ -207,3 +211,86 @@ def test_config5_specialised_kernels(wd):
     _run(mesh, setup["bath"], dict(use_wetting_and_drying=wd, wetting_and_drying_alpha=0.5),
          {"manning_drag_coefficient": setup["manning"], "coriolis": setup["coriolis"]},
          {100: {"elev": 0.0, "uv": (0.0, 0.0)}}, tol=1e-10, bc_arrays={(100, "elev"): tv})
+
+
+# ---------------------------------------------------------------- HorizontalViscosityTerm (SIPG), SURVEY 8f rank 1
+@pytest.mark.parametrize("graddiv", [False, True])
+@pytest.mark.parametrize("graddepth", [False, True])
+def test_viscosity_structured_closed(graddiv, graddepth):
+    mesh = sfc_renumber(rectangle_mesh(20, 14, 2000.0, 1500.0))
+    b = _vertex_field(mesh, lambda x, y: 12.0 + 3.0 * np.sin(x / 400.0) * np.cos(y / 300.0))
+    _run(mesh, b, dict(use_grad_div_viscosity_term=graddiv, use_grad_depth_viscosity_term=graddepth, sipg_factor=1.5),
+         {"viscosity_h": 35.0}, {}, tol=1e-11)
+
+
+def test_viscosity_linear_equations_variable_nu():
+    mesh = sfc_renumber(rectangle_mesh(16, 16, 1000.0, 1000.0, diagonal="right"))
+    nu = _vertex_field(mesh, lambda x, y: 5.0 + 0.01 * x + 0.004 * y)
+    b = _vertex_field(mesh, lambda x, y: 20.0 + 0.002 * x)
+    _run(mesh, b, dict(use_nonlinear_equations=False), {"viscosity_h": nu}, {}, tol=1e-11)
+
+
+def test_viscosity_unstructured_multi_patch():
+    # 6000 triangles = 47 patches: neighbour gradients come from halo cells whose vertices are outside the patch
+    mesh = sfc_renumber(delaunay_mesh(3000, 5e4, 4e4, seed=2))
+    X, Y = mesh.coords[:, 0], mesh.coords[:, 1]
+    nu = 50.0 * (1.0 + 0.5 * np.sin(X / 7e3) * np.cos(Y / 9e3))
+    b = 30.0 + 10.0 * np.cos(X / 1e4)
+    _run(mesh, b, dict(use_grad_div_viscosity_term=True, sipg_factor=2.0),
+         {"viscosity_h": nu, "manning_drag_coefficient": 0.025, "coriolis": 1e-4}, {}, tol=1e-10)
+
+
+def test_viscosity_periodic():
+    mesh = sfc_renumber(periodic_rectangle_mesh(24, 12, 48.0, 24.0, origin=(-24.0, -12.0)))
+    bnd = {m: {"uv": (0.0, 0.0)} for m in mesh.unique_markers()}
+    _run(mesh, 1.0, dict(use_grad_depth_viscosity_term=False), {"viscosity_h": 0.05}, bnd, g=1.0, tol=1e-11)
+
+
+@pytest.mark.parametrize("bc", [
+    {"elev": 0.3, "uv": (0.2, -0.1)},
+    {"elev": 0.3, "un": 0.15},
+    {"elev": -0.2, "flux": 500.0},
+    {"elev": 0.25},
+    {"uv": (0.1, 0.3)},
+    {"un": -0.2},
+    {"flux": -300.0},
+])
+@pytest.mark.parametrize("graddiv", [False, True])
+def test_viscosity_open_boundary_dirichlet_terms(bc, graddiv):
+    mesh = sfc_renumber(rectangle_mesh(12, 10, 600.0, 500.0))
+    b = _vertex_field(mesh, lambda x, y: 12 + 0.004 * x)
+    nu = _vertex_field(mesh, lambda x, y: 2.0 + 0.002 * y)
+    bnd = {1: bc, 2: {"elev": 0.1}, 3: bc}
+    _run(mesh, b, dict(use_grad_div_viscosity_term=graddiv), {"viscosity_h": nu}, bnd, tol=1e-11)
+
+
+def test_viscosity_wetting_drying_grad_depth():
+    mesh = sfc_renumber(rectangle_mesh(14, 6, 14e3, 1.2e3))
+    X = mesh.coords[:, 0]
+    b = 3.0 - 5.0 * X / 14e3
+    _run(mesh, b, dict(use_wetting_and_drying=True, wetting_and_drying_alpha=0.4, use_grad_div_viscosity_term=True),
+         {"viscosity_h": 10.0, "manning_drag_coefficient": 0.02}, {1: {"elev": 0.5}}, tol=1e-10)
+
+
+def test_viscosity_toggle_rebuilds_patch_tables():
+    """the halo-geometry tables are built when viscosity is switched on and dropped when it is cleared"""
+    import thetis_b200._lib as L
+    from thetis_b200.engine import Engine
+    mesh = sfc_renumber(delaunay_mesh(800, 1e4, 1e4, seed=5))
+    uv, eta = _state(mesh, 1)
+    eng = Engine(mesh)
+    eng.set_field(L.F_BATHYMETRY, 20.0)
+    st = eng.upload_nodal(uv, eta)
+    k0, k1, k2 = eng.new_state(), eng.new_state(), eng.new_state()
+    eng.swe_tendency(st, k0)
+    eng.set_field(L.F_VISCOSITY, 3.0)
+    eng.swe_tendency(st, k1)
+    eng.set_field(L.F_VISCOSITY, None)
+    eng.swe_tendency(st, k2)
+    import torch
+    assert torch.equal(k0, k2)
+    assert not torch.equal(k0, k1)
+    orc = SWEOracle(mesh, 20.0, fields={"viscosity_h": 3.0})
+    ku, ke = orc.tendency(uv, eta)
+    gu, ge = eng.download_nodal(k1)
+    assert np.abs(gu - ku).max() / np.abs(ku).max() < 1e-11

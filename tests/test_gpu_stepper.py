@@ -301,7 +301,7 @@ def test_unsupported_configurations_raise():
     from thetis_b200.shim import Constant
     mesh = rectangle_mesh(4, 4, 1.0, 1.0)
     s, _ = _solver(mesh, 1.0, timestep=0.01, simulation_end_time=0.01)
-    s.options.horizontal_viscosity = Constant(1.0)
+    s.options.nikuradse_bed_roughness = Constant(1.0)
     with pytest.raises(NotImplementedError):
         s.assign_initial_conditions()
     s2, _ = _solver(mesh, 1.0, timestep=0.01, simulation_end_time=0.01)

@@ -261,3 +261,125 @@ def test_atmospheric_pressure_convergence():
     e = [_atm_pressure_error(n, dt) for n, dt in ((2, 20.0), (4, 10.0), (8, 5.0))]
     assert e[0] / e[1] > 4 * 0.75 and e[1] / e[2] > 4 * 0.75
     assert e[0] / e[2] > 16 * 0.75
+
+
+# ---------------------------------------------------------------- Butcher-form ERK
+@pytest.mark.parametrize(("name", "rate"), [("ERKEuler", 1.0), ("ERKLSPUM2", 2.0), ("ERKLPUM2", 2.0), ("ERKMidpoint", 2.0)])
+def test_ode_convergence_butcher_form(name, rate):
+    """test/time_integration/test_convergence_ode.py:152-186: slope within 5 % of the expected order"""
+    gold = json.load(open(os.path.join(HERE, "golden", "shuosher_ssprk33.json")))
+    a, b, c, cfl = O.ERK_TABLEAUX[name]
+    if name != "ERKEuler":          # tableau numbers produced by executing the reference's class bodies
+        g = gold[name + "Abstract"]
+        assert np.array_equal(np.array(a, float), np.array(g["a"])) and list(map(float, b)) == g["b"]
+        assert list(map(float, c)) == g["c"] and cfl == g["cfl_coeff"]
+    errs = []
+    for r in (1, 2, 3, 4):
+        alpha = 2 * np.pi
+        n = int(np.round(1.0 / 0.01 * r))
+        dt = 1.0 / n
+        av, bv = np.zeros(1), np.ones(1)
+        ti = O.ButcherStepper(_ODE(alpha), [av, bv], dt, a, b, c)
+        vals = np.zeros((n + 1, 2))
+        vals[0] = av[0], bv[0]
+        for i in range(n):
+            ti.advance((i + 1) * dt)
+            vals[i + 1] = av[0], bv[0]
+        times = np.arange(n + 1) * dt
+        exact = np.vstack((np.sin(alpha * times), np.cos(alpha * times))).T
+        errs.append(np.sqrt(np.mean((vals - exact) ** 2)))
+    slope = stats.linregress(np.log10(1.0 / np.array([1.0, 2, 3, 4])), np.log10(errs)).slope
+    assert abs(slope - rate) / slope < 0.05, slope
+
+
+# ---------------------------------------------------------------- SIPG terms (SURVEY 8f rank 1)
+def test_tracer_diffusion_reference_kat():
+    """test/tracerEq/test_h-diffusion_mes_2d.py:14-160: erf front, L2 error convergence rate > 1.8 over
+    refinements [1, 2, 3] with SSPRK33 (:163-176)"""
+    from scipy.special import erf
+    lx, depth, mu = 20e3, 30.0, 1.0e3
+    t0, t1 = 1000.0, 3000.0
+    ana = lambda X, t: -erf((X - lx / 2) / np.sqrt(4 * mu * t))
+    errs = []
+    for ref in (1, 2, 3):
+        ly = 5e3 / ref
+        mesh = rectangle_mesh(8 * ref + 1, 1, lx, ly)
+        swe = O.SWEOracle(mesh, depth, options=dict(use_nonlinear_equations=False))
+        trc = O.TracerOracle(swe, fields={"diffusivity_h": mu})
+        x = mesh.coords[mesh.cells]
+        trc.set_velocity(np.zeros(x.shape), np.zeros(x.shape[:2]))
+        dt = 0.05 * np.sqrt(swe.geom.area).min() / (np.sqrt(9.81 * depth) + 1.0)     # solver2d.py:150-241
+        lam, w = O.cell_quadrature("dunavant6")
+        xq = np.einsum("qa,ca->cq", lam, x[..., 0])
+        mref = np.einsum("q,qa,qb->ab", w, lam, lam)
+        c = np.linalg.solve(mref, np.einsum("q,qa,cq->ca", w, lam, ana(xq, t0)).T).T.copy()
+        st = O.ShuOsherStepper(trc, [c], dt)
+        t = t0
+        while t < t1 - 1e-8:
+            st.advance(t)
+            t += dt
+        errs.append(O.l2_error(mesh, c, lambda X, Y: ana(X, t)) / np.sqrt(lx * ly))
+    slope = stats.linregress(np.log10(1.0 / np.array([1.0, 2.0, 3.0])), np.log10(errs)).slope
+    assert slope > 1.8, (slope, errs)
+
+
+def test_viscosity_equals_componentwise_tracer_diffusion():
+    """two independent restatements of the same SIPG Laplacian: with grad-div and grad-depth off, the viscosity
+    residual of each velocity component (shallowwater_eq.py:554-590) is the tracer diffusion residual of that
+    component (tracer_eq_2d.py:226-258) -- the latter is pinned by the reference's erf test above"""
+    from thetis_b200.mesh import delaunay_mesh
+    mesh = delaunay_mesh(400, 1.0, 1.0, seed=1)
+    x = mesh.coords[mesh.cells]
+    rng = np.random.default_rng(0)
+    u = np.stack([np.sin(3 * x[..., 0]) * np.cos(2 * x[..., 1]) + 0.1 * rng.standard_normal(x.shape[:2]),
+                  0.1 * rng.standard_normal(x.shape[:2])], -1)
+    eta = np.zeros(x.shape[:2])
+    nu = (0.3 + 0.2 * mesh.coords[:, 0])[mesh.cells]
+    o1 = O.SWEOracle(mesh, 1.0, options=dict(use_nonlinear_equations=False, use_grad_depth_viscosity_term=False,
+                                             sipg_factor=1.7), fields={"viscosity_h": nu})
+    o0 = O.SWEOracle(mesh, 1.0, options=dict(use_nonlinear_equations=False))
+    dv = o1.residual(u, eta)[0] - o0.residual(u, eta)[0]
+    tr = O.TracerOracle(o0, fields={"diffusivity_h": nu}, options=dict(sipg_factor_tracer=1.7))
+    tr.set_velocity(0 * u, eta)
+    for comp in range(2):
+        rc = tr.residual(u[..., comp])
+        assert np.abs(dv[..., comp] - rc).max() < 1e-13 * np.abs(rc).max()
+
+
+@pytest.mark.parametrize("graddiv", [False, True])
+def test_viscosity_vanishes_for_linear_velocity(graddiv):
+    """consistency: a globally linear velocity field with constant viscosity has zero viscous force; the SIPG form
+    must return exactly that on every cell that does not touch the (stress-free) boundary"""
+    from thetis_b200.mesh import delaunay_mesh
+    mesh = delaunay_mesh(300, 1.0, 1.0, seed=2)
+    x = mesh.coords[mesh.cells]
+    B = np.array([[0.3, -0.2], [0.5, 0.1]])
+    ul = np.einsum("ij,caj->cai", B, x)
+    eta = np.zeros(x.shape[:2])
+    base = dict(use_nonlinear_equations=False, use_grad_depth_viscosity_term=False)
+    o2 = O.SWEOracle(mesh, 1.0, options=dict(base, use_grad_div_viscosity_term=graddiv), fields={"viscosity_h": 0.9})
+    o0 = O.SWEOracle(mesh, 1.0, options=base)
+    d = o2.residual(ul, eta)[0] - o0.residual(ul, eta)[0]
+    interior = np.all(mesh.nbr >= 0, axis=1)
+    assert np.abs(d[interior]).max() < 1e-14 and np.abs(d[~interior]).max() > 1e-3
+
+
+def test_conservative_tracer_conserves_mass_and_matches_nonconservative_for_uniform_depth():
+    """ConservativeHorizontalAdvectionTerm (tracer_eq_2d.py:341-395): closed basin => d/dt int q = 0 exactly;
+    with a divergence-free velocity the conservative and non-conservative cell terms coincide"""
+    mesh = rectangle_mesh(10, 8, 1.0, 0.8)
+    x = mesh.coords[mesh.cells]
+    swe = O.SWEOracle(mesh, 1.0)
+    uv = np.stack([0.4 - x[..., 1], x[..., 0] - 0.5], -1)           # solid-body rotation: div u = 0
+    q = 1.0 + np.exp(-((x[..., 0] - 0.3) ** 2 + (x[..., 1] - 0.4) ** 2) / 0.02)
+    tc = O.TracerOracle(swe, options=dict(use_conservative_form=True))
+    tn = O.TracerOracle(swe)
+    for t_ in (tc, tn):
+        t_.set_velocity(uv, np.zeros(x.shape[:2]))
+    rc, rn = tc.residual(q), tn.residual(q)
+    interior = np.all(mesh.nbr >= 0, axis=1)
+    assert np.abs(rc - rn)[interior].max() < 1e-14
+    # closed boundaries: the conservative form loses mass only through u.n on the walls
+    uv0 = uv * (np.minimum(np.minimum(x[..., 0], 1 - x[..., 0]), np.minimum(x[..., 1], 0.8 - x[..., 1])))[..., None]
+    tc.set_velocity(uv0, np.zeros(x.shape[:2]))
+    assert abs(tc.residual(q).sum()) < 1e-14

@@ -10,7 +10,8 @@ __version__ = "0.1.0"
 
 def install(thetis_module=None, sync_policy="every_step"):
     """
-    Rebind `thetis.rungekutta.SSPRK33` and `thetis.limiter.VertexBasedP1DGLimiter` to the B200
+    Rebind `thetis.rungekutta.SSPRK33` (+ the Butcher-form ERK classes and `thetis.timeintegrator.ForwardEuler`
+    where the module has them) and `thetis.limiter.VertexBasedP1DGLimiter` to the B200
     implementations so that FlowSolver2d.create_timestepper() picks them up (the `steppers` dict is built from
     module attributes at call time, thetis/solver2d.py:662-672).  See INTEGRATION.md.
     """
@@ -27,4 +28,20 @@ def install(thetis_module=None, sync_policy="every_step"):
     cls = SSPRK33
     thetis_module.rungekutta.SSPRK33 = cls
     thetis_module.limiter.VertexBasedP1DGLimiter = lim.VertexBasedP1DGLimiter
+
+    def _bind(base):
+        class _Bound(base):
+            def __init__(self, equation, solution, fields, dt, options=None, bnd_conditions=None, terms_to_add="all"):
+                super().__init__(equation, solution, fields, dt, options, bnd_conditions, terms_to_add,
+                                 sync_policy=policy)
+        _Bound.__name__ = _Bound.__qualname__ = base.__name__
+        return _Bound
+
+    # the Butcher-form explicit schemes (rungekutta.py:959-980) and timeintegrator.ForwardEuler, where present
+    for name in ("ERKLSPUM2", "ERKLPUM2", "ERKMidpoint", "ERKEuler"):
+        if hasattr(thetis_module.rungekutta, name):
+            setattr(thetis_module.rungekutta, name, _bind(getattr(rk, name)))
+    ti_mod = getattr(thetis_module, "timeintegrator", None)
+    if ti_mod is not None and hasattr(ti_mod, "ForwardEuler"):
+        ti_mod.ForwardEuler = _bind(rk.ForwardEuler)
     return cls

@@ -16,11 +16,12 @@ TB_OK = 0
 # tb_option
 OPT_G_GRAV, OPT_RHO0, OPT_NONLINEAR, OPT_LAX_FRIEDRICHS, OPT_LF_SCALING, OPT_NORM_SMOOTHER, \
     OPT_WETTING_DRYING, OPT_WD_ALPHA, OPT_LF_TRACER, OPT_LF_TRACER_SCALING, OPT_TRACER_VEL_FACTOR, \
-    OPT_FORCE_GENERIC_KERNEL = range(12)
+    OPT_FORCE_GENERIC_KERNEL, OPT_SIPG_FACTOR, OPT_SIPG_FACTOR_TRACER, OPT_GRAD_DIV_VISCOSITY, \
+    OPT_GRAD_DEPTH_VISCOSITY, OPT_TRACER_CONSERVATIVE = range(17)
 # tb_field
 F_BATHYMETRY, F_CORIOLIS, F_MANNING, F_QUAD_DRAG, F_LINEAR_DRAG, F_WIND_STRESS, F_ATM_PRESSURE, \
-    F_MOMENTUM_SOURCE, F_VOLUME_SOURCE, F_TRACER_SOURCE = range(10)
-BC_ELEV, BC_UV, BC_UN, BC_FLUX, BC_VALUE = 1, 2, 4, 8, 16
+    F_MOMENTUM_SOURCE, F_VOLUME_SOURCE, F_TRACER_SOURCE, F_VISCOSITY, F_DIFFUSIVITY = range(12)
+BC_ELEV, BC_UV, BC_UN, BC_FLUX, BC_VALUE, BC_DIFF_FLUX = 1, 2, 4, 8, 16, 64
 
 
 class TbMesh(C.Structure):
@@ -62,6 +63,8 @@ SIGNATURES = {
     "tb_tracer_from_field": (_I, [_P, _P, _P, _P, _P]),
     "tb_tracer_to_field": (_I, [_P, _P, _P, _P, _P]),
     "tb_swe_integrals": (_I, [_P, _P, _P, _P]),
+    "tb_tracer_integrals": (_I, [_P, _P, _P, _P, _P]),
+    "tb_lincomb": (_I, [_P, _I, _P, _P, _P, _L, _P]),
     "tb_gather_cells": (_I, [_P, _P, _P, _L, _I, _P, _P]),
     "tb_scatter_cells": (_I, [_P, _P, _P, _L, _I, _P, _P]),
     "tb_push_cells": (_I, [_P, _P, _P, _P, _L, _I, _P]),

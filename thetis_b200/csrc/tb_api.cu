@@ -47,6 +47,10 @@ struct tb_ctx {
     double *d_ext[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // elev, uv, un, flux, value (swe)
     double *d_ext_tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double *d_area = nullptr;
+    double *d_bath3 = nullptr;      // bathymetry at the 3 nodes of every owned cell (diagnostics)
+    double *d_partial = nullptr;    // scratch of the two-pass reductions
+    bool halo_geom = false;         // patch tables carry the halo cells' vertices (SIPG terms need the neighbour's gradient)
+    std::vector<uint16_t> patch_hcv;    // [n_patches*NH*3]
     // ring of pinned staging buffers for boundary data uploads (no stream stall in steady state)
     static const int NSTAGE = 8;
     double *h_pinned[NSTAGE] = {nullptr};
@@ -63,6 +67,8 @@ struct tb_ctx {
     int lf_tracer = 0;
     int force_generic = 0;
     double lf_tracer_sigma = 1.0, tracer_vel_factor = 1.0;
+    double sipg = 1.0, sipg_tracer = 1.0;
+    int graddiv = 0, graddepth = 1, tracer_conservative = 0;
     FieldStore fields[TB_F_COUNT];
     // bcs: eq 0 swe, 1 tracer
     std::vector<int> slot_marker;       // slot -> marker
@@ -130,6 +136,17 @@ static int build_patches(tb_ctx *ctx) {
                         cstamp[nb] = (int32_t)p;
                         clocal[nb] = (int32_t)hl.size();
                         hl.push_back(nb);
+                        if (ctx->halo_geom) {
+                            for (int k = 0; k < 3; ++k) {
+                                const int32_t hv = ctx->cells[(size_t)nb * 3 + k];
+                                if (hv < 0 || hv >= ctx->n_vertices) return fail(ctx, TB_ERR_ARG, "cell vertex id out of range");
+                                if (vstamp[hv] != p) {
+                                    vstamp[hv] = (int32_t)p;
+                                    vlocal[hv] = (int32_t)vl.size();
+                                    vl.push_back(hv);
+                                }
+                            }
+                        }
                     }
                 } else if (nb == std::numeric_limits<int32_t>::min()) {
                     return fail(ctx, TB_ERR_ARG, "owned cell with unknown neighbour");
@@ -151,6 +168,7 @@ static int build_patches(tb_ctx *ctx) {
     ctx->patch_cn.assign((size_t)np * TB_P * 3, 0);
     ctx->halo_ids.assign((size_t)np * std::max(NH, 1), 0);
     ctx->halo_cnt.assign(np, 0);
+    ctx->patch_hcv.assign(ctx->halo_geom ? (size_t)np * std::max(NH, 1) * 3 : 0, 0);
     // second pass: local ids (recompute stamps per patch)
     std::fill(vstamp.begin(), vstamp.end(), -1);
     std::fill(cstamp.begin(), cstamp.end(), -1);
@@ -167,6 +185,9 @@ static int build_patches(tb_ctx *ctx) {
             cstamp[hl[k]] = (int32_t)p;
             clocal[hl[k]] = (int32_t)k;
             ctx->halo_ids[(size_t)p * NH + k] = (int32_t)dev_cell(hl[k]);
+            if (ctx->halo_geom)
+                for (int a = 0; a < 3; ++a)
+                    ctx->patch_hcv[((size_t)p * NH + k) * 3 + a] = (uint16_t)vlocal[ctx->cells[(size_t)hl[k] * 3 + a]];
         }
         ctx->halo_cnt[p] = (int32_t)hl.size();
         for (long long c = c0; c < c1; ++c) {
@@ -186,7 +207,28 @@ static int build_patches(tb_ctx *ctx) {
     return TB_OK;
 }
 
+static int upload_halo_tables(tb_ctx *ctx) {
+    if (ctx->d_halo_ids) cudaFree(ctx->d_halo_ids);
+    if (ctx->d_halo_cnt) cudaFree(ctx->d_halo_cnt);
+    ctx->d_halo_ids = ctx->d_halo_cnt = nullptr;
+    CK(cudaMalloc(&ctx->d_halo_ids, sizeof(int32_t) * std::max<size_t>(ctx->halo_ids.size(), 4)));
+    CK(cudaMemcpy(ctx->d_halo_ids, ctx->halo_ids.data(), sizeof(int32_t) * ctx->halo_ids.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->d_halo_cnt, sizeof(int32_t) * ctx->n_patches));
+    CK(cudaMemcpy(ctx->d_halo_cnt, ctx->halo_cnt.data(), sizeof(int32_t) * ctx->n_patches, cudaMemcpyHostToDevice));
+    return TB_OK;
+}
+
 static int upload_layout(tb_ctx *ctx) {
+    // SIPG terms need the geometry of the halo cells: rebuild the patch tables when that requirement changes
+    const bool need_hgeom = ctx->fields[TB_F_VISCOSITY].mode != 0 || ctx->fields[TB_F_DIFFUSIVITY].mode != 0;
+    if (need_hgeom != ctx->halo_geom) {
+        CK(cudaDeviceSynchronize());
+        ctx->halo_geom = need_hgeom;
+        int rc = build_patches(ctx);
+        if (rc != TB_OK) return rc;
+        rc = upload_halo_tables(ctx);
+        if (rc != TB_OK) return rc;
+    }
     // assign columns
     int ncol = 3;
     ctx->fields[TB_F_BATHYMETRY].col = 2;
@@ -203,7 +245,9 @@ static int upload_layout(tb_ctx *ctx) {
     const long long np = ctx->n_patches;
     const size_t off_cv = (size_t)ncol * NV * sizeof(double);
     const size_t off_cn = off_cv + (size_t)TB_P * 3 * sizeof(uint16_t);
-    const size_t stride = off_cn + (size_t)TB_P * 3 * sizeof(int32_t);
+    const size_t off_hcv = off_cn + (size_t)TB_P * 3 * sizeof(int32_t);
+    const size_t hcv_bytes = ctx->halo_geom ? (((size_t)ctx->NH * 3 * sizeof(uint16_t) + 15) & ~(size_t)15) : 0;
+    const size_t stride = off_hcv + hcv_bytes;      // multiple of 16 (NV and NH are even): TMA bulk-copy granularity
     std::vector<unsigned char> host((size_t)np * stride, 0);
     const FieldStore &bath = ctx->fields[TB_F_BATHYMETRY];
     if (bath.mode == 0) return fail(ctx, TB_ERR_STATE, "bathymetry not set");
@@ -226,6 +270,18 @@ static int upload_layout(tb_ctx *ctx) {
         }
         memcpy(blk + off_cv, ctx->patch_cv.data() + (size_t)p * TB_P * 3, (size_t)TB_P * 3 * sizeof(uint16_t));
         memcpy(blk + off_cn, ctx->patch_cn.data() + (size_t)p * TB_P * 3, (size_t)TB_P * 3 * sizeof(int32_t));
+        if (ctx->halo_geom)
+            memcpy(blk + off_hcv, ctx->patch_hcv.data() + (size_t)p * ctx->NH * 3, (size_t)ctx->NH * 3 * sizeof(uint16_t));
+    }
+    // bathymetry at the cell nodes (volume / tracer-mass diagnostics)
+    {
+        std::vector<double> b3((size_t)ctx->n_owned * 3);
+        for (long long c = 0; c < ctx->n_owned; ++c)
+            for (int a = 0; a < 3; ++a)
+                b3[(size_t)c * 3 + a] = bath.mode == 2 ? bath.vert[ctx->cells[(size_t)c * 3 + a]] : bath.v[0];
+        if (!ctx->d_bath3) CK(cudaMalloc(&ctx->d_bath3, sizeof(double) * b3.size()));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(ctx->d_bath3, b3.data(), sizeof(double) * b3.size(), cudaMemcpyHostToDevice));
     }
     if (host.size() != ctx->sblk_bytes) {
         if (ctx->d_sblk) cudaFree(ctx->d_sblk);
@@ -243,6 +299,7 @@ static int upload_layout(tb_ctx *ctx) {
     ctx->pl.ncol = ncol;
     ctx->pl.off_cv = (int)off_cv;
     ctx->pl.off_cn = (int)off_cn;
+    ctx->pl.off_hcv = ctx->halo_geom ? (int)off_hcv : -1;
     ctx->pl.halo_ids = ctx->d_halo_ids;
     ctx->pl.halo_cnt = ctx->d_halo_cnt;
     ctx->layout_dirty = false;
@@ -261,6 +318,7 @@ static void default_quadrature(tb_ctx *ctx) {
         w[i] = 1.0 / 6.0;
     }
     tb_set_quadrature(6, &lam[0][0], w);
+    tb_set_quadrature_tracer(6, &lam[0][0], w);
     ctx->nquad = 6;
 }
 
@@ -360,11 +418,12 @@ extern "C" int tb_create(tb_ctx **out, const tb_mesh *m, int device) {
         }                                                                      \
     } while (0)
     CKC(tb_kernels_init());
-    CKC(cudaMalloc(&ctx->d_halo_ids, sizeof(int32_t) * std::max<size_t>(ctx->halo_ids.size(), 4)));
-    CKC(cudaMemcpy(ctx->d_halo_ids, ctx->halo_ids.data(), sizeof(int32_t) * ctx->halo_ids.size(),
-                   cudaMemcpyHostToDevice));
-    CKC(cudaMalloc(&ctx->d_halo_cnt, sizeof(int32_t) * ctx->n_patches));
-    CKC(cudaMemcpy(ctx->d_halo_cnt, ctx->halo_cnt.data(), sizeof(int32_t) * ctx->n_patches, cudaMemcpyHostToDevice));
+    if (upload_halo_tables(ctx) != TB_OK) {
+        g_create_error = ctx->err;
+        tb_destroy(ctx);
+        return TB_ERR_CUDA;
+    }
+    CKC(cudaMalloc(&ctx->d_partial, sizeof(double) * 4 * TB_NRED));
     CKC(cudaMalloc(&ctx->d_bf_slot, sizeof(int32_t) * std::max<long long>(m->n_bfacets, 4)));
     if (m->n_bfacets)
         CKC(cudaMemcpy(ctx->d_bf_slot, ctx->bf_slot.data(), sizeof(int32_t) * m->n_bfacets, cudaMemcpyHostToDevice));
@@ -387,6 +446,8 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_bf_slot);
     cudaFree(ctx->d_bf_row);
     cudaFree(ctx->d_area);
+    cudaFree(ctx->d_bath3);
+    cudaFree(ctx->d_partial);
     for (int k = 0; k < 5; ++k) {
         cudaFree(ctx->d_ext[k]);
         cudaFree(ctx->d_ext_tr[k]);
@@ -433,6 +494,11 @@ extern "C" int tb_set_option(tb_ctx *ctx, int option, double value) {
         case TB_OPT_LF_TRACER_SCALING: ctx->lf_tracer_sigma = value; break;
         case TB_OPT_TRACER_VEL_FACTOR: ctx->tracer_vel_factor = value; break;
         case TB_OPT_FORCE_GENERIC_KERNEL: ctx->force_generic = value != 0.0; break;
+        case TB_OPT_SIPG_FACTOR: ctx->sipg = value; break;
+        case TB_OPT_SIPG_FACTOR_TRACER: ctx->sipg_tracer = value; break;
+        case TB_OPT_GRAD_DIV_VISCOSITY: ctx->graddiv = value != 0.0; break;
+        case TB_OPT_GRAD_DEPTH_VISCOSITY: ctx->graddepth = value != 0.0; break;
+        case TB_OPT_TRACER_CONSERVATIVE: ctx->tracer_conservative = value != 0.0; break;
         default: return fail(ctx, TB_ERR_ARG, "unknown option");
     }
     return TB_OK;
@@ -445,6 +511,7 @@ extern "C" int tb_set_field_const(tb_ctx *ctx, int field, const double *value, i
     if (ncomp != field_ncomp(field)) return fail(ctx, TB_ERR_ARG, "wrong number of components");
     FieldStore &fs = ctx->fields[field];
     if (fs.mode == 2 || field == TB_F_BATHYMETRY) ctx->layout_dirty = true;
+    if (fs.mode == 0 && (field == TB_F_VISCOSITY || field == TB_F_DIFFUSIVITY)) ctx->layout_dirty = true;
     fs.mode = 1;
     fs.ncomp = ncomp;
     fs.v[0] = value[0];
@@ -468,6 +535,7 @@ extern "C" int tb_clear_field(tb_ctx *ctx, int field) {
     if (!ctx || field < 0 || field >= TB_F_COUNT) return fail(ctx, TB_ERR_ARG, "bad field");
     FieldStore &fs = ctx->fields[field];
     if (fs.mode == 2) ctx->layout_dirty = true;
+    if (fs.mode != 0 && (field == TB_F_VISCOSITY || field == TB_F_DIFFUSIVITY)) ctx->layout_dirty = true;
     fs.mode = 0;
     fs.vert.clear();
     return TB_OK;
@@ -479,18 +547,20 @@ static int find_slot(tb_ctx *ctx, int marker) {
     return -1;
 }
 
-extern "C" int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const double consts[6]) {
+extern "C" int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const double consts[8]) {
     if (!ctx || eq < 0 || eq > 1) return fail(ctx, TB_ERR_ARG, "bad equation id");
     const int s = find_slot(ctx, marker);
     if (s < 0) return TB_OK;   // marker not present on this (sub)mesh: nothing to do (reference loops over mesh markers)
-    if (opcode & ~(TB_BC_ELEV | TB_BC_UV | TB_BC_UN | TB_BC_FLUX | TB_BC_VALUE))
+    if (opcode & ~(TB_BC_ELEV | TB_BC_UV | TB_BC_UN | TB_BC_FLUX | TB_BC_VALUE | TB_BC_DIFF_FLUX))
         return fail(ctx, TB_ERR_ARG, "invalid boundary tag");
+    if ((opcode & TB_BC_DIFF_FLUX) && eq != 1) return fail(ctx, TB_ERR_ARG, "'diff_flux' is a tracer boundary tag");
     TbBcSlot &b = ctx->bc[eq][s];
     b.opcode = opcode | TB_BC_PRESENT;
     b.arr_mask = 0;
     if (consts) {
         b.elev = consts[0]; b.uvx = consts[1]; b.uvy = consts[2];
         b.un = consts[3]; b.flux = consts[4]; b.value = consts[5];
+        b.diff_flux = consts[6];
     }
     return TB_OK;
 }
@@ -625,6 +695,10 @@ extern "C" int tb_swe_stage(tb_ctx *ctx, double a0, double a1, double b_dt, cons
     fill_coef(ctx->fields[TB_F_ATM_PRESSURE], p.pa);
     fill_coef(ctx->fields[TB_F_MOMENTUM_SOURCE], p.msrc);
     fill_coef(ctx->fields[TB_F_VOLUME_SOURCE], p.vsrc);
+    fill_coef(ctx->fields[TB_F_VISCOSITY], p.visc);
+    p.sipg = ctx->sipg;
+    p.graddiv = ctx->graddiv;
+    p.graddepth = ctx->graddepth;
     p.use_quad = (p.man.mode || p.cd.mode || p.wind.mode || p.wd_on) ? 1 : 0;
     p.nquad = ctx->nquad;
     p.force_generic = ctx->force_generic;
@@ -675,6 +749,10 @@ extern "C" int tb_tracer_stage(tb_ctx *ctx, double a0, double a1, double b_dt, c
     p.wd_on = ctx->wd_on && ctx->nonlinear;
     p.wd_alpha2 = ctx->wd_alpha * ctx->wd_alpha;
     fill_coef(ctx->fields[TB_F_TRACER_SOURCE], p.src);
+    fill_coef(ctx->fields[TB_F_DIFFUSIVITY], p.diff);
+    p.sipg = ctx->sipg_tracer;
+    p.conservative = ctx->tracer_conservative;
+    p.nquad = ctx->nquad;
     fill_bc(ctx, 1, p.bc);
     long long first, count;
     patch_range(ctx, first, count);
@@ -792,8 +870,35 @@ extern "C" int tb_tracer_to_field(tb_ctx *ctx, const double *c, const int32_t *n
 }
 extern "C" int tb_swe_integrals(tb_ctx *ctx, const double *state, double *out, void *stream) {
     if (!ctx || !state || !out) return fail(ctx, TB_ERR_ARG, "null pointer");
-    CK(tb_launch_swe_integrals(state, ctx->d_area, ctx->n_owned, out, (cudaStream_t)stream));
+    if (ctx->layout_dirty) {
+        int rc = upload_layout(ctx);
+        if (rc != TB_OK) return rc;
+    }
+    CK(tb_launch_swe_integrals(state, ctx->d_area, ctx->d_bath3, ctx->n_owned, ctx->d_partial, out, (cudaStream_t)stream));
     ctx->launches += 2;
+    return TB_OK;
+}
+extern "C" int tb_tracer_integrals(tb_ctx *ctx, const double *c, const double *swe_state, double *out, void *stream) {
+    if (!ctx || !c || !out) return fail(ctx, TB_ERR_ARG, "null pointer");
+    if (ctx->nonlinear && !swe_state) return fail(ctx, TB_ERR_ARG, "swe_state required for the nonlinear total depth");
+    if (ctx->layout_dirty) {
+        int rc = upload_layout(ctx);
+        if (rc != TB_OK) return rc;
+    }
+    CK(tb_launch_tracer_integrals(c, swe_state, ctx->d_area, ctx->d_bath3, ctx->n_owned, ctx->nonlinear,
+                                  ctx->wd_on && ctx->nonlinear, ctx->wd_alpha * ctx->wd_alpha, ctx->nquad, ctx->d_partial,
+                                  out, (cudaStream_t)stream));
+    ctx->launches += 2;
+    return TB_OK;
+}
+extern "C" int tb_lincomb(tb_ctx *ctx, int n, const double *const *x, const double *w, double *out, int64_t len,
+                          void *stream) {
+    if (!ctx || !x || !w || !out || n < 1 || n > 6 || len < 0 || (len & 1))
+        return fail(ctx, TB_ERR_ARG, "bad linear-combination arguments");
+    for (int j = 0; j < n; ++j)
+        if (!x[j]) return fail(ctx, TB_ERR_ARG, "null operand");
+    CK(tb_launch_lincomb(n, x, w, out, len, (cudaStream_t)stream));
+    ctx->launches += len > 0;
     return TB_OK;
 }
 extern "C" int tb_gather_cells(tb_ctx *ctx, const double *state, const int32_t *idx, int64_t n, int rec_len,
@@ -843,6 +948,7 @@ extern "C" int tb_set_cell_quadrature(tb_ctx *ctx, int n, const double *lam, con
     if (!ctx || !lam || !w || n < 1 || n > TB_MAX_QUAD) return fail(ctx, TB_ERR_ARG, "bad quadrature rule");
     CK(cudaDeviceSynchronize());
     CK(tb_set_quadrature(n, lam, w));
+    CK(tb_set_quadrature_tracer(n, lam, w));
     ctx->nquad = n;
     return TB_OK;
 }

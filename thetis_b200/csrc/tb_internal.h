@@ -24,6 +24,7 @@ struct TbBcSlot {
     int pad;
     double elev, uvx, uvy, un, flux, value;
     double bnd_len;
+    double diff_flux;    // tracer 'diff_flux' datum (tracer_eq_2d.py:264-265)
 };
 
 struct TbBcTable {
@@ -43,11 +44,14 @@ struct TbBcTable {
 //   double col[ncol][NV]   vertex columns: 0 = x, 1 = y, 2 = bathymetry, then optional fields
 //   uint16 cv[TB_P][3]     local vertex ids
 //   int32  cn[TB_P][3]     >= 0: (smem cell index)*4 + local facet in neighbour;  < 0: -(1 + exterior facet)
+//   uint16 hcv[NH][3]      only when a SIPG term (viscosity / diffusion) is active: local vertex ids of the halo
+//                          cells (their vertices are then part of the patch's vertex columns), off_hcv >= 0
 struct TbPatchLayout {
     const unsigned char *sblk;
     long long stride;
     int NV, NH, ncol;
     int off_cv, off_cn;
+    int off_hcv, pad_;
     const int *halo_ids;         // [n_patches*NH] cell ids of off-patch facet neighbours
     const int *halo_cnt;         // [n_patches]
 };
@@ -64,7 +68,9 @@ struct TbSweParams {
     double g, rho0, lf_sigma, eps2, wd_alpha2;
     int lf_on, wd_on, use_quad, nquad;
     int force_generic, pad0;      // developer switch: always run the generic (SPEC 0) kernel
-    TbCoef cor, man, cd, lin, wind, pa, msrc, vsrc;
+    TbCoef cor, man, cd, lin, wind, pa, msrc, vsrc, visc;
+    double sipg;                  // sipg_factor (HorizontalViscosityTerm, shallowwater_eq.py:558)
+    int graddiv, graddepth;       // use_grad_div_viscosity_term, use_grad_depth_viscosity_term
     TbBcTable bc;
 };
 
@@ -80,7 +86,9 @@ struct TbTracerParams {
     double corr, lf_sigma;
     int lf_on, nonlin, wd_on, pad;
     double wd_alpha2;
-    TbCoef src;
+    TbCoef src, diff;
+    double sipg;                  // sipg_factor_tracer
+    int conservative, nquad;
     TbBcTable bc;
 };
 
@@ -88,6 +96,11 @@ struct TbTracerParams {
 cudaError_t tb_launch_swe_stage(const TbSweParams &p, bool nonlinear, int n_patches, size_t smem, cudaStream_t s);
 cudaError_t tb_launch_tracer_stage(const TbTracerParams &p, int n_patches, size_t smem, cudaStream_t s);
 cudaError_t tb_set_quadrature(int n, const double *lam, const double *w);
+cudaError_t tb_set_quadrature_tracer(int n, const double *lam, const double *w);
+cudaError_t tb_launch_lincomb(int n, const double *const *x, const double *w, double *out, long long len, cudaStream_t s);
+cudaError_t tb_launch_tracer_integrals(const double *c, const double *swe, const double *area, const double *bath3,
+                                       long long n_owned, int nonlin, int wd_on, double alpha2, int nquad,
+                                       double *partial, double *out, cudaStream_t s);
 int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear);
 size_t tb_swe_smem_bytes(const TbPatchLayout &pl);
 size_t tb_tracer_smem_bytes(const TbPatchLayout &pl);
@@ -108,8 +121,9 @@ cudaError_t tb_launch_scatter_cells(const double *buf, const int32_t *idx, long 
                                     cudaStream_t s);
 cudaError_t tb_launch_push_cells(const double *state, const int32_t *idx, const unsigned long long *dst, long long n,
                                  int rec, cudaStream_t s);
-cudaError_t tb_launch_swe_integrals(const double *state, const double *area, long long n_owned, double *out,
-                                    cudaStream_t s);
+cudaError_t tb_launch_swe_integrals(const double *state, const double *area, const double *bath3, long long n_owned,
+                                    double *partial, double *out, cudaStream_t s);
+#define TB_NRED 296           // CTAs of the two-pass reductions (2 per SM)
 // limiter: vertex bounds via deterministic CSR gather, then per-cell clamp
 struct TbLimiterData {
     long long n_owned, n_cells, n_tvert;

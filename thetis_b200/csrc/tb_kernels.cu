@@ -13,6 +13,7 @@
 //     with one TMA bulk store.
 //
 // Arithmetic follows thetis/shallowwater_eq.py (line refs at each term).
+#include <algorithm>
 #include "tb_internal.h"
 
 #ifndef TB_HALO_SPEC
@@ -244,6 +245,9 @@ __device__ __noinline__ void open_boundary_flux(const TbBcTable *bc, int gb, int
     out[0] = fx;
     out[1] = fy;
     out[2] = fe;
+    out[3] = ex.ux;      // external velocity and the 'un' datum: Dirichlet terms of the viscosity (:592-609)
+    out[4] = ex.uy;
+    out[5] = un;
 }
 
 template <bool NONLIN, int SPEC>
@@ -331,6 +335,8 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         const bool has_pa = SP::generic ? (prm.pa.mode == 2) : false;
         const bool has_msrc = SP::generic ? (prm.msrc.mode != 0) : false;
         const bool has_vsrc = SP::generic ? (prm.vsrc.mode != 0) : false;
+        const bool has_visc = SP::generic ? (prm.visc.mode != 0) : false;
+        const bool graddiv = SP::generic ? (prm.graddiv != 0) : false;
         const bool use_quad = SP::generic ? (prm.use_quad != 0) : (SP::man || SP::wd);
         const double a2 = prm.wd_alpha2;
 
@@ -485,6 +491,58 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
 #pragma unroll
             for (int a = 0; a < 3; ++a) Re[a] += A * (1.0 / 12.0) * (f[a] + s);
         }
+        // HorizontalViscosityTerm (shallowwater_eq.py:554-616), symmetric interior penalty.  S = stress / nu:
+        // grad(u) or 2 sym(grad(u)), constant per cell.
+        double nuv[3] = {0, 0, 0}, Sxx = 0, Sxy = 0, Syx = 0, Syy = 0;
+        const double itA = has_visc ? tb_rcp(twoA) : 0.0;
+        if (has_visc) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) nuv[a] = coef_at(prm.visc, cols, NV, v[a]);
+            // grad(u)_ij = d u_i / d x_j = -(1/2A) sum_a u_i[a] N_a,j
+            double Gxx = 0, Gxy = 0, Gyx = 0, Gyy = 0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                Gxx += ux[a] * Nx[a]; Gxy += ux[a] * Ny[a];
+                Gyx += uy[a] * Nx[a]; Gyy += uy[a] * Ny[a];
+            }
+            Gxx *= -itA; Gxy *= -itA; Gyx *= -itA; Gyy *= -itA;
+            if (graddiv) { Sxx = 2.0 * Gxx; Sxy = Gxy + Gyx; Syx = Sxy; Syy = 2.0 * Gyy; }
+            else { Sxx = Gxx; Sxy = Gxy; Syx = Gyx; Syy = Gyy; }
+            // cell term (:571): -int grad(psi):stress = +1/2 mean(nu) sum_j N_a,j S_ij
+            const double hn = (1.0 / 6.0) * (nuv[0] + nuv[1] + nuv[2]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                Rux[a] += hn * (Nx[a] * Sxx + Ny[a] * Sxy);
+                Ruy[a] += hn * (Nx[a] * Syx + Ny[a] * Syy);
+            }
+            if (prm.graddepth) {
+                // (:611-612): + int psi . (grad(H)/H . stress), non-polynomial: cell rule
+                double gHx = 0, gHy = 0, hl[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    hl[a] = NONLIN ? b[a] + et[a] : b[a];
+                    gHx += hl[a] * Nx[a];
+                    gHy += hl[a] * Ny[a];
+                }
+                gHx *= -itA;
+                gHy *= -itA;
+                const double Vx = gHx * Sxx + gHy * Syx, Vy = gHx * Sxy + gHy * Syy;
+                for (int qd = 0; qd < prm.nquad; ++qd) {
+                    const double l0 = c_qlam[qd][0], l1 = c_qlam[qd][1], l2 = c_qlam[qd][2];
+                    const double hq = l0 * hl[0] + l1 * hl[1] + l2 * hl[2];
+                    double Hq = hq, fac = 1.0;
+                    if (NONLIN && wd_on) {
+                        // H = (hl + sqrt(hl^2 + alpha^2))/2, dH/dhl = (1 + hl/sqrt(hl^2 + alpha^2))/2
+                        const double r = tb_rsqrt(hq * hq + a2);
+                        Hq = 0.5 * (hq + (hq * hq + a2) * r);
+                        fac = 0.5 * (1.0 + hq * r);
+                    }
+                    const double k = c_qw[qd] * A * (l0 * nuv[0] + l1 * nuv[1] + l2 * nuv[2]) * fac * tb_rcp(Hq);
+                    Rux[0] += l0 * k * Vx; Rux[1] += l1 * k * Vx; Rux[2] += l2 * k * Vx;
+                    Ruy[0] += l0 * k * Vy; Ruy[1] += l1 * k * Vy; Ruy[2] += l2 * k * Vy;
+                }
+            }
+        }
         if (use_quad) {
             // non-polynomial cell integrands by the degree-3 cell rule:
             // QuadraticDragTerm (:679-701), WindStressTerm (:643-649), wetting-drying HUDiv volume term
@@ -565,6 +623,37 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                 // nodal differences along the facet: trace(xi) = v_p + xi (v_q - v_p)
                 const double dKx = ux[q] - ux[p], dKy = uy[q] - uy[p], dKe = et[q] - et[p], dKb = b[q] - b[p];
                 const double dNx = nr[2 * nq_] - uNxp, dNy = nr[2 * nq_ + 1] - uNyp, dNe = nr[6 + nq_] - eNp;
+                // SIPG (:575-590): sigma_max*len, (S^K + S^N).N and the facet integral D of nu*(u_K - u_N)/2
+                double sigl = 0, Tx = 0, Ty = 0, vDx = 0, vDy = 0;
+                if (has_visc) {
+                    const int ni = code >> 2;
+                    const uint16_t *cvn = ni < TB_P
+                        ? reinterpret_cast<const uint16_t *>(blk + prm.pl.off_cv) + ni * 3
+                        : reinterpret_cast<const uint16_t *>(blk + prm.pl.off_hcv) + (ni - TB_P) * 3;
+                    double xn[3], yn[3];
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) {
+                        xn[bb] = cols[cvn[bb]];
+                        yn[bb] = cols[NV + cvn[bb]];
+                    }
+                    const double twoAN = (xn[1] - xn[0]) * (yn[2] - yn[0]) - (yn[1] - yn[0]) * (xn[2] - xn[0]);
+                    double Hxx = 0, Hxy = 0, Hyx = 0, Hyy = 0;      // grad(u) of the neighbour
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) {
+                        const double mx = yn[(bb + 2) % 3] - yn[(bb + 1) % 3], my_ = xn[(bb + 1) % 3] - xn[(bb + 2) % 3];
+                        Hxx += nr[2 * bb] * mx; Hxy += nr[2 * bb] * my_;
+                        Hyx += nr[2 * bb + 1] * mx; Hyy += nr[2 * bb + 1] * my_;
+                    }
+                    const double itAN = -tb_rcp(twoAN);
+                    Hxx *= itAN; Hxy *= itAN; Hyx *= itAN; Hyy *= itAN;
+                    double Qxx, Qxy, Qyx, Qyy;                      // S^K + S^N
+                    if (graddiv) { Qxx = Sxx + 2.0 * Hxx; Qxy = Sxy + Hxy + Hyx; Qyx = Qxy; Qyy = Syy + 2.0 * Hyy; }
+                    else { Qxx = Sxx + Hxx; Qxy = Sxy + Hxy; Qyx = Syx + Hyx; Qyy = Syy + Hyy; }
+                    Tx = Qxx * nxs + Qxy * nys;
+                    Ty = Qyx * nxs + Qyy * nys;
+                    // sigma = sipg*cp*|e|/A (cp = 3 for P1 triangles), max over both sides
+                    sigl = 6.0 * prm.sipg * len2 * tb_rcp(fmin(twoA, twoAN));
+                }
 #pragma unroll
                 for (int gp = 0; gp < 2; ++gp) {
                     const double xi = gp ? TB_XI2 : TB_XI1;
@@ -612,14 +701,43 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                         fx = t * nxs;
                         fy = t * nys;
                     }
+                    if (has_visc) {
+                        const double nug = fma(xi, nuv[q] - nuv[p], nuv[p]);    // nu is continuous (P1): avg(nu) = nu
+                        double vx = sigl * dux, vy = sigl * duy;
+                        if (graddiv) {
+                            const double dn = sigl * dun * il * il;
+                            vx += dn * nxs;
+                            vy += dn * nys;
+                        }
+                        fx += nug * (vx - 0.5 * Tx);
+                        fy += nug * (vy - 0.5 * Ty);
+                        vDx += 0.5 * nug * dux;
+                        vDy += 0.5 * nug * duy;
+                    }
                     Fpx += hp_ * fx; Fpy += hp_ * fy; Fpe += hp_ * fe;
                     Fqx += hq_ * fx; Fqy += hq_ * fy; Fqe += hq_ * fe;
+                }
+                if (has_visc) {
+                    // -inner(avg(grad(psi)), stress_jump) (:588): all three nodes, d_j phi_a = -N_a,j/2A
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const double nn = Nx[a] * nxs + Ny[a] * nys;
+                        double tx = vDx * nn, ty = vDy * nn;
+                        if (graddiv) {
+                            const double nd = Nx[a] * vDx + Ny[a] * vDy;
+                            tx += nxs * nd;
+                            ty += nys * nd;
+                        }
+                        Rux[a] -= 0.5 * itA * tx;
+                        Ruy[a] -= 0.5 * itA * ty;
+                    }
                 }
             } else {
                 const int gb = -(code + 1);
                 const int slot = __ldg(prm.bc.bf_slot + gb);
                 const int op = prm.bc.slots[slot].opcode;
                 const bool closed = (op & (TB_BC_ELEV | TB_BC_UV | TB_BC_UN | TB_BC_FLUX)) == 0;
+                double bDx = 0, bDy = 0;
 #pragma unroll 1
                 for (int gp = 0; gp < 2; ++gp) {
                     const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
@@ -627,7 +745,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                     const double eK = wp_ * et[p] + wq_ * et[q];
                     const double bg = wp_ * b[p] + wq_ * b[q];
                     const double HK = NONLIN ? wd_depth(bg + eK, wd_on, a2) : bg;
-                    double fl[3];
+                    double fl[6];
                     if (closed) {
                         // land boundary (:376-381), mirror-velocity Lax-Friedrichs (:489-497)
                         const double uKN = uKx * nxs + uKy * nys;
@@ -640,9 +758,48 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                     } else {
                         open_boundary_flux<NONLIN>(&prm.bc, gb, slot, wp_, wq_, uKx, uKy, eK, bg, HK, nxs, nys, il, len, g,
                                                    wd_on, a2, fl);
+                        if (has_visc && (op & (TB_BC_UV | TB_BC_UN | TB_BC_FLUX))) {
+                            // Dirichlet terms of the viscosity (:592-609); 'elev' alone leaves uv_ext = uv: skipped
+                            double ddx, ddy;
+                            if (op & TB_BC_UN) {
+                                const double sn = ((uKx * nxs + uKy * nys) * il - fl[5]) * il;
+                                ddx = sn * nxs;
+                                ddy = sn * nys;
+                            } else {
+                                ddx = uKx - fl[3];
+                                ddy = uKy - fl[4];
+                            }
+                            const double nug = wp_ * nuv[p] + wq_ * nuv[q];
+                            const double sl = 6.0 * prm.sipg * len2 * itA;      // sigma*len, own cell only
+                            double vx = sl * ddx, vy = sl * ddy;
+                            if (graddiv) {
+                                const double dn = sl * (ddx * nxs + ddy * nys) * il * il;
+                                vx += dn * nxs;
+                                vy += dn * nys;
+                            }
+                            fl[0] += nug * (vx - (Sxx * nxs + Sxy * nys));
+                            fl[1] += nug * (vy - (Syx * nxs + Syy * nys));
+                            bDx += 0.5 * nug * ddx;
+                            bDy += 0.5 * nug * ddy;
+                        }
                     }
                     Fpx += 0.5 * wp_ * fl[0]; Fpy += 0.5 * wp_ * fl[1]; Fpe += 0.5 * wp_ * fl[2];
                     Fqx += 0.5 * wq_ * fl[0]; Fqy += 0.5 * wq_ * fl[1]; Fqe += 0.5 * wq_ * fl[2];
+                }
+                if (has_visc && !closed) {
+                    // -inner(grad(psi), stress_jump) ds (:606)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const double nn = Nx[a] * nxs + Ny[a] * nys;
+                        double tx = bDx * nn, ty = bDy * nn;
+                        if (graddiv) {
+                            const double nd = Nx[a] * bDx + Ny[a] * bDy;
+                            tx += nxs * nd;
+                            ty += nys * nd;
+                        }
+                        Rux[a] -= itA * tx;
+                        Ruy[a] -= itA * ty;
+                    }
                 }
             }
             Rux[p] -= Fpx; Ruy[p] -= Fpy; Re[p] -= Fpe;
@@ -695,7 +852,8 @@ cudaError_t tb_kernels_init() {
 
 // which specialisation serves this parameter set (0 = generic)
 int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear) {
-    const bool extras = p.cd.mode || p.lin.mode || p.wind.mode || p.pa.mode == 2 || p.msrc.mode || p.vsrc.mode;
+    const bool extras = p.cd.mode || p.lin.mode || p.wind.mode || p.pa.mode == 2 || p.msrc.mode || p.vsrc.mode ||
+                        p.visc.mode;
     if (extras) return 0;
     if (!p.man.mode && !p.cor.mode && !p.wd_on && (!nonlinear || p.lf_on)) return 1;
     if (nonlinear && p.lf_on && p.man.mode && p.cor.mode && p.nquad == 6) return p.wd_on ? 3 : 2;
@@ -824,12 +982,70 @@ cudaError_t tb_launch_scatter_cells(const double *buf, const int32_t *idx, long 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ Butcher-form stage combinations
+// out = sum_j w[j] * x[j]   (ERKGeneric.update_solution / get_final_solution, rungekutta.py:816-852); streaming, HBM bound
+struct TbLincomb {
+    const double *x[6];
+    double w[6];
+    int n;
+};
+__global__ void lincomb_kernel(TbLincomb p, double *__restrict__ out, long long len2) {
+    // two doubles per thread per iteration (16-byte accesses; state arrays are multiples of 2 doubles)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len2; i += (long long)gridDim.x * blockDim.x) {
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            if (j < p.n) {
+                const double2 v = reinterpret_cast<const double2 *>(p.x[j])[i];
+                acc.x = fma(p.w[j], v.x, acc.x);
+                acc.y = fma(p.w[j], v.y, acc.y);
+            }
+        }
+        reinterpret_cast<double2 *>(out)[i] = acc;
+    }
+}
+cudaError_t tb_launch_lincomb(int n, const double *const *x, const double *w, double *out, long long len, cudaStream_t s) {
+    if (len <= 0) return cudaSuccess;
+    TbLincomb p;
+    p.n = n;
+    for (int j = 0; j < 6; ++j) {
+        p.x[j] = j < n ? x[j] : nullptr;
+        p.w[j] = j < n ? w[j] : 0.0;
+    }
+    const long long len2 = len / 2;
+    const unsigned grid = (unsigned)std::min<long long>((len2 + 255) / 256, 148 * 16);
+    lincomb_kernel<<<grid, 256, 0, s>>>(p, out, len2);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ diagnostics
-// out[0] = int eta^2, out[1] = int |u|^2, out[2] = int eta  (deterministic two-pass reduction)
+// Deterministic two-pass reductions (fixed grid, fixed order): TB_NRED CTAs write partials, one CTA sums them.
+template <int NV_>
+__device__ __forceinline__ void block_reduce_store(double (&a)[NV_], double *partial, const int *op) {
+    __shared__ double sh[NV_][8];
+#pragma unroll
+    for (int k = 0; k < NV_; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            const double t = __shfl_down_sync(0xffffffffu, a[k], o);
+            a[k] = op[k] == 0 ? a[k] + t : (op[k] == 1 ? fmin(a[k], t) : fmax(a[k], t));
+        }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0)
+#pragma unroll
+        for (int k = 0; k < NV_; ++k) sh[k][w] = a[k];
+    __syncthreads();
+    if (threadIdx.x < NV_) {
+        const int k = threadIdx.x;
+        double r = sh[k][0];
+        for (int j = 1; j < (int)(blockDim.x >> 5); ++j)
+            r = op[k] == 0 ? r + sh[k][j] : (op[k] == 1 ? fmin(r, sh[k][j]) : fmax(r, sh[k][j]));
+        partial[blockIdx.x * NV_ + k] = r;
+    }
+}
+// out[0] = int eta^2, out[1] = int |u|^2, out[2] = int eta, out[3] = int (eta + bathymetry)  (comp_volume_2d)
 __global__ void swe_integrals_partial(const double *__restrict__ state, const double *__restrict__ area,
-                                      long long n_owned, double *__restrict__ partial) {
-    __shared__ double sh[3][8];
-    double a0 = 0, a1 = 0, a2 = 0;
+                                      const double *__restrict__ bath3, long long n_owned, double *__restrict__ partial) {
+    double a[4] = {0, 0, 0, 0};
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n_owned;
          c += (long long)gridDim.x * blockDim.x) {
         const double *r = state + c * 9;
@@ -837,41 +1053,70 @@ __global__ void swe_integrals_partial(const double *__restrict__ state, const do
         // int f g = A/12 (sum_a f_a g_a + (sum f)(sum g))
         const double se = r[6] + r[7] + r[8];
         const double sx = r[0] + r[2] + r[4], sy = r[1] + r[3] + r[5];
-        a0 += A * (1.0 / 12.0) * (r[6] * r[6] + r[7] * r[7] + r[8] * r[8] + se * se);
-        a1 += A * (1.0 / 12.0) *
-              (r[0] * r[0] + r[2] * r[2] + r[4] * r[4] + sx * sx + r[1] * r[1] + r[3] * r[3] + r[5] * r[5] + sy * sy);
-        a2 += A * (1.0 / 3.0) * se;
+        a[0] += A * (1.0 / 12.0) * (r[6] * r[6] + r[7] * r[7] + r[8] * r[8] + se * se);
+        a[1] += A * (1.0 / 12.0) *
+                (r[0] * r[0] + r[2] * r[2] + r[4] * r[4] + sx * sx + r[1] * r[1] + r[3] * r[3] + r[5] * r[5] + sy * sy);
+        a[2] += A * (1.0 / 3.0) * se;
+        a[3] += A * (1.0 / 3.0) * (se + bath3[c * 3] + bath3[c * 3 + 1] + bath3[c * 3 + 2]);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_down_sync(0xffffffffu, a0, o);
-        a1 += __shfl_down_sync(0xffffffffu, a1, o);
-        a2 += __shfl_down_sync(0xffffffffu, a2, o);
+    const int op[4] = {0, 0, 0, 0};
+    block_reduce_store<4>(a, partial, op);
+}
+// out[0] = int c, out[1] = int H c (comp_tracer_mass_2d with H = total depth), out[2] = min c, out[3] = max c
+__global__ void tracer_integrals_partial(const double *__restrict__ c, const double *__restrict__ swe,
+                                         const double *__restrict__ area, const double *__restrict__ bath3,
+                                         long long n_owned, int nonlin, int wd_on, double alpha2, int nquad,
+                                         double *__restrict__ partial) {
+    double a[4] = {0, 0, 1.0e300, -1.0e300};
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_owned;
+         k += (long long)gridDim.x * blockDim.x) {
+        const double q0 = c[k * 3], q1 = c[k * 3 + 1], q2 = c[k * 3 + 2];
+        const double A = area[k];
+        a[0] += A * (1.0 / 3.0) * (q0 + q1 + q2);
+        double h[3];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) h[n] = bath3[k * 3 + n] + (nonlin ? swe[k * 9 + 6 + n] : 0.0);
+        double m = 0;
+        if (nonlin && wd_on) {
+            // non-polynomial depth: the degree-3 cell rule (c_qlam / c_qw)
+            for (int qd = 0; qd < nquad; ++qd) {
+                const double l0 = c_qlam[qd][0], l1 = c_qlam[qd][1], l2 = c_qlam[qd][2];
+                const double hq = l0 * h[0] + l1 * h[1] + l2 * h[2];
+                m += c_qw[qd] * 0.5 * (hq + sqrt(hq * hq + alpha2)) * (l0 * q0 + l1 * q1 + l2 * q2);
+            }
+            m *= A;
+        } else {
+            m = A * (1.0 / 12.0) * (h[0] * q0 + h[1] * q1 + h[2] * q2 + (h[0] + h[1] + h[2]) * (q0 + q1 + q2));
+        }
+        a[1] += m;
+        a[2] = fmin(a[2], fmin(q0, fmin(q1, q2)));
+        a[3] = fmax(a[3], fmax(q0, fmax(q1, q2)));
     }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { sh[0][w] = a0; sh[1][w] = a1; sh[2][w] = a2; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        double s = 0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += sh[threadIdx.x][k];
-        partial[blockIdx.x * 3 + threadIdx.x] = s;
+    const int op[4] = {0, 0, 1, 2};
+    block_reduce_store<4>(a, partial, op);
+}
+__global__ void integrals_final(const double *__restrict__ partial, int nb, int op2, int op3, double *__restrict__ out) {
+    if (threadIdx.x < 4) {
+        const int k = threadIdx.x;
+        const int op = k == 2 ? op2 : (k == 3 ? op3 : 0);
+        double r = partial[k];
+        for (int j = 1; j < nb; ++j) {
+            const double t = partial[j * 4 + k];
+            r = op == 0 ? r + t : (op == 1 ? fmin(r, t) : fmax(r, t));
+        }
+        out[k] = r;
     }
 }
-__global__ void swe_integrals_final(const double *__restrict__ partial, int nb, double *__restrict__ out) {
-    if (threadIdx.x < 3) {
-        double s = 0;
-        for (int k = 0; k < nb; ++k) s += partial[k * 3 + threadIdx.x];
-        out[threadIdx.x] = s;
-    }
+cudaError_t tb_launch_swe_integrals(const double *state, const double *area, const double *bath3, long long n_owned,
+                                    double *partial, double *out, cudaStream_t s) {
+    swe_integrals_partial<<<TB_NRED, 256, 0, s>>>(state, area, bath3, n_owned, partial);
+    integrals_final<<<1, 32, 0, s>>>(partial, TB_NRED, 0, 0, out);
+    return cudaGetLastError();
 }
-static double *g_partial = nullptr;
-cudaError_t tb_launch_swe_integrals(const double *state, const double *area, long long n_owned, double *out,
-                                    cudaStream_t s) {
-    const int nb = 296;
-    if (!g_partial) {
-        cudaError_t e = cudaMalloc(&g_partial, sizeof(double) * 3 * nb);
-        if (e != cudaSuccess) return e;
-    }
-    swe_integrals_partial<<<nb, 256, 0, s>>>(state, area, n_owned, g_partial);
-    swe_integrals_final<<<1, 32, 0, s>>>(g_partial, nb, out);
+cudaError_t tb_launch_tracer_integrals(const double *c, const double *swe, const double *area, const double *bath3,
+                                       long long n_owned, int nonlin, int wd_on, double alpha2, int nquad,
+                                       double *partial, double *out, cudaStream_t s) {
+    tracer_integrals_partial<<<TB_NRED, 256, 0, s>>>(c, swe, area, bath3, n_owned, nonlin, wd_on, alpha2, nquad, partial);
+    integrals_final<<<1, 32, 0, s>>>(partial, TB_NRED, 1, 2, out);
     return cudaGetLastError();
 }

@@ -7,6 +7,15 @@
 #define TB_XI2 0.78867513459481288225
 #define TB_BC_PRESENT 32   // marker has a (possibly empty) dict in bnd_conditions
 
+// degree-3 cell rule for the non-polynomial integrand of ConservativeSourceTerm (H*source with wetting-drying)
+__constant__ double ct_qlam[TB_MAX_QUAD][3];
+__constant__ double ct_qw[TB_MAX_QUAD];
+cudaError_t tb_set_quadrature_tracer(int n, const double *lam, const double *w) {
+    cudaError_t e = cudaMemcpyToSymbol(ct_qlam, lam, sizeof(double) * 3 * n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(ct_qw, w, sizeof(double) * n);
+}
+
 __device__ __forceinline__ uint32_t t_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void t_mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_smem_u32(bar)), "r"(count));
@@ -111,11 +120,15 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
         const double twoA = (x[1] - x[0]) * (y[2] - y[0]) - (y[1] - y[0]) * (x[2] - x[0]);
         double R[3] = {0, 0, 0};
         const double sc = c[0] + c[1] + c[2];
+        const bool cons = prm.conservative != 0;     // unknown = depth-integrated tracer (tracer_eq_2d.py:323-437)
+        const bool has_diff = prm.diff.mode != 0;
         {
-            // cell part (:159-160): + c div(u phi_a)
+            // cell part (:159-160): + c div(u phi_a); conservative form (:356-357): + c u.grad(phi_a)
             double D = 0;
+            if (!cons) {
 #pragma unroll
-            for (int bb = 0; bb < 3; ++bb) D += -0.5 * (Nx[bb] * ux[bb] + Ny[bb] * uy[bb]);
+                for (int bb = 0; bb < 3; ++bb) D += -0.5 * (Nx[bb] * ux[bb] + Ny[bb] * uy[bb]);
+            }
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 double s = D * (c[a] + sc);
@@ -131,8 +144,37 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
             for (int a = 0; a < 3; ++a)
                 f[a] = prm.src.mode == 2 ? cols[(size_t)prm.src.col * NV + v[a]] : prm.src.v0;
             const double s = f[0] + f[1] + f[2];
+            if (!cons) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) R[a] += 0.5 * twoA * (1.0 / 12.0) * (f[a] + s);
+                for (int a = 0; a < 3; ++a) R[a] += 0.5 * twoA * (1.0 / 12.0) * (f[a] + s);
+            } else {
+                // ConservativeSourceTerm (:429-437): int H*source*phi_a by the cell rule
+                double hl[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) hl[a] = prm.nonlin ? b[a] + et[a] : b[a];
+                for (int qd = 0; qd < prm.nquad; ++qd) {
+                    const double l0 = ct_qlam[qd][0], l1 = ct_qlam[qd][1], l2 = ct_qlam[qd][2];
+                    double Hq = l0 * hl[0] + l1 * hl[1] + l2 * hl[2];
+                    if (prm.nonlin && prm.wd_on) Hq = 0.5 * (Hq + sqrt(Hq * Hq + prm.wd_alpha2));
+                    const double k = ct_qw[qd] * 0.5 * twoA * Hq * (l0 * f[0] + l1 * f[1] + l2 * f[2]);
+                    R[0] += l0 * k; R[1] += l1 * k; R[2] += l2 * k;
+                }
+            }
+        }
+        // HorizontalDiffusionTerm (tracer_eq_2d.py:226-278), symmetric interior penalty
+        double muv[3] = {0, 0, 0}, gcx = 0, gcy = 0;
+        const double itA = 1.0 / twoA;
+        if (has_diff) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                muv[a] = prm.diff.mode == 2 ? cols[(size_t)prm.diff.col * NV + v[a]] : prm.diff.v0;
+                gcx -= itA * c[a] * Nx[a];        // grad(phi_a) = -N_a/2A
+                gcy -= itA * c[a] * Ny[a];
+            }
+            // cell term (:238): -int mu grad(phi_a).grad(c) = +1/2 mean(mu) N_a.grad(c)
+            const double hm = (1.0 / 6.0) * (muv[0] + muv[1] + muv[2]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) R[a] += hm * (Nx[a] * gcx + Ny[a] * gcy);
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -148,6 +190,30 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
                 const int np_ = (lf + 2) % 3, nq_ = (lf + 1) % 3;
                 const double uNxp = corr * nr[2 * np_], uNyp = corr * nr[2 * np_ + 1], cNp = nc[np_];
                 const double uNxq = corr * nr[2 * nq_], uNyq = corr * nr[2 * nq_ + 1], cNq = nc[nq_];
+                double sigl = 0, T = 0, Dc = 0;
+                if (has_diff) {
+                    // neighbour geometry -> its grad(c) and area (:241-258)
+                    const uint16_t *cvn = ni < TB_P
+                        ? reinterpret_cast<const uint16_t *>(blk + prm.pl.off_cv) + ni * 3
+                        : reinterpret_cast<const uint16_t *>(blk + prm.pl.off_hcv) + (ni - TB_P) * 3;
+                    double xn[3], yn[3];
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) {
+                        xn[bb] = cols[cvn[bb]];
+                        yn[bb] = cols[NV + cvn[bb]];
+                    }
+                    const double twoAN = (xn[1] - xn[0]) * (yn[2] - yn[0]) - (yn[1] - yn[0]) * (xn[2] - xn[0]);
+                    double hx = 0, hy = 0;
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) {
+                        hx += nc[bb] * (yn[(bb + 2) % 3] - yn[(bb + 1) % 3]);
+                        hy += nc[bb] * (xn[(bb + 1) % 3] - xn[(bb + 2) % 3]);
+                    }
+                    hx /= -twoAN;
+                    hy /= -twoAN;
+                    T = (gcx + hx) * nxs + (gcy + hy) * nys;
+                    sigl = 6.0 * prm.sipg * (nxs * nxs + nys * nys) / fmin(twoA, twoAN);   // sigma_max * len
+                }
 #pragma unroll
                 for (int gp = 0; gp < 2; ++gp) {
                     const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
@@ -156,11 +222,28 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
                     const double cK = wp_ * c[p] + wq_ * c[q], cN = wp_ * cNp + wq_ * cNq;
                     const double unav = 0.5 * ((uKx + uNx) * nxs + (uKy + uNy) * nys);   // avg(u).n * len (own outward n)
                     // upwind value (:164-168); sign(0) = 0 gives the mean
-                    const double cup = unav > 0.0 ? cK : (unav < 0.0 ? cN : 0.5 * (cK + cN));
-                    double f = cup * (uKx * nxs + uKy * nys);                              // own velocity trace (:170-171)
-                    if (prm.lf_on) f += 0.5 * fabs(unav) * prm.lf_sigma * (cK - cN);     // (:173-175)
+                    double f;
+                    if (!cons) {
+                        const double cup = unav > 0.0 ? cK : (unav < 0.0 ? cN : 0.5 * (cK + cN));
+                        f = cup * (uKx * nxs + uKy * nys);                                 // own velocity trace (:170-171)
+                    } else {
+                        // flux_up = c u of the upwind side (:364-370)
+                        const double fK = cK * (uKx * nxs + uKy * nys), fN = cN * (uNx * nxs + uNy * nys);
+                        f = unav > 0.0 ? fK : (unav < 0.0 ? fN : 0.5 * (fK + fN));
+                    }
+                    if (prm.lf_on) f += 0.5 * fabs(unav) * prm.lf_sigma * (cK - cN);     // (:173-175, 372-380)
+                    if (has_diff) {
+                        const double mug = wp_ * muv[p] + wq_ * muv[q];                    // mu is continuous (P1)
+                        f += mug * (sigl * (cK - cN) - 0.5 * T);
+                        Dc += 0.5 * mug * (cK - cN);
+                    }
                     Fp += wp_ * f;
                     Fq += wq_ * f;
+                }
+                if (has_diff) {
+                    // -inner(avg(mu grad(phi)), jump(c, n)) (:253-254): all three nodes
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) R[a] -= 0.5 * itA * (Nx[a] * nxs + Ny[a] * nys) * Dc;
                 }
             } else {
                 const int gb = -(code + 1);
@@ -221,8 +304,23 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
                             uey = un * nys * il;
                         }
                         const double unav = 0.5 * ((uKx + uex) * nxs + (uKy + uey) * nys);
-                        const double cup = unav > 0.0 ? cK : (unav < 0.0 ? cext : 0.5 * (cK + cext));
-                        f = cup * unav;                                                    // (:181-188)
+                        if (!cons) {
+                            const double cup = unav > 0.0 ? cK : (unav < 0.0 ? cext : 0.5 * (cK + cext));
+                            f = cup * unav;                                                // (:181-188)
+                        } else {
+                            // flux_up = c_in*uv*s + c_ext*uv_ext*(1-s)  (:391-394)
+                            const double fK = cK * (uKx * nxs + uKy * nys), fE = cext * (uex * nxs + uey * nys);
+                            f = unav > 0.0 ? fK : (unav < 0.0 ? fE : 0.5 * (fK + fE));
+                        }
+                        if (has_diff) {
+                            if (op & TB_BC_DIFF_FLUX) {
+                                f -= bs.diff_flux * len2 * il;                              // (:264-265)
+                            } else {
+                                // -test*dot(mu grad(c_up), n) (:267-272): grad(c_ext) = 0 for a Constant 'value'
+                                const double sg = (op & TB_BC_VALUE) ? (unav > 0.0 ? 1.0 : (unav < 0.0 ? 0.0 : 0.5)) : 1.0;
+                                f -= sg * (wp_ * muv[p] + wq_ * muv[q]) * (gcx * nxs + gcy * nys);
+                            }
+                        }
                     }
                     Fp += wp_ * f;
                     Fq += wq_ * f;

@@ -120,9 +120,11 @@ class Engine:
         self._ck(self.lib.tb_set_boundary_length(self.ctx, int(marker), float(length)))
 
     def set_bc(self, eq, marker, opcode, consts=None):
-        c = np.zeros(6, dtype=np.float64)
+        """consts: {elev, uv_x, uv_y, un, flux, value[, diff_flux]}"""
+        c = np.zeros(8, dtype=np.float64)
         if consts is not None:
-            c[:] = consts
+            consts = np.asarray(consts, dtype=np.float64).reshape(-1)
+            c[:consts.shape[0]] = consts
         self._ck(self.lib.tb_set_bc(self.ctx, eq, int(marker), int(opcode), _np_ptr(c)))
 
     def set_bc_array(self, eq, marker, tag, values):
@@ -161,7 +163,19 @@ class Engine:
         self._ck(self.lib.tb_limiter_apply(self.ctx, _ptr(c), self.stream))
 
     def swe_integrals(self, state, out):
+        """out (device, 4 doubles): int eta^2, int |u|^2, int eta, int (eta + bathymetry)"""
         self._ck(self.lib.tb_swe_integrals(self.ctx, _ptr(state), _ptr(out), self.stream))
+
+    def tracer_integrals(self, c, swe_state, out):
+        """out (device, 4 doubles): int c, int H c, min c, max c"""
+        self._ck(self.lib.tb_tracer_integrals(self.ctx, _ptr(c), _ptr(swe_state), _ptr(out), self.stream))
+
+    def lincomb(self, terms, out):
+        """out = sum w*x over ``terms`` = [(w, tensor), ...] (at most 6); out may alias an operand."""
+        n = len(terms)
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for _, t in terms])
+        ws = (C.c_double * n)(*[float(w) for w, _ in terms])
+        self._ck(self.lib.tb_lincomb(self.ctx, n, ptrs, ws, _ptr(out), int(out.numel()), self.stream))
 
     def gather_cells(self, state, idx, rec_len, buf):
         self._ck(self.lib.tb_gather_cells(self.ctx, _ptr(state), _ptr(idx), int(idx.numel()), rec_len, _ptr(buf),

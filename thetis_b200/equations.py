@@ -47,7 +47,7 @@ class ShallowWaterEquations:
 
 
 class TracerEquation2D:
-    """2D tracer advection equation in non-conservative form (descriptor)."""
+    """2D tracer advection-diffusion equation in conservative or non-conservative form (descriptor)."""
 
     def __init__(self, system, function_space, depth, options, velocity):
         self.system = system
@@ -55,8 +55,8 @@ class TracerEquation2D:
         self.depth = depth
         self.options = options
         self.velocity = velocity
+        # conservative (depth-integrated) or non-conservative terms per label, like add_conservative_terms /
+        # add_nonconservative_terms (tracer_eq_2d.py:470-488)
         tr = getattr(options, "tracer", {}) or {}
-        for label in system.split(","):
-            o = tr.get(label)
-            if o is not None and getattr(o, "use_conservative_form", False):
-                raise NotImplementedError("conservative tracer form is outside the accelerated path")
+        self.labels = system.split(",")
+        self.conservative = {label: bool(getattr(tr.get(label), "use_conservative_form", False)) for label in self.labels}

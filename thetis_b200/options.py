@@ -56,6 +56,12 @@ class ModelOptions2d:
         self.nikuradse_bed_roughness = None
         self.norm_smoother = Constant(0.0)
         self.horizontal_viscosity = None
+        self.use_grad_div_viscosity_term = False          # options.py:597
+        self.use_grad_depth_viscosity_term = True         # options.py:602
+        self.sipg_factor = Constant(1.0)                  # options.py:730
+        self.sipg_factor_tracer = Constant(1.0)           # options.py:732
+        self.horizontal_viscosity_scale = Constant(1.0)   # options.py:655 (only used by the implicit SIPG estimate)
+        self.horizontal_diffusivity_scale = Constant(1.0)
         self.coriolis_frequency = None
         self.wind_stress = None
         self.atmospheric_pressure = None

@@ -304,6 +304,17 @@ class HaloPlan:
         dist.all_reduce(t)
         return t
 
+    def allreduce(self, t, ops):
+        """Element-wise global reduction of a small device vector: ops[i] in 's' (sum), 'm' (min), 'M' (max)."""
+        import torch.distributed as dist
+        for kind, op in (("s", dist.ReduceOp.SUM), ("m", dist.ReduceOp.MIN), ("M", dist.ReduceOp.MAX)):
+            idx = [i for i, c in enumerate(ops) if c == kind]
+            if idx:
+                sub = t[idx].contiguous()
+                dist.all_reduce(sub, op=op)
+                t[idx] = sub
+        return t
+
 
 def distribute_mesh(mesh: Mesh2D, rank=None, world=None, halo="vertex", transport="auto", overlap=True):
     """

@@ -25,7 +25,8 @@ from . import _lib as L
 from .adaptor import get_adaptor, is_constant, is_function, constant_value
 from .engine import Engine
 
-__all__ = ["SSPRK33", "ERKGenericShuOsher", "ForwardEuler", "butcher_to_shuosher_form", "CFL_UNCONDITIONALLY_STABLE"]
+__all__ = ["SSPRK33", "ERKGenericShuOsher", "ERKGeneric", "ERKLSPUM2", "ERKLPUM2", "ERKMidpoint", "ERKEuler",
+           "ForwardEuler", "butcher_to_shuosher_form", "CFL_UNCONDITIONALLY_STABLE"]
 
 CFL_UNCONDITIONALLY_STABLE = np.inf
 
@@ -58,10 +59,12 @@ _SWE_FIELDS = {
     "quadratic_drag_coefficient": L.F_QUAD_DRAG, "linear_drag_coefficient": L.F_LINEAR_DRAG,
     "wind_stress": L.F_WIND_STRESS, "atmospheric_pressure": L.F_ATM_PRESSURE,
     "momentum_source": L.F_MOMENTUM_SOURCE, "volume_source": L.F_VOLUME_SOURCE,
+    "viscosity_h": L.F_VISCOSITY,
 }
 _SWE_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX}
-_TRACER_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX, "value": L.BC_VALUE}
-_CONST_SLOT = {"elev": 0, "uv": 1, "un": 3, "flux": 4, "value": 5}
+_TRACER_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX, "value": L.BC_VALUE,
+                "diff_flux": L.BC_DIFF_FLUX}
+_CONST_SLOT = {"elev": 0, "uv": 1, "un": 3, "flux": 4, "value": 5, "diff_flux": 6}
 
 
 def _opt(options, name, default=None):
@@ -95,6 +98,8 @@ class ERKGenericShuOsher:
     b = None
     c = None
     cfl_coeff = 1.0
+    n_buffers = 3
+    butcher_form = False
 
     def __init__(self, equation, solution, fields, dt, options=None, bnd_conditions=None, terms_to_add="all",
                  sync_policy="every_step"):
@@ -112,10 +117,13 @@ class ERKGenericShuOsher:
         self.b = np.array(self.b, dtype=float)
         self.c = np.array(self.c, dtype=float)
         self.n_stages = len(self.b)
-        self.alpha, self.beta = butcher_to_shuosher_form(self.a, self.b)
-        for i in range(self.n_stages):
-            if np.any(self.alpha[i + 1][1:i] != 0.0):
-                raise NotImplementedError("Shu-Osher form uses intermediate stages other than u^(0) and the latest")
+        if self.butcher_form:
+            self.n_buffers = self.n_stages + 2           # solution, stage solution, one tendency per stage
+        else:
+            self.alpha, self.beta = butcher_to_shuosher_form(self.a, self.b)
+            for i in range(self.n_stages):
+                if np.any(self.alpha[i + 1][1:i] != 0.0):
+                    raise NotImplementedError("Shu-Osher form uses intermediate stages other than u^(0) and the latest")
         self.sync_policy = sync_policy          # 'every_step' | 'manual'
         self._kind = self._equation_kind()
         mesh_obj = self._function_space().mesh()
@@ -155,7 +163,8 @@ class ERKGenericShuOsher:
                 raise NotImplementedError("velocity and elevation P1DG spaces must share their node numbering")
             self.node_map = torch.as_tensor(nm_u.reshape(-1)).to(dev)
             n_nodes = int(np.asarray(eta_f.dat.data_ro).shape[0])
-            self.buf = self.halo.alloc(9) if self.halo is not None else [eng.new_state() for _ in range(3)]
+            nb = self.n_buffers
+            self.buf = self.halo.alloc(9, nbuf=nb) if self.halo is not None else [eng.new_state() for _ in range(nb)]
             self._d_uv = torch.empty((n_nodes, 2), dtype=torch.float64, device=dev)
             self._d_eta = torch.empty(n_nodes, dtype=torch.float64, device=dev)
             self._h_uv = torch.empty((n_nodes, 2), dtype=torch.float64).pin_memory()
@@ -165,7 +174,8 @@ class ERKGenericShuOsher:
             nm = ad.dg_node_map(self.solution.function_space())
             self.node_map = torch.as_tensor(nm.reshape(-1)).to(dev)
             n_nodes = int(np.asarray(self.solution.dat.data_ro).shape[0])
-            self.buf = self.halo.alloc(3) if self.halo is not None else [eng.new_tracer() for _ in range(3)]
+            nb = self.n_buffers
+            self.buf = self.halo.alloc(3, nbuf=nb) if self.halo is not None else [eng.new_tracer() for _ in range(nb)]
             self._d_q = torch.empty(n_nodes, dtype=torch.float64, device=dev)
             self._h_q = torch.empty(n_nodes, dtype=torch.float64).pin_memory()
             self._own_swe_state = None
@@ -175,8 +185,6 @@ class ERKGenericShuOsher:
 
     def _check_supported(self):
         if self._kind == "swe":
-            if self.fields.get("viscosity_h") is not None:
-                raise NotImplementedError("horizontal viscosity is outside the accelerated path")
             if self.fields.get("nikuradse_bed_roughness") is not None:
                 raise NotImplementedError("nikuradse_bed_roughness is outside the accelerated path")
             for m, funcs in self.bnd_conditions.items():
@@ -191,13 +199,34 @@ class ERKGenericShuOsher:
             opts = self.equation.options
             if _opt(opts, "use_supg_tracer", False):
                 raise NotImplementedError("SUPG is outside the accelerated path")
-            for k, v in self.fields.items():
-                if k.startswith("diffusivity_h") and v is not None:
-                    raise NotImplementedError("tracer diffusion is outside the accelerated path")
+            diff = self._tracer_field("diffusivity_h")
+            for m, funcs in self.bnd_conditions.items():
+                for k, v in (funcs or {}).items():
+                    if k == "diff_flux" and not is_constant(v):
+                        raise NotImplementedError("spatially varying 'diff_flux' is outside the accelerated path")
+                    if k == "value" and diff is not None and not is_constant(v):
+                        raise NotImplementedError(
+                            "diffusive boundary flux with a spatially varying 'value' is outside the accelerated path")
 
     # ------------------------------------------------------------------ configuration upload
     def _depth(self):
         return self.equation.depth
+
+    def _tracer_label(self):
+        lab = getattr(self.equation, "system", None)
+        if lab is None:
+            lab = getattr(self.equation, "labels", [None])[0]
+        return lab
+
+    def _tracer_field(self, prefix):
+        """fields['<prefix>-<label>'] (solver2d.py:590-592); falls back to any key with that prefix."""
+        lab = self._tracer_label()
+        if lab is not None and f"{prefix}-{lab}" in self.fields:
+            return self.fields[f"{prefix}-{lab}"]
+        for k, v in self.fields.items():
+            if k.startswith(prefix) and v is not None:
+                return v
+        return None
 
     def _push_static(self):
         """Options, bathymetry and everything else read once at construction."""
@@ -216,8 +245,16 @@ class ERKGenericShuOsher:
             eng.set_boundary_length(m, ln)
         if self._kind == "swe":
             eng.set_option(L.OPT_LAX_FRIEDRICHS, bool(_opt(eqo, "use_lax_friedrichs_velocity", True)))
+            eng.set_option(L.OPT_GRAD_DIV_VISCOSITY, bool(_opt(eqo, "use_grad_div_viscosity_term", False)))
+            eng.set_option(L.OPT_GRAD_DEPTH_VISCOSITY, bool(_opt(eqo, "use_grad_depth_viscosity_term", True)))
         else:
             eng.set_option(L.OPT_LF_TRACER, bool(_opt(eqo, "use_lax_friedrichs_tracer", False)))
+            cons = False
+            tr = _opt(eqo, "tracer", None)
+            lab = self._tracer_label()
+            if tr and lab in tr:
+                cons = bool(getattr(tr[lab], "use_conservative_form", False))
+            self._conservative = cons
         self._push_dynamic(force=True)
 
     def _set_field(self, fid, value, key):
@@ -243,8 +280,10 @@ class ERKGenericShuOsher:
             return
         raise NotImplementedError(f"coefficient {key!r}: UFL expressions must be interpolated into a P1 Function first")
 
-    def _push_dynamic(self, force=False):
-        """Everything `update_forcings` may have changed: Constants are re-read, Functions re-uploaded if touched."""
+    def _push_dynamic(self, force=False, functions=True):
+        """Everything `update_forcings` may have changed: Constants are re-read, Functions re-uploaded if touched.
+        ``functions=False`` leaves Function-valued `fields` entries at their last uploaded values (the lagged
+        `fields_old` of timeintegrator.ForwardEuler); boundary data are always live."""
         eng = self.engine
         if self._kind == "swe":
             gc = getattr(self.equation, "physical_constants", None)
@@ -260,21 +299,37 @@ class ERKGenericShuOsher:
             eng.set_option(L.OPT_NORM_SMOOTHER, float(constant_value(_opt(eqo, "norm_smoother", 0.0))[0]))
             lf = self.fields.get("lax_friedrichs_velocity_scaling_factor")
             eng.set_option(L.OPT_LF_SCALING, 1.0 if lf is None else float(constant_value(lf)[0]))
+            sf = _opt(eqo, "sipg_factor", None)
+            eng.set_option(L.OPT_SIPG_FACTOR, 1.0 if sf is None else float(constant_value(sf)[0]))
             for name, fid in _SWE_FIELDS.items():
-                self._set_field(fid, self.fields.get(name), name)
+                if functions or not is_function(self.fields.get(name)):
+                    self._set_field(fid, self.fields.get(name), name)
             self._push_bcs(0, _SWE_TAGS)
         else:
+            # several tracer integrators share one device context: equation-specific switches are re-sent every stage
+            # (cached by value in the engine, so only changes reach the library) and this integrator's own upload
+            # stamps are dropped whenever another tracer integrator configured the context in between
+            if getattr(eng, "_tracer_cfg_owner", None) is not self:
+                if getattr(eng, "_tracer_cfg_owner", None) is not None:
+                    for k in ("tracer_source", "diffusivity_h"):
+                        self._field_versions.pop(k, None)
+                    self._bc_versions = {}
+                eng._tracer_cfg_owner = self
+            eng.set_option(L.OPT_TRACER_CONSERVATIVE, self._conservative)
+            sf = _opt(self.equation.options, "sipg_factor_tracer", None)
+            eng.set_option(L.OPT_SIPG_FACTOR_TRACER, 1.0 if sf is None else float(constant_value(sf)[0]))
+            diff = self._tracer_field("diffusivity_h")
+            if functions or not is_function(diff):
+                self._set_field(L.F_DIFFUSIVITY, diff, "diffusivity_h")
             lf = self.fields.get("lax_friedrichs_tracer_scaling_factor")
             eng.set_option(L.OPT_LF_TRACER_SCALING, 1.0 if lf is None else float(constant_value(lf)[0]))
             cf = self.fields.get("tracer_advective_velocity_factor")
             if cf is not None and not is_constant(cf):
                 raise NotImplementedError("spatially varying tracer_advective_velocity_factor is outside the accelerated path")
             eng.set_option(L.OPT_TRACER_VEL_FACTOR, 1.0 if cf is None else float(constant_value(cf)[0]))
-            src = None
-            for k, v in self.fields.items():
-                if k.startswith("source") and v is not None:
-                    src = v
-            self._set_field(L.F_TRACER_SOURCE, src, "tracer_source")
+            src = self._tracer_field("source")
+            if functions or not is_function(src):
+                self._set_field(L.F_TRACER_SOURCE, src, "tracer_source")
             self._push_bcs(1, _TRACER_TAGS)
 
     def _push_bcs(self, eq, tags):
@@ -283,7 +338,7 @@ class ERKGenericShuOsher:
             if funcs is None:
                 continue
             op = 0
-            consts = np.zeros(6)
+            consts = np.zeros(8)
             arrays = []
             for tag, val in funcs.items():
                 if tag not in tags:
@@ -481,7 +536,132 @@ class SSPRK33(ERKGenericShuOsher):
 
 
 class ForwardEuler(ERKGenericShuOsher):
-    """Forward Euler through the same stage kernel."""
+    """
+    `thetis.timeintegrator.ForwardEuler` (timeintegrator.py:115-165) through the same stage kernel.  The reference
+    calls ``update_forcings(t + dt)`` and assembles with `fields_old`: Function-valued coefficients are the ones of
+    the end of the previous step (`update_fields_old`, :163-165), Constants and boundary data are live.
+    """
+    a = [[0]]
+    b = [1.0]
+    c = [0]
+    cfl_coeff = 1.0
+
+    def initialize(self, solution):
+        super().initialize(solution)
+        self._push_dynamic()                         # update_fields_old (timeintegrator.py:152-153)
+
+    def solve_stage(self, i_stage, t, update_forcings=None):
+        if update_forcings is not None:
+            update_forcings(t + self.dt)             # timeintegrator.py:158-159
+        if not self._host_stale and self._host_changed():
+            self.upload()
+        self._push_dynamic(functions=False)          # fields_old: Functions lag one step
+        self._launch_stage(0)
+        self._push_dynamic()                         # update_fields_old (:165)
+
+
+class ERKGeneric(ERKGenericShuOsher):
+    """
+    Generic explicit Runge-Kutta integrator in Butcher form, `thetis.rungekutta.ERKGeneric`
+    (rungekutta.py:762-867): stage i evaluates  k_i = dt M^-1 R(u_old + sum_j a_ij k_j)  with the forcings at
+    t + c_i dt; the step ends with  u = u_old + sum_j b_j k_j  (get_final_solution).  Each tendency is one launch of
+    the fused stage kernel (a0 = a1 = 0); the stage combinations are one streaming `tb_lincomb` launch each and the
+    last tendency is fused with the final combination.
+    Buffers: buf[0] = solution (u_old between steps), buf[1] = stage solution / scratch, buf[2+i] = k_i.
+    """
+    butcher_form = True
+
+    def initialize(self, solution):
+        """rungekutta.py:811-814"""
+        super().initialize(solution)
+        self._initialized = True
+
+    def _stage_input(self, i_stage):
+        """update_solution (rungekutta.py:816-828): u_old + sum_{j<i} a_ij k_j"""
+        U, S = self.buf[0], self.buf[1]
+        terms = [(1.0, U)] + [(float(self.a[i_stage][j]), self.buf[2 + j]) for j in range(i_stage)
+                               if self.a[i_stage][j] != 0.0]
+        if len(terms) == 1:
+            return U
+        self.engine.lincomb(terms, S)
+        return S
+
+    def _launch_tendency(self, src, a0, u0, bdt, dst):
+        eng = self.engine
+        if self._kind == "swe":
+            if self.halo is not None:
+                self.halo.swe_stage(a0, 0.0, bdt, src, u0, dst)
+            else:
+                eng.swe_stage(a0, 0.0, bdt, src, u0, dst)
+        else:
+            eng.tracer_stage(a0, 0.0, bdt, src, u0, dst, self._swe_state_for_tracer())
+            if self.halo is not None:
+                self.halo.exchange(dst)
+
+    def _launch_stage(self, i_stage):
+        last = i_stage == self.n_stages - 1
+        src = self._stage_input(i_stage)
+        if not last:
+            self._launch_tendency(src, 0.0, None, self.dt, self.buf[2 + i_stage])
+            return
+        # get_final_solution (rungekutta.py:841-852) fused with the last tendency:
+        #   u = [u_old + sum_{j<s-1} b_j k_j] + b_{s-1} dt M^-1 R(u_{s-1})
+        U = self.buf[0]
+        terms = [(1.0, U)] + [(float(self.b[j]), self.buf[2 + j]) for j in range(i_stage) if self.b[j] != 0.0]
+        K = self.buf[2 + i_stage]
+        if len(terms) > 1:
+            self.engine.lincomb(terms, K)            # K is free until this stage's tendency is written
+            base = K
+        else:
+            base = U
+        if float(self.b[i_stage]) == 0.0:
+            if base is not U:
+                self.engine.lincomb([(1.0, base)], U)
+        else:
+            # the stage kernel reads u0 patch by patch before writing the same patch of u_out: u0 may alias u_out,
+            # but u_in (src) must not -> write to a buffer that is neither
+            dst = U if src is not U else self.buf[1]
+            self._launch_tendency(src, 1.0, base, float(self.b[i_stage]) * self.dt, dst)
+            if dst is not U:
+                self.buf[0], self.buf[1] = self.buf[1], self.buf[0]
+        self._host_stale = True
+
+    def solve_stage(self, i_stage, t, update_forcings=None):
+        """rungekutta.py:855-867: stage solution first, then the forcings at t + c_i dt, then the tendency."""
+        if i_stage == 0 and not self._host_stale and self._host_changed():
+            self.upload()
+        if update_forcings is not None:
+            update_forcings(t + self.c[i_stage] * self.dt)
+        self._push_dynamic()
+        self._launch_stage(i_stage)
+
+
+class ERKLSPUM2(ERKGeneric):
+    """3-stage 2nd-order ERK of Higueras et al. (2014), tableau of rungekutta.py:360-365."""
+    a = [[0, 0, 0], [5.0 / 6.0, 0, 0], [11.0 / 24.0, 11.0 / 24.0, 0]]
+    b = [24.0 / 55.0, 1.0 / 5.0, 4.0 / 11.0]
+    c = [0, 5.0 / 6.0, 11.0 / 12.0]
+    cfl_coeff = 1.2
+
+
+class ERKLPUM2(ERKGeneric):
+    """3-stage 2nd-order ERK of Higueras et al. (2014), tableau of rungekutta.py:379-384."""
+    a = [[0, 0, 0], [0.5, 0, 0], [0.5, 0.5, 0]]
+    b = [1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0]
+    c = [0, 0.5, 1.0]
+    cfl_coeff = 2.0
+
+
+class ERKMidpoint(ERKGeneric):
+    """Explicit midpoint rule, tableau of rungekutta.py:388-392."""
+    a = [[0.0, 0.0], [0.5, 0.0]]
+    b = [0.0, 1.0]
+    c = [0.0, 0.5]
+    cfl_coeff = 1.0
+
+
+class ERKEuler(ERKGeneric):
+    """Forward Euler in Butcher form (rungekutta.py:979, ForwardEulerAbstract :142-149)."""
     a = [[0]]
     b = [1.0]
     c = [0]

@@ -254,7 +254,11 @@ class FlowSolver2d:
         if self.equations is None:
             self.create_equations()
         self.set_time_step()
-        steppers = {"SSPRK33": rungekutta.SSPRK33, "ForwardEuler": rungekutta.ForwardEuler}
+        # solver2d.py:662-672 knows 'SSPRK33' and 'ForwardEuler' among the explicit schemes; the Butcher-form ERK
+        # classes of rungekutta.py:959-980 are accepted by name as well
+        steppers = {"SSPRK33": rungekutta.SSPRK33, "ForwardEuler": rungekutta.ForwardEuler,
+                    "ERKLSPUM2": rungekutta.ERKLSPUM2, "ERKLPUM2": rungekutta.ERKLPUM2,
+                    "ERKMidpoint": rungekutta.ERKMidpoint, "ERKEuler": rungekutta.ERKEuler}
         for t in (self.options.swe_timestepper_type, self.options.tracer_timestepper_type):
             if t not in steppers:
                 raise NotImplementedError(f"time integrator {t!r} is outside the accelerated path "
@@ -277,6 +281,8 @@ class FlowSolver2d:
             self.create_equations()
         if self.timestepper is None:
             self.create_timestepper()
+        if not getattr(self, "_exporters_created", False):
+            self.create_exporters()
         self._initialized = True
 
     @staticmethod
@@ -315,6 +321,36 @@ class FlowSolver2d:
     def add_callback(self, callback, eval_interval="export"):
         self.callbacks[eval_interval].append(callback)
 
+    def create_exporters(self):
+        """solver2d.py:1040-1075 (diagnostic callbacks only; file exporters are outside the accelerated path)"""
+        from . import callback
+        o = self.options
+        if o.check_volume_conservation_2d:
+            self.add_callback(callback.VolumeConservation2DCallback(self, append_to_log=True))
+        if o.check_tracer_conservation:
+            for label, tracer in o.tracer.items():
+                cls = (callback.ConservativeTracerMassConservation2DCallback if tracer.use_conservative_form
+                       else callback.TracerMassConservation2DCallback)
+                self.add_callback(cls(label, self, append_to_log=True), eval_interval="export")
+        if o.check_tracer_overshoot:
+            for label in o.tracer:
+                self.add_callback(callback.TracerOvershootCallBack(label, self, append_to_log=True),
+                                  eval_interval="export")
+        self._exporters_created = True
+
+    def _run_callbacks(self, mode):
+        from .callback import DiagnosticCallback
+        host_needed = any(not isinstance(cb, DiagnosticCallback) for cb in self.callbacks[mode])
+        if host_needed:
+            self.sync_to_host()               # user callbacks read host Functions; the device diagnostics do not
+        for cb in self.callbacks[mode]:
+            if isinstance(cb, DiagnosticCallback):
+                cb.evaluate(index=self.i_export)
+            elif hasattr(cb, "evaluate"):
+                cb.evaluate(self)
+            else:
+                cb(self)
+
     # ------------------------------------------------------------ host visibility
     def sync_to_host(self):
         self.timestepper.sync_to_host()
@@ -346,8 +382,7 @@ class FlowSolver2d:
     def export(self, time=None):
         """Fields become host-visible here; VTK/HDF5 writers are outside the accelerated path (exporter.py)."""
         self.sync_to_host()
-        for cb in self.callbacks["export"]:
-            cb.evaluate(self) if hasattr(cb, "evaluate") else cb(self)
+        self._run_callbacks("export")
 
     # ------------------------------------------------------------ time loop (solver2d.py:974-1144)
     def iterate(self, update_forcings=None, export_func=None):
@@ -376,9 +411,7 @@ class FlowSolver2d:
             internal_iteration += 1
             self.simulation_time = initial_simulation_time + internal_iteration * self.dt
             if self.callbacks["timestep"]:
-                self.sync_to_host()
-                for cb in self.callbacks["timestep"]:
-                    cb.evaluate(self) if hasattr(cb, "evaluate") else cb(self)
+                self._run_callbacks("timestep")
             if self.simulation_time >= next_export_t - t_epsilon:
                 self.i_export += 1
                 next_export_t += self.options.simulation_export_time
