@@ -69,7 +69,18 @@ def _run(mesh, bath_v, swe_opts, tr_opts, tr_fields_v, bnd, tol=1e-12, seed=0, c
     gk = eng.download_tracer(k)
     err = np.abs(gk - kc).max() / np.abs(kc).max()
     assert err < tol, err
+    # the specialised (plain advection) kernel and the generic one must agree to rounding
+    eng.set_option(L.OPT_FORCE_GENERIC_KERNEL, 1)
+    k2 = eng.new_tracer()
+    eng.tracer_stage(0.0, 0.0, 1.0, cd, None, k2, st)
+    assert np.abs(eng.download_tracer(k2) - gk).max() <= 1e-13 * np.abs(gk).max()
     return err
+
+
+def test_plain_advection_specialised_kernel():
+    """BASELINE config 4 physics (non-conservative advection only): TSPEC 1 kernel, multi-patch unstructured mesh"""
+    mesh = sfc_renumber(delaunay_mesh(2500, 1.0, 1.0, seed=9))
+    _run(mesh, 1.0, {}, {}, {}, {1: {"value": 0.5}}, tol=1e-12)
 
 
 def test_diffusion_constant_closed():

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("THETIS_B200_LIB", os.path.join(_HERE, "libthetis_b200.so"))   # override: developer A/B builds
+LIB_PATH = os.environ.get("THETIS_B200_LIB") or os.path.join(_HERE, "libthetis_b200.so")   # override: developer A/B builds
 
 TB_OK = 0
 # tb_option

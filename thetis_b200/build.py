@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libthetis_b200.so")
 SOURCES = ["tb_kernels.cu", "tb_tracer.cu", "tb_api.cu"]
-HEADERS = [os.path.join(CSRC, "tb_internal.h"),
+HEADERS = [os.path.join(CSRC, "tb_internal.h"), os.path.join(CSRC, "tb_device.cuh"),
            os.path.join(HERE, "..", "include", "thetis_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -34,13 +34,16 @@ def build_library(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    # developer A/B builds: TB_EXTRA_NVCC="-DTB_T_MINB=5" THETIS_B200_LIB=/path/variant.so python -m thetis_b200.build --force
+    extra = os.environ.get("TB_EXTRA_NVCC", "").split()
+    out = os.environ.get("THETIS_B200_LIB") or LIB
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libthetis_b200.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

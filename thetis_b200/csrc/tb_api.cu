@@ -753,6 +753,7 @@ extern "C" int tb_tracer_stage(tb_ctx *ctx, double a0, double a1, double b_dt, c
     p.sipg = ctx->sipg_tracer;
     p.conservative = ctx->tracer_conservative;
     p.nquad = ctx->nquad;
+    p.force_generic = ctx->force_generic;
     fill_bc(ctx, 1, p.bc);
     long long first, count;
     patch_range(ctx, first, count);

@@ -1,0 +1,98 @@
+// Device-side helpers shared by the stage kernels (tb_kernels.cu, tb_tracer.cu): TMA bulk copies + mbarrier,
+// cp.async, L2 prefetch and the branch-free fp64 reciprocal / root helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// 2-point Gauss-Legendre on [0,1]
+#define TB_XI1 0.21132486540518711775
+#define TB_XI2 0.78867513459481288225
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// TMA 1-D bulk copy shared -> global
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------ fp64 math helpers
+// MUFU / fp32 seed (>= 21 good bits) + ONE third-order (Halley-type) correction: with e = 1 - x*y0^k,
+//   x^(-1/2) = y0 (1 + e/2 + 3e^2/8 + O(e^3)),  x^(-1) = y0 (1 + e + e^2 + O(e^3)),  x^(-1/3) = y0 (1 + e/3 + 2e^2/9 + O(e^3));
+// the dropped e^3 term is < 2^-60, so results are good to ~1 ulp (tests/test_gpu_math.py), branch-free, all FMAs.
+// The CUDA library sqrt / division / rcbrt carry slow-path subroutine calls that cost more fp64-pipe and issue
+// slots than the whole facet flux.  Arguments here are depths, lengths and areas (normal, positive).
+__device__ __forceinline__ double tb_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+__device__ __forceinline__ double tb_sqrt(double x) {   // x > 0
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double g = x * y;
+    const double e = fma(-g, y, 1.0);
+    return fma(g * e, fma(0.375, e, 0.5), g);
+}
+__device__ __forceinline__ double tb_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+}
+__device__ __forceinline__ double tb_rcbrt(double x) {   // x^(-1/3), x > 0 within float range
+    const double y = (double)rcbrtf((float)x);
+    const double e = fma(-(x * y), y * y, 1.0);
+    return fma(y * e, fma(2.0 / 9.0, e, 1.0 / 3.0), y);
+}
+
+__device__ __forceinline__ void cp_async8(void *sdst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+

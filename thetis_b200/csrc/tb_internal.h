@@ -89,6 +89,7 @@ struct TbTracerParams {
     TbCoef src, diff;
     double sipg;                  // sipg_factor_tracer
     int conservative, nquad;
+    int force_generic, pad1;
     TbBcTable bc;
 };
 

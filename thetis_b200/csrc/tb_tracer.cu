@@ -2,10 +2,15 @@
 // VertexBasedP1DGLimiter (limiter.py:48-198) as sm_100a kernels.
 // Same patch / TMA staging scheme as the SWE stage kernel (tb_kernels.cu).
 #include "tb_internal.h"
+#include "tb_device.cuh"
 
-#define TB_XI1 0.21132486540518711775
-#define TB_XI2 0.78867513459481288225
 #define TB_BC_PRESENT 32   // marker has a (possibly empty) dict in bnd_conditions
+#ifndef TB_T_HALO_SPEC
+#define TB_T_HALO_SPEC 4      // halo elements (9 per halo cell) per thread fetched speculatively (covers NH <= 56)
+#endif
+#ifndef TB_T_MINB
+#define TB_T_MINB 5           // resident CTAs per SM the tracer stage kernel is compiled for (96 registers)
+#endif
 
 // degree-3 cell rule for the non-polynomial integrand of ConservativeSourceTerm (H*source with wetting-drying)
 __constant__ double ct_qlam[TB_MAX_QUAD][3];
@@ -16,43 +21,11 @@ cudaError_t tb_set_quadrature_tracer(int n, const double *lam, const double *w) 
     return cudaMemcpyToSymbol(ct_qw, w, sizeof(double) * n);
 }
 
-__device__ __forceinline__ uint32_t t_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void t_mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(t_smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void t_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t_smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void t_mbar_wait(uint64_t *bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(t_smem_u32(bar)),
-        "r"(phase)
-        : "memory");
-}
-__device__ __forceinline__ void t_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     t_smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(t_smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void t_bulk_s2g(void *dst, const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(t_smem_u32(src)),
-                 "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constant__ TbTracerParams prm) {
+// TSPEC 1: plain non-conservative advection (no source, diffusion or Lax-Friedrichs) -- BASELINE config 4;
+// TSPEC 0: every optional term behind a runtime flag.  Same staging as the SWE stage kernel: TMA bulk copies of the
+// patch's SWE records, tracer records, u0 and static block; halo records gathered with cp.async by all threads.
+template <int TSPEC>
+__global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __grid_constant__ TbTracerParams prm) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     double *S = reinterpret_cast<double *>(smem + 16);            // SWE records [(TB_P+NH)][9]
@@ -65,29 +38,55 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
     const long long cell0 = (long long)patch * TB_P;
     const int NV = prm.pl.NV;
 
-    if (tid == 0) t_mbar_init(bar, 1);
-    __syncthreads();
+    // speculative, mutually independent loads first: the halo count and the ids this thread will need (rows of
+    // halo_ids are padded to NH valid entries).  Element i of the halo is double (i % 9) of halo cell (i / 9):
+    // the 6 velocity values of its SWE record, then its 3 tracer values (the neighbour's elevation is never used).
+    const int *hid = prm.pl.halo_ids + (long long)patch * prm.pl.NH;
+    const int NH9 = prm.pl.NH * 9;
+    int hcell[TB_T_HALO_SPEC];
+#pragma unroll
+    for (int j = 0; j < TB_T_HALO_SPEC; ++j) {
+        const int i = j * TB_P + tid;
+        hcell[j] = (i < NH9) ? __ldg(hid + i / 9) : 0;
+    }
+    const int nh9 = __ldg(prm.pl.halo_cnt + patch) * 9;
     if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
         const uint32_t sb = (uint32_t)prm.pl.stride;
         const uint32_t rec9 = TB_P * 9 * sizeof(double), rec3 = TB_P * 3 * sizeof(double);
-        t_mbar_expect_tx(bar, rec9 + rec3 + sb + (prm.c0 ? rec3 : 0u));
-        t_bulk_g2s(S, prm.swe + cell0 * 9, rec9, bar);
-        t_bulk_g2s(C, prm.c_in + cell0 * 3, rec3, bar);
-        t_bulk_g2s(blk, prm.pl.sblk + (long long)patch * prm.pl.stride, sb, bar);
-        if (prm.c0) t_bulk_g2s(O, prm.c0 + cell0 * 3, rec3, bar);
-    }
-    {
-        const int nh = __ldg(prm.pl.halo_cnt + patch);
-        const int *hid = prm.pl.halo_ids + (long long)patch * prm.pl.NH;
-        for (int i = tid; i < nh * 12; i += TB_P) {
-            const int h = i / 12, k = i - h * 12;
-            const long long gc = __ldg(hid + h);
-            if (k < 9) S[(TB_P + h) * 9 + k] = __ldg(prm.swe + gc * 9 + k);
-            else C[(TB_P + h) * 3 + (k - 9)] = __ldg(prm.c_in + gc * 3 + (k - 9));
+        mbar_expect_tx(bar, rec9 + rec3 + sb + (prm.c0 ? rec3 : 0u));
+        bulk_g2s(S, prm.swe + cell0 * 9, rec9, bar);
+        bulk_g2s(C, prm.c_in + cell0 * 3, rec3, bar);
+        bulk_g2s(blk, prm.pl.sblk + (long long)patch * prm.pl.stride, sb, bar);
+        if (prm.c0) bulk_g2s(O, prm.c0 + cell0 * 3, rec3, bar);
+    } else if (tid == 32) {
+        // warm L2 for the patch that runs on this SM slot one wave later
+        const int pb = (int)blockIdx.x + 148 * TB_T_MINB;
+        if (pb < (int)gridDim.x) {
+            const long long pf = prm.patch_first + pb;
+            bulk_prefetch_l2(prm.swe + pf * TB_P * 9, TB_P * 9 * sizeof(double));
+            bulk_prefetch_l2(prm.c_in + pf * TB_P * 3, TB_P * 3 * sizeof(double));
+            bulk_prefetch_l2(prm.pl.sblk + pf * prm.pl.stride, (uint32_t)prm.pl.stride);
+            if (prm.c0) bulk_prefetch_l2(prm.c0 + pf * TB_P * 3, TB_P * 3 * sizeof(double));
         }
     }
-    t_mbar_wait(bar, 0);
-    __syncthreads();
+    {
+        auto halo_copy = [&](int i, long long gc) {
+            const int h = i / 9, k = i - h * 9;
+            if (k < 6) cp_async8(S + (TB_P + h) * 9 + k, prm.swe + gc * 9 + k);
+            else cp_async8(C + (TB_P + h) * 3 + (k - 6), prm.c_in + gc * 3 + (k - 6));
+        };
+#pragma unroll
+        for (int j = 0; j < TB_T_HALO_SPEC; ++j) {
+            const int i = j * TB_P + tid;
+            if (i < nh9) halo_copy(i, hcell[j]);
+        }
+        for (int i = TB_T_HALO_SPEC * TB_P + tid; i < nh9; i += TB_P) halo_copy(i, __ldg(hid + i / 9));   // large halos
+        cp_async_wait_all();
+    }
+    __syncthreads();          // mbarrier initialised before anybody waits on it; halo copies landed
+    mbar_wait(bar, 0);
 
     const bool active = (cell0 + tid) < prm.n_owned;
     double res[3] = {0, 0, 0};
@@ -120,8 +119,10 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
         const double twoA = (x[1] - x[0]) * (y[2] - y[0]) - (y[1] - y[0]) * (x[2] - x[0]);
         double R[3] = {0, 0, 0};
         const double sc = c[0] + c[1] + c[2];
-        const bool cons = prm.conservative != 0;     // unknown = depth-integrated tracer (tracer_eq_2d.py:323-437)
-        const bool has_diff = prm.diff.mode != 0;
+        const bool cons = TSPEC == 1 ? false : prm.conservative != 0;   // depth-integrated unknown (tracer_eq_2d.py:323-437)
+        const bool has_diff = TSPEC == 1 ? false : prm.diff.mode != 0;
+        const bool has_src = TSPEC == 1 ? false : prm.src.mode != 0;
+        const bool lf_on = TSPEC == 1 ? false : prm.lf_on != 0;
         {
             // cell part (:159-160): + c div(u phi_a); conservative form (:356-357): + c u.grad(phi_a)
             double D = 0;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
                 R[a] += s * (1.0 / 12.0);
             }
         }
-        if (prm.src.mode) {
+        if (has_src) {
             // SourceTerm (:293-298)
             double f[3];
 #pragma unroll
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
         }
         // HorizontalDiffusionTerm (tracer_eq_2d.py:226-278), symmetric interior penalty
         double muv[3] = {0, 0, 0}, gcx = 0, gcy = 0;
-        const double itA = 1.0 / twoA;
+        const double itA = tb_rcp(twoA);
         if (has_diff) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
                         const double fK = cK * (uKx * nxs + uKy * nys), fN = cN * (uNx * nxs + uNy * nys);
                         f = unav > 0.0 ? fK : (unav < 0.0 ? fN : 0.5 * (fK + fN));
                     }
-                    if (prm.lf_on) f += 0.5 * fabs(unav) * prm.lf_sigma * (cK - cN);     // (:173-175, 372-380)
+                    if (lf_on) f += 0.5 * fabs(unav) * prm.lf_sigma * (cK - cN);         // (:173-175, 372-380)
                     if (has_diff) {
                         const double mug = wp_ * muv[p] + wq_ * muv[q];                    // mu is continuous (P1)
                         f += mug * (sigl * (cK - cN) - 0.5 * T);
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
                 const int op = bs.opcode;
                 const int row = bs.arr_mask ? __ldg(prm.bc.bf_row + gb) : 0;
                 const double len2 = nxs * nxs + nys * nys;
-                const double il = rsqrt(len2);
+                const double il = tb_rsqrt(len2);
 #pragma unroll
                 for (int gp = 0; gp < 2; ++gp) {
                     const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
             R[p] -= 0.5 * Fp;
             R[q] -= 0.5 * Fq;
         }
-        const double mi = 6.0 / twoA * prm.bdt;
+        const double mi = 6.0 * itA * prm.bdt;
         const double sR = R[0] + R[1] + R[2];
 #pragma unroll
         for (int a = 0; a < 3; ++a) res[a] = prm.a1 * c[a] + mi * (4.0 * R[a] - sR);
@@ -340,9 +341,12 @@ __global__ void __launch_bounds__(TB_P) tracer_stage_kernel(const __grid_constan
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) O[tid * 3 + a] = res[a];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_proxy_async();
     __syncthreads();
-    if (tid == 0) t_bulk_s2g(prm.c_out + cell0 * 3, O, TB_P * 3 * sizeof(double));
+    if (tid == 0) {
+        bulk_s2g(prm.c_out + cell0 * 3, O, TB_P * 3 * sizeof(double));
+        bulk_commit_wait_read();
+    }
 }
 
 size_t tb_tracer_smem_bytes(const TbPatchLayout &pl) {
@@ -353,12 +357,16 @@ cudaError_t tb_launch_tracer_stage(const TbTracerParams &p, int n_patches, size_
     static bool init = false;
     if (!init) {
         cudaError_t e =
-            cudaFuncSetAttribute(tracer_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(tracer_stage_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tracer_stage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         init = true;
     }
     if (n_patches <= 0) return cudaSuccess;
-    tracer_stage_kernel<<<n_patches, TB_P, smem, s>>>(p);
+    const bool plain = !p.conservative && !p.diff.mode && !p.src.mode && !p.lf_on && !p.force_generic;
+    if (plain) tracer_stage_kernel<1><<<n_patches, TB_P, smem, s>>>(p);
+    else tracer_stage_kernel<0><<<n_patches, TB_P, smem, s>>>(p);
     return cudaGetLastError();
 }
 
