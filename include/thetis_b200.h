@@ -183,7 +183,7 @@ int tb_swe_integrals(tb_ctx *ctx, const double *state, double *out, void *stream
  * (TracerOvershootCallBack).  `out`: DEVICE pointer to 4 doubles.  tb_swe_integrals' out[3] is
  * int (eta + bathymetry) dx (VolumeConservation2DCallback / comp_volume_2d). */
 int tb_tracer_integrals(tb_ctx *ctx, const double *c, const double *swe_state, double *out, void *stream);
-/* out = sum_j w[j]*x[j], j < n <= 6, over `len` doubles (len even): the stage combinations of the Butcher-form
+/* out = sum_j w[j]*x[j], j < n <= 6, over `len` doubles (16-byte aligned operands): the stage combinations of the Butcher-form
  * integrators (ERKGeneric.update_solution / get_final_solution, rungekutta.py:816-852).  x: HOST array of n
  * DEVICE pointers, w: HOST weights.  out may alias any x[j]. */
 int tb_lincomb(tb_ctx *ctx, int n, const double *const *x, const double *w, double *out, int64_t len, void *stream);

@@ -150,3 +150,90 @@ def test_coupled_tracer_limiter_distributed_is_bit_identical():
         cells, uv, e, c, norms = out[r]
         assert np.array_equal(uv, uv1[cells]) and np.array_equal(e, e1[cells]) and np.array_equal(c, c1[cells])
         assert abs(norms[0] - s.last_norms[0]) <= 1e-12 * s.last_norms[0]      # all-reduced print_state norms
+
+
+# ---------------------------------------------------------------- SURVEY 8f rows on a distributed mesh
+def _sipg_mesh():
+    from thetis_b200.mesh import delaunay_mesh, sfc_renumber
+    return sfc_renumber(delaunay_mesh(1500, 18e3, 8e3, seed=11))
+
+
+def _sipg_solver(mesh_obj):
+    """viscosity + tracer diffusion + Butcher-form ERK + device callbacks: same set-up on 1 GPU and distributed"""
+    from thetis_b200 import solver2d
+    from thetis_b200.shim import Function, FunctionSpace, Constant, as_shim_mesh, ShimMesh
+    sm = mesh_obj if isinstance(mesh_obj, ShimMesh) else as_shim_mesh(mesh_obj)
+    lx = 18e3
+    P1 = FunctionSpace(sm, "CG", 1)
+    b = Function(P1).interpolate(lambda x, y: 10.0 + 2.0 * np.cos(2 * np.pi * x / lx))
+    s = solver2d.FlowSolver2d(sm, b)
+    o = s.options
+    o.swe_timestepper_type = "ERKLSPUM2"
+    o.tracer_timestepper_type = "ERKLSPUM2"
+    o.swe_timestepper_options.use_automatic_timestep = False
+    o.tracer_timestepper_options.use_automatic_timestep = False
+    o.timestep = 1.0
+    o.simulation_end_time = 1.0 * 24
+    o.simulation_export_time = 1.0 * 8
+    o.horizontal_viscosity = Function(P1).interpolate(lambda x, y: 20.0 * (1.0 + 0.3 * np.sin(y / 2e3)))
+    o.use_grad_div_viscosity_term = True
+    o.check_volume_conservation_2d = True
+    o.check_tracer_conservation = True
+    o.check_tracer_overshoot = True
+    o.add_tracer_2d("tracer_2d", "Depth averaged tracer", "Tracer2d", diffusivity=Constant(12.0))
+    o.use_limiter_for_tracers = True
+    s.bnd_functions["shallow_water"] = {1: {"elev": Constant(0.2), "uv": Constant((0.05, 0.0))}}
+    s.bnd_functions["tracer"] = {1: {"value": Constant(4.0)}}
+    s.assign_initial_conditions(elev=lambda x, y: 0.5 * np.cos(np.pi * x / lx),
+                                tracer=lambda x, y: 4.5 + 2.0 * np.exp(-((x - lx / 2) ** 2 + (y - 4e3) ** 2) / 2e3 ** 2))
+    return s
+
+
+def _worker_sipg(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from thetis_b200.parallel import distribute_mesh
+        sm = distribute_mesh(_sipg_mesh(), rank, world, halo="vertex")
+        lm = sm.topology_mesh
+        s = _sipg_solver(sm)
+        s.iterate()
+        n = sm.halo_plan.part.n_owned
+        hist = {cb.name: [v for _, v in cb.history] for cb in s.callbacks["export"]}
+        out[rank] = (lm.meta["global_cells"][:n].copy(),
+                     s.fields.uv_2d.dat.data_ro.reshape(-1, 3, 2)[:n].copy(),
+                     s.fields.elev_2d.dat.data_ro.reshape(-1, 3)[:n].copy(),
+                     s.fields.tracer_2d.dat.data_ro.reshape(-1, 3)[:n].copy(), hist)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sipg_erk_callbacks_distributed_is_bit_identical():
+    """viscosity (neighbour gradients from ghost cells), tracer diffusion, ERKLSPUM2 (tb_lincomb over owned + ghost
+    records) and the all-reduced device callbacks on 2 GPUs == the 1-GPU run"""
+    import torch
+    import torch.multiprocessing as mp
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_sipg, args=(world, _free_port(), out), nprocs=world, join=True)
+    s = _sipg_solver(_sipg_mesh())
+    s.iterate()
+    uv1 = s.fields.uv_2d.dat.data_ro.reshape(-1, 3, 2)
+    e1 = s.fields.elev_2d.dat.data_ro.reshape(-1, 3)
+    c1 = s.fields.tracer_2d.dat.data_ro.reshape(-1, 3)
+    assert np.isfinite(uv1).all() and np.abs(uv1).max() > 1e-3
+    hist1 = {cb.name: [v for _, v in cb.history] for cb in s.callbacks["export"]}
+    for r in range(world):
+        cells, uv, e, c, hist = out[r]
+        assert np.array_equal(uv, uv1[cells]) and np.array_equal(e, e1[cells]) and np.array_equal(c, c1[cells])
+        for name in ("volume2d", "tracer_2d mass"):
+            for (v, _), (v1, _) in zip(hist[name], hist1[name]):
+                assert abs(v - v1) <= 1e-12 * abs(v1)
+        assert hist["tracer_2d overshoot"][-1][:2] == hist1["tracer_2d overshoot"][-1][:2]     # min / max are exact

@@ -894,10 +894,11 @@ extern "C" int tb_tracer_integrals(tb_ctx *ctx, const double *c, const double *s
 }
 extern "C" int tb_lincomb(tb_ctx *ctx, int n, const double *const *x, const double *w, double *out, int64_t len,
                           void *stream) {
-    if (!ctx || !x || !w || !out || n < 1 || n > 6 || len < 0 || (len & 1))
+    if (!ctx || !x || !w || !out || n < 1 || n > 6 || len < 0)
         return fail(ctx, TB_ERR_ARG, "bad linear-combination arguments");
+    if (reinterpret_cast<uintptr_t>(out) & 15) return fail(ctx, TB_ERR_ARG, "operands must be 16-byte aligned");
     for (int j = 0; j < n; ++j)
-        if (!x[j]) return fail(ctx, TB_ERR_ARG, "null operand");
+        if (!x[j] || (reinterpret_cast<uintptr_t>(x[j]) & 15)) return fail(ctx, TB_ERR_ARG, "null or misaligned operand");
     CK(tb_launch_lincomb(n, x, w, out, len, (cudaStream_t)stream));
     ctx->launches += len > 0;
     return TB_OK;

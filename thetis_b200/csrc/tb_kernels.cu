@@ -898,8 +898,13 @@ struct TbLincomb {
     double w[6];
     int n;
 };
-__global__ void lincomb_kernel(TbLincomb p, double *__restrict__ out, long long len2) {
-    // two doubles per thread per iteration (16-byte accesses; state arrays are multiples of 2 doubles)
+__global__ void lincomb_kernel(TbLincomb p, double *__restrict__ out, long long len2, int tail) {
+    // two doubles per thread per iteration (16-byte accesses); an odd last element is handled by one thread
+    if (tail && blockIdx.x == 0 && threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int j = 0; j < p.n; ++j) acc = fma(p.w[j], p.x[j][2 * len2], acc);
+        out[2 * len2] = acc;
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len2; i += (long long)gridDim.x * blockDim.x) {
         double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
@@ -922,8 +927,8 @@ cudaError_t tb_launch_lincomb(int n, const double *const *x, const double *w, do
         p.w[j] = j < n ? w[j] : 0.0;
     }
     const long long len2 = len / 2;
-    const unsigned grid = (unsigned)std::min<long long>((len2 + 255) / 256, 148 * 16);
-    lincomb_kernel<<<grid, 256, 0, s>>>(p, out, len2);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((len2 + 255) / 256, 148 * 16));
+    lincomb_kernel<<<grid, 256, 0, s>>>(p, out, len2, (int)(len & 1));
     return cudaGetLastError();
 }
 

@@ -170,12 +170,14 @@ class Engine:
         """out (device, 4 doubles): int c, int H c, min c, max c"""
         self._ck(self.lib.tb_tracer_integrals(self.ctx, _ptr(c), _ptr(swe_state), _ptr(out), self.stream))
 
-    def lincomb(self, terms, out):
-        """out = sum w*x over ``terms`` = [(w, tensor), ...] (at most 6); out may alias an operand."""
+    def lincomb(self, terms, out, length=None):
+        """out = sum w*x over ``terms`` = [(w, tensor), ...] (at most 6) for the first ``length`` doubles (default:
+        all of ``out``); out may alias an operand."""
         n = len(terms)
         ptrs = (C.c_void_p * n)(*[t.data_ptr() for _, t in terms])
         ws = (C.c_double * n)(*[float(w) for w, _ in terms])
-        self._ck(self.lib.tb_lincomb(self.ctx, n, ptrs, ws, _ptr(out), int(out.numel()), self.stream))
+        ln = int(out.numel()) if length is None else int(length)
+        self._ck(self.lib.tb_lincomb(self.ctx, n, ptrs, ws, _ptr(out), ln, self.stream))
 
     def gather_cells(self, state, idx, rec_len, buf):
         self._ck(self.lib.tb_gather_cells(self.ctx, _ptr(state), _ptr(idx), int(idx.numel()), rec_len, _ptr(buf),

@@ -567,7 +567,8 @@ class ERKGeneric(ERKGenericShuOsher):
     t + c_i dt; the step ends with  u = u_old + sum_j b_j k_j  (get_final_solution).  Each tendency is one launch of
     the fused stage kernel (a0 = a1 = 0); the stage combinations are one streaming `tb_lincomb` launch each and the
     last tendency is fused with the final combination.
-    Buffers: buf[0] = solution (u_old between steps), buf[1] = stage solution / scratch, buf[2+i] = k_i.
+    Buffers: buf[0] = solution (u_old between steps), buf[1] = stage solution / scratch, buf[2+i] = k_i; the last
+    tendency buffer receives the new solution and swaps roles with buf[0] at the end of every step.
     """
     butcher_form = True
 
@@ -606,24 +607,26 @@ class ERKGeneric(ERKGenericShuOsher):
             return
         # get_final_solution (rungekutta.py:841-852) fused with the last tendency:
         #   u = [u_old + sum_{j<s-1} b_j k_j] + b_{s-1} dt M^-1 R(u_{s-1})
+        # The result goes into the last tendency buffer K (never into U): on a distributed mesh the peers push their
+        # new records into the ghost block of the output while this rank may still be reading the ghost block of U
+        # for its own stage input, so U must stay intact until the next exchange.  K and U then swap roles.
         U = self.buf[0]
-        terms = [(1.0, U)] + [(float(self.b[j]), self.buf[2 + j]) for j in range(i_stage) if self.b[j] != 0.0]
         K = self.buf[2 + i_stage]
-        if len(terms) > 1:
-            self.engine.lincomb(terms, K)            # K is free until this stage's tendency is written
-            base = K
-        else:
-            base = U
+        rec = 9 if self._kind == "swe" else 3
+        n_own = self.engine.n_owned_pad * rec         # the ghost block of K is written by the exchange only
+        terms = [(1.0, U)] + [(float(self.b[j]), self.buf[2 + j]) for j in range(i_stage) if self.b[j] != 0.0]
         if float(self.b[i_stage]) == 0.0:
-            if base is not U:
-                self.engine.lincomb([(1.0, base)], U)
+            self.engine.lincomb(terms, K, length=n_own)
+            if self.halo is not None:
+                self.halo.exchange(K)
         else:
-            # the stage kernel reads u0 patch by patch before writing the same patch of u_out: u0 may alias u_out,
-            # but u_in (src) must not -> write to a buffer that is neither
-            dst = U if src is not U else self.buf[1]
-            self._launch_tendency(src, 1.0, base, float(self.b[i_stage]) * self.dt, dst)
-            if dst is not U:
-                self.buf[0], self.buf[1] = self.buf[1], self.buf[0]
+            if len(terms) > 1:
+                self.engine.lincomb(terms, K, length=n_own)
+                base = K                              # u0 may alias u_out: each CTA reads its patch of u0 before writing
+            else:
+                base = U
+            self._launch_tendency(src, 1.0, base, float(self.b[i_stage]) * self.dt, K)
+        self.buf[0], self.buf[2 + i_stage] = K, U
         self._host_stale = True
 
     def solve_stage(self, i_stage, t, update_forcings=None):
