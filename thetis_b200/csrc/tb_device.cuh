@@ -91,6 +91,11 @@ __device__ __forceinline__ void cp_async8(void *sdst, const void *gsrc) {
 __device__ __forceinline__ void bulk_prefetch_l2(const void *gsrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *gsrc) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");

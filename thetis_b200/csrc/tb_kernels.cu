@@ -204,8 +204,21 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             bulk_prefetch_l2(prm.pl.sblk + (long long)pf * prm.pl.stride, (uint32_t)prm.pl.stride);
             if (prm.u0) bulk_prefetch_l2(prm.u0 + (long long)pf * TB_P * 9, rec);
         }
+    } else if (tid >= 33 && tid < 36) {
+        // ... and its halo-id row (the first dependent load of that CTA's prologue)
+        const int pb = (int)blockIdx.x + TB_PREFETCH_DIST;
+        if (pb < (int)gridDim.x) {
+            const int pf = prm.patch_list ? __ldg(prm.patch_list + pb) : prm.patch_first + pb;
+            const int off = (tid - 33) * 32;
+            if (off < prm.pl.NH) prefetch_l2(prm.pl.halo_ids + (long long)pf * prm.pl.NH + off);
+            if (tid == 33) prefetch_l2(prm.pl.halo_cnt + pf);
+        }
     }
-    // patch halo: records of off-patch facet neighbours, copied asynchronously (LDGSTS) while the bulk copies fly.
+    __syncthreads();          // mbarrier initialised (thread 0) before anybody waits on it
+    mbar_wait(bar, 0);        // every thread observes the TMA completion itself
+    // patch halo: records of off-patch facet neighbours, copied asynchronously (LDGSTS).  The ids were requested at
+    // the top and have arrived while the bulk copies were in flight; the copies themselves land while the volume
+    // terms are evaluated and are only waited for in front of the facet loop.
     // Element i of the halo block is double (i % 9) of halo cell (i / 9): S[TB_P*9 + i].
     {
         double *H = S + TB_P * 9;
@@ -218,21 +231,20 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             const int h = i / 9;
             cp_async8(H + i, prm.u_in + ((long long)__ldg(hid + h) * 9 + (i - h * 9)));
         }
-        cp_async_wait_all();
+        cp_async_commit();
     }
-    __syncthreads();          // mbarrier initialised (thread 0) before anybody waits on it; halo copies landed
-    mbar_wait(bar, 0);        // every thread observes the TMA completion itself: no second barrier needed
 
+    // threads past the last owned cell of the last patch evaluate cell 0 of the patch again (uniform control flow:
+    // there is a block-wide barrier in the middle) and their result is discarded
     const bool active = (cell0 + tid) < prm.n_owned;
+    const int ct = active ? tid : 0;
     double res[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) res[k] = 0.0;
 
-    if (active) {
+    {
         const double *cols = reinterpret_cast<const double *>(blk);
-        const uint16_t *cv = reinterpret_cast<const uint16_t *>(blk + prm.pl.off_cv) + tid * 3;
-        const int *cn = reinterpret_cast<const int *>(blk + prm.pl.off_cn) + tid * 3;
-        const double *my = S + tid * 9;
+        const uint16_t *cv = reinterpret_cast<const uint16_t *>(blk + prm.pl.off_cv) + ct * 3;
+        const int *cn = reinterpret_cast<const int *>(blk + prm.pl.off_cn) + ct * 3;
+        const double *my = S + ct * 9;
         const double g = prm.g;
         const int wd_on = SP::generic ? prm.wd_on : (SP::wd ? 1 : 0);
         const bool lf_on = SP::generic ? (prm.lf_on != 0) : true;
@@ -514,6 +526,8 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         }
 
         // ---------------- facet terms, 2-point Gauss per facet ----------------
+        cp_async_wait_group0();
+        __syncthreads();      // every thread's halo copies have landed
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int p = (i + 1) % 3, q = (i + 2) % 3;
@@ -731,7 +745,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         }
     }
 #pragma unroll
-    for (int k = 0; k < 9; ++k) O[tid * 9 + k] = res[k];
+    for (int k = 0; k < 9; ++k) O[tid * 9 + k] = active ? res[k] : 0.0;
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
