@@ -252,6 +252,7 @@ def main():
     # ---------------- end-to-end through the reference-facing API
     e2e = None
     if not a.no_e2e:
+        run.use_fused_norms(True)
         if not a.no_graph and hasattr(run, "enable_stage_graphs"):
             run.enable_stage_graphs()
         for _ in range(max(a.warmup, 3)):

@@ -183,6 +183,12 @@ int tb_swe_integrals(tb_ctx *ctx, const double *state, double *out, void *stream
  * (TracerOvershootCallBack).  `out`: DEVICE pointer to 4 doubles.  tb_swe_integrals' out[3] is
  * int (eta + bathymetry) dx (VolumeConservation2DCallback / comp_volume_2d). */
 int tb_tracer_integrals(tb_ctx *ctx, const double *c, const double *swe_state, double *out, void *stream);
+/* Fused variant of tb_swe_integrals: while enabled, every tb_swe_stage launch also reduces the four integrals of the
+ * state it WRITES (u_out) per patch in its epilogue; tb_stage_integrals_finish sums the per-patch values (fixed
+ * order, deterministic) into DEVICE out[4].  Saves the extra pass over the state that print_state / the volume
+ * callback would otherwise need after the last RK stage (solver2d.py:955-956). */
+int tb_stage_integrals(tb_ctx *ctx, int enable);
+int tb_stage_integrals_finish(tb_ctx *ctx, double *out, void *stream);
 /* out = sum_j w[j]*x[j], j < n <= 6, over `len` doubles (16-byte aligned operands): the stage combinations of the Butcher-form
  * integrators (ERKGeneric.update_solution / get_final_solution, rungekutta.py:816-852).  x: HOST array of n
  * DEVICE pointers, w: HOST weights.  out may alias any x[j]. */

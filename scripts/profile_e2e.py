@@ -8,6 +8,8 @@ k = int(sys.argv[1]) if len(sys.argv) > 1 else 19
 mesh = north_sea_mesh(k)
 setup = north_sea_setup(mesh)
 run = SingleSWE(mesh, setup)
+if len(sys.argv) > 2 and sys.argv[2] == "graphs":
+    run.enable_stage_graphs()
 for _ in range(5):
     run.step_e2e()
 torch.cuda.synchronize()

@@ -312,3 +312,27 @@ def test_unsupported_configurations_raise():
     s3.options.swe_timestepper_type = "CrankNicolson"
     with pytest.raises(NotImplementedError):
         s3.assign_initial_conditions()
+
+
+def test_fused_stage_integrals_match_separate_reduction():
+    """tb_stage_integrals: the diagnostics reduced in the last RK stage's epilogue equal tb_swe_integrals of the new
+    state (different summation order: 1e-13), through SSPRK33 and through the Butcher-form ERKLSPUM2"""
+    import torch
+    from thetis_b200 import rungekutta
+    mesh = delaunay_mesh(1200, 2.0e4, 1.5e4, seed=5)
+    for name in ("SSPRK33", "ERKLSPUM2"):
+        s, P1 = _solver(mesh, lambda x, y: 12.0 + 3.0 * np.sin(x / 3e3), timestep=0.5, simulation_end_time=1.0,
+                        swe_timestepper_type=name)
+        s.assign_initial_conditions(elev=lambda x, y: 0.4 * np.cos(x / 2e3) * np.sin(y / 3e3),
+                                    uv=lambda x, y: (0.1 * np.sin(y / 2e3), 0.05 * np.cos(x / 4e3)))
+        ts = s.timestepper
+        assert isinstance(ts, getattr(rungekutta, name))
+        fused = torch.zeros(4, dtype=torch.float64, device=ts.engine.device)
+        ts.fused_norms = fused
+        for i in range(3):
+            ts.advance(i * 0.5)
+        sep = torch.zeros(4, dtype=torch.float64, device=ts.engine.device)
+        ts.engine.swe_integrals(ts.device_state(), sep)
+        f, g = fused.cpu().numpy(), sep.cpu().numpy()
+        assert np.all(np.abs(f - g) <= 1e-13 * np.abs(g)), (f, g)
+        assert g[0] > 0 and g[1] > 0 and g[3] > 0

@@ -65,6 +65,8 @@ SIGNATURES = {
     "tb_swe_integrals": (_I, [_P, _P, _P, _P]),
     "tb_tracer_integrals": (_I, [_P, _P, _P, _P, _P]),
     "tb_lincomb": (_I, [_P, _I, _P, _P, _P, _L, _P]),
+    "tb_stage_integrals": (_I, [_P, _I]),
+    "tb_stage_integrals_finish": (_I, [_P, _P, _P]),
     "tb_gather_cells": (_I, [_P, _P, _P, _L, _I, _P, _P]),
     "tb_scatter_cells": (_I, [_P, _P, _P, _L, _I, _P, _P]),
     "tb_push_cells": (_I, [_P, _P, _P, _P, _L, _I, _P]),

@@ -49,6 +49,8 @@ struct tb_ctx {
     double *d_area = nullptr;
     double *d_bath3 = nullptr;      // bathymetry at the 3 nodes of every owned cell (diagnostics)
     double *d_partial = nullptr;    // scratch of the two-pass reductions
+    double *d_stage_partial = nullptr;  // [n_patches][4] written by the stage kernel's fused diagnostics epilogue
+    int stage_integrals = 0;
     bool halo_geom = false;         // patch tables carry the halo cells' vertices (SIPG terms need the neighbour's gradient)
     std::vector<uint16_t> patch_hcv;    // [n_patches*NH*3]
     // ring of pinned staging buffers for boundary data uploads (no stream stall in steady state)
@@ -448,6 +450,7 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_area);
     cudaFree(ctx->d_bath3);
     cudaFree(ctx->d_partial);
+    cudaFree(ctx->d_stage_partial);
     for (int k = 0; k < 5; ++k) {
         cudaFree(ctx->d_ext[k]);
         cudaFree(ctx->d_ext_tr[k]);
@@ -702,6 +705,14 @@ extern "C" int tb_swe_stage(tb_ctx *ctx, double a0, double a1, double b_dt, cons
     p.use_quad = (p.man.mode || p.cd.mode || p.wind.mode || p.wd_on) ? 1 : 0;
     p.nquad = ctx->nquad;
     p.force_generic = ctx->force_generic;
+    p.partials = nullptr;
+    if (ctx->stage_integrals) {
+        if (!ctx->d_stage_partial) {
+            CK(cudaMalloc(&ctx->d_stage_partial, sizeof(double) * 4 * ctx->n_patches));
+            CK(cudaMemset(ctx->d_stage_partial, 0, sizeof(double) * 4 * ctx->n_patches));
+        }
+        p.partials = ctx->d_stage_partial;
+    }
     fill_bc(ctx, 0, p.bc);
     long long first, count;
     patch_range(ctx, first, count);
@@ -877,6 +888,18 @@ extern "C" int tb_swe_integrals(tb_ctx *ctx, const double *state, double *out, v
     }
     CK(tb_launch_swe_integrals(state, ctx->d_area, ctx->d_bath3, ctx->n_owned, ctx->d_partial, out, (cudaStream_t)stream));
     ctx->launches += 2;
+    return TB_OK;
+}
+extern "C" int tb_stage_integrals(tb_ctx *ctx, int enable) {
+    if (!ctx) return TB_ERR_ARG;
+    ctx->stage_integrals = enable != 0;
+    return TB_OK;
+}
+extern "C" int tb_stage_integrals_finish(tb_ctx *ctx, double *out, void *stream) {
+    if (!ctx || !out) return fail(ctx, TB_ERR_ARG, "null pointer");
+    if (!ctx->d_stage_partial) return fail(ctx, TB_ERR_STATE, "no stage launch has produced fused diagnostics yet");
+    CK(tb_launch_patch_partials_final(ctx->d_stage_partial, ctx->n_patches, out, (cudaStream_t)stream));
+    ctx->launches += 1;
     return TB_OK;
 }
 extern "C" int tb_tracer_integrals(tb_ctx *ctx, const double *c, const double *swe_state, double *out, void *stream) {

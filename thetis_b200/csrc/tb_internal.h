@@ -68,6 +68,7 @@ struct TbSweParams {
     double g, rho0, lf_sigma, eps2, wd_alpha2;
     int lf_on, wd_on, use_quad, nquad;
     int force_generic, pad0;      // developer switch: always run the generic (SPEC 0) kernel
+    double *partials;             // optional [n_patches][4]: fused diagnostics of u_out (int eta^2, |u|^2, eta, eta+b)
     TbCoef cor, man, cd, lin, wind, pa, msrc, vsrc, visc;
     double sipg;                  // sipg_factor (HorizontalViscosityTerm, shallowwater_eq.py:558)
     int graddiv, graddepth;       // use_grad_div_viscosity_term, use_grad_depth_viscosity_term
@@ -122,6 +123,7 @@ cudaError_t tb_launch_scatter_cells(const double *buf, const int32_t *idx, long 
                                     cudaStream_t s);
 cudaError_t tb_launch_push_cells(const double *state, const int32_t *idx, const unsigned long long *dst, long long n,
                                  int rec, cudaStream_t s);
+cudaError_t tb_launch_patch_partials_final(const double *partial, long long n, double *out, cudaStream_t s);
 cudaError_t tb_launch_swe_integrals(const double *state, const double *area, const double *bath3, long long n_owned,
                                     double *partial, double *out, cudaStream_t s);
 #define TB_NRED 296           // CTAs of the two-pass reductions (2 per SM)

@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
     const bool active = (cell0 + tid) < prm.n_owned;
     const int ct = active ? tid : 0;
     double res[9];
+    double ia[4] = {0, 0, 0, 0};      // this cell's share of the fused diagnostics (prm.partials)
 
     {
         const double *cols = reinterpret_cast<const double *>(blk);
@@ -743,19 +744,49 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < 9; ++k) res[k] += prm.a0 * O[tid * 9 + k];
         }
+        if (prm.partials && active) {
+            // fused print_state / volume diagnostics of the state this launch produces (same closed forms as
+            // swe_integrals_partial): int f g = A/12 (sum_a f_a g_a + (sum f)(sum g))
+            const double A12 = twoA * (1.0 / 24.0);
+            const double se = res[6] + res[7] + res[8];
+            const double sx = res[0] + res[2] + res[4], sy = res[1] + res[3] + res[5];
+            ia[0] = A12 * (res[6] * res[6] + res[7] * res[7] + res[8] * res[8] + se * se);
+            ia[1] = A12 * (res[0] * res[0] + res[2] * res[2] + res[4] * res[4] + sx * sx + res[1] * res[1] +
+                           res[3] * res[3] + res[5] * res[5] + sy * sy);
+            ia[2] = twoA * (1.0 / 6.0) * se;
+            ia[3] = twoA * (1.0 / 6.0) * (se + b[0] + b[1] + b[2]);
+        }
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) O[tid * 9 + k] = active ? res[k] : 0.0;
+    double *red = reinterpret_cast<double *>(blk + prm.pl.stride);      // [TB_P / 32][4] scratch behind the static block
+    if (prm.partials) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ia[k] += __shfl_down_sync(0xffffffffu, ia[k], o);
+        }
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) red[(tid >> 5) * 4 + k] = ia[k];
+        }
+    }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
         bulk_s2g(prm.u_out + cell0 * 9, O, TB_P * 9 * sizeof(double));
         bulk_commit_wait_read();
+    } else if (prm.partials && tid >= 32 && tid < 36) {
+        const int k = tid - 32;          // fixed order: deterministic
+        double r = red[k];
+#pragma unroll
+        for (int w = 1; w < TB_P / 32; ++w) r += red[w * 4 + k];
+        prm.partials[(long long)patch * 4 + k] = r;
     }
 }
 
 size_t tb_swe_smem_bytes(const TbPatchLayout &pl) {
-    return 16 + (size_t)(TB_P + pl.NH) * 72 + (size_t)TB_P * 72 + (size_t)pl.stride;
+    return 16 + (size_t)(TB_P + pl.NH) * 72 + (size_t)TB_P * 72 + (size_t)pl.stride + (TB_P / 32) * 4 * sizeof(double);
 }
 
 template <bool NL, int SPEC>
@@ -1034,6 +1065,30 @@ __global__ void integrals_final(const double *__restrict__ partial, int nb, int 
         }
         out[k] = r;
     }
+}
+// sum of per-patch partials [n][4] (written by the stage kernel's fused epilogue): one CTA, fixed order
+__global__ void patch_partials_final(const double *__restrict__ partial, long long n, double *__restrict__ out) {
+    __shared__ double sh[4][1024];
+    double a[4] = {0, 0, 0, 0};
+    for (long long j = threadIdx.x; j < n; j += blockDim.x) {
+        const double4 v = reinterpret_cast<const double4 *>(partial)[j];
+        a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] = a[k];
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) out[threadIdx.x] = sh[threadIdx.x][0];
+}
+cudaError_t tb_launch_patch_partials_final(const double *partial, long long n, double *out, cudaStream_t s) {
+    patch_partials_final<<<1, 1024, 0, s>>>(partial, n, out);
+    return cudaGetLastError();
 }
 cudaError_t tb_launch_swe_integrals(const double *state, const double *area, const double *bath3, long long n_owned,
                                     double *partial, double *out, cudaStream_t s) {

@@ -166,6 +166,14 @@ class Engine:
         """out (device, 4 doubles): int eta^2, int |u|^2, int eta, int (eta + bathymetry)"""
         self._ck(self.lib.tb_swe_integrals(self.ctx, _ptr(state), _ptr(out), self.stream))
 
+    def stage_integrals(self, enable):
+        """while enabled, swe_stage launches also reduce the integrals of the state they write (per patch)"""
+        self._ck(self.lib.tb_stage_integrals(self.ctx, int(bool(enable))))
+
+    def stage_integrals_finish(self, out):
+        """out (device, 4 doubles) = sum of the per-patch values of the last integrals-enabled stage launches"""
+        self._ck(self.lib.tb_stage_integrals_finish(self.ctx, _ptr(out), self.stream))
+
     def tracer_integrals(self, c, swe_state, out):
         """out (device, 4 doubles): int c, int H c, min c, max c"""
         self._ck(self.lib.tb_tracer_integrals(self.ctx, _ptr(c), _ptr(swe_state), _ptr(out), self.stream))

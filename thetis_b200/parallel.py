@@ -426,6 +426,11 @@ class SingleSWE:
             self.ts.advance_device()
         self._graph = g
 
+    def use_fused_norms(self, on=True):
+        """e2e path: the print_state norms are reduced in the epilogue of the last RK stage (tb_stage_integrals) instead
+        of by a separate pass over the state.  Call before `enable_stage_graphs`."""
+        self.ts.fused_norms = self._norms if on else None
+
     def enable_stage_graphs(self):
         """One CUDA graph per RK stage for the e2e path: the host-side forcing refresh stays between the launches."""
         torch, ts = self.torch, self.ts
@@ -455,13 +460,14 @@ class SingleSWE:
         if getattr(self.ts, "stage_graphs", None):
             self._replays = getattr(self, "_replays", 0) + 1
         self.t += self.dt
-        self.eng.swe_integrals(self.ts.device_state(), self._norms)
-        self._norms_host.copy_(self._norms, non_blocking=True)
+        if self.ts.fused_norms is None:
+            self.eng.swe_integrals(self.ts.device_state(), self._norms)
+        self._norms_host.copy_(self._norms, non_blocking=True)   # else: reduced by the last stage (tb_stage_integrals)
 
     def e2e_path(self):
         return ("FlowSolver2d mirror -> SSPRK33.advance(t, update_forcings) -> C-ABI: tidal elevation Function updated "
-                "on the host every stage (H2D from pinned memory), print_state norms reduced on the device and read "
-                "back every step")
+                "on the host every stage (H2D from pinned memory), print_state norms reduced on the device (fused "
+                "into the last stage kernel) and read back every step")
 
     def h2d_bytes_per_step(self):
         return 3 * self._n_open * 2 * 8

@@ -100,6 +100,8 @@ class ERKGenericShuOsher:
     cfl_coeff = 1.0
     n_buffers = 3
     butcher_form = False
+    fused_norms = None      # device tensor (4 doubles): when set, the last SWE stage also reduces int eta^2, int |u|^2,
+                            # int eta, int (eta + bathymetry) of the new solution into it (tb_stage_integrals)
 
     def __init__(self, equation, solution, fields, dt, options=None, bnd_conditions=None, terms_to_add="all",
                  sync_policy="every_step"):
@@ -134,6 +136,7 @@ class ERKGenericShuOsher:
         self._last_host_version = None
         self._field_versions = {}
         self._bc_versions = {}
+        self._stamps = {}
         self._setup_buffers()
         self._check_supported()
         self._push_static()
@@ -257,7 +260,27 @@ class ERKGenericShuOsher:
             self._conservative = cons
         self._push_dynamic(force=True)
 
+    def _stamp(self, obj):
+        """Cheap change stamp of a datum: the value itself for None / plain numbers, (identity, version) for
+        Constants and Functions that carry a version counter; None = unknown (always re-read)."""
+        if obj is None or isinstance(obj, (int, float)):
+            return ("v", obj)
+        ver = _version(obj)
+        return None if ver is None else (id(obj), ver)
+
+    def _push_option(self, key, opt_id, obj, default):
+        """Scalar option from None | number | Constant; re-read only when its stamp changed."""
+        st = self._stamp(obj)
+        if st is not None and self._stamps.get(key) == st:
+            return
+        self.engine.set_option(opt_id, default if obj is None else float(constant_value(obj)[0]))
+        self._stamps[key] = st
+
     def _set_field(self, fid, value, key):
+        st = self._stamp(value)
+        if st is not None and self._stamps.get(("field", key)) == st:
+            return
+        self._stamps[("field", key)] = st
         eng = self.engine
         if value is None:
             if self._field_versions.get(key, "unset") != "none":
@@ -293,17 +316,16 @@ class ERKGenericShuOsher:
                 except ImportError:
                     gc = None
             if gc is not None:
-                eng.set_option(L.OPT_G_GRAV, float(constant_value(gc["g_grav"])[0]))
-                eng.set_option(L.OPT_RHO0, float(constant_value(gc["rho0"])[0]))
+                self._push_option("g", L.OPT_G_GRAV, gc["g_grav"], 9.81)
+                self._push_option("rho0", L.OPT_RHO0, gc["rho0"], 1000.0)
             eqo = self.equation.options
-            eng.set_option(L.OPT_NORM_SMOOTHER, float(constant_value(_opt(eqo, "norm_smoother", 0.0))[0]))
-            lf = self.fields.get("lax_friedrichs_velocity_scaling_factor")
-            eng.set_option(L.OPT_LF_SCALING, 1.0 if lf is None else float(constant_value(lf)[0]))
-            sf = _opt(eqo, "sipg_factor", None)
-            eng.set_option(L.OPT_SIPG_FACTOR, 1.0 if sf is None else float(constant_value(sf)[0]))
+            self._push_option("eps", L.OPT_NORM_SMOOTHER, _opt(eqo, "norm_smoother", None), 0.0)
+            self._push_option("lf", L.OPT_LF_SCALING, self.fields.get("lax_friedrichs_velocity_scaling_factor"), 1.0)
+            self._push_option("sipg", L.OPT_SIPG_FACTOR, _opt(eqo, "sipg_factor", None), 1.0)
             for name, fid in _SWE_FIELDS.items():
-                if functions or not is_function(self.fields.get(name)):
-                    self._set_field(fid, self.fields.get(name), name)
+                val = self.fields.get(name)
+                if functions or val is None or not is_function(val):
+                    self._set_field(fid, val, name)
             self._push_bcs(0, _SWE_TAGS)
         else:
             # several tracer integrators share one device context: equation-specific switches are re-sent every stage
@@ -311,24 +333,22 @@ class ERKGenericShuOsher:
             # stamps are dropped whenever another tracer integrator configured the context in between
             if getattr(eng, "_tracer_cfg_owner", None) is not self:
                 if getattr(eng, "_tracer_cfg_owner", None) is not None:
-                    for k in ("tracer_source", "diffusivity_h"):
-                        self._field_versions.pop(k, None)
+                    self._field_versions = {}
                     self._bc_versions = {}
+                    self._stamps = {}
                 eng._tracer_cfg_owner = self
             eng.set_option(L.OPT_TRACER_CONSERVATIVE, self._conservative)
-            sf = _opt(self.equation.options, "sipg_factor_tracer", None)
-            eng.set_option(L.OPT_SIPG_FACTOR_TRACER, 1.0 if sf is None else float(constant_value(sf)[0]))
+            self._push_option("sipg", L.OPT_SIPG_FACTOR_TRACER, _opt(self.equation.options, "sipg_factor_tracer", None), 1.0)
             diff = self._tracer_field("diffusivity_h")
-            if functions or not is_function(diff):
+            if functions or diff is None or not is_function(diff):
                 self._set_field(L.F_DIFFUSIVITY, diff, "diffusivity_h")
-            lf = self.fields.get("lax_friedrichs_tracer_scaling_factor")
-            eng.set_option(L.OPT_LF_TRACER_SCALING, 1.0 if lf is None else float(constant_value(lf)[0]))
+            self._push_option("lf", L.OPT_LF_TRACER_SCALING, self.fields.get("lax_friedrichs_tracer_scaling_factor"), 1.0)
             cf = self.fields.get("tracer_advective_velocity_factor")
             if cf is not None and not is_constant(cf):
                 raise NotImplementedError("spatially varying tracer_advective_velocity_factor is outside the accelerated path")
-            eng.set_option(L.OPT_TRACER_VEL_FACTOR, 1.0 if cf is None else float(constant_value(cf)[0]))
+            self._push_option("corr", L.OPT_TRACER_VEL_FACTOR, cf, 1.0)
             src = self._tracer_field("source")
-            if functions or not is_function(src):
+            if functions or src is None or not is_function(src):
                 self._set_field(L.F_TRACER_SOURCE, src, "tracer_source")
             self._push_bcs(1, _TRACER_TAGS)
 
@@ -337,6 +357,19 @@ class ERKGenericShuOsher:
         for marker, funcs in self.bnd_conditions.items():
             if funcs is None:
                 continue
+            # fast path: nothing in this marker's dict changed since the last stage
+            sig = []
+            for tag, val in funcs.items():
+                st = self._stamp(val)
+                if st is None:
+                    sig = None
+                    break
+                sig.append((tag, st))
+            if sig is not None:
+                sig = tuple(sig)
+                if self._stamps.get(("bc", eq, marker)) == sig:
+                    continue
+            self._stamps[("bc", eq, marker)] = sig
             op = 0
             consts = np.zeros(8)
             arrays = []
@@ -501,10 +534,17 @@ class ERKGenericShuOsher:
         self._cur = dst
         u0 = A if i_stage > 0 else None
         if self._kind == "swe":
+            # optional fused diagnostics of the new solution (print_state norms / volume) in the last stage's epilogue
+            fused = last and self.fused_norms is not None
+            if fused:
+                eng.stage_integrals(True)
             if self.halo is not None:
                 self.halo.swe_stage(a0, a1, bdt, src, u0, dst)        # + one halo exchange per stage
             else:
                 eng.swe_stage(a0, a1, bdt, src, u0, dst)
+            if fused:
+                eng.stage_integrals(False)
+                eng.stage_integrals_finish(self.fused_norms)          # rank-local; callers all-reduce on a distributed mesh
         else:
             eng.tracer_stage(a0, a1, bdt, src, u0, dst, self._swe_state_for_tracer())
             if self.halo is not None:
@@ -625,7 +665,13 @@ class ERKGeneric(ERKGenericShuOsher):
                 base = K                              # u0 may alias u_out: each CTA reads its patch of u0 before writing
             else:
                 base = U
+            fused = self._kind == "swe" and self.fused_norms is not None
+            if fused:
+                self.engine.stage_integrals(True)
             self._launch_tendency(src, 1.0, base, float(self.b[i_stage]) * self.dt, K)
+            if fused:
+                self.engine.stage_integrals(False)
+                self.engine.stage_integrals_finish(self.fused_norms)
         self.buf[0], self.buf[2 + i_stage] = K, U
         self._host_stale = True
 
