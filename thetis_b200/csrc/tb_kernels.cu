@@ -102,12 +102,15 @@ __device__ __forceinline__ double coef_at(const TbCoef &c, const double *cols, i
 //   SPEC 1  no optional cell terms (BASELINE configs 1 and 2)
 //   SPEC 2  Manning drag + Coriolis, 6-point cell rule (config 5 without wetting-drying)
 //   SPEC 3  SPEC 2 + wetting-drying (config 5)
+//   SPEC 4  Coriolis + wind stress + linear drag, 6-point cell rule (config 3, stommel2d; linear equations)
 template <int SPEC>
 struct StageSpec {
     static constexpr bool generic = SPEC == 0;
     static constexpr bool wd = SPEC == 3;
-    static constexpr bool man = SPEC >= 2;
+    static constexpr bool man = SPEC == 2 || SPEC == 3;
     static constexpr bool cor = SPEC >= 2;
+    static constexpr bool wind = SPEC == 4;
+    static constexpr bool lin = SPEC == 4;
 };
 
 // Open-boundary fluxes at one Gauss point (shallowwater_eq.py:370-375, 431-442, 498-509).  Rare (only facets of
@@ -252,14 +255,14 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         const bool has_cor = SP::generic ? (prm.cor.mode != 0) : SP::cor;
         const bool has_man = SP::generic ? (prm.man.mode != 0) : SP::man;
         const bool has_cd = SP::generic ? (prm.cd.mode != 0) : false;
-        const bool has_lin = SP::generic ? (prm.lin.mode != 0) : false;
-        const bool has_wind = SP::generic ? (prm.wind.mode != 0) : false;
+        const bool has_lin = SP::generic ? (prm.lin.mode != 0) : SP::lin;
+        const bool has_wind = SP::generic ? (prm.wind.mode != 0) : SP::wind;
         const bool has_pa = SP::generic ? (prm.pa.mode == 2) : false;
         const bool has_msrc = SP::generic ? (prm.msrc.mode != 0) : false;
         const bool has_vsrc = SP::generic ? (prm.vsrc.mode != 0) : false;
         const bool has_visc = SP::generic ? (prm.visc.mode != 0) : false;
         const bool graddiv = SP::generic ? (prm.graddiv != 0) : false;
-        const bool use_quad = SP::generic ? (prm.use_quad != 0) : (SP::man || SP::wd);
+        const bool use_quad = SP::generic ? (prm.use_quad != 0) : (SP::man || SP::wd || SP::wind);
         const double a2 = prm.wd_alpha2;
 
         double ux[3], uy[3], et[3], x[3], y[3], b[3];
@@ -801,14 +804,16 @@ cudaError_t tb_kernels_init() {
     if ((e = stage_attr<true, 2>()) != cudaSuccess) return e;
     if ((e = stage_attr<true, 3>()) != cudaSuccess) return e;
     if ((e = stage_attr<false, 0>()) != cudaSuccess) return e;
+    if ((e = stage_attr<false, 4>()) != cudaSuccess) return e;
     return stage_attr<false, 1>();
 }
 
 // which specialisation serves this parameter set (0 = generic)
 int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear) {
-    const bool extras = p.cd.mode || p.lin.mode || p.wind.mode || p.pa.mode == 2 || p.msrc.mode || p.vsrc.mode ||
-                        p.visc.mode;
-    if (extras) return 0;
+    const bool rare = p.cd.mode || p.pa.mode == 2 || p.msrc.mode || p.vsrc.mode || p.visc.mode;
+    if (rare) return 0;
+    if (!nonlinear && p.cor.mode && p.wind.mode && p.lin.mode && !p.man.mode && !p.wd_on && p.nquad == 6) return 4;
+    if (p.lin.mode || p.wind.mode) return 0;
     if (!p.man.mode && !p.cor.mode && !p.wd_on && (!nonlinear || p.lf_on)) return 1;
     if (nonlinear && p.lf_on && p.man.mode && p.cor.mode && p.nquad == 6) return p.wd_on ? 3 : 2;
     return 0;
@@ -826,6 +831,7 @@ cudaError_t tb_launch_swe_stage(const TbSweParams &p, bool nonlinear, int n_patc
         }
     } else {
         if (spec == 1) swe_stage_kernel<false, 1><<<n_patches, TB_P, smem, s>>>(p);
+        else if (spec == 4) swe_stage_kernel<false, 4><<<n_patches, TB_P, smem, s>>>(p);
         else swe_stage_kernel<false, 0><<<n_patches, TB_P, smem, s>>>(p);
     }
     return cudaGetLastError();
