@@ -6,7 +6,9 @@
 #include <vector>
 #include "../../include/thetis_b200.h"
 
+#ifndef TB_P
 #define TB_P 128            // cells per patch == threads per CTA (one thread per cell)
+#endif
 #define TB_MAX_SLOTS 16     // distinct boundary markers
 #define TB_MAX_QUAD 12      // max cell quadrature points
 

@@ -1061,16 +1061,19 @@ __global__ void tracer_integrals_partial(const double *__restrict__ c, const dou
     block_reduce_store<4>(a, partial, op);
 }
 __global__ void integrals_final(const double *__restrict__ partial, int nb, int op2, int op3, double *__restrict__ out) {
-    if (threadIdx.x < 4) {
-        const int k = threadIdx.x;
-        const int op = k == 2 ? op2 : (k == 3 ? op3 : 0);
-        double r = partial[k];
-        for (int j = 1; j < nb; ++j) {
-            const double t = partial[j * 4 + k];
-            r = op == 0 ? r + t : (op == 1 ? fmin(r, t) : fmax(r, t));
-        }
-        out[k] = r;
+    // warp k reduces component k: lanes take the partials strided by 32, then a fixed shuffle tree (deterministic)
+    const int k = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int op = k == 2 ? op2 : (k == 3 ? op3 : 0);
+    double r = op == 0 ? 0.0 : (op == 1 ? 1.0e300 : -1.0e300);
+    for (int j = l; j < nb; j += 32) {
+        const double t = partial[j * 4 + k];
+        r = op == 0 ? r + t : (op == 1 ? fmin(r, t) : fmax(r, t));
     }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_down_sync(0xffffffffu, r, o);
+        r = op == 0 ? r + t : (op == 1 ? fmin(r, t) : fmax(r, t));
+    }
+    if (l == 0) out[k] = r;
 }
 // sum of per-patch partials [n][4] (written by the stage kernel's fused epilogue): one CTA, fixed order
 __global__ void patch_partials_final(const double *__restrict__ partial, long long n, double *__restrict__ out) {
@@ -1099,13 +1102,13 @@ cudaError_t tb_launch_patch_partials_final(const double *partial, long long n, d
 cudaError_t tb_launch_swe_integrals(const double *state, const double *area, const double *bath3, long long n_owned,
                                     double *partial, double *out, cudaStream_t s) {
     swe_integrals_partial<<<TB_NRED, 256, 0, s>>>(state, area, bath3, n_owned, partial);
-    integrals_final<<<1, 32, 0, s>>>(partial, TB_NRED, 0, 0, out);
+    integrals_final<<<1, 128, 0, s>>>(partial, TB_NRED, 0, 0, out);
     return cudaGetLastError();
 }
 cudaError_t tb_launch_tracer_integrals(const double *c, const double *swe, const double *area, const double *bath3,
                                        long long n_owned, int nonlin, int wd_on, double alpha2, int nquad,
                                        double *partial, double *out, cudaStream_t s) {
     tracer_integrals_partial<<<TB_NRED, 256, 0, s>>>(c, swe, area, bath3, n_owned, nonlin, wd_on, alpha2, nquad, partial);
-    integrals_final<<<1, 32, 0, s>>>(partial, TB_NRED, 1, 2, out);
+    integrals_final<<<1, 128, 0, s>>>(partial, TB_NRED, 1, 2, out);
     return cudaGetLastError();
 }
