@@ -66,3 +66,15 @@ if a.mode in ("all", "northsea_wd"):
     eng.set_bc_array(0, 100, L.BC_ELEV, np.zeros((m.n_bfacets, 2)))
     eng.set_option(L.OPT_WETTING_DRYING, 1)
     run("north sea + wetting-drying", 236)
+if a.mode in ("all", "northsea_wd_visc"):
+    eng.set_option(L.OPT_NONLINEAR, 1)
+    eng.set_field(L.F_MANNING, 0.03 + 0 * X)
+    eng.set_field(L.F_CORIOLIS, 1.2e-4 + 1e-11 * Y)
+    eng.set_bc(0, 100, L.BC_ELEV | L.BC_UV, [0.0, 0, 0, 0, 0, 0])
+    eng.set_bc_array(0, 100, L.BC_ELEV, np.zeros((m.n_bfacets, 2)))
+    eng.set_option(L.OPT_WETTING_DRYING, 1)
+    eng.set_field(L.F_VISCOSITY, 10.0 + 0 * X)
+    run("north sea + wetting-drying + viscosity (SPEC 6)", 240 + 14)
+    eng.set_option(L.OPT_FORCE_GENERIC_KERNEL, 1)
+    run("north sea + wetting-drying + viscosity (generic)", 240 + 14)
+    eng.set_option(L.OPT_FORCE_GENERIC_KERNEL, 0)

@@ -13,6 +13,20 @@ if len(sys.argv) > 2 and sys.argv[2] == "graphs":
 for _ in range(5):
     run.step_e2e()
 torch.cuda.synchronize()
+if len(sys.argv) > 3 and sys.argv[3] == "fused":
+    run.use_fused_norms(True)
+    if len(sys.argv) > 2 and sys.argv[2] == "graphs":
+        run.enable_stage_graphs()
+    for _ in range(5):
+        run.step_e2e()
+    torch.cuda.synchronize()
+# plain wall-clock first (no profiler overhead)
+t0 = time.perf_counter()
+for _ in range(300):
+    run.step_e2e()
+t_host = time.perf_counter() - t0
+torch.cuda.synchronize()
+print(f"no profiler: host issue time {t_host/300*1e3:.3f} ms/step; incl. GPU drain {(time.perf_counter()-t0)/300*1e3:.3f} ms/step")
 t0 = time.perf_counter()
 pr = cProfile.Profile()
 pr.enable()

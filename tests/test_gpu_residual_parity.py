@@ -294,3 +294,19 @@ def test_viscosity_toggle_rebuilds_patch_tables():
     ku, ke = orc.tendency(uv, eta)
     gu, ge = eng.download_nodal(k1)
     assert np.abs(gu - ku).max() / np.abs(ku).max() < 1e-11
+
+
+@pytest.mark.parametrize("wd", [False, True])
+@pytest.mark.parametrize("graddiv", [False, True])
+def test_config5_with_viscosity_specialised_kernels(wd, graddiv):
+    """North-Sea physics + horizontal viscosity (examples/north_sea prescribes a viscosity sponge): SPEC 5 / SPEC 6"""
+    from thetis_b200.workloads import north_sea_mesh, north_sea_setup, tide_values
+    mesh = north_sea_mesh(k=1)
+    setup = north_sea_setup(mesh, wetting_drying=wd)
+    tv = tide_values(setup, 4321.0)
+    X = mesh.coords[:, 0]
+    nu = 50.0 + 200.0 * np.exp(-((X - X.min()) / 5e4) ** 2)          # sponge towards the open boundary
+    _run(mesh, setup["bath"], dict(use_wetting_and_drying=wd, wetting_and_drying_alpha=0.5,
+                                   use_grad_div_viscosity_term=graddiv),
+         {"manning_drag_coefficient": setup["manning"], "coriolis": setup["coriolis"], "viscosity_h": nu},
+         {100: {"elev": 0.0, "uv": (0.0, 0.0)}}, tol=1e-10, bc_arrays={(100, "elev"): tv})

@@ -103,14 +103,17 @@ __device__ __forceinline__ double coef_at(const TbCoef &c, const double *cols, i
 //   SPEC 2  Manning drag + Coriolis, 6-point cell rule (config 5 without wetting-drying)
 //   SPEC 3  SPEC 2 + wetting-drying (config 5)
 //   SPEC 4  Coriolis + wind stress + linear drag, 6-point cell rule (config 3, stommel2d; linear equations)
+//   SPEC 5  SPEC 2 + horizontal viscosity (tidal set-ups that prescribe a viscosity / sponge, e.g. examples/north_sea)
+//   SPEC 6  SPEC 3 + horizontal viscosity
 template <int SPEC>
 struct StageSpec {
     static constexpr bool generic = SPEC == 0;
-    static constexpr bool wd = SPEC == 3;
-    static constexpr bool man = SPEC == 2 || SPEC == 3;
+    static constexpr bool wd = SPEC == 3 || SPEC == 6;
+    static constexpr bool man = SPEC == 2 || SPEC == 3 || SPEC == 5 || SPEC == 6;
     static constexpr bool cor = SPEC >= 2;
     static constexpr bool wind = SPEC == 4;
     static constexpr bool lin = SPEC == 4;
+    static constexpr bool visc = SPEC == 5 || SPEC == 6;
 };
 
 // Open-boundary fluxes at one Gauss point (shallowwater_eq.py:370-375, 431-442, 498-509).  Rare (only facets of
@@ -260,8 +263,8 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         const bool has_pa = SP::generic ? (prm.pa.mode == 2) : false;
         const bool has_msrc = SP::generic ? (prm.msrc.mode != 0) : false;
         const bool has_vsrc = SP::generic ? (prm.vsrc.mode != 0) : false;
-        const bool has_visc = SP::generic ? (prm.visc.mode != 0) : false;
-        const bool graddiv = SP::generic ? (prm.graddiv != 0) : false;
+        const bool has_visc = SP::generic ? (prm.visc.mode != 0) : SP::visc;
+        const bool graddiv = (SP::generic || SP::visc) ? (prm.graddiv != 0) : false;
         const bool use_quad = SP::generic ? (prm.use_quad != 0) : (SP::man || SP::wd || SP::wind);
         const double a2 = prm.wd_alpha2;
 
@@ -803,6 +806,8 @@ cudaError_t tb_kernels_init() {
     if ((e = stage_attr<true, 1>()) != cudaSuccess) return e;
     if ((e = stage_attr<true, 2>()) != cudaSuccess) return e;
     if ((e = stage_attr<true, 3>()) != cudaSuccess) return e;
+    if ((e = stage_attr<true, 5>()) != cudaSuccess) return e;
+    if ((e = stage_attr<true, 6>()) != cudaSuccess) return e;
     if ((e = stage_attr<false, 0>()) != cudaSuccess) return e;
     if ((e = stage_attr<false, 4>()) != cudaSuccess) return e;
     return stage_attr<false, 1>();
@@ -810,8 +815,13 @@ cudaError_t tb_kernels_init() {
 
 // which specialisation serves this parameter set (0 = generic)
 int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear) {
-    const bool rare = p.cd.mode || p.pa.mode == 2 || p.msrc.mode || p.vsrc.mode || p.visc.mode;
+    const bool rare = p.cd.mode || p.pa.mode == 2 || p.msrc.mode || p.vsrc.mode;
     if (rare) return 0;
+    if (p.visc.mode) {
+        if (nonlinear && p.lf_on && p.man.mode && p.cor.mode && !p.lin.mode && !p.wind.mode && p.nquad == 6)
+            return p.wd_on ? 6 : 5;
+        return 0;
+    }
     if (!nonlinear && p.cor.mode && p.wind.mode && p.lin.mode && !p.man.mode && !p.wd_on && p.nquad == 6) return 4;
     if (p.lin.mode || p.wind.mode) return 0;
     if (!p.man.mode && !p.cor.mode && !p.wd_on && (!nonlinear || p.lf_on)) return 1;
@@ -827,6 +837,8 @@ cudaError_t tb_launch_swe_stage(const TbSweParams &p, bool nonlinear, int n_patc
             case 1: swe_stage_kernel<true, 1><<<n_patches, TB_P, smem, s>>>(p); break;
             case 2: swe_stage_kernel<true, 2><<<n_patches, TB_P, smem, s>>>(p); break;
             case 3: swe_stage_kernel<true, 3><<<n_patches, TB_P, smem, s>>>(p); break;
+            case 5: swe_stage_kernel<true, 5><<<n_patches, TB_P, smem, s>>>(p); break;
+            case 6: swe_stage_kernel<true, 6><<<n_patches, TB_P, smem, s>>>(p); break;
             default: swe_stage_kernel<true, 0><<<n_patches, TB_P, smem, s>>>(p); break;
         }
     } else {
