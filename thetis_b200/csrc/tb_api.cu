@@ -420,6 +420,7 @@ extern "C" int tb_create(tb_ctx **out, const tb_mesh *m, int device) {
         }                                                                      \
     } while (0)
     CKC(tb_kernels_init());
+    CKC(tb_tracer_kernels_init());
     if (upload_halo_tables(ctx) != TB_OK) {
         g_create_error = ctx->err;
         tb_destroy(ctx);

@@ -108,7 +108,8 @@ cudaError_t tb_launch_tracer_integrals(const double *c, const double *swe, const
 int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear);
 size_t tb_swe_smem_bytes(const TbPatchLayout &pl);
 size_t tb_tracer_smem_bytes(const TbPatchLayout &pl);
-cudaError_t tb_kernels_init();
+cudaError_t tb_kernels_init();          // per device: raises the dynamic shared-memory limit of the stage kernels
+cudaError_t tb_tracer_kernels_init();
 cudaError_t tb_launch_test_math(const double *x, double *out, int n, cudaStream_t s);
 
 cudaError_t tb_launch_state_from_fields(const double *uv, const double *eta, const int32_t *node_map,

@@ -9,7 +9,7 @@
 #define TB_T_HALO_SPEC 4      // halo elements (9 per halo cell) per thread fetched speculatively (covers NH <= 56)
 #endif
 #ifndef TB_T_MINB
-#define TB_T_MINB 5           // resident CTAs per SM the tracer stage kernel is compiled for (96 registers)
+#define TB_T_MINB 7           // resident CTAs per SM the tracer stage kernel is compiled for (72 registers)
 #endif
 
 // degree-3 cell rule for the non-polynomial integrand of ConservativeSourceTerm (H*source with wetting-drying)
@@ -96,18 +96,20 @@ __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __g
         const int *cn = reinterpret_cast<const int *>(blk + prm.pl.off_cn) + tid * 3;
         const double *my = S + tid * 9;
         const double corr = prm.corr;
-        double ux[3], uy[3], et[3], c[3], x[3], y[3], b[3];
+        double ux[3], uy[3], c[3], x[3], y[3];
+        // elevation and bathymetry are needed by rare branches only ('flux' boundary data, conservative source): they
+        // are read from shared memory there instead of being kept in registers
+        auto et = [&](int a) { return my[6 + a]; };
+        auto b = [&](int a) { return cols[2 * NV + cv[a]]; };
         int v[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             ux[a] = corr * my[2 * a];
             uy[a] = corr * my[2 * a + 1];
-            et[a] = my[6 + a];
             c[a] = C[tid * 3 + a];
             v[a] = cv[a];
             x[a] = cols[v[a]];
             y[a] = cols[NV + v[a]];
-            b[a] = cols[2 * NV + v[a]];
         }
         double Nx[3], Ny[3];
 #pragma unroll
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __g
                 // ConservativeSourceTerm (:429-437): int H*source*phi_a by the cell rule
                 double hl[3];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) hl[a] = prm.nonlin ? b[a] + et[a] : b[a];
+                for (int a = 0; a < 3; ++a) hl[a] = prm.nonlin ? b(a) + et(a) : b(a);
                 for (int qd = 0; qd < prm.nquad; ++qd) {
                     const double l0 = ct_qlam[qd][0], l1 = ct_qlam[qd][1], l2 = ct_qlam[qd][2];
                     double Hq = l0 * hl[0] + l1 * hl[1] + l2 * hl[2];
@@ -282,13 +284,13 @@ __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __g
                             double flux = bs.flux;
                             if (bs.arr_mask & TB_BC_FLUX)
                                 flux = wp_ * __ldg(prm.bc.ext_flux + 2 * row) + wq_ * __ldg(prm.bc.ext_flux + 2 * row + 1);
-                            double eext = wp_ * et[p] + wq_ * et[q];
+                            double eext = wp_ * et(p) + wq_ * et(q);
                             if (op & TB_BC_ELEV) {
                                 eext = bs.elev;
                                 if (bs.arr_mask & TB_BC_ELEV)
                                     eext = wp_ * __ldg(prm.bc.ext_elev + 2 * row) + wq_ * __ldg(prm.bc.ext_elev + 2 * row + 1);
                             }
-                            const double bg = wp_ * b[p] + wq_ * b[q];
+                            const double bg = wp_ * b(p) + wq_ * b(q);
                             double hext = bg;
                             if (prm.nonlin) {
                                 hext = bg + eext;
@@ -353,16 +355,13 @@ size_t tb_tracer_smem_bytes(const TbPatchLayout &pl) {
     return 16 + (size_t)(TB_P + pl.NH) * 96 + (size_t)TB_P * 24 + (size_t)pl.stride;
 }
 
+cudaError_t tb_tracer_kernels_init() {
+    cudaError_t e = cudaFuncSetAttribute(tracer_stage_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tracer_stage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 cudaError_t tb_launch_tracer_stage(const TbTracerParams &p, int n_patches, size_t smem, cudaStream_t s) {
-    static bool init = false;
-    if (!init) {
-        cudaError_t e =
-            cudaFuncSetAttribute(tracer_stage_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(tracer_stage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        init = true;
-    }
     if (n_patches <= 0) return cudaSuccess;
     const bool plain = !p.conservative && !p.diff.mode && !p.src.mode && !p.lf_on && !p.force_generic;
     if (plain) tracer_stage_kernel<1><<<n_patches, TB_P, smem, s>>>(p);
