@@ -489,6 +489,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
 #pragma unroll
             for (int a = 0; a < 3; ++a) hl[a] = NONLIN ? b[a] + et[a] : b[a];
             const int nq = SP::generic ? prm.nquad : 6;
+            double HUx = 0.0, HUy = 0.0;
 #pragma unroll
             for (int qd = 0; qd < (SP::generic ? TB_MAX_QUAD : 6); ++qd) {
                 if (SP::generic && qd >= nq) break;
@@ -524,11 +525,18 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                 Rux[0] += l0 * sx; Rux[1] += l1 * sx; Rux[2] += l2 * sx;
                 Ruy[0] += l0 * sy; Ruy[1] += l1 * sy; Ruy[2] += l2 * sy;
                 if (NONLIN && wd_on) {
-                    // grad(phi_a).(H u) * w*A  with A grad(phi_a) = -N_a/2
-                    const double hx = -0.5 * c_qw[qd] * Hq * uq, hy = -0.5 * c_qw[qd] * Hq * vq;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) Re[a] += Nx[a] * hx + Ny[a] * hy;
+                    // int H u over the cell by the rule (the test-function gradients are constant: applied after the loop)
+                    const double wH = c_qw[qd] * Hq;
+                    HUx = fma(wH, uq, HUx);
+                    HUy = fma(wH, vq, HUy);
                 }
+            }
+            if (NONLIN && wd_on) {
+                // grad(phi_a).(int H u)  with A grad(phi_a) = -N_a/2
+                HUx *= -0.5;
+                HUy *= -0.5;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) Re[a] += Nx[a] * HUx + Ny[a] * HUy;
             }
         }
 
