@@ -23,6 +23,14 @@
 #ifndef TB_PREFETCH_DIST
 #define TB_PREFETCH_DIST 592   // patches ahead to warm in L2: one wave of 148 SMs x 4 CTAs
 #endif
+#ifndef TB_GP_UNROLL
+#define TB_GP_UNROLL 2        // unroll factor of the two facet Gauss points
+#endif
+#ifndef TB_QUAD_UNROLL
+#define TB_QUAD_UNROLL 6      // unroll factor of the cell-quadrature loop (code size vs. scheduling freedom)
+#endif
+#define TB_PRAGMA_(x) _Pragma(#x)
+#define TB_UNROLL(n) TB_PRAGMA_(unroll n)
 #ifndef TB_MINB
 #define TB_MINB 4      // resident CTAs per SM the stage kernel is compiled for (register budget)
 #endif
@@ -490,7 +498,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             for (int a = 0; a < 3; ++a) hl[a] = NONLIN ? b[a] + et[a] : b[a];
             const int nq = SP::generic ? prm.nquad : 6;
             double HUx = 0.0, HUy = 0.0;
-#pragma unroll
+TB_UNROLL(TB_QUAD_UNROLL)
             for (int qd = 0; qd < (SP::generic ? TB_MAX_QUAD : 6); ++qd) {
                 if (SP::generic && qd >= nq) break;
                 const double l0 = c_qlam[qd][0], l1 = c_qlam[qd][1], l2 = c_qlam[qd][2];
@@ -592,7 +600,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                     // sigma = sipg*cp*|e|/A (cp = 3 for P1 triangles), max over both sides
                     sigl = 6.0 * prm.sipg * len2 * tb_rcp(fmin(twoA, twoAN));
                 }
-#pragma unroll
+TB_UNROLL(TB_GP_UNROLL)
                 for (int gp = 0; gp < 2; ++gp) {
                     const double xi = gp ? TB_XI2 : TB_XI1;
                     const double hq_ = 0.5 * xi, hp_ = 0.5 - hq_;      // Gauss weight 1/2 folded into the test functions
