@@ -209,7 +209,7 @@ class HaloPlan:
             mask[bp] = True
             self._plist_b = torch.as_tensor(np.nonzero(mask)[0].astype(np.int32)).to(engine.device)
             self._plist_i = torch.as_tensor(np.nonzero(~mask)[0].astype(np.int32)).to(engine.device)
-            self._comm_stream = torch.cuda.Stream(device=engine.device)
+            self._comm_stream = torch.cuda.Stream(device=engine.device, priority=-1)   # boundary work goes first
             self._ev_b = torch.cuda.Event()
             self._ev_x = torch.cuda.Event()
             self.overlap = self._plist_b.numel() > 0 and self._plist_i.numel() > 0
@@ -283,18 +283,22 @@ class HaloPlan:
             eng.swe_stage(a0, a1, bdt, src, u0, dst)
             self.exchange(dst)
             return
+        # The partition-boundary patches and the interior patches write disjoint parts of dst and read the same src:
+        # they run CONCURRENTLY, the (few) boundary patches on a high-priority side stream followed by the push and
+        # the cross-rank barrier, the interior patches on the main stream filling the SMs the boundary launch leaves
+        # idle.  The next stage waits for both.
         main = torch.cuda.current_stream(eng.device)
-        eng.set_patch_list(self._plist_b)
-        eng.swe_stage(a0, a1, bdt, src, u0, dst)                 # partition-boundary patches
-        self._ev_b.record(main)
+        self._ev_b.record(main)                                  # everything src / u0 depend on
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(self._ev_b)
+            eng.set_patch_list(self._plist_b)
+            eng.swe_stage(a0, a1, bdt, src, u0, dst)             # partition-boundary patches
             self.exchange(dst)                                    # push + barrier while the interior computes
             self._ev_x.record(self._comm_stream)
         eng.set_patch_list(self._plist_i)
         eng.swe_stage(a0, a1, bdt, src, u0, dst)                 # interior patches
         eng.set_patch_list(None)
-        main.wait_event(self._ev_x)                              # ghosts of dst are complete before the next stage
+        main.wait_event(self._ev_x)                              # boundary patches + ghosts of dst are complete
 
     def kernels_per_swe_stage(self):
         return (2 if self.overlap else 1) + (1 if self.n_send else 0)
