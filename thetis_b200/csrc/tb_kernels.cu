@@ -124,6 +124,23 @@ struct StageSpec {
     static constexpr bool visc = SPEC == 5 || SPEC == 6;
 };
 
+// grad(u)_ij = d u_i / d x_j of a P1 cell and twice its area, from its record r = [u0x u0y u1x u1y u2x u2y ...] and its
+// vertex coordinates: g = {Gxx, Gxy, Gyx, Gyy, 2A}.  ONE routine, written in explicit fma form, serves the cell itself
+// and every neighbour (in-patch or halo), so the value a cell sees for a neighbour's gradient does not depend on which
+// thread produced it (partition-independent results).
+__device__ __forceinline__ void tb_cell_gradient(const double *r, const double *x, const double *y, double *g) {
+    const double twoA = fma(x[1] - x[0], y[2] - y[0], -((y[1] - y[0]) * (x[2] - x[0])));
+    double gxx = 0.0, gxy = 0.0, gyx = 0.0, gyy = 0.0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const double mx = y[(b + 2) % 3] - y[(b + 1) % 3], my = x[(b + 1) % 3] - x[(b + 2) % 3];   // |e_b| n_b
+        gxx = fma(r[2 * b], mx, gxx); gxy = fma(r[2 * b], my, gxy);
+        gyx = fma(r[2 * b + 1], mx, gyx); gyy = fma(r[2 * b + 1], my, gyy);
+    }
+    const double s = -tb_rcp(twoA);      // grad(phi_b) = -N_b / 2A
+    g[0] = gxx * s; g[1] = gxy * s; g[2] = gyx * s; g[3] = gyy * s; g[4] = twoA;
+}
+
 // Open-boundary fluxes at one Gauss point (shallowwater_eq.py:370-375, 431-442, 498-509).  Rare (only facets of
 // open markers), kept out of line so that it does not bloat the hot instruction stream.
 template <bool NONLIN>
@@ -429,19 +446,25 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         }
         // HorizontalViscosityTerm (shallowwater_eq.py:554-616), symmetric interior penalty.  S = stress / nu:
         // grad(u) or 2 sym(grad(u)), constant per cell.
-        double nuv[3] = {0, 0, 0}, Sxx = 0, Sxy = 0, Syx = 0, Syy = 0;
         const double itA = has_visc ? tb_rcp(twoA) : 0.0;
+        // nu at a cell node and the cell's stress / nu are re-read from shared memory in the facet part instead of being
+        // carried in registers across the whole kernel (the stage kernel is at its 128-register limit)
+        auto nu_at = [&](int a) { return coef_at(prm.visc, cols, NV, cv[a]); };
+        // [(TB_P + NH)][5] gradients + 2A of the patch and halo cells, behind the reduction scratch (only allocated
+        // when a SIPG coefficient is set: pl.off_hcv >= 0)
+        double *Gs = reinterpret_cast<double *>(blk + prm.pl.stride) + (TB_P / 32) * 4;
         if (has_visc) {
+            double nuv[3], Sxx, Sxy, Syx, Syy;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) nuv[a] = coef_at(prm.visc, cols, NV, v[a]);
-            // grad(u)_ij = d u_i / d x_j = -(1/2A) sum_a u_i[a] N_a,j
-            double Gxx = 0, Gxy = 0, Gyx = 0, Gyy = 0;
+            for (int a = 0; a < 3; ++a) nuv[a] = nu_at(a);
+            // grad(u) and 2A of this cell, published for the threads of the facet neighbours
+            double gk[5];
+            tb_cell_gradient(my, x, y, gk);
+            if (active) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                Gxx += ux[a] * Nx[a]; Gxy += ux[a] * Ny[a];
-                Gyx += uy[a] * Nx[a]; Gyy += uy[a] * Ny[a];
+                for (int k = 0; k < 5; ++k) Gs[tid * 5 + k] = gk[k];
             }
-            Gxx *= -itA; Gxy *= -itA; Gyx *= -itA; Gyy *= -itA;
+            const double Gxx = gk[0], Gxy = gk[1], Gyx = gk[2], Gyy = gk[3];
             if (graddiv) { Sxx = 2.0 * Gxx; Sxy = Gxy + Gyx; Syx = Sxy; Syy = 2.0 * Gyy; }
             else { Sxx = Gxx; Sxy = Gxy; Syx = Gyx; Syy = Gyy; }
             // cell term (:571): -int grad(psi):stress = +1/2 mean(nu) sum_j N_a,j S_ij
@@ -551,6 +574,22 @@ TB_UNROLL(TB_QUAD_UNROLL)
         // ---------------- facet terms, 2-point Gauss per facet ----------------
         cp_async_wait_group0();
         __syncthreads();      // every thread's halo copies have landed
+        if (has_visc) {
+            // gradients of the halo cells, one thread each, then visible to everybody
+            const uint16_t *hcv = reinterpret_cast<const uint16_t *>(blk + prm.pl.off_hcv);
+            for (int h = tid; h * 9 < nh9; h += TB_P) {
+                double xh[3], yh[3], gh5[5];
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb) {
+                    xh[bb] = cols[hcv[h * 3 + bb]];
+                    yh[bb] = cols[NV + hcv[h * 3 + bb]];
+                }
+                tb_cell_gradient(S + (TB_P + h) * 9, xh, yh, gh5);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) Gs[(TB_P + h) * 5 + k] = gh5[k];
+            }
+            __syncthreads();
+        }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int p = (i + 1) % 3, q = (i + 2) % 3;
@@ -570,35 +609,21 @@ TB_UNROLL(TB_QUAD_UNROLL)
                 const double dKx = ux[q] - ux[p], dKy = uy[q] - uy[p], dKe = et[q] - et[p], dKb = b[q] - b[p];
                 const double dNx = nr[2 * nq_] - uNxp, dNy = nr[2 * nq_ + 1] - uNyp, dNe = nr[6 + nq_] - eNp;
                 // SIPG (:575-590): sigma_max*len, (S^K + S^N).N and the facet integral D of nu*(u_K - u_N)/2
-                double sigl = 0, Tx = 0, Ty = 0, vDx = 0, vDy = 0;
+                double sigl = 0, Tx = 0, Ty = 0, vDx = 0, vDy = 0, nup_ = 0, nuq_ = 0;
                 if (has_visc) {
-                    const int ni = code >> 2;
-                    const uint16_t *cvn = ni < TB_P
-                        ? reinterpret_cast<const uint16_t *>(blk + prm.pl.off_cv) + ni * 3
-                        : reinterpret_cast<const uint16_t *>(blk + prm.pl.off_hcv) + (ni - TB_P) * 3;
-                    double xn[3], yn[3];
-#pragma unroll
-                    for (int bb = 0; bb < 3; ++bb) {
-                        xn[bb] = cols[cvn[bb]];
-                        yn[bb] = cols[NV + cvn[bb]];
-                    }
-                    const double twoAN = (xn[1] - xn[0]) * (yn[2] - yn[0]) - (yn[1] - yn[0]) * (xn[2] - xn[0]);
-                    double Hxx = 0, Hxy = 0, Hyx = 0, Hyy = 0;      // grad(u) of the neighbour
-#pragma unroll
-                    for (int bb = 0; bb < 3; ++bb) {
-                        const double mx = yn[(bb + 2) % 3] - yn[(bb + 1) % 3], my_ = xn[(bb + 1) % 3] - xn[(bb + 2) % 3];
-                        Hxx += nr[2 * bb] * mx; Hxy += nr[2 * bb] * my_;
-                        Hyx += nr[2 * bb + 1] * mx; Hyy += nr[2 * bb + 1] * my_;
-                    }
-                    const double itAN = -tb_rcp(twoAN);
-                    Hxx *= itAN; Hxy *= itAN; Hyx *= itAN; Hyy *= itAN;
+                    const double *gn = Gs + (code >> 2) * 5;        // the neighbour's grad(u) and 2A
+                    const double *go = Gs + ct * 5;                  // this cell's
+                    const double Hxx = gn[0] + go[0], Hxy = gn[1] + go[1], Hyx = gn[2] + go[2], Hyy = gn[3] + go[3];
+                    const double twoAN = gn[4];
+                    nup_ = nu_at(p);
+                    nuq_ = nu_at(q);
                     double Qxx, Qxy, Qyx, Qyy;                      // S^K + S^N
-                    if (graddiv) { Qxx = Sxx + 2.0 * Hxx; Qxy = Sxy + Hxy + Hyx; Qyx = Qxy; Qyy = Syy + 2.0 * Hyy; }
-                    else { Qxx = Sxx + Hxx; Qxy = Sxy + Hxy; Qyx = Syx + Hyx; Qyy = Syy + Hyy; }
+                    if (graddiv) { Qxx = 2.0 * Hxx; Qxy = Hxy + Hyx; Qyx = Qxy; Qyy = 2.0 * Hyy; }
+                    else { Qxx = Hxx; Qxy = Hxy; Qyx = Hyx; Qyy = Hyy; }
                     Tx = Qxx * nxs + Qxy * nys;
                     Ty = Qyx * nxs + Qyy * nys;
                     // sigma = sipg*cp*|e|/A (cp = 3 for P1 triangles), max over both sides
-                    sigl = 6.0 * prm.sipg * len2 * tb_rcp(fmin(twoA, twoAN));
+                    sigl = 6.0 * prm.sipg * len2 * tb_rcp(fmin(Gs[ct * 5 + 4], twoAN));
                 }
 TB_UNROLL(TB_GP_UNROLL)
                 for (int gp = 0; gp < 2; ++gp) {
@@ -648,7 +673,7 @@ TB_UNROLL(TB_GP_UNROLL)
                         fy = t * nys;
                     }
                     if (has_visc) {
-                        const double nug = fma(xi, nuv[q] - nuv[p], nuv[p]);    // nu is continuous (P1): avg(nu) = nu
+                        const double nug = fma(xi, nuq_ - nup_, nup_);          // nu is continuous (P1): avg(nu) = nu
                         double vx = sigl * dux, vy = sigl * duy;
                         if (graddiv) {
                             const double dn = sigl * dun * il * il;
@@ -715,7 +740,11 @@ TB_UNROLL(TB_GP_UNROLL)
                                 ddx = uKx - fl[3];
                                 ddy = uKy - fl[4];
                             }
-                            const double nug = wp_ * nuv[p] + wq_ * nuv[q];
+                            const double nug = wp_ * nu_at(p) + wq_ * nu_at(q);
+                            const double *go = Gs + ct * 5;
+                            double Sxx, Sxy, Syx, Syy;
+                            if (graddiv) { Sxx = 2.0 * go[0]; Sxy = go[1] + go[2]; Syx = Sxy; Syy = 2.0 * go[3]; }
+                            else { Sxx = go[0]; Sxy = go[1]; Syx = go[2]; Syy = go[3]; }
                             const double sl = 6.0 * prm.sipg * len2 * itA;      // sigma*len, own cell only
                             double vx = sl * ddx, vy = sl * ddy;
                             if (graddiv) {
@@ -808,7 +837,8 @@ TB_UNROLL(TB_GP_UNROLL)
 }
 
 size_t tb_swe_smem_bytes(const TbPatchLayout &pl) {
-    return 16 + (size_t)(TB_P + pl.NH) * 72 + (size_t)TB_P * 72 + (size_t)pl.stride + (TB_P / 32) * 4 * sizeof(double);
+    return 16 + (size_t)(TB_P + pl.NH) * 72 + (size_t)TB_P * 72 + (size_t)pl.stride + (TB_P / 32) * 4 * sizeof(double) +
+           (pl.off_hcv >= 0 ? (size_t)(TB_P + pl.NH) * 5 * sizeof(double) : 0);      // cell gradients (SIPG terms)
 }
 
 template <bool NL, int SPEC>
