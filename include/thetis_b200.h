@@ -79,7 +79,9 @@ typedef enum {
     TB_OPT_SIPG_FACTOR_TRACER = 13,    /* sipg_factor_tracer (options.py:732; tracer_eq_2d.py:235)  */
     TB_OPT_GRAD_DIV_VISCOSITY = 14,    /* use_grad_div_viscosity_term (options.py:597)              */
     TB_OPT_GRAD_DEPTH_VISCOSITY = 15,  /* use_grad_depth_viscosity_term (options.py:602), default on */
-    TB_OPT_TRACER_CONSERVATIVE = 16    /* tracer use_conservative_form (options.py:543; tracer_eq_2d.py:323-437) */
+    TB_OPT_TRACER_CONSERVATIVE = 16,   /* tracer use_conservative_form (options.py:543; tracer_eq_2d.py:323-437) */
+    TB_OPT_MOMENTUM_ADVECTION = 17     /* 0: no HorizontalAdvectionTerm although the depth is nonlinear
+                                          (ModeSplit2DEquations, shallowwater_eq.py:931-966); default 1 */
 } tb_option;
 
 /* Coefficient fields: the `fields` dict of solver2d.py:546-558 plus bathymetry. */

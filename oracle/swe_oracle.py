@@ -182,7 +182,10 @@ class SWEOracle:
         o = dict(use_nonlinear_equations=True, use_lax_friedrichs_velocity=True,
                  use_wetting_and_drying=False, wetting_and_drying_alpha=0.5,
                  norm_smoother=0.0, use_grad_div_viscosity_term=False,
-                 use_grad_depth_viscosity_term=True, sipg_factor=1.0)
+                 use_grad_depth_viscosity_term=True, sipg_factor=1.0,
+                 # False: ModeSplit2DEquations (shallowwater_eq.py:931-966): the term list has no
+                 # HorizontalAdvectionTerm (nor drag / wind / viscosity terms) although the depth is nonlinear
+                 include_momentum_advection=True)
         o.update(options or {})
         self.options = o
         self.fields = dict(fields or {})
@@ -312,6 +315,7 @@ class SWEOracle:
         o = self.options
         lam, qw = self.lam, self.qw
         nonlin = o["use_nonlinear_equations"]
+        adv = nonlin and o["include_momentum_advection"]
         Ru = np.zeros((nt, 3, 2))
         Re = np.zeros((nt, 3))
         A = geo.area
@@ -328,7 +332,7 @@ class SWEOracle:
         Ru += g * np.einsum("cq,cq,cai->cai", wq, eta_q, grad)
         # HUDiv: f = -inner(grad(phi), H*uv) dx
         Re += np.einsum("cq,cqi,cai->ca", wq, H_q[..., None] * u_q, grad)
-        if nonlin:
+        if adv:
             # HorizontalAdvection: f = -inner(div(outer(psi, uv_old)), uv) dx
             divu = np.einsum("cai,cai->c", grad, uv)      # constant per cell
             gu = np.einsum("cai,cqi->cqa", grad, u_q)     # grad(phi_a).u at q
@@ -430,7 +434,7 @@ class SWEOracle:
             hu_star = h_av[..., None] * uv_rie
             fe_p = np.einsum("fqi,fqi->fq", hu_star, np.broadcast_to(n_p, hu_star.shape))
             fe_m = np.einsum("fqi,fqi->fq", hu_star, np.broadcast_to(n_m, hu_star.shape))
-            if nonlin:
+            if adv:
                 uv_avg = 0.5 * (up + um)
                 un_av = np.einsum("fqi,fqi->fq", uv_avg, np.broadcast_to(n_m, uv_avg.shape))
                 # inner(uv_avg, jump(outer(psi, uv_old), n))
@@ -506,7 +510,7 @@ class SWEOracle:
                 eta_rie2 = 0.5 * (e + eta_ext) + np.sqrt(h_av / g) * un_jump
                 h_rie = self.total_depth(b, eta_rie2)
                 fe = fe + h_rie * un_rie
-                if nonlin:
+                if adv:
                     # advection (:498-509)
                     un_rie_a = 0.5 * np.einsum("fqi,fqi->fq", u + uv_ext, nb) + np.sqrt(g / H) * eta_jump
                     uv_av = 0.5 * (uv_ext + u)
@@ -516,7 +520,7 @@ class SWEOracle:
                 un_jump = np.einsum("fqi,fqi->fq", u, nb)
                 head_rie = e + np.sqrt(H / g) * un_jump
                 fu = fu + g * head_rie[..., None] * nb
-                if nonlin and o["use_lax_friedrichs_velocity"]:
+                if adv and o["use_lax_friedrichs_velocity"]:
                     # mirror velocity (:489-497)
                     sig = float(self.fields.get("lax_friedrichs_velocity_scaling_factor", 1.0))
                     uv_ext = u - 2 * un_jump[..., None] * nb

@@ -296,3 +296,42 @@ def test_viscous_spin_down_unstructured():
     for i in range(nsteps):
         st.advance(i * dt)
     assert _rel(eta_g, eta) < 1e-10 and _rel(uv_g, uv) < 1e-10
+
+
+def test_modesplit_equations_through_the_integrator():
+    """An explicit integrator built on a ModeSplit2DEquations descriptor: advection off, fields the equation has no
+    term for (Manning, wind, viscosity) are ignored exactly like the reference's term list does"""
+    from thetis_b200.shim import Function, FunctionSpace, MixedFunctionSpace, Constant, as_shim_mesh
+    from thetis_b200.equations import ModeSplit2DEquations, DepthExpression
+    from thetis_b200.options import ModelOptions2d
+    from thetis_b200 import rungekutta
+    mesh = rectangle_mesh(16, 10, 16e3, 10e3)
+    sm = as_shim_mesh(mesh)
+    P1 = FunctionSpace(sm, "CG", 1)
+    bath = Function(P1).interpolate(lambda x, y: 20.0 + 3.0 * np.sin(x / 3e3))
+    U = FunctionSpace(sm, "DG", 1, value_size=2)
+    H = FunctionSpace(sm, "DG", 1)
+    V = MixedFunctionSpace([U, H])
+    sol = Function(V)
+    uvf, ef = sol.subfunctions
+    ef.interpolate(lambda x, y: 0.3 * np.cos(np.pi * x / 16e3))
+    opts = ModelOptions2d()
+    eq = ModeSplit2DEquations(V, DepthExpression(bath), opts)
+    fields = {"coriolis": Constant(1.0e-4), "manning_drag_coefficient": Constant(0.05),
+              "wind_stress": Constant((0.3, 0.1)), "viscosity_h": Constant(100.0),
+              "momentum_source": Constant((1e-5, -2e-5))}
+    dt, nsteps = 5.0, 20
+    ts = rungekutta.ERKLPUM2(eq, sol, fields, dt, opts.swe_timestepper_options, {})
+    for i in range(nsteps):
+        ts.advance(i * dt)
+    uv_g = uvf.dat.data_ro.reshape(mesh.n_cells, 3, 2).copy()
+    e_g = ef.dat.data_ro.reshape(mesh.n_cells, 3).copy()
+    x = mesh.coords[mesh.cells]
+    orc = O.SWEOracle(mesh, 20.0 + 3.0 * np.sin(x[..., 0] / 3e3), options=dict(include_momentum_advection=False),
+                      fields={"coriolis": 1.0e-4, "momentum_source": (1e-5, -2e-5)})
+    eta = 0.3 * np.cos(np.pi * x[..., 0] / 16e3)
+    uv = np.zeros(eta.shape + (2,))
+    st = O.ButcherStepper(orc, [uv, eta], dt, *O.ERK_TABLEAUX["ERKLPUM2"][:3])
+    for i in range(nsteps):
+        st.advance(i * dt)
+    assert _rel(e_g, eta) < 1e-11 and _rel(uv_g, uv) < 1e-11

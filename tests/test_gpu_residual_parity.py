@@ -310,3 +310,47 @@ def test_config5_with_viscosity_specialised_kernels(wd, graddiv):
                                    use_grad_div_viscosity_term=graddiv),
          {"manning_drag_coefficient": setup["manning"], "coriolis": setup["coriolis"], "viscosity_h": nu},
          {100: {"elev": 0.0, "uv": (0.0, 0.0)}}, tol=1e-10, bc_arrays={(100, "elev"): tv})
+
+
+@pytest.mark.parametrize("bc", [{"elev": 0.3, "uv": (0.2, -0.1)}, {"un": -0.2}, {}])
+def test_modesplit_equations_no_momentum_advection(bc):
+    """ModeSplit2DEquations (shallowwater_eq.py:931-966): nonlinear depth in HUDiv, external pressure
+    gradient, Coriolis, momentum source, atmospheric pressure -- and no HorizontalAdvectionTerm"""
+    import thetis_b200._lib as L
+    from thetis_b200.engine import Engine
+    mesh = sfc_renumber(delaunay_mesh(1500, 2e4, 1.5e4, seed=6))
+    X, Y = mesh.coords[:, 0], mesh.coords[:, 1]
+    b = 15.0 + 4.0 * np.sin(X / 4e3)
+    f = 1e-4 + 1e-9 * Y
+    ms = np.stack([1e-4 * np.sin(X / 3e3), 2e-4 * np.cos(Y / 2e3)], -1)
+    pa = 500.0 * np.cos(X / 5e3)
+    uv, eta = _state(mesh, 4)
+    cells = mesh.cells
+    bnd = {1: bc} if bc else {}
+    orc = SWEOracle(mesh, b[cells], options=dict(include_momentum_advection=False),
+                    fields={"coriolis": f[cells], "momentum_source": ms[cells], "atmospheric_pressure": pa[cells]},
+                    bnd_conditions=bnd)
+    ku, ke = orc.tendency(uv, eta)
+    full = SWEOracle(mesh, b[cells], fields={"coriolis": f[cells], "momentum_source": ms[cells],
+                                             "atmospheric_pressure": pa[cells]}, bnd_conditions=bnd).tendency(uv, eta)
+    assert np.abs(full[0] - ku).max() > 1e-3 * np.abs(ku).max()        # the advection term is not negligible here
+    eng = Engine(mesh)
+    eng.set_option(L.OPT_MOMENTUM_ADVECTION, 0)
+    eng.set_field(L.F_BATHYMETRY, b)
+    eng.set_field(L.F_CORIOLIS, f)
+    eng.set_field(L.F_MOMENTUM_SOURCE, ms)
+    eng.set_field(L.F_ATM_PRESSURE, pa)
+    if bc:
+        tags = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN}
+        op, consts = 0, np.zeros(8)
+        for tag, val in bc.items():
+            op |= tags[tag]
+            if tag == "elev": consts[0] = val
+            if tag == "uv": consts[1:3] = val
+            if tag == "un": consts[3] = val
+        eng.set_bc(0, 1, op, consts)
+    st = eng.upload_nodal(uv, eta)
+    k = eng.new_state()
+    eng.swe_tendency(st, k)
+    gu, ge = eng.download_nodal(k)
+    assert np.abs(gu - ku).max() / np.abs(ku).max() < 1e-11 and np.abs(ge - ke).max() / np.abs(ke).max() < 1e-11

@@ -70,7 +70,7 @@ struct tb_ctx {
     int force_generic = 0;
     double lf_tracer_sigma = 1.0, tracer_vel_factor = 1.0;
     double sipg = 1.0, sipg_tracer = 1.0;
-    int graddiv = 0, graddepth = 1, tracer_conservative = 0;
+    int graddiv = 0, graddepth = 1, tracer_conservative = 0, momentum_advection = 1;
     FieldStore fields[TB_F_COUNT];
     // bcs: eq 0 swe, 1 tracer
     std::vector<int> slot_marker;       // slot -> marker
@@ -503,6 +503,7 @@ extern "C" int tb_set_option(tb_ctx *ctx, int option, double value) {
         case TB_OPT_GRAD_DIV_VISCOSITY: ctx->graddiv = value != 0.0; break;
         case TB_OPT_GRAD_DEPTH_VISCOSITY: ctx->graddepth = value != 0.0; break;
         case TB_OPT_TRACER_CONSERVATIVE: ctx->tracer_conservative = value != 0.0; break;
+        case TB_OPT_MOMENTUM_ADVECTION: ctx->momentum_advection = value != 0.0; break;
         default: return fail(ctx, TB_ERR_ARG, "unknown option");
     }
     return TB_OK;
@@ -706,6 +707,7 @@ extern "C" int tb_swe_stage(tb_ctx *ctx, double a0, double a1, double b_dt, cons
     p.use_quad = (p.man.mode || p.cd.mode || p.wind.mode || p.wd_on) ? 1 : 0;
     p.nquad = ctx->nquad;
     p.force_generic = ctx->force_generic;
+    p.adv_on = ctx->momentum_advection;
     p.partials = nullptr;
     if (ctx->stage_integrals) {
         if (!ctx->d_stage_partial) {

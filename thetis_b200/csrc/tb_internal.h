@@ -69,7 +69,7 @@ struct TbSweParams {
     double a0, a1, bdt;
     double g, rho0, lf_sigma, eps2, wd_alpha2;
     int lf_on, wd_on, use_quad, nquad;
-    int force_generic, pad0;      // developer switch: always run the generic (SPEC 0) kernel
+    int force_generic, adv_on;    // developer switch: always run the generic (SPEC 0) kernel; momentum advection on/off
     double *partials;             // optional [n_patches][4]: fused diagnostics of u_out (int eta^2, |u|^2, eta, eta+b)
     TbCoef cor, man, cd, lin, wind, pa, msrc, vsrc, visc;
     double sipg;                  // sipg_factor (HorizontalViscosityTerm, shallowwater_eq.py:558)

@@ -146,7 +146,8 @@ __device__ __forceinline__ void tb_cell_gradient(const double *r, const double *
 template <bool NONLIN>
 __device__ __noinline__ void open_boundary_flux(const TbBcTable *bc, int gb, int slot, double wp_, double wq_, double uKx,
                                                 double uKy, double eK, double bg, double HK, double nxs, double nys,
-                                                double il, double len, double g, int wd_on, double a2, double *out) {
+                                                double il, double len, double g, int wd_on, double a2, int adv_on,
+                                                double *out) {
     const TbBcSlot &bs = bc->slots[slot];
     const int op = bs.opcode;
     const int row = bs.arr_mask ? __ldg(bc->bf_row + gb) : 0;
@@ -176,7 +177,7 @@ __device__ __noinline__ void open_boundary_flux(const TbBcTable *bc, int gb, int
     const double eta_rie = 0.5 * (eK + ex.eta) + (cav * ig) * dun * il;
     const double h_rie = NONLIN ? wd_depth(bg + eta_rie, wd_on, a2) : bg;
     const double fe = h_rie * un_rie_len;
-    if (NONLIN) {
+    if (NONLIN && adv_on) {
         // advection (:498-509)
         const double un_a_len = 0.5 * usN + (cK * tb_rcp(HK)) * ejump * len;
         fx += 0.5 * usx * un_a_len;
@@ -288,6 +289,8 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         const bool has_pa = SP::generic ? (prm.pa.mode == 2) : false;
         const bool has_msrc = SP::generic ? (prm.msrc.mode != 0) : false;
         const bool has_vsrc = SP::generic ? (prm.vsrc.mode != 0) : false;
+        // ModeSplit2DEquations (shallowwater_eq.py:931-966) has no HorizontalAdvectionTerm although the depth is nonlinear
+        const bool adv_on = SP::generic ? (prm.adv_on != 0) : true;
         const bool has_visc = SP::generic ? (prm.visc.mode != 0) : SP::visc;
         const bool graddiv = (SP::generic || SP::visc) ? (prm.graddiv != 0) : false;
         const bool use_quad = SP::generic ? (prm.use_quad != 0) : (SP::man || SP::wd || SP::wind);
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
 #pragma unroll
             for (int a = 0; a < 3; ++a) Re[a] += Nx[a] * Wx + Ny[a] * Wy;
         }
-        if (NONLIN) {
+        if (NONLIN && adv_on) {
             // HorizontalAdvectionTerm cell part (:478): +div(outer(psi,u)).u
             //   int (grad phi_a . u) u_i = 1/12 sum_j (A grad phi_a)_j T_ji,  T_ji = sum_b u_b,j (u_b,i + su_i)
             //   int phi_a (div u) u_i   = D/12 (u_a,i + su_i),                D = sum_b (A grad phi_b).u_b
@@ -657,7 +660,7 @@ TB_UNROLL(TB_GP_UNROLL)
                     // HUDiv (:424-427): h*(avg(u) + sqrt(g/h)*jump(eta,n)).n
                     const double fe = fma(c * len, ediff, hh * usN);
                     double fx, fy;
-                    if (NONLIN) {
+                    if (NONLIN && adv_on) {
                         // advection (:480-488): avg(u) (u_K.n) + gamma (u_K - u_N);  u_K.N = (us.N + du.N)/2
                         const double hu = 0.25 * (usN + dun);
                         if (lf_on) {
@@ -722,13 +725,13 @@ TB_UNROLL(TB_GP_UNROLL)
                         const double uKN = uKx * nxs + uKy * nys;
                         const double c = tb_sqrt(g * HK);
                         double t = g * eK + c * uKN * il;
-                        if (NONLIN && lf_on) t += prm.lf_sigma * fabs(uKN) * uKN * il * il;
+                        if (NONLIN && adv_on && lf_on) t += prm.lf_sigma * fabs(uKN) * uKN * il * il;
                         fl[0] = t * nxs;
                         fl[1] = t * nys;
                         fl[2] = 0.0;
                     } else {
                         open_boundary_flux<NONLIN>(&prm.bc, gb, slot, wp_, wq_, uKx, uKy, eK, bg, HK, nxs, nys, il, len, g,
-                                                   wd_on, a2, fl);
+                                                   wd_on, a2, adv_on ? 1 : 0, fl);
                         if (has_visc && (op & (TB_BC_UV | TB_BC_UN | TB_BC_FLUX))) {
                             // Dirichlet terms of the viscosity (:592-609); 'elev' alone leaves uv_ext = uv: skipped
                             double ddx, ddy;
@@ -861,7 +864,7 @@ cudaError_t tb_kernels_init() {
 
 // which specialisation serves this parameter set (0 = generic)
 int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear) {
-    const bool rare = p.cd.mode || p.pa.mode == 2 || p.msrc.mode || p.vsrc.mode;
+    const bool rare = p.cd.mode || p.pa.mode == 2 || p.msrc.mode || p.vsrc.mode || !p.adv_on;
     if (rare) return 0;
     if (p.visc.mode) {
         if (nonlinear && p.lf_on && p.man.mode && p.cor.mode && !p.lin.mode && !p.wind.mode && p.nquad == 6)

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 from .shim import Constant
 
-__all__ = ["physical_constants", "DepthExpression", "ShallowWaterEquations", "TracerEquation2D"]
+__all__ = ["physical_constants", "DepthExpression", "ShallowWaterEquations", "ModeSplit2DEquations", "TracerEquation2D"]
 
 # mutable Constants, read live at every stage like the UFL forms do
 # (thetis/physical_constants.py:37-45; test/swe2d/test_rossby_wave.py:153-155 mutates g_grav)
@@ -44,6 +44,12 @@ class ShallowWaterEquations:
         self.tidal_farms = tidal_farms
         self.bnd_functions = {}
         self.physical_constants = physical_constants
+
+
+class ModeSplit2DEquations(ShallowWaterEquations):
+    """2D depth-averaged shallow water equations for mode splitting schemes (descriptor of
+    thetis/shallowwater_eq.py:931-966): external pressure gradient, Coriolis, momentum source, atmospheric pressure
+    and the continuity terms -- no momentum advection, drag, wind stress or viscosity."""
 
 
 class TracerEquation2D:

@@ -61,6 +61,7 @@ _SWE_FIELDS = {
     "momentum_source": L.F_MOMENTUM_SOURCE, "volume_source": L.F_VOLUME_SOURCE,
     "viscosity_h": L.F_VISCOSITY,
 }
+_MODESPLIT_FIELDS = ("coriolis", "momentum_source", "atmospheric_pressure", "volume_source")
 _SWE_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX}
 _TRACER_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX, "value": L.BC_VALUE,
                 "diff_flux": L.BC_DIFF_FLUX}
@@ -149,11 +150,13 @@ class ERKGenericShuOsher:
 
     def _equation_kind(self):
         n = self.equation.__class__.__name__
-        if n == "ShallowWaterEquations":
+        self._modesplit = n == "ModeSplit2DEquations"
+        if n in ("ShallowWaterEquations", "ModeSplit2DEquations"):
             return "swe"
         if n == "TracerEquation2D":
             return "tracer"
-        raise NotImplementedError(f"{n} is outside the accelerated path (ShallowWaterEquations, TracerEquation2D)")
+        raise NotImplementedError(f"{n} is outside the accelerated path (ShallowWaterEquations, ModeSplit2DEquations, "
+                                  "TracerEquation2D)")
 
     def _setup_buffers(self):
         eng, ad = self.engine, self.adaptor
@@ -250,6 +253,7 @@ class ERKGenericShuOsher:
             eng.set_option(L.OPT_LAX_FRIEDRICHS, bool(_opt(eqo, "use_lax_friedrichs_velocity", True)))
             eng.set_option(L.OPT_GRAD_DIV_VISCOSITY, bool(_opt(eqo, "use_grad_div_viscosity_term", False)))
             eng.set_option(L.OPT_GRAD_DEPTH_VISCOSITY, bool(_opt(eqo, "use_grad_depth_viscosity_term", True)))
+            eng.set_option(L.OPT_MOMENTUM_ADVECTION, not self._modesplit)
         else:
             eng.set_option(L.OPT_LF_TRACER, bool(_opt(eqo, "use_lax_friedrichs_tracer", False)))
             cons = False
@@ -324,6 +328,8 @@ class ERKGenericShuOsher:
             self._push_option("sipg", L.OPT_SIPG_FACTOR, _opt(eqo, "sipg_factor", None), 1.0)
             for name, fid in _SWE_FIELDS.items():
                 val = self.fields.get(name)
+                if self._modesplit and name not in _MODESPLIT_FIELDS:
+                    val = None      # ModeSplit2DEquations has no term that reads this field (shallowwater_eq.py:953-957)
                 if functions or val is None or not is_function(val):
                     self._set_field(fid, val, name)
             self._push_bcs(0, _SWE_TAGS)
