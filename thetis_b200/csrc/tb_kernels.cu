@@ -246,11 +246,10 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             if (tid == 33) prefetch_l2(prm.pl.halo_cnt + pf);
         }
     }
-    __syncthreads();          // mbarrier initialised (thread 0) before anybody waits on it
-    mbar_wait(bar, 0);        // every thread observes the TMA completion itself
     // patch halo: records of off-patch facet neighbours, copied asynchronously (LDGSTS).  The ids were requested at
-    // the top and have arrived while the bulk copies were in flight; the copies themselves land while the volume
-    // terms are evaluated and are only waited for in front of the facet loop.
+    // the top (their row was prefetched to L2 one wave earlier); the copies are issued as soon as the ids are here --
+    // while the bulk copies are still in flight -- and only waited for in front of the facet loop, so their latency
+    // hides behind the bulk-copy wait and the volume terms.
     // Element i of the halo block is double (i % 9) of halo cell (i / 9): S[TB_P*9 + i].
     {
         double *H = S + TB_P * 9;
@@ -265,6 +264,8 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         }
         cp_async_commit();
     }
+    __syncthreads();          // mbarrier initialised (thread 0) before anybody waits on it
+    mbar_wait(bar, 0);        // every thread observes the TMA completion itself
 
     // threads past the last owned cell of the last patch evaluate cell 0 of the patch again (uniform control flow:
     // there is a block-wide barrier in the middle) and their result is discarded
