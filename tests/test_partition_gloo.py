@@ -120,3 +120,128 @@ def test_halo_exchange_gloo(world):
     for r in range(world):
         eu, ee = out[r]
         assert eu < 1e-13 and ee < 1e-13, (r, eu, ee)
+
+
+# ---------------------------------------------------------------- SURVEY 8f rows on a partitioned mesh (CPU, gloo)
+def _local_oracle(mesh, part, bath_v, **kw):
+    """numpy oracle on a rank's local sub-mesh (owned + ghost cells); unknown facets of ghost cells become fake
+    closed facets -- they only affect the ghost cells' own (discarded) residuals"""
+    lm = part.mesh
+    lm2 = type(lm)(coords=lm.coords, cells=lm.cells, topo=lm.topo)
+    nbr = lm.nbr.copy().astype(np.int64)
+    unknown = nbr == np.iinfo(np.int32).min
+    nfake = int(unknown.sum())
+    nbr[unknown] = -(1 + lm.n_bfacets + np.arange(nfake))
+    lm2.nbr = nbr.astype(np.int32)
+    lm2.nbr_lf = lm.nbr_lf
+    cu, fu = np.nonzero(unknown)
+    lm2.bf_cell = np.concatenate([lm.bf_cell, cu]).astype(np.int32)
+    lm2.bf_lf = np.concatenate([lm.bf_lf, fu]).astype(np.int8)
+    lm2.bf_marker = np.concatenate([lm.bf_marker, np.full(nfake, 999)]).astype(np.int32)
+    gv = lm.meta["global_vertices"]
+    orc = O.SWEOracle(lm2, bath_v[gv][lm.cells], **kw)
+    orc.boundary_len = dict(mesh.boundary_length())
+    orc.boundary_len[999] = 1.0
+    return orc
+
+
+def _exchange(part, world, local):
+    """ghost rows of `local` (n_owned + n_ghost, 9) <- owners' rows, like HaloPlan.exchange"""
+    send_idx = np.concatenate([part.send_lists[q] for q in range(world) if q in part.send_lists]) \
+        if part.send_lists else np.zeros(0, np.int64)
+    sendbuf = torch.as_tensor(local[send_idx].copy())
+    ghost = torch.zeros((part.n_ghost, 9), dtype=torch.float64)
+    exchange_halo(part, sendbuf, ghost)
+    local[part.n_owned:] = ghost.numpy()
+
+
+def _worker_erk_visc(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mesh = _mesh()
+        part = partition_mesh(mesh, world)[rank]
+        uv, eta = _global_state(mesh)
+        bath_v = 30.0 + 5 * np.sin(mesh.coords[:, 0] / 7.0)
+        kw = dict(options=dict(use_grad_div_viscosity_term=True), fields={"viscosity_h": 0.8},
+                  bnd_conditions={100: {"elev": 0.3, "uv": (0.0, 0.0)}})
+        orc = _local_oracle(mesh, part, bath_v, **kw)
+        glob = np.concatenate([part.owned_global, part.ghost_global])
+        rec = np.concatenate([uv.reshape(-1, 6), eta], axis=1)
+        n_own = part.n_owned
+        U = rec[glob].copy()                       # owned + ghost records (ghosts start current, like upload())
+        a, b, c, _ = O.ERK_TABLEAUX["ERKLSPUM2"]
+        dt, nsteps = 0.02, 3
+
+        def tend(S):
+            ku, ke = orc.tendency(S[:, :6].reshape(-1, 3, 2), S[:, 6:], dt=dt)
+            K = np.zeros_like(S)
+            K[:n_own] = np.concatenate([ku.reshape(-1, 6), ke], axis=1)[:n_own]
+            _exchange(part, world, K)              # the tendency buffers are exchanged like state arrays
+            return K
+
+        for _ in range(nsteps):
+            Ks = []
+            for i in range(len(b)):
+                S = U + sum(a[i][j] * Ks[j] for j in range(i)) if i else U      # owned AND ghost rows (tb_lincomb)
+                if i < len(b) - 1:
+                    Ks.append(tend(S))
+                else:
+                    # last stage: new solution into a separate buffer, ghosts by exchange (rungekutta.ERKGeneric)
+                    ku, ke = orc.tendency(S[:, :6].reshape(-1, 3, 2), S[:, 6:], dt=dt)
+                    Kl = np.concatenate([ku.reshape(-1, 6), ke], axis=1)
+                    Un = np.zeros_like(U)
+                    Un[:n_own] = (U + sum(b[j] * Ks[j] for j in range(i)))[:n_own] + b[i] * Kl[:n_own]
+                    _exchange(part, world, Un)
+                    U = Un
+        out[rank] = (part.owned_global.copy(), U[:n_own].copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_butcher_erk_with_viscosity_gloo():
+    """Butcher-form ERK + SIPG viscosity on 2 ranks with a one-deep facet halo == the global run: the neighbour's
+    gradient needs the ghost cell's three nodal values and its geometry only, and exchanged tendencies make the
+    stage inputs of ghost cells current without an extra exchange"""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_erk_visc, args=(world, _free_port(), out), nprocs=world, join=True)
+    mesh = _mesh()
+    uv, eta = _global_state(mesh)
+    bath_v = 30.0 + 5 * np.sin(mesh.coords[:, 0] / 7.0)
+    gorc = O.SWEOracle(mesh, bath_v[mesh.cells], options=dict(use_grad_div_viscosity_term=True),
+                       fields={"viscosity_h": 0.8}, bnd_conditions={100: {"elev": 0.3, "uv": (0.0, 0.0)}})
+    a, b, c, _ = O.ERK_TABLEAUX["ERKLSPUM2"]
+    st = O.ButcherStepper(gorc, [uv, eta], 0.02, a, b, c)
+    for i in range(3):
+        st.advance(i * 0.02)
+    ref = np.concatenate([uv.reshape(-1, 6), eta], axis=1)
+    for r in range(world):
+        owned, U = out[r]
+        assert np.abs(U - ref[owned]).max() < 1e-13 * np.abs(ref).max()
+
+
+def _worker_allreduce(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from thetis_b200.parallel import HaloPlan
+        plan = HaloPlan(partition_mesh(_mesh(), world), rank)
+        t = torch.tensor([1.0 + rank, 10.0 * (rank + 1), 5.0 - rank, -3.0 + 2 * rank], dtype=torch.float64)
+        plan.allreduce(t, "ssmM")
+        out[rank] = t.numpy().copy()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_callback_allreduce_sum_min_max_gloo():
+    """device callbacks on a distributed mesh: integrals are summed, extrema are min / max-reduced (callback.py:477-481)"""
+    world = 3
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_allreduce, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        assert np.array_equal(out[r], np.array([1.0 + 2.0 + 3.0, 10.0 + 20.0 + 30.0, 3.0, 1.0]))
