@@ -208,6 +208,33 @@ int tb_scatter_cells(tb_ctx *ctx, const double *buf, const int32_t *idx, int64_t
  * pointers into peer GPUs' ghost blocks, e.g. from torch symmetric memory).  Replaces pack + all-to-all. */
 int tb_push_cells(tb_ctx *ctx, const double *state, const int32_t *idx, const uint64_t *dst_ptrs, int64_t n,
                   int rec_len, void *stream);
+/* Fused compute + halo exchange (the exchange hidden in every `self.solver.solve()` of the reference,
+ * rungekutta.py:940, PETSc SF halo update): ONE launch per RK stage evaluates the partition-boundary patches first,
+ * stores the records the peer ranks need straight into their ghost blocks from the kernel epilogue (NVLink peer
+ * stores) and publishes a per-peer epoch flag; the boundary patches of the next stage wait for the flags of the ranks
+ * they receive from.  No pack kernel, no collective, no host involvement; replayable from a CUDA graph. */
+typedef struct {
+    int64_t n_bpatch;            /* leading entries of patch_order that hold cells a peer needs        */
+    const int32_t *patch_order;  /* HOST [tb_n_patches] launch order, a permutation, boundary patches first */
+    const int32_t *push_ptr;     /* HOST [n_bpatch+1] CSR over those patches into the push entries     */
+    const int32_t *push_cell;    /* HOST [n_entries] cell index inside its patch, one entry per (cell, peer) */
+    int32_t n_recv, n_send;      /* <= 16 each                                                         */
+    int32_t recv_peer[16];       /* ranks this rank receives ghosts from (index into flags)            */
+    uint64_t remote_flag[16];    /* DEVICE address of flags[this rank] on every rank this rank sends to */
+    uint64_t flags;              /* DEVICE address of this rank's uint64 flags[world], zero-initialised, peer-writable */
+} tb_halo_fused;
+int tb_halo_fused_setup(tb_ctx *ctx, const tb_halo_fused *h);
+/* tb_swe_stage over all patches + push: push_dst is a DEVICE array [n_entries] of peer addresses (uint64) of the
+ * pushed records inside the peers' copies of THIS output buffer.  Every rank must issue the same sequence of fused
+ * launches. */
+int tb_swe_stage_fused(tb_ctx *ctx, double a0, double a1, double b_dt, const double *u_in, const double *u0,
+                       double *u_out, const uint64_t *push_dst, void *stream);
+/* Stream-ordered wait until the ghost records of the last fused launch have arrived from every peer: required in
+ * front of any other kernel that reads them (the tracer stage reads the frozen SWE state of its halo cells). */
+int tb_halo_fused_wait(tb_ctx *ctx, void *stream);
+/* Fused launches completed so far and whether a flag wait ever timed out (a peer stopped).  Synchronises. */
+int tb_halo_fused_status(tb_ctx *ctx, int64_t *epoch, int32_t *error);
+
 /* Restrict the next tb_swe_stage / tb_tracer_stage launches to patches
  * [first, first+count) (interior / partition-boundary split for overlap).
  * count < 0 resets to all patches. */

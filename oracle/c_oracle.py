@@ -38,7 +38,7 @@ class _Problem(C.Structure):
                 ("bf_flux", C.c_void_p), ("bf_len", C.c_void_p), ("bath", C.c_void_p), ("coriolis", C.c_void_p),
                 ("manning", C.c_void_p), ("linear_drag", C.c_double), ("g", C.c_double), ("lf_sigma", C.c_double),
                 ("eps2", C.c_double), ("nonlinear", C.c_int), ("lf_on", C.c_int), ("wd_on", C.c_int),
-                ("wd_alpha", C.c_double)]
+                ("wd_alpha", C.c_double), ("wind", C.c_void_p), ("rho0", C.c_double)]
 
 
 class COracle:
@@ -49,17 +49,21 @@ class COracle:
     """
 
     def __init__(self, mesh, bath, nonlinear=True, lf_on=True, g=9.81, coriolis=None, manning=None, linear_drag=0.0,
-                 bnd=None, bf_elev=None, norm_smoother=0.0, lf_sigma=1.0, threads=None, wd_on=False, wd_alpha=0.5):
+                 bnd=None, bf_elev=None, norm_smoother=0.0, lf_sigma=1.0, threads=None, wd_on=False, wd_alpha=0.5,
+                 wind_stress=None, rho0=1000.0):
         self.lib = C.CDLL(build())
         self.lib.swe_oracle_threads.restype = C.c_int
+        self.lib.swe_oracle_set_threads.argtypes = [C.c_int]
         if threads:
-            os.environ["OMP_NUM_THREADS"] = str(threads)
+            # explicit: an inherited OMP_NUM_THREADS (torchrun sets 1) must not decide the baseline's core count
+            self.lib.swe_oracle_set_threads(int(threads))
         nv, nt, nb = mesh.n_vertices, mesh.n_cells, mesh.n_bfacets
         full = lambda v: None if v is None else np.ascontiguousarray(np.broadcast_to(np.asarray(v, float), (nv,)))
         k = self._keep = dict(
             coords=np.ascontiguousarray(mesh.coords, np.float64), cells=np.ascontiguousarray(mesh.cells, np.int32),
             nbr=np.ascontiguousarray(mesh.nbr, np.int32), nbr_lf=np.ascontiguousarray(mesh.nbr_lf, np.int8),
             bath=full(bath), coriolis=full(coriolis), manning=full(manning),
+            wind=None if wind_stress is None else np.ascontiguousarray(np.broadcast_to(np.asarray(wind_stress, float), (nv, 2))),
             bf_opcode=np.zeros(max(nb, 1), np.int32), bf_elev=np.zeros((max(nb, 1), 2)), bf_uv=np.zeros((max(nb, 1), 4)),
             bf_un=np.zeros((max(nb, 1), 2)), bf_flux=np.zeros((max(nb, 1), 2)), bf_len=np.ones(max(nb, 1)))
         tags = {"elev": 1, "uv": 2, "un": 4, "flux": 8}
@@ -80,12 +84,13 @@ class COracle:
         p = self.p = _Problem()
         p.n_cells, p.n_vertices, p.n_bfacets = nt, nv, nb
         for name in ("coords", "cells", "nbr", "nbr_lf", "bf_opcode", "bf_elev", "bf_uv", "bf_un", "bf_flux", "bf_len",
-                     "bath", "coriolis", "manning"):
+                     "bath", "coriolis", "manning", "wind"):
             a = k[name]
             setattr(p, name, None if a is None else a.ctypes.data)
         p.linear_drag, p.g, p.lf_sigma, p.eps2 = float(linear_drag), float(g), float(lf_sigma), float(norm_smoother) ** 2
         p.nonlinear, p.lf_on = int(nonlinear), int(lf_on)
         p.wd_on, p.wd_alpha = int(wd_on), float(wd_alpha)
+        p.rho0 = float(rho0)
         self.nt = nt
 
     def threads(self):
@@ -109,6 +114,14 @@ class COracle:
         self.lib.swe_oracle_ssprk33(C.byref(self.p), C.c_double(dt), C.c_int(nsteps), C.c_void_p(state.ctypes.data),
                                     C.c_void_p(work.ctypes.data))
         return state
+
+
+def host_threads():
+    """Threads the timed CPU baseline may use: the cores this process is allowed to run on."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def records_from_nodal(uv, eta):

@@ -50,6 +50,8 @@ typedef struct {
     int nonlinear, lf_on;
     int wd_on;                 /* use_wetting_and_drying (utility.py:975-985) */
     double wd_alpha;
+    const double *wind;        /* [nv*2] wind stress or NULL (WindStressTerm, shallowwater_eq.py:643-649) */
+    double rho0;
 } swe_problem;
 
 static const double QL[6][3] = {
@@ -90,6 +92,7 @@ void swe_oracle_stage(const swe_problem *P, double a0, double a1, double bdt, co
     for (int64_t c = 0; c < P->n_cells; ++c) {
         const double *r = u + c * 9;
         double x[3], y[3], b[3], ux[3], uy[3], et[3], f[3] = {0, 0, 0}, mu[3] = {0, 0, 0};
+        double twx[3] = {0, 0, 0}, twy[3] = {0, 0, 0};
         for (int a = 0; a < 3; ++a) {
             const int32_t v = P->cells[c * 3 + a];
             x[a] = P->coords[2 * v];
@@ -97,6 +100,7 @@ void swe_oracle_stage(const swe_problem *P, double a0, double a1, double bdt, co
             b[a] = P->bath[v];
             if (P->coriolis) f[a] = P->coriolis[v];
             if (P->manning) mu[a] = P->manning[v];
+            if (P->wind) { twx[a] = P->wind[2 * v]; twy[a] = P->wind[2 * v + 1]; }
             ux[a] = r[2 * a];
             uy[a] = r[2 * a + 1];
             et[a] = r[6 + a];
@@ -140,6 +144,11 @@ void swe_oracle_stage(const swe_problem *P, double a0, double a1, double bdt, co
             if (P->linear_drag != 0.0) {
                 sx -= P->linear_drag * uq;
                 sy -= P->linear_drag * vq;
+            }
+            if (P->wind) {
+                /* +tau / (H rho0) */
+                sx += (l[0] * twx[0] + l[1] * twx[1] + l[2] * twx[2]) / (H * P->rho0);
+                sy += (l[0] * twy[0] + l[1] * twy[1] + l[2] * twy[2]) / (H * P->rho0);
             }
             for (int a = 0; a < 3; ++a) {
                 /* PG: +g*eta*div(psi) ; HUDiv: +grad(phi).(H u) */
@@ -280,6 +289,15 @@ void swe_oracle_ssprk33(const swe_problem *P, double dt, int nsteps, double *sta
         swe_oracle_stage(P, 1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0 * dt, C, state, B);
         memcpy(state, B, sizeof(double) * n);
     }
+}
+
+/* torchrun exports OMP_NUM_THREADS=1 to its children: the timed CPU baseline sets its thread count explicitly */
+void swe_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 int swe_oracle_threads(void) {

@@ -2,8 +2,8 @@
 import os, sys, cProfile, pstats, time
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import torch
-from thetis_b200.workloads import north_sea_mesh, north_sea_setup
-from thetis_b200.parallel import SingleSWE
+from harness.workloads import north_sea_mesh, north_sea_setup
+from harness.runs import SingleSWE
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 19
 mesh = north_sea_mesh(k)
 setup = north_sea_setup(mesh)

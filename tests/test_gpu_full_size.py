@@ -129,7 +129,7 @@ def test_config5_north_sea_4m_properties():
     to rounding (VolumeConservation2DCallback criterion) and stays finite"""
     import torch
     import thetis_b200._lib as L
-    from thetis_b200.workloads import north_sea_mesh, north_sea_setup, tide_values
+    from harness.workloads import north_sea_mesh, north_sea_setup, tide_values
     mesh = north_sea_mesh(19)
     assert mesh.n_cells == 3_942_120
     setup = north_sea_setup(mesh, wetting_drying=True)

@@ -28,29 +28,38 @@ def _worker(rank, world, port, k, nsteps, transport, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from thetis_b200.workloads import north_sea_mesh, north_sea_setup
-        from thetis_b200.parallel import PartitionedSWE
+        from harness.workloads import north_sea_mesh, north_sea_setup
+        from harness.runs import PartitionedSWE
         mesh = north_sea_mesh(k)
         setup = north_sea_setup(mesh, wetting_drying=True)
-        run = PartitionedSWE(mesh, setup, rank, world, wd=True, transport=transport)
-        assert run.transport == transport
+        fused = transport == "symm"
+        tr = "symm" if transport.startswith("symm") else transport
+        run = PartitionedSWE(mesh, setup, rank, world, wd=True, transport=tr, fused=fused)
+        assert run.transport == tr
         assert run.overlap
+        assert run.plan.fused == fused
         for _ in range(nsteps - 2):
             run.step_e2e()
         # the last two steps: one plain resident step, one replay of its CUDA graph (forcing frozen on both sides)
-        if transport == "symm":
+        if tr == "symm":
             run.enable_graph()            # runs one warm-up step, then captures
         else:
             run.step_resident()
         run.step_resident()
         torch.cuda.synchronize()
         uv, eta = run.owned_nodal()
+        if fused:
+            # 3 fused launches per step (the capture itself launches nothing), no flag wait timed out
+            epoch, err = run.eng.halo_fused_status()
+            assert err == 0 and epoch == 3 * nsteps, (epoch, err)
         out[rank] = (run.part.owned_global.copy(), uv, eta)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("transport", ["nccl", "symm"])
+# "symm": fused compute + halo push (tb_swe_stage_fused, per-peer epoch flags); "symm-unfused": boundary launch +
+# push kernel + cross-rank barrier; "nccl": pack + all-to-all
+@pytest.mark.parametrize("transport", ["nccl", "symm", "symm-unfused"])
 @pytest.mark.parametrize("world", [2])
 def test_partitioned_run_is_bit_identical(world, transport):
     import torch
@@ -61,8 +70,8 @@ def test_partitioned_run_is_bit_identical(world, transport):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), k, nsteps, transport, out), nprocs=world, join=True)
-    from thetis_b200.workloads import north_sea_mesh, north_sea_setup
-    from thetis_b200.parallel import SingleSWE
+    from harness.workloads import north_sea_mesh, north_sea_setup
+    from harness.runs import SingleSWE
     mesh = north_sea_mesh(k)
     setup = north_sea_setup(mesh, wetting_drying=True)
     single = SingleSWE(mesh, setup, wd=True)

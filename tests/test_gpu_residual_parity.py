@@ -204,7 +204,7 @@ def test_wetting_drying_residual():
 def test_config5_specialised_kernels(wd):
     """North-Sea physics (Manning + Coriolis + LF + tidal elevation array [+ wetting-drying]): SPEC 2 / SPEC 3 kernels"""
     import os
-    from thetis_b200.workloads import north_sea_mesh, north_sea_setup, tide_values
+    from harness.workloads import north_sea_mesh, north_sea_setup, tide_values
     mesh = north_sea_mesh(k=1)
     setup = north_sea_setup(mesh, wetting_drying=wd)
     tv = tide_values(setup, 1234.0)
@@ -300,7 +300,7 @@ def test_viscosity_toggle_rebuilds_patch_tables():
 @pytest.mark.parametrize("graddiv", [False, True])
 def test_config5_with_viscosity_specialised_kernels(wd, graddiv):
     """North-Sea physics + horizontal viscosity (examples/north_sea prescribes a viscosity sponge): SPEC 5 / SPEC 6"""
-    from thetis_b200.workloads import north_sea_mesh, north_sea_setup, tide_values
+    from harness.workloads import north_sea_mesh, north_sea_setup, tide_values
     mesh = north_sea_mesh(k=1)
     setup = north_sea_setup(mesh, wetting_drying=wd)
     tv = tide_values(setup, 4321.0)

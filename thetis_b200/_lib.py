@@ -32,6 +32,14 @@ class TbMesh(C.Structure):
     ]
 
 
+class TbHaloFused(C.Structure):
+    _fields_ = [
+        ("n_bpatch", C.c_int64), ("patch_order", C.c_void_p), ("push_ptr", C.c_void_p), ("push_cell", C.c_void_p),
+        ("n_recv", C.c_int32), ("n_send", C.c_int32), ("recv_peer", C.c_int32 * 16), ("remote_flag", C.c_uint64 * 16),
+        ("flags", C.c_uint64),
+    ]
+
+
 # every symbol include/thetis_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _D = C.c_double
@@ -56,6 +64,10 @@ SIGNATURES = {
     "tb_set_cell_quadrature": (_I, [_P, _I, _P, _P]),
     "tb_swe_stage": (_I, [_P, _D, _D, _D, _P, _P, _P, _P]),
     "tb_swe_tendency": (_I, [_P, _P, _P, _P]),
+    "tb_swe_stage_fused": (_I, [_P, _D, _D, _D, _P, _P, _P, _P, _P]),
+    "tb_halo_fused_setup": (_I, [_P, C.POINTER(TbHaloFused)]),
+    "tb_halo_fused_wait": (_I, [_P, _P]),
+    "tb_halo_fused_status": (_I, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "tb_tracer_stage": (_I, [_P, _D, _D, _D, _P, _P, _P, _P, _P]),
     "tb_limiter_apply": (_I, [_P, _P, _P]),
     "tb_state_from_fields": (_I, [_P, _P, _P, _P, _P, _P]),

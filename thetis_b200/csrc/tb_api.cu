@@ -83,6 +83,12 @@ struct tb_ctx {
     const int32_t *patch_list = nullptr;
     long long patch_list_n = 0;
     long long launches = 0;
+    // fused halo exchange (tb_halo_fused_setup)
+    bool fused_ready = false;
+    int fused_n_bpatch = 0;
+    TbHaloFused *d_fused = nullptr;
+    int32_t *d_fused_order = nullptr, *d_push_ptr = nullptr, *d_push_cell = nullptr;
+    unsigned long long *d_fused_epoch = nullptr;     // epoch (8 B), done counter (4 B), error flag (4 B)
     // limiter
     bool lim_ready = false;
     TbLimiterData lim{};
@@ -456,6 +462,11 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
         cudaFree(ctx->d_ext[k]);
         cudaFree(ctx->d_ext_tr[k]);
     }
+    cudaFree(ctx->d_fused);
+    cudaFree(ctx->d_fused_order);
+    cudaFree(ctx->d_push_ptr);
+    cudaFree(ctx->d_push_cell);
+    cudaFree(ctx->d_fused_epoch);
     cudaFree(ctx->d_v2c_ptr);
     cudaFree(ctx->d_v2b_ptr);
     cudaFree(ctx->d_v2c_idx);
@@ -664,8 +675,8 @@ static void patch_range(tb_ctx *ctx, long long &first, long long &count) {
     }
 }
 
-extern "C" int tb_swe_stage(tb_ctx *ctx, double a0, double a1, double b_dt, const double *u_in, const double *u0,
-                            double *u_out, void *stream) {
+static int swe_stage_impl(tb_ctx *ctx, double a0, double a1, double b_dt, const double *u_in, const double *u0,
+                          double *u_out, const unsigned long long *push_dst, void *stream) {
     if (!ctx || !u_in || !u_out) return fail(ctx, TB_ERR_ARG, "null state pointer");
     if (u_in == u_out) return fail(ctx, TB_ERR_ARG, "u_out must not alias u_in");
     if (a0 != 0.0 && !u0) return fail(ctx, TB_ERR_ARG, "u0 required when a0 != 0");
@@ -725,10 +736,100 @@ extern "C" int tb_swe_stage(tb_ctx *ctx, double a0, double a1, double b_dt, cons
         p.patch_first = 0;
         count = ctx->patch_list_n;
     }
+    if (push_dst) {
+        // one launch over all patches, partition-boundary patches first; they push their records to the peers
+        if (!ctx->fused_ready) return fail(ctx, TB_ERR_STATE, "tb_halo_fused_setup has not been called");
+        p.patch_list = ctx->d_fused_order;
+        p.patch_first = 0;
+        count = ctx->n_patches;
+        p.halo = ctx->d_fused;
+        p.push_dst = push_dst;
+        p.n_bpatch = ctx->fused_n_bpatch;
+    }
     const size_t smem = tb_swe_smem_bytes(ctx->pl);
     if (smem > 200 * 1024) return fail(ctx, TB_ERR_UNSUPPORTED, "patch halo too large for shared memory");
     CK(tb_launch_swe_stage(p, ctx->nonlinear != 0, (int)count, smem, (cudaStream_t)stream));
     ctx->launches += count > 0 ? 1 : 0;
+    return TB_OK;
+}
+
+extern "C" int tb_swe_stage(tb_ctx *ctx, double a0, double a1, double b_dt, const double *u_in, const double *u0,
+                            double *u_out, void *stream) {
+    return swe_stage_impl(ctx, a0, a1, b_dt, u_in, u0, u_out, nullptr, stream);
+}
+
+extern "C" int tb_swe_stage_fused(tb_ctx *ctx, double a0, double a1, double b_dt, const double *u_in, const double *u0,
+                                  double *u_out, const uint64_t *push_dst, void *stream) {
+    if (!push_dst) return fail(ctx, TB_ERR_ARG, "null push table");
+    return swe_stage_impl(ctx, a0, a1, b_dt, u_in, u0, u_out, reinterpret_cast<const unsigned long long *>(push_dst),
+                          stream);
+}
+
+extern "C" int tb_halo_fused_setup(tb_ctx *ctx, const tb_halo_fused *h) {
+    if (!ctx || !h) return fail(ctx, TB_ERR_ARG, "null argument");
+    if (h->n_bpatch < 0 || h->n_bpatch > ctx->n_patches || !h->patch_order || !h->flags ||
+        (h->n_bpatch > 0 && (!h->push_ptr || !h->push_cell)))
+        return fail(ctx, TB_ERR_ARG, "invalid fused halo description");
+    if (h->n_recv < 0 || h->n_recv > TB_MAX_PEERS || h->n_send < 0 || h->n_send > TB_MAX_PEERS)
+        return fail(ctx, TB_ERR_UNSUPPORTED, "more than 16 neighbouring ranks");
+    std::vector<char> seen(ctx->n_patches, 0);
+    for (long long k = 0; k < ctx->n_patches; ++k) {
+        const int32_t q = h->patch_order[k];
+        if (q < 0 || q >= ctx->n_patches || seen[q]) return fail(ctx, TB_ERR_ARG, "patch_order is not a permutation");
+        seen[q] = 1;
+    }
+    const long long ne = h->n_bpatch > 0 ? h->push_ptr[h->n_bpatch] : 0;
+    for (long long e = 0; e < ne; ++e)
+        if (h->push_cell[e] < 0 || h->push_cell[e] >= TB_P) return fail(ctx, TB_ERR_ARG, "push cell outside its patch");
+    CK(cudaDeviceSynchronize());
+    cudaFree(ctx->d_fused); cudaFree(ctx->d_fused_order); cudaFree(ctx->d_push_ptr); cudaFree(ctx->d_push_cell);
+    cudaFree(ctx->d_fused_epoch);
+    ctx->d_fused = nullptr; ctx->d_fused_order = ctx->d_push_ptr = ctx->d_push_cell = nullptr; ctx->d_fused_epoch = nullptr;
+    ctx->fused_ready = false;
+    CK(cudaMalloc(&ctx->d_fused_order, sizeof(int32_t) * ctx->n_patches));
+    CK(cudaMemcpy(ctx->d_fused_order, h->patch_order, sizeof(int32_t) * ctx->n_patches, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->d_push_ptr, sizeof(int32_t) * (h->n_bpatch + 1)));
+    CK(cudaMalloc(&ctx->d_push_cell, sizeof(int32_t) * std::max<long long>(ne, 1)));
+    if (h->n_bpatch > 0) {
+        CK(cudaMemcpy(ctx->d_push_ptr, h->push_ptr, sizeof(int32_t) * (h->n_bpatch + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_push_cell, h->push_cell, sizeof(int32_t) * ne, cudaMemcpyHostToDevice));
+    } else {
+        CK(cudaMemset(ctx->d_push_ptr, 0, sizeof(int32_t)));
+    }
+    CK(cudaMalloc(&ctx->d_fused_epoch, 16));
+    CK(cudaMemset(ctx->d_fused_epoch, 0, 16));
+    TbHaloFused hf;
+    memset(&hf, 0, sizeof(hf));
+    hf.epoch = ctx->d_fused_epoch;
+    hf.done_count = reinterpret_cast<unsigned int *>(ctx->d_fused_epoch + 1);
+    hf.error = reinterpret_cast<int *>(ctx->d_fused_epoch + 1) + 1;
+    hf.flags = reinterpret_cast<const unsigned long long *>(h->flags);
+    hf.push_ptr = ctx->d_push_ptr;
+    hf.push_cell = ctx->d_push_cell;
+    hf.n_recv = h->n_recv;
+    hf.n_send = h->n_send;
+    for (int q = 0; q < h->n_recv; ++q) hf.recv_peer[q] = h->recv_peer[q];
+    for (int q = 0; q < h->n_send; ++q) hf.remote_flag[q] = reinterpret_cast<unsigned long long *>(h->remote_flag[q]);
+    CK(cudaMalloc(&ctx->d_fused, sizeof(TbHaloFused)));
+    CK(cudaMemcpy(ctx->d_fused, &hf, sizeof(hf), cudaMemcpyHostToDevice));
+    ctx->fused_n_bpatch = (int)h->n_bpatch;
+    ctx->fused_ready = true;
+    return TB_OK;
+}
+
+extern "C" int tb_halo_fused_wait(tb_ctx *ctx, void *stream) {
+    if (!ctx || !ctx->fused_ready) return fail(ctx, TB_ERR_STATE, "tb_halo_fused_setup has not been called");
+    CK(tb_launch_halo_fused_wait(ctx->d_fused, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return TB_OK;
+}
+
+extern "C" int tb_halo_fused_status(tb_ctx *ctx, int64_t *epoch, int32_t *error) {
+    if (!ctx || !ctx->fused_ready) return fail(ctx, TB_ERR_STATE, "tb_halo_fused_setup has not been called");
+    unsigned long long h[2];
+    CK(cudaMemcpy(h, ctx->d_fused_epoch, 16, cudaMemcpyDeviceToHost));      // synchronises
+    if (epoch) *epoch = (int64_t)h[0];
+    if (error) *error = (int32_t)(h[1] >> 32);
     return TB_OK;
 }
 

@@ -58,6 +58,24 @@ struct TbPatchLayout {
     const int *halo_cnt;         // [n_patches]
 };
 
+// Fused halo exchange of the distributed SWE stage (tb_swe_stage_fused): the CTAs of the first n_bpatch patches of
+// the launch order hold every cell a peer rank needs.  They (1) wait until every peer they receive from has published
+// the ghost records of the stage input (per-peer flag >= epoch), (2) evaluate their patch, (3) store the records the
+// peers need straight into the peers' ghost blocks (NVLink peer stores) and (4) the last of them to finish publishes
+// epoch + 1 in every receiving peer's flag array.  Device-resident so that a captured CUDA graph replays correctly.
+#define TB_MAX_PEERS 16
+struct TbHaloFused {
+    unsigned long long *epoch;         // [1] fused stage launches completed by this rank
+    unsigned int *done_count;          // [1] boundary CTAs of the running launch that finished their push
+    int *error;                        // [1] set when a flag wait timed out
+    const unsigned long long *flags;   // [world] local: flags[q] = epochs published by peer q
+    const int *push_ptr;               // [n_bpatch+1] CSR over the boundary CTAs of the launch order
+    const int *push_cell;              // [n_entries] cell index inside the patch
+    int n_recv, n_send;
+    int recv_peer[TB_MAX_PEERS];                   // ranks whose flags this rank waits for
+    unsigned long long *remote_flag[TB_MAX_PEERS]; // &flags[my rank] on every rank this rank sends to
+};
+
 struct TbSweParams {
     const double *u_in;
     const double *u0;
@@ -71,6 +89,9 @@ struct TbSweParams {
     int lf_on, wd_on, use_quad, nquad;
     int force_generic, adv_on;    // developer switch: always run the generic (SPEC 0) kernel; momentum advection on/off
     double *partials;             // optional [n_patches][4]: fused diagnostics of u_out (int eta^2, |u|^2, eta, eta+b)
+    const TbHaloFused *halo;      // optional (device): fused halo exchange, CTAs [0, n_bpatch) push
+    const unsigned long long *push_dst;   // [n_entries] peer addresses of the pushed records for THIS output buffer
+    int n_bpatch, pad1_;
     TbCoef cor, man, cd, lin, wind, pa, msrc, vsrc, visc;
     double sipg;                  // sipg_factor (HorizontalViscosityTerm, shallowwater_eq.py:558)
     int graddiv, graddepth;       // use_grad_div_viscosity_term, use_grad_depth_viscosity_term
@@ -126,6 +147,7 @@ cudaError_t tb_launch_scatter_cells(const double *buf, const int32_t *idx, long 
                                     cudaStream_t s);
 cudaError_t tb_launch_push_cells(const double *state, const int32_t *idx, const unsigned long long *dst, long long n,
                                  int rec, cudaStream_t s);
+cudaError_t tb_launch_halo_fused_wait(const TbHaloFused *hf, cudaStream_t s);
 cudaError_t tb_launch_patch_partials_final(const double *partial, long long n, double *out, cudaStream_t s);
 cudaError_t tb_launch_swe_integrals(const double *state, const double *area, const double *bath3, long long n_owned,
                                     double *partial, double *out, cudaStream_t s);

@@ -205,6 +205,26 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
     const long long cell0 = (long long)patch * TB_P;
     const int NV = prm.pl.NV;
 
+    // Distributed run, partition-boundary patch: the ghost records this patch reads were stored by the peers' previous
+    // stage launch; wait until every peer has published them (TbHaloFused).  The boundary patches are the first CTAs
+    // of the launch and their peers pushed early in THEIR previous launch, so the wait is normally already satisfied.
+    const bool bpatch = prm.halo != nullptr && (int)blockIdx.x < prm.n_bpatch;
+    unsigned long long epoch = 0;
+    if (bpatch) {
+        const TbHaloFused *hf = prm.halo;
+        epoch = *hf->epoch;
+        const long long t0 = clock64();
+        for (int q = 0; q < hf->n_recv; ++q) {
+            const unsigned long long *f = hf->flags + hf->recv_peer[q];
+            while (ld_acquire_sys(f) < epoch) {
+                if (clock64() - t0 > 6000000000ll) {      // ~3 s: a peer died; do not hang the GPU
+                    *hf->error = 1;
+                    break;
+                }
+            }
+        }
+    }
+
     // Speculative, mutually independent global loads first (one DRAM latency instead of a chain of three): the halo
     // count and the ids this thread will need (rows of halo_ids are padded to NH valid entries).
     const int *hid = prm.pl.halo_ids + (long long)patch * prm.pl.NH;
@@ -838,6 +858,29 @@ TB_UNROLL(TB_GP_UNROLL)
         for (int w = 1; w < TB_P / 32; ++w) r += red[w * 4 + k];
         prm.partials[(long long)patch * 4 + k] = r;
     }
+    if (bpatch) {
+        // fused halo push: the records the peers need go from shared memory straight into their ghost blocks
+        // (consecutive threads store consecutive doubles of a record: 72-byte runs over NVLink)
+        const TbHaloFused *hf = prm.halo;
+        const int e0 = __ldg(hf->push_ptr + blockIdx.x), n9 = (__ldg(hf->push_ptr + blockIdx.x + 1) - e0) * 9;
+        for (int i = tid; i < n9; i += TB_P) {
+            const int ent = i / 9, k = i - ent * 9;
+            double *dst = reinterpret_cast<double *>(__ldg(prm.push_dst + e0 + ent));
+            dst[k] = O[__ldg(hf->push_cell + e0 + ent) * 9 + k];
+        }
+        __threadfence_system();          // this thread's peer stores are ordered before the signal below
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int done = atomicAdd(hf->done_count, 1u);
+            if (done == (unsigned int)prm.n_bpatch - 1u) {
+                // every boundary CTA of this launch has pushed: publish the new epoch to the receiving peers
+                *hf->done_count = 0u;
+                __threadfence_system();
+                for (int q = 0; q < hf->n_send; ++q) st_release_sys(hf->remote_flag[q], epoch + 1ull);
+                *hf->epoch = epoch + 1ull;
+            }
+        }
+    }
 }
 
 size_t tb_swe_smem_bytes(const TbPatchLayout &pl) {
@@ -1001,6 +1044,28 @@ cudaError_t tb_launch_gather_cells(const double *state, const int32_t *idx, long
 cudaError_t tb_launch_scatter_cells(const double *buf, const int32_t *idx, long long n, int rec, double *state,
                                     cudaStream_t s) {
     if (n) scatter_cells_kernel<<<nblk(n * rec, 256), 256, 0, s>>>(buf, idx, n, rec, state);
+    return cudaGetLastError();
+}
+
+// Stream-ordered wait for the fused halo exchange: returns when every peer this rank receives from has published the
+// ghost records of the last fused stage launch (needed in front of any OTHER kernel that reads those ghost records,
+// e.g. the tracer stage reading the frozen SWE state).
+__global__ void halo_fused_wait_kernel(const TbHaloFused *hf) {
+    const unsigned long long epoch = *hf->epoch;
+    const int q = threadIdx.x;
+    if (q < hf->n_recv) {
+        const unsigned long long *f = hf->flags + hf->recv_peer[q];
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < epoch) {
+            if (clock64() - t0 > 6000000000ll) {
+                *hf->error = 1;
+                break;
+            }
+        }
+    }
+}
+cudaError_t tb_launch_halo_fused_wait(const TbHaloFused *hf, cudaStream_t s) {
+    halo_fused_wait_kernel<<<1, 32, 0, s>>>(hf);
     return cudaGetLastError();
 }
 

@@ -152,6 +152,33 @@ class Engine:
     def swe_stage(self, a0, a1, b_dt, u_in, u0, u_out):
         self._ck(self.lib.tb_swe_stage(self.ctx, a0, a1, b_dt, _ptr(u_in), _ptr(u0), _ptr(u_out), self.stream))
 
+    def swe_stage_fused(self, a0, a1, b_dt, u_in, u0, u_out, push_dst):
+        """stage kernel over all patches, boundary patches first, halo push from the epilogue (tb_swe_stage_fused)"""
+        self._ck(self.lib.tb_swe_stage_fused(self.ctx, a0, a1, b_dt, _ptr(u_in), _ptr(u0), _ptr(u_out), _ptr(push_dst),
+                                             self.stream))
+
+    def halo_fused_setup(self, order, push_ptr, push_cell, recv_peers, remote_flags, flags_ptr):
+        h = L.TbHaloFused()
+        keep = [np.ascontiguousarray(order, np.int32), np.ascontiguousarray(push_ptr, np.int32),
+                np.ascontiguousarray(push_cell if len(push_cell) else [0], np.int32)]
+        h.n_bpatch = len(push_ptr) - 1
+        h.patch_order, h.push_ptr, h.push_cell = (a.ctypes.data for a in keep)
+        h.n_recv, h.n_send = len(recv_peers), len(remote_flags)
+        for i, q in enumerate(recv_peers):
+            h.recv_peer[i] = int(q)
+        for i, a in enumerate(remote_flags):
+            h.remote_flag[i] = int(a)
+        h.flags = int(flags_ptr)
+        self._ck(self.lib.tb_halo_fused_setup(self.ctx, C.byref(h)))
+
+    def halo_fused_wait(self):
+        self._ck(self.lib.tb_halo_fused_wait(self.ctx, self.stream))
+
+    def halo_fused_status(self):
+        ep, err = C.c_int64(), C.c_int32()
+        self._ck(self.lib.tb_halo_fused_status(self.ctx, C.byref(ep), C.byref(err)))
+        return int(ep.value), int(err.value)
+
     def swe_tendency(self, u, k_out):
         self._ck(self.lib.tb_swe_tendency(self.ctx, _ptr(u), _ptr(k_out), self.stream))
 

@@ -13,8 +13,8 @@ contiguous, so the receive side needs no unpack).
 Cells are evaluated from their own side only, so the result of an owned cell does
 not depend on who owns its neighbours: an N-GPU run is bit-identical to the 1-GPU run.
 
-Also holds the two bench drivers (`SingleSWE`, `PartitionedSWE`) that bench.py,
-the GPU tests and __graft_entry__.smoke() share.
+The bench / test drivers built on top of this (`SingleSWE`, `PartitionedSWE`,
+`ConfigRun`) live in the top-level `harness/` package, outside the product.
 """
 from __future__ import annotations
 
@@ -22,7 +22,7 @@ import numpy as np
 
 from .mesh import Mesh2D, FACET_NODES
 
-__all__ = ["LocalPart", "partition_mesh", "SingleSWE", "PartitionedSWE", "exchange_halo"]
+__all__ = ["LocalPart", "partition_mesh", "HaloPlan", "distribute_mesh", "exchange_halo"]
 
 INT32_MIN = np.iinfo(np.int32).min
 
@@ -164,12 +164,13 @@ class HaloPlan:
     boundary-first / interior-overlapped launch of the SWE stage kernel.
     """
 
-    def __init__(self, parts, rank, transport="auto", overlap=True):
+    def __init__(self, parts, rank, transport="auto", overlap=True, fused=True):
         self.parts = parts
         self.part = parts[rank]
         self.rank, self.world = rank, len(parts)
         self.requested_transport = transport
         self.want_overlap = overlap
+        self.requested_fused = fused
         self.transport = None
         self.engine = None
         self.overlap = False
@@ -203,6 +204,9 @@ class HaloPlan:
                 if self.requested_transport == "symm":
                     raise
                 self.symm_error = repr(exc)
+        self.fused = False
+        if self.transport == "symm" and self.requested_fused:
+            self._setup_fused(send_idx, P)
         if self.want_overlap and self.n_send:
             bp = np.unique(send_idx // P)
             mask = np.zeros(engine.n_patches, dtype=bool)
@@ -213,6 +217,36 @@ class HaloPlan:
             self._ev_b = torch.cuda.Event()
             self._ev_x = torch.cuda.Event()
             self.overlap = self._plist_b.numel() > 0 and self._plist_i.numel() > 0
+
+    def _setup_fused(self, send_idx, P):
+        """Tables of the fused compute + halo-push launch (tb_swe_stage_fused): launch order with the partition-
+        boundary patches first, per-patch push entries, and the per-peer epoch flags in symmetric memory."""
+        import torch.distributed as dist
+        torch, eng, p = self.torch, self.engine, self.part
+        bp = np.unique(send_idx // P).astype(np.int64)
+        mask = np.zeros(eng.n_patches, dtype=bool)
+        mask[bp] = True
+        order = np.concatenate([bp, np.nonzero(~mask)[0]]).astype(np.int32)
+        pos = np.full(eng.n_patches, -1, dtype=np.int64)
+        pos[bp] = np.arange(bp.shape[0])
+        # entries in the order `alloc` computes the destination addresses (peer by peer), then grouped by patch
+        key = pos[send_idx // P]
+        self._push_perm = np.argsort(key, kind="stable")
+        cnt = np.bincount(key, minlength=bp.shape[0]) if send_idx.size else np.zeros(0, np.int64)
+        push_ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+        push_cell = (send_idx % P)[self._push_perm].astype(np.int32)
+        nflag = max(self.world, 4)
+        self._flags = self._symm_mem.empty(nflag, dtype=torch.int64, device=eng.device)
+        self._flags.zero_()
+        self._flags_hdl = self._symm_mem.rendezvous(self._flags, dist.group.WORLD)
+        ptrs = [int(x) for x in self._flags_hdl.buffer_ptrs]
+        send_peers = [q for q in range(self.world) if q in p.send_lists and p.send_lists[q].shape[0]]
+        recv_peers = [q for q in range(self.world) if p.recv_counts[q] > 0]
+        eng.halo_fused_setup(order, push_ptr, push_cell, recv_peers, [ptrs[q] + 8 * self.rank for q in send_peers],
+                             ptrs[self.rank])
+        torch.cuda.synchronize(eng.device)
+        dist.barrier()            # every rank's flags are zeroed and registered before anybody publishes into them
+        self.fused = True
 
     def _alloc_symmetric(self, rec, nbuf):
         import torch.distributed as dist
@@ -252,6 +286,11 @@ class HaloPlan:
             e += n
         grp = dict(L=L, tensor=t, handle=hdl,
                    dst_ptrs=[torch.as_tensor(dst[b].view(np.int64)).to(eng.device) for b in range(nbuf)])
+        if self.fused and rec == 9:
+            # the same addresses grouped by patch, for the fused launch's epilogue push
+            grp["push_dst"] = [torch.as_tensor(dst[b][:self.n_send][self._push_perm].view(np.int64).copy()).to(eng.device)
+                               if self.n_send else torch.zeros(1, dtype=torch.int64, device=eng.device)
+                               for b in range(nbuf)]
         gid = len(self._groups)
         self._groups[gid] = grp
         for b, bt in enumerate(bufs):
@@ -276,9 +315,16 @@ class HaloPlan:
         ghost = state[g0:g0 + p.n_ghost * rec].view(-1, rec)
         exchange_halo(p, sb[:self.n_send], ghost)
 
-    def swe_stage(self, a0, a1, bdt, src, u0, dst):
-        """Stage kernel + halo exchange of its output; boundary patches first so the exchange overlaps the rest."""
+    def swe_stage(self, a0, a1, bdt, src, u0, dst, fused=True):
+        """Stage kernel + halo exchange of its output; boundary patches first so the exchange overlaps the rest.
+        ``fused``: one launch that pushes from its epilogue and signals per-peer flags (safe when ghost blocks are
+        only ever read by stage launches, i.e. the Shu-Osher integrators); otherwise boundary launch + push kernel +
+        cross-rank barrier."""
         eng, torch = self.engine, self.torch
+        if fused and self.fused:
+            rec, gid, b = self._buf_info[dst.data_ptr()]
+            eng.swe_stage_fused(a0, a1, bdt, src, u0, dst, self._groups[gid]["push_dst"][b])
+            return
         if not self.overlap:
             eng.swe_stage(a0, a1, bdt, src, u0, dst)
             self.exchange(dst)
@@ -300,7 +346,14 @@ class HaloPlan:
         eng.set_patch_list(None)
         main.wait_event(self._ev_x)                              # boundary patches + ghosts of dst are complete
 
+    def wait_ghosts(self):
+        """Stream-ordered: the ghost records written by the peers' last fused stage launch have arrived."""
+        if self.fused:
+            self.engine.halo_fused_wait()
+
     def kernels_per_swe_stage(self):
+        if self.fused:
+            return 1
         return (2 if self.overlap else 1) + (1 if self.n_send else 0)
 
     def allreduce_sum(self, t):
@@ -320,7 +373,7 @@ class HaloPlan:
         return t
 
 
-def distribute_mesh(mesh: Mesh2D, rank=None, world=None, halo="vertex", transport="auto", overlap=True):
+def distribute_mesh(mesh: Mesh2D, rank=None, world=None, halo="vertex", transport="auto", overlap=True, fused=True):
     """
     This rank's share of `mesh` as a shim mesh (owned cells first, then ghosts) carrying a `HaloPlan`; the
     integrators, the limiter and FlowSolver2d pick the plan up from the mesh.  Analogue of Firedrake distributing a
@@ -336,198 +389,6 @@ def distribute_mesh(mesh: Mesh2D, rank=None, world=None, halo="vertex", transpor
     lm = parts[rank].mesh
     sm = ShimMesh(lm)
     sm.boundary_len = dict(lm.meta["global_boundary_len"])     # boundary lengths are global sums (utility.py:821-832)
-    sm.halo_plan = HaloPlan(parts, rank, transport=transport, overlap=overlap)
+    sm.halo_plan = HaloPlan(parts, rank, transport=transport, overlap=overlap, fused=fused)
     sm.global_mesh = mesh
     return sm
-
-
-# ---------------------------------------------------------------------- bench drivers
-def _make_solver(mesh, setup, wd, n_owned=None):
-    """FlowSolver2d mirror configured for the North Sea workload (thetis_b200/workloads.py)."""
-    from . import solver2d
-    from .shim import Function, FunctionSpace, Constant, ShimMesh, as_shim_mesh
-    sm = mesh if isinstance(mesh, ShimMesh) else as_shim_mesh(mesh)
-    P1 = FunctionSpace(sm, "CG", 1)
-    bath = Function(P1, name="Bathymetry")
-    bath.dat.data[:] = setup["bath"]
-    s = solver2d.FlowSolver2d(sm, bath)
-    o = s.options
-    o.swe_timestepper_type = "SSPRK33"
-    o.swe_timestepper_options.use_automatic_timestep = False
-    o.timestep = setup["dt"]
-    o.simulation_end_time = 1e30
-    o.simulation_export_time = 1e30
-    o.use_wetting_and_drying = bool(wd)
-    o.wetting_and_drying_alpha = Constant(setup["wd_alpha"])
-    man = Function(P1, name="Manning coefficient")
-    man.dat.data[:] = setup["manning"]
-    cor = Function(P1, name="Coriolis forcing")
-    cor.dat.data[:] = setup["coriolis"]
-    o.manning_drag_coefficient = man
-    o.coriolis_frequency = cor
-    o.horizontal_velocity_scale = Constant(1.5)
-    tide = Function(P1, name="Tidal elevation")
-    s.bnd_functions["shallow_water"] = {100: {"elev": tide, "uv": Constant((0.0, 0.0))}}
-    return s, tide
-
-
-class SingleSWE:
-    """North Sea workload on one GPU through the reference-shaped surface."""
-
-    def __init__(self, mesh, setup, wd=True):
-        import torch
-        from .workloads import M2_PERIOD
-        self.torch = torch
-        self.solver, self.tide = _make_solver(mesh, setup, wd)
-        mesh = self.solver.mesh2d.topology_mesh          # local Mesh2D (whole mesh on one GPU)
-        self.mesh, self.setup = mesh, setup
-        s = self.solver
-        s.create_function_spaces()
-        s.create_equations()
-        uv0 = setup["uv0"]
-        eta0 = setup["eta0"]
-        s.initialize()
-        s.fields.uv_2d.dat.data[:] = uv0.reshape(-1, 2)
-        s.fields.elev_2d.dat.data[:] = eta0.reshape(-1)
-        s.timestepper.initialize(s.fields.solution_2d)
-        self.ts = s.timestepper
-        self.eng = self.ts.engine
-        self.t = 0.0
-        self.dt = setup["dt"]
-        # open-boundary vertices of the P1 tide Function and their phase (host-side forcing, like TPXO in the demo)
-        m = mesh
-        open_f = m.bf_marker == 100
-        nodes = m.cells[m.bf_cell[open_f][:, None], FACET_NODES[m.bf_lf[open_f]]]      # geometric vertices (nb_open, 2)
-        self._tide_nodes = m.topo[nodes].reshape(-1)
-        self._tide_phase = setup["tide_phase"][open_f].reshape(-1)
-        self._omega = 2 * np.pi / M2_PERIOD
-        self._n_open = int(open_f.sum())
-        self._norms = torch.zeros(4, dtype=torch.float64, device=self.eng.device)
-        self._norms_host = torch.zeros(4, dtype=torch.float64).pin_memory()
-        self.update_forcings(0.0)
-        self.ts._push_dynamic()
-
-    def update_forcings(self, t):
-        """user callback of iterate(update_forcings=...): set the tidal elevation Function at time t"""
-        self.tide.dat.data[self._tide_nodes] = np.sin(self._omega * t + self._tide_phase)
-
-    def n_owned(self):
-        return self.mesh.n_cells
-
-    def stage_launches_per_step(self):
-        return 3
-
-    def launches_per_step(self):
-        return 3
-
-    def enable_graph(self):
-        """Capture one resident step (3 fused stage launches + halo traffic) in a CUDA graph."""
-        torch = self.torch
-        self.ts.advance_device()                 # warm-up outside capture (lazy uploads)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.ts.advance_device()
-        self._graph = g
-
-    def use_fused_norms(self, on=True):
-        """e2e path: the print_state norms are reduced in the epilogue of the last RK stage (tb_stage_integrals) instead
-        of by a separate pass over the state.  Call before `enable_stage_graphs`."""
-        self.ts.fused_norms = self._norms if on else None
-
-    def enable_stage_graphs(self):
-        """One CUDA graph per RK stage for the e2e path: the host-side forcing refresh stays between the launches."""
-        torch, ts = self.torch, self.ts
-        ts.advance_device()
-        torch.cuda.synchronize()
-        self._stage_graphs = []
-        for i in range(ts.n_stages):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                ts._launch_stage(i)
-            self._stage_graphs.append(g)
-        ts.stage_graphs = self._stage_graphs     # SSPRK33.solve_stage replays them instead of re-launching
-
-    def launches(self):
-        return self.eng.launch_count() + getattr(self, "_replays", 0) * self.launches_per_step()
-
-    def step_resident(self):
-        g = getattr(self, "_graph", None)
-        if g is not None:
-            g.replay()
-            self._replays = getattr(self, "_replays", 0) + 1
-        else:
-            self.ts.advance_device()
-
-    def step_e2e(self):
-        self.ts.advance(self.t, self.update_forcings)
-        if getattr(self.ts, "stage_graphs", None):
-            self._replays = getattr(self, "_replays", 0) + 1
-        self.t += self.dt
-        if self.ts.fused_norms is None:
-            self.eng.swe_integrals(self.ts.device_state(), self._norms)
-        self._norms_host.copy_(self._norms, non_blocking=True)   # else: reduced by the last stage (tb_stage_integrals)
-
-    def e2e_path(self):
-        return ("FlowSolver2d mirror -> SSPRK33.advance(t, update_forcings) -> C-ABI: tidal elevation Function updated "
-                "on the host every stage (H2D from pinned memory), print_state norms reduced on the device (fused "
-                "into the last stage kernel) and read back every step")
-
-    def h2d_bytes_per_step(self):
-        return 3 * self._n_open * 2 * 8
-
-    def d2h_bytes_per_step(self):
-        return 4 * 8
-
-    def state_nodal(self):
-        self.ts._host_stale = True
-        self.ts.sync_to_host()
-        s = self.solver
-        return (s.fields.uv_2d.dat.data_ro.reshape(-1, 3, 2).copy(), s.fields.elev_2d.dat.data_ro.reshape(-1, 3).copy())
-
-
-def localize_setup(setup, lm):
-    """Restrict the global workload arrays (thetis_b200.workloads.north_sea_setup) to a rank's local mesh."""
-    gv, gc, gb = lm.meta["global_vertices"], lm.meta["global_cells"], lm.meta["global_bfacets"]
-    out = dict(setup)
-    for k in ("bath", "coriolis", "manning"):
-        out[k] = setup[k][gv]
-    for k in ("eta0", "uv0"):
-        out[k] = setup[k][gc]
-    out["tide_phase"] = setup["tide_phase"][gb]
-    return out
-
-
-class PartitionedSWE(SingleSWE):
-    """
-    North Sea workload on `world` GPUs through the SAME reference-shaped surface as `SingleSWE` (FlowSolver2d mirror
-    -> SSPRK33): the mesh is distributed with `distribute_mesh`, the integrator picks the rank's HaloPlan up from it
-    and exchanges the one-deep halo once per RK stage.
-    """
-
-    def __init__(self, mesh, setup, rank, world, wd=True, transport="auto", overlap=True, halo="facet"):
-        self.rank, self.world = rank, world
-        sm = distribute_mesh(mesh, rank, world, halo=halo, transport=transport, overlap=overlap)
-        self.part = sm.halo_plan.part
-        super().__init__(sm, localize_setup(setup, self.part.mesh), wd=wd)
-        self.plan = sm.halo_plan
-        self.transport = self.plan.transport
-        self.overlap = self.plan.overlap
-
-    def n_owned(self):
-        return self.part.n_owned
-
-    def stage_launches_per_step(self):
-        return 3 * (2 if self.plan.overlap else 1)
-
-    def launches_per_step(self):
-        return 3 * self.plan.kernels_per_swe_stage()
-
-    def e2e_path(self):
-        return ("distribute_mesh -> " + SingleSWE.e2e_path(self) + "; one halo exchange per RK stage ("
-                + self.plan.transport + ")")
-
-    def owned_nodal(self):
-        uv, eta = self.state_nodal()
-        n = self.part.n_owned
-        return uv[:n], eta[:n]

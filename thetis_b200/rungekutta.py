@@ -491,6 +491,8 @@ class ERKGenericShuOsher:
         if sw is not None and uv_f is not None and any(uv_f is s for s in sw.solution.subfunctions):
             if not sw._host_stale and sw._host_changed():
                 sw.upload()
+            if sw.halo is not None:
+                sw.halo.wait_ghosts()         # the tracer kernel reads the SWE records of its halo cells
             return sw.device_state()
         # tracer-only run: velocity / elevation come from host Functions
         if uv_f is None:
@@ -637,7 +639,9 @@ class ERKGeneric(ERKGenericShuOsher):
         eng = self.engine
         if self._kind == "swe":
             if self.halo is not None:
-                self.halo.swe_stage(a0, 0.0, bdt, src, u0, dst)
+                # not the fused push: the ghost blocks of the tendency buffers are also read by the stage
+                # combinations (tb_lincomb), which the per-peer flags of the fused launch do not order
+                self.halo.swe_stage(a0, 0.0, bdt, src, u0, dst, fused=False)
             else:
                 eng.swe_stage(a0, 0.0, bdt, src, u0, dst)
         else:
