@@ -80,8 +80,9 @@ typedef enum {
     TB_OPT_GRAD_DIV_VISCOSITY = 14,    /* use_grad_div_viscosity_term (options.py:597)              */
     TB_OPT_GRAD_DEPTH_VISCOSITY = 15,  /* use_grad_depth_viscosity_term (options.py:602), default on */
     TB_OPT_TRACER_CONSERVATIVE = 16,   /* tracer use_conservative_form (options.py:543; tracer_eq_2d.py:323-437) */
-    TB_OPT_MOMENTUM_ADVECTION = 17     /* 0: no HorizontalAdvectionTerm although the depth is nonlinear
+    TB_OPT_MOMENTUM_ADVECTION = 17,    /* 0: no HorizontalAdvectionTerm although the depth is nonlinear
                                           (ModeSplit2DEquations, shallowwater_eq.py:931-966); default 1 */
+    TB_OPT_VON_KARMAN = 18             /* physical_constants['von_karman'] (Nikuradse drag, shallowwater_eq.py:696) */
 } tb_option;
 
 /* Coefficient fields: the `fields` dict of solver2d.py:546-558 plus bathymetry. */
@@ -98,7 +99,10 @@ typedef enum {
     TB_F_TRACER_SOURCE = 9,    /* 'source-<label>' of the tracer equation         */
     TB_F_VISCOSITY = 10,       /* 'viscosity_h' (HorizontalViscosityTerm, shallowwater_eq.py:554-616) */
     TB_F_DIFFUSIVITY = 11,     /* 'diffusivity_h-<label>' (HorizontalDiffusionTerm, tracer_eq_2d.py:226-278) */
-    TB_F_COUNT = 12
+    TB_F_NIKURADSE = 12,       /* 'nikuradse_bed_roughness' (QuadraticDragTerm, shallowwater_eq.py:689-697) */
+    TB_F_WD_ALPHA = 13,        /* wetting_and_drying_alpha as a P1 Function (solver2d.py:279-287, utility.py:981-983);
+                                  overrides TB_OPT_WD_ALPHA in the shallow-water stage */
+    TB_F_COUNT = 14
 } tb_field;
 
 /* Boundary tags (shallowwater_eq.py:243-267); a marker's opcode is the OR of
@@ -124,12 +128,26 @@ int tb_set_option(tb_ctx *ctx, int option, double value);
 int tb_set_field_const(tb_ctx *ctx, int field, const double *value, int ncomp);
 /* P1 coefficient given at the geometric vertices, HOST [n_vertices*ncomp] */
 int tb_set_field_vertex(tb_ctx *ctx, int field, const double *values, int ncomp);
+/* Genuinely discontinuous P1DG coefficient (e.g. Coriolis / sources projected into H_2d or U_2d,
+ * test/swe2d/test_steady_state_basin_mms.py:169-177; P1DG atmospheric pressure, test_atmospheric_pressure.py:57-63):
+ * HOST [n_owned*3*ncomp], values at the CCW nodes of every owned cell in the context's cell order.  Copied
+ * asynchronously on `stream` (cheap to repeat every RK stage).  Only for coefficients of cell terms: bathymetry,
+ * viscosity, diffusivity and the wetting-drying alpha enter facet terms and must be continuous (TB_ERR_UNSUPPORTED). */
+int tb_set_field_cell(tb_ctx *ctx, int field, const double *values, int ncomp, void *stream);
 int tb_clear_field(tb_ctx *ctx, int field);     /* field = None                     */
+/* Apply pending coefficient changes stream-ordered on `stream` (every stage launch does this itself; call it
+ * explicitly before replaying a captured CUDA graph).  New VALUES of an existing P1 field rewrite only that field's
+ * columns (async copy + one scatter kernel, no device synchronisation: time-dependent wind / pressure forcing in
+ * update_forcings); structural changes rebuild the per-patch blocks (synchronising, set-up time only). */
+int tb_sync_fields(tb_ctx *ctx, void *stream);
 /* Boundary condition of one marker for equation eq (0 = shallow water,
  * 1 = tracer): opcode = OR of TB_BC_*, consts = {elev, uv_x, uv_y, un, flux, value, diff_flux, reserved}.
  * replaces ShallowWaterTerm.get_bnd_functions (shallowwater_eq.py:232-272)
  * and TracerTerm.get_bnd_functions (tracer_eq_2d.py:78-115) */
 int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const double consts[8]);
+/* The marker has no entry in this equation's bnd_conditions dict (closed boundary; each tracer equation is built
+ * from its own dict, solver2d.py:580-598, while the device context is shared). */
+int tb_clear_bc(tb_ctx *ctx, int eq, int marker);
 /* Spatially varying datum for one tag of one marker: HOST values at the two
  * nodes of every exterior facet of the mesh, [n_bfacets*2*ncomp] (entries of
  * other markers ignored).  Copied asynchronously on `stream`. */

@@ -21,7 +21,7 @@ What is restated (all paths relative to /root/reference):
 * thetis/rungekutta.py:13-87,326-347,870-952  Shu-Osher SSPRK33
 * thetis/tracer_eq_2d.py:78-193,281-298       tracer advection + source
 * thetis/tracer_eq_2d.py:196-278              HorizontalDiffusionTerm (SIPG)
-* thetis/conservative_tracer_eq_2d.py:57-137  conservative tracer advection + source
+* thetis/tracer_eq_2d.py:300-437              conservative tracer advection + source
 * thetis/rungekutta.py:762-867                ERKGeneric (Butcher form)
 * thetis/limiter.py:48-198 + firedrake.VertexBasedLimiter (recalled)
 
@@ -36,7 +36,10 @@ PARITY STATUS: pinned against the reference's own known-answer criteria
 (tests/test_oracle_kat.py: Shu-Osher coefficients produced by executing
 rungekutta.py:13-87 itself, ODE convergence slope, eta-norm 6251.2574, standing
 wave thresholds, limiter invariants, tracer conservation, atmospheric-pressure
-and Rossby-soliton criteria).  There are no stored field dumps in the
+criteria; tests/test_oracle_reference_kat.py: Rossby-soliton peak/phase criteria,
+steady-state basin MMS order 2 with flux/un/elev/uv boundary data, tracer
+h-advection slope -- their analytic fields pinned to values produced by executing
+the reference's own test functions, tests/golden/reference_kat_fields.npz).  There are no stored field dumps in the
 reference for this path, so field-level parity vs Firedrake itself is
 "pinned through those criteria only"; explicit wetting-drying is
 "parity unpinned" (not a reference code path).
@@ -203,17 +206,26 @@ class SWEOracle:
         self.mass = self.geom.area[:, None, None] * mref[None]
 
     # ------------------------------------------------------------ depth (utility.py:975-996)
-    def wd_bathymetry_displacement(self, b, eta):
+    def wd_bathymetry_displacement(self, b, eta, alpha=None):
+        """utility.py:975-985; ``alpha``: wetting_and_drying_alpha at the evaluation points when it is a P1 field
+        (solver2d.py:279-287), else the constant option."""
         if self.options["use_wetting_and_drying"]:
             H = b + eta
-            al = self.options["wetting_and_drying_alpha"]
+            al = self.options["wetting_and_drying_alpha"] if alpha is None else alpha
             return 0.5 * (np.sqrt(H ** 2 + np.asarray(al) ** 2) - H)
         return 0.0
 
-    def total_depth(self, b, eta):
+    def total_depth(self, b, eta, alpha=None):
         if self.options["use_nonlinear_equations"]:
-            return b + eta + self.wd_bathymetry_displacement(b, eta)
+            return b + eta + self.wd_bathymetry_displacement(b, eta, alpha)
         return b + 0.0 * eta
+
+    def _alpha_nodal(self):
+        """(nt, 3) nodal values when wetting_and_drying_alpha is a spatially varying P1 field, else None."""
+        al = self.options["wetting_and_drying_alpha"]
+        if isinstance(al, np.ndarray) and al.ndim == 2:
+            return al
+        return None
 
     # ------------------------------------------------------------ helpers
     def _field(self, name, ncomp=None):
@@ -259,6 +271,8 @@ class SWEOracle:
         """shallowwater_eq.py:232-272; everything evaluated at facet Gauss points."""
         bnd_len = self.boundary_len[marker]
         cells, lf = self._bf_sel[marker]
+        aln = self._alpha_nodal()
+        al_b = None if aln is None else self._facet_trace(aln, cells, lf, _GS)
         eta_ext = uv_ext = None
         if 'elev' in funcs and 'uv' in funcs:
             eta_ext = self._bc_value(funcs['elev'], cells, lf)
@@ -268,7 +282,7 @@ class SWEOracle:
             uv_ext = self._bc_value(funcs['un'], cells, lf)[..., None] * normal
         elif 'elev' in funcs and 'flux' in funcs:
             eta_ext = self._bc_value(funcs['elev'], cells, lf)
-            h_ext = self.total_depth(b, eta_ext)
+            h_ext = self.total_depth(b, eta_ext, al_b)
             area = h_ext * bnd_len
             uv_ext = (self._bc_value(funcs['flux'], cells, lf) / area)[..., None] * normal
         elif 'elev' in funcs:
@@ -282,7 +296,7 @@ class SWEOracle:
             uv_ext = self._bc_value(funcs['un'], cells, lf)[..., None] * normal
         elif 'flux' in funcs:
             eta_ext = eta_in
-            h_ext = self.total_depth(b, eta_ext)
+            h_ext = self.total_depth(b, eta_ext, al_b)
             area = h_ext * bnd_len
             uv_ext = (self._bc_value(funcs['flux'], cells, lf) / area)[..., None] * normal
         if eta_ext is None or uv_ext is None:
@@ -327,7 +341,10 @@ class SWEOracle:
         u_q = self._at_cell_q(uv, lam)                    # (nt, nq, 2)
         eta_q = self._at_cell_q(eta, lam)
         b_q = self._at_cell_q(self.bath, lam)
-        H_q = self.total_depth(b_q, eta_q)
+        aln = self._alpha_nodal()
+        if aln is not None and self.fields.get("viscosity_h") is not None and o["use_grad_depth_viscosity_term"]:
+            raise NotImplementedError("grad-depth viscosity term with a spatially varying wetting-drying alpha")
+        H_q = self.total_depth(b_q, eta_q, None if aln is None else self._at_cell_q(aln, lam))
         # ExternalPressureGradient: f = -g*eta*div(psi) dx ; R = -f
         Ru += g * np.einsum("cq,cq,cai->cai", wq, eta_q, grad)
         # HUDiv: f = -inner(grad(phi), H*uv) dx
@@ -354,14 +371,24 @@ class SWEOracle:
             Ru -= np.einsum("cq,ci,qa->cai", wq, gp / self.rho0, phi)
         mann = self._field("manning_drag_coefficient")
         cd = self._field("quadratic_drag_coefficient")
-        if self.fields.get("nikuradse_bed_roughness") is not None:
-            raise NotImplementedError("nikuradse_bed_roughness is not on the accelerated path")
+        nik = self._field("nikuradse_bed_roughness")
         cd_q = None
+        if nik is not None:
+            # shallowwater_eq.py:689-697
+            if mann is not None:
+                raise Exception('Cannot set both Nikuradse drag and Manning drag parameter')
+            if cd is not None:
+                raise Exception('Cannot set both dimensionless and Nikuradse drag parameter')
+            kappa = float(self.fields.get("von_karman", 0.4))
+            ks_q = self._at_cell_q(nik, lam)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                cd_n = 2 * kappa ** 2 / np.log(11.036 * H_q / ks_q) ** 2
+            cd_q = np.where(H_q > ks_q, cd_n, 0.0)
         if mann is not None:
             if cd is not None:
                 raise Exception('Cannot set both dimensionless and Manning drag parameter')
             cd_q = g * self._at_cell_q(mann, lam) ** 2 / H_q ** (1. / 3.)
-        elif cd is not None:
+        elif cd is not None and nik is None:
             cd_q = self._at_cell_q(cd, lam)
         if cd_q is not None:
             eps = float(o["norm_smoother"])
@@ -414,8 +441,9 @@ class SWEOracle:
             em = self._facet_trace(eta, cm, fm, s, reverse=True)
             bp = self._facet_trace(self.bath, cp, fp, s)
             bm = self._facet_trace(self.bath, cm, fm, s, reverse=True)
-            Hp = self.total_depth(bp, ep)
-            Hm = self.total_depth(bm, em)
+            al_f = None if aln is None else self._facet_trace(aln, cp, fp, s)       # alpha is continuous (P1)
+            Hp = self.total_depth(bp, ep, al_f)
+            Hm = self.total_depth(bm, em, al_f)
             # test functions: '+' nodes (n0: 1-s, n1: s); '-' nodes reversed
             php = np.stack([1 - s, s], -1)                # (ngp, 2) for nodes FACET_NODES[fp]
             nodes_p = FACET_NODES[fp]                     # (nf, 2)
@@ -491,7 +519,8 @@ class SWEOracle:
             u = self._facet_trace(uv, cells, lf, s)
             e = self._facet_trace(eta, cells, lf, s)
             b = self._facet_trace(self.bath, cells, lf, s)
-            H = self.total_depth(b, e)
+            al_b = None if aln is None else self._facet_trace(aln, cells, lf, s)
+            H = self.total_depth(b, e, al_b)
             nodes = FACET_NODES[lf]
             php = np.stack([1 - s, s], -1)
             fu = np.zeros_like(u)
@@ -503,12 +532,12 @@ class SWEOracle:
                 eta_rie = 0.5 * (e + eta_ext) + np.sqrt(H / g) * un_jump
                 fu = fu + g * eta_rie[..., None] * nb
                 # HUDiv (:431-442)
-                H_ext = self.total_depth(b, eta_ext)
+                H_ext = self.total_depth(b, eta_ext, al_b)
                 h_av = 0.5 * (H + H_ext)
                 eta_jump = e - eta_ext
                 un_rie = 0.5 * np.einsum("fqi,fqi->fq", u + uv_ext, nb) + np.sqrt(g / h_av) * eta_jump
                 eta_rie2 = 0.5 * (e + eta_ext) + np.sqrt(h_av / g) * un_jump
-                h_rie = self.total_depth(b, eta_rie2)
+                h_rie = self.total_depth(b, eta_rie2, al_b)
                 fe = fe + h_rie * un_rie
                 if adv:
                     # advection (:498-509)

@@ -335,3 +335,131 @@ def test_modesplit_equations_through_the_integrator():
     for i in range(nsteps):
         st.advance(i * dt)
     assert _rel(e_g, eta) < 1e-11 and _rel(uv_g, uv) < 1e-11
+
+
+def test_coupled_two_stage_rk_2d_mode_loop():
+    """the 2-D side of CoupledTwoStageRK (coupled_timeintegrator.py:563-715): ModeSplit2DEquations
+    stepped stage by stage through `swe2d.solve_stage`, with the coupling term split_residual_2d (+ momentum_source_2d)
+    re-assigned by a (synthetic) 3-D side after every stage from the stage solution it reads on the host"""
+    from thetis_b200.shim import Function, FunctionSpace, MixedFunctionSpace, Constant, as_shim_mesh
+    from thetis_b200.equations import ModeSplit2DEquations, DepthExpression
+    from thetis_b200.options import ModelOptions2d
+    from thetis_b200.solver2d import AttrDict
+    from thetis_b200.coupled_timeintegrator import CoupledTwoStageRK2D
+    from thetis_b200 import rungekutta
+    mesh = rectangle_mesh(14, 9, 14e3, 9e3)
+    sm = as_shim_mesh(mesh)
+    P1 = FunctionSpace(sm, "CG", 1)
+    bath_fn = lambda x, y: 25.0 + 4.0 * np.sin(x / 2.5e3) * np.cos(y / 3e3)
+    bath = Function(P1).interpolate(bath_fn)
+    U, H = FunctionSpace(sm, "DG", 1, value_size=2), FunctionSpace(sm, "DG", 1)
+    V = MixedFunctionSpace([U, H])
+    sol = Function(V)
+    uvf, ef = sol.subfunctions
+    ic = lambda x, y: 0.4 * np.cos(np.pi * x / 14e3) * np.cos(np.pi * y / 9e3)
+    ef.interpolate(ic)
+    opts = ModelOptions2d()
+    opts.coriolis_frequency = Constant(1.0e-4)
+    opts.momentum_source_2d = Constant((2e-5, -1e-5))
+    dt, nsteps = 6.0, 15
+    solver = AttrDict()
+    solver.options = opts
+    solver.fields = AttrDict(solution_2d=sol, split_residual_2d=Function(U, name="split_residual_2d"))
+    solver.equations = AttrDict(sw=ModeSplit2DEquations(V, DepthExpression(bath), opts))
+    solver.dt = dt
+    solver.bnd_functions = {"shallow_water": {1: {"elev": Constant(0.1)}}}
+    calls = []
+
+    class Mode3D:
+        """stand-in for the reference's 3-D side: reads the 2-D stage solution, returns the coupling term"""
+        def prepare_stage(self, i, t, uf3d):
+            calls.append(("prepare", i))
+
+        def solve_stage(self, i):
+            calls.append(("solve", i))
+
+        def update_2d_coupling(self, last):
+            # split_residual_2d = uv_dav_2d / dt (:65-70); here a damping of the 2-D stage velocity
+            solver.fields.split_residual_2d.dat.data[...] = -0.02 / dt * uvf.dat.data_ro + 1e-6 * (1 + int(last))
+            calls.append(("couple", last))
+
+    ti = CoupledTwoStageRK2D(solver, mode3d=Mode3D())
+    assert isinstance(ti.timesteppers.swe2d, rungekutta.SSPRK22) and ti.n_stages == 2
+    for i in range(nsteps):
+        ti.advance(i * dt)
+    assert calls[:6] == [("prepare", 0), ("solve", 0), ("couple", False), ("prepare", 1), ("solve", 1), ("couple", True)]
+    uv_g = uvf.dat.data_ro.reshape(mesh.n_cells, 3, 2).copy()
+    e_g = ef.dat.data_ro.reshape(mesh.n_cells, 3).copy()
+    # the same loop on the oracle
+    x = mesh.coords[mesh.cells]
+    orc = O.SWEOracle(mesh, bath_fn(x[..., 0], x[..., 1]), options=dict(include_momentum_advection=False),
+                      fields={"coriolis": 1.0e-4, "momentum_source": np.zeros((mesh.n_cells, 3, 2)) + (2e-5, -1e-5)},
+                      bnd_conditions={1: {"elev": 0.1}})
+    eta = ic(x[..., 0], x[..., 1]) + 0.0
+    uv = np.zeros(eta.shape + (2,))
+    st = O.ShuOsherStepper(orc, [uv, eta], dt, a=[[0, 0], [1.0, 0]], b=[0.5, 0.5], c=[0, 1.0])
+    for i in range(nsteps):
+        for k in range(2):
+            st.solve_stage(k, i * dt)
+            orc.fields["momentum_source"] = (-0.02 / dt * uv + 1e-6 * (1 + int(k == 1))) + (2e-5, -1e-5)
+    assert np.abs(uv).max() > 1e-3
+    assert _rel(e_g, eta) < 1e-11 and _rel(uv_g, uv) < 1e-11
+
+
+def test_nonblocking_export_staging():
+    """8f-3: stage_export() copies the solution to pinned host memory on a side stream while the time loop keeps
+    running; what the handle returns is the solution AT THE TIME OF THE CALL, bit-identical to a blocking sync"""
+    import torch
+    from thetis_b200 import solver2d
+    from thetis_b200.shim import Function, FunctionSpace, as_shim_mesh
+    mesh = delaunay_mesh(4000, 2.0e4, 1.5e4, seed=11)
+    sm = as_shim_mesh(mesh)
+    b = Function(FunctionSpace(sm, "CG", 1)).interpolate(lambda x, y: 15.0 + 3.0 * np.sin(x / 3e3))
+    s = solver2d.FlowSolver2d(sm, b)
+    s.options.swe_timestepper_options.use_automatic_timestep = False
+    s.options.update(dict(timestep=1.0, simulation_end_time=10.0, no_exports=True))
+    s.assign_initial_conditions(elev=lambda x, y: 0.3 * np.cos(x / 2e3) * np.sin(y / 3e3))
+    ts = s.timestepper
+    handles, blocking = [], []
+    for i in range(6):
+        ts.advance(i * 1.0)
+        handles.append(ts.stage_export())               # returns at once; the loop goes on
+        if i in (1, 3):                                 # reference copies, taken the blocking way
+            ts.sync_to_host()
+            blocking.append((i, s.fields.uv_2d.dat.data_ro.copy(), s.fields.elev_2d.dat.data_ro.copy()))
+        if i >= 1:
+            # double buffering: a handle stays valid until the second-next stage_export()
+            uv_h, eta_h = handles[i - 1].wait()
+            for j, uv_b, eta_b in blocking:
+                if j == i - 1:
+                    assert np.array_equal(uv_h, uv_b.reshape(uv_h.shape)) and np.array_equal(eta_h, eta_b)
+    assert handles[-1].wait()[1].shape == s.fields.elev_2d.dat.data_ro.shape
+    assert all(h.ready() for h in handles)
+
+
+def test_flowsolver_export_consumers_run_behind_the_time_loop():
+    """FlowSolver2d.add_export_consumer: every export is staged without blocking and delivered in order with the
+    fields of ITS export time (compared with a second, blocking, run)"""
+    from thetis_b200 import solver2d
+    from thetis_b200.shim import Function, FunctionSpace, as_shim_mesh
+
+    def make():
+        mesh = rectangle_mesh(20, 8, 2.0e4, 8e3)
+        sm = as_shim_mesh(mesh)
+        b = Function(FunctionSpace(sm, "CG", 1)).interpolate(lambda x, y: 12.0 + 2.0 * np.cos(x / 3e3))
+        s = solver2d.FlowSolver2d(sm, b)
+        s.options.swe_timestepper_options.use_automatic_timestep = False
+        s.options.update(dict(timestep=2.0, simulation_end_time=40.0, simulation_export_time=8.0, no_exports=True))
+        s.assign_initial_conditions(elev=lambda x, y: 0.3 * np.cos(np.pi * x / 2.0e4))
+        return s
+    got = []
+    s1 = make()
+    s1.add_export_consumer(lambda t, i, arr: got.append((t, i, arr["uv_2d"].copy(), arr["elev_2d"].copy())))
+    s1.iterate()
+    ref = []
+    s2 = make()
+    s2.iterate(export_func=lambda: ref.append((s2.simulation_time, s2.i_export, s2.fields.uv_2d.dat.data_ro.copy(),
+                                               s2.fields.elev_2d.dat.data_ro.copy())))
+    assert [g[:2] for g in got] == [r[:2] for r in ref] and len(got) == 6        # t = 0, 8, ..., 40
+    for g, r in zip(got, ref):
+        assert np.array_equal(g[2], r[2].reshape(g[2].shape)) and np.array_equal(g[3], r[3])

@@ -165,3 +165,44 @@ def test_config5_north_sea_4m_properties():
     eng.swe_integrals(A, o4)
     assert torch.isfinite(A).all()
     assert abs(o4[3].item() - vol0) <= 1e-13 * abs(vol0)
+
+
+@pytest.mark.parametrize("wd", [True, False])
+def test_config5_north_sea_4m_one_step_matches_c_oracle(wd):
+    """BASELINE config 5 at full size (3 942 120 triangles): one SSPRK33 step with the tidal elevation re-assigned at
+    every stage, GPU (specialised SPEC 3 / SPEC 2 kernels) against oracle/swe_oracle.c on the host cores; fp64,
+    relative 1e-10 of each field's max-norm."""
+    import thetis_b200._lib as L
+    from harness.workloads import north_sea_mesh, north_sea_setup, tide_values
+    from oracle import c_oracle as CO
+    mesh = north_sea_mesh(19)
+    setup = north_sea_setup(mesh, wetting_drying=wd)
+    dt = setup["dt"]
+    eng = _engine(mesh)
+    eng.set_option(L.OPT_WETTING_DRYING, int(wd))
+    eng.set_option(L.OPT_WD_ALPHA, setup["wd_alpha"])
+    eng.set_field(L.F_BATHYMETRY, setup["bath"])
+    eng.set_field(L.F_MANNING, setup["manning"])
+    eng.set_field(L.F_CORIOLIS, setup["coriolis"])
+    eng.set_bc(0, 100, L.BC_ELEV | L.BC_UV, [0.0] * 6)
+    orc = CO.COracle(mesh, setup["bath"], nonlinear=True, lf_on=True, coriolis=setup["coriolis"], manning=setup["manning"],
+                     bnd={100: {"elev": 0.0, "uv": (0.0, 0.0)}}, wd_on=wd, wd_alpha=setup["wd_alpha"],
+                     threads=CO.host_threads())
+    A = eng.upload_nodal(setup["uv0"], setup["eta0"])
+    B, C = eng.new_state(), eng.new_state()
+    u0 = CO.records_from_nodal(setup["uv0"], setup["eta0"])
+    stages = [(0.0, 1.0, 1.0, 0.0), (0.75, 0.25, 0.25, 1.0), (1.0 / 3.0, 2.0 / 3.0, 2.0 / 3.0, 0.5)]   # a0, a1, beta, c
+    bufs = [(A, None, B), (B, A, C), (C, A, A)]
+    u = u0
+    t0 = 1000.0
+    for (a0, a1, beta, c), (uin, uz, uout) in zip(stages, bufs):
+        tv = tide_values(setup, t0 + c * dt)
+        eng.set_bc_array(0, 100, L.BC_ELEV, tv)
+        eng.swe_stage(a0, a1, beta * dt, uin, uz, uout)
+        orc.set_bf_elev(tv)
+        u = orc.stage(a0, a1, beta * dt, u, u0 if a0 != 0.0 else None)
+    uv_g, eta_g = eng.download_nodal(A)
+    uv_c, eta_c = CO.nodal_from_records(u)
+    assert np.isfinite(uv_g).all() and np.isfinite(eta_g).all()
+    assert np.abs(uv_g - uv_c).max() <= 1e-10 * np.abs(uv_c).max()
+    assert np.abs(eta_g - eta_c).max() <= 1e-10 * np.abs(eta_c).max()

@@ -29,14 +29,20 @@ def _vertex_field(mesh, fn):
     return fn(mesh.coords[:, 0], mesh.coords[:, 1])
 
 
-def _run(mesh, bath_v, options, fields_v, bnd, g=9.81, tol=1e-12, seed=0, bc_arrays=None):
+def _run(mesh, bath_v, options, fields_v, bnd, g=9.81, tol=1e-12, seed=0, bc_arrays=None, return_engine=False):
     """fields_v: dict name -> None | const | per-vertex array; bnd: {marker: {tag: const}}"""
     import thetis_b200._lib as L
     from thetis_b200.engine import Engine
     uv, eta = _state(mesh, seed)
     cells = mesh.cells
-    to_nodal = lambda a: a[cells] if (isinstance(a, np.ndarray) and a.shape[0] == mesh.n_vertices) else a
+    # per-vertex arrays (P1) -> cell-nodal; (nt, 3[,2]) arrays are genuinely discontinuous P1DG fields: as they are
+    is_dg = lambda a: isinstance(a, np.ndarray) and a.ndim >= 2 and a.shape[:2] == (mesh.n_cells, 3)
+    to_nodal = lambda a: a[cells] if (isinstance(a, np.ndarray) and not is_dg(a) and a.shape[0] == mesh.n_vertices) else a
     ofields = {k: to_nodal(v) for k, v in fields_v.items() if v is not None}
+    options = dict(options)
+    wd_alpha = options.get("wetting_and_drying_alpha", 0.5)
+    if isinstance(wd_alpha, np.ndarray):
+        options["wetting_and_drying_alpha"] = wd_alpha[cells]          # P1 field: nodal for the oracle
     obnd = {}
     for m, d in bnd.items():
         obnd[m] = dict(d)
@@ -56,7 +62,10 @@ def _run(mesh, bath_v, options, fields_v, bnd, g=9.81, tol=1e-12, seed=0, bc_arr
     eng.set_option(L.OPT_LAX_FRIEDRICHS, options.get("use_lax_friedrichs_velocity", True))
     eng.set_option(L.OPT_NORM_SMOOTHER, options.get("norm_smoother", 0.0))
     eng.set_option(L.OPT_WETTING_DRYING, options.get("use_wetting_and_drying", False))
-    eng.set_option(L.OPT_WD_ALPHA, options.get("wetting_and_drying_alpha", 0.5))
+    if isinstance(wd_alpha, np.ndarray):
+        eng.set_field(L.F_WD_ALPHA, wd_alpha)
+    else:
+        eng.set_option(L.OPT_WD_ALPHA, wd_alpha)
     eng.set_option(L.OPT_LF_SCALING, fields_v.get("lax_friedrichs_velocity_scaling_factor", 1.0))
     eng.set_option(L.OPT_SIPG_FACTOR, options.get("sipg_factor", 1.0))
     eng.set_option(L.OPT_GRAD_DIV_VISCOSITY, options.get("use_grad_div_viscosity_term", False))
@@ -66,7 +75,7 @@ def _run(mesh, bath_v, options, fields_v, bnd, g=9.81, tol=1e-12, seed=0, bc_arr
              "quadratic_drag_coefficient": L.F_QUAD_DRAG, "linear_drag_coefficient": L.F_LINEAR_DRAG,
              "wind_stress": L.F_WIND_STRESS, "atmospheric_pressure": L.F_ATM_PRESSURE,
              "momentum_source": L.F_MOMENTUM_SOURCE, "volume_source": L.F_VOLUME_SOURCE,
-             "viscosity_h": L.F_VISCOSITY}
+             "viscosity_h": L.F_VISCOSITY, "nikuradse_bed_roughness": L.F_NIKURADSE}
     for k, fid in names.items():
         if fields_v.get(k) is not None:
             eng.set_field(fid, fields_v[k])
@@ -100,6 +109,8 @@ def _run(mesh, bath_v, options, fields_v, bnd, g=9.81, tol=1e-12, seed=0, bc_arr
     eu = np.abs(gu - ku).max() / su
     ee = np.abs(ge - ke).max() / se
     assert eu < tol and ee < tol, (eu, ee)
+    if return_engine:
+        return eng, orc, (uv, eta)
     return eu, ee
 
 
@@ -354,3 +365,104 @@ def test_modesplit_equations_no_momentum_advection(bc):
     eng.swe_tendency(st, k)
     gu, ge = eng.download_nodal(k)
     assert np.abs(gu - ku).max() / np.abs(ku).max() < 1e-11 and np.abs(ge - ke).max() / np.abs(ke).max() < 1e-11
+
+
+# ---------------------------------------------------------------- round 2: coefficient forms the reference accepts
+def _dg_field(mesh, seed, base, amp, ncomp=None):
+    """genuinely discontinuous P1DG nodal data (nt, 3[,k]): smooth part + per-node noise"""
+    rng = np.random.default_rng(seed)
+    shape = (mesh.n_cells, 3) + (() if ncomp is None else (ncomp,))
+    return base + amp * rng.standard_normal(shape)
+
+
+def test_p1dg_coefficient_fields_linear():
+    """Coriolis / sources / drag / wind / pressure given as discontinuous P1DG Functions (the reference projects
+    Coriolis and the MMS sources into H_2d / U_2d, test_steady_state_basin_mms.py:169-177, and passes P1DG atmospheric
+    pressure, test_atmospheric_pressure.py:57-63): stored per cell node (tb_set_field_cell), generic kernel"""
+    mesh = sfc_renumber(delaunay_mesh(900, 1000.0, 800.0, seed=3))
+    fields = {"coriolis": _dg_field(mesh, 1, 1e-2, 3e-3), "linear_drag_coefficient": _dg_field(mesh, 2, 2e-3, 5e-4),
+              "wind_stress": _dg_field(mesh, 3, 0.1, 0.05, 2), "atmospheric_pressure": _dg_field(mesh, 4, 1e5, 300.0),
+              "momentum_source": _dg_field(mesh, 5, 0.0, 1e-3, 2), "volume_source": _dg_field(mesh, 6, 0.0, 1e-3)}
+    _run(mesh, 30.0, dict(use_nonlinear_equations=False), fields, {})
+
+
+def test_p1dg_coefficient_fields_nonlinear_manning():
+    mesh = sfc_renumber(delaunay_mesh(700, 1000.0, 800.0, seed=5))
+    b = _vertex_field(mesh, lambda x, y: 12.0 + 3 * np.sin(x / 200.0) * np.cos(y / 150.0))
+    fields = {"coriolis": _dg_field(mesh, 1, 1e-2, 3e-3), "manning_drag_coefficient": _dg_field(mesh, 2, 0.03, 0.004),
+              "momentum_source": _dg_field(mesh, 5, 0.0, 1e-3, 2), "volume_source": _dg_field(mesh, 6, 0.0, 1e-3)}
+    bnd = {m: {"elev": 0.2, "uv": (0.1, -0.05)} for m in mesh.unique_markers()[:1]}
+    _run(mesh, b, dict(norm_smoother=1e-3), fields, bnd, tol=1e-11)
+
+
+def test_discontinuous_coefficient_of_a_facet_term_is_rejected():
+    import thetis_b200._lib as L
+    from thetis_b200.engine import Engine
+    mesh = rectangle_mesh(4, 4, 10.0, 10.0)
+    eng = Engine(mesh)
+    for fid in (L.F_BATHYMETRY, L.F_VISCOSITY, L.F_WD_ALPHA):
+        with pytest.raises(L.TbError):
+            eng.set_field(fid, _dg_field(mesh, 0, 10.0, 1.0))
+
+
+@pytest.mark.parametrize("as_dg", [False, True])
+def test_nikuradse_bed_roughness(as_dg):
+    """QuadraticDragTerm with the Nikuradse law (shallowwater_eq.py:689-697), incl. cells where H < k_s (C_D = 0)"""
+    mesh = sfc_renumber(rectangle_mesh(14, 11, 700.0, 500.0))
+    b = _vertex_field(mesh, lambda x, y: 0.6 + 0.5 * np.sin(x / 90.0) * np.cos(y / 70.0))       # H in ~[0.1, 1.4]
+    ks = _vertex_field(mesh, lambda x, y: 0.25 + 0.2 * np.cos(x / 130.0))
+    if as_dg:
+        ks = ks[mesh.cells] * (1.0 + 0.1 * np.random.default_rng(0).standard_normal((mesh.n_cells, 3)))
+    _run(mesh, b, dict(norm_smoother=1e-2), {"nikuradse_bed_roughness": ks}, {}, tol=1e-11)
+
+
+def test_nikuradse_and_manning_together_raise():
+    import thetis_b200._lib as L
+    from thetis_b200.engine import Engine
+    mesh = rectangle_mesh(4, 4, 10.0, 10.0)
+    eng = Engine(mesh)
+    eng.set_field(L.F_BATHYMETRY, 5.0)
+    eng.set_field(L.F_MANNING, 0.02)
+    eng.set_field(L.F_NIKURADSE, 0.1)
+    st = eng.new_state()
+    with pytest.raises(L.TbError, match="Nikuradse"):
+        eng.swe_tendency(st, eng.new_state())
+
+
+def test_wetting_drying_alpha_as_p1_field():
+    """wetting_and_drying_alpha as a P1 Function (use_automatic_wetting_and_drying_alpha, solver2d.py:279-287;
+    utility.py:981-983): interior facets, cell rule (Manning), closed and open boundaries"""
+    mesh = sfc_renumber(read_gmsh(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "mini_tagged.msh")))
+    b = _vertex_field(mesh, lambda x, y: 1.5 + 2.0 * np.sin(x / 9.0) * np.cos(y / 7.0))          # dries in places
+    alpha = _vertex_field(mesh, lambda x, y: 0.4 + 0.3 * np.cos(x / 11.0) ** 2 + 0.1 * np.sin(y / 5.0))
+    bnd = {100: {"elev": 0.3, "flux": -40.0}}
+    _run(mesh, b, dict(use_wetting_and_drying=True, wetting_and_drying_alpha=alpha, norm_smoother=1e-3),
+         {"manning_drag_coefficient": 0.03}, bnd, tol=1e-11)
+
+
+def test_time_dependent_p1_field_updates_only_its_columns():
+    """new VALUES of an existing P1 coefficient (wind stress / pressure assigned in update_forcings) are refreshed
+    stream-ordered column by column (tb_sync_fields) and give the same tendency as a fresh context"""
+    mesh = sfc_renumber(delaunay_mesh(600, 1000.0, 800.0, seed=9))
+    w0 = np.stack([_vertex_field(mesh, lambda x, y: 0.1 * np.sin(x / 300.0)), _vertex_field(mesh, lambda x, y: 0.05 + 0 * x)], -1)
+    pa0 = _vertex_field(mesh, lambda x, y: 1e5 + 200.0 * np.cos(y / 200.0))
+    opts = dict(use_nonlinear_equations=False)
+    eng, orc, (uv, eta) = _run(mesh, 25.0, opts, {"wind_stress": w0, "atmospheric_pressure": pa0}, {}, return_engine=True)
+    import thetis_b200._lib as L
+    eng.set_option(L.OPT_FORCE_GENERIC_KERNEL, 0)
+    n0 = eng.launch_count()
+    for step in range(1, 4):
+        w = w0 * (1.0 + 0.3 * step)
+        pa = pa0 + 50.0 * step * np.sin(mesh.coords[:, 0] / 150.0)
+        eng.set_field(L.F_WIND_STRESS, w)
+        eng.set_field(L.F_ATM_PRESSURE, pa)
+        st = eng.upload_nodal(uv, eta)
+        k = eng.new_state()
+        eng.swe_tendency(st, k)
+        gu, ge = eng.download_nodal(k)
+        orc.fields["wind_stress"] = w[mesh.cells]
+        orc.fields["atmospheric_pressure"] = pa[mesh.cells]
+        ku, ke = orc.tendency(uv, eta)
+        assert np.abs(gu - ku).max() < 1e-12 * np.abs(ku).max() and np.abs(ge - ke).max() < 1e-12 * np.abs(ke).max()
+    # per refresh: one column-scatter launch per field (2), not a rebuild; plus layout conversion and the stage itself
+    assert eng.launch_count() - n0 <= 3 * (2 + 3)

@@ -302,7 +302,8 @@ def test_unsupported_configurations_raise():
     mesh = rectangle_mesh(4, 4, 1.0, 1.0)
     s, _ = _solver(mesh, 1.0, timestep=0.01, simulation_end_time=0.01)
     s.options.nikuradse_bed_roughness = Constant(1.0)
-    with pytest.raises(NotImplementedError):
+    s.options.manning_drag_coefficient = Constant(0.02)
+    with pytest.raises(Exception, match="Cannot set both Nikuradse"):      # shallowwater_eq.py:690-694
         s.assign_initial_conditions()
     s2, _ = _solver(mesh, 1.0, timestep=0.01, simulation_end_time=0.01)
     s2.bnd_functions["shallow_water"] = {1: {"bogus": Constant(1.0)}}
@@ -336,3 +337,135 @@ def test_fused_stage_integrals_match_separate_reduction():
         f, g = fused.cpu().numpy(), sep.cpu().numpy()
         assert np.all(np.abs(f - g) <= 1e-13 * np.abs(g)), (f, g)
         assert g[0] > 0 and g[1] > 0 and g[3] > 0
+
+
+# ---------------------------------------------------------------- round 2: boundary gaps
+def test_ufl_expression_boundary_data_north_sea_style():
+    """examples/north_sea/model_config.py:181-192: 'elev' = elev_ramp * elev_tide_2d with
+    elev_ramp = conditional(bnd_time < ramp_t, bnd_time / ramp_t, 1.0), bnd_time and the tidal Function re-assigned in
+    update_forcings.  The expression is affine in its Function operand, so nodal evaluation is exact."""
+    from thetis_b200.shim import Constant, Function, FunctionSpace, conditional
+    mesh = rectangle_mesh(16, 6, 16e3, 6e3)
+    dt, nsteps = 4.0, 30
+    bath_fn = lambda x, y: 12.0 + 2.0 * np.cos(x / 3e3)
+    s, P1 = _solver(mesh, bath_fn, timestep=dt, simulation_end_time=dt * nsteps, simulation_export_time=dt * nsteps)
+    s.options.manning_drag_coefficient = Constant(0.02)
+    elev_tide = Function(P1, name="Tidal elevation")
+    bnd_time = Constant(0.0)
+    ramp_t = 60.0
+    elev_ramp = conditional(bnd_time < ramp_t, bnd_time / ramp_t, 1.0)
+    s.bnd_functions["shallow_water"] = {1: {"elev": elev_ramp * elev_tide, "uv": Constant(np.array([0.0, 0.0]))}}
+    tide = lambda t: (lambda x, y: 0.5 * np.sin(2 * np.pi * t / 300.0 + y / 4e3))
+
+    def update_forcings(t):
+        bnd_time.assign(t)
+        elev_tide.interpolate(tide(t))
+    update_forcings(0.0)
+    s.assign_initial_conditions(elev=lambda x, y: 0.0 * x)
+    s.iterate(update_forcings=update_forcings)
+    uv_g, eta_g = _fields_nodal(s, mesh)
+    x = mesh.coords[mesh.cells]
+    orc = O.SWEOracle(mesh, bath_fn(x[..., 0], x[..., 1]), fields={"manning_drag_coefficient": 0.02},
+                      bnd_conditions={1: {"elev": 0.0, "uv": (0.0, 0.0)}})
+    eta = np.zeros(x.shape[:2])
+    uv = np.zeros(eta.shape + (2,))
+
+    def uf(t):
+        ramp = t / ramp_t if t < ramp_t else 1.0
+        orc.bnd = {1: {"elev": ramp * tide(t)(x[..., 0], x[..., 1]), "uv": (0.0, 0.0)}}
+    st = O.ShuOsherStepper(orc, [uv, eta], dt)
+    for i in range(nsteps):
+        st.advance(i * dt, uf)
+    assert np.abs(eta).max() > 1e-2
+    assert _rel(eta_g, eta) < 1e-10 and _rel(uv_g, uv) < 1e-10
+
+
+def test_nonaffine_expression_is_refused():
+    from thetis_b200.shim import Constant, Function
+    mesh = rectangle_mesh(4, 4, 1.0, 1.0)
+    s, P1 = _solver(mesh, 1.0, timestep=0.01, simulation_end_time=0.01)
+    f = Function(P1).interpolate(lambda x, y: x)
+    s.bnd_functions["shallow_water"] = {1: {"elev": f * f}}
+    with pytest.raises(NotImplementedError, match="affine"):
+        s.assign_initial_conditions()
+
+
+def test_two_tracers_with_different_boundary_markers_do_not_share_slots():
+    """each tracer equation is built from its own bnd_conditions dict (solver2d.py:580-598) although both integrators
+    share one device context: salt has an inflow 'value' on marker 1, temp has no entry there (closed form)"""
+    from thetis_b200.shim import Constant
+    lx, ly = 12e3, 3e3
+    mesh = rectangle_mesh(12, 3, lx, ly)
+    dt, nsteps = 5.0, 20
+    s, P1 = _solver(mesh, 10.0, timestep=dt, simulation_end_time=dt * nsteps, simulation_export_time=dt * nsteps)
+    s.options.add_tracer_2d("salt_2d", "Salinity", "Salinity2d")
+    s.options.add_tracer_2d("temp_2d", "Temperature", "Temperature2d")
+    s.options.use_limiter_for_tracers = False
+    s.bnd_functions["shallow_water"] = {1: {"un": Constant(-0.3)}, 2: {"elev": Constant(0.0)}}
+    s.bnd_functions["salt"] = {1: {"value": Constant(35.0)}}
+    s.bnd_functions["temp"] = {2: {"value": Constant(3.0)}}
+    ic_s = lambda x, y: 30.0 + 2.0 * np.sin(x / 2e3)
+    ic_t = lambda x, y: 10.0 + 1.0 * np.cos(x / 1.5e3)
+    s.assign_initial_conditions(salt=ic_s, temp=ic_t)
+    s.iterate()
+    sal_g = s.fields.salt_2d.dat.data_ro.reshape(-1, 3)
+    tmp_g = s.fields.temp_2d.dat.data_ro.reshape(-1, 3)
+    x = mesh.coords[mesh.cells]
+    orc = O.SWEOracle(mesh, 10.0, bnd_conditions={1: {"un": -0.3}, 2: {"elev": 0.0}})
+    t_s = O.TracerOracle(orc, bnd_conditions={1: {"value": 35.0}})
+    t_t = O.TracerOracle(orc, bnd_conditions={2: {"value": 3.0}})
+    eta = np.zeros(x.shape[:2])
+    uv = np.zeros(eta.shape + (2,))
+    cs, ct = ic_s(x[..., 0], x[..., 1]) + 0.0, ic_t(x[..., 0], x[..., 1]) + 0.0
+    ss = O.ShuOsherStepper(orc, [uv, eta], dt)
+    st_s, st_t = O.ShuOsherStepper(t_s, [cs], dt), O.ShuOsherStepper(t_t, [ct], dt)
+    for i in range(nsteps):
+        ss.advance(i * dt)
+        for trc, stp in ((t_s, st_s), (t_t, st_t)):
+            trc.set_velocity(uv, eta)
+            stp.advance(i * dt)
+    assert _rel(sal_g, cs) < 1e-10 and _rel(tmp_g, ct) < 1e-10
+
+
+def test_nikuradse_run_through_flowsolver():
+    from thetis_b200.shim import Constant
+    mesh = rectangle_mesh(10, 4, 5e3, 2e3)
+    dt, nsteps = 2.0, 25
+    s, P1 = _solver(mesh, 3.0, timestep=dt, simulation_end_time=dt * nsteps, simulation_export_time=dt * nsteps)
+    s.options.nikuradse_bed_roughness = Constant(0.05)
+    ic = lambda x, y: 0.3 * np.cos(np.pi * x / 5e3)
+    s.assign_initial_conditions(elev=ic)
+    s.iterate()
+    uv_g, eta_g = _fields_nodal(s, mesh)
+    orc = O.SWEOracle(mesh, 3.0, fields={"nikuradse_bed_roughness": 0.05})
+    eta = O.interpolate(mesh, ic)
+    uv = np.zeros(eta.shape + (2,))
+    st = O.ShuOsherStepper(orc, [uv, eta], dt)
+    for i in range(nsteps):
+        st.advance(i * dt)
+    assert _rel(eta_g, eta) < 1e-10 and _rel(uv_g, uv) < 1e-10
+
+
+def test_wetting_drying_alpha_function_through_flowsolver():
+    """wetting_and_drying_alpha as a P1 Function (solver2d.py:279-287)"""
+    from thetis_b200.shim import Function
+    mesh = rectangle_mesh(12, 5, 6e3, 2.5e3)
+    dt, nsteps = 1.0, 20
+    bath_fn = lambda x, y: 1.0 + 1.5 * np.cos(np.pi * x / 6e3)       # dry towards x = lx
+    s, P1 = _solver(mesh, bath_fn, timestep=dt, simulation_end_time=dt * nsteps, simulation_export_time=dt * nsteps,
+                    use_wetting_and_drying=True)
+    al_fn = lambda x, y: 0.3 + 0.2 * np.sin(x / 1e3) ** 2
+    s.options.wetting_and_drying_alpha = Function(P1).interpolate(al_fn)
+    ic = lambda x, y: 0.2 * np.cos(np.pi * x / 6e3)
+    s.assign_initial_conditions(elev=ic)
+    s.iterate()
+    uv_g, eta_g = _fields_nodal(s, mesh)
+    x = mesh.coords[mesh.cells]
+    orc = O.SWEOracle(mesh, bath_fn(x[..., 0], x[..., 1]),
+                      options=dict(use_wetting_and_drying=True, wetting_and_drying_alpha=al_fn(x[..., 0], x[..., 1])))
+    eta = O.interpolate(mesh, ic)
+    uv = np.zeros(eta.shape + (2,))
+    st = O.ShuOsherStepper(orc, [uv, eta], dt)
+    for i in range(nsteps):
+        st.advance(i * dt)
+    assert _rel(eta_g, eta) < 1e-9 and _rel(uv_g, uv) < 1e-9

@@ -181,3 +181,42 @@ def test_install_rebinds_reference_attributes():
     assert issubclass(fake.rungekutta.SSPRK33, SSPRK33) and cls is fake.rungekutta.SSPRK33
     assert fake.limiter.VertexBasedP1DGLimiter is VertexBasedP1DGLimiter
     assert SSPRK33.cfl_coeff == 1.0 and len(SSPRK33.b) == 3
+
+
+def test_constant_function_expression_classification():
+    """a real firedrake.Constant carries `.dat`, `.function_space()` (-> None) and `.values()`: classification is by
+    capability, and the shim Constant now looks the same, so the adaptor path the tests run is the real one"""
+    from thetis_b200.adaptor import is_constant, is_function, is_expression, expression_degree, expression_leaves
+    from thetis_b200.shim import Constant, Function, FunctionSpace, as_shim_mesh, conditional
+    from thetis_b200.rungekutta import _version
+    c = Constant(2.0)
+    assert hasattr(c, "dat") and c.function_space() is None and callable(c.values)
+    assert is_constant(c) and not is_function(c) and not is_expression(c)
+    v0 = _version(c)
+    c.assign(3.0)
+    assert _version(c) != v0 and float(c) == 3.0
+    sm = as_shim_mesh(M.rectangle_mesh(3, 3, 1.0, 1.0))
+    f = Function(FunctionSpace(sm, "CG", 1)).interpolate(lambda x, y: x + 2 * y)
+    assert is_function(f) and not is_constant(f) and not is_expression(f)
+    ramp = conditional(c < 10.0, c / 10.0, 1.0)
+    e = ramp * f
+    assert is_expression(e) and expression_degree(e) == 1 and expression_degree(f * f) == 2
+    assert expression_degree(conditional(f < 1.0, f, 0.0)) is None and expression_degree(c / f) is None
+    leaves = expression_leaves(e)
+    assert any(l is c for l in leaves) and any(l is f for l in leaves) and len(leaves) == 2
+    v1 = _version(e)
+    c.assign(5.0)
+    assert _version(e) != v1
+    # nodal evaluation (no device needed): 0.5 * f at every cell node
+    from thetis_b200.adaptor import MeshAdaptor
+    ad = MeshAdaptor(sm, renumber=False)
+    x = ad.mesh.coords[ad.mesh.cells]
+    assert np.allclose(ad.evaluate(e), 0.5 * (x[..., 0] + 2 * x[..., 1]))
+    kind, vals = ad.coefficient_values(e)
+    assert kind == "vertex" and np.allclose(vals, 0.5 * (ad.mesh.coords[:, 0] + 2 * ad.mesh.coords[:, 1]))
+    dg = Function(FunctionSpace(sm, "DG", 1))
+    dg.dat.data[:] = np.arange(dg.dat.data_ro.shape[0], dtype=float)
+    kind, vals = ad.coefficient_values(dg)
+    assert kind == "cell" and vals.shape == (ad.mesh.n_cells, 3)
+    with pytest.raises(NotImplementedError):
+        ad.vertex_values(dg)

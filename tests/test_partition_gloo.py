@@ -245,3 +245,43 @@ def test_callback_allreduce_sum_min_max_gloo():
     mp.spawn(_worker_allreduce, args=(world, _free_port(), out), nprocs=world, join=True)
     for r in range(world):
         assert np.array_equal(out[r], np.array([1.0 + 2.0 + 3.0, 10.0 + 20.0 + 30.0, 3.0, 1.0]))
+
+
+def _worker_auto_dt(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from thetis_b200 import solver2d
+        from thetis_b200.parallel import distribute_mesh
+        from thetis_b200.shim import Function, FunctionSpace
+        sm = distribute_mesh(_mesh(), rank, world, halo="vertex", transport="nccl")
+        b = Function(FunctionSpace(sm, "CG", 1)).interpolate(lambda x, y: 5.0 + 0.4 * x)    # deepest at large x
+        s = solver2d.FlowSolver2d(sm, b)
+        assert s.options.swe_timestepper_options.use_automatic_timestep      # the reference's default (options.py:26)
+        s.create_function_spaces()
+        s.create_fields()
+        s.set_time_step()
+        out[rank] = float(s.dt)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_automatic_timestep_is_min_reduced_over_ranks_gloo():
+    """solver2d.py:241: dt = comm.allreduce(dt, op=MPI.MIN) -- every rank of a distributed run must advance with the same
+    time step, and it is the most restrictive one (close to the serial value: the local P1 projections differ from
+    the global one only near the cuts)."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_auto_dt, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] == out[1]
+    from thetis_b200 import solver2d
+    from thetis_b200.shim import Function, FunctionSpace, as_shim_mesh
+    sm = as_shim_mesh(_mesh())
+    b = Function(FunctionSpace(sm, "CG", 1)).interpolate(lambda x, y: 5.0 + 0.4 * x)
+    s = solver2d.FlowSolver2d(sm, b)
+    s.create_function_spaces()
+    s.create_fields()
+    s.set_time_step()
+    assert abs(out[0] - s.dt) / s.dt < 0.05

@@ -17,10 +17,10 @@ TB_OK = 0
 OPT_G_GRAV, OPT_RHO0, OPT_NONLINEAR, OPT_LAX_FRIEDRICHS, OPT_LF_SCALING, OPT_NORM_SMOOTHER, \
     OPT_WETTING_DRYING, OPT_WD_ALPHA, OPT_LF_TRACER, OPT_LF_TRACER_SCALING, OPT_TRACER_VEL_FACTOR, \
     OPT_FORCE_GENERIC_KERNEL, OPT_SIPG_FACTOR, OPT_SIPG_FACTOR_TRACER, OPT_GRAD_DIV_VISCOSITY, \
-    OPT_GRAD_DEPTH_VISCOSITY, OPT_TRACER_CONSERVATIVE, OPT_MOMENTUM_ADVECTION = range(18)
+    OPT_GRAD_DEPTH_VISCOSITY, OPT_TRACER_CONSERVATIVE, OPT_MOMENTUM_ADVECTION, OPT_VON_KARMAN = range(19)
 # tb_field
 F_BATHYMETRY, F_CORIOLIS, F_MANNING, F_QUAD_DRAG, F_LINEAR_DRAG, F_WIND_STRESS, F_ATM_PRESSURE, \
-    F_MOMENTUM_SOURCE, F_VOLUME_SOURCE, F_TRACER_SOURCE, F_VISCOSITY, F_DIFFUSIVITY = range(12)
+    F_MOMENTUM_SOURCE, F_VOLUME_SOURCE, F_TRACER_SOURCE, F_VISCOSITY, F_DIFFUSIVITY, F_NIKURADSE, F_WD_ALPHA = range(14)
 BC_ELEV, BC_UV, BC_UN, BC_FLUX, BC_VALUE, BC_DIFF_FLUX = 1, 2, 4, 8, 16, 64
 
 
@@ -57,7 +57,10 @@ SIGNATURES = {
     "tb_set_option": (_I, [_P, _I, _D]),
     "tb_set_field_const": (_I, [_P, _I, _P, _I]),
     "tb_set_field_vertex": (_I, [_P, _I, _P, _I]),
+    "tb_set_field_cell": (_I, [_P, _I, _P, _I, _P]),
     "tb_clear_field": (_I, [_P, _I]),
+    "tb_sync_fields": (_I, [_P, _P]),
+    "tb_clear_bc": (_I, [_P, _I, _I]),
     "tb_set_bc": (_I, [_P, _I, _I, _I, _P]),
     "tb_set_bc_array": (_I, [_P, _I, _I, _I, _P, _I, _P]),
     "tb_set_boundary_length": (_I, [_P, _I, _D]),

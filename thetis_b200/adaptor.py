@@ -22,21 +22,87 @@ import numpy as np
 
 from .mesh import Mesh2D, FACET_NODES, sfc_renumber
 
-__all__ = ["MeshAdaptor", "is_constant", "is_function", "constant_value", "get_adaptor"]
+__all__ = ["MeshAdaptor", "is_constant", "is_function", "is_expression", "constant_value", "get_adaptor",
+           "expression_leaves", "expression_degree"]
+
+
+def _space_of(x):
+    """`x.function_space()` or None.  A real firedrake.Constant has the method too -- it returns None."""
+    fs = getattr(x, "function_space", None)
+    if fs is None or not callable(fs):
+        return None
+    try:
+        return fs()
+    except Exception:
+        return None
 
 
 def is_function(x):
-    return hasattr(x, "function_space") and hasattr(x, "dat") or hasattr(x, "subfunctions") and hasattr(x, "function_space")
+    """A Function: lives in a function space and carries data (`dat`, or `subfunctions` for a mixed one)."""
+    return _space_of(x) is not None and (hasattr(x, "dat") or hasattr(x, "subfunctions"))
 
 
 def is_constant(x):
+    """Plain numbers, or a Constant: has `values()` and no function space (classified by capability, because a real
+    firedrake.Constant also has `.dat` and `.function_space()`)."""
     if isinstance(x, (int, float, np.integer, np.floating)):
         return True
     if isinstance(x, (tuple, list)) and all(isinstance(v, (int, float, np.integer, np.floating)) for v in x):
         return True
     if isinstance(x, np.ndarray) and x.ndim <= 1 and x.size <= 3:
         return True
-    return hasattr(x, "values") and callable(x.values) and not hasattr(x, "dat")
+    return hasattr(x, "values") and callable(x.values) and _space_of(x) is None
+
+
+def is_expression(x):
+    """A UFL expression tree that is neither a Function nor a Constant (e.g. `elev_ramp * elev_tide_2d`)."""
+    return hasattr(x, "ufl_operands") and not is_function(x) and not is_constant(x)
+
+
+def expression_leaves(expr):
+    """The Functions and Constants an expression reads (its change stamp is the tuple of theirs)."""
+    out = []
+
+    def walk(e):
+        if is_function(e) or (is_constant(e) and hasattr(e, "values")):
+            if not any(e is o for o in out):
+                out.append(e)
+            return
+        for o in getattr(e, "ufl_operands", ()):
+            walk(o)
+    walk(expr)
+    return out
+
+
+_SHIM_KINDS = {"mul", "add", "sub", "div", "lt", "gt", "le", "ge", "conditional", "vector"}
+
+
+def expression_degree(expr):
+    """Polynomial degree of an expression in its Function operands (P1 Functions count 1, Constants 0); None when it
+    is not a polynomial (division by a Function, a condition that depends on a Function).  Degree <= 1 means nodal
+    evaluation reproduces the expression exactly, which is what the accelerated path requires."""
+    if is_constant(expr):
+        return 0
+    if is_function(expr):
+        return 1
+    kind = getattr(expr, "kind", None)
+    if kind is None:           # real UFL
+        from ufl.algorithms import estimate_total_polynomial_degree
+        return estimate_total_polynomial_degree(expr)
+    ops = [expression_degree(o) for o in expr.ufl_operands]
+    if any(d is None for d in ops):
+        return None
+    if kind == "mul":
+        return sum(ops)
+    if kind in ("add", "sub", "vector"):
+        return max(ops)
+    if kind == "div":
+        return ops[0] if ops[1] == 0 else None
+    if kind in ("lt", "gt", "le", "ge"):
+        return 0 if max(ops) == 0 else None
+    if kind == "conditional":
+        return max(ops[1:]) if ops[0] == 0 else None
+    return None
 
 
 def constant_value(x):
@@ -177,26 +243,96 @@ class MeshAdaptor:
         data = np.asarray(func.dat.data_ro)
         return data[self._cell_nodes(fs)]
 
-    def vertex_values(self, func):
+    def evaluate(self, expr):
         """
-        Values of a P1 (CG, or continuous DG) Function at the device mesh's
-        geometric vertices.  Discontinuous coefficients are outside the
-        accelerated path.
+        (nt, 3[,k]) nodal values, at the device cells' nodes, of a Function or of an expression over Functions and
+        Constants that is affine in its Function operands (e.g. `elev_ramp * elev_tide_2d`,
+        examples/north_sea/model_config.py:188-192): evaluating it at the nodes and interpolating linearly is then
+        identical to evaluating the UFL expression at the quadrature points.  Anything of higher degree must be
+        interpolated into a P1 Function by the caller (a modelling decision the library does not take silently).
         """
-        nodal = self.nodal_values(func)
+        if is_function(expr):
+            return self.nodal_values(expr)
+        if is_constant(expr):
+            v = constant_value(expr)
+            return np.broadcast_to(v if v.size > 1 else v[0], (self.mesh.n_cells, 3) + ((v.size,) if v.size > 1 else ()))
+        deg = expression_degree(expr)
+        if deg is None or deg > 1:
+            raise NotImplementedError(
+                "expression is not affine in its Function operands: interpolate it into a P1 / P1DG Function first")
+        kind = getattr(expr, "kind", None)
+        if kind is None:
+            # real UFL: let Firedrake do the nodal evaluation (exact for degree <= 1).  UNTESTED HERE (no Firedrake).
+            import firedrake as fd
+            mesh_obj = self.mesh_obj_ref()
+            shape = getattr(expr, "ufl_shape", ())
+            fs = fd.VectorFunctionSpace(mesh_obj, "DG", 1) if shape else fd.FunctionSpace(mesh_obj, "DG", 1)
+            return self.nodal_values(fd.Function(fs).interpolate(expr))
+        ops = [self.evaluate(o) for o in expr.ufl_operands]
+        if kind == "mul":
+            a, b = ops
+            if a.ndim < b.ndim:
+                a = a[..., None]
+            elif b.ndim < a.ndim:
+                b = b[..., None]
+            return a * b
+        if kind == "add":
+            return ops[0] + ops[1]
+        if kind == "sub":
+            return ops[0] - ops[1]
+        if kind == "div":
+            return ops[0] / ops[1]
+        if kind == "lt":
+            return ops[0] < ops[1]
+        if kind == "gt":
+            return ops[0] > ops[1]
+        if kind == "le":
+            return ops[0] <= ops[1]
+        if kind == "ge":
+            return ops[0] >= ops[1]
+        if kind == "conditional":
+            return np.where(ops[0], ops[1], ops[2])
+        if kind == "vector":
+            return np.stack(ops, axis=-1)
+        raise NotImplementedError(f"expression node {kind!r}")
+
+    def coefficient_values(self, func):
+        """
+        ('vertex', (nv[,k])) for a continuous field (P1 CG, or a P1DG Function whose values agree at shared
+        vertices), else ('cell', (nt, 3[,k])) for a genuinely discontinuous P1DG one (e.g. Coriolis / sources
+        projected into H_2d, test/swe2d/test_steady_state_basin_mms.py:169-177).
+        """
+        nodal = np.asarray(self.evaluate(func), dtype=np.float64)
         vert = np.zeros((self.mesh.n_vertices,) + nodal.shape[2:])
         vert[self.mesh.cells] = nodal
         err = np.abs(vert[self.mesh.cells] - nodal).max() if nodal.size else 0.0
         scale = max(np.abs(nodal).max() if nodal.size else 0.0, 1e-300)
         if err > 1e-10 * scale:
-            raise NotImplementedError("discontinuous coefficient fields are not supported on the accelerated path")
-        return vert
+            return "cell", np.ascontiguousarray(nodal)
+        return "vertex", vert
+
+    def vertex_values(self, func):
+        """
+        Values of a continuous P1 field (CG, or continuous DG) at the device mesh's geometric vertices; raises for
+        discontinuous data (coefficients of facet terms -- bathymetry, viscosity, diffusivity, wetting-drying alpha --
+        must be continuous on the accelerated path).
+        """
+        kind, vals = self.coefficient_values(func)
+        if kind != "vertex":
+            raise NotImplementedError("this coefficient enters facet terms and must be continuous: discontinuous "
+                                      "fields are not supported on the accelerated path")
+        return vals
 
     def bfacet_values(self, func, marker=None):
         """
         (nb, 2[,k]) values of a P1/P1DG Function at the two nodes of every exterior facet.  With ``marker`` only
         the rows of that marker are evaluated (the rest of the returned, reused, buffer is untouched).
         """
+        if not is_function(func):
+            # expression over Functions / Constants (affine): nodal evaluation, then the facet nodes
+            nodal = np.asarray(self.evaluate(func), dtype=np.float64)
+            m = self.mesh
+            return np.stack([nodal[m.bf_cell, FACET_NODES[m.bf_lf, 0]], nodal[m.bf_cell, FACET_NODES[m.bf_lf, 1]]], axis=1)
         fs = func.function_space()
         cache = self.__dict__.setdefault("_bf_nodes", {})
         idx = cache.get(id(fs))

@@ -17,7 +17,9 @@ class GeneralCoupledTimeIntegrator2D:
         self.fields = solver.fields
         self.swe_integrator = integrators.get("shallow_water")
         self.tracer_integrator = integrators.get("tracer")
-        self.timesteppers = {}
+        # attribute access like the reference's AttrDict (tests reach for `.timesteppers.tracer_2d`,
+        # test/tracerEq/test_h-advection_mes_2d.py:97)
+        self.timesteppers = type(solver.fields)()
         self._initialized = False
         if not self.options.tracer_only:
             self.timesteppers["swe2d"] = solver.get_swe_timestepper(self.swe_integrator)

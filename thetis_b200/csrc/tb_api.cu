@@ -6,18 +6,31 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <nvtx3/nvToolsExt.h>
 #include "tb_internal.h"
 
 #define TB_BC_PRESENT 32
 
+// NVTX range over one C-ABI call (header-only NVTX 3: a no-op unless a profiler is attached); the ranges name the
+// phases of a step in an Nsight Systems timeline: tb_swe_stage[_fused], tb_tracer_stage, tb_limiter_apply,
+// tb_push_cells, tb_sync_fields, tb_set_bc_array.
+struct TbRange {
+    explicit TbRange(const char *name) { nvtxRangePushA(name); }
+    ~TbRange() { nvtxRangePop(); }
+};
+
 static thread_local std::string g_create_error;
 
 struct FieldStore {
-    int mode = 0;            // 0 none, 1 const, 2 vertex
+    int mode = 0;            // 0 none, 1 const, 2 vertex (P1), 3 cell nodes (P1DG)
     int ncomp = 1;
     double v[2] = {0, 0};
     std::vector<double> vert;   // [nv*ncomp]
     int col = -1;
+    bool col_dirty = false;     // mode 2: `vert` changed, the columns of the static blocks are stale (tb_sync_fields)
+    double *d_cell = nullptr;   // mode 3: DEVICE [n_owned_pad*3*ncomp]
+    double *h_cell = nullptr;   // mode 3: pinned staging copy
+    cudaEvent_t cell_event = nullptr;
 };
 
 struct tb_ctx {
@@ -46,6 +59,9 @@ struct tb_ctx {
     std::vector<long long> slot_row0;            // first compact row of each slot
     double *d_ext[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // elev, uv, un, flux, value (swe)
     double *d_ext_tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int32_t *d_patch_vglob = nullptr;   // [n_patches*NV] device copy of patch_vglob (stream-ordered column updates)
+    double *d_vert = nullptr, *h_vert = nullptr;     // staging of one vertex field (device / pinned), [n_vertices*2]
+    cudaEvent_t vert_event = nullptr;
     double *d_area = nullptr;
     double *d_bath3 = nullptr;      // bathymetry at the 3 nodes of every owned cell (diagnostics)
     double *d_partial = nullptr;    // scratch of the two-pass reductions
@@ -69,7 +85,7 @@ struct tb_ctx {
     int lf_tracer = 0;
     int force_generic = 0;
     double lf_tracer_sigma = 1.0, tracer_vel_factor = 1.0;
-    double sipg = 1.0, sipg_tracer = 1.0;
+    double sipg = 1.0, sipg_tracer = 1.0, von_karman = 0.4;
     int graddiv = 0, graddepth = 1, tracer_conservative = 0, momentum_advection = 1;
     FieldStore fields[TB_F_COUNT];
     // bcs: eq 0 swe, 1 tracer
@@ -229,9 +245,11 @@ static int upload_halo_tables(tb_ctx *ctx) {
 static int upload_layout(tb_ctx *ctx) {
     // SIPG terms need the geometry of the halo cells: rebuild the patch tables when that requirement changes
     const bool need_hgeom = ctx->fields[TB_F_VISCOSITY].mode != 0 || ctx->fields[TB_F_DIFFUSIVITY].mode != 0;
-    if (need_hgeom != ctx->halo_geom) {
+    // (sticky: several tracers with and without diffusivity share one context; switching back would rebuild the
+    // tables on every change of owner)
+    if (need_hgeom && !ctx->halo_geom) {
         CK(cudaDeviceSynchronize());
-        ctx->halo_geom = need_hgeom;
+        ctx->halo_geom = true;
         int rc = build_patches(ctx);
         if (rc != TB_OK) return rc;
         rc = upload_halo_tables(ctx);
@@ -310,8 +328,52 @@ static int upload_layout(tb_ctx *ctx) {
     ctx->pl.off_hcv = ctx->halo_geom ? (int)off_hcv : -1;
     ctx->pl.halo_ids = ctx->d_halo_ids;
     ctx->pl.halo_cnt = ctx->d_halo_cnt;
+    if (ctx->d_patch_vglob) cudaFree(ctx->d_patch_vglob);
+    ctx->d_patch_vglob = nullptr;
+    CK(cudaMalloc(&ctx->d_patch_vglob, sizeof(int32_t) * std::max<size_t>(ctx->patch_vglob.size(), 4)));
+    CK(cudaMemcpy(ctx->d_patch_vglob, ctx->patch_vglob.data(), sizeof(int32_t) * ctx->patch_vglob.size(),
+                  cudaMemcpyHostToDevice));
+    for (int f = 0; f < TB_F_COUNT; ++f) ctx->fields[f].col_dirty = false;
     ctx->layout_dirty = false;
     return TB_OK;
+}
+
+// Stream-ordered refresh of coefficient data that changed since the last launch.  A P1 field whose VALUES changed
+// (time-dependent wind stress / atmospheric pressure assigned in update_forcings) only rewrites its own columns of
+// the per-patch static blocks: pinned staging copy -> async H2D -> one scatter kernel on `stream`; no device-wide
+// synchronisation, so it is cheap every RK stage.  Structural changes (a field appearing / disappearing, bathymetry,
+// the SIPG halo geometry) still rebuild the blocks (set-up time only).
+static int sync_fields(tb_ctx *ctx, cudaStream_t st) {
+    if (ctx->layout_dirty) {
+        TbRange r("tb_sync_fields:rebuild_layout");
+        return upload_layout(ctx);
+    }
+    for (int f = 1; f < TB_F_COUNT; ++f) {
+        FieldStore &fs = ctx->fields[f];
+        if (fs.mode != 2 || !fs.col_dirty) continue;
+        TbRange r("tb_sync_fields:update_columns");
+        const size_t n = (size_t)ctx->n_vertices * fs.ncomp;
+        if (!ctx->d_vert) {
+            CK(cudaMalloc(&ctx->d_vert, sizeof(double) * 2 * ctx->n_vertices));
+            CK(cudaMallocHost(&ctx->h_vert, sizeof(double) * 2 * ctx->n_vertices));
+            CK(cudaEventCreateWithFlags(&ctx->vert_event, cudaEventDisableTiming));
+        } else {
+            CK(cudaEventSynchronize(ctx->vert_event));       // the previous staging copy has been consumed
+        }
+        memcpy(ctx->h_vert, fs.vert.data(), sizeof(double) * n);
+        CK(cudaMemcpyAsync(ctx->d_vert, ctx->h_vert, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        CK(tb_launch_update_columns(ctx->d_sblk, ctx->pl.stride, ctx->NV, ctx->n_patches, ctx->d_patch_vglob, ctx->d_vert,
+                                    fs.col, fs.ncomp, st));
+        CK(cudaEventRecord(ctx->vert_event, st));
+        ctx->launches += 1;
+        fs.col_dirty = false;
+    }
+    return TB_OK;
+}
+
+extern "C" int tb_sync_fields(tb_ctx *ctx, void *stream) {
+    if (!ctx) return TB_ERR_ARG;
+    return sync_fields(ctx, (cudaStream_t)stream);
 }
 
 static void default_quadrature(tb_ctx *ctx) {
@@ -455,6 +517,15 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_bf_slot);
     cudaFree(ctx->d_bf_row);
     cudaFree(ctx->d_area);
+    cudaFree(ctx->d_patch_vglob);
+    cudaFree(ctx->d_vert);
+    if (ctx->h_vert) cudaFreeHost(ctx->h_vert);
+    if (ctx->vert_event) cudaEventDestroy(ctx->vert_event);
+    for (int f = 0; f < TB_F_COUNT; ++f) {
+        cudaFree(ctx->fields[f].d_cell);
+        if (ctx->fields[f].h_cell) cudaFreeHost(ctx->fields[f].h_cell);
+        if (ctx->fields[f].cell_event) cudaEventDestroy(ctx->fields[f].cell_event);
+    }
     cudaFree(ctx->d_bath3);
     cudaFree(ctx->d_partial);
     cudaFree(ctx->d_stage_partial);
@@ -515,6 +586,7 @@ extern "C" int tb_set_option(tb_ctx *ctx, int option, double value) {
         case TB_OPT_GRAD_DEPTH_VISCOSITY: ctx->graddepth = value != 0.0; break;
         case TB_OPT_TRACER_CONSERVATIVE: ctx->tracer_conservative = value != 0.0; break;
         case TB_OPT_MOMENTUM_ADVECTION: ctx->momentum_advection = value != 0.0; break;
+        case TB_OPT_VON_KARMAN: ctx->von_karman = value; break;
         default: return fail(ctx, TB_ERR_ARG, "unknown option");
     }
     return TB_OK;
@@ -540,10 +612,45 @@ extern "C" int tb_set_field_vertex(tb_ctx *ctx, int field, const double *values,
     if (!ctx || !values || field < 0 || field >= TB_F_COUNT) return fail(ctx, TB_ERR_ARG, "bad field");
     if (ncomp != field_ncomp(field)) return fail(ctx, TB_ERR_ARG, "wrong number of components");
     FieldStore &fs = ctx->fields[field];
+    // same field, same shape, new values: only its columns are refreshed (sync_fields); bathymetry also feeds the
+    // diagnostics tables and a new field changes the block layout: full rebuild
+    if (fs.mode == 2 && fs.ncomp == ncomp && field != TB_F_BATHYMETRY && !ctx->layout_dirty) fs.col_dirty = true;
+    else ctx->layout_dirty = true;
     fs.mode = 2;
     fs.ncomp = ncomp;
     fs.vert.assign(values, values + (size_t)ctx->n_vertices * ncomp);
-    ctx->layout_dirty = true;
+    return TB_OK;
+}
+
+extern "C" int tb_set_field_cell(tb_ctx *ctx, int field, const double *values, int ncomp, void *stream) {
+    if (!ctx || !values || field < 0 || field >= TB_F_COUNT) return fail(ctx, TB_ERR_ARG, "bad field");
+    if (ncomp != field_ncomp(field)) return fail(ctx, TB_ERR_ARG, "wrong number of components");
+    if (field == TB_F_BATHYMETRY || field == TB_F_VISCOSITY || field == TB_F_DIFFUSIVITY || field == TB_F_WD_ALPHA)
+        return fail(ctx, TB_ERR_UNSUPPORTED,
+                    "this coefficient enters facet terms and must be continuous (P1): discontinuous data are outside "
+                    "the accelerated path");
+    FieldStore &fs = ctx->fields[field];
+    const size_t n_owned3 = (size_t)ctx->n_owned * 3 * ncomp, n_pad3 = (size_t)ctx->n_owned_pad * 3 * ncomp;
+    if (fs.mode == 2) ctx->layout_dirty = true;
+    if (fs.d_cell && fs.ncomp != ncomp) {
+        cudaFree(fs.d_cell);
+        cudaFreeHost(fs.h_cell);
+        fs.d_cell = fs.h_cell = nullptr;
+    }
+    if (!fs.d_cell) {
+        CK(cudaMalloc(&fs.d_cell, sizeof(double) * n_pad3));
+        CK(cudaMemset(fs.d_cell, 0, sizeof(double) * n_pad3));
+        CK(cudaMallocHost(&fs.h_cell, sizeof(double) * n_owned3));
+        if (!fs.cell_event) CK(cudaEventCreateWithFlags(&fs.cell_event, cudaEventDisableTiming));
+    } else {
+        CK(cudaEventSynchronize(fs.cell_event));
+    }
+    memcpy(fs.h_cell, values, sizeof(double) * n_owned3);
+    CK(cudaMemcpyAsync(fs.d_cell, fs.h_cell, sizeof(double) * n_owned3, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CK(cudaEventRecord(fs.cell_event, (cudaStream_t)stream));
+    fs.mode = 3;
+    fs.ncomp = ncomp;
+    fs.vert.clear();
     return TB_OK;
 }
 
@@ -581,6 +688,17 @@ extern "C" int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const doub
     return TB_OK;
 }
 
+extern "C" int tb_clear_bc(tb_ctx *ctx, int eq, int marker) {
+    if (!ctx || eq < 0 || eq > 1) return fail(ctx, TB_ERR_ARG, "bad equation id");
+    const int s = find_slot(ctx, marker);
+    if (s < 0) return TB_OK;
+    TbBcSlot &b = ctx->bc[eq][s];
+    b.opcode = 0;            // not even TB_BC_PRESENT: the marker has no entry in bnd_conditions (closed boundary)
+    b.arr_mask = 0;
+    b.elev = b.uvx = b.uvy = b.un = b.flux = b.value = b.diff_flux = 0.0;
+    return TB_OK;
+}
+
 extern "C" int tb_set_boundary_length(tb_ctx *ctx, int marker, double length) {
     if (!ctx) return TB_ERR_ARG;
     const int s = find_slot(ctx, marker);
@@ -592,6 +710,7 @@ extern "C" int tb_set_boundary_length(tb_ctx *ctx, int marker, double length) {
 
 extern "C" int tb_set_bc_array(tb_ctx *ctx, int eq, int marker, int tag, const double *values, int ncomp,
                                void *stream) {
+    TbRange range("tb_set_bc_array");
     if (!ctx || eq < 0 || eq > 1 || !values) return fail(ctx, TB_ERR_ARG, "bad argument");
     const int s = find_slot(ctx, marker);
     if (s < 0) return TB_OK;
@@ -651,6 +770,8 @@ static void fill_coef(const FieldStore &fs, TbCoef &c) {
     c.col = fs.col;
     c.v0 = fs.v[0];
     c.v1 = fs.v[1];
+    c.cell = fs.d_cell;
+    c.nc = fs.ncomp;
 }
 
 static void fill_bc(tb_ctx *ctx, int eq, TbBcTable &t) {
@@ -677,15 +798,18 @@ static void patch_range(tb_ctx *ctx, long long &first, long long &count) {
 
 static int swe_stage_impl(tb_ctx *ctx, double a0, double a1, double b_dt, const double *u_in, const double *u0,
                           double *u_out, const unsigned long long *push_dst, void *stream) {
+    TbRange range(push_dst ? "tb_swe_stage_fused" : "tb_swe_stage");
     if (!ctx || !u_in || !u_out) return fail(ctx, TB_ERR_ARG, "null state pointer");
     if (u_in == u_out) return fail(ctx, TB_ERR_ARG, "u_out must not alias u_in");
     if (a0 != 0.0 && !u0) return fail(ctx, TB_ERR_ARG, "u0 required when a0 != 0");
     if (ctx->fields[TB_F_MANNING].mode && ctx->fields[TB_F_QUAD_DRAG].mode)
         return fail(ctx, TB_ERR_ARG, "Cannot set both dimensionless and Manning drag parameter");
-    if (ctx->layout_dirty) {
-        int rc = upload_layout(ctx);
+    {
+        int rc = sync_fields(ctx, (cudaStream_t)stream);
         if (rc != TB_OK) return rc;
     }
+    if ((ctx->fields[TB_F_MANNING].mode || ctx->fields[TB_F_QUAD_DRAG].mode) && ctx->fields[TB_F_NIKURADSE].mode)
+        return fail(ctx, TB_ERR_ARG, "Cannot set both Nikuradse drag and Manning / dimensionless drag parameter");
     TbSweParams p;
     memset(&p, 0, sizeof(p));
     p.u_in = u_in;
@@ -712,10 +836,17 @@ static int swe_stage_impl(tb_ctx *ctx, double a0, double a1, double b_dt, const 
     fill_coef(ctx->fields[TB_F_MOMENTUM_SOURCE], p.msrc);
     fill_coef(ctx->fields[TB_F_VOLUME_SOURCE], p.vsrc);
     fill_coef(ctx->fields[TB_F_VISCOSITY], p.visc);
+    fill_coef(ctx->fields[TB_F_NIKURADSE], p.nik);
+    fill_coef(ctx->fields[TB_F_WD_ALPHA], p.wda);
+    if (p.wda.mode == 1) {       // a Constant given as a field: same as the scalar option
+        p.wd_alpha2 = p.wda.v0 * p.wda.v0;
+        p.wda.mode = 0;
+    }
+    p.kappa = ctx->von_karman;
     p.sipg = ctx->sipg;
     p.graddiv = ctx->graddiv;
     p.graddepth = ctx->graddepth;
-    p.use_quad = (p.man.mode || p.cd.mode || p.wind.mode || p.wd_on) ? 1 : 0;
+    p.use_quad = (p.man.mode || p.cd.mode || p.nik.mode || p.wind.mode || p.wd_on) ? 1 : 0;
     p.nquad = ctx->nquad;
     p.force_generic = ctx->force_generic;
     p.adv_on = ctx->momentum_advection;
@@ -839,11 +970,12 @@ extern "C" int tb_swe_tendency(tb_ctx *ctx, const double *u, double *k_out, void
 
 extern "C" int tb_tracer_stage(tb_ctx *ctx, double a0, double a1, double b_dt, const double *c_in, const double *c0,
                                double *c_out, const double *swe_state, void *stream) {
+    TbRange range("tb_tracer_stage");
     if (!ctx || !c_in || !c_out || !swe_state) return fail(ctx, TB_ERR_ARG, "null state pointer");
     if (c_in == c_out) return fail(ctx, TB_ERR_ARG, "c_out must not alias c_in");
     if (a0 != 0.0 && !c0) return fail(ctx, TB_ERR_ARG, "c0 required when a0 != 0");
-    if (ctx->layout_dirty) {
-        int rc = upload_layout(ctx);
+    {
+        int rc = sync_fields(ctx, (cudaStream_t)stream);
         if (rc != TB_OK) return rc;
     }
     TbTracerParams p;
@@ -947,6 +1079,7 @@ static int limiter_setup(tb_ctx *ctx) {
 }
 
 extern "C" int tb_limiter_apply(tb_ctx *ctx, double *c, void *stream) {
+    TbRange range("tb_limiter_apply");
     if (!ctx || !c) return fail(ctx, TB_ERR_ARG, "null pointer");
     if (!ctx->lim_ready) {
         int rc = limiter_setup(ctx);
@@ -986,8 +1119,8 @@ extern "C" int tb_tracer_to_field(tb_ctx *ctx, const double *c, const int32_t *n
 }
 extern "C" int tb_swe_integrals(tb_ctx *ctx, const double *state, double *out, void *stream) {
     if (!ctx || !state || !out) return fail(ctx, TB_ERR_ARG, "null pointer");
-    if (ctx->layout_dirty) {
-        int rc = upload_layout(ctx);
+    {
+        int rc = sync_fields(ctx, (cudaStream_t)stream);
         if (rc != TB_OK) return rc;
     }
     CK(tb_launch_swe_integrals(state, ctx->d_area, ctx->d_bath3, ctx->n_owned, ctx->d_partial, out, (cudaStream_t)stream));
@@ -1009,8 +1142,8 @@ extern "C" int tb_stage_integrals_finish(tb_ctx *ctx, double *out, void *stream)
 extern "C" int tb_tracer_integrals(tb_ctx *ctx, const double *c, const double *swe_state, double *out, void *stream) {
     if (!ctx || !c || !out) return fail(ctx, TB_ERR_ARG, "null pointer");
     if (ctx->nonlinear && !swe_state) return fail(ctx, TB_ERR_ARG, "swe_state required for the nonlinear total depth");
-    if (ctx->layout_dirty) {
-        int rc = upload_layout(ctx);
+    {
+        int rc = sync_fields(ctx, (cudaStream_t)stream);
         if (rc != TB_OK) return rc;
     }
     CK(tb_launch_tracer_integrals(c, swe_state, ctx->d_area, ctx->d_bath3, ctx->n_owned, ctx->nonlinear,
@@ -1046,6 +1179,7 @@ extern "C" int tb_scatter_cells(tb_ctx *ctx, const double *buf, const int32_t *i
 }
 extern "C" int tb_push_cells(tb_ctx *ctx, const double *state, const int32_t *idx, const uint64_t *dst_ptrs, int64_t n,
                              int rec_len, void *stream) {
+    TbRange range("tb_push_cells");
     if (!ctx || (n > 0 && (!state || !idx || !dst_ptrs))) return fail(ctx, TB_ERR_ARG, "null pointer");
     CK(tb_launch_push_cells(state, idx, reinterpret_cast<const unsigned long long *>(dst_ptrs), n, rec_len,
                             (cudaStream_t)stream));

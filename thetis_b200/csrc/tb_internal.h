@@ -12,11 +12,14 @@
 #define TB_MAX_SLOTS 16     // distinct boundary markers
 #define TB_MAX_QUAD 12      // max cell quadrature points
 
-// coefficient descriptor: mode 0 = None, 1 = Constant, 2 = P1 vertex column(s)
+// coefficient descriptor: mode 0 = None, 1 = Constant, 2 = P1 vertex column(s) of the static block,
+// 3 = discontinuous P1DG field stored per cell node: cell[(cell*3 + node)*nc + comp] (generic kernels only)
 struct TbCoef {
     int mode;
     int col;
     double v0, v1;
+    const double *cell;
+    int nc, pad_;
 };
 
 struct TbBcSlot {
@@ -92,7 +95,8 @@ struct TbSweParams {
     const TbHaloFused *halo;      // optional (device): fused halo exchange, CTAs [0, n_bpatch) push
     const unsigned long long *push_dst;   // [n_entries] peer addresses of the pushed records for THIS output buffer
     int n_bpatch, pad1_;
-    TbCoef cor, man, cd, lin, wind, pa, msrc, vsrc, visc;
+    TbCoef cor, man, cd, lin, wind, pa, msrc, vsrc, visc, nik, wda;
+    double kappa;                 // physical_constants['von_karman'] (Nikuradse drag)
     double sipg;                  // sipg_factor (HorizontalViscosityTerm, shallowwater_eq.py:558)
     int graddiv, graddepth;       // use_grad_div_viscosity_term, use_grad_depth_viscosity_term
     TbBcTable bc;
@@ -148,6 +152,8 @@ cudaError_t tb_launch_scatter_cells(const double *buf, const int32_t *idx, long 
 cudaError_t tb_launch_push_cells(const double *state, const int32_t *idx, const unsigned long long *dst, long long n,
                                  int rec, cudaStream_t s);
 cudaError_t tb_launch_halo_fused_wait(const TbHaloFused *hf, cudaStream_t s);
+cudaError_t tb_launch_update_columns(unsigned char *sblk, long long stride, int NV, long long n_patches,
+                                     const int32_t *patch_vglob, const double *vert, int col, int ncomp, cudaStream_t s);
 cudaError_t tb_launch_patch_partials_final(const double *partial, long long n, double *out, cudaStream_t s);
 cudaError_t tb_launch_swe_integrals(const double *state, const double *area, const double *bath3, long long n_owned,
                                     double *partial, double *out, cudaStream_t s);

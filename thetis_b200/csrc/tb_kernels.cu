@@ -305,9 +305,10 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         const bool has_cor = SP::generic ? (prm.cor.mode != 0) : SP::cor;
         const bool has_man = SP::generic ? (prm.man.mode != 0) : SP::man;
         const bool has_cd = SP::generic ? (prm.cd.mode != 0) : false;
+        const bool has_nik = SP::generic ? (prm.nik.mode != 0) : false;      // nikuradse_bed_roughness (:689-697)
         const bool has_lin = SP::generic ? (prm.lin.mode != 0) : SP::lin;
         const bool has_wind = SP::generic ? (prm.wind.mode != 0) : SP::wind;
-        const bool has_pa = SP::generic ? (prm.pa.mode == 2) : false;
+        const bool has_pa = SP::generic ? (prm.pa.mode >= 2) : false;
         const bool has_msrc = SP::generic ? (prm.msrc.mode != 0) : false;
         const bool has_vsrc = SP::generic ? (prm.vsrc.mode != 0) : false;
         // ModeSplit2DEquations (shallowwater_eq.py:931-966) has no HorizontalAdvectionTerm although the depth is nonlinear
@@ -340,6 +341,20 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         const double twoA = (x[1] - x[0]) * (y[2] - y[0]) - (y[1] - y[0]) * (x[2] - x[0]);
 
         double Rux[3] = {0, 0, 0}, Ruy[3] = {0, 0, 0}, Re[3] = {0, 0, 0};
+
+        // coefficient at local node a: Constant, P1 vertex column of the static block, or (generic kernel only) a
+        // genuinely discontinuous P1DG field stored per cell node (tb_set_field_cell)
+        auto cf = [&](const TbCoef &c, int a, int comp = 0) -> double {
+            if (SP::generic && c.mode == 3) return __ldg(c.cell + ((cell0 + ct) * 3 + a) * c.nc + comp);
+            return coef_at(c, cols, NV, v[a], comp);
+        };
+        // wetting_and_drying_alpha as a P1 field (solver2d.py:279-287): alpha^2 at a point from the nodal values
+        const bool var_al = SP::generic && wd_on && prm.wda.mode == 2;
+        double al[3] = {0, 0, 0};
+        if (var_al) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) al[a] = coef_at(prm.wda, cols, NV, v[a]);
+        }
 
         // ---------------- volume terms (closed-form P1 integrals) ----------------
         const double sux = ux[0] + ux[1] + ux[2], suy = uy[0] + uy[1] + uy[2];
@@ -398,7 +413,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             // CoriolisTerm (:632-633): R_x += int f u_y phi, R_y -= int f u_x phi
             double f[3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) f[a] = coef_at(prm.cor, cols, NV, v[a]);
+            for (int a = 0; a < 3; ++a) f[a] = cf(prm.cor, a);
             const double F = f[0] + f[1] + f[2];
             const double fux_ = f[0] * ux[0] + f[1] * ux[1] + f[2] * ux[2];
             const double fuy_ = f[0] * uy[0] + f[1] * uy[1] + f[2] * uy[2];
@@ -417,7 +432,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             // LinearDragTerm (:734-740): -C u
             double f[3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) f[a] = coef_at(prm.lin, cols, NV, v[a]);
+            for (int a = 0; a < 3; ++a) f[a] = cf(prm.lin, a);
             const double F = f[0] + f[1] + f[2];
             const double fux_ = f[0] * ux[0] + f[1] * ux[1] + f[2] * ux[2];
             const double fuy_ = f[0] * uy[0] + f[1] * uy[1] + f[2] * uy[2];
@@ -433,7 +448,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             double gx = 0, gy = 0;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                const double pa = coef_at(prm.pa, cols, NV, v[a]);
+                const double pa = cf(prm.pa, a);
                 gx += pa * Nx[a];
                 gy += pa * Ny[a];
             }
@@ -449,8 +464,8 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             double fx[3], fy[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                fx[a] = coef_at(prm.msrc, cols, NV, v[a], 0);
-                fy[a] = coef_at(prm.msrc, cols, NV, v[a], 1);
+                fx[a] = cf(prm.msrc, a, 0);
+                fy[a] = cf(prm.msrc, a, 1);
             }
             const double sx = fx[0] + fx[1] + fx[2], sy = fy[0] + fy[1] + fy[2];
 #pragma unroll
@@ -463,7 +478,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             // ContinuitySourceTerm (:824-831)
             double f[3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) f[a] = coef_at(prm.vsrc, cols, NV, v[a]);
+            for (int a = 0; a < 3; ++a) f[a] = cf(prm.vsrc, a);
             const double s = f[0] + f[1] + f[2];
 #pragma unroll
             for (int a = 0; a < 3; ++a) Re[a] += A * (1.0 / 12.0) * (f[a] + s);
@@ -516,8 +531,14 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                     double Hq = hq, fac = 1.0;
                     if (NONLIN && wd_on) {
                         // H = (hl + sqrt(hl^2 + alpha^2))/2, dH/dhl = (1 + hl/sqrt(hl^2 + alpha^2))/2
-                        const double r = tb_rsqrt(hq * hq + a2);
-                        Hq = 0.5 * (hq + (hq * hq + a2) * r);
+                        double a2q = a2;
+                        if (var_al) {
+                            const double aq = l0 * al[0] + l1 * al[1] + l2 * al[2];
+                            a2q = aq * aq;
+                            // NB grad(H) of the wetting-drying depth also has a d/d(alpha) part when alpha varies
+                        }
+                        const double r = tb_rsqrt(hq * hq + a2q);
+                        Hq = 0.5 * (hq + (hq * hq + a2q) * r);
                         fac = 0.5 * (1.0 + hq * r);
                     }
                     const double k = c_qw[qd] * A * (l0 * nuv[0] + l1 * nuv[1] + l2 * nuv[2]) * fac * tb_rcp(Hq);
@@ -532,11 +553,12 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             double mu[3] = {0, 0, 0}, cdn[3] = {0, 0, 0}, twx[3] = {0, 0, 0}, twy[3] = {0, 0, 0};
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                if (has_man) mu[a] = coef_at(prm.man, cols, NV, v[a]);
-                if (has_cd) cdn[a] = coef_at(prm.cd, cols, NV, v[a]);
+                if (has_man) mu[a] = cf(prm.man, a);
+                if (has_cd) cdn[a] = cf(prm.cd, a);
+                if (has_nik) cdn[a] = cf(prm.nik, a);
                 if (has_wind) {
-                    twx[a] = coef_at(prm.wind, cols, NV, v[a], 0);
-                    twy[a] = coef_at(prm.wind, cols, NV, v[a], 1);
+                    twx[a] = cf(prm.wind, a, 0);
+                    twy[a] = cf(prm.wind, a, 1);
                 }
             }
             const double irho = has_wind ? tb_rcp(prm.rho0) : 0.0;
@@ -553,9 +575,16 @@ TB_UNROLL(TB_QUAD_UNROLL)
                 const double uq = l0 * ux[0] + l1 * ux[1] + l2 * ux[2];
                 const double vq = l0 * uy[0] + l1 * uy[1] + l2 * uy[2];
                 double Hq = l0 * hl[0] + l1 * hl[1] + l2 * hl[2];
-                if (NONLIN) Hq = wd_depth(Hq, wd_on, a2);
+                if (NONLIN) {
+                    double a2q = a2;
+                    if (var_al) {
+                        const double aq = l0 * al[0] + l1 * al[1] + l2 * al[2];
+                        a2q = aq * aq;
+                    }
+                    Hq = wd_depth(Hq, wd_on, a2q);
+                }
                 double sx = 0, sy = 0;   // momentum source density at the point
-                if (has_man || has_cd) {
+                if (has_man || has_cd || has_nik) {
                     const double s2 = uq * uq + vq * vq + prm.eps2;
                     const double umag = s2 > 0.0 ? s2 * tb_rsqrt(s2) : 0.0;
                     double k;
@@ -564,6 +593,11 @@ TB_UNROLL(TB_QUAD_UNROLL)
                         const double r = tb_rcbrt(Hq);             // H^(-1/3)
                         const double r2 = r * r;
                         k = g * m * m * (r2 * r2) * umag;          // g mu^2 / H^(1/3) * |u| / H
+                    } else if (has_nik) {
+                        // C_D = 2 kappa^2 / ln(11.036 H / k_s)^2 where H > k_s, else 0 (:697)
+                        const double ks = l0 * cdn[0] + l1 * cdn[1] + l2 * cdn[2];
+                        const double lg = log(11.036 * Hq / ks);
+                        k = Hq > ks ? 2.0 * prm.kappa * prm.kappa / (lg * lg) * umag / Hq : 0.0;
                     } else {
                         k = (l0 * cdn[0] + l1 * cdn[1] + l2 * cdn[2]) * umag * tb_rcp(Hq);
                     }
@@ -663,7 +697,12 @@ TB_UNROLL(TB_GP_UNROLL)
                     double gh, hh;           // g*hbar and hbar/2, hbar = avg(total depth)
                     if (NONLIN && wd_on) {
                         const double hlK = bg + eK, hlN = bg + eN;
-                        const double sig = (hlK + hlN) + (tb_sqrt(fma(hlK, hlK, a2)) + tb_sqrt(fma(hlN, hlN, a2)));   // 4*hbar
+                        double a2g = a2;
+                        if (var_al) {
+                            const double ag = fma(xi, al[q] - al[p], al[p]);      // alpha is continuous (P1)
+                            a2g = ag * ag;
+                        }
+                        const double sig = (hlK + hlN) + (tb_sqrt(fma(hlK, hlK, a2g)) + tb_sqrt(fma(hlN, hlN, a2g)));   // 4*hbar
                         gh = (0.25 * g) * sig;
                         hh = 0.125 * sig;
                     } else {
@@ -739,7 +778,12 @@ TB_UNROLL(TB_GP_UNROLL)
                     const double uKx = wp_ * ux[p] + wq_ * ux[q], uKy = wp_ * uy[p] + wq_ * uy[q];
                     const double eK = wp_ * et[p] + wq_ * et[q];
                     const double bg = wp_ * b[p] + wq_ * b[q];
-                    const double HK = NONLIN ? wd_depth(bg + eK, wd_on, a2) : bg;
+                    double a2b = a2;
+                    if (var_al) {
+                        const double ab = wp_ * al[p] + wq_ * al[q];
+                        a2b = ab * ab;
+                    }
+                    const double HK = NONLIN ? wd_depth(bg + eK, wd_on, a2b) : bg;
                     double fl[6];
                     if (closed) {
                         // land boundary (:376-381), mirror-velocity Lax-Friedrichs (:489-497)
@@ -752,7 +796,7 @@ TB_UNROLL(TB_GP_UNROLL)
                         fl[2] = 0.0;
                     } else {
                         open_boundary_flux<NONLIN>(&prm.bc, gb, slot, wp_, wq_, uKx, uKy, eK, bg, HK, nxs, nys, il, len, g,
-                                                   wd_on, a2, adv_on ? 1 : 0, fl);
+                                                   wd_on, a2b, adv_on ? 1 : 0, fl);
                         if (has_visc && (op & (TB_BC_UV | TB_BC_UN | TB_BC_FLUX))) {
                             // Dirichlet terms of the viscosity (:592-609); 'elev' alone leaves uv_ext = uv: skipped
                             double ddx, ddy;
@@ -908,7 +952,9 @@ cudaError_t tb_kernels_init() {
 
 // which specialisation serves this parameter set (0 = generic)
 int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear) {
-    const bool rare = p.cd.mode || p.pa.mode == 2 || p.msrc.mode || p.vsrc.mode || !p.adv_on;
+    const bool dg_coef = p.cor.mode == 3 || p.man.mode == 3 || p.lin.mode == 3 || p.wind.mode == 3;   // P1DG coefficient fields
+    const bool rare = p.cd.mode || p.pa.mode >= 2 || p.msrc.mode || p.vsrc.mode || !p.adv_on || p.nik.mode || p.wda.mode == 2 ||
+                      dg_coef;
     if (rare) return 0;
     if (p.visc.mode) {
         if (nonlinear && p.lf_on && p.man.mode && p.cor.mode && !p.lin.mode && !p.wind.mode && p.nquad == 6)
@@ -1066,6 +1112,28 @@ __global__ void halo_fused_wait_kernel(const TbHaloFused *hf) {
 }
 cudaError_t tb_launch_halo_fused_wait(const TbHaloFused *hf, cudaStream_t s) {
     halo_fused_wait_kernel<<<1, 32, 0, s>>>(hf);
+    return cudaGetLastError();
+}
+
+// Rewrite the columns [col, col + ncomp) of every patch's static block from a P1 field given at the geometric
+// vertices (vert[v*ncomp + comp]): stream-ordered refresh of a time-dependent coefficient (tb_sync_fields).
+__global__ void update_columns_kernel(unsigned char *sblk, long long stride, int NV, long long n_patches,
+                                      const int32_t *__restrict__ patch_vglob, const double *__restrict__ vert, int col,
+                                      int ncomp) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_patches * NV) return;
+    const long long p = i / NV;
+    const int k = (int)(i - p * NV);
+    int gv = patch_vglob[i];
+    if (gv < 0) gv = patch_vglob[p * NV];        // padding repeats the patch's first vertex (upload_layout)
+    if (gv < 0) return;
+    double *cols = reinterpret_cast<double *>(sblk + p * stride);
+    for (int c = 0; c < ncomp; ++c) cols[(size_t)(col + c) * NV + k] = vert[(size_t)gv * ncomp + c];
+}
+cudaError_t tb_launch_update_columns(unsigned char *sblk, long long stride, int NV, long long n_patches,
+                                     const int32_t *patch_vglob, const double *vert, int col, int ncomp, cudaStream_t s) {
+    const long long n = n_patches * NV;
+    if (n > 0) update_columns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sblk, stride, NV, n_patches, patch_vglob, vert, col, ncomp);
     return cudaGetLastError();
 }
 

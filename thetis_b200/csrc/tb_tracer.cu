@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __g
             double f[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a)
-                f[a] = prm.src.mode == 2 ? cols[(size_t)prm.src.col * NV + v[a]] : prm.src.v0;
+                f[a] = prm.src.mode == 3 ? __ldg(prm.src.cell + (cell0 + tid) * 3 + a)       // P1DG source (tb_set_field_cell)
+                       : prm.src.mode == 2 ? cols[(size_t)prm.src.col * NV + v[a]] : prm.src.v0;
             const double s = f[0] + f[1] + f[2];
             if (!cons) {
 #pragma unroll

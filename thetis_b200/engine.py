@@ -102,12 +102,17 @@ class Engine:
         self._opt_cache[opt] = value
 
     def set_field(self, field, value):
-        """value: None | scalar/sequence (Constant) | ndarray over geometric vertices (nv,) / (nv, 2)."""
+        """value: None | scalar/sequence (Constant) | ndarray over geometric vertices (nv,) / (nv, 2) (P1) |
+        ndarray over cell nodes (n_cells, 3) / (n_cells, 3, 2) (discontinuous P1DG, cell terms only)."""
         if value is None:
             self._ck(self.lib.tb_clear_field(self.ctx, field))
             return
         a = np.ascontiguousarray(np.asarray(value, dtype=np.float64))
         ncomp = 2 if field in (L.F_WIND_STRESS, L.F_MOMENTUM_SOURCE) else 1
+        if a.ndim >= 2 and a.shape[0] == self.mesh.n_cells and a.shape[1] == 3 and a.ndim == (3 if ncomp == 2 else 2):
+            a = np.ascontiguousarray(a[: self.n_owned])
+            self._ck(self.lib.tb_set_field_cell(self.ctx, field, _np_ptr(a), ncomp, self.stream))
+            return
         if a.ndim == 0 or (a.ndim == 1 and a.shape[0] == ncomp and a.shape[0] != self.mesh.n_vertices):
             a = np.atleast_1d(a)
             self._ck(self.lib.tb_set_field_const(self.ctx, field, _np_ptr(a), int(a.shape[0])))
@@ -115,6 +120,14 @@ class Engine:
             if a.shape[0] != self.mesh.n_vertices:
                 raise ValueError("vertex field has wrong length")
             self._ck(self.lib.tb_set_field_vertex(self.ctx, field, _np_ptr(a), ncomp))
+
+    def sync_fields(self):
+        """Apply pending coefficient changes on the current stream (needed in front of a CUDA-graph replay; plain
+        stage launches do it themselves)."""
+        self._ck(self.lib.tb_sync_fields(self.ctx, self.stream))
+
+    def clear_bc(self, eq, marker):
+        self._ck(self.lib.tb_clear_bc(self.ctx, eq, int(marker)))
 
     def set_boundary_length(self, marker, length):
         self._ck(self.lib.tb_set_boundary_length(self.ctx, int(marker), float(length)))

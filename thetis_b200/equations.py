@@ -19,7 +19,7 @@ __all__ = ["physical_constants", "DepthExpression", "ShallowWaterEquations", "Mo
 physical_constants = {
     "g_grav": Constant(9.81),
     "rho0": Constant(1000.0),
-    "von_karman": Constant(0.41),
+    "von_karman": Constant(0.4),       # thetis/physical_constants.py:9
 }
 
 

@@ -26,13 +26,22 @@ class VertexBasedP1DGLimiter:
         self.adaptor = get_adaptor(p1dg_space.mesh())
         self.engine = self.adaptor.get_engine()
         self.halo = self.adaptor.halo
+        # the bounds of a vertex use the centroids of ALL cells around it (limiter.py:109-145): on a distributed mesh
+        # the one-deep FACET halo is not enough, the partition must carry the vertex-neighbour ghosts
+        if self.halo is not None:
+            kind = self.adaptor.mesh.meta.get("halo") or getattr(self.halo.part, "halo", None)
+            if kind != "vertex":
+                raise NotImplementedError(
+                    "VertexBasedP1DGLimiter on a distributed mesh needs distribute_mesh(..., halo='vertex'); this "
+                    f"partition was built with halo={kind!r}")
         self.node_map = None
 
     def apply(self, field):
         """Applies the limiter on the given field (in place)."""
         assert field.function_space() is self.P1DG or field.function_space().ufl_element().degree() == 1
         eng = self.engine
-        st = getattr(eng, "tracer_steppers", {}).get(id(field))
+        ent = getattr(eng, "tracer_steppers", {}).get(id(field))
+        st = ent[1] if ent is not None and ent[0]() is field else None
         if st is not None:
             # the field lives on the device: limit there, no host round trip
             if not st._host_stale and st._host_changed():

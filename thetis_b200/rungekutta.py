@@ -21,11 +21,13 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+import weakref
+
 from . import _lib as L
-from .adaptor import get_adaptor, is_constant, is_function, constant_value
+from .adaptor import get_adaptor, is_constant, is_function, is_expression, expression_leaves, constant_value
 from .engine import Engine
 
-__all__ = ["SSPRK33", "ERKGenericShuOsher", "ERKGeneric", "ERKLSPUM2", "ERKLPUM2", "ERKMidpoint", "ERKEuler",
+__all__ = ["SSPRK33", "SSPRK22", "ExportStage", "ERKGenericShuOsher", "ERKGeneric", "ERKLSPUM2", "ERKLPUM2", "ERKMidpoint", "ERKEuler",
            "ForwardEuler", "butcher_to_shuosher_form", "CFL_UNCONDITIONALLY_STABLE"]
 
 CFL_UNCONDITIONALLY_STABLE = np.inf
@@ -59,8 +61,10 @@ _SWE_FIELDS = {
     "quadratic_drag_coefficient": L.F_QUAD_DRAG, "linear_drag_coefficient": L.F_LINEAR_DRAG,
     "wind_stress": L.F_WIND_STRESS, "atmospheric_pressure": L.F_ATM_PRESSURE,
     "momentum_source": L.F_MOMENTUM_SOURCE, "volume_source": L.F_VOLUME_SOURCE,
-    "viscosity_h": L.F_VISCOSITY,
+    "viscosity_h": L.F_VISCOSITY, "nikuradse_bed_roughness": L.F_NIKURADSE,
 }
+# coefficients of facet terms: must be continuous (P1); the others may be genuinely discontinuous P1DG fields
+_CONTINUOUS_ONLY = {"bathymetry", "viscosity_h", "diffusivity_h", "wetting_and_drying_alpha"}
 _MODESPLIT_FIELDS = ("coriolis", "momentum_source", "atmospheric_pressure", "volume_source")
 _SWE_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX}
 _TRACER_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX, "value": L.BC_VALUE,
@@ -77,7 +81,11 @@ def _opt(options, name, default=None):
 
 
 def _version(obj):
-    """Cheap change stamp of a Function/Constant (PyOP2 dat_version when available)."""
+    """Cheap change stamp of a Function/Constant (PyOP2 dat_version when available); for an expression the tuple of
+    its operands' stamps."""
+    if is_expression(obj):
+        vs = tuple((id(o), _version(o)) for o in expression_leaves(obj))
+        return None if any(v[1] is None for v in vs) else ("expr", vs)
     d = getattr(obj, "dat", None)
     if d is not None:
         v = getattr(d, "dat_version", None)
@@ -187,12 +195,15 @@ class ERKGenericShuOsher:
             self._own_swe_state = None
             if not hasattr(eng, "tracer_steppers"):
                 eng.tracer_steppers = {}
-            eng.tracer_steppers[id(self.solution)] = self
+            # keyed by id() for the lookup, validated through a weak reference (an id can be reused after GC)
+            eng.tracer_steppers[id(self.solution)] = (weakref.ref(self.solution), self)
 
     def _check_supported(self):
         if self._kind == "swe":
-            if self.fields.get("nikuradse_bed_roughness") is not None:
-                raise NotImplementedError("nikuradse_bed_roughness is outside the accelerated path")
+            if self.fields.get("nikuradse_bed_roughness") is not None and (
+                    self.fields.get("manning_drag_coefficient") is not None
+                    or self.fields.get("quadratic_drag_coefficient") is not None):
+                raise Exception("Cannot set both Nikuradse drag and Manning / dimensionless drag parameter")
             for m, funcs in self.bnd_conditions.items():
                 for k in (funcs or {}):
                     if k == "drag":
@@ -243,9 +254,16 @@ class ERKGenericShuOsher:
         eng.set_option(L.OPT_WETTING_DRYING, bool(depth.use_wetting_and_drying))
         if depth.use_wetting_and_drying:
             al = depth.wetting_and_drying_alpha
-            if not is_constant(al):
-                raise NotImplementedError("spatially varying wetting_and_drying_alpha is outside the accelerated path")
-            eng.set_option(L.OPT_WD_ALPHA, float(constant_value(al)[0]))
+            if is_constant(al):
+                eng.set_option(L.OPT_WD_ALPHA, float(constant_value(al)[0]))
+                if self._kind == "swe":
+                    eng.set_field(L.F_WD_ALPHA, None)
+            elif self._kind == "swe":
+                # P1 Function (use_automatic_wetting_and_drying_alpha, solver2d.py:279-287): one vertex column
+                self._set_field(L.F_WD_ALPHA, al, "wetting_and_drying_alpha")
+            else:
+                raise NotImplementedError("tracer equation with a spatially varying wetting_and_drying_alpha is "
+                                          "outside the accelerated path")
         self._set_field(L.F_BATHYMETRY, depth.bathymetry_2d, "bathymetry")
         for m, ln in self.adaptor.boundary_len.items():
             eng.set_boundary_length(m, ln)
@@ -298,14 +316,18 @@ class ERKGenericShuOsher:
                 eng.set_field(fid, v if v.size > 1 else float(v[0]))
                 self._field_versions[key] = stamp
             return
-        if is_function(value):
+        if is_function(value) or is_expression(value):
+            # Functions, and expressions that are affine in their Function operands (evaluated nodally: exact)
             ver = _version(value)
             stamp = ("f", id(value), ver)
             if ver is None or self._field_versions.get(key) != stamp:
-                eng.set_field(fid, self.adaptor.vertex_values(value))
+                if key in _CONTINUOUS_ONLY:
+                    eng.set_field(fid, self.adaptor.vertex_values(value))
+                else:
+                    eng.set_field(fid, self.adaptor.coefficient_values(value)[1])    # P1 column or P1DG cell nodes
                 self._field_versions[key] = stamp
             return
-        raise NotImplementedError(f"coefficient {key!r}: UFL expressions must be interpolated into a P1 Function first")
+        raise NotImplementedError(f"coefficient {key!r}: unsupported value {type(value).__name__}")
 
     def _push_dynamic(self, force=False, functions=True):
         """Everything `update_forcings` may have changed: Constants are re-read, Functions re-uploaded if touched.
@@ -322,6 +344,8 @@ class ERKGenericShuOsher:
             if gc is not None:
                 self._push_option("g", L.OPT_G_GRAV, gc["g_grav"], 9.81)
                 self._push_option("rho0", L.OPT_RHO0, gc["rho0"], 1000.0)
+                if "von_karman" in gc:
+                    self._push_option("kappa", L.OPT_VON_KARMAN, gc["von_karman"], 0.4)
             eqo = self.equation.options
             self._push_option("eps", L.OPT_NORM_SMOOTHER, _opt(eqo, "norm_smoother", None), 0.0)
             self._push_option("lf", L.OPT_LF_SCALING, self.fields.get("lax_friedrichs_velocity_scaling_factor"), 1.0)
@@ -357,9 +381,18 @@ class ERKGenericShuOsher:
             if functions or src is None or not is_function(src):
                 self._set_field(L.F_TRACER_SOURCE, src, "tracer_source")
             self._push_bcs(1, _TRACER_TAGS)
+        eng.sync_fields()      # pending coefficient uploads go out now (the stage may be a CUDA-graph replay)
 
     def _push_bcs(self, eq, tags):
         eng = self.engine
+        if eq == 1 and not self._stamps.get("bc_cleared"):
+            # the device context is shared by every tracer on the mesh while each tracer equation is built from its
+            # own bnd_conditions dict (solver2d.py:580-598): markers without an entry here must not inherit another
+            # tracer's opcode / data.  (_stamps is dropped whenever another tracer configured the context.)
+            for marker in self.adaptor.mesh.unique_markers():
+                if self.bnd_conditions.get(marker) is None:
+                    eng.clear_bc(1, marker)
+            self._stamps["bc_cleared"] = True
         for marker, funcs in self.bnd_conditions.items():
             if funcs is None:
                 continue
@@ -389,11 +422,11 @@ class ERKGenericShuOsher:
                     v = constant_value(val)
                     s = _CONST_SLOT[tag]
                     consts[s:s + v.size] = v
-                elif is_function(val):
-                    arrays.append((tag, val))
+                elif is_function(val) or is_expression(val):
+                    arrays.append((tag, val))     # expressions: affine in their Functions, evaluated nodally (exact)
                 else:
-                    raise NotImplementedError(
-                        f"boundary datum {tag!r} on marker {marker}: UFL expressions must be interpolated into a P1 Function first")
+                    raise NotImplementedError(f"boundary datum {tag!r} on marker {marker}: unsupported value "
+                                              f"{type(val).__name__}")
             stamp = (op,) + tuple(consts.tolist())
             key = (eq, marker)
             if self._bc_versions.get(key) != stamp:
@@ -434,13 +467,20 @@ class ERKGenericShuOsher:
         self._host_stale = False
         self._last_host_version = self._solution_version()
 
+    def _visible_state(self):
+        """The device buffer a host observer should see: the solution, or -- between the stages of a step, where the
+        reference leaves the stage solution in `self.solution` (rungekutta.py:936-946) -- the latest stage."""
+        return self._cur if getattr(self, "_mid_step", False) else self.buf[0]
+
     def sync_to_host(self):
-        """D2H: device state -> `solution.dat.data` (in place; sub-function views stay valid)."""
+        """D2H: device state -> `solution.dat.data` (in place; sub-function views stay valid).  Blocking; exports that
+        can run behind the time loop use `stage_export()` / `ExportStage.wait()` instead."""
         if not self._host_stale:
             return
         eng = self.engine
+        src = self._visible_state()
         if self._kind == "swe":
-            eng.state_to_fields(self.buf[0], self.node_map, self._d_uv, self._d_eta)
+            eng.state_to_fields(src, self.node_map, self._d_uv, self._d_eta)
             self._h_uv.copy_(self._d_uv, non_blocking=True)
             self._h_eta.copy_(self._d_eta, non_blocking=True)
             torch.cuda.current_stream(eng.device).synchronize()
@@ -448,12 +488,56 @@ class ERKGenericShuOsher:
             uv_f.dat.data[...] = self._h_uv.numpy().reshape(np.asarray(uv_f.dat.data_ro).shape)
             eta_f.dat.data[...] = self._h_eta.numpy()
         else:
-            eng.tracer_to_field(self.buf[0], self.node_map, self._d_q)
+            eng.tracer_to_field(src, self.node_map, self._d_q)
             self._h_q.copy_(self._d_q, non_blocking=True)
             torch.cuda.current_stream(eng.device).synchronize()
             self.solution.dat.data[...] = self._h_q.numpy()
         self._host_stale = False
         self._last_host_version = self._solution_version()
+
+    def stage_export(self):
+        """
+        Non-blocking export staging (the D2H the reference does implicitly whenever `export()` / `print_state` read
+        `solution.dat.data`, solver2d.py:1132-1142): the current device solution is converted to the Thetis layout and
+        copied into one of two pinned host buffers on a SIDE stream; the time loop keeps launching stages on the main
+        stream.  Returns an `ExportStage`; `wait()` blocks on its event only and hands out numpy views of the pinned
+        buffers (valid until the second-next `stage_export()`).  The host `solution` is not touched.
+        """
+        eng = self.engine
+        dev = eng.device
+        ring = self.__dict__.get("_export_ring")
+        if ring is None:
+            side = torch.cuda.Stream(device=dev)
+            slots = []
+            for _ in range(2):
+                if self._kind == "swe":
+                    d = (torch.empty_like(self._d_uv), torch.empty_like(self._d_eta))
+                    h = (torch.empty(self._d_uv.shape, dtype=torch.float64).pin_memory(),
+                         torch.empty(self._d_eta.shape, dtype=torch.float64).pin_memory())
+                else:
+                    d = (torch.empty_like(self._d_q),)
+                    h = (torch.empty(self._d_q.shape, dtype=torch.float64).pin_memory(),)
+                slots.append(dict(d=d, h=h, done=torch.cuda.Event(), snap=torch.empty_like(self.buf[0])))
+            ring = self._export_ring = dict(side=side, slots=slots, next=0)
+        slot = ring["slots"][ring["next"]]
+        ring["next"] ^= 1
+        main = torch.cuda.current_stream(dev)
+        slot["done"].synchronize()                      # the copy that used this slot two exports ago has landed
+        # snapshot on the main stream (device-to-device, HBM speed): later stages may overwrite the solution buffer
+        slot["snap"].copy_(self._visible_state(), non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side = ring["side"]
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            if self._kind == "swe":
+                eng.state_to_fields(slot["snap"], self.node_map, slot["d"][0], slot["d"][1])
+            else:
+                eng.tracer_to_field(slot["snap"], self.node_map, slot["d"][0])
+            for dd, hh in zip(slot["d"], slot["h"]):
+                hh.copy_(dd, non_blocking=True)
+            slot["done"].record(side)
+        return ExportStage(slot["done"], tuple(h.numpy() for h in slot["h"]))
 
     def device_state(self):
         """Device tensor holding the current solution (cell records)."""
@@ -524,6 +608,8 @@ class ERKGenericShuOsher:
                 self._host_stale = True
         else:
             self._launch_stage(i_stage)
+        if self.sync_policy == "every_stage":
+            self.sync_to_host()                # the reference leaves every stage solution in `solution` (:936-946)
 
     def _launch_stage(self, i_stage):
         """One fused kernel launch: residual + mass inverse + Shu-Osher update of stage i."""
@@ -557,10 +643,11 @@ class ERKGenericShuOsher:
             eng.tracer_stage(a0, a1, bdt, src, u0, dst, self._swe_state_for_tracer())
             if self.halo is not None:
                 self.halo.exchange(dst)
+        self._mid_step = not last
+        self._host_stale = True
         if last:
             if dst is not A:
                 self.buf[0], self.buf[1] = self.buf[1], self.buf[0]
-            self._host_stale = True
 
     def advance_device(self):
         """One step with every input already resident on the device (no forcing refresh, no host sync)."""
@@ -573,6 +660,34 @@ class ERKGenericShuOsher:
             self.solve_stage(i, t, update_forcings)
         if self.sync_policy == "every_step":
             self.sync_to_host()
+
+
+class ExportStage:
+    """Handle of one non-blocking export (`stage_export`): `wait()` -> numpy views of the pinned host copy."""
+
+    def __init__(self, event, arrays):
+        self.event = event
+        self._arrays = arrays
+
+    def ready(self):
+        return self.event.query()
+
+    def wait(self):
+        self.event.synchronize()
+        return self._arrays
+
+
+class SSPRK22(ERKGenericShuOsher):
+    """
+    SSP(2,2):  u1 = u0 + dt F(u0),  u = (u0 + u1 + dt F(u1)) / 2,  forcings at t and t + dt -- the explicit scheme
+    `timeintegrator.SSPRK22ALE` applies to the 3-D fields (timeintegrator.py:609-660, c = [0, 1]), here as an
+    explicit `integrator_2d` for the external mode of the two-stage coupled loop
+    (thetis_b200.coupled_timeintegrator.CoupledTwoStageRK2D).
+    """
+    a = [[0, 0], [1.0, 0]]
+    b = [0.5, 0.5]
+    c = [0, 1.0]
+    cfl_coeff = 1.0
 
 
 class SSPRK33(ERKGenericShuOsher):

@@ -16,22 +16,92 @@ import numpy as np
 
 from .mesh import Mesh2D, FACET_NODES
 
-__all__ = ["Constant", "Function", "FunctionSpace", "MixedFunctionSpace", "ShimMesh", "as_shim_mesh"]
+__all__ = ["Constant", "Function", "FunctionSpace", "MixedFunctionSpace", "ShimMesh", "as_shim_mesh",
+           "conditional", "lt", "gt", "le", "ge", "as_vector"]
 
 
-class Constant:
-    """Look-alike of firedrake.Constant (scalar or small vector)."""
+class _Expr:
+    """
+    Minimal look-alike of a UFL expression tree over Constants and Functions (`ufl_operands`, operator overloads,
+    `conditional`), enough to write boundary data the way the reference's examples do, e.g.
+    ``elev_ramp * elev_tide_2d`` with ``elev_ramp = conditional(bnd_time < ramp_t, bnd_time / ramp_t, 1.0)``
+    (examples/north_sea/model_config.py:181-192).  Data only: the adaptor evaluates it nodally.
+    """
+    ufl_operands = ()
+
+    def __mul__(self, o): return _Op("mul", self, o)
+    def __rmul__(self, o): return _Op("mul", o, self)
+    def __add__(self, o): return _Op("add", self, o)
+    def __radd__(self, o): return _Op("add", o, self)
+    def __sub__(self, o): return _Op("sub", self, o)
+    def __rsub__(self, o): return _Op("sub", o, self)
+    def __truediv__(self, o): return _Op("div", self, o)
+    def __rtruediv__(self, o): return _Op("div", o, self)
+    def __neg__(self): return _Op("mul", -1.0, self)
+    def __lt__(self, o): return _Op("lt", self, o)
+    def __gt__(self, o): return _Op("gt", self, o)
+    def __le__(self, o): return _Op("le", self, o)
+    def __ge__(self, o): return _Op("ge", self, o)
+
+
+class _Op(_Expr):
+    def __init__(self, kind, *operands):
+        self.kind = kind
+        self.ufl_operands = tuple(operands)
+
+
+def conditional(condition, true_value, false_value):
+    return _Op("conditional", condition, true_value, false_value)
+
+
+def lt(a, b): return _Op("lt", a, b)
+def gt(a, b): return _Op("gt", a, b)
+def le(a, b): return _Op("le", a, b)
+def ge(a, b): return _Op("ge", a, b)
+
+
+def as_vector(components):
+    """`as_vector([..])` of numbers / scalar expressions."""
+    if all(isinstance(c, (int, float, np.integer, np.floating)) for c in components):
+        return np.asarray(components, dtype=np.float64)
+    return _Op("vector", *components)
+
+
+class _ConstDat:
+    """`Constant.dat` of real Firedrake: a PyOP2 Global with a version counter."""
+
+    def __init__(self, owner):
+        self._owner = owner
+        self.dat_version = 0
+
+    @property
+    def data(self):
+        self.dat_version += 1
+        return self._owner._v
+
+    @property
+    def data_ro(self):
+        return self._owner._v
+
+
+class Constant(_Expr):
+    """Look-alike of firedrake.Constant (scalar or small vector): like the real one it carries `.dat`,
+    `function_space()` (returning None) and `values()`."""
 
     def __init__(self, value):
+        if isinstance(value, Constant):
+            value = value._v if not value._scalar else float(value)
         self._v = np.atleast_1d(np.asarray(value, dtype=np.float64)).copy()
         self._scalar = np.ndim(value) == 0
-        self.version = 0
+        self.dat = _ConstDat(self)
+
+    def function_space(self):
+        return None
 
     def assign(self, value):
         if isinstance(value, Constant):
             value = value._v
-        self._v[...] = np.asarray(value, dtype=np.float64)
-        self.version += 1
+        self.dat.data[...] = np.asarray(value, dtype=np.float64)
         return self
 
     def values(self):
@@ -208,7 +278,7 @@ class _Dat:
         return self._data
 
 
-class Function:
+class Function(_Expr):
     """Look-alike of firedrake.Function (data container only)."""
 
     def __init__(self, space, name=None, val=None):

@@ -101,6 +101,8 @@ class FlowSolver2d:
         self.sediment_model = None
         self.bnd_functions = {"shallow_water": {}, "tracer": {}, "sediment": {}}
         self.callbacks = {"timestep": [], "export": []}
+        self._export_consumers = []
+        self._pending_exports = []
         self.solve_tracer = False
         self.keep_log = False
         self._initialized = False
@@ -148,7 +150,24 @@ class FlowSolver2d:
                 automatic = True
         if automatic:
             mesh2d_dt = self.compute_time_step(u_scale=self.options.horizontal_velocity_scale)
-            self.dt = self.options.cfl_2d * alpha * float(mesh2d_dt.dat.data_ro.min())
+            vals = np.asarray(mesh2d_dt.dat.data_ro, dtype=float)
+            plan = getattr(self.mesh2d, "halo_plan", None)
+            if plan is not None:
+                # distributed mesh (solver2d.py:241: dt = comm.allreduce(dt, op=MPI.MIN)): the minimum is taken over
+                # the nodes of the cells this rank owns (the projection is polluted on the far side of the ghost
+                # layer, where the local mass matrix misses neighbours) and then over the ranks, so that every rank
+                # advances with the same time step
+                import torch
+                import torch.distributed as dist
+                nodes = np.unique(mesh2d_dt.function_space().cell_node_map().values[: plan.part.n_owned])
+                local = torch.tensor([float(vals[nodes].min())], dtype=torch.float64)
+                if dist.get_backend() == "nccl":
+                    local = local.cuda()
+                dist.all_reduce(local, op=dist.ReduceOp.MIN)
+                dt_min = float(local.item())
+            else:
+                dt_min = float(vals.min())
+            self.dt = self.options.cfl_2d * alpha * dt_min
         else:
             assert self.options.timestep is not None and self.options.timestep > 0.0
             self.dt = self.options.timestep
@@ -379,9 +398,52 @@ class FlowSolver2d:
             print_output(" ".join([e[0].rjust(len(f"{e[1]:{e[2]}}")) for e in entries]))
         print_output(" ".join([f"{e[1]:{e[2]}}" for e in entries]))
 
+    def add_export_consumer(self, consumer):
+        """
+        Register ``consumer(time, i_export, arrays)`` for NON-BLOCKING exports: at every export the device solution
+        is staged into pinned host memory on a side stream (`TimeIntegrator.stage_export`) and the consumer runs when
+        the copy has landed -- at the next export, or at the end of `iterate()` at the latest -- while the time loop
+        keeps the GPU busy.  ``arrays``: {'uv_2d': (n, 2), 'elev_2d': (n,), '<tracer>': (n,)} numpy views in the
+        Thetis dof order, valid during the call.  This is what a file exporter (exporter.py) plugs into; exports
+        that need the host `Function`s themselves (`export_func`, user callbacks) still synchronise.
+        """
+        self._export_consumers.append(consumer)
+
+    def _stage_exports(self, time):
+        ts = self.timestepper
+        handles = {}
+        if isinstance(ts, GeneralCoupledTimeIntegrator2D):
+            for name, st in ts.timesteppers.items():
+                handles[name] = st.stage_export()
+        else:
+            handles["swe2d"] = ts.stage_export()
+        self._pending_exports.append((time, self.i_export, handles))
+
+    def _drain_exports(self, block=False):
+        while self._pending_exports:
+            time, i_export, handles = self._pending_exports[0]
+            if not block and not all(h.ready() for h in handles.values()):
+                return
+            arrays = {}
+            for name, h in handles.items():
+                a = h.wait()
+                if name == "swe2d":
+                    arrays["uv_2d"], arrays["elev_2d"] = a
+                else:
+                    arrays[name] = a[0]
+            for c in self._export_consumers:
+                c(time, i_export, arrays)
+            self._pending_exports.pop(0)
+
     def export(self, time=None):
-        """Fields become host-visible here; VTK/HDF5 writers are outside the accelerated path (exporter.py)."""
-        self.sync_to_host()
+        """Fields become host-visible here; VTK/HDF5 writers are outside the accelerated path (exporter.py).
+        With export consumers registered the D2H is staged asynchronously instead (solver2d.py:1132-1142 blocks the
+        time loop on every export)."""
+        if self._export_consumers:
+            self._drain_exports(block=len(self._pending_exports) >= 2)      # two staging buffers per integrator
+            self._stage_exports(self.simulation_time if time is None else time)
+        else:
+            self.sync_to_host()
         self._run_callbacks("export")
 
     # ------------------------------------------------------------ time loop (solver2d.py:974-1144)
@@ -403,6 +465,7 @@ class FlowSolver2d:
         if self.export_initial_state:
             self.export(time=self.simulation_time)
             if export_func is not None:
+                self.sync_to_host()
                 export_func()
         while self.simulation_time <= self.options.simulation_end_time - t_epsilon:
             self.timestepper.advance(self.simulation_time, update_forcings)
@@ -420,6 +483,8 @@ class FlowSolver2d:
                 self.print_state(cputime)
                 self.export(time=self.simulation_time)
                 if export_func is not None:
+                    self.sync_to_host()            # a user export function reads the host Functions
                     export_func()
+        self._drain_exports(block=True)
         self.sync_to_host()
         return self.simulation_time
