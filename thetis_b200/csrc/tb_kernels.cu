@@ -20,6 +20,9 @@
 #ifndef TB_HALO_SPEC
 #define TB_HALO_SPEC 6        // halo elements per thread fetched speculatively (covers NH <= 85)
 #endif
+#ifndef TB_ID_SPEC
+#define TB_ID_SPEC 1          // halo ids per thread loaded up front (covers NH <= TB_P)
+#endif
 #ifndef TB_PREFETCH_DIST
 #define TB_PREFETCH_DIST 592   // patches ahead to warm in L2: one wave of 148 SMs x 4 CTAs
 #endif
@@ -34,6 +37,8 @@
 #ifndef TB_MINB
 #define TB_MINB 4      // resident CTAs per SM the stage kernel is compiled for (register budget)
 #endif
+
+__host__ __device__ inline size_t tb_ids_offset(const TbPatchLayout &pl);
 
 // ------------------------------------------------------------------ constants
 __constant__ double c_qlam[TB_MAX_QUAD][3];
@@ -225,15 +230,16 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         }
     }
 
-    // Speculative, mutually independent global loads first (one DRAM latency instead of a chain of three): the halo
-    // count and the ids this thread will need (rows of halo_ids are padded to NH valid entries).
+    // Halo ids of this patch: one coalesced load per thread (the row was prefetched to L2 one wave earlier), staged in
+    // shared memory so that the gather below indexes them with cheap 32-bit shared loads instead of one global load
+    // plus 64-bit address arithmetic per gathered element (that index arithmetic was 7 % of all executed instructions).
     const int *hid = prm.pl.halo_ids + (long long)patch * prm.pl.NH;
-    const int NH9 = prm.pl.NH * 9;
-    int hcell[TB_HALO_SPEC];
+    int *ids_s = reinterpret_cast<int *>(smem + tb_ids_offset(prm.pl));
+    int myid[TB_ID_SPEC];
 #pragma unroll
-    for (int j = 0; j < TB_HALO_SPEC; ++j) {
-        const int i = j * TB_P + tid;
-        hcell[j] = (i < NH9) ? __ldg(hid + i / 9) : 0;
+    for (int j = 0; j < TB_ID_SPEC; ++j) {
+        const int h = j * TB_P + tid;
+        myid[j] = (h < prm.pl.NH) ? __ldg(hid + h) : 0;
     }
     const int nh9 = __ldg(prm.pl.halo_cnt + patch) * 9;
 
@@ -266,25 +272,31 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             if (tid == 33) prefetch_l2(prm.pl.halo_cnt + pf);
         }
     }
-    // patch halo: records of off-patch facet neighbours, copied asynchronously (LDGSTS).  The ids were requested at
-    // the top (their row was prefetched to L2 one wave earlier); the copies are issued as soon as the ids are here --
-    // while the bulk copies are still in flight -- and only waited for in front of the facet loop, so their latency
+    // patch halo: records of off-patch facet neighbours, copied asynchronously (LDGSTS) as soon as the ids are staged
+    // -- while the bulk copies are still in flight -- and only waited for in front of the facet loop, so their latency
     // hides behind the bulk-copy wait and the volume terms.
     // Element i of the halo block is double (i % 9) of halo cell (i / 9): S[TB_P*9 + i].
+#pragma unroll
+    for (int j = 0; j < TB_ID_SPEC; ++j) {
+        const int h = j * TB_P + tid;
+        if (h < prm.pl.NH) ids_s[h] = myid[j];
+    }
+    for (int h = TB_ID_SPEC * TB_P + tid; h < prm.pl.NH; h += TB_P) ids_s[h] = __ldg(hid + h);      // very large halos only
+    __syncthreads();          // ids staged; mbarrier initialised (thread 0) before anybody waits on it
     {
         double *H = S + TB_P * 9;
 #pragma unroll
         for (int j = 0; j < TB_HALO_SPEC; ++j) {
-            const int i = j * TB_P + tid;
-            if (i < nh9) cp_async8(H + i, prm.u_in + ((long long)hcell[j] * 9 + (i - (i / 9) * 9)));
+            const unsigned i = (unsigned)(j * TB_P + tid);
+            const unsigned h = i / 9u;
+            if ((int)i < nh9) cp_async8(H + i, prm.u_in + ((long long)ids_s[h] * 9 + (int)(i - h * 9u)));
         }
         for (int i = TB_HALO_SPEC * TB_P + tid; i < nh9; i += TB_P) {      // very large halos only
             const int h = i / 9;
-            cp_async8(H + i, prm.u_in + ((long long)__ldg(hid + h) * 9 + (i - h * 9)));
+            cp_async8(H + i, prm.u_in + ((long long)ids_s[h] * 9 + (i - h * 9)));
         }
         cp_async_commit();
     }
-    __syncthreads();          // mbarrier initialised (thread 0) before anybody waits on it
     mbar_wait(bar, 0);        // every thread observes the TMA completion itself
 
     // threads past the last owned cell of the last patch evaluate cell 0 of the patch again (uniform control flow:
@@ -927,9 +939,14 @@ TB_UNROLL(TB_GP_UNROLL)
     }
 }
 
-size_t tb_swe_smem_bytes(const TbPatchLayout &pl) {
+// shared-memory layout of the stage kernel: barrier | S (own + halo records) | O | static block | reduction scratch |
+// [cell gradients (SIPG terms)] | halo ids
+__host__ __device__ inline size_t tb_ids_offset(const TbPatchLayout &pl) {
     return 16 + (size_t)(TB_P + pl.NH) * 72 + (size_t)TB_P * 72 + (size_t)pl.stride + (TB_P / 32) * 4 * sizeof(double) +
-           (pl.off_hcv >= 0 ? (size_t)(TB_P + pl.NH) * 5 * sizeof(double) : 0);      // cell gradients (SIPG terms)
+           (pl.off_hcv >= 0 ? (size_t)(TB_P + pl.NH) * 5 * sizeof(double) : 0);
+}
+size_t tb_swe_smem_bytes(const TbPatchLayout &pl) {
+    return tb_ids_offset(pl) + (((size_t)pl.NH * sizeof(int) + 15) & ~(size_t)15);
 }
 
 template <bool NL, int SPEC>

@@ -334,6 +334,8 @@ class ERKGenericShuOsher:
         ``functions=False`` leaves Function-valued `fields` entries at their last uploaded values (the lagged
         `fields_old` of timeintegrator.ForwardEuler); boundary data are always live."""
         eng = self.engine
+        if self._kind == "swe" and functions and not force and self._watch_fast():
+            return
         if self._kind == "swe":
             gc = getattr(self.equation, "physical_constants", None)
             if gc is None:
@@ -357,6 +359,8 @@ class ERKGenericShuOsher:
                 if functions or val is None or not is_function(val):
                     self._set_field(fid, val, name)
             self._push_bcs(0, _SWE_TAGS)
+            if functions:
+                self._watch_build(gc)
         else:
             # several tracer integrators share one device context: equation-specific switches are re-sent every stage
             # (cached by value in the engine, so only changes reach the library) and this integrator's own upload
@@ -383,6 +387,71 @@ class ERKGenericShuOsher:
             self._push_bcs(1, _TRACER_TAGS)
         eng.sync_fields()      # pending coefficient uploads go out now (the stage may be a CUDA-graph replay)
 
+    # -- watch list: after the first full pass, a stage only looks at the version counters of the objects that CAN
+    # change (Constants, Functions, leaves of expressions) and re-pushes just the consumers of those that did.  The
+    # reference builds its forms once from the `fields` / `bnd_conditions` entries present at construction, so
+    # entries replaced later are not part of the contract; a cheap identity signature still catches that and falls
+    # back to the full pass.
+    def _watch_signature(self):
+        sig = [id(v) for v in self.fields.values()]
+        for funcs in self.bnd_conditions.values():
+            if funcs:
+                sig.extend(id(v) for v in funcs.values())
+        return tuple(sig)
+
+    def _watch_build(self, gc):
+        watch = []          # (object, last version, [actions])
+        index = {}
+
+        def add(obj, action):
+            if obj is None or isinstance(obj, (int, float, tuple, list, np.ndarray)):
+                return
+            leaves = expression_leaves(obj) if is_expression(obj) else [obj]
+            for leaf in leaves:
+                ent = index.get(id(leaf))
+                if ent is None:
+                    ent = index[id(leaf)] = [leaf, _version(leaf), []]
+                    watch.append(ent)
+                ent[2].append(action)
+        eqo = self.equation.options
+        if gc is not None:
+            add(gc["g_grav"], lambda: self._push_option("g", L.OPT_G_GRAV, gc["g_grav"], 9.81))
+            add(gc["rho0"], lambda: self._push_option("rho0", L.OPT_RHO0, gc["rho0"], 1000.0))
+            if "von_karman" in gc:
+                add(gc["von_karman"], lambda: self._push_option("kappa", L.OPT_VON_KARMAN, gc["von_karman"], 0.4))
+        for key, opt_id, obj, default in (("eps", L.OPT_NORM_SMOOTHER, _opt(eqo, "norm_smoother", None), 0.0),
+                                          ("lf", L.OPT_LF_SCALING, self.fields.get("lax_friedrichs_velocity_scaling_factor"), 1.0),
+                                          ("sipg", L.OPT_SIPG_FACTOR, _opt(eqo, "sipg_factor", None), 1.0)):
+            add(obj, lambda key=key, opt_id=opt_id, obj=obj, default=default: self._push_option(key, opt_id, obj, default))
+        for name, fid in _SWE_FIELDS.items():
+            val = self.fields.get(name)
+            if self._modesplit and name not in _MODESPLIT_FIELDS:
+                continue
+            add(val, lambda fid=fid, val=val, name=name: self._set_field(fid, val, name))
+        for marker, funcs in self.bnd_conditions.items():
+            for val in (funcs or {}).values():
+                add(val, lambda marker=marker, funcs=funcs: self._push_bc_marker(0, _SWE_TAGS, marker, funcs))
+        self._watch = watch
+        self._watch_sig = self._watch_signature()
+        # a datum without a version counter must be re-read every stage: no fast path then
+        self._watch_ok = all(ent[1] is not None for ent in watch)
+
+    def _watch_fast(self):
+        """True when the stage's dynamic inputs were refreshed through the watch list (else: do the full pass)."""
+        if not getattr(self, "_watch_ok", False) or self._watch_signature() != self._watch_sig:
+            return False
+        dirty = False
+        for ent in self._watch:
+            v = _version(ent[0])
+            if v != ent[1]:
+                ent[1] = v
+                for act in ent[2]:
+                    act()
+                dirty = True
+        if dirty:
+            self.engine.sync_fields()
+        return True
+
     def _push_bcs(self, eq, tags):
         eng = self.engine
         if eq == 1 and not self._stamps.get("bc_cleared"):
@@ -396,6 +465,11 @@ class ERKGenericShuOsher:
         for marker, funcs in self.bnd_conditions.items():
             if funcs is None:
                 continue
+            self._push_bc_marker(eq, tags, marker, funcs)
+
+    def _push_bc_marker(self, eq, tags, marker, funcs):
+        eng = self.engine
+        if True:
             # fast path: nothing in this marker's dict changed since the last stage
             sig = []
             for tag, val in funcs.items():
@@ -407,7 +481,7 @@ class ERKGenericShuOsher:
             if sig is not None:
                 sig = tuple(sig)
                 if self._stamps.get(("bc", eq, marker)) == sig:
-                    continue
+                    return
             self._stamps[("bc", eq, marker)] = sig
             op = 0
             consts = np.zeros(8)
