@@ -411,7 +411,7 @@ def main():
             if err:
                 raise RuntimeError("a halo flag wait timed out during the run")
     dt = run.dt
-    graph_on = hasattr(run, "_graph")
+    graph_on = hasattr(run, "_graph") or hasattr(run, "_graphs")
 
     # ---------------- config 5: the same measurement with wetting-drying off, reported side by side
     no_wd = None

@@ -249,10 +249,18 @@ class ConfigRun:
             if s.options.use_limiter_for_tracers:
                 s.tracer_limiter.apply(s.fields[system])
 
+    def _swaps_buffers(self):
+        # the limiter works out of place and swaps the tracer integrator's solution / scratch buffers every step
+        return bool(self.tracers) and bool(self.solver.options.use_limiter_for_tracers)
+
     def step_resident(self):
-        g = getattr(self, "_graph", None)
-        if g is not None:
-            g.replay()
+        gs = getattr(self, "_graphs", None)
+        if gs is not None:
+            gs[self._gi].replay()
+            if len(gs) == 2:
+                self._gi ^= 1
+                for tr in self.tracers:          # keep the integrators' view in step with what the graph did
+                    tr.buf[0], tr.buf[1] = tr.buf[1], tr.buf[0]
             self._replays = getattr(self, "_replays", 0) + 1
             return
         self.swe.advance_device()
@@ -261,15 +269,19 @@ class ConfigRun:
         self._limit()
 
     def enable_graph(self):
+        """Capture the resident step in a CUDA graph -- two graphs replayed alternately when the step swaps buffers."""
         torch = self.torch
         self.step_resident()
         torch.cuda.synchronize()
-        l0 = self.eng.launch_count()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.step_resident()
-        self._launches_per_step = self.eng.launch_count() - l0
-        self._graph = g
+        graphs = []
+        for _ in range(2 if self._swaps_buffers() else 1):
+            l0 = self.eng.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.step_resident()
+            self._launches_per_step = self.eng.launch_count() - l0
+            graphs.append(g)
+        self._graphs, self._gi = graphs, 0
 
     def launches(self):
         return self.eng.launch_count() + getattr(self, "_replays", 0) * getattr(self, "_launches_per_step", 0)

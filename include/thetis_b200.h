@@ -179,6 +179,9 @@ int tb_tracer_stage(tb_ctx *ctx, double a0, double a1, double b_dt,
                     const double *swe_state, void *stream);
 /* VertexBasedP1DGLimiter.apply (limiter.py:182-198), in place. */
 int tb_limiter_apply(tb_ctx *ctx, double *c, void *stream);
+/* Same, out of place: c_out (owned cells) = limited c_in; ghost cells of c_out are not written.  One patch-staged
+ * kernel (bounds in shared memory); the integrator swaps its buffers instead of copying back. */
+int tb_limiter_apply_to(tb_ctx *ctx, const double *c_in, double *c_out, void *stream);
 
 /* ---- layout conversion & diagnostics ----------------------------------- */
 /* Thetis' mixed Function layout <-> cell records.  uv: [n_nodes*2] interleaved,

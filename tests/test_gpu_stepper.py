@@ -469,3 +469,33 @@ def test_wetting_drying_alpha_function_through_flowsolver():
     for i in range(nsteps):
         st.advance(i * dt)
     assert _rel(eta_g, eta) < 1e-9 and _rel(uv_g, uv) < 1e-9
+
+
+@pytest.mark.parametrize("which", ["unstructured", "periodic", "north_sea"])
+def test_patch_staged_limiter_multi_patch_meshes(which):
+    """the patch-staged limiter kernel (bounds in shared memory, vertex halo gathered per patch) against the oracle's
+    global gather on meshes with many patches: unstructured with boundaries, x-periodic (vertices identified across
+    the seam), the tagged North Sea coastline; noisy data so that most cells are limited"""
+    import os
+    from thetis_b200.limiter import VertexBasedP1DGLimiter
+    from thetis_b200.shim import Function, FunctionSpace, as_shim_mesh
+    from thetis_b200.mesh import load_npz_mesh
+    if which == "unstructured":
+        mesh = delaunay_mesh(3000, 5.0, 4.0, seed=2)
+    elif which == "periodic":
+        mesh = periodic_rectangle_mesh(40, 21, 8.0, 4.0)
+    else:
+        mesh = load_npz_mesh(os.path.join(os.path.dirname(__file__), "golden", "north_sea_mesh.npz"))
+    sm = as_shim_mesh(mesh)
+    p1dg = FunctionSpace(sm, "DG", 1)
+    rng = np.random.default_rng(4)
+    x = mesh.coords[mesh.cells]
+    L = np.ptp(mesh.coords, axis=0)
+    q0 = np.tanh(4 * (x[..., 0] - mesh.coords[:, 0].mean()) / L[0]) + 0.3 * rng.standard_normal(x.shape[:2])
+    tracer = Function(p1dg, name="tracer")
+    tracer.dat.data[:] = q0.reshape(-1)
+    VertexBasedP1DGLimiter(p1dg).apply(tracer)
+    q = tracer.dat.data_ro.reshape(-1, 3)
+    ref = O.vertex_based_limiter(mesh, q0)
+    assert np.abs(ref - q0).max() > 0.05                       # the limiter did act
+    assert np.abs(q - ref).max() < 1e-14

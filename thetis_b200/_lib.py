@@ -73,6 +73,7 @@ SIGNATURES = {
     "tb_halo_fused_status": (_I, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "tb_tracer_stage": (_I, [_P, _D, _D, _D, _P, _P, _P, _P, _P]),
     "tb_limiter_apply": (_I, [_P, _P, _P]),
+    "tb_limiter_apply_to": (_I, [_P, _P, _P, _P]),
     "tb_state_from_fields": (_I, [_P, _P, _P, _P, _P, _P]),
     "tb_state_to_fields": (_I, [_P, _P, _P, _P, _P, _P]),
     "tb_tracer_from_field": (_I, [_P, _P, _P, _P, _P]),

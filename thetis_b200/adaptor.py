@@ -74,9 +74,6 @@ def expression_leaves(expr):
     return out
 
 
-_SHIM_KINDS = {"mul", "add", "sub", "div", "lt", "gt", "le", "ge", "conditional", "vector"}
-
-
 def expression_degree(expr):
     """Polynomial degree of an expression in its Function operands (P1 Functions count 1, Constants 0); None when it
     is not a polynomial (division by a Function, a condition that depends on a Function).  Degree <= 1 means nodal
@@ -268,12 +265,21 @@ class MeshAdaptor:
             shape = getattr(expr, "ufl_shape", ())
             fs = fd.VectorFunctionSpace(mesh_obj, "DG", 1) if shape else fd.FunctionSpace(mesh_obj, "DG", 1)
             return self.nodal_values(fd.Function(fs).interpolate(expr))
-        ops = [self.evaluate(o) for o in expr.ufl_operands]
+        return self._eval_tree(expr, self.evaluate)
+
+    @staticmethod
+    def _eval_tree(expr, leaf):
+        """Apply the operators of a shim expression tree to arrays produced by ``leaf`` for Functions / Constants."""
+        kind = getattr(expr, "kind", None)
+        if kind is None:
+            return leaf(expr)
+        ops = [MeshAdaptor._eval_tree(o, leaf) if hasattr(o, "ufl_operands") else np.asarray(o, dtype=np.float64)
+               for o in expr.ufl_operands]
         if kind == "mul":
             a, b = ops
-            if a.ndim < b.ndim:
+            if a.ndim and b.ndim and a.ndim < b.ndim:
                 a = a[..., None]
-            elif b.ndim < a.ndim:
+            elif a.ndim and b.ndim and b.ndim < a.ndim:
                 b = b[..., None]
             return a * b
         if kind == "add":
@@ -293,7 +299,7 @@ class MeshAdaptor:
         if kind == "conditional":
             return np.where(ops[0], ops[1], ops[2])
         if kind == "vector":
-            return np.stack(ops, axis=-1)
+            return np.stack(np.broadcast_arrays(*ops), axis=-1)
         raise NotImplementedError(f"expression node {kind!r}")
 
     def coefficient_values(self, func):
@@ -329,10 +335,27 @@ class MeshAdaptor:
         the rows of that marker are evaluated (the rest of the returned, reused, buffer is untouched).
         """
         if not is_function(func):
-            # expression over Functions / Constants (affine): nodal evaluation, then the facet nodes
-            nodal = np.asarray(self.evaluate(func), dtype=np.float64)
-            m = self.mesh
-            return np.stack([nodal[m.bf_cell, FACET_NODES[m.bf_lf, 0]], nodal[m.bf_cell, FACET_NODES[m.bf_lf, 1]]], axis=1)
+            # expression over Functions / Constants, affine in the Functions: evaluated at the facet nodes only (its
+            # Function leaves through the cached index path below), every stage of a tidal run
+            deg = expression_degree(func)
+            if deg is None or deg > 1:
+                raise NotImplementedError(
+                    "expression is not affine in its Function operands: interpolate it into a P1 / P1DG Function first")
+            if getattr(func, "kind", None) is None:       # real UFL: nodal interpolation by Firedrake
+                nodal = np.asarray(self.evaluate(func), dtype=np.float64)
+                m = self.mesh
+                return np.stack([nodal[m.bf_cell, FACET_NODES[m.bf_lf, 0]], nodal[m.bf_cell, FACET_NODES[m.bf_lf, 1]]], axis=1)
+
+            def leaf(x):
+                if is_function(x):
+                    return self.bfacet_values(x, marker)
+                v = constant_value(x)
+                return v if v.size > 1 else v[0]
+            out = np.asarray(self._eval_tree(func, leaf), dtype=np.float64)
+            nb = self.mesh.n_bfacets
+            if out.ndim < 2 or out.shape[0] != nb:        # expression of Constants only: broadcast over the facets
+                out = np.broadcast_to(out, (nb, 2) + ((out.shape[-1],) if out.ndim == 1 else ())).copy()
+            return out
         fs = func.function_space()
         cache = self.__dict__.setdefault("_bf_nodes", {})
         idx = cache.get(id(fs))

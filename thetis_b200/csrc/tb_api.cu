@@ -108,9 +108,9 @@ struct tb_ctx {
     // limiter
     bool lim_ready = false;
     TbLimiterData lim{};
-    long long *d_v2c_ptr = nullptr, *d_v2b_ptr = nullptr;
-    int *d_v2c_idx = nullptr, *d_v2b_idx = nullptr, *d_cell_tv = nullptr;
-    double *d_qmin = nullptr, *d_qmax = nullptr;
+    unsigned char *d_lim_tab = nullptr;
+    int32_t *d_lim_nhv = nullptr;
+    double *d_lim_tmp = nullptr;
 };
 
 #define CK(call)                                                                                       \
@@ -538,13 +538,9 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_push_ptr);
     cudaFree(ctx->d_push_cell);
     cudaFree(ctx->d_fused_epoch);
-    cudaFree(ctx->d_v2c_ptr);
-    cudaFree(ctx->d_v2b_ptr);
-    cudaFree(ctx->d_v2c_idx);
-    cudaFree(ctx->d_v2b_idx);
-    cudaFree(ctx->d_cell_tv);
-    cudaFree(ctx->d_qmin);
-    cudaFree(ctx->d_qmax);
+    cudaFree(ctx->d_lim_tab);
+    cudaFree(ctx->d_lim_nhv);
+    cudaFree(ctx->d_lim_tmp);
     for (int k = 0; k < tb_ctx::NSTAGE; ++k) {
         if (ctx->h_pinned[k]) cudaFreeHost(ctx->h_pinned[k]);
         if (ctx->h_event[k]) cudaEventDestroy(ctx->h_event[k]);
@@ -1013,80 +1009,134 @@ extern "C" int tb_tracer_stage(tb_ctx *ctx, double a0, double a1, double b_dt, c
 }
 
 static int limiter_setup(tb_ctx *ctx) {
-    const long long nc = ctx->n_cells, no = ctx->n_owned, nt = ctx->n_tvert;
+    // per-patch tables of the patch-staged limiter kernel (tb_tracer.cu): vertex halo, patch-local topological
+    // vertex ids of own and halo cells, exterior-facet masks
+    const long long nc = ctx->n_cells, no = ctx->n_owned, nt = ctx->n_tvert, np = ctx->n_patches;
     auto dev_cell = [&](long long c) -> long long { return c < no ? c : c - no + ctx->n_owned_pad; };
-    std::vector<long long> cnt(nt + 1, 0);
-    std::vector<int> cell_tv((size_t)(ctx->n_owned_pad + (nc - no)) * 3, 0);
-    for (long long c = 0; c < nc; ++c)
-        for (int a = 0; a < 3; ++a) {
-            const int tv = ctx->topo[ctx->cells[3 * c + a]];
-            cnt[tv + 1]++;
-            cell_tv[(size_t)dev_cell(c) * 3 + a] = tv;
+    auto tvert = [&](long long c, int a) -> int { return ctx->topo[ctx->cells[3 * c + a]]; };
+    auto bmask = [&](long long c) -> unsigned char {
+        unsigned char m = 0;
+        for (int f = 0; f < 3; ++f) {
+            const int32_t nb = ctx->nbr[3 * c + f];
+            if (nb < 0 && nb != std::numeric_limits<int32_t>::min()) m |= (unsigned char)(1 << f);
         }
+        return m;
+    };
+    // cells around each topological vertex (all local cells, ghosts included)
     std::vector<long long> ptr(nt + 1, 0);
-    for (long long v = 0; v < nt; ++v) ptr[v + 1] = ptr[v] + cnt[v + 1];
+    for (long long c = 0; c < nc; ++c)
+        for (int a = 0; a < 3; ++a) ptr[tvert(c, a) + 1]++;
+    for (long long v = 0; v < nt; ++v) ptr[v + 1] += ptr[v];
     std::vector<int> idx(ptr[nt]);
-    std::vector<long long> fillp(ptr.begin(), ptr.end() - 1);
-    for (long long c = 0; c < nc; ++c)
-        for (int a = 0; a < 3; ++a) idx[fillp[ctx->topo[ctx->cells[3 * c + a]]]++] = (int)dev_cell(c);
-    // exterior facets per vertex
-    std::vector<long long> bcnt(nt + 1, 0);
-    for (long long c = 0; c < nc; ++c)
-        for (int f = 0; f < 3; ++f) {
-            const int32_t nb = ctx->nbr[3 * c + f];
-            if (nb < 0 && nb != std::numeric_limits<int32_t>::min()) {
-                bcnt[ctx->topo[ctx->cells[3 * c + (f + 1) % 3]] + 1]++;
-                bcnt[ctx->topo[ctx->cells[3 * c + (f + 2) % 3]] + 1]++;
+    {
+        std::vector<long long> fill(ptr.begin(), ptr.end() - 1);
+        for (long long c = 0; c < nc; ++c)
+            for (int a = 0; a < 3; ++a) idx[fill[tvert(c, a)]++] = (int)c;
+    }
+    std::vector<std::vector<int>> pverts(np), phalo(np);
+    std::vector<int> vstamp(nt, -1), vloc(nt, 0), cstamp(nc, -1);
+    int NVT = 0, NHV = 0;
+    for (long long p = 0; p < np; ++p) {
+        const long long c0 = p * TB_P, c1 = std::min(no, c0 + TB_P);
+        for (long long c = c0; c < c1; ++c)
+            for (int a = 0; a < 3; ++a) {
+                const int v = tvert(c, a);
+                if (vstamp[v] != p) {
+                    vstamp[v] = (int)p;
+                    pverts[p].push_back(v);
+                    for (long long k = ptr[v]; k < ptr[v + 1]; ++k) {
+                        const int h = idx[k];
+                        if ((h < c0 || h >= c1) && cstamp[h] != p) {
+                            cstamp[h] = (int)p;
+                            phalo[p].push_back(h);
+                        }
+                    }
+                }
             }
+        NVT = std::max(NVT, (int)pverts[p].size());
+        NHV = std::max(NHV, (int)phalo[p].size());
+    }
+    if (NVT >= 0xffff) return fail(ctx, TB_ERR_UNSUPPORTED, "patch vertex table too large");
+    NVT = (NVT + 1) & ~1;
+    NHV = std::max((NHV + 3) & ~3, 4);
+    const size_t off_hvt = (size_t)NHV * sizeof(int32_t);
+    const size_t off_ctv = off_hvt + (size_t)NHV * 3 * sizeof(uint16_t);
+    const size_t off_hmask = off_ctv + (size_t)TB_P * 3 * sizeof(uint16_t);
+    const size_t off_cmask = off_hmask + (size_t)NHV;
+    const size_t stride = (off_cmask + TB_P + 15) & ~(size_t)15;
+    std::vector<unsigned char> tab((size_t)np * stride, 0);
+    std::vector<int32_t> nhv(np, 0);
+    std::fill(vstamp.begin(), vstamp.end(), -1);
+    for (long long p = 0; p < np; ++p) {
+        const long long c0 = p * TB_P, c1 = std::min(no, c0 + TB_P);
+        for (size_t k = 0; k < pverts[p].size(); ++k) {
+            vstamp[pverts[p][k]] = (int)p;
+            vloc[pverts[p][k]] = (int)k;
         }
-    std::vector<long long> bptr(nt + 1, 0);
-    for (long long v = 0; v < nt; ++v) bptr[v + 1] = bptr[v] + bcnt[v + 1];
-    std::vector<int> bidx(std::max<long long>(bptr[nt], 1));
-    std::vector<long long> bfill(bptr.begin(), bptr.end() - 1);
-    for (long long c = 0; c < nc; ++c)
-        for (int f = 0; f < 3; ++f) {
-            const int32_t nb = ctx->nbr[3 * c + f];
-            if (nb < 0 && nb != std::numeric_limits<int32_t>::min()) {
-                const int code = (int)dev_cell(c) * 4 + f;
-                bidx[bfill[ctx->topo[ctx->cells[3 * c + (f + 1) % 3]]]++] = code;
-                bidx[bfill[ctx->topo[ctx->cells[3 * c + (f + 2) % 3]]]++] = code;
+        unsigned char *blk = tab.data() + (size_t)p * stride;
+        int32_t *hids = reinterpret_cast<int32_t *>(blk);
+        uint16_t *hvt = reinterpret_cast<uint16_t *>(blk + off_hvt);
+        uint16_t *ctv = reinterpret_cast<uint16_t *>(blk + off_ctv);
+        nhv[p] = (int32_t)phalo[p].size();
+        for (size_t k = 0; k < phalo[p].size(); ++k) {
+            const long long h = phalo[p][k];
+            hids[k] = (int32_t)dev_cell(h);
+            for (int a = 0; a < 3; ++a) {
+                const int v = tvert(h, a);
+                hvt[k * 3 + a] = vstamp[v] == p ? (uint16_t)vloc[v] : (uint16_t)0xffff;
             }
+            blk[off_hmask + k] = bmask(h);
         }
-    CK(cudaMalloc(&ctx->d_v2c_ptr, sizeof(long long) * (nt + 1)));
-    CK(cudaMemcpy(ctx->d_v2c_ptr, ptr.data(), sizeof(long long) * (nt + 1), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&ctx->d_v2c_idx, sizeof(int) * std::max<size_t>(idx.size(), 1)));
-    CK(cudaMemcpy(ctx->d_v2c_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&ctx->d_v2b_ptr, sizeof(long long) * (nt + 1)));
-    CK(cudaMemcpy(ctx->d_v2b_ptr, bptr.data(), sizeof(long long) * (nt + 1), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&ctx->d_v2b_idx, sizeof(int) * bidx.size()));
-    CK(cudaMemcpy(ctx->d_v2b_idx, bidx.data(), sizeof(int) * bidx.size(), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&ctx->d_cell_tv, sizeof(int) * cell_tv.size()));
-    CK(cudaMemcpy(ctx->d_cell_tv, cell_tv.data(), sizeof(int) * cell_tv.size(), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&ctx->d_qmin, sizeof(double) * nt));
-    CK(cudaMalloc(&ctx->d_qmax, sizeof(double) * nt));
+        for (long long c = c0; c < c1; ++c) {
+            for (int a = 0; a < 3; ++a) ctv[(c - c0) * 3 + a] = (uint16_t)vloc[tvert(c, a)];
+            blk[off_cmask + (c - c0)] = bmask(c);
+        }
+    }
+    cudaFree(ctx->d_lim_tab);
+    cudaFree(ctx->d_lim_nhv);
+    ctx->d_lim_tab = nullptr;
+    ctx->d_lim_nhv = nullptr;
+    CK(cudaMalloc(&ctx->d_lim_tab, std::max<size_t>(tab.size(), 16)));
+    CK(cudaMemcpy(ctx->d_lim_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->d_lim_nhv, sizeof(int32_t) * np));
+    CK(cudaMemcpy(ctx->d_lim_nhv, nhv.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice));
     ctx->lim.n_owned = no;
     ctx->lim.n_cells = nc;
-    ctx->lim.n_tvert = nt;
-    ctx->lim.v2c_ptr = ctx->d_v2c_ptr;
-    ctx->lim.v2c_idx = ctx->d_v2c_idx;
-    ctx->lim.v2b_ptr = ctx->d_v2b_ptr;
-    ctx->lim.v2b_idx = ctx->d_v2b_idx;
-    ctx->lim.cell_tv = ctx->d_cell_tv;
-    ctx->lim.qmin = ctx->d_qmin;
-    ctx->lim.qmax = ctx->d_qmax;
+    ctx->lim.tab = ctx->d_lim_tab;
+    ctx->lim.stride = (long long)stride;
+    ctx->lim.NHV = NHV;
+    ctx->lim.NVT = NVT;
+    ctx->lim.off_hvt = (int)off_hvt;
+    ctx->lim.off_ctv = (int)off_ctv;
+    ctx->lim.off_hmask = (int)off_hmask;
+    ctx->lim.off_cmask = (int)off_cmask;
+    ctx->lim.nhv = ctx->d_lim_nhv;
     ctx->lim_ready = true;
     return TB_OK;
 }
 
-extern "C" int tb_limiter_apply(tb_ctx *ctx, double *c, void *stream) {
+extern "C" int tb_limiter_apply_to(tb_ctx *ctx, const double *c_in, double *c_out, void *stream) {
     TbRange range("tb_limiter_apply");
-    if (!ctx || !c) return fail(ctx, TB_ERR_ARG, "null pointer");
+    if (!ctx || !c_in || !c_out) return fail(ctx, TB_ERR_ARG, "null pointer");
+    if (c_in == c_out) return fail(ctx, TB_ERR_ARG, "c_out must not alias c_in (use tb_limiter_apply)");
     if (!ctx->lim_ready) {
         int rc = limiter_setup(ctx);
         if (rc != TB_OK) return rc;
     }
-    CK(tb_launch_limiter(ctx->lim, c, (cudaStream_t)stream));
-    ctx->launches += 2;
+    CK(tb_launch_limiter(ctx->lim, c_in, c_out, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return TB_OK;
+}
+
+extern "C" int tb_limiter_apply(tb_ctx *ctx, double *c, void *stream) {
+    // in place = out of place into a scratch array + copy back of the owned cells (neighbouring patches read the
+    // original values of each other's cells); integrators that can swap buffers use tb_limiter_apply_to
+    if (!ctx || !c) return fail(ctx, TB_ERR_ARG, "null pointer");
+    if (!ctx->d_lim_tmp) CK(cudaMalloc(&ctx->d_lim_tmp, sizeof(double) * (size_t)tb_tracer_len(ctx)));
+    int rc = tb_limiter_apply_to(ctx, c, ctx->d_lim_tmp, stream);
+    if (rc != TB_OK) return rc;
+    CK(cudaMemcpyAsync(c, ctx->d_lim_tmp, sizeof(double) * (size_t)ctx->n_owned * 3, cudaMemcpyDeviceToDevice,
+                       (cudaStream_t)stream));
     return TB_OK;
 }
 

@@ -158,14 +158,17 @@ cudaError_t tb_launch_patch_partials_final(const double *partial, long long n, d
 cudaError_t tb_launch_swe_integrals(const double *state, const double *area, const double *bath3, long long n_owned,
                                     double *partial, double *out, cudaStream_t s);
 #define TB_NRED 296           // CTAs of the two-pass reductions (2 per SM)
-// limiter: vertex bounds via deterministic CSR gather, then per-cell clamp
+// limiter: one patch-staged kernel (tb_tracer.cu); per patch a static table at tab + patch*stride:
+//   int32  hids[NHV]      device cell ids of the vertex halo (cells outside the patch sharing a vertex with it)
+//   uint16 hvt[NHV][3]    patch-local topological vertex of each halo-cell node, 0xffff = not a patch vertex
+//   uint16 ctv[TB_P][3]   patch-local topological vertex of each own-cell node
+//   uint8  hmask[NHV], cmask[TB_P]   bit f = local facet f is an exterior facet
 struct TbLimiterData {
-    long long n_owned, n_cells, n_tvert;
-    const long long *v2c_ptr;    // [n_tvert+1]
-    const int *v2c_idx;          // cells around each topological vertex
-    const long long *v2b_ptr;    // [n_tvert+1]
-    const int *v2b_idx;          // exterior facets touching each topological vertex: cell*4 + local facet
-    const int *cell_tv;          // [n_cells*3] topological vertex of each cell node
-    double *qmin, *qmax;         // [n_tvert]
+    long long n_owned, n_cells;
+    const unsigned char *tab;
+    long long stride;
+    int NHV, NVT;                // padded sizes: vertex-halo cells / topological vertices per patch
+    int off_hvt, off_ctv, off_hmask, off_cmask;
+    const int *nhv;              // [n_patches] vertex-halo cells of each patch
 };
-cudaError_t tb_launch_limiter(const TbLimiterData &d, double *c, cudaStream_t s);
+cudaError_t tb_launch_limiter(const TbLimiterData &d, const double *c_in, double *c_out, cudaStream_t s);

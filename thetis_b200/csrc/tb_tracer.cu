@@ -371,50 +371,118 @@ cudaError_t tb_launch_tracer_stage(const TbTracerParams &p, int n_patches, size_
 }
 
 // ------------------------------------------------------------------ limiter
-// (i) vertex bounds: max/min over the centroids of the cells around each vertex plus the means of the
-// exterior facets touching it; deterministic gather over CSR lists (no atomics).
-__global__ void limiter_bounds_kernel(TbLimiterData d, const double *__restrict__ c) {
-    long long vtx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (vtx >= d.n_tvert) return;
-    double qmax = -1.0e10, qmin = 1.0e10;   // firedrake VertexBasedLimiter.compute_bounds initial values
-    for (long long k = d.v2c_ptr[vtx]; k < d.v2c_ptr[vtx + 1]; ++k) {
-        const double *r = c + (long long)d.v2c_idx[k] * 3;
-        // P0 projection of a P1 field = mean of nodal values (limiter.py:90-97)
-        const double qb = (r[0] + r[1] + r[2]) / 3.0;
-        qmax = fmax(qmax, qb);
-        qmin = fmin(qmin, qb);
-    }
-    for (long long k = d.v2b_ptr[vtx]; k < d.v2b_ptr[vtx + 1]; ++k) {
-        const int code = d.v2b_idx[k];
-        const double *r = c + (long long)(code >> 2) * 3;
-        const int lf = code & 3;
-        const double fm = (r[(lf + 1) % 3] + r[(lf + 2) % 3]) / 2;   // limiter.py:123-137
-        qmax = fmax(qmax, fm);
-        qmin = fmin(qmin, fm);
-    }
-    d.qmax[vtx] = qmax;
-    d.qmin[vtx] = qmin;
+// VertexBasedP1DGLimiter.apply (limiter.py:182-198 over firedrake's VertexBasedLimiter) as ONE patch-staged kernel.
+// One CTA = one patch of TB_P cells (the patches of the stage kernels).  Per patch a static table (built once,
+// limiter_setup in tb_api.cu) lists the cells outside the patch that share a vertex with it ("vertex halo") and, for
+// own and halo cells, the patch-local id of each of their vertices and a mask of their exterior facets.
+//   (i)   every thread loads its cell (24 B, read once) and forms the P0 projection = mean of the nodal values
+//         (limiter.py:90-97); the vertex-halo cells are gathered by the same threads (mostly L2 hits: they belong to
+//         patches running at the same time);
+//   (ii)  vertex bounds in shared memory: min / max over the means of ALL cells around each vertex, plus the mean of
+//         the two nodal values of every exterior facet touching it (limiter.py:109-145), by shared-memory atomicMin /
+//         atomicMax on an order-preserving 64-bit encoding of the doubles -- min and max are exact and
+//         order-independent, so the result is deterministic and identical to the serial gather;
+//   (iii) per-cell clamp (VertexBasedLimiter._limit_kernel) and ONE write of the limited cell (24 B).
+// Out of place (c_in -> c_out): neighbouring patches read this patch's ORIGINAL values as their vertex halo.
+// Replaces the two global passes (vertex CSR gather + per-cell clamp) that moved 94 B per triangle for 64 needed.
+__device__ __forceinline__ unsigned long long tb_enc_ordered(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
-// (ii) per-cell clamp (firedrake VertexBasedLimiter._limit_kernel)
-__global__ void limiter_apply_kernel(TbLimiterData d, double *__restrict__ c) {
-    long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= d.n_owned) return;
-    double q[3] = {c[cell * 3], c[cell * 3 + 1], c[cell * 3 + 2]};
+__device__ __forceinline__ double tb_dec_ordered(unsigned long long u) {
+    const unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(TB_P) limiter_patch_kernel(TbLimiterData d, const double *__restrict__ c_in,
+                                                             double *__restrict__ c_out) {
+    extern __shared__ __align__(16) unsigned char lsm[];
+    unsigned long long *qmin_s = reinterpret_cast<unsigned long long *>(lsm);
+    unsigned long long *qmax_s = qmin_s + d.NVT;
+    const int tid = threadIdx.x;
+    const long long patch = blockIdx.x;
+    const long long cell = patch * TB_P + tid;
+    const bool active = cell < d.n_owned;
+    const unsigned char *blk = d.tab + patch * d.stride;
+    const int *hids = reinterpret_cast<const int *>(blk);
+    const unsigned short *hvt = reinterpret_cast<const unsigned short *>(blk + d.off_hvt);
+    const unsigned short *ctv = reinterpret_cast<const unsigned short *>(blk + d.off_ctv);
+    const unsigned char *hmask = blk + d.off_hmask;
+    const unsigned char *cmask = blk + d.off_cmask;
+    const int nhv = __ldg(d.nhv + patch);
+
+    double q[3] = {0, 0, 0};
+    int lv[3] = {0, 0, 0};
+    int msk = 0;
+    if (active) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            q[a] = __ldg(c_in + cell * 3 + a);
+            lv[a] = ctv[tid * 3 + a];
+        }
+        msk = cmask[tid];
+    }
+    for (int v = tid; v < d.NVT; v += TB_P) {
+        qmin_s[v] = tb_enc_ordered(1.0e10);        // firedrake VertexBasedLimiter.compute_bounds initial values
+        qmax_s[v] = tb_enc_ordered(-1.0e10);
+    }
+    __syncthreads();
     const double qavg = (q[0] + q[1] + q[2]) / 3.0;
+    if (active) {
+        const unsigned long long e = tb_enc_ordered(qavg);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(qmin_s + lv[a], e);
+            atomicMax(qmax_s + lv[a], e);
+        }
+        if (msk) {
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+                if (msk & (1 << f)) {
+                    const int p = (f + 1) % 3, r = (f + 2) % 3;
+                    const unsigned long long fe = tb_enc_ordered((q[p] + q[r]) / 2);      // limiter.py:123-137
+                    atomicMin(qmin_s + lv[p], fe); atomicMax(qmax_s + lv[p], fe);
+                    atomicMin(qmin_s + lv[r], fe); atomicMax(qmax_s + lv[r], fe);
+                }
+        }
+    }
+    for (int h = tid; h < nhv; h += TB_P) {
+        const double *r = c_in + (long long)__ldg(hids + h) * 3;
+        const double h0 = __ldg(r), h1 = __ldg(r + 1), h2 = __ldg(r + 2);
+        const unsigned long long e = tb_enc_ordered((h0 + h1 + h2) / 3.0);
+        const int v0 = hvt[h * 3], v1 = hvt[h * 3 + 1], v2 = hvt[h * 3 + 2];
+        if (v0 != 0xffff) { atomicMin(qmin_s + v0, e); atomicMax(qmax_s + v0, e); }
+        if (v1 != 0xffff) { atomicMin(qmin_s + v1, e); atomicMax(qmax_s + v1, e); }
+        if (v2 != 0xffff) { atomicMin(qmin_s + v2, e); atomicMax(qmax_s + v2, e); }
+        const int hm = hmask[h];
+        if (hm) {
+            const double hq[3] = {h0, h1, h2};
+            const int hv[3] = {v0, v1, v2};
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+                if (hm & (1 << f)) {
+                    const int p = (f + 1) % 3, rr = (f + 2) % 3;
+                    const unsigned long long fe = tb_enc_ordered((hq[p] + hq[rr]) / 2);
+                    if (hv[p] != 0xffff) { atomicMin(qmin_s + hv[p], fe); atomicMax(qmax_s + hv[p], fe); }
+                    if (hv[rr] != 0xffff) { atomicMin(qmin_s + hv[rr], fe); atomicMax(qmax_s + hv[rr], fe); }
+                }
+        }
+    }
+    __syncthreads();
+    if (!active) return;
     double alpha = 1.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const int tv = d.cell_tv[cell * 3 + i];
         if (q[i] > qavg)
-            alpha = fmin(alpha, fmin(1.0, (d.qmax[tv] - qavg) / (q[i] - qavg)));
+            alpha = fmin(alpha, fmin(1.0, (tb_dec_ordered(qmax_s[lv[i]]) - qavg) / (q[i] - qavg)));
         else if (q[i] < qavg)
-            alpha = fmin(alpha, fmin(1.0, (qavg - d.qmin[tv]) / (qavg - q[i])));
+            alpha = fmin(alpha, fmin(1.0, (qavg - tb_dec_ordered(qmin_s[lv[i]])) / (qavg - q[i])));
     }
 #pragma unroll
-    for (int i = 0; i < 3; ++i) c[cell * 3 + i] = qavg + alpha * (q[i] - qavg);
+    for (int i = 0; i < 3; ++i) c_out[cell * 3 + i] = qavg + alpha * (q[i] - qavg);
 }
-cudaError_t tb_launch_limiter(const TbLimiterData &d, double *c, cudaStream_t s) {
-    if (d.n_tvert) limiter_bounds_kernel<<<(unsigned)((d.n_tvert + 255) / 256), 256, 0, s>>>(d, c);
-    if (d.n_owned) limiter_apply_kernel<<<(unsigned)((d.n_owned + 255) / 256), 256, 0, s>>>(d, c);
+cudaError_t tb_launch_limiter(const TbLimiterData &d, const double *c_in, double *c_out, cudaStream_t s) {
+    const long long np = (d.n_owned + TB_P - 1) / TB_P;
+    if (np > 0) limiter_patch_kernel<<<(unsigned)np, TB_P, (size_t)d.NVT * 16, s>>>(d, c_in, c_out);
     return cudaGetLastError();
 }

@@ -202,6 +202,10 @@ class Engine:
     def limiter_apply(self, c):
         self._ck(self.lib.tb_limiter_apply(self.ctx, _ptr(c), self.stream))
 
+    def limiter_apply_to(self, c_in, c_out):
+        """out of place: owned cells of c_out = limited c_in (one patch-staged kernel, no copy back)"""
+        self._ck(self.lib.tb_limiter_apply_to(self.ctx, _ptr(c_in), _ptr(c_out), self.stream))
+
     def swe_integrals(self, state, out):
         """out (device, 4 doubles): int eta^2, int |u|^2, int eta, int (eta + bathymetry)"""
         self._ck(self.lib.tb_swe_integrals(self.ctx, _ptr(state), _ptr(out), self.stream))

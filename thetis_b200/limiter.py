@@ -46,7 +46,11 @@ class VertexBasedP1DGLimiter:
             # the field lives on the device: limit there, no host round trip
             if not st._host_stale and st._host_changed():
                 st.upload()
-            eng.limiter_apply(st.device_state())
+            # out of place into the integrator's scratch buffer (neighbouring patches read each other's ORIGINAL
+            # values), then the two buffers swap roles: no copy back
+            src, dst = st.buf[0], st.buf[1]
+            eng.limiter_apply_to(src, dst)
+            st.buf[0], st.buf[1] = dst, src
             if self.halo is not None:
                 self.halo.exchange(st.device_state())      # limited ghost values for the next step
             st.mark_device_modified()

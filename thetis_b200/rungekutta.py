@@ -83,15 +83,15 @@ def _opt(options, name, default=None):
 def _version(obj):
     """Cheap change stamp of a Function/Constant (PyOP2 dat_version when available); for an expression the tuple of
     its operands' stamps."""
-    if is_expression(obj):
-        vs = tuple((id(o), _version(o)) for o in expression_leaves(obj))
-        return None if any(v[1] is None for v in vs) else ("expr", vs)
     d = getattr(obj, "dat", None)
-    if d is not None:
+    if d is not None:        # Functions and Constants: the common, cheap case first
         v = getattr(d, "dat_version", None)
         if v is not None:
             return ("dat", v)
         return None          # unknown: always refresh
+    if is_expression(obj):
+        vs = tuple((id(o), _version(o)) for o in expression_leaves(obj))
+        return None if any(v[1] is None for v in vs) else ("expr", vs)
     v = getattr(obj, "version", None)
     return None if v is None else ("const", v)
 
@@ -410,7 +410,8 @@ class ERKGenericShuOsher:
             for leaf in leaves:
                 ent = index.get(id(leaf))
                 if ent is None:
-                    ent = index[id(leaf)] = [leaf, _version(leaf), []]
+                    d = getattr(leaf, "dat", None)
+                    ent = index[id(leaf)] = [leaf, _version(leaf), [], d if hasattr(d, "dat_version") else None]
                     watch.append(ent)
                 ent[2].append(action)
         eqo = self.equation.options
@@ -429,8 +430,13 @@ class ERKGenericShuOsher:
                 continue
             add(val, lambda fid=fid, val=val, name=name: self._set_field(fid, val, name))
         for marker, funcs in self.bnd_conditions.items():
-            for val in (funcs or {}).values():
-                add(val, lambda marker=marker, funcs=funcs: self._push_bc_marker(0, _SWE_TAGS, marker, funcs))
+            for tag, val in (funcs or {}).items():
+                if is_constant(val):
+                    # a Constant is a kernel parameter of the marker's slot: re-push the slot
+                    add(val, lambda marker=marker, funcs=funcs: self._push_bc_marker(0, _SWE_TAGS, marker, funcs))
+                else:
+                    # Function / expression data: only that array travels (the tidal elevation of every stage)
+                    add(val, lambda marker=marker, tag=tag, val=val: self._push_bc_array(0, _SWE_TAGS, marker, tag, val))
         self._watch = watch
         self._watch_sig = self._watch_signature()
         # a datum without a version counter must be re-read every stage: no fast path then
@@ -442,7 +448,8 @@ class ERKGenericShuOsher:
             return False
         dirty = False
         for ent in self._watch:
-            v = _version(ent[0])
+            d = ent[3]
+            v = ("dat", d.dat_version) if d is not None else _version(ent[0])
             if v != ent[1]:
                 ent[1] = v
                 for act in ent[2]:
@@ -509,12 +516,18 @@ class ERKGenericShuOsher:
                 for tag, _ in arrays:
                     self._bc_versions.pop((eq, marker, tag), None)
             for tag, val in arrays:
-                ver = _version(val)
-                akey = (eq, marker, tag)
-                astamp = (id(val), ver)
-                if ver is None or self._bc_versions.get(akey) != astamp:
-                    eng.set_bc_array(eq, marker, tags[tag], self.adaptor.bfacet_values(val, marker))
-                    self._bc_versions[akey] = astamp
+                self._push_bc_array(eq, tags, marker, tag, val)
+
+    def _push_bc_array(self, eq, tags, marker, tag, val):
+        """Upload one Function- / expression-valued boundary datum if it changed (pinned ring + async H2D)."""
+        ver = _version(val)
+        akey = (eq, marker, tag)
+        astamp = (id(val), ver)
+        if ver is None or self._bc_versions.get(akey) != astamp:
+            self.engine.set_bc_array(eq, marker, tags[tag], self.adaptor.bfacet_values(val, marker))
+            self._bc_versions[akey] = astamp
+            # keep the marker-level fast-path signature of _push_bc_marker consistent with what is on the device
+            self._stamps.pop(("bc", eq, marker), None)
 
     # ------------------------------------------------------------------ host <-> device
     def _solution_version(self):
