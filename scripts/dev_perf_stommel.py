@@ -29,7 +29,7 @@ def timeit(label, alg):
         eng.swe_stage(0.0, 1.0, 1.0, A, None, B); eng.swe_stage(0.75, 0.25, 0.25, B, A, C); eng.swe_stage(1 / 3, 2 / 3, 2 / 3, C, A, B)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 120
-    print(f"{label}: {ms:.4f} ms/stage  alg {alg*nt/ms/1e6:.0f} GB/s ({alg*nt/ms/1e6/6555.8*100:.1f}%)", flush=True)
+    print(f"{label}: {ms:.4f} ms/stage  alg {alg*nt/ms/1e6:.0f} GB/s ({alg*nt/ms/1e6/6551.0*100:.1f}%)", flush=True)
 
 
 eng.set_field(L.F_BATHYMETRY, 1000.0)

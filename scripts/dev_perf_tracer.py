@@ -35,5 +35,5 @@ ms = timeit(step)
 print(f"coupled step: {ms:.3f} ms  -> {(9+3)*nt/ms/1e3:.0f} M dof-updates/s")
 ms_s = timeit(lambda: eng.swe_stage(0.75, 0.25, dt, B, A, C))
 ms_t = timeit(lambda: eng.tracer_stage(0.75, 0.25, dt, cb, ca, cc, A))
-ms_l = timeit(lambda: eng.limiter_apply(ca))
+ms_l = timeit(lambda: eng.limiter_apply_to(ca, cb))
 print(f"swe stage {ms_s:.4f} ms ({228*nt/ms_s/1e6:.0f} GB/s alg)  tracer stage {ms_t:.4f} ms ({(64+72)*nt/ms_t/1e6:.0f} GB/s alg incl. SWE record read)  limiter {ms_l:.4f} ms ({64*nt/ms_l/1e6:.0f} GB/s alg)")

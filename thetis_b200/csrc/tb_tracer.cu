@@ -379,8 +379,8 @@ cudaError_t tb_launch_tracer_stage(const TbTracerParams &p, int n_patches, size_
 //         (limiter.py:90-97); the vertex-halo cells are gathered by the same threads (mostly L2 hits: they belong to
 //         patches running at the same time);
 //   (ii)  vertex bounds in shared memory: min / max over the means of ALL cells around each vertex, plus the mean of
-//         the two nodal values of every exterior facet touching it (limiter.py:109-145), by shared-memory atomicMin /
-//         atomicMax on an order-preserving 64-bit encoding of the doubles -- min and max are exact and
+//         the two nodal values of every exterior facet touching it (limiter.py:109-145), by shared-memory atomic
+//         min / max on an order-preserving 64-bit encoding of the doubles -- min and max are exact and
 //         order-independent, so the result is deterministic and identical to the serial gather;
 //   (iii) per-cell clamp (VertexBasedLimiter._limit_kernel) and ONE write of the limited cell (24 B).
 // Out of place (c_in -> c_out): neighbouring patches read this patch's ORIGINAL values as their vertex halo.
@@ -394,11 +394,38 @@ __device__ __forceinline__ double tb_dec_ordered(unsigned long long u) {
     return __longlong_as_double((long long)b);
 }
 
+// The 64-bit min / max of the ordered encodings is taken lexicographically with NATIVE 32-bit shared-memory atomics in
+// two passes (high words, then the low words of the contributions whose high word won): 64-bit atomicMin / atomicMax
+// on shared memory compile to compare-and-swap loops, which made the first version of this kernel instruction-bound.
+struct LimBounds {
+    unsigned *hmin, *lmin, *hmax, *lmax;
+    __device__ __forceinline__ void pass1(int v, unsigned long long e) const {
+        const unsigned hi = (unsigned)(e >> 32);
+        atomicMin(hmin + v, hi);
+        atomicMax(hmax + v, hi);
+    }
+    __device__ __forceinline__ void pass2(int v, unsigned long long e) const {
+        const unsigned hi = (unsigned)(e >> 32), lo = (unsigned)e;
+        if (hi == hmin[v]) atomicMin(lmin + v, lo);
+        if (hi == hmax[v]) atomicMax(lmax + v, lo);
+    }
+    __device__ __forceinline__ double qmin(int v) const {
+        return tb_dec_ordered(((unsigned long long)hmin[v] << 32) | lmin[v]);
+    }
+    __device__ __forceinline__ double qmax(int v) const {
+        return tb_dec_ordered(((unsigned long long)hmax[v] << 32) | lmax[v]);
+    }
+};
+
 __global__ void __launch_bounds__(TB_P) limiter_patch_kernel(TbLimiterData d, const double *__restrict__ c_in,
                                                              double *__restrict__ c_out) {
     extern __shared__ __align__(16) unsigned char lsm[];
-    unsigned long long *qmin_s = reinterpret_cast<unsigned long long *>(lsm);
-    unsigned long long *qmax_s = qmin_s + d.NVT;
+    LimBounds B;
+    B.hmin = reinterpret_cast<unsigned *>(lsm);
+    B.lmin = B.hmin + d.NVT;
+    B.hmax = B.lmin + d.NVT;
+    B.lmax = B.hmax + d.NVT;
+    unsigned long long *hmean = reinterpret_cast<unsigned long long *>(B.lmax + d.NVT);     // [NHV] encoded halo means
     const int tid = threadIdx.x;
     const long long patch = blockIdx.x;
     const long long cell = patch * TB_P + tid;
@@ -410,6 +437,8 @@ __global__ void __launch_bounds__(TB_P) limiter_patch_kernel(TbLimiterData d, co
     const unsigned char *hmask = blk + d.off_hmask;
     const unsigned char *cmask = blk + d.off_cmask;
     const int nhv = __ldg(d.nhv + patch);
+    // firedrake VertexBasedLimiter.compute_bounds initial values
+    const unsigned long long e0min = tb_enc_ordered(1.0e10), e0max = tb_enc_ordered(-1.0e10);
 
     double q[3] = {0, 0, 0};
     int lv[3] = {0, 0, 0};
@@ -423,66 +452,107 @@ __global__ void __launch_bounds__(TB_P) limiter_patch_kernel(TbLimiterData d, co
         msk = cmask[tid];
     }
     for (int v = tid; v < d.NVT; v += TB_P) {
-        qmin_s[v] = tb_enc_ordered(1.0e10);        // firedrake VertexBasedLimiter.compute_bounds initial values
-        qmax_s[v] = tb_enc_ordered(-1.0e10);
+        B.hmin[v] = (unsigned)(e0min >> 32);
+        B.hmax[v] = (unsigned)(e0max >> 32);
+        B.lmin[v] = 0xffffffffu;
+        B.lmax[v] = 0u;
     }
     __syncthreads();
-    const double qavg = (q[0] + q[1] + q[2]) / 3.0;
+    // ---- pass 1: high words
+    const double qavg = (q[0] + q[1] + q[2]) / 3.0;        // P0 projection = mean of the nodal values (limiter.py:90-97)
+    const unsigned long long e = tb_enc_ordered(qavg);
     if (active) {
-        const unsigned long long e = tb_enc_ordered(qavg);
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            atomicMin(qmin_s + lv[a], e);
-            atomicMax(qmax_s + lv[a], e);
-        }
+        for (int a = 0; a < 3; ++a) B.pass1(lv[a], e);
         if (msk) {
 #pragma unroll
             for (int f = 0; f < 3; ++f)
                 if (msk & (1 << f)) {
                     const int p = (f + 1) % 3, r = (f + 2) % 3;
                     const unsigned long long fe = tb_enc_ordered((q[p] + q[r]) / 2);      // limiter.py:123-137
-                    atomicMin(qmin_s + lv[p], fe); atomicMax(qmax_s + lv[p], fe);
-                    atomicMin(qmin_s + lv[r], fe); atomicMax(qmax_s + lv[r], fe);
+                    B.pass1(lv[p], fe);
+                    B.pass1(lv[r], fe);
                 }
         }
     }
     for (int h = tid; h < nhv; h += TB_P) {
         const double *r = c_in + (long long)__ldg(hids + h) * 3;
         const double h0 = __ldg(r), h1 = __ldg(r + 1), h2 = __ldg(r + 2);
-        const unsigned long long e = tb_enc_ordered((h0 + h1 + h2) / 3.0);
-        const int v0 = hvt[h * 3], v1 = hvt[h * 3 + 1], v2 = hvt[h * 3 + 2];
-        if (v0 != 0xffff) { atomicMin(qmin_s + v0, e); atomicMax(qmax_s + v0, e); }
-        if (v1 != 0xffff) { atomicMin(qmin_s + v1, e); atomicMax(qmax_s + v1, e); }
-        if (v2 != 0xffff) { atomicMin(qmin_s + v2, e); atomicMax(qmax_s + v2, e); }
+        const unsigned long long he = tb_enc_ordered((h0 + h1 + h2) / 3.0);
+        hmean[h] = he;
+        const int hv[3] = {hvt[h * 3], hvt[h * 3 + 1], hvt[h * 3 + 2]};
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (hv[a] != 0xffff) B.pass1(hv[a], he);
         const int hm = hmask[h];
         if (hm) {
             const double hq[3] = {h0, h1, h2};
-            const int hv[3] = {v0, v1, v2};
 #pragma unroll
             for (int f = 0; f < 3; ++f)
                 if (hm & (1 << f)) {
                     const int p = (f + 1) % 3, rr = (f + 2) % 3;
                     const unsigned long long fe = tb_enc_ordered((hq[p] + hq[rr]) / 2);
-                    if (hv[p] != 0xffff) { atomicMin(qmin_s + hv[p], fe); atomicMax(qmax_s + hv[p], fe); }
-                    if (hv[rr] != 0xffff) { atomicMin(qmin_s + hv[rr], fe); atomicMax(qmax_s + hv[rr], fe); }
+                    if (hv[p] != 0xffff) B.pass1(hv[p], fe);
+                    if (hv[rr] != 0xffff) B.pass1(hv[rr], fe);
+                }
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: low words of the contributions whose high word won (the initial values take part too)
+    for (int v = tid; v < d.NVT; v += TB_P) {
+        if ((unsigned)(e0min >> 32) == B.hmin[v]) atomicMin(B.lmin + v, (unsigned)e0min);
+        if ((unsigned)(e0max >> 32) == B.hmax[v]) atomicMax(B.lmax + v, (unsigned)e0max);
+    }
+    if (active) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) B.pass2(lv[a], e);
+        if (msk) {
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+                if (msk & (1 << f)) {
+                    const int p = (f + 1) % 3, r = (f + 2) % 3;
+                    const unsigned long long fe = tb_enc_ordered((q[p] + q[r]) / 2);
+                    B.pass2(lv[p], fe);
+                    B.pass2(lv[r], fe);
+                }
+        }
+    }
+    for (int h = tid; h < nhv; h += TB_P) {
+        const unsigned long long he = hmean[h];
+        const int hv[3] = {hvt[h * 3], hvt[h * 3 + 1], hvt[h * 3 + 2]};
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (hv[a] != 0xffff) B.pass2(hv[a], he);
+        const int hm = hmask[h];
+        if (hm) {        // exterior facets of halo cells (rare): the nodal values are read again
+            const double *r = c_in + (long long)__ldg(hids + h) * 3;
+            const double hq[3] = {__ldg(r), __ldg(r + 1), __ldg(r + 2)};
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+                if (hm & (1 << f)) {
+                    const int p = (f + 1) % 3, rr = (f + 2) % 3;
+                    const unsigned long long fe = tb_enc_ordered((hq[p] + hq[rr]) / 2);
+                    if (hv[p] != 0xffff) B.pass2(hv[p], fe);
+                    if (hv[rr] != 0xffff) B.pass2(hv[rr], fe);
                 }
         }
     }
     __syncthreads();
     if (!active) return;
+    // ---- per-cell clamp (VertexBasedLimiter._limit_kernel) and ONE write of the limited cell
     double alpha = 1.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         if (q[i] > qavg)
-            alpha = fmin(alpha, fmin(1.0, (tb_dec_ordered(qmax_s[lv[i]]) - qavg) / (q[i] - qavg)));
+            alpha = fmin(alpha, fmin(1.0, (B.qmax(lv[i]) - qavg) / (q[i] - qavg)));
         else if (q[i] < qavg)
-            alpha = fmin(alpha, fmin(1.0, (qavg - tb_dec_ordered(qmin_s[lv[i]])) / (qavg - q[i])));
+            alpha = fmin(alpha, fmin(1.0, (qavg - B.qmin(lv[i])) / (qavg - q[i])));
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) c_out[cell * 3 + i] = qavg + alpha * (q[i] - qavg);
 }
 cudaError_t tb_launch_limiter(const TbLimiterData &d, const double *c_in, double *c_out, cudaStream_t s) {
     const long long np = (d.n_owned + TB_P - 1) / TB_P;
-    if (np > 0) limiter_patch_kernel<<<(unsigned)np, TB_P, (size_t)d.NVT * 16, s>>>(d, c_in, c_out);
+    if (np > 0) limiter_patch_kernel<<<(unsigned)np, TB_P, (size_t)d.NVT * 16 + (size_t)d.NHV * 8, s>>>(d, c_in, c_out);
     return cudaGetLastError();
 }

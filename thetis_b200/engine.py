@@ -16,6 +16,11 @@ from .mesh import Mesh2D, sfc_renumber
 
 __all__ = ["Engine", "get_engine"]
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+if _raw_stream is None:
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+
 
 def _ptr(t):
     if t is None:
@@ -42,6 +47,8 @@ class Engine:
         self.lib = L.load()
         self.mesh = mesh
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self._dev_index = self.device.index
+        self._fields_pending = True
         self.n_cells = mesh.n_cells
         self.n_owned = mesh.n_cells if n_owned is None else int(n_owned)
         tm = L.TbMesh()
@@ -79,7 +86,9 @@ class Engine:
     # ------------------------------------------------------------ helpers
     @property
     def stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # raw handle of torch's current stream on this device (the C-level getter: ~10x cheaper than building a
+        # torch.cuda.Stream object, and this is read on every call into the library)
+        return C.c_void_p(_raw_stream(self._dev_index))
 
     def _ck(self, rc):
         L.check(self.ctx, rc)
@@ -104,6 +113,7 @@ class Engine:
     def set_field(self, field, value):
         """value: None | scalar/sequence (Constant) | ndarray over geometric vertices (nv,) / (nv, 2) (P1) |
         ndarray over cell nodes (n_cells, 3) / (n_cells, 3, 2) (discontinuous P1DG, cell terms only)."""
+        self._fields_pending = True
         if value is None:
             self._ck(self.lib.tb_clear_field(self.ctx, field))
             return
@@ -124,7 +134,10 @@ class Engine:
     def sync_fields(self):
         """Apply pending coefficient changes on the current stream (needed in front of a CUDA-graph replay; plain
         stage launches do it themselves)."""
+        if not self._fields_pending:
+            return
         self._ck(self.lib.tb_sync_fields(self.ctx, self.stream))
+        self._fields_pending = False
 
     def clear_bc(self, eq, marker):
         self._ck(self.lib.tb_clear_bc(self.ctx, eq, int(marker)))
