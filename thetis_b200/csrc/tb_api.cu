@@ -1056,16 +1056,46 @@ static int limiter_setup(tb_ctx *ctx) {
         NVT = std::max(NVT, (int)pverts[p].size());
         NHV = std::max(NHV, (int)phalo[p].size());
     }
-    if (NVT >= 0xffff) return fail(ctx, TB_ERR_UNSUPPORTED, "patch vertex table too large");
+    if (NHV + TB_P >= 8192) return fail(ctx, TB_ERR_UNSUPPORTED, "patch vertex halo too large");
     NVT = (NVT + 1) & ~1;
     NHV = std::max((NHV + 3) & ~3, 4);
-    const size_t off_hvt = (size_t)NHV * sizeof(int32_t);
-    const size_t off_ctv = off_hvt + (size_t)NHV * 3 * sizeof(uint16_t);
-    const size_t off_hmask = off_ctv + (size_t)TB_P * 3 * sizeof(uint16_t);
-    const size_t off_cmask = off_hmask + (size_t)NHV;
-    const size_t stride = (off_cmask + TB_P + 15) & ~(size_t)15;
+    // per-vertex entry lists (second pass) to size the CSR
+    std::vector<std::vector<uint16_t>> pent(np);
+    std::vector<std::vector<uint16_t>> pptr(np);
+    std::vector<int> hslot(nc, 0);
+    size_t NE = 0;
+    std::fill(vstamp.begin(), vstamp.end(), -1);
+    for (long long p = 0; p < np; ++p) {
+        const long long c0 = p * TB_P, c1 = std::min(no, c0 + TB_P);
+        for (size_t k = 0; k < phalo[p].size(); ++k) hslot[phalo[p][k]] = TB_P + (int)k;
+        auto slot_of = [&](long long c) -> int { return (c >= c0 && c < c1) ? (int)(c - c0) : hslot[c]; };
+        auto &ent = pent[p];
+        auto &vp = pptr[p];
+        vp.push_back(0);
+        for (size_t k = 0; k < pverts[p].size(); ++k) {
+            const int v = pverts[p][k];
+            for (long long kk = ptr[v]; kk < ptr[v + 1]; ++kk) {
+                const long long c = idx[kk];
+                const int sl = slot_of(c);
+                ent.push_back((uint16_t)sl);
+                const unsigned char m = bmask(c);
+                if (m)
+                    for (int f = 0; f < 3; ++f)
+                        if ((m & (1 << f)) && (tvert(c, (f + 1) % 3) == v || tvert(c, (f + 2) % 3) == v))
+                            ent.push_back((uint16_t)(0x8000 | (sl << 2) | f));
+            }
+            if (ent.size() > 0xffff) return fail(ctx, TB_ERR_UNSUPPORTED, "patch vertex adjacency too large");
+            vp.push_back((uint16_t)ent.size());
+        }
+        NE = std::max(NE, ent.size());
+    }
+    NE = (NE + 7) & ~(size_t)7;
+    const size_t off_ctv = (size_t)NHV * sizeof(int32_t);
+    const size_t off_vptr = off_ctv + (size_t)TB_P * 3 * sizeof(uint16_t);
+    const size_t off_vidx = off_vptr + (((size_t)(NVT + 1) * sizeof(uint16_t) + 3) & ~(size_t)3);
+    const size_t stride = (off_vidx + NE * sizeof(uint16_t) + 15) & ~(size_t)15;
     std::vector<unsigned char> tab((size_t)np * stride, 0);
-    std::vector<int32_t> nhv(np, 0);
+    std::vector<int32_t> nhv((size_t)np * 2, 0);
     std::fill(vstamp.begin(), vstamp.end(), -1);
     for (long long p = 0; p < np; ++p) {
         const long long c0 = p * TB_P, c1 = std::min(no, c0 + TB_P);
@@ -1075,22 +1105,14 @@ static int limiter_setup(tb_ctx *ctx) {
         }
         unsigned char *blk = tab.data() + (size_t)p * stride;
         int32_t *hids = reinterpret_cast<int32_t *>(blk);
-        uint16_t *hvt = reinterpret_cast<uint16_t *>(blk + off_hvt);
         uint16_t *ctv = reinterpret_cast<uint16_t *>(blk + off_ctv);
-        nhv[p] = (int32_t)phalo[p].size();
-        for (size_t k = 0; k < phalo[p].size(); ++k) {
-            const long long h = phalo[p][k];
-            hids[k] = (int32_t)dev_cell(h);
-            for (int a = 0; a < 3; ++a) {
-                const int v = tvert(h, a);
-                hvt[k * 3 + a] = vstamp[v] == p ? (uint16_t)vloc[v] : (uint16_t)0xffff;
-            }
-            blk[off_hmask + k] = bmask(h);
-        }
-        for (long long c = c0; c < c1; ++c) {
+        nhv[2 * p] = (int32_t)phalo[p].size();
+        nhv[2 * p + 1] = (int32_t)pverts[p].size();
+        for (size_t k = 0; k < phalo[p].size(); ++k) hids[k] = (int32_t)dev_cell(phalo[p][k]);
+        for (long long c = c0; c < c1; ++c)
             for (int a = 0; a < 3; ++a) ctv[(c - c0) * 3 + a] = (uint16_t)vloc[tvert(c, a)];
-            blk[off_cmask + (c - c0)] = bmask(c);
-        }
+        memcpy(blk + off_vptr, pptr[p].data(), pptr[p].size() * sizeof(uint16_t));
+        memcpy(blk + off_vidx, pent[p].data(), pent[p].size() * sizeof(uint16_t));
     }
     cudaFree(ctx->d_lim_tab);
     cudaFree(ctx->d_lim_nhv);
@@ -1098,19 +1120,18 @@ static int limiter_setup(tb_ctx *ctx) {
     ctx->d_lim_nhv = nullptr;
     CK(cudaMalloc(&ctx->d_lim_tab, std::max<size_t>(tab.size(), 16)));
     CK(cudaMemcpy(ctx->d_lim_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&ctx->d_lim_nhv, sizeof(int32_t) * np));
-    CK(cudaMemcpy(ctx->d_lim_nhv, nhv.data(), sizeof(int32_t) * np, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&ctx->d_lim_nhv, sizeof(int32_t) * 2 * np));
+    CK(cudaMemcpy(ctx->d_lim_nhv, nhv.data(), sizeof(int32_t) * 2 * np, cudaMemcpyHostToDevice));
     ctx->lim.n_owned = no;
     ctx->lim.n_cells = nc;
     ctx->lim.tab = ctx->d_lim_tab;
     ctx->lim.stride = (long long)stride;
     ctx->lim.NHV = NHV;
     ctx->lim.NVT = NVT;
-    ctx->lim.off_hvt = (int)off_hvt;
     ctx->lim.off_ctv = (int)off_ctv;
-    ctx->lim.off_hmask = (int)off_hmask;
-    ctx->lim.off_cmask = (int)off_cmask;
-    ctx->lim.nhv = ctx->d_lim_nhv;
+    ctx->lim.off_vptr = (int)off_vptr;
+    ctx->lim.off_vidx = (int)off_vidx;
+    ctx->lim.counts = ctx->d_lim_nhv;
     ctx->lim_ready = true;
     return TB_OK;
 }

@@ -160,15 +160,16 @@ cudaError_t tb_launch_swe_integrals(const double *state, const double *area, con
 #define TB_NRED 296           // CTAs of the two-pass reductions (2 per SM)
 // limiter: one patch-staged kernel (tb_tracer.cu); per patch a static table at tab + patch*stride:
 //   int32  hids[NHV]      device cell ids of the vertex halo (cells outside the patch sharing a vertex with it)
-//   uint16 hvt[NHV][3]    patch-local topological vertex of each halo-cell node, 0xffff = not a patch vertex
 //   uint16 ctv[TB_P][3]   patch-local topological vertex of each own-cell node
-//   uint8  hmask[NHV], cmask[TB_P]   bit f = local facet f is an exterior facet
+//   uint16 vptr[NVT+1]    CSR over the patch vertices into vidx
+//   uint16 vidx[NE]       cells around the vertex as shared-memory slots (own cell t = t, halo cell h = TB_P + h), or
+//                         0x8000 | slot << 2 | f : exterior facet f of that cell touches the vertex
 struct TbLimiterData {
     long long n_owned, n_cells;
     const unsigned char *tab;
     long long stride;
     int NHV, NVT;                // padded sizes: vertex-halo cells / topological vertices per patch
-    int off_hvt, off_ctv, off_hmask, off_cmask;
-    const int *nhv;              // [n_patches] vertex-halo cells of each patch
+    int off_ctv, off_vptr, off_vidx, pad_;
+    const int *counts;           // [n_patches][2] (vertex-halo cells, vertices) of each patch
 };
 cudaError_t tb_launch_limiter(const TbLimiterData &d, const double *c_in, double *c_out, cudaStream_t s);

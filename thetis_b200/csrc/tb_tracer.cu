@@ -373,169 +373,114 @@ cudaError_t tb_launch_tracer_stage(const TbTracerParams &p, int n_patches, size_
 // ------------------------------------------------------------------ limiter
 // VertexBasedP1DGLimiter.apply (limiter.py:182-198 over firedrake's VertexBasedLimiter) as ONE patch-staged kernel.
 // One CTA = one patch of TB_P cells (the patches of the stage kernels).  Per patch a static table (built once,
-// limiter_setup in tb_api.cu) lists the cells outside the patch that share a vertex with it ("vertex halo") and, for
-// own and halo cells, the patch-local id of each of their vertices and a mask of their exterior facets.
-//   (i)   every thread loads its cell (24 B, read once) and forms the P0 projection = mean of the nodal values
-//         (limiter.py:90-97); the vertex-halo cells are gathered by the same threads (mostly L2 hits: they belong to
-//         patches running at the same time);
-//   (ii)  vertex bounds in shared memory: min / max over the means of ALL cells around each vertex, plus the mean of
-//         the two nodal values of every exterior facet touching it (limiter.py:109-145), by shared-memory atomic
-//         min / max on an order-preserving 64-bit encoding of the doubles -- min and max are exact and
-//         order-independent, so the result is deterministic and identical to the serial gather;
+// limiter_setup in tb_api.cu) lists the cells outside the patch that share a vertex with it ("vertex halo"), the
+// patch-local vertex of each own-cell node, and -- per patch vertex -- the cells around it (CSR over shared-memory
+// slots: own cells 0..TB_P-1, halo cells TB_P..) plus the exterior facets touching it.
+//   (i)   every thread loads its cell (24 B, read once) into shared memory together with its P0 projection = mean of
+//         the nodal values (limiter.py:90-97); the vertex-halo cells are gathered by the same threads (mostly L2
+//         hits: they belong to patches running at the same time);
+//   (ii)  one thread per patch vertex: min / max over the means of ALL cells around it, plus the mean of the two nodal
+//         values of every exterior facet touching it (limiter.py:109-145) -- a deterministic gather from shared
+//         memory, no atomics (a first version with shared-memory atomic min / max was bound by the atomic unit:
+//         ~2 400 atomics per patch);
 //   (iii) per-cell clamp (VertexBasedLimiter._limit_kernel) and ONE write of the limited cell (24 B).
 // Out of place (c_in -> c_out): neighbouring patches read this patch's ORIGINAL values as their vertex halo.
 // Replaces the two global passes (vertex CSR gather + per-cell clamp) that moved 94 B per triangle for 64 needed.
-__device__ __forceinline__ unsigned long long tb_enc_ordered(double x) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double tb_dec_ordered(unsigned long long u) {
-    const unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
-    return __longlong_as_double((long long)b);
-}
+#ifndef TB_LIM_MINB
+#define TB_LIM_MINB 10      // resident CTAs per SM the limiter kernel is compiled for (the kernel is latency bound)
+#endif
+#ifndef TB_LIM_PREFETCH
+#define TB_LIM_PREFETCH (148 * TB_LIM_MINB)      // patches ahead to warm in L2: one wave
+#endif
+#ifndef TB_LIM_SPEC
+#define TB_LIM_SPEC 2       // vertex-halo cells per thread gathered speculatively (covers NHV <= 2 TB_P)
+#endif
 
-// The 64-bit min / max of the ordered encodings is taken lexicographically with NATIVE 32-bit shared-memory atomics in
-// two passes (high words, then the low words of the contributions whose high word won): 64-bit atomicMin / atomicMax
-// on shared memory compile to compare-and-swap loops, which made the first version of this kernel instruction-bound.
-struct LimBounds {
-    unsigned *hmin, *lmin, *hmax, *lmax;
-    __device__ __forceinline__ void pass1(int v, unsigned long long e) const {
-        const unsigned hi = (unsigned)(e >> 32);
-        atomicMin(hmin + v, hi);
-        atomicMax(hmax + v, hi);
-    }
-    __device__ __forceinline__ void pass2(int v, unsigned long long e) const {
-        const unsigned hi = (unsigned)(e >> 32), lo = (unsigned)e;
-        if (hi == hmin[v]) atomicMin(lmin + v, lo);
-        if (hi == hmax[v]) atomicMax(lmax + v, lo);
-    }
-    __device__ __forceinline__ double qmin(int v) const {
-        return tb_dec_ordered(((unsigned long long)hmin[v] << 32) | lmin[v]);
-    }
-    __device__ __forceinline__ double qmax(int v) const {
-        return tb_dec_ordered(((unsigned long long)hmax[v] << 32) | lmax[v]);
-    }
-};
-
-__global__ void __launch_bounds__(TB_P) limiter_patch_kernel(TbLimiterData d, const double *__restrict__ c_in,
-                                                             double *__restrict__ c_out) {
+__global__ void __launch_bounds__(TB_P, TB_LIM_MINB) limiter_patch_kernel(TbLimiterData d, const double *__restrict__ c_in,
+                                                                          double *__restrict__ c_out) {
     extern __shared__ __align__(16) unsigned char lsm[];
-    LimBounds B;
-    B.hmin = reinterpret_cast<unsigned *>(lsm);
-    B.lmin = B.hmin + d.NVT;
-    B.hmax = B.lmin + d.NVT;
-    B.lmax = B.hmax + d.NVT;
-    unsigned long long *hmean = reinterpret_cast<unsigned long long *>(B.lmax + d.NVT);     // [NHV] encoded halo means
+    double *qs = reinterpret_cast<double *>(lsm);                   // [(TB_P + NHV)][3] nodal values, own + halo
+    double *ms = qs + (size_t)(TB_P + d.NHV) * 3;                   // [(TB_P + NHV)] cell means
+    double *qmin_s = ms + (TB_P + d.NHV);                           // [NVT]
+    double *qmax_s = qmin_s + d.NVT;
     const int tid = threadIdx.x;
     const long long patch = blockIdx.x;
     const long long cell = patch * TB_P + tid;
     const bool active = cell < d.n_owned;
     const unsigned char *blk = d.tab + patch * d.stride;
     const int *hids = reinterpret_cast<const int *>(blk);
-    const unsigned short *hvt = reinterpret_cast<const unsigned short *>(blk + d.off_hvt);
     const unsigned short *ctv = reinterpret_cast<const unsigned short *>(blk + d.off_ctv);
-    const unsigned char *hmask = blk + d.off_hmask;
-    const unsigned char *cmask = blk + d.off_cmask;
-    const int nhv = __ldg(d.nhv + patch);
-    // firedrake VertexBasedLimiter.compute_bounds initial values
-    const unsigned long long e0min = tb_enc_ordered(1.0e10), e0max = tb_enc_ordered(-1.0e10);
+    const unsigned short *vptr = reinterpret_cast<const unsigned short *>(blk + d.off_vptr);
+    const unsigned short *vidx = reinterpret_cast<const unsigned short *>(blk + d.off_vidx);
+    const int2 cnt = __ldg(reinterpret_cast<const int2 *>(d.counts) + patch);      // (vertex-halo cells, vertices)
+    const int nhv = cnt.x, nvt = cnt.y;
 
+    // warm L2 for the patch that will run on this SM slot one wave later (the kernel is bound by the latency of its
+    // dependent loads -- table -> ids -> gathered values -- not by bandwidth)
+    if (tid < 2) {
+        const long long pf = patch + (long long)TB_LIM_PREFETCH;
+        if (pf < (long long)gridDim.x) {
+            if (tid == 0) bulk_prefetch_l2(c_in + pf * TB_P * 3, TB_P * 3 * sizeof(double));
+            else bulk_prefetch_l2(d.tab + pf * d.stride, (uint32_t)d.stride);
+        }
+    }
+    // every independent global load first (one memory latency instead of a chain): the ids of the halo cells this
+    // thread will gather (rows are padded to NHV valid entries), its own cell and its table entries
+    int hid[TB_LIM_SPEC];
+#pragma unroll
+    for (int j = 0; j < TB_LIM_SPEC; ++j) {
+        const int h = j * TB_P + tid;
+        hid[j] = h < d.NHV ? __ldg(hids + h) : 0;
+    }
     double q[3] = {0, 0, 0};
     int lv[3] = {0, 0, 0};
-    int msk = 0;
     if (active) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             q[a] = __ldg(c_in + cell * 3 + a);
             lv[a] = ctv[tid * 3 + a];
         }
-        msk = cmask[tid];
     }
-    for (int v = tid; v < d.NVT; v += TB_P) {
-        B.hmin[v] = (unsigned)(e0min >> 32);
-        B.hmax[v] = (unsigned)(e0max >> 32);
-        B.lmin[v] = 0xffffffffu;
-        B.lmax[v] = 0u;
-    }
-    __syncthreads();
-    // ---- pass 1: high words
     const double qavg = (q[0] + q[1] + q[2]) / 3.0;        // P0 projection = mean of the nodal values (limiter.py:90-97)
-    const unsigned long long e = tb_enc_ordered(qavg);
-    if (active) {
+    qs[tid * 3] = q[0]; qs[tid * 3 + 1] = q[1]; qs[tid * 3 + 2] = q[2];
+    ms[tid] = qavg;
+    // ... then the gathers that depend on the ids
 #pragma unroll
-        for (int a = 0; a < 3; ++a) B.pass1(lv[a], e);
-        if (msk) {
-#pragma unroll
-            for (int f = 0; f < 3; ++f)
-                if (msk & (1 << f)) {
-                    const int p = (f + 1) % 3, r = (f + 2) % 3;
-                    const unsigned long long fe = tb_enc_ordered((q[p] + q[r]) / 2);      // limiter.py:123-137
-                    B.pass1(lv[p], fe);
-                    B.pass1(lv[r], fe);
-                }
+    for (int j = 0; j < TB_LIM_SPEC; ++j) {
+        const int h = j * TB_P + tid;
+        if (h < nhv) {
+            const double *r = c_in + (long long)hid[j] * 3;
+            const double h0 = __ldg(r), h1 = __ldg(r + 1), h2 = __ldg(r + 2);
+            qs[(TB_P + h) * 3] = h0; qs[(TB_P + h) * 3 + 1] = h1; qs[(TB_P + h) * 3 + 2] = h2;
+            ms[TB_P + h] = (h0 + h1 + h2) / 3.0;
         }
     }
-    for (int h = tid; h < nhv; h += TB_P) {
+    for (int h = TB_LIM_SPEC * TB_P + tid; h < nhv; h += TB_P) {        // very large vertex halos only
         const double *r = c_in + (long long)__ldg(hids + h) * 3;
         const double h0 = __ldg(r), h1 = __ldg(r + 1), h2 = __ldg(r + 2);
-        const unsigned long long he = tb_enc_ordered((h0 + h1 + h2) / 3.0);
-        hmean[h] = he;
-        const int hv[3] = {hvt[h * 3], hvt[h * 3 + 1], hvt[h * 3 + 2]};
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-            if (hv[a] != 0xffff) B.pass1(hv[a], he);
-        const int hm = hmask[h];
-        if (hm) {
-            const double hq[3] = {h0, h1, h2};
-#pragma unroll
-            for (int f = 0; f < 3; ++f)
-                if (hm & (1 << f)) {
-                    const int p = (f + 1) % 3, rr = (f + 2) % 3;
-                    const unsigned long long fe = tb_enc_ordered((hq[p] + hq[rr]) / 2);
-                    if (hv[p] != 0xffff) B.pass1(hv[p], fe);
-                    if (hv[rr] != 0xffff) B.pass1(hv[rr], fe);
-                }
-        }
+        qs[(TB_P + h) * 3] = h0; qs[(TB_P + h) * 3 + 1] = h1; qs[(TB_P + h) * 3 + 2] = h2;
+        ms[TB_P + h] = (h0 + h1 + h2) / 3.0;
     }
     __syncthreads();
-    // ---- pass 2: low words of the contributions whose high word won (the initial values take part too)
-    for (int v = tid; v < d.NVT; v += TB_P) {
-        if ((unsigned)(e0min >> 32) == B.hmin[v]) atomicMin(B.lmin + v, (unsigned)e0min);
-        if ((unsigned)(e0max >> 32) == B.hmax[v]) atomicMax(B.lmax + v, (unsigned)e0max);
-    }
-    if (active) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) B.pass2(lv[a], e);
-        if (msk) {
-#pragma unroll
-            for (int f = 0; f < 3; ++f)
-                if (msk & (1 << f)) {
-                    const int p = (f + 1) % 3, r = (f + 2) % 3;
-                    const unsigned long long fe = tb_enc_ordered((q[p] + q[r]) / 2);
-                    B.pass2(lv[p], fe);
-                    B.pass2(lv[r], fe);
-                }
+    // ---- vertex bounds: one thread per patch vertex, gather over the cells / exterior facets around it
+    for (int v = tid; v < nvt; v += TB_P) {
+        double qmax = -1.0e10, qmin = 1.0e10;   // firedrake VertexBasedLimiter.compute_bounds initial values
+        const int k1 = vptr[v + 1];
+        for (int k = vptr[v]; k < k1; ++k) {
+            const int ent = vidx[k];
+            double val;
+            if (ent & 0x8000) {
+                // exterior facet f of the cell in slot s touches this vertex: mean of its two nodal values (:123-137)
+                const int sl = (ent & 0x7fff) >> 2, f = ent & 3;
+                val = (qs[sl * 3 + (f + 1) % 3] + qs[sl * 3 + (f + 2) % 3]) / 2;
+            } else {
+                val = ms[ent];
+            }
+            qmax = fmax(qmax, val);
+            qmin = fmin(qmin, val);
         }
-    }
-    for (int h = tid; h < nhv; h += TB_P) {
-        const unsigned long long he = hmean[h];
-        const int hv[3] = {hvt[h * 3], hvt[h * 3 + 1], hvt[h * 3 + 2]};
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-            if (hv[a] != 0xffff) B.pass2(hv[a], he);
-        const int hm = hmask[h];
-        if (hm) {        // exterior facets of halo cells (rare): the nodal values are read again
-            const double *r = c_in + (long long)__ldg(hids + h) * 3;
-            const double hq[3] = {__ldg(r), __ldg(r + 1), __ldg(r + 2)};
-#pragma unroll
-            for (int f = 0; f < 3; ++f)
-                if (hm & (1 << f)) {
-                    const int p = (f + 1) % 3, rr = (f + 2) % 3;
-                    const unsigned long long fe = tb_enc_ordered((hq[p] + hq[rr]) / 2);
-                    if (hv[p] != 0xffff) B.pass2(hv[p], fe);
-                    if (hv[rr] != 0xffff) B.pass2(hv[rr], fe);
-                }
-        }
+        qmin_s[v] = qmin;
+        qmax_s[v] = qmax;
     }
     __syncthreads();
     if (!active) return;
@@ -544,15 +489,16 @@ __global__ void __launch_bounds__(TB_P) limiter_patch_kernel(TbLimiterData d, co
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         if (q[i] > qavg)
-            alpha = fmin(alpha, fmin(1.0, (B.qmax(lv[i]) - qavg) / (q[i] - qavg)));
+            alpha = fmin(alpha, fmin(1.0, (qmax_s[lv[i]] - qavg) / (q[i] - qavg)));
         else if (q[i] < qavg)
-            alpha = fmin(alpha, fmin(1.0, (qavg - B.qmin(lv[i])) / (qavg - q[i])));
+            alpha = fmin(alpha, fmin(1.0, (qavg - qmin_s[lv[i]]) / (qavg - q[i])));
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) c_out[cell * 3 + i] = qavg + alpha * (q[i] - qavg);
 }
 cudaError_t tb_launch_limiter(const TbLimiterData &d, const double *c_in, double *c_out, cudaStream_t s) {
     const long long np = (d.n_owned + TB_P - 1) / TB_P;
-    if (np > 0) limiter_patch_kernel<<<(unsigned)np, TB_P, (size_t)d.NVT * 16 + (size_t)d.NHV * 8, s>>>(d, c_in, c_out);
+    const size_t smem = ((size_t)(TB_P + d.NHV) * 4 + (size_t)d.NVT * 2) * sizeof(double);
+    if (np > 0) limiter_patch_kernel<<<(unsigned)np, TB_P, smem, s>>>(d, c_in, c_out);
     return cudaGetLastError();
 }
