@@ -250,6 +250,13 @@ int tb_halo_fused_setup(tb_ctx *ctx, const tb_halo_fused *h);
  * launches. */
 int tb_swe_stage_fused(tb_ctx *ctx, double a0, double a1, double b_dt, const double *u_in, const double *u0,
                        double *u_out, const uint64_t *push_dst, void *stream);
+/* The same for the tracer stage and the limiter (3 doubles per pushed cell): push_dst holds the peer addresses of the
+ * pushed cells inside the peers' copies of c_out.  SWE, tracer and limiter launches share ONE epoch sequence: every
+ * rank issues the same sequence of fused launches, and the boundary patches of launch k+1 wait for the peers' launch k
+ * (the tracer stage thereby also sees the frozen SWE ghosts of the last SWE stage). */
+int tb_tracer_stage_fused(tb_ctx *ctx, double a0, double a1, double b_dt, const double *c_in, const double *c0,
+                          double *c_out, const double *swe_state, const uint64_t *push_dst, void *stream);
+int tb_limiter_apply_to_fused(tb_ctx *ctx, const double *c_in, double *c_out, const uint64_t *push_dst, void *stream);
 /* Stream-ordered wait until the ghost records of the last fused launch have arrived from every peer: required in
  * front of any other kernel that reads them (the tracer stage reads the frozen SWE state of its halo cells). */
 int tb_halo_fused_wait(tb_ctx *ctx, void *stream);

@@ -74,6 +74,8 @@ SIGNATURES = {
     "tb_tracer_stage": (_I, [_P, _D, _D, _D, _P, _P, _P, _P, _P]),
     "tb_limiter_apply": (_I, [_P, _P, _P]),
     "tb_limiter_apply_to": (_I, [_P, _P, _P, _P]),
+    "tb_limiter_apply_to_fused": (_I, [_P, _P, _P, _P, _P]),
+    "tb_tracer_stage_fused": (_I, [_P, _D, _D, _D, _P, _P, _P, _P, _P, _P]),
     "tb_state_from_fields": (_I, [_P, _P, _P, _P, _P, _P]),
     "tb_state_to_fields": (_I, [_P, _P, _P, _P, _P, _P]),
     "tb_tracer_from_field": (_I, [_P, _P, _P, _P, _P]),

@@ -964,9 +964,9 @@ extern "C" int tb_swe_tendency(tb_ctx *ctx, const double *u, double *k_out, void
     return tb_swe_stage(ctx, 0.0, 0.0, 1.0, u, nullptr, k_out, stream);
 }
 
-extern "C" int tb_tracer_stage(tb_ctx *ctx, double a0, double a1, double b_dt, const double *c_in, const double *c0,
-                               double *c_out, const double *swe_state, void *stream) {
-    TbRange range("tb_tracer_stage");
+static int tracer_stage_impl(tb_ctx *ctx, double a0, double a1, double b_dt, const double *c_in, const double *c0,
+                             double *c_out, const double *swe_state, const unsigned long long *push_dst, void *stream) {
+    TbRange range(push_dst ? "tb_tracer_stage_fused" : "tb_tracer_stage");
     if (!ctx || !c_in || !c_out || !swe_state) return fail(ctx, TB_ERR_ARG, "null state pointer");
     if (c_in == c_out) return fail(ctx, TB_ERR_ARG, "c_out must not alias c_in");
     if (a0 != 0.0 && !c0) return fail(ctx, TB_ERR_ARG, "c0 required when a0 != 0");
@@ -1001,11 +1001,33 @@ extern "C" int tb_tracer_stage(tb_ctx *ctx, double a0, double a1, double b_dt, c
     long long first, count;
     patch_range(ctx, first, count);
     p.patch_first = (int)first;
+    if (push_dst) {
+        // one launch over all patches, partition-boundary patches first; they push their values to the peers
+        if (!ctx->fused_ready) return fail(ctx, TB_ERR_STATE, "tb_halo_fused_setup has not been called");
+        p.patch_list = ctx->d_fused_order;
+        p.patch_first = 0;
+        count = ctx->n_patches;
+        p.halo = ctx->d_fused;
+        p.push_dst = push_dst;
+        p.n_bpatch = ctx->fused_n_bpatch;
+    }
     const size_t smem = tb_tracer_smem_bytes(ctx->pl);
     if (smem > 200 * 1024) return fail(ctx, TB_ERR_UNSUPPORTED, "patch halo too large for shared memory");
     CK(tb_launch_tracer_stage(p, (int)count, smem, (cudaStream_t)stream));
     ctx->launches += count > 0 ? 1 : 0;
     return TB_OK;
+}
+
+extern "C" int tb_tracer_stage(tb_ctx *ctx, double a0, double a1, double b_dt, const double *c_in, const double *c0,
+                               double *c_out, const double *swe_state, void *stream) {
+    return tracer_stage_impl(ctx, a0, a1, b_dt, c_in, c0, c_out, swe_state, nullptr, stream);
+}
+
+extern "C" int tb_tracer_stage_fused(tb_ctx *ctx, double a0, double a1, double b_dt, const double *c_in, const double *c0,
+                                     double *c_out, const double *swe_state, const uint64_t *push_dst, void *stream) {
+    if (!push_dst) return fail(ctx, TB_ERR_ARG, "null push table");
+    return tracer_stage_impl(ctx, a0, a1, b_dt, c_in, c0, c_out, swe_state,
+                             reinterpret_cast<const unsigned long long *>(push_dst), stream);
 }
 
 static int limiter_setup(tb_ctx *ctx) {
@@ -1136,17 +1158,35 @@ static int limiter_setup(tb_ctx *ctx) {
     return TB_OK;
 }
 
-extern "C" int tb_limiter_apply_to(tb_ctx *ctx, const double *c_in, double *c_out, void *stream) {
-    TbRange range("tb_limiter_apply");
+static int limiter_impl(tb_ctx *ctx, const double *c_in, double *c_out, const unsigned long long *push_dst, void *stream) {
+    TbRange range(push_dst ? "tb_limiter_apply_fused" : "tb_limiter_apply");
     if (!ctx || !c_in || !c_out) return fail(ctx, TB_ERR_ARG, "null pointer");
     if (c_in == c_out) return fail(ctx, TB_ERR_ARG, "c_out must not alias c_in (use tb_limiter_apply)");
     if (!ctx->lim_ready) {
         int rc = limiter_setup(ctx);
         if (rc != TB_OK) return rc;
     }
-    CK(tb_launch_limiter(ctx->lim, c_in, c_out, (cudaStream_t)stream));
+    TbLimiterData d = ctx->lim;
+    if (push_dst) {
+        if (!ctx->fused_ready) return fail(ctx, TB_ERR_STATE, "tb_halo_fused_setup has not been called");
+        d.patch_list = ctx->d_fused_order;
+        d.halo = ctx->d_fused;
+        d.push_dst = push_dst;
+        d.n_bpatch = ctx->fused_n_bpatch;
+    }
+    CK(tb_launch_limiter(d, c_in, c_out, (cudaStream_t)stream));
     ctx->launches += 1;
     return TB_OK;
+}
+
+extern "C" int tb_limiter_apply_to(tb_ctx *ctx, const double *c_in, double *c_out, void *stream) {
+    return limiter_impl(ctx, c_in, c_out, nullptr, stream);
+}
+
+extern "C" int tb_limiter_apply_to_fused(tb_ctx *ctx, const double *c_in, double *c_out, const uint64_t *push_dst,
+                                         void *stream) {
+    if (!push_dst) return fail(ctx, TB_ERR_ARG, "null push table");
+    return limiter_impl(ctx, c_in, c_out, reinterpret_cast<const unsigned long long *>(push_dst), stream);
 }
 
 extern "C" int tb_limiter_apply(tb_ctx *ctx, double *c, void *stream) {

@@ -116,3 +116,51 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+
+
+// ------------------------------------------------------------------ fused halo exchange (TbHaloFused, tb_internal.h)
+// Shared by the SWE stage, tracer stage and limiter kernels: every rank issues the same sequence of fused launches and
+// one epoch counter orders them all.
+#ifdef TB_HAVE_HALO_FUSED
+// Partition-boundary CTA, before it reads ghost records: wait until every peer this rank receives from has published
+// the ghosts written by ITS previous fused launch.  Returns the epoch of the running launch.
+__device__ __forceinline__ unsigned long long tb_fused_wait(const TbHaloFused *hf) {
+    const unsigned long long epoch = *hf->epoch;
+    const long long t0 = clock64();
+    for (int q = 0; q < hf->n_recv; ++q) {
+        const unsigned long long *f = hf->flags + hf->recv_peer[q];
+        while (ld_acquire_sys(f) < epoch) {
+            if (clock64() - t0 > 6000000000ll) {      // ~3 s: a peer died; do not hang the GPU
+                *hf->error = 1;
+                break;
+            }
+        }
+    }
+    return epoch;
+}
+// Partition-boundary CTA, after its results are staged in shared memory (O: [TB_P][REC] doubles): store the records
+// the peers need straight into their ghost blocks (consecutive threads store consecutive doubles of a record) and let
+// the last boundary CTA of the launch publish the new epoch to the receiving peers.  All threads must call it.
+template <int REC>
+__device__ __forceinline__ void tb_fused_push(const TbHaloFused *hf, const unsigned long long *push_dst, const double *O,
+                                              int n_bpatch, unsigned long long epoch, int tid) {
+    const int e0 = __ldg(hf->push_ptr + blockIdx.x), n = (__ldg(hf->push_ptr + blockIdx.x + 1) - e0) * REC;
+    for (int i = tid; i < n; i += TB_P) {
+        const int ent = i / REC, k = i - ent * REC;
+        double *dst = reinterpret_cast<double *>(__ldg(push_dst + e0 + ent));
+        dst[k] = O[__ldg(hf->push_cell + e0 + ent) * REC + k];
+    }
+    __threadfence_system();          // this thread's peer stores are ordered before the signal below
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int done = atomicAdd(hf->done_count, 1u);
+        if (done == (unsigned int)n_bpatch - 1u) {
+            // every boundary CTA of this launch has pushed: publish the new epoch to the receiving peers
+            *hf->done_count = 0u;
+            __threadfence_system();
+            for (int q = 0; q < hf->n_send; ++q) st_release_sys(hf->remote_flag[q], epoch + 1ull);
+            *hf->epoch = epoch + 1ull;
+        }
+    }
+}
+#endif

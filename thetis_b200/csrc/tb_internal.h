@@ -67,6 +67,7 @@ struct TbPatchLayout {
 // peers need straight into the peers' ghost blocks (NVLink peer stores) and (4) the last of them to finish publishes
 // epoch + 1 in every receiving peer's flag array.  Device-resident so that a captured CUDA graph replays correctly.
 #define TB_MAX_PEERS 16
+#define TB_HAVE_HALO_FUSED 1
 struct TbHaloFused {
     unsigned long long *epoch;         // [1] fused stage launches completed by this rank
     unsigned int *done_count;          // [1] boundary CTAs of the running launch that finished their push
@@ -118,6 +119,10 @@ struct TbTracerParams {
     double sipg;                  // sipg_factor_tracer
     int conservative, nquad;
     int force_generic, pad1;
+    const int *patch_list;        // optional launch order (fused halo exchange: partition-boundary patches first)
+    const TbHaloFused *halo;      // optional (device): CTAs [0, n_bpatch) wait for / push ghost records
+    const unsigned long long *push_dst;   // [n_entries] peer addresses of the pushed records for THIS output buffer
+    int n_bpatch, pad2;
     TbBcTable bc;
 };
 
@@ -171,5 +176,9 @@ struct TbLimiterData {
     int NHV, NVT;                // padded sizes: vertex-halo cells / topological vertices per patch
     int off_ctv, off_vptr, off_vidx, pad_;
     const int *counts;           // [n_patches][2] (vertex-halo cells, vertices) of each patch
+    const int *patch_list;       // optional launch order (fused halo exchange: partition-boundary patches first)
+    const TbHaloFused *halo;     // optional (device): CTAs [0, n_bpatch) wait for / push ghost records
+    const unsigned long long *push_dst;
+    int n_bpatch, pad2_;
 };
 cudaError_t tb_launch_limiter(const TbLimiterData &d, const double *c_in, double *c_out, cudaStream_t s);

@@ -214,21 +214,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
     // stage launch; wait until every peer has published them (TbHaloFused).  The boundary patches are the first CTAs
     // of the launch and their peers pushed early in THEIR previous launch, so the wait is normally already satisfied.
     const bool bpatch = prm.halo != nullptr && (int)blockIdx.x < prm.n_bpatch;
-    unsigned long long epoch = 0;
-    if (bpatch) {
-        const TbHaloFused *hf = prm.halo;
-        epoch = *hf->epoch;
-        const long long t0 = clock64();
-        for (int q = 0; q < hf->n_recv; ++q) {
-            const unsigned long long *f = hf->flags + hf->recv_peer[q];
-            while (ld_acquire_sys(f) < epoch) {
-                if (clock64() - t0 > 6000000000ll) {      // ~3 s: a peer died; do not hang the GPU
-                    *hf->error = 1;
-                    break;
-                }
-            }
-        }
-    }
+    const unsigned long long epoch = bpatch ? tb_fused_wait(prm.halo) : 0ull;
 
     // Halo ids of this patch: one coalesced load per thread (the row was prefetched to L2 one wave earlier), staged in
     // shared memory so that the gather below indexes them with cheap 32-bit shared loads instead of one global load
@@ -914,29 +900,8 @@ TB_UNROLL(TB_GP_UNROLL)
         for (int w = 1; w < TB_P / 32; ++w) r += red[w * 4 + k];
         prm.partials[(long long)patch * 4 + k] = r;
     }
-    if (bpatch) {
-        // fused halo push: the records the peers need go from shared memory straight into their ghost blocks
-        // (consecutive threads store consecutive doubles of a record: 72-byte runs over NVLink)
-        const TbHaloFused *hf = prm.halo;
-        const int e0 = __ldg(hf->push_ptr + blockIdx.x), n9 = (__ldg(hf->push_ptr + blockIdx.x + 1) - e0) * 9;
-        for (int i = tid; i < n9; i += TB_P) {
-            const int ent = i / 9, k = i - ent * 9;
-            double *dst = reinterpret_cast<double *>(__ldg(prm.push_dst + e0 + ent));
-            dst[k] = O[__ldg(hf->push_cell + e0 + ent) * 9 + k];
-        }
-        __threadfence_system();          // this thread's peer stores are ordered before the signal below
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int done = atomicAdd(hf->done_count, 1u);
-            if (done == (unsigned int)prm.n_bpatch - 1u) {
-                // every boundary CTA of this launch has pushed: publish the new epoch to the receiving peers
-                *hf->done_count = 0u;
-                __threadfence_system();
-                for (int q = 0; q < hf->n_send; ++q) st_release_sys(hf->remote_flag[q], epoch + 1ull);
-                *hf->epoch = epoch + 1ull;
-            }
-        }
-    }
+    // fused halo push: the records the peers need go from shared memory straight into their ghost blocks
+    if (bpatch) tb_fused_push<9>(prm.halo, prm.push_dst, O, prm.n_bpatch, epoch, tid);
 }
 
 // shared-memory layout of the stage kernel: barrier | S (own + halo records) | O | static block | reduction scratch |

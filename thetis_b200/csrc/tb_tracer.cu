@@ -34,9 +34,13 @@ __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __g
     unsigned char *blk = reinterpret_cast<unsigned char *>(O + TB_P * 3);
 
     const int tid = threadIdx.x;
-    const int patch = prm.patch_first + blockIdx.x;
+    const int patch = prm.patch_list ? __ldg(prm.patch_list + blockIdx.x) : prm.patch_first + (int)blockIdx.x;
     const long long cell0 = (long long)patch * TB_P;
     const int NV = prm.pl.NV;
+    // distributed run, partition-boundary patch: its ghost records (tracer AND frozen SWE state) were written by the
+    // peers' previous fused launch (tb_fused_wait, tb_device.cuh)
+    const bool bpatch = prm.halo != nullptr && (int)blockIdx.x < prm.n_bpatch;
+    const unsigned long long epoch = bpatch ? tb_fused_wait(prm.halo) : 0ull;
 
     // speculative, mutually independent loads first: the halo count and the ids this thread will need (rows of
     // halo_ids are padded to NH valid entries).  Element i of the halo is double (i % 9) of halo cell (i / 9):
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __g
         // warm L2 for the patch that runs on this SM slot one wave later
         const int pb = (int)blockIdx.x + 148 * TB_T_MINB;
         if (pb < (int)gridDim.x) {
-            const long long pf = prm.patch_first + pb;
+            const long long pf = prm.patch_list ? __ldg(prm.patch_list + pb) : prm.patch_first + pb;
             bulk_prefetch_l2(prm.swe + pf * TB_P * 9, TB_P * 9 * sizeof(double));
             bulk_prefetch_l2(prm.c_in + pf * TB_P * 3, TB_P * 3 * sizeof(double));
             bulk_prefetch_l2(prm.pl.sblk + pf * prm.pl.stride, (uint32_t)prm.pl.stride);
@@ -350,6 +354,8 @@ __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __g
         bulk_s2g(prm.c_out + cell0 * 3, O, TB_P * 3 * sizeof(double));
         bulk_commit_wait_read();
     }
+    // fused halo push of the new tracer values (3 doubles per cell) into the peers' ghost blocks
+    if (bpatch) tb_fused_push<3>(prm.halo, prm.push_dst, O, prm.n_bpatch, epoch, tid);
 }
 
 size_t tb_tracer_smem_bytes(const TbPatchLayout &pl) {
@@ -404,9 +410,12 @@ __global__ void __launch_bounds__(TB_P, TB_LIM_MINB) limiter_patch_kernel(TbLimi
     double *qmin_s = ms + (TB_P + d.NHV);                           // [NVT]
     double *qmax_s = qmin_s + d.NVT;
     const int tid = threadIdx.x;
-    const long long patch = blockIdx.x;
+    const long long patch = d.patch_list ? __ldg(d.patch_list + blockIdx.x) : (long long)blockIdx.x;
     const long long cell = patch * TB_P + tid;
     const bool active = cell < d.n_owned;
+    // distributed run, partition-boundary patch: its vertex-halo ghosts were written by the peers' previous fused launch
+    const bool bpatch = d.halo != nullptr && (int)blockIdx.x < d.n_bpatch;
+    const unsigned long long epoch = bpatch ? tb_fused_wait(d.halo) : 0ull;
     const unsigned char *blk = d.tab + patch * d.stride;
     const int *hids = reinterpret_cast<const int *>(blk);
     const unsigned short *ctv = reinterpret_cast<const unsigned short *>(blk + d.off_ctv);
@@ -418,8 +427,9 @@ __global__ void __launch_bounds__(TB_P, TB_LIM_MINB) limiter_patch_kernel(TbLimi
     // warm L2 for the patch that will run on this SM slot one wave later (the kernel is bound by the latency of its
     // dependent loads -- table -> ids -> gathered values -- not by bandwidth)
     if (tid < 2) {
-        const long long pf = patch + (long long)TB_LIM_PREFETCH;
-        if (pf < (long long)gridDim.x) {
+        const long long pb = (long long)blockIdx.x + (long long)TB_LIM_PREFETCH;
+        if (pb < (long long)gridDim.x) {
+            const long long pf = d.patch_list ? __ldg(d.patch_list + pb) : pb;
             if (tid == 0) bulk_prefetch_l2(c_in + pf * TB_P * 3, TB_P * 3 * sizeof(double));
             else bulk_prefetch_l2(d.tab + pf * d.stride, (uint32_t)d.stride);
         }
@@ -483,18 +493,30 @@ __global__ void __launch_bounds__(TB_P, TB_LIM_MINB) limiter_patch_kernel(TbLimi
         qmax_s[v] = qmax;
     }
     __syncthreads();
-    if (!active) return;
     // ---- per-cell clamp (VertexBasedLimiter._limit_kernel) and ONE write of the limited cell
     double alpha = 1.0;
+    if (active) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        if (q[i] > qavg)
-            alpha = fmin(alpha, fmin(1.0, (qmax_s[lv[i]] - qavg) / (q[i] - qavg)));
-        else if (q[i] < qavg)
-            alpha = fmin(alpha, fmin(1.0, (qavg - qmin_s[lv[i]]) / (qavg - q[i])));
+        for (int i = 0; i < 3; ++i) {
+            if (q[i] > qavg)
+                alpha = fmin(alpha, fmin(1.0, (qmax_s[lv[i]] - qavg) / (q[i] - qavg)));
+            else if (q[i] < qavg)
+                alpha = fmin(alpha, fmin(1.0, (qavg - qmin_s[lv[i]]) / (qavg - q[i])));
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            q[i] = qavg + alpha * (q[i] - qavg);
+            c_out[cell * 3 + i] = q[i];
+        }
     }
+    if (bpatch) {
+        // fused halo push of the limited values: staged over this patch's own slots of qs (every thread is past
+        // the bounds phase: the barrier above)
 #pragma unroll
-    for (int i = 0; i < 3; ++i) c_out[cell * 3 + i] = qavg + alpha * (q[i] - qavg);
+        for (int i = 0; i < 3; ++i) qs[tid * 3 + i] = q[i];
+        __syncthreads();
+        tb_fused_push<3>(d.halo, d.push_dst, qs, d.n_bpatch, epoch, tid);
+    }
 }
 cudaError_t tb_launch_limiter(const TbLimiterData &d, const double *c_in, double *c_out, cudaStream_t s) {
     const long long np = (d.n_owned + TB_P - 1) / TB_P;

@@ -212,6 +212,13 @@ class Engine:
         self._ck(self.lib.tb_tracer_stage(self.ctx, a0, a1, b_dt, _ptr(c_in), _ptr(c0), _ptr(c_out),
                                           _ptr(swe_state), self.stream))
 
+    def tracer_stage_fused(self, a0, a1, b_dt, c_in, c0, c_out, swe_state, push_dst):
+        self._ck(self.lib.tb_tracer_stage_fused(self.ctx, a0, a1, b_dt, _ptr(c_in), _ptr(c0), _ptr(c_out),
+                                                _ptr(swe_state), _ptr(push_dst), self.stream))
+
+    def limiter_apply_to_fused(self, c_in, c_out, push_dst):
+        self._ck(self.lib.tb_limiter_apply_to_fused(self.ctx, _ptr(c_in), _ptr(c_out), _ptr(push_dst), self.stream))
+
     def limiter_apply(self, c):
         self._ck(self.lib.tb_limiter_apply(self.ctx, _ptr(c), self.stream))
 

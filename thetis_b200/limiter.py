@@ -49,10 +49,11 @@ class VertexBasedP1DGLimiter:
             # out of place into the integrator's scratch buffer (neighbouring patches read each other's ORIGINAL
             # values), then the two buffers swap roles: no copy back
             src, dst = st.buf[0], st.buf[1]
-            eng.limiter_apply_to(src, dst)
-            st.buf[0], st.buf[1] = dst, src
             if self.halo is not None:
-                self.halo.exchange(st.device_state())      # limited ghost values for the next step
+                self.halo.limiter_apply_to(src, dst)       # + limited ghost values for the next step
+            else:
+                eng.limiter_apply_to(src, dst)
+            st.buf[0], st.buf[1] = dst, src
             st.mark_device_modified()
             if st.sync_policy == "every_step":
                 st.sync_to_host()

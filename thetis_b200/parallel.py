@@ -286,8 +286,9 @@ class HaloPlan:
             e += n
         grp = dict(L=L, tensor=t, handle=hdl,
                    dst_ptrs=[torch.as_tensor(dst[b].view(np.int64)).to(eng.device) for b in range(nbuf)])
-        if self.fused and rec == 9:
-            # the same addresses grouped by patch, for the fused launch's epilogue push
+        if self.fused:
+            # the same addresses grouped by patch, for the fused launches' epilogue push (SWE: 9 doubles per cell,
+            # tracer stage / limiter: 3)
             grp["push_dst"] = [torch.as_tensor(dst[b][:self.n_send][self._push_perm].view(np.int64).copy()).to(eng.device)
                                if self.n_send else torch.zeros(1, dtype=torch.int64, device=eng.device)
                                for b in range(nbuf)]
@@ -345,6 +346,27 @@ class HaloPlan:
         eng.swe_stage(a0, a1, bdt, src, u0, dst)                 # interior patches
         eng.set_patch_list(None)
         main.wait_event(self._ev_x)                              # boundary patches + ghosts of dst are complete
+
+    def tracer_stage(self, a0, a1, bdt, src, u0, dst, swe_state):
+        """Tracer stage + halo exchange of its output.  Fused: one launch (the SWE, tracer and limiter launches share
+        one epoch sequence, so its boundary patches also see the SWE ghosts of the last SWE stage)."""
+        eng = self.engine
+        if self.fused:
+            rec, gid, b = self._buf_info[dst.data_ptr()]
+            eng.tracer_stage_fused(a0, a1, bdt, src, u0, dst, swe_state, self._groups[gid]["push_dst"][b])
+            return
+        eng.tracer_stage(a0, a1, bdt, src, u0, dst, swe_state)
+        self.exchange(dst)
+
+    def limiter_apply_to(self, src, dst):
+        """Limiter (out of place) + halo exchange of the limited values."""
+        eng = self.engine
+        if self.fused:
+            rec, gid, b = self._buf_info[dst.data_ptr()]
+            eng.limiter_apply_to_fused(src, dst, self._groups[gid]["push_dst"][b])
+            return
+        eng.limiter_apply_to(src, dst)
+        self.exchange(dst)
 
     def wait_ghosts(self):
         """Stream-ordered: the ghost records written by the peers' last fused stage launch have arrived."""

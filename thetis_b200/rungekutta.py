@@ -662,8 +662,9 @@ class ERKGenericShuOsher:
         if sw is not None and uv_f is not None and any(uv_f is s for s in sw.solution.subfunctions):
             if not sw._host_stale and sw._host_changed():
                 sw.upload()
-            if sw.halo is not None:
-                sw.halo.wait_ghosts()         # the tracer kernel reads the SWE records of its halo cells
+            if sw.halo is not None and not (self.halo is not None and self.halo.fused):
+                sw.halo.wait_ghosts()         # the tracer kernel reads the SWE records of its halo cells (a fused
+                                              # tracer launch waits for them itself: one epoch sequence)
             return sw.device_state()
         # tracer-only run: velocity / elevation come from host Functions
         if uv_f is None:
@@ -726,10 +727,10 @@ class ERKGenericShuOsher:
             if fused:
                 eng.stage_integrals(False)
                 eng.stage_integrals_finish(self.fused_norms)          # rank-local; callers all-reduce on a distributed mesh
+        elif self.halo is not None:
+            self.halo.tracer_stage(a0, a1, bdt, src, u0, dst, self._swe_state_for_tracer())
         else:
             eng.tracer_stage(a0, a1, bdt, src, u0, dst, self._swe_state_for_tracer())
-            if self.halo is not None:
-                self.halo.exchange(dst)
         self._mid_step = not last
         self._host_stale = True
         if last:
