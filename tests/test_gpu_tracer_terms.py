@@ -31,7 +31,8 @@ def _run(mesh, bath_v, swe_opts, tr_opts, tr_fields_v, bnd, tol=1e-12, seed=0, c
     from thetis_b200.engine import Engine
     uv, eta, c = _fields(mesh, seed)
     cells = mesh.cells
-    to_nodal = lambda a: a[cells] if (isinstance(a, np.ndarray) and a.shape[0] == mesh.n_vertices) else a
+    is_dg = lambda a: isinstance(a, np.ndarray) and a.ndim == 2 and a.shape == (mesh.n_cells, 3)
+    to_nodal = lambda a: a[cells] if (isinstance(a, np.ndarray) and not is_dg(a) and a.shape[0] == mesh.n_vertices) else a
     swe = O.SWEOracle(mesh, to_nodal(bath_v), options=swe_opts)
     of = {k: to_nodal(v) for k, v in tr_fields_v.items()}
     of["tracer_advective_velocity_factor"] = corr
@@ -179,3 +180,14 @@ def test_lincomb_and_integrals():
     Hq = 0.5 * (hq + np.sqrt(hq ** 2 + 0.49))
     mass_wd = (area[:, None] * w[None] * Hq * np.einsum("qa,ca->cq", lam, c)).sum()
     assert abs(t4[1].item() - mass_wd) / mass_wd < 1e-13
+
+
+@pytest.mark.parametrize("cons", [False, True])
+def test_discontinuous_p1dg_tracer_source(cons):
+    """`source` of the tracer equation given as a genuinely discontinuous P1DG Function (the usual space of tracer
+    sources, Q_2d): stored per cell node (tb_set_field_cell); non-conservative and depth-integrated forms"""
+    mesh = sfc_renumber(delaunay_mesh(800, 900.0, 700.0, seed=6))
+    rng = np.random.default_rng(8)
+    src = 1e-3 * (1.0 + rng.standard_normal((mesh.n_cells, 3)))
+    b = 20.0 + 4.0 * np.sin(mesh.coords[:, 0] / 150.0)
+    _run(mesh, b, {}, dict(use_conservative_form=cons), {"source": src}, {}, tol=1e-11)

@@ -24,6 +24,11 @@ cudaError_t tb_set_quadrature_tracer(int n, const double *lam, const double *w) 
 // TSPEC 1: plain non-conservative advection (no source, diffusion or Lax-Friedrichs) -- BASELINE config 4;
 // TSPEC 0: every optional term behind a runtime flag.  Same staging as the SWE stage kernel: TMA bulk copies of the
 // patch's SWE records, tracer records, u0 and static block; halo records gathered with cp.async by all threads.
+// shared-memory layout: barrier | S | C | O | static block | halo ids
+__host__ __device__ inline size_t tb_tracer_ids_offset(const TbPatchLayout &pl) {
+    return 16 + (size_t)(TB_P + pl.NH) * 96 + (size_t)TB_P * 24 + (size_t)pl.stride;
+}
+
 template <int TSPEC>
 __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __grid_constant__ TbTracerParams prm) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -42,17 +47,12 @@ __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __g
     const bool bpatch = prm.halo != nullptr && (int)blockIdx.x < prm.n_bpatch;
     const unsigned long long epoch = bpatch ? tb_fused_wait(prm.halo) : 0ull;
 
-    // speculative, mutually independent loads first: the halo count and the ids this thread will need (rows of
-    // halo_ids are padded to NH valid entries).  Element i of the halo is double (i % 9) of halo cell (i / 9):
-    // the 6 velocity values of its SWE record, then its 3 tracer values (the neighbour's elevation is never used).
+    // halo ids of this patch: one coalesced load per thread, staged in shared memory for the gather below (as in the
+    // SWE stage kernel).  Element i of the halo is double (i % 9) of halo cell (i / 9): the 6 velocity values of its
+    // SWE record, then its 3 tracer values (the neighbour's elevation is never used).
     const int *hid = prm.pl.halo_ids + (long long)patch * prm.pl.NH;
-    const int NH9 = prm.pl.NH * 9;
-    int hcell[TB_T_HALO_SPEC];
-#pragma unroll
-    for (int j = 0; j < TB_T_HALO_SPEC; ++j) {
-        const int i = j * TB_P + tid;
-        hcell[j] = (i < NH9) ? __ldg(hid + i / 9) : 0;
-    }
+    int *ids_s = reinterpret_cast<int *>(smem + tb_tracer_ids_offset(prm.pl));
+    const int myid = tid < prm.pl.NH ? __ldg(hid + tid) : 0;
     const int nh9 = __ldg(prm.pl.halo_cnt + patch) * 9;
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -75,21 +75,25 @@ __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __g
             if (prm.c0) bulk_prefetch_l2(prm.c0 + pf * TB_P * 3, TB_P * 3 * sizeof(double));
         }
     }
+    if (tid < prm.pl.NH) ids_s[tid] = myid;
+    for (int h = TB_P + tid; h < prm.pl.NH; h += TB_P) ids_s[h] = __ldg(hid + h);      // very large halos only
+    __syncthreads();          // ids staged; mbarrier initialised before anybody waits on it
     {
-        auto halo_copy = [&](int i, long long gc) {
-            const int h = i / 9, k = i - h * 9;
+        auto halo_copy = [&](unsigned i) {
+            const unsigned h = i / 9u, k = i - h * 9u;
+            const long long gc = ids_s[h];
             if (k < 6) cp_async8(S + (TB_P + h) * 9 + k, prm.swe + gc * 9 + k);
             else cp_async8(C + (TB_P + h) * 3 + (k - 6), prm.c_in + gc * 3 + (k - 6));
         };
 #pragma unroll
         for (int j = 0; j < TB_T_HALO_SPEC; ++j) {
             const int i = j * TB_P + tid;
-            if (i < nh9) halo_copy(i, hcell[j]);
+            if (i < nh9) halo_copy((unsigned)i);
         }
-        for (int i = TB_T_HALO_SPEC * TB_P + tid; i < nh9; i += TB_P) halo_copy(i, __ldg(hid + i / 9));   // large halos
+        for (int i = TB_T_HALO_SPEC * TB_P + tid; i < nh9; i += TB_P) halo_copy((unsigned)i);   // large halos
         cp_async_wait_all();
     }
-    __syncthreads();          // mbarrier initialised before anybody waits on it; halo copies landed
+    __syncthreads();          // every thread's halo copies have landed
     mbar_wait(bar, 0);
 
     const bool active = (cell0 + tid) < prm.n_owned;
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(TB_P, TB_T_MINB) tracer_stage_kernel(const __g
 }
 
 size_t tb_tracer_smem_bytes(const TbPatchLayout &pl) {
-    return 16 + (size_t)(TB_P + pl.NH) * 96 + (size_t)TB_P * 24 + (size_t)pl.stride;
+    return tb_tracer_ids_offset(pl) + (((size_t)pl.NH * sizeof(int) + 15) & ~(size_t)15);
 }
 
 cudaError_t tb_tracer_kernels_init() {
