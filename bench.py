@@ -324,11 +324,23 @@ def main():
         # load phase so that the clock samples see the same kernel mix even when K is small
         t_load0 = time.time()
         burn_until = time.time() + 1.5
-        while time.time() < burn_until:
+        while True:
             for _ in range(10):
                 run.step_resident()
             torch.cuda.synchronize()
+            # EVERY rank must issue the same number of steps (the fused halo exchange counts launches; a rank that
+            # leaves this time-based loop one iteration earlier than its peers would starve them): rank 0 decides
+            go = torch.tensor([1 if time.time() < burn_until else 0], dtype=torch.int32, device="cuda")
+            if world > 1:
+                dist.broadcast(go, src=0)
+            if int(go.item()) == 0:
+                break
         barrier()
+        if world > 1 and getattr(run, "plan", None) is not None and run.plan.fused:
+            ep, err = run.eng.halo_fused_status()
+            if err:
+                raise RuntimeError("a halo flag wait timed out during warm-up: the ranks did not issue the same "
+                                   "sequence of fused launches")
         l0 = run.launches()
         # L2 policy (timing rules): when the per-GPU working set (3 rotating state arrays + the static patch blocks)
         # is not clearly larger than L2 (N = 8: 3 x 36 MB), L2 is flushed between timed steps by writing a buffer

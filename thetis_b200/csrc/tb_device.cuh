@@ -126,6 +126,9 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 // the ghosts written by ITS previous fused launch.  Returns the epoch of the running launch.
 __device__ __forceinline__ unsigned long long tb_fused_wait(const TbHaloFused *hf) {
     const unsigned long long epoch = *hf->epoch;
+    // fail fast: once a wait has timed out (a peer stopped, or the ranks did not issue the same sequence of fused
+    // launches) no later launch spins again -- the host reads the flag (tb_halo_fused_status) and aborts the run
+    if (*reinterpret_cast<volatile int *>(hf->error)) return epoch;
     const long long t0 = clock64();
     for (int q = 0; q < hf->n_recv; ++q) {
         const unsigned long long *f = hf->flags + hf->recv_peer[q];

@@ -1081,7 +1081,7 @@ cudaError_t tb_launch_scatter_cells(const double *buf, const int32_t *idx, long 
 __global__ void halo_fused_wait_kernel(const TbHaloFused *hf) {
     const unsigned long long epoch = *hf->epoch;
     const int q = threadIdx.x;
-    if (q < hf->n_recv) {
+    if (q < hf->n_recv && !*reinterpret_cast<volatile int *>(hf->error)) {
         const unsigned long long *f = hf->flags + hf->recv_peer[q];
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < epoch) {
