@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: boundary launch + push kernel + barrier instead of "
                     "the fused compute + halo-push launch")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the resident step in a CUDA graph")
+    ap.add_argument("--e2e-graph", default="step", choices=["step", "stage"], help="e2e path: one CUDA graph per step "
+                    "(boundary data of the three stages in three banks) or one per RK stage")
     ap.add_argument("--no-l2-flush", action="store_true", help="never flush L2 between steps (default: flush when the "
                     "per-GPU working set is smaller than 1.5 x L2)")
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "symm"], help="multi-GPU halo transport")
@@ -404,7 +406,9 @@ def main():
     e2e = None
     if not a.no_e2e:
         run.use_fused_norms(True)
-        if not a.no_graph and hasattr(run, "enable_stage_graphs"):
+        if not a.no_graph and a.e2e_graph == "step" and hasattr(run, "enable_step_graph"):
+            run.enable_step_graph()        # one graph per step, the forcing of stage i in bank i of the boundary arrays
+        elif not a.no_graph and hasattr(run, "enable_stage_graphs"):
             run.enable_stage_graphs()
         for _ in range(max(a.warmup, 3)):
             run.step_e2e()

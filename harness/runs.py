@@ -117,6 +117,12 @@ class SingleSWE:
             self._stage_graphs.append(g)
         ts.stage_graphs = self._stage_graphs     # SSPRK33.solve_stage replays them instead of re-launching
 
+    def enable_step_graph(self):
+        """e2e path with ONE graph per step: the tidal elevation of every stage goes into its own bank of the device
+        boundary arrays (tb_set_bc_bank), then all stages replay from one graph."""
+        self.ts.stage_graphs = None
+        self.ts.enable_step_graph()
+
     def launches(self):
         return self.eng.launch_count() + getattr(self, "_replays", 0) * self.launches_per_step()
 
@@ -130,7 +136,7 @@ class SingleSWE:
 
     def step_e2e(self):
         self.ts.advance(self.t, self.update_forcings)
-        if getattr(self.ts, "stage_graphs", None):
+        if getattr(self.ts, "stage_graphs", None) or getattr(self.ts, "step_graph", None) is not None:
             self._replays = getattr(self, "_replays", 0) + 1
         self.t += self.dt
         if self.ts.fused_norms is None:
@@ -138,9 +144,11 @@ class SingleSWE:
         self._norms_host.copy_(self._norms, non_blocking=True)   # else: reduced by the last stage (tb_stage_integrals)
 
     def e2e_path(self):
+        how = ("one CUDA graph per step, the boundary data of stage i in bank i" if getattr(self.ts, "step_graph", None)
+               is not None else "one CUDA graph per RK stage" if getattr(self.ts, "stage_graphs", None) else "direct launches")
         return ("FlowSolver2d mirror -> SSPRK33.advance(t, update_forcings) -> C-ABI: tidal elevation Function updated "
-                "on the host every stage (H2D from pinned memory), print_state norms reduced on the device (fused "
-                "into the last stage kernel) and read back every step")
+                "on the host for every stage (H2D from pinned memory), print_state norms reduced on the device (fused "
+                "into the last stage kernel) and read back every step; " + how)
 
     def h2d_bytes_per_step(self):
         return 3 * self._n_open * 2 * 8

@@ -154,6 +154,12 @@ int tb_clear_bc(tb_ctx *ctx, int eq, int marker);
 int tb_set_bc_array(tb_ctx *ctx, int eq, int marker, int tag, const double *values,
                     int ncomp, void *stream);
 int tb_set_boundary_length(tb_ctx *ctx, int marker, double length); /* utility.py:821-832 */
+/* Banks of the Function-valued shallow-water boundary data (0 <= bank < 4): subsequent tb_set_bc_array calls fill,
+ * and subsequent stage launches read, the selected bank.  Lets a whole RK step be captured in ONE CUDA graph whose
+ * stage i reads bank i, while `update_forcings(t + c_i dt)` (rungekutta.py:933-934) still provides different boundary
+ * data to every stage: the host fills the banks, then replays the graph.  Default bank 0; a new bank starts as a
+ * copy of bank 0. */
+int tb_set_bc_bank(tb_ctx *ctx, int bank);
 
 /* Cell quadrature for the non-polynomial cell integrands (Manning drag, wind
  * stress / H, wetting-drying): n <= 12 points, barycentric lam[n*3], weights

@@ -499,3 +499,39 @@ def test_patch_staged_limiter_multi_patch_meshes(which):
     ref = O.vertex_based_limiter(mesh, q0)
     assert np.abs(ref - q0).max() > 0.05                       # the limiter did act
     assert np.abs(q - ref).max() < 1e-14
+
+
+def test_step_graph_with_banked_boundary_data_is_bit_identical():
+    """One CUDA graph per step on the reference-facing path: update_forcings still runs for every stage, the tidal
+    elevation of stage i goes into bank i of the device boundary arrays, one replay does the step.  Bit-identical to
+    the stage-by-stage path; a Constant changing mid-run makes the integrator fall back (and stay correct)."""
+    import torch
+    from harness.workloads import north_sea_mesh, north_sea_setup
+    from harness.runs import SingleSWE
+    from thetis_b200.solver2d import physical_constants
+    mesh = north_sea_mesh(1)
+    setup = north_sea_setup(mesh, wetting_drying=True)
+    a = SingleSWE(mesh, setup, wd=True)
+    b = SingleSWE(mesh, setup, wd=True)
+    b.enable_step_graph()
+    assert b.ts.step_graph is not None
+    for _ in range(6):
+        a.step_e2e()
+        b.step_e2e()
+    assert b.ts.step_graph is not None                       # still on the graph path
+    ua, ea = a.state_nodal()
+    ub, eb = b.state_nodal()
+    assert np.array_equal(ua, ub) and np.array_equal(ea, eb)
+    assert np.abs(ea - setup["eta0"]).max() > 1e-6           # the tide did enter
+    g_old = float(physical_constants["g_grav"])
+    try:
+        physical_constants["g_grav"].assign(9.5)             # not a boundary array: the graph cannot honour it
+        for _ in range(3):
+            a.step_e2e()
+            b.step_e2e()
+    finally:
+        physical_constants["g_grav"].assign(g_old)
+    assert b.ts.step_graph is None                           # fell back to the stage-by-stage path
+    ua, ea = a.state_nodal()
+    ub, eb = b.state_nodal()
+    assert np.array_equal(ua, ub) and np.array_equal(ea, eb)

@@ -61,6 +61,7 @@ SIGNATURES = {
     "tb_clear_field": (_I, [_P, _I]),
     "tb_sync_fields": (_I, [_P, _P]),
     "tb_clear_bc": (_I, [_P, _I, _I]),
+    "tb_set_bc_bank": (_I, [_P, _I]),
     "tb_set_bc": (_I, [_P, _I, _I, _I, _P]),
     "tb_set_bc_array": (_I, [_P, _I, _I, _I, _P, _I, _P]),
     "tb_set_boundary_length": (_I, [_P, _I, _D]),

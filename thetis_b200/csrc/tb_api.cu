@@ -57,7 +57,10 @@ struct tb_ctx {
     std::vector<int32_t> bf_row;                 // compact row of each exterior facet (grouped by slot)
     std::vector<std::vector<int32_t>> slot_rows; // exterior facets of each slot, ascending
     std::vector<long long> slot_row0;            // first compact row of each slot
-    double *d_ext[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // elev, uv, un, flux, value (swe)
+    // elev, uv, un, flux, value (swe), in TB_MAX_BANKS banks: bank i holds the boundary data of RK stage i when a whole
+    // step is replayed from one CUDA graph (tb_set_bc_bank); everything else uses bank 0
+    double *d_ext[TB_MAX_BANKS][5] = {};
+    int bc_bank = 0;
     double *d_ext_tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int32_t *d_patch_vglob = nullptr;   // [n_patches*NV] device copy of patch_vglob (stream-ordered column updates)
     double *d_vert = nullptr, *h_vert = nullptr;     // staging of one vertex field (device / pinned), [n_vertices*2]
@@ -530,7 +533,7 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
     cudaFree(ctx->d_partial);
     cudaFree(ctx->d_stage_partial);
     for (int k = 0; k < 5; ++k) {
-        cudaFree(ctx->d_ext[k]);
+        for (int b = 0; b < TB_MAX_BANKS; ++b) cudaFree(ctx->d_ext[b][k]);
         cudaFree(ctx->d_ext_tr[k]);
     }
     cudaFree(ctx->d_fused);
@@ -684,6 +687,12 @@ extern "C" int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const doub
     return TB_OK;
 }
 
+extern "C" int tb_set_bc_bank(tb_ctx *ctx, int bank) {
+    if (!ctx || bank < 0 || bank >= TB_MAX_BANKS) return fail(ctx, TB_ERR_ARG, "bad boundary-data bank");
+    ctx->bc_bank = bank;
+    return TB_OK;
+}
+
 extern "C" int tb_clear_bc(tb_ctx *ctx, int eq, int marker) {
     if (!ctx || eq < 0 || eq > 1) return fail(ctx, TB_ERR_ARG, "bad equation id");
     const int s = find_slot(ctx, marker);
@@ -722,11 +731,17 @@ extern "C" int tb_set_bc_array(tb_ctx *ctx, int eq, int marker, int tag, const d
     const int nc = (tag == TB_BC_UV) ? 2 : 1;
     if (ncomp != nc) return fail(ctx, TB_ERR_ARG, "wrong number of components");
     if (!(ctx->bc[eq][s].opcode & tag)) return fail(ctx, TB_ERR_STATE, "tag not declared with tb_set_bc");
-    double **slot_arr = eq == 0 ? ctx->d_ext : ctx->d_ext_tr;
+    double **slot_arr = eq == 0 ? ctx->d_ext[ctx->bc_bank] : ctx->d_ext_tr;
     const size_t n = (size_t)ctx->n_bfacets * 2 * nc;
     if (!slot_arr[k]) {
         CK(cudaMalloc(&slot_arr[k], sizeof(double) * std::max<size_t>(n, 2)));
-        CK(cudaMemset(slot_arr[k], 0, sizeof(double) * std::max<size_t>(n, 2)));
+        if (eq == 0 && ctx->bc_bank > 0 && ctx->d_ext[0][k]) {
+            // a new bank starts as a copy of bank 0: data of other markers / tags that do not change inside a step
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(slot_arr[k], ctx->d_ext[0][k], sizeof(double) * std::max<size_t>(n, 2), cudaMemcpyDeviceToDevice));
+        } else {
+            CK(cudaMemset(slot_arr[k], 0, sizeof(double) * std::max<size_t>(n, 2)));
+        }
     }
     // The device arrays are compact: rows grouped by marker slot (bf_row), so one marker's data is one contiguous
     // block: gather its rows from the caller's full-size array into a pinned ring slot, one async copy.
@@ -774,7 +789,7 @@ static void fill_bc(tb_ctx *ctx, int eq, TbBcTable &t) {
     t.n_slots = (int)ctx->slot_marker.size();
     t.bf_slot = ctx->d_bf_slot;
     t.bf_row = ctx->d_bf_row;
-    double **a = eq == 0 ? ctx->d_ext : ctx->d_ext_tr;
+    double **a = eq == 0 ? ctx->d_ext[ctx->bc_bank] : ctx->d_ext_tr;
     t.ext_elev = a[0];
     t.ext_uv = a[1];
     t.ext_un = a[2];

@@ -11,6 +11,7 @@
 #endif
 #define TB_MAX_SLOTS 16     // distinct boundary markers
 #define TB_MAX_QUAD 12      // max cell quadrature points
+#define TB_MAX_BANKS 4      // banks of Function-valued boundary data (one per RK stage of a graph-replayed step)
 
 // coefficient descriptor: mode 0 = None, 1 = Constant, 2 = P1 vertex column(s) of the static block,
 // 3 = discontinuous P1DG field stored per cell node: cell[(cell*3 + node)*nc + comp] (generic kernels only)

@@ -139,6 +139,12 @@ class Engine:
         self._ck(self.lib.tb_sync_fields(self.ctx, self.stream))
         self._fields_pending = False
 
+    def set_bc_bank(self, bank):
+        """bank of the Function-valued SWE boundary data the next uploads fill / the next stage launches read"""
+        if getattr(self, "_bc_bank", 0) != bank:
+            self._ck(self.lib.tb_set_bc_bank(self.ctx, int(bank)))
+            self._bc_bank = bank
+
     def clear_bc(self, eq, marker):
         self._ck(self.lib.tb_clear_bc(self.ctx, eq, int(marker)))
 

@@ -400,10 +400,11 @@ class ERKGenericShuOsher:
         return tuple(sig)
 
     def _watch_build(self, gc):
-        watch = []          # (object, last version, [actions])
+        watch = []          # [object, last version, [actions], dat, feeds something other than a boundary array]
         index = {}
+        self._bc_array_items = []
 
-        def add(obj, action):
+        def add(obj, action, array_only=False):
             if obj is None or isinstance(obj, (int, float, tuple, list, np.ndarray)):
                 return
             leaves = expression_leaves(obj) if is_expression(obj) else [obj]
@@ -411,9 +412,11 @@ class ERKGenericShuOsher:
                 ent = index.get(id(leaf))
                 if ent is None:
                     d = getattr(leaf, "dat", None)
-                    ent = index[id(leaf)] = [leaf, _version(leaf), [], d if hasattr(d, "dat_version") else None]
+                    ent = index[id(leaf)] = [leaf, _version(leaf), [], d if hasattr(d, "dat_version") else None, False]
                     watch.append(ent)
                 ent[2].append(action)
+                if not array_only:
+                    ent[4] = True
         eqo = self.equation.options
         if gc is not None:
             add(gc["g_grav"], lambda: self._push_option("g", L.OPT_G_GRAV, gc["g_grav"], 9.81))
@@ -436,7 +439,10 @@ class ERKGenericShuOsher:
                     add(val, lambda marker=marker, funcs=funcs: self._push_bc_marker(0, _SWE_TAGS, marker, funcs))
                 else:
                     # Function / expression data: only that array travels (the tidal elevation of every stage)
-                    add(val, lambda marker=marker, tag=tag, val=val: self._push_bc_array(0, _SWE_TAGS, marker, tag, val))
+                    add(val, lambda marker=marker, tag=tag, val=val: self._push_bc_array(0, _SWE_TAGS, marker, tag, val),
+                        array_only=True)
+                    if tag in _SWE_TAGS:
+                        self._bc_array_items.append((marker, tag, val))
         self._watch = watch
         self._watch_sig = self._watch_signature()
         # a datum without a version counter must be re-read every stage: no fast path then
@@ -518,13 +524,16 @@ class ERKGenericShuOsher:
             for tag, val in arrays:
                 self._push_bc_array(eq, tags, marker, tag, val)
 
-    def _push_bc_array(self, eq, tags, marker, tag, val):
-        """Upload one Function- / expression-valued boundary datum if it changed (pinned ring + async H2D)."""
+    def _push_bc_array(self, eq, tags, marker, tag, val, bank=0):
+        """Upload one Function- / expression-valued boundary datum if it changed (pinned ring + async H2D).  ``bank``:
+        the copy of the boundary arrays RK stage ``bank`` of a graph-replayed step reads (tb_set_bc_bank)."""
         ver = _version(val)
-        akey = (eq, marker, tag)
+        akey = (eq, marker, tag) if bank == 0 else (eq, marker, tag, bank)
         astamp = (id(val), ver)
         if ver is None or self._bc_versions.get(akey) != astamp:
+            self.engine.set_bc_bank(bank)
             self.engine.set_bc_array(eq, marker, tags[tag], self.adaptor.bfacet_values(val, marker))
+            self.engine.set_bc_bank(0)
             self._bc_versions[akey] = astamp
             # keep the marker-level fast-path signature of _push_bc_marker consistent with what is on the device
             self._stamps.pop(("bc", eq, marker), None)
@@ -737,6 +746,62 @@ class ERKGenericShuOsher:
             if dst is not A:
                 self.buf[0], self.buf[1] = self.buf[1], self.buf[0]
 
+    # -- one CUDA graph per STEP on the reference-facing path.  `update_forcings(t + c_i dt)` still runs before every
+    # stage (rungekutta.py:933-934), but its effect is gathered first: the Function-valued boundary data it assigned
+    # for stage i go into bank i of the device arrays, then ONE graph replays all stages, stage i reading bank i.
+    # Anything else that changes inside a step (a Constant, a coefficient field, the entries of the dicts) cannot be
+    # replayed from a graph with baked parameters: the step is then done stage by stage as usual and the graph dropped.
+    def enable_step_graph(self):
+        if self._kind != "swe" or self.butcher_form or self.n_stages < 2 or self.n_stages > 4 or \
+                self.sync_policy == "every_stage":
+            raise NotImplementedError("step graph: Shu-Osher SWE integrators with 2-4 stages, sync_policy != 'every_stage'")
+        self.step_graph = None
+        self._push_dynamic()                                  # full pass: builds the watch list
+        for i in range(self.n_stages):                        # allocate / fill every bank before the capture
+            if self._push_banked(i):
+                raise NotImplementedError("step graph: a datum without a version counter is re-read every stage")
+        saved = self.buf[0].clone()
+        self.advance_device()                                 # warm-up outside the capture (lazy allocations) ...
+        self.buf[0].copy_(saved)                              # ... on a copy: the solution is not advanced
+        torch.cuda.synchronize(self.engine.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(self.n_stages):
+                self.engine.set_bc_bank(i)
+                self._launch_stage(i)
+            self.engine.set_bc_bank(0)
+        self.step_graph = g
+        return g
+
+    def _push_banked(self, i_stage):
+        """Stage i of a graph-replayed step: upload the boundary arrays that differ from what bank i holds.  Returns
+        True when something the graph cannot honour changed (the caller falls back to the stage-by-stage path)."""
+        if not getattr(self, "_watch_ok", False) or self._watch_signature() != self._watch_sig:
+            return True
+        for ent in self._watch:
+            d = ent[3]
+            v = ("dat", d.dat_version) if d is not None else _version(ent[0])
+            if v != ent[1]:
+                if ent[4]:
+                    return True            # a Constant / coefficient field moved: not an array-only change
+                ent[1] = v
+        for marker, tag, val in self._bc_array_items:
+            self._push_bc_array(0, _SWE_TAGS, marker, tag, val, bank=i_stage)
+        return False
+
+    def _advance_step_graph(self, t, update_forcings):
+        for i in range(self.n_stages):
+            if update_forcings is not None:
+                update_forcings(t + self.c[i] * self.dt)
+            if i == 0 and not self._host_stale and self._host_changed():
+                self.upload()
+            if self._push_banked(i):
+                return False
+        self.step_graph.replay()
+        self._mid_step = False
+        self._host_stale = True
+        return True
+
     def advance_device(self):
         """One step with every input already resident on the device (no forcing refresh, no host sync)."""
         for i in range(self.n_stages):
@@ -744,6 +809,12 @@ class ERKGenericShuOsher:
 
     def advance(self, t, update_forcings=None):
         """Advances equations for one time step (rungekutta.py:948-952)."""
+        if getattr(self, "step_graph", None) is not None:
+            if self._advance_step_graph(t, update_forcings):
+                if self.sync_policy == "every_step":
+                    self.sync_to_host()
+                return
+            self.step_graph = None          # something other than boundary arrays changed: stage by stage from now on
         for i in range(self.n_stages):
             self.solve_stage(i, t, update_forcings)
         if self.sync_policy == "every_step":
