@@ -285,3 +285,43 @@ def test_automatic_timestep_is_min_reduced_over_ranks_gloo():
     s.create_fields()
     s.set_time_step()
     assert abs(out[0] - s.dt) / s.dt < 0.05
+
+
+@pytest.mark.parametrize("halo", ["facet", "vertex"])
+def test_fused_push_tables_deliver_every_ghost(halo):
+    """Host logic of the fused compute + halo-push launches, emulated in numpy for 3 ranks: with the launch order,
+    the per-patch push entries (`fused_push_tables`) and the destination slots `HaloPlan.alloc` computes, every ghost
+    slot of every rank receives exactly the record of the owned cell it mirrors, and only partition-boundary patches
+    push (they come first in the launch order, which is a permutation of all patches)."""
+    from thetis_b200.parallel import fused_push_tables
+    mesh = _mesh()
+    world, P = 3, 16                                     # small patches so that a rank has several boundary patches
+    parts = partition_mesh(mesh, world, halo=halo)
+    pads = [((q.n_owned + P - 1) // P) * P for q in parts]
+    # "device" arrays: owned cells (padded) then ghosts; the value of a cell is its global id
+    arrays = [np.full(pads[r] + parts[r].n_ghost, -1.0) for r in range(world)]
+    for r, p in enumerate(parts):
+        arrays[r][: p.n_owned] = p.owned_global
+    for r, p in enumerate(parts):
+        send_idx = np.concatenate([p.send_lists[q] for q in range(world) if q in p.send_lists])
+        n_patches = pads[r] // P
+        order, push_ptr, push_cell, perm = fused_push_tables(send_idx, n_patches, P)
+        assert np.array_equal(np.sort(order), np.arange(n_patches))
+        n_b = push_ptr.shape[0] - 1
+        assert n_b == np.unique(send_idx // P).shape[0] and push_ptr[-1] == send_idx.shape[0]
+        # destination (rank, slot) of every send entry, as in HaloPlan.alloc
+        dst = []
+        for q in range(world):
+            if q not in p.send_lists:
+                continue
+            n = p.send_lists[q].shape[0]
+            first = int((parts[q].ghost_owner < r).sum())
+            dst += [(q, pads[q] + first + k) for k in range(n)]
+        for b in range(n_b):                              # CTA b of the launch = patch order[b]
+            for e in range(push_ptr[b], push_ptr[b + 1]):
+                cell = order[b] * P + push_cell[e]
+                assert cell == send_idx[perm[e]]
+                q, slot = dst[perm[e]]
+                arrays[q][slot] = arrays[r][cell]
+    for r, p in enumerate(parts):
+        assert np.array_equal(arrays[r][pads[r]:], p.ghost_global.astype(float))

@@ -156,6 +156,7 @@ __device__ __forceinline__ void tb_fused_push(const TbHaloFused *hf, const unsig
     __threadfence_system();          // this thread's peer stores are ordered before the signal below
     __syncthreads();
     if (tid == 0) {
+        __threadfence_system();      // cumulative over the whole CTA's stores (observed through the barrier)
         const unsigned int done = atomicAdd(hf->done_count, 1u);
         if (done == (unsigned int)n_bpatch - 1u) {
             // every boundary CTA of this launch has pushed: publish the new epoch to the receiving peers

@@ -43,6 +43,30 @@ class LocalPart:
         self.mesh = mesh                            # local Mesh2D: owned cells first, then ghosts
 
 
+def fused_push_tables(send_idx, n_patches, P):
+    """
+    Tables of the fused compute + halo-push launches (tb_halo_fused_setup) from this rank's send list (owned cell
+    ids, peer by peer, in the order `HaloPlan.alloc` computes the destination addresses):
+    `order`  launch order of the patches, those holding a cell some peer needs first;
+    `push_ptr` / `push_cell`  CSR over those leading patches: for CTA b the cells (index inside the patch) it pushes,
+    one entry per (cell, peer);  `perm`  maps the entries back to positions in `send_idx` (so that entry e goes to
+    destination address dst[perm[e]]).
+    """
+    send_idx = np.asarray(send_idx, dtype=np.int64)
+    bp = np.unique(send_idx // P).astype(np.int64)
+    mask = np.zeros(n_patches, dtype=bool)
+    mask[bp] = True
+    order = np.concatenate([bp, np.nonzero(~mask)[0]]).astype(np.int32)
+    pos = np.full(n_patches, -1, dtype=np.int64)
+    pos[bp] = np.arange(bp.shape[0])
+    key = pos[send_idx // P]
+    perm = np.argsort(key, kind="stable")
+    cnt = np.bincount(key, minlength=bp.shape[0]) if send_idx.size else np.zeros(0, np.int64)
+    push_ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    push_cell = (send_idx % P)[perm].astype(np.int32)
+    return order, push_ptr, push_cell, perm
+
+
 def partition_mesh(mesh: Mesh2D, world: int, halo: str = "facet"):
     """
     Cut the (SFC-ordered) mesh into `world` contiguous chunks with a one-deep halo of ghost cells:
@@ -223,18 +247,7 @@ class HaloPlan:
         boundary patches first, per-patch push entries, and the per-peer epoch flags in symmetric memory."""
         import torch.distributed as dist
         torch, eng, p = self.torch, self.engine, self.part
-        bp = np.unique(send_idx // P).astype(np.int64)
-        mask = np.zeros(eng.n_patches, dtype=bool)
-        mask[bp] = True
-        order = np.concatenate([bp, np.nonzero(~mask)[0]]).astype(np.int32)
-        pos = np.full(eng.n_patches, -1, dtype=np.int64)
-        pos[bp] = np.arange(bp.shape[0])
-        # entries in the order `alloc` computes the destination addresses (peer by peer), then grouped by patch
-        key = pos[send_idx // P]
-        self._push_perm = np.argsort(key, kind="stable")
-        cnt = np.bincount(key, minlength=bp.shape[0]) if send_idx.size else np.zeros(0, np.int64)
-        push_ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
-        push_cell = (send_idx % P)[self._push_perm].astype(np.int32)
+        order, push_ptr, push_cell, self._push_perm = fused_push_tables(send_idx, eng.n_patches, P)
         nflag = max(self.world, 4)
         self._flags = self._symm_mem.empty(nflag, dtype=torch.int64, device=eng.device)
         self._flags.zero_()

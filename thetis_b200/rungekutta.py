@@ -482,47 +482,46 @@ class ERKGenericShuOsher:
 
     def _push_bc_marker(self, eq, tags, marker, funcs):
         eng = self.engine
-        if True:
-            # fast path: nothing in this marker's dict changed since the last stage
-            sig = []
-            for tag, val in funcs.items():
-                st = self._stamp(val)
-                if st is None:
-                    sig = None
-                    break
-                sig.append((tag, st))
-            if sig is not None:
-                sig = tuple(sig)
-                if self._stamps.get(("bc", eq, marker)) == sig:
-                    return
-            self._stamps[("bc", eq, marker)] = sig
-            op = 0
-            consts = np.zeros(8)
-            arrays = []
-            for tag, val in funcs.items():
-                if tag not in tags:
-                    if eq == 0:
-                        raise Exception(f'Invalid boundary tag "{tag}" specified on boundary {marker}')
-                    continue
-                op |= tags[tag]
-                if is_constant(val):
-                    v = constant_value(val)
-                    s = _CONST_SLOT[tag]
-                    consts[s:s + v.size] = v
-                elif is_function(val) or is_expression(val):
-                    arrays.append((tag, val))     # expressions: affine in their Functions, evaluated nodally (exact)
-                else:
-                    raise NotImplementedError(f"boundary datum {tag!r} on marker {marker}: unsupported value "
-                                              f"{type(val).__name__}")
-            stamp = (op,) + tuple(consts.tolist())
-            key = (eq, marker)
-            if self._bc_versions.get(key) != stamp:
-                eng.set_bc(eq, marker, op, consts)
-                self._bc_versions[key] = stamp
-                for tag, _ in arrays:
-                    self._bc_versions.pop((eq, marker, tag), None)
-            for tag, val in arrays:
-                self._push_bc_array(eq, tags, marker, tag, val)
+        # fast path: nothing in this marker's dict changed since the last stage
+        sig = []
+        for tag, val in funcs.items():
+            st = self._stamp(val)
+            if st is None:
+                sig = None
+                break
+            sig.append((tag, st))
+        if sig is not None:
+            sig = tuple(sig)
+            if self._stamps.get(("bc", eq, marker)) == sig:
+                return
+        self._stamps[("bc", eq, marker)] = sig
+        op = 0
+        consts = np.zeros(8)
+        arrays = []
+        for tag, val in funcs.items():
+            if tag not in tags:
+                if eq == 0:
+                    raise Exception(f'Invalid boundary tag "{tag}" specified on boundary {marker}')
+                continue
+            op |= tags[tag]
+            if is_constant(val):
+                v = constant_value(val)
+                s = _CONST_SLOT[tag]
+                consts[s:s + v.size] = v
+            elif is_function(val) or is_expression(val):
+                arrays.append((tag, val))     # expressions: affine in their Functions, evaluated nodally (exact)
+            else:
+                raise NotImplementedError(f"boundary datum {tag!r} on marker {marker}: unsupported value "
+                                          f"{type(val).__name__}")
+        stamp = (op,) + tuple(consts.tolist())
+        key = (eq, marker)
+        if self._bc_versions.get(key) != stamp:
+            eng.set_bc(eq, marker, op, consts)
+            self._bc_versions[key] = stamp
+            for tag, _ in arrays:
+                self._bc_versions.pop((eq, marker, tag), None)
+        for tag, val in arrays:
+            self._push_bc_array(eq, tags, marker, tag, val)
 
     def _push_bc_array(self, eq, tags, marker, tag, val, bank=0):
         """Upload one Function- / expression-valued boundary datum if it changed (pinned ring + async H2D).  ``bank``:
