@@ -218,3 +218,64 @@ def test_tracer_h_advection_convergence_on_gpu():
                 tt += dt
             assert _rel(c, co) < 1e-10
     assert K.convergence_slope(refs, errs) > 2 * (1 - 0.2), errs
+
+
+# ---------------------------------------------------------------- tracer diffusion with a diff_flux boundary
+def _diff_flux_series(x, t, lx, nu, D, n_terms=100):
+    """The truncated Fourier-series solution of test/tracerEq/test_bcs_2d.py:6-83 (c_t = nu c_xx, c_x(0) = -D,
+    c_x(lx) = 0, c(x, 0) = 0), with the coefficients of I(x) = D (lx - x)^2 / (2 lx) in closed form:
+    a_0 = D lx / 3, a_k = 2 D lx / (k pi)^2; the source -nu D / lx only feeds the mean."""
+    ic = D * 0.5 * (lx - x) ** 2 / lx
+    expr = 0.5 * (2.0 * (-nu * D / lx)) * t + 0.5 * (D * lx / 3.0) - ic
+    for k in range(1, n_terms):
+        expr = expr + 2.0 * D * lx / (k * np.pi) ** 2 * np.exp(-nu * (k * np.pi / lx) ** 2 * t) * np.cos(k * np.pi * x / lx)
+    return -expr
+
+
+def _diff_flux_gpu(refinement, nsteps=None):
+    from thetis_b200.shim import Constant
+    from thetis_b200.mesh import rectangle_mesh
+    lx, ly, nu, D, depth = 10.0, 1.0, 0.1, 0.2, 40.0
+    mesh = rectangle_mesh(40 * refinement, 4, lx, ly)
+    dt = 0.1 / refinement
+    s = _solver(mesh, depth, timestep=dt, simulation_export_time=0.1, simulation_end_time=1.0 - 0.5 * dt,
+                tracer_only=True, tracer_timestepper_type="SSPRK33", horizontal_velocity_scale=0.0)
+    s.options.horizontal_diffusivity_scale = Constant(nu)
+    s.options.add_tracer_2d("tracer_2d", "Depth averaged tracer", "Tracer2d", diffusivity=Constant(nu))
+    s.options.use_limiter_for_tracers = True                           # tracer_element_family == 'dg' (:118)
+    s.bnd_functions["tracer_2d"] = {1: {"diff_flux": D * nu}}           # :123
+    if nsteps is not None:
+        s.options.tracer_timestepper_options.use_automatic_timestep = False
+        s.options.swe_timestepper_options.use_automatic_timestep = False
+        s.options.timestep = 2.0e-4
+        s.options.simulation_end_time = nsteps * 2.0e-4 - 1e-9
+    s.assign_initial_conditions()
+    s.iterate()
+    c = s.fields.tracer_2d.dat.data_ro.reshape(mesh.n_cells, 3).copy()
+    return mesh, s, c, (lx, ly, nu, D, depth)
+
+
+def test_tracer_diff_flux_boundary_convergence_on_gpu():
+    """test/tracerEq/test_bcs_2d.py:86-148 with SSPRK33 / dg: refinements 1, 2, 4, successive L2 error ratios > 2
+    against the Fourier-series solution (the explicit stepper runs with the reference's automatic time step)"""
+    errs = []
+    for r in (1, 2, 4):
+        mesh, s, c, (lx, ly, nu, D, depth) = _diff_flux_gpu(r)
+        assert s.simulation_time >= 1.0 - 0.5 * 0.1 / r - 1e-9
+        errs.append(O.l2_error(mesh, c, lambda X, Y: _diff_flux_series(X, 1.0, lx, nu, D)))
+    assert errs[0] / errs[1] > 2 and errs[1] / errs[2] > 2, errs
+
+
+def test_tracer_diff_flux_boundary_steps_match_oracle():
+    """the same set-up, 60 steps against the oracle (SIPG diffusion + 'diff_flux' boundary term + limiter)"""
+    mesh, s, c_g, (lx, ly, nu, D, depth) = _diff_flux_gpu(1, nsteps=60)
+    swe = O.SWEOracle(mesh, depth)
+    trc = O.TracerOracle(swe, bnd_conditions={1: {"diff_flux": D * nu}}, fields={"diffusivity_h": nu})
+    trc.set_velocity(np.zeros((mesh.n_cells, 3, 2)), np.zeros((mesh.n_cells, 3)))
+    c = np.zeros((mesh.n_cells, 3))
+    st = O.ShuOsherStepper(trc, [c], 2.0e-4)
+    for i in range(60):
+        st.advance(i * 2.0e-4)
+        c[...] = O.vertex_based_limiter(mesh, c)
+    assert np.abs(c).max() > 1e-6
+    assert _rel(c_g, c) < 1e-10
