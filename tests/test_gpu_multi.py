@@ -1,7 +1,9 @@
 """
-Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the domain-decomposed run (one process per GPU, NCCL halo
-exchange once per RK stage) must reproduce the single-GPU run BIT FOR BIT -- every cell is evaluated from its own
-side by the same kernel, so ownership cannot change a result.
+Multi-GPU parity: the domain-decomposed run (one process per GPU; fused compute + halo-push launches, or the unfused /
+NCCL transports) must reproduce the single-GPU run BIT FOR BIT -- every cell is evaluated from its own side by the
+same kernel, so ownership cannot change a result.  The NVLink variants need >= 2 GPUs (skipped otherwise); the
+"host" / one_gpu variants put both ranks on ONE GPU with the halo staged through the host over gloo, so a single-GPU
+test run still exercises partitioning, ghost cells, the vertex halo of the limiter and the all-reduced diagnostics.
 """
 import os
 import socket
@@ -20,13 +22,26 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, k, nsteps, transport, out):
+def _init(rank, world, port, one_gpu):
+    """one process per GPU over NCCL -- or, with ``one_gpu``, every rank on cuda:0 over gloo (host-staged halo)"""
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    if one_gpu:
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+
+
+def _worker(rank, world, port, k, nsteps, transport, out):
+    import torch
+    import torch.distributed as dist
+    _init(rank, world, port, transport == "host")
+    if transport == "host":
+        transport = "nccl"              # pack + exchange_halo + scatter; gloo stages it through the host
     try:
         from harness.workloads import north_sea_mesh, north_sea_setup
         from harness.runs import PartitionedSWE
@@ -59,12 +74,14 @@ def _worker(rank, world, port, k, nsteps, transport, out):
 
 # "symm": fused compute + halo push (tb_swe_stage_fused, per-peer epoch flags); "symm-unfused": boundary launch +
 # push kernel + cross-rank barrier; "nccl": pack + all-to-all
-@pytest.mark.parametrize("transport", ["nccl", "symm", "symm-unfused"])
+# "host": both ranks on ONE GPU, halo staged through the host over gloo -- runs on a single-GPU box, so the
+# partition / ghost-cell / boundary-patch logic and the ownership-independence of the kernels are always exercised
+@pytest.mark.parametrize("transport", ["nccl", "symm", "symm-unfused", "host"])
 @pytest.mark.parametrize("world", [2])
 def test_partitioned_run_is_bit_identical(world, transport):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < world:
+    if transport != "host" and torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     k, nsteps = 2, 4
     mgr = mp.Manager()
@@ -88,13 +105,10 @@ def test_partitioned_run_is_bit_identical(world, transport):
     assert np.isfinite(uv1).all() and np.abs(eta1).max() > 0
 
 
-def _worker_coupled(rank, world, port, out):
+def _worker_coupled(rank, world, port, out, one_gpu=False):
     import torch
     import torch.distributed as dist
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    _init(rank, world, port, one_gpu)
     try:
         from thetis_b200.parallel import distribute_mesh
         mesh = _coupled_mesh()
@@ -139,16 +153,18 @@ def _coupled_solver(mesh_obj):
     return s
 
 
-def test_coupled_tracer_limiter_distributed_is_bit_identical():
-    """SWE -> tracer -> limiter on 2 GPUs (vertex halo for the limiter bounds) == the 1-GPU run, bit for bit"""
+@pytest.mark.parametrize("one_gpu", [False, True])
+def test_coupled_tracer_limiter_distributed_is_bit_identical(one_gpu):
+    """SWE -> tracer -> limiter on 2 ranks (vertex halo for the limiter bounds) == the 1-GPU run, bit for bit; on 2 GPUs
+    with the fused compute + halo-push launches, or both ranks on one GPU with the halo staged through the host"""
     import torch
     import torch.multiprocessing as mp
     world = 2
-    if torch.cuda.device_count() < world:
+    if not one_gpu and torch.cuda.device_count() < world:
         pytest.skip("needs 2 GPUs")
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker_coupled, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker_coupled, args=(world, _free_port(), out, one_gpu), nprocs=world, join=True)
     s = _coupled_solver(_coupled_mesh())
     s.iterate()
     uv1 = s.fields.uv_2d.dat.data_ro.reshape(-1, 3, 2)

@@ -327,6 +327,14 @@ class HaloPlan:
             eng.gather_cells(state, self.send_idx, rec, sb)
         g0 = eng.n_owned_pad * rec
         ghost = state[g0:g0 + p.n_ghost * rec].view(-1, rec)
+        import torch.distributed as dist
+        if dist.get_backend() == "gloo":
+            # host-staged transport: gloo moves CPU tensors only.  Slow and synchronous -- it exists so that N ranks
+            # can share ONE GPU (debugging, and the partition / ghost logic in a single-GPU test run)
+            recv_h = self.torch.empty(ghost.shape, dtype=ghost.dtype)
+            exchange_halo(p, sb[:self.n_send].cpu(), recv_h)
+            ghost.copy_(recv_h)
+            return
         exchange_halo(p, sb[:self.n_send], ghost)
 
     def swe_stage(self, a0, a1, bdt, src, u0, dst, fused=True):
