@@ -490,6 +490,9 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         // [(TB_P + NH)][5] gradients + 2A of the patch and halo cells, behind the reduction scratch (only allocated
         // when a SIPG coefficient is set: pl.off_hcv >= 0)
         double *Gs = reinterpret_cast<double *>(blk + prm.pl.stride) + (TB_P / 32) * 4;
+        // grad-depth viscosity source evaluated inside the Manning cell-rule loop (shares the depth and H^(-1/3))
+        const bool gd_merge = has_visc && prm.graddepth != 0 && use_quad && has_man;
+        double gdVx = 0.0, gdVy = 0.0, gdnu[3] = {0, 0, 0};
         if (has_visc) {
             double nuv[3], Sxx, Sxy, Syx, Syy;
 #pragma unroll
@@ -522,26 +525,39 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                 }
                 gHx *= -itA;
                 gHy *= -itA;
-                const double Vx = gHx * Sxx + gHy * Syx, Vy = gHx * Sxy + gHy * Syy;
-                for (int qd = 0; qd < prm.nquad; ++qd) {
-                    const double l0 = c_qlam[qd][0], l1 = c_qlam[qd][1], l2 = c_qlam[qd][2];
-                    const double hq = l0 * hl[0] + l1 * hl[1] + l2 * hl[2];
-                    double Hq = hq, fac = 1.0;
-                    if (NONLIN && wd_on) {
-                        // H = (hl + sqrt(hl^2 + alpha^2))/2, dH/dhl = (1 + hl/sqrt(hl^2 + alpha^2))/2
-                        double a2q = a2;
-                        if (var_al) {
-                            const double aq = l0 * al[0] + l1 * al[1] + l2 * al[2];
-                            a2q = aq * aq;
-                            // NB grad(H) of the wetting-drying depth also has a d/d(alpha) part when alpha varies
+                gdVx = gHx * Sxx + gHy * Syx;
+                gdVy = gHx * Sxy + gHy * Syy;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) gdnu[a] = nuv[a];
+                // With Manning drag the cell-rule loop below already evaluates the depth and H^(-1/3) at every point:
+                // the integrand k = w nu (dH/dhl) / H is accumulated there (gd_merge); otherwise here.
+                if (!gd_merge) {
+                    double Gd[3] = {0, 0, 0};
+                    for (int qd = 0; qd < prm.nquad; ++qd) {
+                        const double l0 = c_qlam[qd][0], l1 = c_qlam[qd][1], l2 = c_qlam[qd][2];
+                        const double hq = l0 * hl[0] + l1 * hl[1] + l2 * hl[2];
+                        double Hq = hq, fac = 1.0;
+                        if (NONLIN && wd_on) {
+                            // H = (hl + sqrt(hl^2 + alpha^2))/2, dH/dhl = (1 + hl/sqrt(hl^2 + alpha^2))/2
+                            double a2q = a2;
+                            if (var_al) {
+                                const double aq = l0 * al[0] + l1 * al[1] + l2 * al[2];
+                                a2q = aq * aq;
+                                // NB grad(H) of the wetting-drying depth also has a d/d(alpha) part when alpha varies
+                            }
+                            const double x2 = fma(hq, hq, a2q);
+                            const double r = tb_rsqrt(x2);
+                            Hq = 0.5 * (hq + x2 * r);
+                            fac = fma(0.5 * hq, r, 0.5);
                         }
-                        const double r = tb_rsqrt(hq * hq + a2q);
-                        Hq = 0.5 * (hq + (hq * hq + a2q) * r);
-                        fac = 0.5 * (1.0 + hq * r);
+                        const double k = c_qw[qd] * A * (l0 * nuv[0] + l1 * nuv[1] + l2 * nuv[2]) * fac * tb_rcp(Hq);
+                        Gd[0] = fma(l0, k, Gd[0]); Gd[1] = fma(l1, k, Gd[1]); Gd[2] = fma(l2, k, Gd[2]);
                     }
-                    const double k = c_qw[qd] * A * (l0 * nuv[0] + l1 * nuv[1] + l2 * nuv[2]) * fac * tb_rcp(Hq);
-                    Rux[0] += l0 * k * Vx; Rux[1] += l1 * k * Vx; Rux[2] += l2 * k * Vx;
-                    Ruy[0] += l0 * k * Vy; Ruy[1] += l1 * k * Vy; Ruy[2] += l2 * k * Vy;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        Rux[a] = fma(Gd[a], gdVx, Rux[a]);
+                        Ruy[a] = fma(Gd[a], gdVy, Ruy[a]);
+                    }
                 }
             }
         }
@@ -565,6 +581,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             for (int a = 0; a < 3; ++a) hl[a] = NONLIN ? b[a] + et[a] : b[a];
             const int nq = SP::generic ? prm.nquad : 6;
             double HUx = 0.0, HUy = 0.0;
+            double Gdm[3] = {0, 0, 0};
 TB_UNROLL(TB_QUAD_UNROLL)
             for (int qd = 0; qd < (SP::generic ? TB_MAX_QUAD : 6); ++qd) {
                 if (SP::generic && qd >= nq) break;
@@ -573,13 +590,21 @@ TB_UNROLL(TB_QUAD_UNROLL)
                 const double uq = l0 * ux[0] + l1 * ux[1] + l2 * ux[2];
                 const double vq = l0 * uy[0] + l1 * uy[1] + l2 * uy[2];
                 double Hq = l0 * hl[0] + l1 * hl[1] + l2 * hl[2];
+                double gfac = 1.0;           // dH/dhl of the wetting-drying depth (grad-depth viscosity term)
                 if (NONLIN) {
                     double a2q = a2;
                     if (var_al) {
                         const double aq = l0 * al[0] + l1 * al[1] + l2 * al[2];
                         a2q = aq * aq;
                     }
-                    Hq = wd_depth(Hq, wd_on, a2q);
+                    if (gd_merge && wd_on) {
+                        const double x2 = fma(Hq, Hq, a2q);
+                        const double rs = tb_rsqrt(x2);
+                        gfac = fma(0.5 * Hq, rs, 0.5);
+                        Hq = 0.5 * (Hq + x2 * rs);
+                    } else {
+                        Hq = wd_depth(Hq, wd_on, a2q);
+                    }
                 }
                 double sx = 0, sy = 0;   // momentum source density at the point
                 if (has_man || has_cd || has_nik) {
@@ -591,6 +616,11 @@ TB_UNROLL(TB_QUAD_UNROLL)
                         const double r = tb_rcbrt(Hq);             // H^(-1/3)
                         const double r2 = r * r;
                         k = g * m * m * (r2 * r2) * umag;          // g mu^2 / H^(1/3) * |u| / H
+                        if (gd_merge) {
+                            // (:611-612) k = w nu (dH/dhl) / H with 1/H = (H^(-1/3))^3
+                            const double kk = w * (l0 * gdnu[0] + l1 * gdnu[1] + l2 * gdnu[2]) * gfac * (r2 * r);
+                            Gdm[0] = fma(l0, kk, Gdm[0]); Gdm[1] = fma(l1, kk, Gdm[1]); Gdm[2] = fma(l2, kk, Gdm[2]);
+                        }
                     } else if (has_nik) {
                         // C_D = 2 kappa^2 / ln(11.036 H / k_s)^2 where H > k_s, else 0 (:697)
                         const double ks = l0 * cdn[0] + l1 * cdn[1] + l2 * cdn[2];
@@ -616,6 +646,13 @@ TB_UNROLL(TB_QUAD_UNROLL)
                     const double wH = c_qw[qd] * Hq;
                     HUx = fma(wH, uq, HUx);
                     HUy = fma(wH, vq, HUy);
+                }
+            }
+            if (gd_merge) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    Rux[a] = fma(Gdm[a], gdVx, Rux[a]);
+                    Ruy[a] = fma(Gdm[a], gdVy, Ruy[a]);
                 }
             }
             if (NONLIN && wd_on) {
