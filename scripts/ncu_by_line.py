@@ -8,11 +8,9 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(out.splitlines()))
 # the export is a sequence of blocks: ["File Path", path], ["Function Name", f], header row, then per source line a row with
 # a line number followed by its SASS rows (empty line number)
-launch = -1
 cur_file = None
 hdr = None
 agg = collections.defaultdict(lambda: [0, 0, ""])      # (file, line) -> [inst, samples, text]
-seen_funcs = []
 fp64 = collections.Counter()
 for r in rows:
     if not r:
@@ -21,8 +19,6 @@ for r in rows:
         cur_file = r[1].split("/")[-1]
         continue
     if r[0] == "Function Name":
-        if not seen_funcs or seen_funcs[-1] != r[1] or cur_file == first_file:
-            pass
         continue
     if r[0] == "Kernel Name" or r[0] == "ID":
         continue
