@@ -165,7 +165,11 @@ int tb_set_bc_bank(tb_ctx *ctx, int bank);
  * stress / H, wetting-drying): n <= 12 points, barycentric lam[n*3], weights
  * summing to 1.  Default: the 6-point degree-3 Strang-Fix rule (the reference
  * asks for degree 2p+1 = 3, shallowwater_eq.py:225-230; FIAT's default rule for
- * that degree is version dependent). */
+ * that degree is version dependent).  The rule is held in
+ * constant memory of the device, i.e. it is shared by every context of the
+ * process, and tb_create resets it to the default.  The specialised stage
+ * kernels exploit the structure of the default rule (one symmetric orbit,
+ * equal weights); any other rule is served by the generic stage kernel. */
 int tb_set_cell_quadrature(tb_ctx *ctx, int n, const double *lam, const double *w);
 
 /* ---- the hot path ------------------------------------------------------ */

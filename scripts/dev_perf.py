@@ -10,9 +10,16 @@ import thetis_b200._lib as L
 ap = argparse.ArgumentParser()
 ap.add_argument("--k", type=int, default=19)
 ap.add_argument("--steps", type=int, default=20)
-ap.add_argument("--mode", default="all")
+ap.add_argument("--mode", default="all", help="all, or a comma-separated list of modes")
 ap.add_argument("--nosfc", action="store_true")
 a = ap.parse_args()
+MODES = a.mode.split(",")
+
+
+def sel(name):
+    return "all" in MODES or name in MODES
+
+
 t0 = time.time()
 m = refine_uniform(load_npz_mesh(os.path.join(os.path.dirname(__file__), "..", "tests/golden/north_sea_mesh.npz")), a.k)
 if not a.nosfc:
@@ -45,20 +52,20 @@ def run(label, alg_bytes):
     print(f"{label}: {ms:.4f} ms/stage  {nt/ms/1e6:.2f} Gtri-stage/s  alg {alg_bytes*nt/ms/1e6:.0f} GB/s "
           f"({alg_bytes*nt/ms/1e6/6551.0*100:.1f}% of 6551.0)  {9*nt/(3*ms)/1e3:.0f} Mdof-upd/s", flush=True)
 
-if a.mode in ("all", "linear"):
+if sel("linear"):
     eng.set_option(L.OPT_NONLINEAR, 0)
     run("linear closed", 228)
-if a.mode in ("all", "nonlinear"):
+if sel("nonlinear"):
     eng.set_option(L.OPT_NONLINEAR, 1)
     run("nonlinear+LF closed", 228)
-if a.mode in ("all", "northsea"):
+if sel("northsea"):
     eng.set_option(L.OPT_NONLINEAR, 1)
     eng.set_field(L.F_MANNING, 0.03 + 0 * X)
     eng.set_field(L.F_CORIOLIS, 1.2e-4 + 1e-11 * Y)
     eng.set_bc(0, 100, L.BC_ELEV | L.BC_UV, [0.0, 0, 0, 0, 0, 0])
     eng.set_bc_array(0, 100, L.BC_ELEV, np.zeros((m.n_bfacets, 2)))
     run("north sea (nonlinear+LF+Manning+Coriolis+tide)", 236)
-if a.mode in ("all", "northsea_wd"):
+if sel("northsea_wd"):
     eng.set_option(L.OPT_NONLINEAR, 1)
     eng.set_field(L.F_MANNING, 0.03 + 0 * X)
     eng.set_field(L.F_CORIOLIS, 1.2e-4 + 1e-11 * Y)
@@ -66,7 +73,7 @@ if a.mode in ("all", "northsea_wd"):
     eng.set_bc_array(0, 100, L.BC_ELEV, np.zeros((m.n_bfacets, 2)))
     eng.set_option(L.OPT_WETTING_DRYING, 1)
     run("north sea + wetting-drying", 236)
-if a.mode in ("all", "northsea_wd_visc"):
+if sel("northsea_wd_visc"):
     eng.set_option(L.OPT_NONLINEAR, 1)
     eng.set_field(L.F_MANNING, 0.03 + 0 * X)
     eng.set_field(L.F_CORIOLIS, 1.2e-4 + 1e-11 * Y)

@@ -43,6 +43,14 @@ __host__ __device__ inline size_t tb_ids_offset(const TbPatchLayout &pl);
 // ------------------------------------------------------------------ constants
 __constant__ double c_qlam[TB_MAX_QUAD][3];
 __constant__ double c_qw[TB_MAX_QUAD];
+// The default degree-3 rule (and FIAT's) is ONE symmetric orbit: its six points are the permutations of a single
+// barycentric triple (a, b, c), all weights equal.  The specialised stage kernels use that structure (tb_set_quadrature
+// verifies it; any other rule is served by the generic kernel):  c_qsym = {a - c, b - c, c, weight}, and at point k
+// node tb_quad_ia(k) carries a, node tb_quad_ib(k) carries b.
+__constant__ double c_qsym[4];
+static bool g_quad_sym = false;
+__host__ __device__ constexpr int tb_quad_ia(int k) { return k == 0 ? 1 : k == 1 ? 1 : k == 2 ? 2 : k == 3 ? 0 : k == 4 ? 2 : 0; }
+__host__ __device__ constexpr int tb_quad_ib(int k) { return k == 0 ? 2 : k == 1 ? 0 : k == 2 ? 1 : k == 3 ? 1 : k == 4 ? 0 : 2; }
 
 __global__ void test_math_kernel(const double *x, double *out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
         }
         {
             // ExternalPressureGradientTerm cell part (shallowwater_eq.py:361): +g*eta*div(psi)
-            const double c = -g * se * (1.0 / 6.0);   // g * (se/3) * (-N/2)
+            const double c = (g * (-1.0 / 6.0)) * se;   // g * (se/3) * (-N/2)
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 Rux[a] += c * Nx[a];
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             Wx *= (-1.0 / 24.0);
             Wy *= (-1.0 / 24.0);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) Re[a] += Nx[a] * Wx + Ny[a] * Wy;
+            for (int a = 0; a < 3; ++a) Re[a] = fma(Nx[a], Wx, fma(Ny[a], Wy, Re[a]));
         }
         if (NONLIN && adv_on) {
             // HorizontalAdvectionTerm cell part (:478): +div(outer(psi,u)).u
@@ -393,17 +401,19 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             double Txx = 0, Txy = 0, Tyx = 0, Tyy = 0, D = 0;
 #pragma unroll
             for (int bb = 0; bb < 3; ++bb) {
-                Txx += ux[bb] * wx[bb];
-                Txy += ux[bb] * wy[bb];
-                Tyx += uy[bb] * wx[bb];
-                Tyy += uy[bb] * wy[bb];
-                D += Nx[bb] * ux[bb] + Ny[bb] * uy[bb];
+                Txx = fma(ux[bb], wx[bb], Txx);
+                Txy = fma(ux[bb], wy[bb], Txy);
+                Tyx = fma(uy[bb], wx[bb], Tyx);
+                Tyy = fma(uy[bb], wy[bb], Tyy);
+                D = fma(Nx[bb], ux[bb], fma(Ny[bb], uy[bb], D));
             }
-            D *= (-1.0 / 24.0);          // (-1/2) * (1/12)
+            // the common factor (-1/2) * (1/12) once on T and D instead of once per node
+            Txx *= (-1.0 / 24.0); Txy *= (-1.0 / 24.0); Tyx *= (-1.0 / 24.0); Tyy *= (-1.0 / 24.0);
+            D *= (-1.0 / 24.0);
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                Rux[a] += (-1.0 / 24.0) * (Nx[a] * Txx + Ny[a] * Tyx) + D * wx[a];
-                Ruy[a] += (-1.0 / 24.0) * (Nx[a] * Txy + Ny[a] * Tyy) + D * wy[a];
+                Rux[a] = fma(Nx[a], Txx, fma(Ny[a], Tyx, fma(D, wx[a], Rux[a])));
+                Ruy[a] = fma(Nx[a], Txy, fma(Ny[a], Tyy, fma(D, wy[a], Ruy[a])));
             }
         }
         const double A = 0.5 * twoA;
@@ -422,8 +432,8 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
                 // int f w phi_a = A/60 [F W + f_a W + sum f_b w_b + F w_a + 2 f_a w_a] = A/60 [bx + f_a (W + w_a) + F w_a + f_a w_a]
                 const double ix = bx + f[a] * (wx[a] + ux[a]) + F * ux[a];
                 const double iy = by + f[a] * (wy[a] + uy[a]) + F * uy[a];
-                Rux[a] += c * iy;
-                Ruy[a] -= c * ix;
+                Rux[a] = fma(c, iy, Rux[a]);
+                Ruy[a] = fma(-c, ix, Ruy[a]);
             }
         }
         if (has_lin) {
@@ -582,14 +592,43 @@ __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_c
             const int nq = SP::generic ? prm.nquad : 6;
             double HUx = 0.0, HUy = 0.0;
             double Gdm[3] = {0, 0, 0};
+            const double gA = g * A;
+            // Specialised kernels, symmetric rule (c_qsym): a P1 field f at point k is
+            //   c sum_n f_n + (a - c) f_ia(k) + (b - c) f_ib(k) = fma(b - c, f_ib, P_ia),  P_n = fma(a - c, f_n, c sum_n f_n)
+            // -- 10 operations per field for the six points instead of 18 -- and the common weight leaves the loop.
+            const double qac = c_qsym[0], qbc = c_qsym[1], qc = c_qsym[2], qws = c_qsym[3];
+            double Pu[3] = {0, 0, 0}, Pv[3] = {0, 0, 0}, Ph[3] = {0, 0, 0}, Pm[3] = {0, 0, 0}, Ptx[3] = {0, 0, 0},
+                   Pty[3] = {0, 0, 0};
+            if (!SP::generic) {
+                const double cu = qc * sux, cv_ = qc * suy, ch = qc * (hl[0] + hl[1] + hl[2]);
+                const double cm = qc * (mu[0] + mu[1] + mu[2]);
+                const double ctx_ = qc * (twx[0] + twx[1] + twx[2]), cty_ = qc * (twy[0] + twy[1] + twy[2]);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    Pu[a] = fma(qac, ux[a], cu);
+                    Pv[a] = fma(qac, uy[a], cv_);
+                    Ph[a] = fma(qac, hl[a], ch);
+                    Pm[a] = fma(qac, mu[a], cm);
+                    Ptx[a] = fma(qac, twx[a], ctx_);
+                    Pty[a] = fma(qac, twy[a], cty_);
+                }
+            }
 TB_UNROLL(TB_QUAD_UNROLL)
             for (int qd = 0; qd < (SP::generic ? TB_MAX_QUAD : 6); ++qd) {
                 if (SP::generic && qd >= nq) break;
                 const double l0 = c_qlam[qd][0], l1 = c_qlam[qd][1], l2 = c_qlam[qd][2];
-                const double w = c_qw[qd] * A;
-                const double uq = l0 * ux[0] + l1 * ux[1] + l2 * ux[2];
-                const double vq = l0 * uy[0] + l1 * uy[1] + l2 * uy[2];
-                double Hq = l0 * hl[0] + l1 * hl[1] + l2 * hl[2];
+                const double wq = SP::generic ? c_qw[qd] : qws;
+                const double w = wq * A;
+                double uq, vq, Hq;
+                if constexpr (SP::generic) {
+                    uq = l0 * ux[0] + l1 * ux[1] + l2 * ux[2];
+                    vq = l0 * uy[0] + l1 * uy[1] + l2 * uy[2];
+                    Hq = l0 * hl[0] + l1 * hl[1] + l2 * hl[2];
+                } else {
+                    uq = fma(qbc, ux[tb_quad_ib(qd)], Pu[tb_quad_ia(qd)]);
+                    vq = fma(qbc, uy[tb_quad_ib(qd)], Pv[tb_quad_ia(qd)]);
+                    Hq = fma(qbc, hl[tb_quad_ib(qd)], Ph[tb_quad_ia(qd)]);
+                }
                 double gfac = 1.0;           // dH/dhl of the wetting-drying depth (grad-depth viscosity term)
                 if (NONLIN) {
                     double a2q = a2;
@@ -606,44 +645,52 @@ TB_UNROLL(TB_QUAD_UNROLL)
                         Hq = wd_depth(Hq, wd_on, a2q);
                     }
                 }
-                double sx = 0, sy = 0;   // momentum source density at the point
+                double sx = 0, sy = 0;   // w * momentum source density at the point (the weight rides in the factors)
                 if (has_man || has_cd || has_nik) {
-                    const double s2 = uq * uq + vq * vq + prm.eps2;
-                    const double umag = s2 > 0.0 ? s2 * tb_rsqrt(s2) : 0.0;
+                    const double s2 = fma(uq, uq, fma(vq, vq, prm.eps2));
+                    const double umag = s2 > 0.0 ? tb_sqrt(s2) : 0.0;
                     double k;
                     if (has_man) {
-                        const double m = l0 * mu[0] + l1 * mu[1] + l2 * mu[2];
+                        double m;
+                        if constexpr (SP::generic) m = l0 * mu[0] + l1 * mu[1] + l2 * mu[2];
+                        else m = fma(qbc, mu[tb_quad_ib(qd)], Pm[tb_quad_ia(qd)]);
                         const double r = tb_rcbrt(Hq);             // H^(-1/3)
-                        const double r2 = r * r;
-                        k = g * m * m * (r2 * r2) * umag;          // g mu^2 / H^(1/3) * |u| / H
+                        const double mr = m * (r * r);
+                        k = (wq * -gA) * (mr * mr) * umag;         // -w g mu^2 / H^(1/3) * |u| / H = -w g (mu H^(-2/3))^2 |u|
                         if (gd_merge) {
                             // (:611-612) k = w nu (dH/dhl) / H with 1/H = (H^(-1/3))^3
-                            const double kk = w * (l0 * gdnu[0] + l1 * gdnu[1] + l2 * gdnu[2]) * gfac * (r2 * r);
+                            const double kk = w * (l0 * gdnu[0] + l1 * gdnu[1] + l2 * gdnu[2]) * gfac * (r * r * r);
                             Gdm[0] = fma(l0, kk, Gdm[0]); Gdm[1] = fma(l1, kk, Gdm[1]); Gdm[2] = fma(l2, kk, Gdm[2]);
                         }
                     } else if (has_nik) {
                         // C_D = 2 kappa^2 / ln(11.036 H / k_s)^2 where H > k_s, else 0 (:697)
                         const double ks = l0 * cdn[0] + l1 * cdn[1] + l2 * cdn[2];
                         const double lg = log(11.036 * Hq / ks);
-                        k = Hq > ks ? 2.0 * prm.kappa * prm.kappa / (lg * lg) * umag / Hq : 0.0;
+                        k = Hq > ks ? -w * (2.0 * prm.kappa * prm.kappa / (lg * lg) * umag / Hq) : 0.0;
                     } else {
-                        k = (l0 * cdn[0] + l1 * cdn[1] + l2 * cdn[2]) * umag * tb_rcp(Hq);
+                        k = -w * (l0 * cdn[0] + l1 * cdn[1] + l2 * cdn[2]) * umag * tb_rcp(Hq);
                     }
-                    sx -= k * uq;
-                    sy -= k * vq;
+                    sx = k * uq;      // k carries the sign of the drag
+                    sy = k * vq;
                 }
                 if (has_wind) {
-                    const double k = irho * tb_rcp(Hq);
-                    sx += k * (l0 * twx[0] + l1 * twx[1] + l2 * twx[2]);
-                    sy += k * (l0 * twy[0] + l1 * twy[1] + l2 * twy[2]);
+                    const double k = (w * irho) * tb_rcp(Hq);
+                    double tx, ty;
+                    if constexpr (SP::generic) {
+                        tx = l0 * twx[0] + l1 * twx[1] + l2 * twx[2];
+                        ty = l0 * twy[0] + l1 * twy[1] + l2 * twy[2];
+                    } else {
+                        tx = fma(qbc, twx[tb_quad_ib(qd)], Ptx[tb_quad_ia(qd)]);
+                        ty = fma(qbc, twy[tb_quad_ib(qd)], Pty[tb_quad_ia(qd)]);
+                    }
+                    sx = fma(k, tx, sx);
+                    sy = fma(k, ty, sy);
                 }
-                sx *= w;
-                sy *= w;
                 Rux[0] += l0 * sx; Rux[1] += l1 * sx; Rux[2] += l2 * sx;
                 Ruy[0] += l0 * sy; Ruy[1] += l1 * sy; Ruy[2] += l2 * sy;
                 if (NONLIN && wd_on) {
                     // int H u over the cell by the rule (the test-function gradients are constant: applied after the loop)
-                    const double wH = c_qw[qd] * Hq;
+                    const double wH = SP::generic ? c_qw[qd] * Hq : Hq;      // symmetric rule: the weight is applied after the loop
                     HUx = fma(wH, uq, HUx);
                     HUy = fma(wH, vq, HUy);
                 }
@@ -657,16 +704,18 @@ TB_UNROLL(TB_QUAD_UNROLL)
             }
             if (NONLIN && wd_on) {
                 // grad(phi_a).(int H u)  with A grad(phi_a) = -N_a/2
-                HUx *= -0.5;
-                HUy *= -0.5;
+                const double hs = SP::generic ? -0.5 : -0.5 * qws;
+                HUx *= hs;
+                HUy *= hs;
 #pragma unroll
-                for (int a = 0; a < 3; ++a) Re[a] += Nx[a] * HUx + Ny[a] * HUy;
+                for (int a = 0; a < 3; ++a) Re[a] = fma(Nx[a], HUx, fma(Ny[a], HUy, Re[a]));
             }
         }
 
         // ---------------- facet terms, 2-point Gauss per facet ----------------
         cp_async_wait_group0();
         __syncthreads();      // every thread's halo copies have landed
+        const double g_half = 0.5 * g, g_quarter = 0.25 * g, lf_quarter = 0.25 * prm.lf_sigma;
         if (has_visc) {
             // gradients of the halo cells, one thread each, then visible to everybody
             const uint16_t *hcv = reinterpret_cast<const uint16_t *>(blk + prm.pl.off_hcv);
@@ -691,8 +740,6 @@ TB_UNROLL(TB_QUAD_UNROLL)
             const double il = tb_rsqrt(len2);
             const double len = len2 * il;
             const int code = cn[i];
-            // flux accumulators tested against phi_p and phi_q
-            double Fpx = 0, Fpy = 0, Fpe = 0, Fqx = 0, Fqy = 0, Fqe = 0;
             if (code >= 0) {
                 const int lf = code & 3;
                 const double *nr = S + (code >> 2) * 9;
@@ -738,7 +785,7 @@ TB_UNROLL(TB_GP_UNROLL)
                             a2g = ag * ag;
                         }
                         const double sig = (hlK + hlN) + (tb_sqrt(fma(hlK, hlK, a2g)) + tb_sqrt(fma(hlN, hlN, a2g)));   // 4*hbar
-                        gh = (0.25 * g) * sig;
+                        gh = g_quarter * sig;
                         hh = 0.125 * sig;
                     } else {
                         const double hbar = NONLIN ? fma(0.5, esum, bg) : bg;
@@ -751,7 +798,7 @@ TB_UNROLL(TB_GP_UNROLL)
                     const double dun = fma(dux, nxs, duy * nys);
                     const double usN = fma(usx, nxs, usy * nys);
                     // PG (:363-366): g*(avg(eta) + sqrt(h/g)*jump(u,n)) n
-                    const double t = fma(c * il, dun, (0.5 * g) * esum);
+                    const double t = fma(c * il, dun, g_half * esum);
                     // HUDiv (:424-427): h*(avg(u) + sqrt(g/h)*jump(eta,n)).n
                     const double fe = fma(c * len, ediff, hh * usN);
                     double fx, fy;
@@ -759,7 +806,7 @@ TB_UNROLL(TB_GP_UNROLL)
                         // advection (:480-488): avg(u) (u_K.n) + gamma (u_K - u_N);  u_K.N = (us.N + du.N)/2
                         const double hu = 0.25 * (usN + dun);
                         if (lf_on) {
-                            const double gam = (0.25 * prm.lf_sigma) * fabs(usN);
+                            const double gam = lf_quarter * fabs(usN);
                             fx = fma(t, nxs, fma(hu, usx, gam * dux));
                             fy = fma(t, nys, fma(hu, usy, gam * duy));
                         } else {
@@ -783,8 +830,9 @@ TB_UNROLL(TB_GP_UNROLL)
                         vDx += 0.5 * nug * dux;
                         vDy += 0.5 * nug * duy;
                     }
-                    Fpx += hp_ * fx; Fpy += hp_ * fy; Fpe += hp_ * fe;
-                    Fqx += hq_ * fx; Fqy += hq_ * fy; Fqe += hq_ * fe;
+                    // tested against phi_p and phi_q, straight into the residual (no separate flux accumulators)
+                    Rux[p] = fma(-hp_, fx, Rux[p]); Ruy[p] = fma(-hp_, fy, Ruy[p]); Re[p] = fma(-hp_, fe, Re[p]);
+                    Rux[q] = fma(-hq_, fx, Rux[q]); Ruy[q] = fma(-hq_, fy, Ruy[q]); Re[q] = fma(-hq_, fe, Re[q]);
                 }
                 if (has_visc) {
                     // -inner(avg(grad(psi)), stress_jump) (:588): all three nodes, d_j phi_a = -N_a,j/2A
@@ -807,6 +855,7 @@ TB_UNROLL(TB_GP_UNROLL)
                 const int op = prm.bc.slots[slot].opcode;
                 const bool closed = (op & (TB_BC_ELEV | TB_BC_UV | TB_BC_UN | TB_BC_FLUX)) == 0;
                 double bDx = 0, bDy = 0;
+                double Fpx = 0, Fpy = 0, Fpe = 0, Fqx = 0, Fqy = 0, Fqe = 0;   // boundary flux tested against phi_p, phi_q
 #pragma unroll 1
                 for (int gp = 0; gp < 2; ++gp) {
                     const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
@@ -879,24 +928,25 @@ TB_UNROLL(TB_GP_UNROLL)
                         Ruy[a] -= itA * ty;
                     }
                 }
+                Rux[p] -= Fpx; Ruy[p] -= Fpy; Re[p] -= Fpe;
+                Rux[q] -= Fqx; Ruy[q] -= Fqy; Re[q] -= Fqe;
             }
-            Rux[p] -= Fpx; Ruy[p] -= Fpy; Re[p] -= Fpe;
-            Rux[q] -= Fqx; Ruy[q] -= Fqy; Re[q] -= Fqe;
         }
 
         // ---------------- P1 mass inverse (equation.py:99-105) and Shu-Osher update ----------------
         // M_K^-1 = (3/A)(4 I - 1 1^T)
-        const double mi = 6.0 * tb_rcp(twoA) * prm.bdt;
-        const double sRx = Rux[0] + Rux[1] + Rux[2], sRy = Ruy[0] + Ruy[1] + Ruy[2], sRe = Re[0] + Re[1] + Re[2];
+        const double mi = 6.0 * tb_rcp(twoA) * prm.bdt, mi4 = 4.0 * mi;
+        const double sRx = mi * (Rux[0] + Rux[1] + Rux[2]), sRy = mi * (Ruy[0] + Ruy[1] + Ruy[2]),
+                     sRe = mi * (Re[0] + Re[1] + Re[2]);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            res[2 * a] = prm.a1 * ux[a] + mi * (4.0 * Rux[a] - sRx);
-            res[2 * a + 1] = prm.a1 * uy[a] + mi * (4.0 * Ruy[a] - sRy);
-            res[6 + a] = prm.a1 * et[a] + mi * (4.0 * Re[a] - sRe);
+            res[2 * a] = fma(mi4, Rux[a], fma(prm.a1, ux[a], -sRx));
+            res[2 * a + 1] = fma(mi4, Ruy[a], fma(prm.a1, uy[a], -sRy));
+            res[6 + a] = fma(mi4, Re[a], fma(prm.a1, et[a], -sRe));
         }
         if (prm.u0) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) res[k] += prm.a0 * O[tid * 9 + k];
+            for (int k = 0; k < 9; ++k) res[k] = fma(prm.a0, O[tid * 9 + k], res[k]);
         }
         if (prm.partials && active) {
             // fused print_state / volume diagnostics of the state this launch produces (same closed forms as
@@ -975,15 +1025,17 @@ int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear) {
     const bool rare = p.cd.mode || p.pa.mode >= 2 || p.msrc.mode || p.vsrc.mode || !p.adv_on || p.nik.mode || p.wda.mode == 2 ||
                       dg_coef;
     if (rare) return 0;
+    // the specialised kernels with a cell rule are written for the symmetric 6-point rule (c_qsym)
+    const bool quad6 = p.nquad == 6 && g_quad_sym;
     if (p.visc.mode) {
-        if (nonlinear && p.lf_on && p.man.mode && p.cor.mode && !p.lin.mode && !p.wind.mode && p.nquad == 6)
+        if (nonlinear && p.lf_on && p.man.mode && p.cor.mode && !p.lin.mode && !p.wind.mode && quad6)
             return p.wd_on ? 6 : 5;
         return 0;
     }
-    if (!nonlinear && p.cor.mode && p.wind.mode && p.lin.mode && !p.man.mode && !p.wd_on && p.nquad == 6) return 4;
+    if (!nonlinear && p.cor.mode && p.wind.mode && p.lin.mode && !p.man.mode && !p.wd_on && quad6) return 4;
     if (p.lin.mode || p.wind.mode) return 0;
     if (!p.man.mode && !p.cor.mode && !p.wd_on && (!nonlinear || p.lf_on)) return 1;
-    if (nonlinear && p.lf_on && p.man.mode && p.cor.mode && p.nquad == 6) return p.wd_on ? 3 : 2;
+    if (nonlinear && p.lf_on && p.man.mode && p.cor.mode && quad6) return p.wd_on ? 3 : 2;
     return 0;
 }
 
@@ -1010,7 +1062,22 @@ cudaError_t tb_launch_swe_stage(const TbSweParams &p, bool nonlinear, int n_patc
 cudaError_t tb_set_quadrature(int n, const double *lam, const double *w) {
     cudaError_t e = cudaMemcpyToSymbol(c_qlam, lam, sizeof(double) * 3 * n);
     if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_qw, w, sizeof(double) * n);
+    if ((e = cudaMemcpyToSymbol(c_qw, w, sizeof(double) * n)) != cudaSuccess) return e;
+    // symmetric structure the specialised kernels rely on: point k = (a at node ia(k), b at node ib(k), c at the third
+    // node) for one triple (a, b, c), equal weights
+    bool sym = (n == 6);
+    double v[4] = {0, 0, 0, 0};
+    if (sym) {
+        const double a = lam[3 * 3 + 0], b = lam[3 * 3 + 1], c = lam[3 * 3 + 2];      // point 3 is (a, b, c)
+        for (int k = 0; k < 6 && sym; ++k) {
+            const int ia = tb_quad_ia(k), ib = tb_quad_ib(k), ic = 3 - ia - ib;
+            sym = fabs(lam[3 * k + ia] - a) < 1e-14 && fabs(lam[3 * k + ib] - b) < 1e-14 && fabs(lam[3 * k + ic] - c) < 1e-14 &&
+                  fabs(w[k] - w[0]) < 1e-15;
+        }
+        v[0] = a - c; v[1] = b - c; v[2] = c; v[3] = w[0];
+    }
+    g_quad_sym = sym;
+    return cudaMemcpyToSymbol(c_qsym, v, sizeof(v));
 }
 
 // ------------------------------------------------------------------ layout conversion
