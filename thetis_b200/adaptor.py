@@ -133,8 +133,9 @@ def _family_of_name(fam):
 
 def _mesh2d_from_firedrake(mesh):
     """
-    Build a `Mesh2D` from a real Firedrake mesh.  UNTESTED HERE (no Firedrake);
-    written against the attribute names listed in SURVEY.md 8b.
+    Build a `Mesh2D` from a real Firedrake mesh.  Written against the attribute names listed in SURVEY.md 8b;
+    exercised against a Firedrake-shaped look-alike (tests/test_firedrake_lookalike_mesh.py), never against
+    Firedrake itself (not installable here).
     """
     import firedrake as fd  # noqa: F401  (ImportError if absent, by design)
     coords_f = mesh.coordinates
