@@ -2,11 +2,13 @@
 Generates tests/golden/reference_residuals.npz by EXECUTING THE REFERENCE'S OWN SOURCE on the cases of
 tests/reference_cases.py:
 
-* thetis/shallowwater_eq.py   ShallowWaterEquations.residual('all', ...)  -- every term class, get_bnd_functions,
-                              impose_dynamic_bnd -- and Equation.mass_term            (equation.py:99-105)
+* thetis/shallowwater_eq.py   ShallowWaterEquations / ModeSplit2DEquations .residual('all', ...)  -- every term class,
+                              get_bnd_functions, impose_dynamic_bnd -- and Equation.mass_term     (equation.py:99-105)
 * thetis/utility.py           DepthExpression, compute_boundary_length, tensor_jump, element_continuity
 * thetis/tracer_eq_2d.py      TracerEquation2D (non-conservative and conservative terms)
-* thetis/rungekutta.py        SSPRK33 = ERKGenericShuOsher + SSPRK33Abstract: whole steps through `advance()`
+* thetis/rungekutta.py        SSPRK33 = ERKGenericShuOsher + SSPRK33Abstract, the Butcher-form ERKGeneric schemes
+                              (ERKLSPUM2, ERKLPUM2, ERKMidpoint, ERKEuler) and thetis/timeintegrator.py ForwardEuler:
+                              whole steps through `advance()`
 
 are imported from /root/reference (tests/golden/refenv.py) and run on `ufl_lite`, the numpy stand-in for the
 Firedrake / UFL operators those files use (Firedrake itself is not installable here).  The stored numbers are
@@ -120,7 +122,10 @@ def _solve_mass(mass_form, rhs_form, space):
 
 def swe_equation(st):
     depth, opts, o = st.depth_and_options()
-    eq = sweq.ShallowWaterEquations(st.V, depth, opts)
+    if st.case.get("equation") == "modesplit":
+        eq = sweq.ModeSplit2DEquations(st.V, depth, opts)
+    else:
+        eq = sweq.ShallowWaterEquations(st.V, depth, opts)
     fields = {"lax_friedrichs_velocity_scaling_factor": U.Constant(1.0)}          # solver2d.py:546-558 default
     for name, spec in st.case.get("fields", {}).items():
         fields[name] = st.obj(spec)
@@ -176,9 +181,13 @@ def run_steps(name, spec, seed):
     assert not o["use_wetting_and_drying"]
     sol, uv, eta = st.swe_solution(seed)
     topt = types.SimpleNamespace(ad_block_tag=None, solver_parameters={})
-    ti = rk.SSPRK33(eq, sol, fields, spec["dt"], topt, bnd)
+    kind = spec.get("integrator", "SSPRK33")
+    cls = MODS["timeintegrator"].ForwardEuler if kind == "ForwardEuler" else getattr(rk, kind)
+    ti = cls(eq, sol, fields, spec["dt"], topt, bnd)
     ti.initialize(sol)
     base = {}
+    drag = fields.get("linear_drag_coefficient") if spec["forcing"] == "lagged_drag" else None
+    drag_base = drag.dat.data.copy() if drag is not None else None
     if spec["forcing"] == "elev_const":
         for mk, funcs in bnd.items():
             if "elev" in funcs:
@@ -197,6 +206,9 @@ def run_steps(name, spec, seed):
             else:
                 el.dat.data[...] = b * f
                 el.dat.dat_version += 1
+        if drag is not None:
+            drag.dat.data[...] = drag_base * f
+            drag.dat.dat_version += 1
 
     t = 0.0
     for _ in range(spec["n_steps"]):

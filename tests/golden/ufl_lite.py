@@ -1006,7 +1006,7 @@ class Function(Expr):
         return [f.dat.data.copy() for f in self.subfunctions]
 
     def assign(self, other):
-        vals = _nodal(other)
+        vals = other if isinstance(other, list) else _nodal(other)
         if isinstance(vals, float):
             for f in self.subfunctions:
                 f.dat.data[...] = vals
@@ -1017,6 +1017,11 @@ class Function(Expr):
                 f.dat.data[...] = v
                 f.dat.dat_version += 1
         return self
+
+    def __iadd__(self, other):
+        if isinstance(other, numbers.Number) and other == 0:
+            return self
+        return self.assign(_nodal_add(self.nodal(), _nodal(other)))
 
     def interpolate(self, expr):
         """nodal interpolation (P1 / P1DG): the expression at the three vertices of every cell"""

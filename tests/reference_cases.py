@@ -159,6 +159,16 @@ SWE_CASES["viscosity_wetting_drying_grad_depth"] = dict(
     bath=P("bath_slope"), fields={"viscosity_h": P("visc"), "manning_drag_coefficient": C(0.025)},
     bnd={1: {"elev": P("elev_bc"), "uv": P("uv_bc")}})
 
+# ModeSplit2DEquations (shallowwater_eq.py:931-966): pressure gradient, Coriolis, momentum source, atmospheric pressure
+# and the continuity terms only -- `equation="modesplit"` selects that class on the reference side and
+# include_momentum_advection=False on the oracle side (fields the class has no term for must be absent)
+SWE_CASES["modesplit_open_bcs"] = dict(mesh=RECT, bath=P("bath_wavy"), equation="modesplit",
+                                       fields={"coriolis": P("coriolis"), "momentum_source": P("msrc"),
+                                               "atmospheric_pressure": P("pressure"), "volume_source": P("vsrc")},
+                                       bnd={1: {"elev": C(0.3), "uv": C((0.2, -0.1))}, 2: {"un": C(-0.2)}})
+SWE_CASES["modesplit_closed_unstructured"] = dict(mesh=DELAUNAY, bath=P("bath_wavy"), equation="modesplit",
+                                                  fields={"coriolis": C(1.0e-4), "momentum_source": ("dg", 11, 0.0, 1.0e-4, 2)})
+
 TRACER_CASES = {
     "advection_closed_source": dict(mesh=RECT, bath=P("bath_wavy"), fields={"source": P("tsrc")}),
     "advection_bcs_lf": dict(mesh=RECT, bath=P("bath_wavy"), options=dict(use_lax_friedrichs_tracer=True),
@@ -186,6 +196,17 @@ STEP_CASES = {
     "ssprk33_tidal_constant": dict(case="open_bc_const_1_nonlinear", dt=4.0, n_steps=5, forcing="elev_const"),
     "ssprk33_tidal_function_manning": dict(case="open_bc_functions_1", dt=4.0, n_steps=5, forcing="elev_function"),
     "ssprk33_closed_linear": dict(case="linear_variable_depth_ragged", dt=6.0, n_steps=4, forcing=None),
+    # Butcher-form integrators (rungekutta.py:762-867, tableaux :350-392) and timeintegrator.ForwardEuler (:115-165,
+    # whose Function-valued coefficients lag one step: fields_old)
+    "erklspum2_tidal_function": dict(case="open_bc_functions_1", dt=4.0, n_steps=4, forcing="elev_function",
+                                     integrator="ERKLSPUM2"),
+    "erklpum2_tidal_constant": dict(case="open_bc_const_1_nonlinear", dt=5.0, n_steps=4, forcing="elev_const",
+                                    integrator="ERKLPUM2"),
+    "erkmidpoint_viscous": dict(case="viscosity_graddiv1_graddepth1", dt=1.0, n_steps=4, forcing="elev_const",
+                                integrator="ERKMidpoint"),
+    "erkeuler_closed": dict(case="nonlinear_lf_closed", dt=2.0, n_steps=5, forcing=None, integrator="ERKEuler"),
+    "forward_euler_lagged_drag": dict(case="quadratic_drag_const_linear_drag_field", dt=2.0, n_steps=5,
+                                      forcing="lagged_drag", integrator="ForwardEuler"),
 }
 
 

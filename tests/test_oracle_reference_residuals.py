@@ -29,6 +29,8 @@ TOL = 1e-12
 
 def _options(case, mesh):
     o = dict(case.get("options", {}))
+    if case.get("equation") == "modesplit":
+        o["include_momentum_advection"] = False
     al = o.get("wetting_and_drying_alpha")
     if isinstance(al, tuple):
         o["wetting_and_drying_alpha"] = RC.nodal_value(al, mesh)
@@ -89,9 +91,10 @@ def test_tracer_tendency_equals_the_reference_terms(name):
 
 
 @pytest.mark.parametrize("name", list(RC.STEP_CASES))
-def test_ssprk33_steps_equal_the_reference_integrator(name):
-    """whole steps: the reference's rungekutta.SSPRK33.advance (update_forcings at t + c_i dt, Shu-Osher stages, mass
-    solve per stage) against the oracle's stepper on the same forcing"""
+def test_whole_steps_equal_the_reference_integrators(name):
+    """whole steps: the reference's rungekutta.SSPRK33 / ERKLSPUM2 / ERKLPUM2 / ERKMidpoint / ERKEuler and
+    timeintegrator.ForwardEuler `advance()` (update_forcings at the stage times, stage combinations, one mass solve per
+    stage) against the oracle's steppers on the same forcing"""
     spec = RC.STEP_CASES[name]
     case = RC.SWE_CASES[spec["case"]]
     mesh = RC.build_mesh(case["mesh"])
@@ -106,11 +109,27 @@ def test_ssprk33_steps_equal_the_reference_integrator(name):
         for mk, b in base.items():
             orc.bnd[mk] = dict(orc.bnd[mk], elev=(b * f if isinstance(b, np.ndarray) else float(b) * f))
 
-    stp = ShuOsherStepper(orc, [uv, eta], spec["dt"])
-    t = 0.0
-    for _ in range(spec["n_steps"]):
-        stp.advance(t, update_forcings if spec["forcing"] else None)
-        t += spec["dt"]
+    kind = spec.get("integrator", "SSPRK33")
+    dt, t = spec["dt"], 0.0
+    if kind == "ForwardEuler":
+        # timeintegrator.py:115-165: update_forcings(t + dt), then one Euler step assembled with `fields_old`: the
+        # Function-valued drag coefficient is the one of the END OF THE PREVIOUS step, boundary data are live
+        drag_base = orc.fields["linear_drag_coefficient"].copy()
+        stp = ShuOsherStepper(orc, [uv, eta], dt, a=[[0]], b=[1.0], c=[0])
+        for _ in range(spec["n_steps"]):
+            drag_new = drag_base * RC.forcing_factor(t + dt)      # what update_forcings assigns to the Function
+            stp.advance(t)                                       # ... but the step still reads fields_old
+            orc.fields["linear_drag_coefficient"] = drag_new      # update_fields_old
+            t += dt
+    else:
+        if kind == "SSPRK33":
+            stp = ShuOsherStepper(orc, [uv, eta], dt)
+        else:
+            from oracle.swe_oracle import ButcherStepper, ERK_TABLEAUX
+            stp = ButcherStepper(orc, [uv, eta], dt, *ERK_TABLEAUX[kind])
+        for _ in range(spec["n_steps"]):
+            stp.advance(t, update_forcings if spec["forcing"] else None)
+            t += dt
     eu, ee = _rel(uv, GOLD[f"step/{name}/uv"]), _rel(eta, GOLD[f"step/{name}/eta"])
     assert eu < TOL and ee < TOL, (eu, ee)
 
