@@ -9,6 +9,8 @@ tests/reference_cases.py:
 * thetis/rungekutta.py        SSPRK33 = ERKGenericShuOsher + SSPRK33Abstract, the Butcher-form ERKGeneric schemes
                               (ERKLSPUM2, ERKLPUM2, ERKMidpoint, ERKEuler) and thetis/timeintegrator.py ForwardEuler:
                               whole steps through `advance()`
+* thetis/coupled_timeintegrator_2d.py   GeneralCoupledTimeIntegrator2D.advance: SWE step, then the tracer step with the
+                              new velocity (driven through a stand-in for the FlowSolver2d attributes it reads)
 
 are imported from /root/reference (tests/golden/refenv.py) and run on `ufl_lite`, the numpy stand-in for the
 Firedrake / UFL operators those files use (Firedrake itself is not installable here).  The stored numbers are
@@ -219,6 +221,86 @@ def run_steps(name, spec, seed):
                 eta=sol.subfunctions[1].dat.data.reshape(nt, 3).copy())
 
 
+class _FakeSolver:
+    """What coupled_timeintegrator_2d.CoupledTimeIntegrator2D reads from a FlowSolver2d; the two factory methods
+    restate solver2d.py:540-598 (which fields go to which integrator)."""
+
+    def __init__(self, st, swe_case, tr_case, dt, seed):
+        self.dt = dt
+        self.solve_tracer, self.sediment_model = True, None
+        depth, opts, o = st.depth_and_options()
+        trc = Setup(tr_case)
+        trc.m2, trc.mesh, trc.P1, trc.P1v, trc.H, trc.Uv, trc.V = st.m2, st.mesh, st.P1, st.P1v, st.H, st.Uv, st.V
+        _, topts, to = trc.depth_and_options()
+        for k in ("use_lax_friedrichs_tracer", "sipg_factor_tracer", "tracer"):
+            opts[k] = topts[k]
+        self.eq_sw = sweq.ShallowWaterEquations(st.V, depth, opts)
+        self.eq_tr = treq.TracerEquation2D("tracer_2d", st.H, depth, opts, None)
+        self.swe_fields = {"lax_friedrichs_velocity_scaling_factor": U.Constant(1.0)}
+        for name, spec in swe_case.get("fields", {}).items():
+            self.swe_fields[name] = st.obj(spec)
+        self.bnd_functions = {"shallow_water": st.bnd(), "tracer_2d": trc.bnd()}
+        sol, self.uv0, self.eta0 = st.swe_solution(seed)
+        rng = np.random.default_rng(seed + 100)
+        x = st.m2.coords[st.m2.cells]
+        self.c0 = 1.0 + 0.5 * np.sin(x[..., 0] / 900.0) * np.cos(x[..., 1] / 700.0) + 0.05 * rng.standard_normal(x.shape[:2])
+        q = U.Function(st.H, name="tracer_2d")
+        q.dat.data[...] = self.c0.reshape(-1)
+        self.fields = util.AttrDict(solution_2d=sol, tracer_2d=q)
+        tf = {k: trc.obj(v) for k, v in tr_case.get("fields", {}).items()}
+        sed = types.SimpleNamespace(solve_suspended_sediment=False, solve_exner=False)
+        self.options = util.AttrDict(
+            tracer_only=False, tracer_fields=["tracer_2d"], sediment_model_options=sed, tracer_picard_iterations=1,
+            use_limiter_for_tracers=False,
+            lax_friedrichs_tracer_scaling_factor=tf.get("lax_friedrichs_tracer_scaling_factor", U.Constant(1.0)),
+            tracer_advective_velocity_factor=tf.get("tracer_advective_velocity_factor", U.Constant(1.0)),
+            tracer={"tracer_2d": types.SimpleNamespace(diffusivity=tf.get("diffusivity_h"), source=tf.get("source"))},
+            swe_timestepper_options=types.SimpleNamespace(ad_block_tag=None, solver_parameters={}),
+            tracer_timestepper_options=types.SimpleNamespace(ad_block_tag=None, solver_parameters={}))
+
+    def get_swe_timestepper(self, integrator):                 # solver2d.py:541-572
+        return integrator(self.eq_sw, self.fields.solution_2d, self.swe_fields, self.dt,
+                          self.options.swe_timestepper_options, self.bnd_functions["shallow_water"])
+
+    def get_tracer_timestepper(self, integrator, system):      # solver2d.py:575-598
+        uv, elev = self.fields.solution_2d.subfunctions
+        fields = {"elev_2d": elev, "uv_2d": uv,
+                  "lax_friedrichs_tracer_scaling_factor": self.options.lax_friedrichs_tracer_scaling_factor,
+                  "tracer_advective_velocity_factor": self.options.tracer_advective_velocity_factor}
+        for label in system.split(","):
+            fields[f"diffusivity_h-{label}"] = self.options.tracer[label].diffusivity
+            fields[f"source-{label}"] = self.options.tracer[label].source
+        return integrator(self.eq_tr, self.fields[system], fields, self.dt, self.options.tracer_timestepper_options,
+                          self.bnd_functions.get(system, {}))
+
+
+def run_coupled(name, spec, seed):
+    swe_case, tr_case = RC.SWE_CASES[spec["swe"]], RC.TRACER_CASES[spec["tracer"]]
+    assert swe_case["mesh"] == tr_case["mesh"] and swe_case["bath"] == tr_case["bath"]
+    st = Setup(swe_case)
+    solver = _FakeSolver(st, swe_case, tr_case, spec["dt"], seed)
+    cti = MODS["coupled_timeintegrator_2d"].GeneralCoupledTimeIntegrator2D(
+        solver, {"shallow_water": rk.SSPRK33, "tracer": rk.SSPRK33})
+    cti.initialize(solver.fields.solution_2d)
+    bnd = solver.bnd_functions["shallow_water"]
+    base = {mk: float(f["elev"]) for mk, f in bnd.items() if "elev" in f} if spec["forcing"] else {}
+
+    def update_forcings(t):
+        for mk, b in base.items():
+            bnd[mk]["elev"].assign(b * RC.forcing_factor(t))
+
+    t = 0.0
+    for _ in range(spec["n_steps"]):
+        cti.advance(t, update_forcings if spec["forcing"] else None)
+        t += spec["dt"]
+    nt = st.m2.n_cells
+    sol = solver.fields.solution_2d
+    return dict(uv0=solver.uv0, eta0=solver.eta0, c0=solver.c0,
+                uv=sol.subfunctions[0].dat.data.reshape(nt, 3, 2).copy(),
+                eta=sol.subfunctions[1].dat.data.reshape(nt, 3).copy(),
+                c=solver.fields.tracer_2d.dat.data.reshape(nt, 3).copy())
+
+
 def main():
     out = {}
     for i, (name, case) in enumerate(RC.SWE_CASES.items()):
@@ -236,6 +318,11 @@ def main():
         for k, v in r.items():
             out[f"step/{name}/{k}"] = v
         print(f"step   {name:44s} |uv| {np.abs(r['uv']).max():.3e}  |eta| {np.abs(r['eta']).max():.3e}")
+    for i, (name, spec) in enumerate(RC.COUPLED_CASES.items()):
+        r = run_coupled(name, spec, seed=120 + i)
+        for k, v in r.items():
+            out[f"coupled/{name}/{k}"] = v
+        print(f"coupled {name:43s} |uv| {np.abs(r['uv']).max():.3e}  |c| {np.abs(r['c']).max():.3e}")
     path = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else os.path.join(HERE, "reference_residuals.npz")
     np.savez_compressed(path, **out)
     print(path, len(out), "arrays", os.path.getsize(path), "bytes")

@@ -2,6 +2,7 @@
 TEST INFRASTRUCTURE ONLY.  Imports the reference's own modules
 
     thetis/utility.py  equation.py  shallowwater_eq.py  tracer_eq_2d.py  timeintegrator.py  rungekutta.py
+    coupled_timeintegrator_2d.py
     physical_constants.py  field_defs.py  log.py
 
 from /root/reference and lets them run on top of `ufl_lite` (the numpy stand-in for `firedrake` / `ufl`): the stand-in
@@ -101,7 +102,8 @@ def install():
                       ("pyop2.profiling", prof), ("pyadjoint", pyad), ("pyadjoint.tape", tape), ("thetis", pkg)):
         sys.modules[name] = mod
     mods = {}
-    for name in ("utility", "equation", "shallowwater_eq", "tracer_eq_2d", "timeintegrator", "rungekutta"):
+    for name in ("utility", "equation", "shallowwater_eq", "tracer_eq_2d", "timeintegrator", "rungekutta",
+                 "coupled_timeintegrator_2d"):
         mods[name] = importlib.import_module("thetis." + name)
         assert os.path.realpath(mods[name].__file__).startswith(os.path.realpath(REF_ROOT)), mods[name].__file__
     mods["physical_constants"] = sys.modules["thetis.physical_constants"].physical_constants

@@ -210,6 +210,16 @@ STEP_CASES = {
 }
 
 
+# SWE step, then tracer step with the NEW velocity / elevation (coupled_timeintegrator_2d.py:94-105, the tracer's
+# `uv_2d` / `elev_2d` are the sub-functions of solution_2d, solver2d.py:580-598), update_forcings passed to both
+COUPLED_CASES = {
+    "coupled_ssprk33_advection": dict(swe="open_bc_const_1_nonlinear", tracer="advection_bcs_lf", dt=4.0, n_steps=4,
+                                      forcing="elev_const"),
+    "coupled_ssprk33_diffusion_unstructured": dict(swe="nonlinear_no_lf", tracer="diffusion_sipg", dt=2.0, n_steps=4,
+                                                   forcing=None),
+}
+
+
 def forcing_factor(t):
     """time dependence applied by `update_forcings(t)` in the step cases"""
     return 1.0 + 0.5 * np.sin(2.0 * np.pi * t / 40.0)

@@ -53,6 +53,7 @@ def test_every_case_has_reference_output():
     assert have == set(RC.SWE_CASES)
     assert {k.split("/")[1] for k in GOLD.files if k.startswith("tracer/")} == set(RC.TRACER_CASES)
     assert {k.split("/")[1] for k in GOLD.files if k.startswith("step/")} == set(RC.STEP_CASES)
+    assert {k.split("/")[1] for k in GOLD.files if k.startswith("coupled/")} == set(RC.COUPLED_CASES)
 
 
 @pytest.mark.parametrize("name", list(RC.SWE_CASES))
@@ -132,6 +133,41 @@ def test_whole_steps_equal_the_reference_integrators(name):
             t += dt
     eu, ee = _rel(uv, GOLD[f"step/{name}/uv"]), _rel(eta, GOLD[f"step/{name}/eta"])
     assert eu < TOL and ee < TOL, (eu, ee)
+
+
+@pytest.mark.parametrize("name", list(RC.COUPLED_CASES))
+def test_coupled_swe_then_tracer_steps_equal_the_reference(name):
+    """coupled_timeintegrator_2d.CoupledTimeIntegrator2D.advance executed from the reference tree: the SWE step, then
+    the tracer step reading the NEW velocity / elevation, `update_forcings` handed to both integrators"""
+    spec = RC.COUPLED_CASES[name]
+    swe_case, tr_case = RC.SWE_CASES[spec["swe"]], RC.TRACER_CASES[spec["tracer"]]
+    mesh = RC.build_mesh(swe_case["mesh"])
+    uv, eta, c = (GOLD[f"coupled/{name}/{k}"].copy() for k in ("uv0", "eta0", "c0"))
+    orc = _swe_oracle(swe_case, mesh)
+    o = _options(tr_case, mesh)
+    fields = {k: RC.nodal_value(v, mesh) for k, v in tr_case.get("fields", {}).items()}
+    bnd = {mk: {tag: RC.nodal_value(v, mesh) for tag, v in funcs.items()} for mk, funcs in tr_case.get("bnd", {}).items()}
+    tr = TracerOracle(orc, bnd_conditions=bnd, fields=fields,
+                      options={k: v for k, v in o.items()
+                               if k in ("use_lax_friedrichs_tracer", "use_conservative_form", "sipg_factor_tracer")})
+    tr.set_velocity(uv, eta)                  # the same arrays the SWE stepper updates in place (solver2d.py:580-583)
+    base = {mk: funcs["elev"] for mk, funcs in orc.bnd.items() if "elev" in funcs} if spec["forcing"] else {}
+
+    def update_forcings(t):
+        for mk, b in base.items():
+            orc.bnd[mk] = dict(orc.bnd[mk], elev=float(b) * RC.forcing_factor(t))
+
+    uf = update_forcings if spec["forcing"] else None
+    s_swe = ShuOsherStepper(orc, [uv, eta], spec["dt"])
+    s_tr = ShuOsherStepper(tr, [c], spec["dt"])
+    t = 0.0
+    for _ in range(spec["n_steps"]):
+        s_swe.advance(t, uf)
+        s_tr.advance(t, uf)
+        t += spec["dt"]
+    for got, key in ((uv, "uv"), (eta, "eta"), (c, "c")):
+        e = _rel(got, GOLD[f"coupled/{name}/{key}"])
+        assert e < TOL, (key, e)
 
 
 # cases the C port's interface covers (per-vertex bathymetry / Coriolis / Manning / wind, constant linear drag, constant
