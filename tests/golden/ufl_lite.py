@@ -41,8 +41,14 @@ def cell_rule():
 
 # ------------------------------------------------------------------------------------------------ mesh
 class ExteriorFacets:
-    def __init__(self, markers):
-        self.unique_markers = np.unique(markers)
+    """mesh.exterior_facets: unique_markers, and Firedrake's per-facet arrays (cell, local facet number, marker)"""
+
+    def __init__(self, m):
+        self.unique_markers = np.unique(m.bf_marker)
+        self.markers = np.asarray(m.bf_marker, dtype=np.int64)
+        self.facet_cell = np.asarray(m.bf_cell, dtype=np.int64).reshape(-1, 1)
+        self.local_facet_dat = _Dat()
+        self.local_facet_dat.data = np.asarray(m.bf_lf, dtype=np.int64).reshape(-1, 1)
 
 
 class Mesh:
@@ -50,7 +56,8 @@ class Mesh:
 
     def __init__(self, m):
         self.m = m
-        self.exterior_facets = ExteriorFacets(m.bf_marker)
+        self.exterior_facets = ExteriorFacets(m)
+        self.cell_set = _Sized(m.n_cells)
         self.boundary_len = None
         self.geometric_dimension = 2
         x = m.coords[m.cells]                                   # (nt, 3, 2)
@@ -69,6 +76,19 @@ class Mesh:
 
     def ufl_cell(self):
         return triangle
+
+    @property
+    def coordinates(self):
+        """the coordinate Function: P1 vector, DG on a periodic mesh (every cell carries its own vertex positions)"""
+        if getattr(self, "_coords", None) is None:
+            sp = Space(self, "DG" if self.m.periodic else "CG", 2, name="coordinates")
+            f = Function(sp, name="coordinates")
+            if self.m.periodic:
+                f.dat.data[...] = self.x.reshape(-1, 2)
+            else:
+                f.dat.data[...] = self.m.coords
+            self._coords = f
+        return self._coords
 
     def context(self, kind, marker=None):
         key = (kind, marker)
@@ -287,10 +307,14 @@ class Constant(Expr):
         self._v = np.array(value, dtype=float)
         self.shape = self._v.shape
         self.name = name
+        self.dat = _Dat()                        # a real firedrake.Constant carries a (versioned) PyOP2 Global
+        self.dat.data = self._v
 
     def assign(self, value):
         v = value.values() if isinstance(value, Constant) else value
         self._v = np.array(v, dtype=float).reshape(self.shape)
+        self.dat.data = self._v
+        self.dat.dat_version += 1
         return self
 
     def values(self):
@@ -747,11 +771,28 @@ def FiniteElement(family, cell=None, degree=1, variant=None, **kw):
                     "DP": "Discontinuous Lagrange"}.get(family, family), degree)
 
 
+class _Sized:
+    def __init__(self, size):
+        self.size = size
+
+
 class _Dat:
-    """owner.data is the nodal array"""
+    """PyOP2 Dat look-alike: `data` is the nodal array (`data_ro`, `*_with_halos`: the same array, one process), and
+    `dat_version` counts the assignments"""
 
     def __init__(self):
         self.dat_version = 0
+        self.data = None
+
+    data_ro = property(lambda self: self.data)
+    data_with_halos = property(lambda self: self.data)
+    data_ro_with_halos = property(lambda self: self.data)
+
+
+class _NodeMap:
+    def __init__(self, values):
+        self.values = values
+        self.arity = values.shape[1]
 
 
 class Space:
@@ -793,6 +834,9 @@ class Space:
 
     def __len__(self):
         return 1
+
+    def cell_node_map(self):
+        return _NodeMap(self.cell_nodes)
 
     # local basis function t of the space on one cell: node t // ncomp, component t % ncomp
     def basis_layout(self):
@@ -971,7 +1015,6 @@ class Function(Expr):
             self.subfunctions = [self]
             self.dat = _Dat()
             self.dat.data = np.zeros((space.ndof, 2) if space.vdim else space.ndof)
-            self.dat.data_ro = self.dat.data
             self.dof_dset = _DofDset((space.ncomp,))
         if val is not None:
             self.assign(val)

@@ -1,0 +1,235 @@
+"""
+The drop-in boundary exercised with the REFERENCE'S OWN OBJECTS, on the CPU.
+
+`thetis_b200.rungekutta.SSPRK33 / ERKLSPUM2 / ... / ForwardEuler` are constructed exactly as
+`FlowSolver2d.get_swe_timestepper` constructs the reference classes (solver2d.py:541-572):
+
+    integrator(equation, solution, fields, dt, options, bnd_conditions)
+
+with `equation` an instance of the reference's `thetis.shallowwater_eq.ShallowWaterEquations` (imported from the
+reference tree, tests/golden/refenv.py), `solution` / `fields` / `bnd_conditions` Firedrake-shaped Functions and Constants
+(tests/golden/ufl_lite.py) and the reference's own `physical_constants`.  Everything the host classes do -- mesh
+extraction from the Firedrake-shaped mesh, classification of Constants / P1 / P1DG data, node maps through the SFC
+renumbering, boundary slots and arrays, per-stage `update_forcings`, version tracking, stage coefficients, buffer
+rotation, write-back into `solution.dat.data` -- runs for real; only the C-ABI engine is replaced by
+tests/oracle_engine.py, which evaluates each stage with the CPU oracle from what was SENT to it.  The result after N
+steps must equal what the reference's own integrator produced from the same objects
+(tests/golden/reference_residuals.npz, `step/*`).  The kernels behind the real engine are tied to the same oracle by
+the `-m gpu` tests.
+
+Needs the reference tree (build container); skipped elsewhere.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/thetis"),
+                                reason="the reference tree only exists in the build container")
+
+
+@pytest.fixture
+def ref(monkeypatch):
+    """reference modules on the numpy UFL stand-in + the generator's set-up helpers; the stand-in modules are removed
+    from sys.modules afterwards (other tests rely on `import firedrake` failing)"""
+    for p in (HERE, os.path.join(HERE, "golden")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in
+             ("firedrake", "ufl", "mpi4py", "pyop2", "pyadjoint", "thetis")}
+    sys.modules.pop("make_reference_residual_golden", None)
+    import refenv
+    import make_reference_residual_golden as G          # installs the stand-ins and imports the reference modules
+    from thetis_b200 import adaptor
+    from oracle_engine import OracleEngine
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: type("S", (), {"synchronize": lambda s: None})())
+    engines = []
+
+    def get_engine(self):
+        if self.engine is None:
+            self.engine = OracleEngine(self.mesh)
+            engines.append(self.engine)
+        return self.engine
+    monkeypatch.setattr(adaptor.MeshAdaptor, "get_engine", get_engine)
+    yield types.SimpleNamespace(G=G, engines=engines)
+    refenv.uninstall()
+    sys.modules.pop("make_reference_residual_golden", None)
+    sys.modules.update(saved)
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+STEP_NAMES = ["ssprk33_tidal_constant", "ssprk33_tidal_function_manning", "ssprk33_closed_linear",
+              "erklspum2_tidal_function", "erklpum2_tidal_constant", "erkmidpoint_viscous", "erkeuler_closed",
+              "forward_euler_lagged_drag"]
+
+
+@pytest.mark.parametrize("name", STEP_NAMES)
+def test_b200_integrator_on_reference_objects_reproduces_the_reference_integrator(ref, name):
+    import reference_cases as RC
+    from thetis_b200 import rungekutta as B
+    G = ref.G
+    gold = np.load(os.path.join(HERE, "golden", "reference_residuals.npz"))
+    spec = RC.STEP_CASES[name]
+    case = RC.SWE_CASES[spec["case"]]
+    st = G.Setup(case)
+    eq, fields, bnd, o = G.swe_equation(st)                     # the reference's ShallowWaterEquations instance
+    assert type(eq).__module__ == "thetis.shallowwater_eq"
+    seed = 80 + list(RC.STEP_CASES).index(name)
+    sol, uv0, eta0 = st.swe_solution(seed)
+    assert np.array_equal(uv0, gold[f"step/{name}/uv0"])
+    topt = types.SimpleNamespace(ad_block_tag=None, solver_parameters={})
+    cls = getattr(B, spec.get("integrator", "SSPRK33"))
+    ti = cls(eq, sol, fields, spec["dt"], topt, bnd)            # the reference's constructor signature
+    ti.initialize(sol)
+    U = G.U
+    base, drag, drag_base = {}, None, None
+    if spec["forcing"] in ("elev_const", "elev_function"):
+        for mk, funcs in bnd.items():
+            if "elev" in funcs:
+                el = funcs["elev"]
+                base[mk] = float(el) if isinstance(el, U.Constant) else el.dat.data.copy()
+    elif spec["forcing"] == "lagged_drag":
+        drag = fields["linear_drag_coefficient"]
+        drag_base = drag.dat.data.copy()
+
+    def update_forcings(t):                                     # what a user script does: assign to its own objects
+        f = RC.forcing_factor(t)
+        for mk, b in base.items():
+            el = bnd[mk]["elev"]
+            if isinstance(el, U.Constant):
+                el.assign(b * f)
+            else:
+                el.dat.data[...] = b * f
+                el.dat.dat_version += 1
+        if drag is not None:
+            drag.dat.data[...] = drag_base * f
+            drag.dat.dat_version += 1
+
+    t = 0.0
+    for _ in range(spec["n_steps"]):
+        ti.advance(t, update_forcings if spec["forcing"] else None)
+        t += spec["dt"]
+    nt = st.m2.n_cells
+    uv = sol.subfunctions[0].dat.data.reshape(nt, 3, 2)         # written back in place by the drop-in
+    eta = sol.subfunctions[1].dat.data.reshape(nt, 3)
+    eu, ee = _rel(uv, gold[f"step/{name}/uv"]), _rel(eta, gold[f"step/{name}/eta"])
+    assert eu < 1e-12 and ee < 1e-12, (eu, ee)
+    eng = ref.engines[-1]
+    assert eng.n_stage_launches == spec["n_steps"] * ti.n_stages     # one fused launch per stage, nothing else
+
+
+@pytest.mark.parametrize("name", ["coupled_ssprk33_advection", "coupled_ssprk33_diffusion_unstructured"])
+def test_b200_classes_inside_the_reference_coupled_integrator(ref, name):
+    """The reference's own `coupled_timeintegrator_2d.GeneralCoupledTimeIntegrator2D` (executed from the reference
+    tree) drives the B200 classes handed to it as `integrators` -- the route a Thetis user takes after
+    `thetis_b200.install()`: SWE step, then the tracer step on the new velocity, both through the reference's
+    `advance()`; the result must equal the run in which the reference drove its own SSPRK33 classes."""
+    import reference_cases as RC
+    from thetis_b200 import rungekutta as B
+    G = ref.G
+    gold = np.load(os.path.join(HERE, "golden", "reference_residuals.npz"))
+    spec = RC.COUPLED_CASES[name]
+    swe_case, tr_case = RC.SWE_CASES[spec["swe"]], RC.TRACER_CASES[spec["tracer"]]
+    st = G.Setup(swe_case)
+    seed = 120 + list(RC.COUPLED_CASES).index(name)
+    solver = G._FakeSolver(st, swe_case, tr_case, spec["dt"], seed)
+    cti = G.MODS["coupled_timeintegrator_2d"].GeneralCoupledTimeIntegrator2D(
+        solver, {"shallow_water": B.SSPRK33, "tracer": B.SSPRK33})
+    assert type(cti.timesteppers.swe2d).__module__ == "thetis_b200.rungekutta"
+    cti.initialize(solver.fields.solution_2d)
+    bnd = solver.bnd_functions["shallow_water"]
+    base = {mk: float(f["elev"]) for mk, f in bnd.items() if "elev" in f} if spec["forcing"] else {}
+
+    def update_forcings(t):
+        for mk, b in base.items():
+            bnd[mk]["elev"].assign(b * RC.forcing_factor(t))
+
+    t = 0.0
+    for _ in range(spec["n_steps"]):
+        cti.advance(t, update_forcings if spec["forcing"] else None)
+        t += spec["dt"]
+    nt = st.m2.n_cells
+    sol = solver.fields.solution_2d
+    got = dict(uv=sol.subfunctions[0].dat.data.reshape(nt, 3, 2), eta=sol.subfunctions[1].dat.data.reshape(nt, 3),
+               c=solver.fields.tracer_2d.dat.data.reshape(nt, 3))
+    for k, v in got.items():
+        e = _rel(v, gold[f"coupled/{name}/{k}"])
+        assert e < 1e-12, (k, e)
+
+
+def _swe_case_names():
+    sys.path.insert(0, HERE)
+    import reference_cases as RC
+    return list(RC.SWE_CASES)
+
+
+@pytest.mark.parametrize("name", _swe_case_names())
+def test_b200_tendency_on_reference_objects_equals_the_reference_terms(ref, name):
+    """Every SWE set-up of tests/reference_cases.py handed to the drop-in as the reference's own equation object plus
+    Firedrake-shaped Constants / P1 / P1DG Functions: one forward-Euler step of size 1 (`ERKEuler`, so that
+    u1 - u0 = M^-1 R(u0)) must reproduce the tendency the reference's term classes produced.  Covers the adaptor's
+    classification of every coefficient and boundary-datum form on objects it did not create."""
+    import reference_cases as RC
+    from thetis_b200 import rungekutta as B
+    G = ref.G
+    gold = np.load(os.path.join(HERE, "golden", "reference_residuals.npz"))
+    case = RC.SWE_CASES[name]
+    st = G.Setup(case)
+    g_old = float(G.PC["g_grav"])
+    G.PC["g_grav"].assign(case.get("g", g_old))                   # the reference's own Constant, as a script mutates it
+    try:
+        eq, fields, bnd, o = G.swe_equation(st)
+        sol, uv0, eta0 = st.swe_solution(list(RC.SWE_CASES).index(name))
+        ti = B.ERKEuler(eq, sol, fields, 1.0, types.SimpleNamespace(ad_block_tag=None, solver_parameters={}), bnd)
+        ti.initialize(sol)
+        ti.advance(0.0)
+    finally:
+        G.PC["g_grav"].assign(g_old)
+    nt = st.m2.n_cells
+    ku = sol.subfunctions[0].dat.data.reshape(nt, 3, 2) - uv0
+    ke = sol.subfunctions[1].dat.data.reshape(nt, 3) - eta0
+    eu, ee = _rel(ku, gold[f"swe/{name}/ku"]), _rel(ke, gold[f"swe/{name}/ke"])
+    assert eu < 1e-11 and ee < 1e-11, (eu, ee)        # the difference u1 - u0 costs a few digits
+
+
+def _tracer_case_names():
+    sys.path.insert(0, HERE)
+    import reference_cases as RC
+    return list(RC.TRACER_CASES)
+
+
+@pytest.mark.parametrize("name", _tracer_case_names())
+def test_b200_tracer_tendency_on_reference_objects_equals_the_reference_terms(ref, name):
+    """The same for the reference's own `TracerEquation2D` (both forms): fields named as
+    `FlowSolver2d.get_tracer_timestepper` names them (solver2d.py:575-598), velocity / elevation as host Functions."""
+    import reference_cases as RC
+    from thetis_b200 import rungekutta as B
+    G = ref.G
+    U = G.U
+    gold = np.load(os.path.join(HERE, "golden", "reference_residuals.npz"))
+    case = RC.TRACER_CASES[name]
+    st = G.Setup(case)
+    depth, opts, o = st.depth_and_options()
+    eq = G.treq.TracerEquation2D("tracer_2d", st.H, depth, opts, None)
+    sol, uv, eta = st.swe_solution(50 + list(RC.TRACER_CASES).index(name))
+    c0 = gold[f"tracer/{name}/c"]
+    q = U.Function(st.H, name="tracer_2d")
+    q.dat.data[...] = c0.reshape(-1)
+    fields = {"uv_2d": sol.subfunctions[0], "elev_2d": sol.subfunctions[1],
+              "tracer_advective_velocity_factor": U.Constant(1.0), "lax_friedrichs_tracer_scaling_factor": U.Constant(1.0)}
+    for fname, spec in case.get("fields", {}).items():
+        fields[f"{fname}-tracer_2d" if fname in ("source", "diffusivity_h") else fname] = st.obj(spec)
+    ti = B.ERKEuler(eq, q, fields, 1.0, types.SimpleNamespace(ad_block_tag=None, solver_parameters={}), st.bnd())
+    ti.initialize(q)
+    ti.advance(0.0)
+    kc = q.dat.data.reshape(-1, 3) - c0
+    e = _rel(kc, gold[f"tracer/{name}/kc"])
+    assert e < 1e-10, e                              # c ~ 1, dc ~ 1e-3: the difference costs three digits

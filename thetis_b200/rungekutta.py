@@ -230,9 +230,27 @@ class ERKGenericShuOsher:
         return self.equation.depth
 
     def _tracer_label(self):
+        """Label of the tracer this equation advances ('tracer_2d', 'salinity_2d', ...).  The reference's
+        `TracerEquation2D` does not keep its `system` argument; every term it adds carries the label
+        (`TracerTerm.label`, tracer_eq_2d.py:62, keys 'HorizontalAdvectionTerm_<label>' in `equation.terms`), whereas
+        `equation.labels` is the term-key -> 'explicit'/'source' dict of `Equation` (equation.py:69), not a list."""
         lab = getattr(self.equation, "system", None)
         if lab is None:
-            lab = getattr(self.equation, "labels", [None])[0]
+            terms = getattr(self.equation, "terms", None)
+            found = []
+            for term in (terms.values() if hasattr(terms, "values") else ()):
+                tl = getattr(term, "label", None)
+                if tl is not None and tl not in found:
+                    found.append(tl)
+            if len(found) > 1:
+                raise NotImplementedError("mixed systems of several tracers are outside the accelerated path")
+            if found:
+                return found[0]
+            labels = getattr(self.equation, "labels", None)
+            if isinstance(labels, (list, tuple)) and labels:
+                lab = labels[0]
+        if isinstance(lab, str) and "," in lab:
+            raise NotImplementedError("mixed systems of several tracers are outside the accelerated path")
         return lab
 
     def _tracer_field(self, prefix):
