@@ -1455,6 +1455,14 @@ def Identity(d):
     return Const(np.eye(d))
 
 
+class VertexBasedLimiter:
+    """Placeholder so that `thetis/limiter.py` imports: Firedrake's limiter kernels are C strings run by PyOP2 and are
+    not restated here (the reference's limiter cannot be executed on this stand-in)."""
+
+    def __init__(self, space):
+        raise NotImplementedError("firedrake.VertexBasedLimiter is not available on the numpy stand-in")
+
+
 triangle = "triangle"
 quadrilateral = "quadrilateral"
 

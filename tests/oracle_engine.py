@@ -179,6 +179,13 @@ class OracleEngine:
             new = new + a0 * self._rec(u0, 9)
         self._rec(dst, 9)[...] = new
 
+    def limiter_apply_to(self, c_in, c_out):
+        from oracle.swe_oracle import vertex_based_limiter
+        self._rec(c_out, 3)[...] = vertex_based_limiter(self.mesh, self._rec(c_in, 3).copy())
+
+    def limiter_apply(self, c):
+        self.limiter_apply_to(c, c)
+
     def tracer_stage(self, a0, a1, bdt, src, u0, dst, swe_state):
         self.n_stage_launches += 1
         o, f = self.opt, self.fields

@@ -233,3 +233,69 @@ def test_b200_tracer_tendency_on_reference_objects_equals_the_reference_terms(re
     kc = q.dat.data.reshape(-1, 3) - c0
     e = _rel(kc, gold[f"tracer/{name}/kc"])
     assert e < 1e-10, e                              # c ~ 1, dc ~ 1e-3: the difference costs three digits
+
+
+def test_install_rebinds_the_reference_modules_and_the_coupled_run_still_matches(ref):
+    """`thetis_b200.install(thetis)` on the REAL `thetis.rungekutta` / `thetis.timeintegrator` / `thetis.limiter` modules
+    (imported from the reference tree): the attributes `FlowSolver2d.create_timestepper` looks up at call time
+    (solver2d.py:662-672, :535-539) now resolve to the B200 classes, and the reference's coupled integrator fed from
+    those attributes reproduces the reference-only run."""
+    import importlib
+    import reference_cases as RC
+    import thetis_b200
+    from thetis_b200 import rungekutta as B, limiter as BL
+    G = ref.G
+    thetis = sys.modules["thetis"]
+    importlib.import_module("thetis.limiter")
+    rk_mod, ti_mod, lim_mod = thetis.rungekutta, thetis.timeintegrator, thetis.limiter
+    saved = {(m, n): getattr(m, n) for m, n in [(rk_mod, "SSPRK33"), (rk_mod, "ERKLSPUM2"), (rk_mod, "ERKLPUM2"),
+                                                (rk_mod, "ERKMidpoint"), (rk_mod, "ERKEuler"),
+                                                (ti_mod, "ForwardEuler"), (lim_mod, "VertexBasedP1DGLimiter")]}
+    assert saved[(rk_mod, "SSPRK33")].__module__ == "thetis.rungekutta"
+    try:
+        thetis_b200.install(thetis, sync_policy="every_step")
+        assert issubclass(rk_mod.SSPRK33, B.SSPRK33) and issubclass(rk_mod.ERKLSPUM2, B.ERKLSPUM2)
+        assert issubclass(ti_mod.ForwardEuler, B.ForwardEuler)
+        assert lim_mod.VertexBasedP1DGLimiter is BL.VertexBasedP1DGLimiter
+        steppers = {"SSPRK33": rk_mod.SSPRK33}                      # what solver2d.py:662-672 builds at call time
+        name = "coupled_ssprk33_advection"
+        spec = RC.COUPLED_CASES[name]
+        swe_case, tr_case = RC.SWE_CASES[spec["swe"]], RC.TRACER_CASES[spec["tracer"]]
+        st = G.Setup(swe_case)
+        solver = G._FakeSolver(st, swe_case, tr_case, spec["dt"], 120)
+        cti = thetis.coupled_timeintegrator_2d.GeneralCoupledTimeIntegrator2D(
+            solver, {"shallow_water": steppers["SSPRK33"], "tracer": steppers["SSPRK33"]})
+        cti.initialize(solver.fields.solution_2d)
+        bnd = solver.bnd_functions["shallow_water"]
+        base = {mk: float(f["elev"]) for mk, f in bnd.items() if "elev" in f}
+        t = 0.0
+        for _ in range(spec["n_steps"]):
+            cti.advance(t, lambda tt: [bnd[mk]["elev"].assign(b * RC.forcing_factor(tt)) for mk, b in base.items()])
+            t += spec["dt"]
+        gold = np.load(os.path.join(HERE, "golden", "reference_residuals.npz"))
+        nt = st.m2.n_cells
+        assert _rel(solver.fields.tracer_2d.dat.data.reshape(nt, 3), gold[f"coupled/{name}/c"]) < 1e-12
+        assert _rel(solver.fields.solution_2d.subfunctions[1].dat.data.reshape(nt, 3), gold[f"coupled/{name}/eta"]) < 1e-12
+    finally:
+        for (m, n), v in saved.items():
+            setattr(m, n, v)
+
+
+def test_b200_limiter_on_a_reference_shaped_space(ref):
+    """`VertexBasedP1DGLimiter(p1dg_space).apply(field)` with a Firedrake-shaped space / Function it did not create:
+    the node maps through the SFC renumbering must bring back, dof by dof, what the oracle limiter gives in the
+    caller's own cell order (the limiter arithmetic itself is pinned elsewhere)."""
+    import reference_cases as RC
+    from thetis_b200.limiter import VertexBasedP1DGLimiter
+    from oracle.swe_oracle import vertex_based_limiter
+    G = ref.G
+    st = G.Setup(RC.SWE_CASES["nonlinear_no_lf"])                   # unstructured mesh
+    x = st.m2.coords[st.m2.cells]
+    rng = np.random.default_rng(3)
+    q0 = np.tanh((x[..., 0] - 2.5e3) / 300.0) + 0.3 * rng.standard_normal(x.shape[:2])     # over- and undershoots
+    f = G.U.Function(st.H, name="tracer_2d")
+    f.dat.data[...] = q0.reshape(-1)
+    VertexBasedP1DGLimiter(st.H).apply(f)
+    want = vertex_based_limiter(st.m2, q0)
+    assert np.abs(want - q0).max() > 0.05                           # the limiter did something
+    assert np.abs(f.dat.data.reshape(-1, 3) - want).max() < 1e-13
