@@ -176,12 +176,35 @@ def run_tracer(name, case, seed):
     return dict(uv=uv, eta=eta, c=c, kc=k.dat.data.reshape(nt, 3).copy())
 
 
+def install_elev_expression(bnd, spec):
+    """Replace every 'elev' Function of `bnd` by the UFL expression elev_ramp * elev_tide_2d of
+    examples/north_sea/model_config.py:181-192; returns what update_forcings has to assign."""
+    bnd_time, ramp_t = U.Constant(0.0), U.Constant(spec["ramp_t"])
+    elev_ramp = U.conditional(bnd_time < ramp_t, bnd_time / ramp_t, 1.0)
+    tides = []
+    for mk, funcs in bnd.items():
+        if "elev" in funcs:
+            tide = funcs["elev"]
+            tides.append((tide, tide.dat.data.copy()))
+            funcs["elev"] = elev_ramp * tide
+    return bnd_time, tides
+
+
+def update_elev_expression(parts, t):
+    bnd_time, tides = parts
+    bnd_time.assign(t)
+    for tide, base in tides:
+        tide.dat.data[...] = base * RC.forcing_factor(t)
+        tide.dat.dat_version += 1
+
+
 def run_steps(name, spec, seed):
     case = RC.SWE_CASES[spec["case"]]
     st = Setup(case)
     eq, fields, bnd, o = swe_equation(st)
     assert not o["use_wetting_and_drying"]
     sol, uv, eta = st.swe_solution(seed)
+    expr_parts = install_elev_expression(bnd, spec) if spec["forcing"] == "elev_expression" else None
     topt = types.SimpleNamespace(ad_block_tag=None, solver_parameters={})
     kind = spec.get("integrator", "SSPRK33")
     cls = MODS["timeintegrator"].ForwardEuler if kind == "ForwardEuler" else getattr(rk, kind)
@@ -201,6 +224,8 @@ def run_steps(name, spec, seed):
 
     def update_forcings(t):
         f = RC.forcing_factor(t)
+        if expr_parts is not None:
+            update_elev_expression(expr_parts, t)
         for mk, b in base.items():
             el = bnd[mk]["elev"]
             if isinstance(el, U.Constant):

@@ -25,7 +25,7 @@ if HERE not in sys.path:
     sys.path.insert(0, HERE)
 import ufl_lite as U   # noqa: E402
 
-_STUBBED = ["firedrake", "firedrake.petsc", "ufl", "mpi4py", "pyop2", "pyop2.profiling", "pyadjoint", "pyadjoint.tape",
+_STUBBED = ["firedrake", "firedrake.petsc", "ufl", "ufl.algorithms", "mpi4py", "pyop2", "pyop2.profiling", "pyadjoint", "pyadjoint.tape",
             "thetis"]
 
 
@@ -84,6 +84,10 @@ def install():
     for k in dir(U):
         if not k.startswith("_"):
             setattr(ufl, k, getattr(U, k))
+    alg = types.ModuleType("ufl.algorithms")
+    alg.estimate_total_polynomial_degree = U.estimate_total_polynomial_degree
+    ufl.algorithms = alg
+    sys.modules["ufl.algorithms"] = alg
     mpi = types.ModuleType("mpi4py")
     mpi.MPI = types.SimpleNamespace(MIN="min", MAX="max", SUM="sum", COMM_WORLD=fd.COMM_WORLD)
     pyop2 = types.ModuleType("pyop2")

@@ -195,6 +195,19 @@ class Expr:
         return self.shape
 
     @property
+    def ufl_operands(self):
+        """child expressions, like ufl.core.Operator.ufl_operands (terminals: an empty tuple)"""
+        if isinstance(self, (Function, Constant, Const, Argument, FacetNormal, _CellGeom, SpatialCoordinate)):
+            return ()
+        out = []
+        for k in vars(self).values():
+            if isinstance(k, (Expr, Condition)):
+                out.append(k)
+            elif isinstance(k, (list, tuple)):
+                out.extend(c for c in k if isinstance(c, (Expr, Condition)))
+        return tuple(out)
+
+    @property
     def rank(self):
         return len(self.shape)
 
@@ -469,6 +482,10 @@ class Condition:
     def __init__(self, op, a, b):
         assert a.rank == 0 and b.rank == 0
         self.op, self.a, self.b = op, a, b
+
+    @property
+    def ufl_operands(self):
+        return (self.a, self.b)
 
     def ev(self, ctx, side):
         av, _ = self.a.ev(ctx, side, False)
@@ -1461,6 +1478,34 @@ class VertexBasedLimiter:
 
     def __init__(self, space):
         raise NotImplementedError("firedrake.VertexBasedLimiter is not available on the numpy stand-in")
+
+
+def estimate_total_polynomial_degree(e, default_degree=1):
+    """ufl.algorithms.estimate_total_polynomial_degree for the node types above, with UFL's own rules: coefficients
+    count their element degree, sums take the maximum, products AND quotients add, a conditional takes the maximum of
+    its two values (UFL ignores the condition), non-polynomial functions add 2"""
+    d = estimate_total_polynomial_degree
+    if isinstance(e, (Function, Argument)):
+        return 1
+    if isinstance(e, SpatialCoordinate):
+        return 1
+    if isinstance(e, (Const, Constant, FacetNormal, _CellGeom)):
+        return 0
+    if isinstance(e, (Sum, ListTensor)):
+        return max(d(k) for k in e.ufl_operands)
+    if isinstance(e, (Product, Division, Dot, Outer)):
+        return sum(d(k) for k in e.ufl_operands)
+    if isinstance(e, Power):
+        p = e.p.ev(None, None, False)[0].reshape(()) if isinstance(e.p, (Const, Constant)) else 2
+        return d(e.a) * int(p) if float(p) == int(p) and p >= 0 else d(e.a) + 2
+    if isinstance(e, Conditional):
+        return max(d(e.a), d(e.b))
+    if isinstance(e, (Sqrt, Ln, Cos, Sin, Exp)):
+        return d(e.a) + 2
+    if isinstance(e, (Grad, NablaGrad, Div, Dx)):
+        return max(d(e.a) - 1, 0)
+    ops = e.ufl_operands
+    return max(d(k) for k in ops) if ops else 0
 
 
 triangle = "triangle"

@@ -205,6 +205,11 @@ STEP_CASES = {
     "erkmidpoint_viscous": dict(case="viscosity_graddiv1_graddepth1", dt=1.0, n_steps=4, forcing="elev_const",
                                 integrator="ERKMidpoint"),
     "erkeuler_closed": dict(case="nonlinear_lf_closed", dt=2.0, n_steps=5, forcing=None, integrator="ERKEuler"),
+    # boundary elevation given as a UFL EXPRESSION over a Constant-valued ramp and a Function, the way
+    # examples/north_sea/model_config.py:181-192 writes it: elev_ramp * elev_tide_2d with
+    # elev_ramp = conditional(bnd_time < ramp_t, bnd_time / ramp_t, 1.0); update_forcings assigns bnd_time and the tide
+    "ssprk33_tidal_ufl_expression": dict(case="open_bc_functions_1", dt=4.0, n_steps=5, forcing="elev_expression",
+                                         ramp_t=12.0),
     "forward_euler_lagged_drag": dict(case="quadratic_drag_const_linear_drag_field", dt=2.0, n_steps=5,
                                       forcing="lagged_drag", integrator="ForwardEuler"),
 }

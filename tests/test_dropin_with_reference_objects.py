@@ -67,6 +67,7 @@ def _rel(a, b):
 
 
 STEP_NAMES = ["ssprk33_tidal_constant", "ssprk33_tidal_function_manning", "ssprk33_closed_linear",
+              "ssprk33_tidal_ufl_expression",
               "erklspum2_tidal_function", "erklpum2_tidal_constant", "erkmidpoint_viscous", "erkeuler_closed",
               "forward_euler_lagged_drag"]
 
@@ -85,6 +86,7 @@ def test_b200_integrator_on_reference_objects_reproduces_the_reference_integrato
     seed = 80 + list(RC.STEP_CASES).index(name)
     sol, uv0, eta0 = st.swe_solution(seed)
     assert np.array_equal(uv0, gold[f"step/{name}/uv0"])
+    expr_parts = G.install_elev_expression(bnd, spec) if spec["forcing"] == "elev_expression" else None
     topt = types.SimpleNamespace(ad_block_tag=None, solver_parameters={})
     cls = getattr(B, spec.get("integrator", "SSPRK33"))
     ti = cls(eq, sol, fields, spec["dt"], topt, bnd)            # the reference's constructor signature
@@ -102,6 +104,8 @@ def test_b200_integrator_on_reference_objects_reproduces_the_reference_integrato
 
     def update_forcings(t):                                     # what a user script does: assign to its own objects
         f = RC.forcing_factor(t)
+        if expr_parts is not None:
+            G.update_elev_expression(expr_parts, t)
         for mk, b in base.items():
             el = bnd[mk]["elev"]
             if isinstance(el, U.Constant):

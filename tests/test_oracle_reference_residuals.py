@@ -107,6 +107,8 @@ def test_whole_steps_equal_the_reference_integrators(name):
 
     def update_forcings(t):
         f = RC.forcing_factor(t)
+        if spec["forcing"] == "elev_expression":      # elev_ramp * elev_tide_2d, evaluated by hand
+            f = f * (t / spec["ramp_t"] if t < spec["ramp_t"] else 1.0)
         for mk, b in base.items():
             orc.bnd[mk] = dict(orc.bnd[mk], elev=(b * f if isinstance(b, np.ndarray) else float(b) * f))
 

@@ -74,6 +74,19 @@ def expression_leaves(expr):
     return out
 
 
+def _condition_reads_a_function(expr):
+    """True when the condition of some `conditional(...)` inside a (real-UFL) expression depends on a Function."""
+    def has_function(e):
+        return is_function(e) or any(has_function(o) for o in getattr(e, "ufl_operands", ()))
+
+    def walk(e):
+        ops = getattr(e, "ufl_operands", ())
+        if type(e).__name__ == "Conditional" and ops and has_function(ops[0]):
+            return True
+        return any(walk(o) for o in ops)
+    return walk(expr)
+
+
 def expression_degree(expr):
     """Polynomial degree of an expression in its Function operands (P1 Functions count 1, Constants 0); None when it
     is not a polynomial (division by a Function, a condition that depends on a Function).  Degree <= 1 means nodal
@@ -85,6 +98,10 @@ def expression_degree(expr):
     kind = getattr(expr, "kind", None)
     if kind is None:           # real UFL
         from ufl.algorithms import estimate_total_polynomial_degree
+        # UFL's estimate ignores the condition of a `conditional`: one that depends on a Function switches inside
+        # cells and is not reproduced by nodal evaluation, whatever degree its two values have
+        if _condition_reads_a_function(expr):
+            return None
         return estimate_total_polynomial_degree(expr)
     ops = [expression_degree(o) for o in expr.ufl_operands]
     if any(d is None for d in ops):
@@ -260,7 +277,8 @@ class MeshAdaptor:
                 "expression is not affine in its Function operands: interpolate it into a P1 / P1DG Function first")
         kind = getattr(expr, "kind", None)
         if kind is None:
-            # real UFL: let Firedrake do the nodal evaluation (exact for degree <= 1).  UNTESTED HERE (no Firedrake).
+            # real UFL: let Firedrake do the nodal evaluation (exact for degree <= 1).  Exercised on the numpy stand-in
+            # for UFL only (tests/test_dropin_with_reference_objects.py), never against Firedrake itself.
             import firedrake as fd
             mesh_obj = self.mesh_obj_ref()
             shape = getattr(expr, "ufl_shape", ())
