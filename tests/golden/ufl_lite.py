@@ -1212,6 +1212,8 @@ class Form:
     __mul__ = __rmul__
 
     def __eq__(self, o):
+        if isinstance(o, Form):
+            return FormEquation(self, o)          # `a == L`, the argument of solve()
         return self is o
 
     def __ne__(self, o):
@@ -1309,6 +1311,31 @@ def _find_mesh(e):
 class BlockMatrix:
     def __init__(self, test, trial, blocks):
         self.test, self.trial, self.blocks = test, trial, blocks
+
+
+class FormEquation:
+    def __init__(self, lhs, rhs):
+        self.lhs, self.rhs = lhs, rhs
+
+    def __bool__(self):
+        return False
+
+
+def solve(equation, u, bcs=None, solver_parameters=None, **kw):
+    """solve(a == L, u): the cell blocks of `a` scattered into a global sparse matrix (continuous spaces couple the
+    cells), direct solve"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    A = assemble(equation.lhs)
+    b = assemble(equation.rhs).vector_data()
+    cells = np.arange(A.test.mesh().m.n_cells)
+    rows = A.test.local_dofs(cells)
+    cols = A.trial.local_dofs(cells)
+    M = sp.coo_matrix((A.blocks.reshape(-1), (np.repeat(rows, cols.shape[1], axis=1).reshape(-1),
+                                             np.tile(cols, (1, rows.shape[1])).reshape(-1))),
+                      shape=(A.test.size, A.trial.size)).tocsc()
+    u.set_vector_data(spla.spsolve(M, b))
+    return u
 
 
 class LinearVariationalProblem:
