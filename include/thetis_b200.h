@@ -108,7 +108,10 @@ typedef enum {
 /* Boundary tags (shallowwater_eq.py:243-267); a marker's opcode is the OR of
  * the tags present.  0 = closed (land) boundary. */
 enum { TB_BC_ELEV = 1, TB_BC_UV = 2, TB_BC_UN = 4, TB_BC_FLUX = 8, TB_BC_VALUE = 16,
-       TB_BC_DIFF_FLUX = 64 /* tracer 'diff_flux' (tracer_eq_2d.py:264-265); 32 is reserved */ };
+       TB_BC_DIFF_FLUX = 64, /* tracer 'diff_flux' (tracer_eq_2d.py:264-265); 32 is reserved */
+       TB_BC_DRAG = 128      /* shallow water 'drag': quadratic friction of the tangential velocity on the marker's
+                                facets (BoundaryDragTerm, shallowwater_eq.py:704-726); not an open-boundary tag, it
+                                combines with a closed boundary or with any of the open ones (:286-296) */ };
 
 /* ---- lifetime ---------------------------------------------------------- */
 int tb_create(tb_ctx **out, const tb_mesh *mesh, int device);
@@ -141,7 +144,7 @@ int tb_clear_field(tb_ctx *ctx, int field);     /* field = None                 
  * update_forcings); structural changes rebuild the per-patch blocks (synchronising, set-up time only). */
 int tb_sync_fields(tb_ctx *ctx, void *stream);
 /* Boundary condition of one marker for equation eq (0 = shallow water,
- * 1 = tracer): opcode = OR of TB_BC_*, consts = {elev, uv_x, uv_y, un, flux, value, diff_flux, reserved}.
+ * 1 = tracer): opcode = OR of TB_BC_*, consts = {elev, uv_x, uv_y, un, flux, value, diff_flux, drag}.
  * replaces ShallowWaterTerm.get_bnd_functions (shallowwater_eq.py:232-272)
  * and TracerTerm.get_bnd_functions (tracer_eq_2d.py:78-115) */
 int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const double consts[8]);

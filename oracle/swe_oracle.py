@@ -339,6 +339,8 @@ class SWEOracle:
         lam, qw = self.lam, self.qw
         nonlin = o["use_nonlinear_equations"]
         adv = nonlin and o["include_momentum_advection"]
+        # ModeSplit2DEquations (include_momentum_advection=False) has no BoundaryDragTerm (shallowwater_eq.py:953-957)
+        boundary_drag = bool(o["include_momentum_advection"])
         Ru = np.zeros((nt, 3, 2))
         Re = np.zeros((nt, 3))
         A = geo.area
@@ -584,8 +586,12 @@ class SWEOracle:
                     fu = fu + np.einsum("fqij,fqj->fqi", sig[..., None, None] * SJb - Sb, nb)
                     SJint = np.einsum("fq,fqij->fij", wf, SJb)
                     np.add.at(Ru, cells, np.einsum("faj,fij->fai", grad[cells], SJint))
-            if funcs is not None and 'drag' in funcs:
-                raise NotImplementedError("BoundaryDragTerm is not on the accelerated path")
+            if funcs is not None and 'drag' in funcs and boundary_drag:
+                # BoundaryDragTerm (shallowwater_eq.py:704-726): C_D |u_t| u_t, u_t the tangential velocity
+                cd = self._bc_value(funcs['drag'], cells, lf)
+                ut = u - np.einsum("fqi,fqi->fq", u, nb)[..., None] * nb
+                ut_mag = np.sqrt(np.einsum("fqi,fqi->fq", ut, ut))
+                fu = fu + (cd * ut_mag)[..., None] * ut
             for k in range(2):
                 np.subtract.at(Ru, (cells, nodes[:, k]), np.einsum("fq,fqi,q->fi", wf, fu, php[:, k]))
                 np.subtract.at(Re, (cells, nodes[:, k]), np.einsum("fq,fq,q->f", wf, fe, php[:, k]))

@@ -25,6 +25,7 @@ _FIELD_NAMES = {
 }
 _SWE_TAGS = {L.BC_ELEV: ("elev", 0, 1), L.BC_UV: ("uv", 1, 2), L.BC_UN: ("un", 3, 1), L.BC_FLUX: ("flux", 4, 1)}
 _TRACER_TAGS = dict(_SWE_TAGS)
+_SWE_TAGS[L.BC_DRAG] = ("drag", 7, 1)          # BoundaryDragTerm: shallow water only
 _TRACER_TAGS.update({L.BC_VALUE: ("value", 5, 1), L.BC_DIFF_FLUX: ("diff_flux", 6, 1)})
 
 

@@ -169,6 +169,22 @@ SWE_CASES["modesplit_open_bcs"] = dict(mesh=RECT, bath=P("bath_wavy"), equation=
 SWE_CASES["modesplit_closed_unstructured"] = dict(mesh=DELAUNAY, bath=P("bath_wavy"), equation="modesplit",
                                                   fields={"coriolis": C(1.0e-4), "momentum_source": ("dg", 11, 0.0, 1.0e-4, 2)})
 
+# BoundaryDragTerm (shallowwater_eq.py:704-726): 'drag' on a closed marker, combined with open tags, on every marker of
+# an unstructured mesh, and with the linear equations (the term does not depend on use_nonlinear_equations)
+SWE_CASES["boundary_drag_closed_and_open"] = dict(
+    mesh=RECT, bath=P("bath_wavy"),
+    bnd={1: {"drag": C(0.05)}, 2: {"elev": C(-0.2), "un": C(0.15), "drag": C(0.02)}, 3: {"uv": C((0.1, 0.05)), "drag": C(0.1)}})
+SWE_CASES["boundary_drag_unstructured_manning"] = dict(
+    mesh=DELAUNAY, bath=P("bath_wavy"), fields={"manning_drag_coefficient": C(0.03), "coriolis": P("coriolis")},
+    bnd={m: {"drag": C(0.01 * m)} for m in (1, 2, 3, 4)})
+SWE_CASES["boundary_drag_linear"] = dict(mesh=RAGGED, options=dict(use_nonlinear_equations=False), bath=P("bath_wavy"),
+                                         bnd={1: {"drag": C(0.05)}, 4: {"elev": C(0.1), "drag": C(0.03)}})
+
+# ModeSplit2DEquations accepts the tag (impose_dynamic_bnd, :286-296) but adds no BoundaryDragTerm (:953-957)
+SWE_CASES["modesplit_ignores_boundary_drag"] = dict(mesh=RECT, bath=P("bath_wavy"), equation="modesplit",
+                                                    fields={"coriolis": C(1.0e-4)},
+                                                    bnd={1: {"drag": C(0.05)}, 2: {"elev": C(0.2), "drag": C(0.1)}})
+
 TRACER_CASES = {
     "advection_closed_source": dict(mesh=RECT, bath=P("bath_wavy"), fields={"source": P("tsrc")}),
     "advection_bcs_lf": dict(mesh=RECT, bath=P("bath_wavy"), options=dict(use_lax_friedrichs_tracer=True),

@@ -84,10 +84,10 @@ def _run(mesh, bath_v, options, fields_v, bnd, g=9.81, tol=1e-12, seed=0, bc_arr
     for k, fid in names.items():
         if fields_v.get(k) is not None:
             eng.set_field(fid, fields_v[k])
-    tags = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX}
+    tags = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX, "drag": L.BC_DRAG}
     for m, d in obnd.items():
         op = 0
-        consts = np.zeros(6)
+        consts = np.zeros(8)
         for tag, val in d.items():
             op |= tags[tag]
             if not (isinstance(val, np.ndarray) and val.ndim >= 2):
@@ -95,6 +95,7 @@ def _run(mesh, bath_v, options, fields_v, bnd, g=9.81, tol=1e-12, seed=0, bc_arr
                 if tag == "uv": consts[1:3] = val
                 if tag == "un": consts[3] = val
                 if tag == "flux": consts[4] = val
+                if tag == "drag": consts[7] = val
         eng.set_bc(0, m, op, consts)
     if bc_arrays:
         for (m, tag), arr in bc_arrays.items():
@@ -194,6 +195,46 @@ def test_open_boundary_opcodes(bc, nonlinear):
     b = _vertex_field(mesh, lambda x, y: 12 + 0.004 * x)
     bnd = {1: bc, 2: {"elev": 0.1}, 3: bc}
     _run(mesh, b, dict(use_nonlinear_equations=nonlinear), {}, bnd, tol=1e-11)
+
+
+@pytest.mark.parametrize("nonlinear", [True, False])
+def test_boundary_drag_term(nonlinear):
+    """BoundaryDragTerm (shallowwater_eq.py:704-726): quadratic friction of the tangential velocity on markers that carry
+    a 'drag' tag -- alone (closed boundary) and combined with open tags; Manning + Coriolis are on so that a
+    specialised kernel would be chosen without the tag (the term lives in the generic kernel).  The oracle side of this
+    comparison reproduces the reference's own BoundaryDragTerm (tests/test_oracle_reference_residuals.py)."""
+    import thetis_b200._lib as L
+    mesh = sfc_renumber(delaunay_mesh(900, 5.0e3, 4.0e3, seed=5))
+    X, Y = mesh.coords[:, 0], mesh.coords[:, 1]
+    b = 20.0 + 3.0 * np.sin(X / 900.0) * np.cos(Y / 700.0)
+    bnd = {1: {"drag": 0.05}, 2: {"elev": -0.2, "un": 0.15, "drag": 0.02}, 3: {"uv": (0.1, 0.05), "drag": 0.1}, 4: {"drag": 0.2}}
+    fields = {"manning_drag_coefficient": 0.03, "coriolis": 1e-4 + 2e-8 * Y} if nonlinear else {}
+    eng, orc, (uv, eta) = _run(mesh, b, dict(use_nonlinear_equations=nonlinear), fields, bnd, tol=1e-11, return_engine=True)
+    # the term is really there: without the tags the tendency moves far beyond the tolerance
+    ku, _ = orc.tendency(uv, eta)
+    orc.bnd = {m: {t: v for t, v in d.items() if t != "drag"} for m, d in bnd.items()}
+    ku0, _ = orc.tendency(uv, eta)
+    assert np.abs(ku - ku0).max() > 1e-4 * np.abs(ku).max()
+    # fluid at rest: |u_t| = 0 exactly on every boundary facet, the root must not produce NaN
+    eng.set_option(L.OPT_FORCE_GENERIC_KERNEL, 0)
+    st = eng.upload_nodal(np.zeros_like(uv), eta)
+    k = eng.new_state()
+    eng.swe_tendency(st, k)
+    gu, ge = eng.download_nodal(k)
+    orc.bnd = bnd
+    ku, ke = orc.tendency(np.zeros_like(uv), eta)
+    assert np.isfinite(gu).all() and np.isfinite(ge).all()
+    assert np.abs(gu - ku).max() <= 1e-11 * np.abs(ku).max() and np.abs(ge - ke).max() <= 1e-11 * np.abs(ke).max()
+
+
+def test_boundary_drag_is_a_shallow_water_tag():
+    import thetis_b200._lib as L
+    from thetis_b200.engine import Engine
+    eng = Engine(rectangle_mesh(4, 4, 10.0, 10.0))
+    c = np.zeros(8)
+    c[7] = 0.1
+    with pytest.raises(L.TbError):
+        eng.set_bc(1, 1, L.BC_DRAG, c)          # the tracer equation has no boundary drag
 
 
 def test_open_boundary_arrays_north_sea():

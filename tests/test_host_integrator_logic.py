@@ -205,6 +205,38 @@ def test_discontinuous_fields_nikuradse_and_wd_alpha_routing(setup):
         s3.assign_initial_conditions()
 
 
+def test_boundary_drag_tag_routing(setup):
+    """'drag' (BoundaryDragTerm, shallowwater_eq.py:704-726) is a kernel parameter of the marker's slot: bit
+    TB_BC_DRAG + consts[7], alone (the boundary stays closed) or next to open tags; a changed Constant re-sends just
+    that slot; a Function-valued coefficient is refused at construction; an unknown tag raises like the reference
+    (shallowwater_eq.py:291-293)."""
+    make, engines = setup
+    from thetis_b200.shim import Constant, Function
+    s, P1, mesh = make()
+    cd = Constant(0.05)
+    s.bnd_functions["shallow_water"] = {1: {"drag": cd}, 2: {"elev": Constant(0.5), "drag": Constant(0.02)}}
+    s.assign_initial_conditions()
+    eng = engines[0]
+    bcs = {c[2]: c for c in eng.named("set_bc")}
+    assert bcs[1][3] == L.BC_DRAG and bcs[1][4][7] == 0.05 and not bcs[1][4][:7].any()
+    assert bcs[2][3] == L.BC_ELEV | L.BC_DRAG and bcs[2][4][0] == 0.5 and bcs[2][4][7] == 0.02
+    eng.calls.clear()
+    s.timestepper.advance(0.0)
+    assert not eng.named("set_bc")
+    cd.assign(0.08)
+    s.timestepper.advance(1.0)
+    (bc,) = eng.named("set_bc")
+    assert bc[2] == 1 and bc[3] == L.BC_DRAG and bc[4][7] == 0.08
+    s2, P1b, _ = make()
+    s2.bnd_functions["shallow_water"] = {1: {"drag": Function(P1b).assign(0.05)}}
+    with pytest.raises(NotImplementedError, match="drag"):
+        s2.assign_initial_conditions()
+    s3, _, _ = make()
+    s3.bnd_functions["shallow_water"] = {1: {"dragg": Constant(0.05)}}
+    with pytest.raises(Exception, match="Invalid boundary tag"):
+        s3.assign_initial_conditions()
+
+
 def test_each_tracer_sees_only_its_own_boundary_conditions(setup):
     make, engines = setup
     from thetis_b200.shim import Constant

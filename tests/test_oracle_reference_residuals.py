@@ -69,6 +69,18 @@ def test_swe_tendency_equals_the_reference_terms(name):
     assert eu < TOL and ee < TOL, (eu, ee)
 
 
+@pytest.mark.parametrize("name", [n for n in RC.SWE_CASES if n.startswith("boundary_drag")])
+def test_boundary_drag_cases_are_sensitive_to_the_term(name):
+    """BoundaryDragTerm (shallowwater_eq.py:704-726): dropping the 'drag' tags must move the tendency far beyond the
+    parity tolerance, otherwise the cases above would pin nothing"""
+    case = RC.SWE_CASES[name]
+    mesh = RC.build_mesh(case["mesh"])
+    uv, eta = (GOLD[f"swe/{name}/{k}"] for k in ("uv", "eta"))
+    nodrag = dict(case, bnd={mk: {t: v for t, v in funcs.items() if t != "drag"} for mk, funcs in case["bnd"].items()})
+    ku, _ = _swe_oracle(nodrag, mesh).tendency(uv, eta)
+    assert _rel(ku, GOLD[f"swe/{name}/ku"]) > 1e-4
+
+
 @pytest.mark.parametrize("name", list(RC.TRACER_CASES))
 def test_tracer_tendency_equals_the_reference_terms(name):
     case = RC.TRACER_CASES[name]

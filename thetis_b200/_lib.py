@@ -21,7 +21,7 @@ OPT_G_GRAV, OPT_RHO0, OPT_NONLINEAR, OPT_LAX_FRIEDRICHS, OPT_LF_SCALING, OPT_NOR
 # tb_field
 F_BATHYMETRY, F_CORIOLIS, F_MANNING, F_QUAD_DRAG, F_LINEAR_DRAG, F_WIND_STRESS, F_ATM_PRESSURE, \
     F_MOMENTUM_SOURCE, F_VOLUME_SOURCE, F_TRACER_SOURCE, F_VISCOSITY, F_DIFFUSIVITY, F_NIKURADSE, F_WD_ALPHA = range(14)
-BC_ELEV, BC_UV, BC_UN, BC_FLUX, BC_VALUE, BC_DIFF_FLUX = 1, 2, 4, 8, 16, 64
+BC_ELEV, BC_UV, BC_UN, BC_FLUX, BC_VALUE, BC_DIFF_FLUX, BC_DRAG = 1, 2, 4, 8, 16, 64, 128
 
 
 class TbMesh(C.Structure):

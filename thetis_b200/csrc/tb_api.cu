@@ -673,9 +673,11 @@ extern "C" int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const doub
     if (!ctx || eq < 0 || eq > 1) return fail(ctx, TB_ERR_ARG, "bad equation id");
     const int s = find_slot(ctx, marker);
     if (s < 0) return TB_OK;   // marker not present on this (sub)mesh: nothing to do (reference loops over mesh markers)
-    if (opcode & ~(TB_BC_ELEV | TB_BC_UV | TB_BC_UN | TB_BC_FLUX | TB_BC_VALUE | TB_BC_DIFF_FLUX))
+    if (opcode & ~(TB_BC_ELEV | TB_BC_UV | TB_BC_UN | TB_BC_FLUX | TB_BC_VALUE | TB_BC_DIFF_FLUX | TB_BC_DRAG))
         return fail(ctx, TB_ERR_ARG, "invalid boundary tag");
     if ((opcode & TB_BC_DIFF_FLUX) && eq != 1) return fail(ctx, TB_ERR_ARG, "'diff_flux' is a tracer boundary tag");
+    if ((opcode & TB_BC_DRAG) && eq != 0) return fail(ctx, TB_ERR_ARG, "'drag' is a shallow-water boundary tag");
+    if ((opcode & TB_BC_DRAG) && !consts) return fail(ctx, TB_ERR_ARG, "'drag' needs its coefficient in consts[7]");
     TbBcSlot &b = ctx->bc[eq][s];
     b.opcode = opcode | TB_BC_PRESENT;
     b.arr_mask = 0;
@@ -683,6 +685,8 @@ extern "C" int tb_set_bc(tb_ctx *ctx, int eq, int marker, int opcode, const doub
         b.elev = consts[0]; b.uvx = consts[1]; b.uvy = consts[2];
         b.un = consts[3]; b.flux = consts[4]; b.value = consts[5];
         b.diff_flux = consts[6];
+        // shallow-water slots have no 'value' datum (a tracer tag): the field carries the 'drag' coefficient there
+        if (eq == 0) b.value = (opcode & TB_BC_DRAG) ? consts[7] : 0.0;
     }
     return TB_OK;
 }

@@ -28,7 +28,7 @@ struct TbBcSlot {
     int opcode;      // OR of TB_BC_*
     int arr_mask;    // tags whose datum is a per-facet-node array instead of a constant
     int pad;
-    double elev, uvx, uvy, un, flux, value;
+    double elev, uvx, uvy, un, flux, value;   // value: tracer 'value'; in a shallow-water slot the 'drag' coefficient
     double bnd_len;
     double diff_flux;    // tracer 'diff_flux' datum (tracer_eq_2d.py:264-265)
 };

@@ -204,6 +204,26 @@ __device__ __noinline__ void open_boundary_flux(const TbBcTable *bc, int gb, int
     out[5] = un;
 }
 
+// Quadratic friction of the tangential velocity on a boundary facet (BoundaryDragTerm, shallowwater_eq.py:704-726):
+//   f += C_D |u_t| (psi . u_t) ds,  u_t = u - (u.n) n,  2-point Gauss rule like every other facet integral.
+// F[0..3] = the facet's momentum flux tested against phi_p (x, y) and phi_q (x, y).  Rare: out of line and after the
+// Gauss-point loop of the other boundary terms (nothing extra stays live across it), generic kernel only.
+// |u_t| may be exactly zero: library sqrt.
+__device__ __noinline__ void boundary_drag_facet(double cd, double upx, double upy, double uqx, double uqy, double nxs,
+                                                 double nys, double il, double len, double *F) {
+    const double nx = nxs * il, ny = nys * il;
+#pragma unroll 1
+    for (int gp = 0; gp < 2; ++gp) {
+        const double wq_ = gp ? TB_XI2 : TB_XI1, wp_ = 1.0 - wq_;
+        const double uKx = wp_ * upx + wq_ * uqx, uKy = wp_ * upy + wq_ * uqy;
+        const double un = uKx * nx + uKy * ny;
+        const double utx = uKx - un * nx, uty = uKy - un * ny;
+        const double m = 0.5 * cd * sqrt(utx * utx + uty * uty) * len;
+        F[0] += wp_ * m * utx; F[1] += wp_ * m * uty;
+        F[2] += wq_ * m * utx; F[3] += wq_ * m * uty;
+    }
+}
+
 template <bool NONLIN, int SPEC>
 __global__ void __launch_bounds__(TB_P, TB_MINB) swe_stage_kernel(const __grid_constant__ TbSweParams prm) {
     typedef StageSpec<SPEC> SP;
@@ -928,6 +948,11 @@ TB_UNROLL(TB_GP_UNROLL)
                         Ruy[a] -= itA * ty;
                     }
                 }
+                if (SP::generic && (op & TB_BC_DRAG)) {
+                    double Fd[4] = {0.0, 0.0, 0.0, 0.0};
+                    boundary_drag_facet(prm.bc.slots[slot].value, ux[p], uy[p], ux[q], uy[q], nxs, nys, il, len, Fd);
+                    Fpx += Fd[0]; Fpy += Fd[1]; Fqx += Fd[2]; Fqy += Fd[3];
+                }
                 Rux[p] -= Fpx; Ruy[p] -= Fpy; Re[p] -= Fpe;
                 Rux[q] -= Fqx; Ruy[q] -= Fqy; Re[q] -= Fqe;
             }
@@ -1025,6 +1050,8 @@ int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear) {
     const bool rare = p.cd.mode || p.pa.mode >= 2 || p.msrc.mode || p.vsrc.mode || !p.adv_on || p.nik.mode || p.wda.mode == 2 ||
                       dg_coef;
     if (rare) return 0;
+    for (int j = 0; j < p.bc.n_slots; ++j)
+        if (p.bc.slots[j].opcode & TB_BC_DRAG) return 0;     // BoundaryDragTerm lives in the generic kernel only
     // the specialised kernels with a cell rule are written for the symmetric 6-point rule (c_qsym)
     const bool quad6 = p.nquad == 6 && g_quad_sym;
     if (p.visc.mode) {

@@ -66,10 +66,10 @@ _SWE_FIELDS = {
 # coefficients of facet terms: must be continuous (P1); the others may be genuinely discontinuous P1DG fields
 _CONTINUOUS_ONLY = {"bathymetry", "viscosity_h", "diffusivity_h", "wetting_and_drying_alpha"}
 _MODESPLIT_FIELDS = ("coriolis", "momentum_source", "atmospheric_pressure", "volume_source")
-_SWE_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX}
+_SWE_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX, "drag": L.BC_DRAG}
 _TRACER_TAGS = {"elev": L.BC_ELEV, "uv": L.BC_UV, "un": L.BC_UN, "flux": L.BC_FLUX, "value": L.BC_VALUE,
                 "diff_flux": L.BC_DIFF_FLUX}
-_CONST_SLOT = {"elev": 0, "uv": 1, "un": 3, "flux": 4, "value": 5, "diff_flux": 6}
+_CONST_SLOT = {"elev": 0, "uv": 1, "un": 3, "flux": 4, "value": 5, "diff_flux": 6, "drag": 7}
 
 
 def _opt(options, name, default=None):
@@ -205,11 +205,12 @@ class ERKGenericShuOsher:
                     or self.fields.get("quadratic_drag_coefficient") is not None):
                 raise Exception("Cannot set both Nikuradse drag and Manning / dimensionless drag parameter")
             for m, funcs in self.bnd_conditions.items():
-                for k in (funcs or {}):
-                    if k == "drag":
-                        raise NotImplementedError("boundary drag is outside the accelerated path")
+                for k, v in (funcs or {}).items():
                     if k not in _SWE_TAGS:
                         raise Exception(f'Invalid boundary tag "{k}" specified on boundary {m}')
+                    if k == "drag" and not is_constant(v):
+                        # BoundaryDragTerm (shallowwater_eq.py:704-726): the coefficient is a kernel parameter
+                        raise NotImplementedError("spatially varying boundary 'drag' is outside the accelerated path")
             if getattr(self.equation, "tidal_farms", None):
                 raise NotImplementedError("tidal turbines are outside the accelerated path")
         else:
@@ -521,6 +522,8 @@ class ERKGenericShuOsher:
                 if eq == 0:
                     raise Exception(f'Invalid boundary tag "{tag}" specified on boundary {marker}')
                 continue
+            if tag == "drag" and self._modesplit:
+                continue        # ModeSplit2DEquations accepts the tag but has no BoundaryDragTerm (shallowwater_eq.py:953-957)
             op |= tags[tag]
             if is_constant(val):
                 v = constant_value(val)
