@@ -608,6 +608,41 @@ class SWEOracle:
         Ru, Re = self.residual(uv, eta)
         return self.solve_mass(dt * Ru, dt * Re)
 
+    # ------------------------------------------------------------ the reference's wetting-drying mass functional
+    def displaced_mass(self, eta):
+        """`ShallowWaterEquations.mass_term` of the elevation with wetting-drying (shallowwater_eq.py:917-920 =
+        `Equation.mass_term` + `BathymetryDisplacementMassTerm`, :834-850): F(eta)_a = int (eta + f(b + eta)) phi_a dx,
+        f = wd_bathymetry_displacement (utility.py:975-985), cell rule of degree 3 like every `self.dx` integral."""
+        lam, qw = self.lam, self.qw
+        aln = self._alpha_nodal()
+        f = self.wd_bathymetry_displacement(self._at_cell_q(self.bath, lam), self._at_cell_q(eta, lam),
+                                            None if aln is None else self._at_cell_q(aln, lam))
+        F = np.einsum("cab,cb->ca", self.mass, eta)
+        if self.options["use_wetting_and_drying"]:
+            F = F + self.geom.area[:, None] * np.einsum("q,cq,qa->ca", qw, f, lam)
+        return F
+
+    def solve_displaced_mass(self, target, guess, tol=1e-12, max_it=50):
+        """eta with displaced_mass(eta) = target: cell-local Newton iteration (the functional is convex in eta:
+        d/d eta (eta + f) = (1 + H / sqrt(H^2 + alpha^2)) / 2 in (0, 1))."""
+        lam, qw = self.lam, self.qw
+        aln = self._alpha_nodal()
+        al = self.options["wetting_and_drying_alpha"] if aln is None else self._at_cell_q(aln, lam)
+        b_q = self._at_cell_q(self.bath, lam)
+        eta = np.array(guess, dtype=float, copy=True)
+        for _ in range(max_it):
+            G = self.displaced_mass(eta) - target
+            J = self.mass
+            if self.options["use_wetting_and_drying"]:
+                H = b_q + self._at_cell_q(eta, lam)
+                fp = 0.5 * (H / np.sqrt(H ** 2 + np.asarray(al) ** 2) - 1.0)
+                J = J + self.geom.area[:, None, None] * np.einsum("q,cq,qa,qb->cab", qw, fp, lam, lam)
+            d = np.linalg.solve(J, G[..., None])[..., 0]
+            eta -= d
+            if np.abs(d).max() <= tol * max(1.0, np.abs(eta).max()):
+                return eta
+        raise RuntimeError("displaced-mass Newton iteration did not converge")
+
 
 class ShuOsherStepper:
     """
@@ -651,6 +686,44 @@ class ShuOsherStepper:
     def advance(self, t, update_forcings=None):
         for i in range(self.n_stages):
             self.solve_stage(i, t, update_forcings)
+
+
+class DisplacedMassShuOsherStepper(ShuOsherStepper):
+    """
+    Shu-Osher stepper that advances the reference's OWN wetting-drying mass functional (shallowwater_eq.py:917-920):
+        F(eta^(i+1)) = sum_j alpha_ij F(eta^(j)) + beta_i dt R_eta(u^(i)),   F = SWEOracle.displaced_mass,
+    solved cell by cell for eta^(i+1); the velocity keeps the plain P1DG mass.  This is what `d/dt mass_term(u) = R(u)`
+    (the equation every implicit integrator of the reference solves with wetting-drying on, e.g. test_thacker.py)
+    becomes under an explicit Shu-Osher scheme.  `ERKGenericShuOsher` itself cannot be run with wetting-drying in the
+    reference -- its `LinearVariationalProblem` puts the TrialFunction into this nonlinear term -- so
+    neither this stepper nor `ShuOsherStepper` with wetting-drying (plain mass: the extension the CUDA path
+    implements) has a reference counterpart; tests/test_oracle_reference_kat.py compares the two
+    on the Thacker basin of test/swe2d/test_thacker.py.
+    """
+
+    def solve_stage(self, i, t, update_forcings=None):
+        if update_forcings is not None:
+            update_forcings(t + self.c[i] * self.dt)
+        orc = self.rhs
+        uv, eta = self.state
+        if i == 0:
+            self.stage_sol[0][0][...] = uv
+            self.stage_sol[0][1][...] = eta
+            self._F = [orc.displaced_mass(eta)]
+        Ru, Re = orc.residual(uv, eta)
+        ku = np.linalg.solve(orc.mass, self.dt * Ru)
+        new_uv = self.beta[i + 1][i] * ku
+        target = self.beta[i + 1][i] * self.dt * Re
+        for j in range(i + 1):
+            if self.alpha[i + 1][j] != 0.0:
+                new_uv = new_uv + self.alpha[i + 1][j] * self.stage_sol[j][0]
+                target = target + self.alpha[i + 1][j] * self._F[j]
+        eta[...] = orc.solve_displaced_mass(target, eta)
+        uv[...] = new_uv
+        if i < self.n_stages - 1:
+            self.stage_sol[i + 1][0][...] = uv
+            self.stage_sol[i + 1][1][...] = eta
+            self._F.append(orc.displaced_mass(eta))
 
 
 class ButcherStepper:

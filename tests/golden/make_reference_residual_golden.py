@@ -147,11 +147,18 @@ def run_swe(name, case, seed):
         else:
             mass = eq.mass_term(eq.trial)
         k = _solve_mass(mass, F, st.V)
+        nt = st.m2.n_cells
+        out = dict(uv=uv, eta=eta, ku=k.subfunctions[0].dat.data.reshape(nt, 3, 2).copy(),
+                   ke=k.subfunctions[1].dat.data.reshape(nt, 3).copy())
+        if o["use_wetting_and_drying"]:
+            # the reference's OWN mass functional of the state with wetting-drying (shallowwater_eq.py:917-920:
+            # Equation.mass_term + BathymetryDisplacementMassTerm), stored as M^-1 F(u) with the plain P1DG mass M
+            m = _solve_mass(mass, eq.mass_term(sol), st.V)
+            out["me"] = m.subfunctions[1].dat.data.reshape(nt, 3).copy()
+            assert np.allclose(m.subfunctions[0].dat.data.reshape(nt, 3, 2), uv, rtol=0, atol=1e-13)
     finally:
         PC["g_grav"].assign(g_old)
-    nt = st.m2.n_cells
-    return dict(uv=uv, eta=eta, ku=k.subfunctions[0].dat.data.reshape(nt, 3, 2).copy(),
-                ke=k.subfunctions[1].dat.data.reshape(nt, 3).copy())
+    return out
 
 
 def run_tracer(name, case, seed):

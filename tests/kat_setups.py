@@ -255,3 +255,67 @@ def hadv_timestep(mesh):
     uniform mesh and constant depth make both P1 projections exact."""
     h = np.sqrt(mesh.cell_area().min())
     return 0.05 * h / (np.sqrt(9.81 * HADV["depth"]) + abs(HADV["u"]))
+
+
+# ------------------------------------------------------------------------------------------------ Thacker basin
+# test/swe2d/test_thacker.py:40-96 (wetting-drying; the reference runs it with its implicit integrators only)
+THACKER = dict(l_mesh=951646.46, D0=50.0, L=430620.0, eta0=2.0, t_end=43200.0,
+               # max_err of test_thacker.py:17-26 for (n, stepper family)
+               max_err={(10, "BackwardEuler"): 0.33, (25, "BackwardEuler"): 0.19, (10, "other"): 0.26, (25, "other"): 0.15})
+
+
+def thacker_problem(n):
+    """Mesh (`SquareMesh(n, n, l_mesh)`), nodal bathymetry, projected initial elevation and the P1 wetting-drying alpha
+    of `use_automatic_wetting_and_drying_alpha` (solver2d.py:279-287: cell widths . |grad b|, utility.py:716-739,
+    interpolated into P1 -- where cells meet at a vertex Firedrake keeps the value of whichever cell it visits last; the
+    maximum over the adjacent cells is taken here)."""
+    from thetis_b200.mesh import rectangle_mesh
+    T = THACKER
+    l, D0, L, eta0 = T["l_mesh"], T["D0"], T["L"], T["eta0"]
+    A = ((D0 + eta0) ** 2 - D0 ** 2) / ((D0 + eta0) ** 2 + D0 ** 2)
+    x0 = y0 = l / 2
+    r2 = lambda x, y: (x - x0) ** 2 + (y - y0) ** 2            # noqa: E731
+    bath = lambda x, y: D0 * (1 - r2(x, y) / L ** 2)            # noqa: E731
+    elev = lambda x, y: D0 * (np.sqrt(1 - A * A) / (1 - A) - 1 - r2(x, y) * ((1 + A) / (1 - A) - 1) / L ** 2)   # noqa: E731
+    mesh = rectangle_mesh(n, n, l, l)
+    bv = bath(mesh.coords[:, 0], mesh.coords[:, 1])
+    xc = mesh.coords[mesh.cells]
+    widths = np.ptp(xc, axis=1)                                                # (nt, 2)
+    area2 = ((xc[:, 1, 0] - xc[:, 0, 0]) * (xc[:, 2, 1] - xc[:, 0, 1])
+             - (xc[:, 1, 1] - xc[:, 0, 1]) * (xc[:, 2, 0] - xc[:, 0, 0]))
+    # gradient of the P1 bathymetry per cell
+    b = bv[mesh.cells]
+    gx = (b[:, 0] * (xc[:, 1, 1] - xc[:, 2, 1]) + b[:, 1] * (xc[:, 2, 1] - xc[:, 0, 1]) + b[:, 2] * (xc[:, 0, 1] - xc[:, 1, 1])) / area2
+    gy = (b[:, 0] * (xc[:, 2, 0] - xc[:, 1, 0]) + b[:, 1] * (xc[:, 0, 0] - xc[:, 2, 0]) + b[:, 2] * (xc[:, 1, 0] - xc[:, 0, 0])) / area2
+    al_cell = widths[:, 0] * np.abs(gx) + widths[:, 1] * np.abs(gy)
+    al_v = np.zeros(mesh.n_vertices)
+    np.maximum.at(al_v, mesh.cells.reshape(-1), np.repeat(al_cell, 3))
+    return dict(mesh=mesh, bath=bv[mesh.cells], alpha=al_v[mesh.cells], elev_init=elev, eta0=project_dg1(mesh, elev),
+                centre=(x0, y0))
+
+
+def thacker_error(p, eta, k=8):
+    """test_thacker.py:83-93: mask = (1 - tanh((r - 420 km) / 1 km)) / 2, eta <- project(mask * eta),
+    errornorm(mask * elev_init, eta) / l_mesh.  Integrals by a degree-10 Duffy rule on a k x k sub-triangulation of
+    every cell (the 1 km wide mask edge is far below the cell size of the test's meshes)."""
+    mesh = p["mesh"]
+    lam6, w6 = duffy_rule(6)
+    pts, wts = [], []
+    for i in range(k):
+        for j in range(k - i):
+            tris = [np.array([[i, j], [i + 1, j], [i, j + 1]], float) / k]
+            if j < k - i - 1:
+                tris.append(np.array([[i + 1, j], [i + 1, j + 1], [i, j + 1]], float) / k)
+            for t in tris:
+                xy = lam6 @ t
+                pts.append(np.stack([1 - xy[:, 0] - xy[:, 1], xy[:, 0], xy[:, 1]], 1))
+                wts.append(w6 / k ** 2)
+    lam, w = np.concatenate(pts), np.concatenate(wts)
+    xc = mesh.coords[mesh.cells]
+    xq = np.einsum("qa,cai->cqi", lam, xc)
+    r = np.hypot(xq[..., 0] - p["centre"][0], xq[..., 1] - p["centre"][1])
+    mask = 0.5 * (1 - np.tanh((r - 420000.0) / 1000.0))
+    rhs = np.einsum("q,cq,qa->ca", w, mask * np.einsum("qa,ca->cq", lam, eta), lam)
+    proj = np.einsum("ab,cb->ca", np.linalg.inv(_MREF), rhs)
+    diff = mask * p["elev_init"](xq[..., 0], xq[..., 1]) - np.einsum("qa,ca->cq", lam, proj)
+    return float(np.sqrt((mesh.cell_area()[:, None] * w[None] * diff ** 2).sum())) / THACKER["l_mesh"]

@@ -163,3 +163,54 @@ def test_tracer_h_advection_convergence():
     errs = [hadv_run_oracle(r) for r in refs]
     slope = K.convergence_slope(refs, errs)
     assert slope > 2 * (1 - 0.2), (slope, errs)
+
+
+# ---------------------------------------------------------------- Thacker basin (wetting-drying)
+def thacker_run(n, dt, stepper_cls):
+    """run of test_thacker.py:40-82 with an EXPLICIT SSPRK33 stepper of the oracle: closed basin, nonlinear equations,
+    Lax-Friedrichs on, wetting-drying with the automatic P1 alpha, one period of the analytic oscillation."""
+    p = K.thacker_problem(n)
+    orc = O.SWEOracle(p["mesh"], p["bath"], options=dict(use_wetting_and_drying=True, wetting_and_drying_alpha=p["alpha"]))
+    eta = p["eta0"].copy()
+    uv = np.zeros(eta.shape + (2,))
+    st = stepper_cls(orc, [uv, eta], dt)
+    xc = p["mesh"].coords[p["mesh"].cells].mean(1)
+    ic = int(np.argmin(np.hypot(xc[:, 0] - p["centre"][0], xc[:, 1] - p["centre"][1])))
+    nsteps = int(round(K.THACKER["t_end"] / dt))
+    vol0 = orc.displaced_mass(eta).sum()
+    centre = [float(eta[ic].mean())]
+    with np.errstate(all="ignore"):
+        for i in range(nsteps):
+            st.advance(i * dt)
+            centre.append(float(eta[ic].mean()))
+    return p, orc, eta, np.array(centre), (orc.displaced_mass(eta).sum() - vol0) / abs(vol0)
+
+
+def test_thacker_displaced_mass_explicit_step_meets_a_reference_threshold():
+    """The explicit Shu-Osher step that advances the reference's own wetting-drying mass functional
+    (O.DisplacedMassShuOsherStepper; shallowwater_eq.py:917-920) carries the Thacker oscillation through its full period
+    and ends inside the reference's threshold for its first-order implicit stepper on the same 10 x 10 mesh
+    (test_thacker.py:19: BackwardEuler 0.33; the second-order implicit steppers are held to 0.26, which this explicit
+    step misses at 0.29 -- reported, not asserted).  The displaced volume int (eta + f) is conserved to rounding."""
+    p, orc, eta, centre, dvol = thacker_run(10, 100.0, O.DisplacedMassShuOsherStepper)
+    assert np.isfinite(eta).all()
+    err = K.thacker_error(p, eta)
+    assert err < K.THACKER["max_err"][(10, "BackwardEuler")], err
+    assert abs(dvol) < 1e-12
+    # the free surface at the centre of the basin falls below -2 m at half period and is back near +2 m at the end
+    assert centre.min() < -2.0 and centre[-1] > 1.5, (centre.min(), centre[-1])
+
+
+def test_thacker_plain_mass_extension_is_not_a_drying_model():
+    """KNOWN LIMITATION, pinned so that the documentation stays true: the explicit wetting-drying
+    step the CUDA path implements keeps the PLAIN P1DG mass matrix (O.ShuOsherStepper; the same step the -m gpu tests
+    compare the kernels with).  It drops d/dt of the bathymetry displacement, so cells that are almost dry keep their
+    full storage while their transport depth goes to zero: in the Thacker basin the water that ran up the rim during
+    the first half period does not come back, and the reference's criterion is missed by a factor of six.  The
+    extension is therefore meaningful only where the water stays deep against alpha (the benchmark configuration: depth
+    10 - 200 m, alpha = 0.5 m), not as a model of a moving shoreline."""
+    p, orc, eta, centre, _ = thacker_run(10, 300.0, O.ShuOsherStepper)
+    assert np.isfinite(eta).all()
+    err = K.thacker_error(p, eta)
+    assert err > 1.0, err                                # threshold of the reference: 0.26 - 0.33
+    assert centre[-1] < -1.0                             # the centre never recovers from the half-period low

@@ -69,6 +69,23 @@ def test_swe_tendency_equals_the_reference_terms(name):
     assert eu < TOL and ee < TOL, (eu, ee)
 
 
+@pytest.mark.parametrize("name", [n for n, c in RC.SWE_CASES.items() if c.get("options", {}).get("use_wetting_and_drying")])
+def test_wetting_drying_mass_functional_equals_the_reference_mass_term(name):
+    """`ShallowWaterEquations.mass_term(solution)` with wetting-drying (shallowwater_eq.py:917-920: the plain mass
+    plus BathymetryDisplacementMassTerm, :834-850) executed from the reference tree, against the oracle's
+    `displaced_mass`; and the cell-local Newton solve inverts it (used by DisplacedMassShuOsherStepper)."""
+    case = RC.SWE_CASES[name]
+    mesh = RC.build_mesh(case["mesh"])
+    eta = GOLD[f"swe/{name}/eta"]
+    orc = _swe_oracle(case, mesh)
+    F = orc.displaced_mass(eta)
+    me = np.linalg.solve(orc.mass, F[..., None])[..., 0]
+    assert _rel(me, GOLD[f"swe/{name}/me"]) < TOL
+    assert _rel(me, eta) > 1e-3                        # the displacement term is really there
+    back = orc.solve_displaced_mass(F, np.zeros_like(eta))
+    assert _rel(back, eta) < 1e-11
+
+
 @pytest.mark.parametrize("name", [n for n in RC.SWE_CASES if n.startswith("boundary_drag")])
 def test_boundary_drag_cases_are_sensitive_to_the_term(name):
     """BoundaryDragTerm (shallowwater_eq.py:704-726): dropping the 'drag' tags must move the tendency far beyond the
