@@ -82,7 +82,12 @@ typedef enum {
     TB_OPT_TRACER_CONSERVATIVE = 16,   /* tracer use_conservative_form (options.py:543; tracer_eq_2d.py:323-437) */
     TB_OPT_MOMENTUM_ADVECTION = 17,    /* 0: no HorizontalAdvectionTerm although the depth is nonlinear
                                           (ModeSplit2DEquations, shallowwater_eq.py:931-966); default 1 */
-    TB_OPT_VON_KARMAN = 18             /* physical_constants['von_karman'] (Nikuradse drag, shallowwater_eq.py:696) */
+    TB_OPT_VON_KARMAN = 18,            /* physical_constants['von_karman'] (Nikuradse drag, shallowwater_eq.py:696) */
+    TB_OPT_WD_DISPLACED_MASS = 19      /* wetting-drying, nonlinear equations: the elevation update of every Shu-Osher
+                                          stage (a0 + a1 = 1) advances the reference's own mass functional
+                                          int (eta + f(b + eta)) phi (shallowwater_eq.py:917-920, :834-850) instead of the
+                                          plain mass: cell-local Newton solve in the stage kernel's epilogue (generic
+                                          kernel).  Default 0 = plain mass.  DESIGN.md section 6. */
 } tb_option;
 
 /* Coefficient fields: the `fields` dict of solver2d.py:546-558 plus bathymetry. */

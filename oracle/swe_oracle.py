@@ -630,6 +630,7 @@ class SWEOracle:
         al = self.options["wetting_and_drying_alpha"] if aln is None else self._at_cell_q(aln, lam)
         b_q = self._at_cell_q(self.bath, lam)
         eta = np.array(guess, dtype=float, copy=True)
+        prev = np.inf
         for _ in range(max_it):
             G = self.displaced_mass(eta) - target
             J = self.mass
@@ -639,8 +640,11 @@ class SWEOracle:
                 J = J + self.geom.area[:, None, None] * np.einsum("q,cq,qa,qb->cab", qw, fp, lam, lam)
             d = np.linalg.solve(J, G[..., None])[..., 0]
             eta -= d
-            if np.abs(d).max() <= tol * max(1.0, np.abs(eta).max()):
+            dm, scale = np.abs(d).max(), max(1.0, np.abs(eta).max())
+            # converged, or stagnated at the rounding level of an ill-conditioned (almost dry) cell
+            if dm <= tol * scale or (dm >= 0.5 * prev and dm <= 1e-8 * scale):
                 return eta
+            prev = dm
         raise RuntimeError("displaced-mass Newton iteration did not converge")
 
 

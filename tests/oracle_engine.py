@@ -174,10 +174,19 @@ class OracleEngine:
         self.n_stage_launches += 1
         s = self._rec(src, 9)
         uv, eta = s[:, :6].reshape(-1, 3, 2).copy(), s[:, 6:].copy()
-        ku, ke = self.swe_oracle().tendency(uv, eta)
+        orc = self.swe_oracle()
+        ku, ke = orc.tendency(uv, eta)
         new = a1 * s + bdt * np.concatenate([ku.reshape(-1, 6), ke], axis=1)
         if u0 is not None:
             new = new + a0 * self._rec(u0, 9)
+        if self.opt.get(L.OPT_WD_DISPLACED_MASS) and orc.options["use_wetting_and_drying"]:
+            # TB_OPT_WD_DISPLACED_MASS: the stage advances the reference's mass functional of the elevation
+            assert abs(a0 + a1 - 1.0) < 1e-9
+            _, Re = orc.residual(uv, eta)
+            target = a1 * orc.displaced_mass(eta) + bdt * Re
+            if u0 is not None:
+                target = target + a0 * orc.displaced_mass(self._rec(u0, 9)[:, 6:].copy())
+            new[:, 6:] = orc.solve_displaced_mass(target, eta)
         self._rec(dst, 9)[...] = new
 
     def limiter_apply_to(self, c_in, c_out):

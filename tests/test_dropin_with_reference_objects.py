@@ -303,3 +303,51 @@ def test_b200_limiter_on_a_reference_shaped_space(ref):
     want = vertex_based_limiter(st.m2, q0)
     assert np.abs(want - q0).max() > 0.05                           # the limiter did something
     assert np.abs(f.dat.data.reshape(-1, 3) - want).max() < 1e-13
+
+
+@pytest.mark.parametrize("name", ["wetting_drying_manning", "wetting_drying_alpha_p1"])
+def test_displaced_mass_wetting_drying_step_on_reference_objects(ref, name):
+    """`SSPRK33(..., wd_mass='displaced')` on the reference's own ShallowWaterEquations instance with wetting-drying:
+    the option reaches the engine, every stage advances the reference's mass functional (the oracle-backed engine does
+    what TB_OPT_WD_DISPLACED_MASS does in the kernel) and the run equals the oracle's DisplacedMassShuOsherStepper; the
+    displaced volume int (eta + f) is conserved on the closed set-up; the Butcher-form classes refuse the option."""
+    import reference_cases as RC
+    from thetis_b200 import rungekutta as B
+    from thetis_b200 import _lib as L
+    from oracle import swe_oracle as O
+    import test_oracle_reference_residuals as T
+    G = ref.G
+    case = RC.SWE_CASES[name]
+    st = G.Setup(case)
+    eq, fields, bnd, o = G.swe_equation(st)
+    sol, uv0, eta0 = st.swe_solution(7)
+    topt = types.SimpleNamespace(ad_block_tag=None, solver_parameters={})
+    dt, n_steps = 2.0, 3
+    ti = B.SSPRK33(eq, sol, fields, dt, topt, bnd, wd_mass="displaced")
+    eng = ref.engines[-1]
+    assert eng.opt[L.OPT_WD_DISPLACED_MASS] == 1.0
+    for i in range(n_steps):
+        ti.advance(i * dt)
+    nt = st.m2.n_cells
+    uv = sol.subfunctions[0].dat.data.reshape(nt, 3, 2)
+    eta = sol.subfunctions[1].dat.data.reshape(nt, 3)
+    orc = T._swe_oracle(case, st.m2)
+    wuv, weta = uv0.copy(), eta0.copy()
+    ost = O.DisplacedMassShuOsherStepper(orc, [wuv, weta], dt)
+    for i in range(n_steps):
+        ost.advance(i * dt)
+    assert _rel(uv, wuv) < 1e-11 and _rel(eta, weta) < 1e-11
+    # ... and differs from the plain-mass step by far more than that
+    puv, peta = uv0.copy(), eta0.copy()
+    pst = O.ShuOsherStepper(orc, [puv, peta], dt)
+    for i in range(n_steps):
+        pst.advance(i * dt)
+    assert _rel(eta, peta) > 1e-4
+    if not case.get("bnd"):
+        v0, v1 = orc.displaced_mass(eta0).sum(), orc.displaced_mass(eta).sum()
+        assert abs(v1 - v0) <= 1e-12 * abs(v0)
+    with pytest.raises(NotImplementedError, match="displaced"):
+        B.ERKLSPUM2(eq, st.swe_solution(7)[0], fields, dt, topt, bnd, wd_mass="displaced")
+    # default: plain mass, the option is sent as 0
+    B.SSPRK33(eq, st.swe_solution(7)[0], fields, dt, topt, bnd)
+    assert ref.engines[-1].opt[L.OPT_WD_DISPLACED_MASS] == 0.0

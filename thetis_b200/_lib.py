@@ -17,7 +17,8 @@ TB_OK = 0
 OPT_G_GRAV, OPT_RHO0, OPT_NONLINEAR, OPT_LAX_FRIEDRICHS, OPT_LF_SCALING, OPT_NORM_SMOOTHER, \
     OPT_WETTING_DRYING, OPT_WD_ALPHA, OPT_LF_TRACER, OPT_LF_TRACER_SCALING, OPT_TRACER_VEL_FACTOR, \
     OPT_FORCE_GENERIC_KERNEL, OPT_SIPG_FACTOR, OPT_SIPG_FACTOR_TRACER, OPT_GRAD_DIV_VISCOSITY, \
-    OPT_GRAD_DEPTH_VISCOSITY, OPT_TRACER_CONSERVATIVE, OPT_MOMENTUM_ADVECTION, OPT_VON_KARMAN = range(19)
+    OPT_GRAD_DEPTH_VISCOSITY, OPT_TRACER_CONSERVATIVE, OPT_MOMENTUM_ADVECTION, OPT_VON_KARMAN, \
+    OPT_WD_DISPLACED_MASS = range(20)
 # tb_field
 F_BATHYMETRY, F_CORIOLIS, F_MANNING, F_QUAD_DRAG, F_LINEAR_DRAG, F_WIND_STRESS, F_ATM_PRESSURE, \
     F_MOMENTUM_SOURCE, F_VOLUME_SOURCE, F_TRACER_SOURCE, F_VISCOSITY, F_DIFFUSIVITY, F_NIKURADSE, F_WD_ALPHA = range(14)

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libthetis_b200.so")
 SOURCES = ["tb_kernels.cu", "tb_tracer.cu", "tb_api.cu"]
-HEADERS = [os.path.join(CSRC, "tb_internal.h"), os.path.join(CSRC, "tb_device.cuh"),
+HEADERS = [os.path.join(CSRC, "tb_internal.h"), os.path.join(CSRC, "tb_device.cuh"), os.path.join(CSRC, "tb_wd_mass.cuh"),
            os.path.join(HERE, "..", "include", "thetis_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

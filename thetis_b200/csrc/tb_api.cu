@@ -90,6 +90,7 @@ struct tb_ctx {
     double lf_tracer_sigma = 1.0, tracer_vel_factor = 1.0;
     double sipg = 1.0, sipg_tracer = 1.0, von_karman = 0.4;
     int graddiv = 0, graddepth = 1, tracer_conservative = 0, momentum_advection = 1;
+    int wd_mass = 0;                // TB_OPT_WD_DISPLACED_MASS
     FieldStore fields[TB_F_COUNT];
     // bcs: eq 0 swe, 1 tracer
     std::vector<int> slot_marker;       // slot -> marker
@@ -586,6 +587,7 @@ extern "C" int tb_set_option(tb_ctx *ctx, int option, double value) {
         case TB_OPT_TRACER_CONSERVATIVE: ctx->tracer_conservative = value != 0.0; break;
         case TB_OPT_MOMENTUM_ADVECTION: ctx->momentum_advection = value != 0.0; break;
         case TB_OPT_VON_KARMAN: ctx->von_karman = value; break;
+        case TB_OPT_WD_DISPLACED_MASS: ctx->wd_mass = value != 0.0; break;
         default: return fail(ctx, TB_ERR_ARG, "unknown option");
     }
     return TB_OK;
@@ -842,6 +844,11 @@ static int swe_stage_impl(tb_ctx *ctx, double a0, double a1, double b_dt, const 
     p.wd_alpha2 = ctx->wd_alpha * ctx->wd_alpha;
     p.lf_on = ctx->lf_on;
     p.wd_on = ctx->wd_on && ctx->nonlinear;
+    p.wd_mass = (ctx->wd_mass && p.wd_on) ? 1 : 0;
+    if (p.wd_mass && fabs(a0 + a1 - 1.0) > 1e-9)
+        return fail(ctx, TB_ERR_STATE,
+                    "TB_OPT_WD_DISPLACED_MASS advances a mass functional: it needs a Shu-Osher stage (a0 + a1 = 1), not a "
+                    "tendency evaluation");
     fill_coef(ctx->fields[TB_F_CORIOLIS], p.cor);
     fill_coef(ctx->fields[TB_F_MANNING], p.man);
     fill_coef(ctx->fields[TB_F_QUAD_DRAG], p.cd);

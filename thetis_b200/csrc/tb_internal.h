@@ -96,7 +96,8 @@ struct TbSweParams {
     double *partials;             // optional [n_patches][4]: fused diagnostics of u_out (int eta^2, |u|^2, eta, eta+b)
     const TbHaloFused *halo;      // optional (device): fused halo exchange, CTAs [0, n_bpatch) push
     const unsigned long long *push_dst;   // [n_entries] peer addresses of the pushed records for THIS output buffer
-    int n_bpatch, pad1_;
+    int n_bpatch;
+    int wd_mass;                  // TB_OPT_WD_DISPLACED_MASS: displaced-mass elevation update (tb_wd_mass.cuh)
     TbCoef cor, man, cd, lin, wind, pa, msrc, vsrc, visc, nik, wda;
     double kappa;                 // physical_constants['von_karman'] (Nikuradse drag)
     double sipg;                  // sipg_factor (HorizontalViscosityTerm, shallowwater_eq.py:558)

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include "tb_internal.h"
 #include "tb_device.cuh"
+#include "tb_wd_mass.cuh"
 
 #ifndef TB_HALO_SPEC
 #define TB_HALO_SPEC 6        // halo elements per thread fetched speculatively (covers NH <= 85)
@@ -973,6 +974,18 @@ TB_UNROLL(TB_GP_UNROLL)
 #pragma unroll
             for (int k = 0; k < 9; ++k) res[k] = fma(prm.a0, O[tid * 9 + k], res[k]);
         }
+        if (SP::generic && NONLIN && prm.wd_mass) {
+            // explicit step on the reference's wetting-drying mass functional int (eta + f(b + eta)) phi
+            // (shallowwater_eq.py:917-920) instead of the plain mass: res[6..8] holds the plain-mass update, the
+            // cell-local Newton solve of tb_wd_mass.cuh turns it into the displaced-mass one
+            double e0[3] = {0.0, 0.0, 0.0};
+            if (prm.u0) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) e0[a] = O[tid * 9 + 6 + a];
+            }
+            tb_wd_displaced_update(res + 6, prm.u0 ? prm.a0 : 0.0, e0, prm.a1, et, b, var_al ? al : nullptr, a2,
+                                   &c_qlam[0][0], c_qw, prm.nquad);
+        }
         if (prm.partials && active) {
             // fused print_state / volume diagnostics of the state this launch produces (same closed forms as
             // swe_integrals_partial): int f g = A/12 (sum_a f_a g_a + (sum f)(sum g))
@@ -1049,7 +1062,7 @@ int tb_swe_stage_spec(const TbSweParams &p, bool nonlinear) {
     const bool dg_coef = p.cor.mode == 3 || p.man.mode == 3 || p.lin.mode == 3 || p.wind.mode == 3;   // P1DG coefficient fields
     const bool rare = p.cd.mode || p.pa.mode >= 2 || p.msrc.mode || p.vsrc.mode || !p.adv_on || p.nik.mode || p.wda.mode == 2 ||
                       dg_coef;
-    if (rare) return 0;
+    if (rare || p.wd_mass) return 0;
     for (int j = 0; j < p.bc.n_slots; ++j)
         if (p.bc.slots[j].opcode & TB_BC_DRAG) return 0;     // BoundaryDragTerm lives in the generic kernel only
     // the specialised kernels with a cell rule are written for the symmetric 6-point rule (c_qsym)

@@ -113,7 +113,12 @@ class ERKGenericShuOsher:
                             # int eta, int (eta + bathymetry) of the new solution into it (tb_stage_integrals)
 
     def __init__(self, equation, solution, fields, dt, options=None, bnd_conditions=None, terms_to_add="all",
-                 sync_policy="every_step"):
+                 sync_policy="every_step", wd_mass=None):
+        # wd_mass: 'plain' (default) | 'displaced' -- which mass functional the explicit wetting-drying step advances
+        # (DESIGN.md section 6); also read from options.explicit_wetting_and_drying_mass when not given
+        self.wd_mass = wd_mass if wd_mass is not None else _opt(options, "explicit_wetting_and_drying_mass", "plain")
+        if self.wd_mass not in ("plain", "displaced"):
+            raise ValueError(f"wd_mass must be 'plain' or 'displaced', not {self.wd_mass!r}")
         self.equation = equation
         self.solution = solution
         self.fields = fields if fields is not None else {}
@@ -287,6 +292,11 @@ class ERKGenericShuOsher:
         for m, ln in self.adaptor.boundary_len.items():
             eng.set_boundary_length(m, ln)
         if self._kind == "swe":
+            displaced = self.wd_mass == "displaced" and bool(depth.use_wetting_and_drying)
+            if displaced and (self.butcher_form or not depth.use_nonlinear_equations):
+                raise NotImplementedError("wd_mass='displaced' advances the reference's wetting-drying mass functional "
+                                          "stage by stage: Shu-Osher integrators with nonlinear equations only")
+            eng.set_option(L.OPT_WD_DISPLACED_MASS, displaced)
             eng.set_option(L.OPT_LAX_FRIEDRICHS, bool(_opt(eqo, "use_lax_friedrichs_velocity", True)))
             eng.set_option(L.OPT_GRAD_DIV_VISCOSITY, bool(_opt(eqo, "use_grad_div_viscosity_term", False)))
             eng.set_option(L.OPT_GRAD_DEPTH_VISCOSITY, bool(_opt(eqo, "use_grad_depth_viscosity_term", True)))
