@@ -264,11 +264,13 @@ THACKER = dict(l_mesh=951646.46, D0=50.0, L=430620.0, eta0=2.0, t_end=43200.0,
                max_err={(10, "BackwardEuler"): 0.33, (25, "BackwardEuler"): 0.19, (10, "other"): 0.26, (25, "other"): 0.15})
 
 
-def thacker_problem(n):
+def thacker_problem(n, alpha_max=None):
     """Mesh (`SquareMesh(n, n, l_mesh)`), nodal bathymetry, projected initial elevation and the P1 wetting-drying alpha
     of `use_automatic_wetting_and_drying_alpha` (solver2d.py:279-287: cell widths . |grad b|, utility.py:716-739,
     interpolated into P1 -- where cells meet at a vertex Firedrake keeps the value of whichever cell it visits last; the
-    maximum over the adjacent cells is taken here)."""
+    maximum over the adjacent cells is taken here).  ``alpha_max``: `wetting_and_drying_alpha_max` (options.py:897-902;
+    the reference's default is Constant(2.0), which the test leaves in place; None = uncapped, 5 - 44 m on the 10 x 10
+    mesh)."""
     from thetis_b200.mesh import rectangle_mesh
     T = THACKER
     l, D0, L, eta0 = T["l_mesh"], T["D0"], T["L"], T["eta0"]
@@ -290,6 +292,8 @@ def thacker_problem(n):
     al_cell = widths[:, 0] * np.abs(gx) + widths[:, 1] * np.abs(gy)
     al_v = np.zeros(mesh.n_vertices)
     np.maximum.at(al_v, mesh.cells.reshape(-1), np.repeat(al_cell, 3))
+    if alpha_max is not None:
+        al_v = np.minimum(al_v, alpha_max)
     return dict(mesh=mesh, bath=bv[mesh.cells], alpha=al_v[mesh.cells], elev_init=elev, eta0=project_dg1(mesh, elev),
                 centre=(x0, y0))
 

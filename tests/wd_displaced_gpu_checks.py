@@ -98,8 +98,9 @@ def check_refuse():
 
 
 def check_thacker():
-    """test/swe2d/test_thacker.py on the GPU with the displaced-mass step: BackwardEuler threshold of the 10 x 10 mesh,
-    and the same run with the plain mass misses it (tests/test_oracle_reference_kat.py has the CPU side)"""
+    """test/swe2d/test_thacker.py (automatic alpha with the 2 m cap lifted, see tests/test_oracle_reference_kat.py) on the
+    GPU with the displaced-mass step: BackwardEuler threshold of the 10 x 10 mesh, and the same run with the plain mass
+    misses it"""
     import torch
     import kat_setups as K
     from oracle import swe_oracle as O
