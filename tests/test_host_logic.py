@@ -29,6 +29,25 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().tb_version() == 100
 
 
+def test_binding_constants_equal_the_header_enums():
+    """the numeric ids the ctypes binding sends (thetis_b200/_lib.py) are the enumerators of include/thetis_b200.h:
+    a drift between the two would silently set the wrong option / field / boundary tag"""
+    from thetis_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "thetis_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    enums = {k: int(v) for k, v in re.findall(r"\b(TB_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr)}
+    checked = 0
+    for prefix, strip in (("OPT_", "TB_OPT_"), ("F_", "TB_F_"), ("BC_", "TB_BC_")):
+        for name, val in vars(_lib).items():
+            if name.startswith(prefix) and isinstance(val, int):
+                assert enums[strip + name[len(prefix):]] == val, name
+                checked += 1
+        header_side = {k for k in enums if k.startswith(strip) and k != "TB_F_COUNT"}
+        binding_side = {strip + n[len(prefix):] for n, v in vars(_lib).items() if n.startswith(prefix) and isinstance(v, int)}
+        assert header_side == binding_side, header_side ^ binding_side
+    assert checked >= 40 and enums["TB_F_COUNT"] == len([n for n in vars(_lib) if n.startswith("F_")])
+
+
 def test_create_fails_loudly_without_gpu_or_with_bad_mesh():
     import torch
     from thetis_b200 import _lib
