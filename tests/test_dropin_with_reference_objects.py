@@ -351,3 +351,10 @@ def test_displaced_mass_wetting_drying_step_on_reference_objects(ref, name):
     # default: plain mass, the option is sent as 0
     B.SSPRK33(eq, st.swe_solution(7)[0], fields, dt, topt, bnd)
     assert ref.engines[-1].opt[L.OPT_WD_DISPLACED_MASS] == 0.0
+    # behind an unmodified FlowSolver2d (which constructs the integrators itself): the module-level default
+    B.WD_MASS_DEFAULT = "displaced"
+    try:
+        B.SSPRK33(eq, st.swe_solution(7)[0], fields, dt, topt, bnd)
+        assert ref.engines[-1].opt[L.OPT_WD_DISPLACED_MASS] == 1.0
+    finally:
+        B.WD_MASS_DEFAULT = "plain"

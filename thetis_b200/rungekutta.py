@@ -31,6 +31,11 @@ __all__ = ["SSPRK33", "SSPRK22", "ExportStage", "ERKGenericShuOsher", "ERKGeneri
            "ForwardEuler", "butcher_to_shuosher_form", "CFL_UNCONDITIONALLY_STABLE"]
 
 CFL_UNCONDITIONALLY_STABLE = np.inf
+# which mass functional the explicit wetting-drying step advances when neither the `wd_mass` argument nor
+# `options.explicit_wetting_and_drying_mass` says so: 'plain' | 'displaced' (DESIGN.md section 6).  FlowSolver2d builds
+# the integrators itself (solver2d.py:572-573), so a script that wants the displaced-mass step behind an unmodified
+# Thetis sets  thetis_b200.rungekutta.WD_MASS_DEFAULT = 'displaced'  before create_timestepper().
+WD_MASS_DEFAULT = "plain"
 
 
 def butcher_to_shuosher_form(a, b):
@@ -116,7 +121,9 @@ class ERKGenericShuOsher:
                  sync_policy="every_step", wd_mass=None):
         # wd_mass: 'plain' (default) | 'displaced' -- which mass functional the explicit wetting-drying step advances
         # (DESIGN.md section 6); also read from options.explicit_wetting_and_drying_mass when not given
-        self.wd_mass = wd_mass if wd_mass is not None else _opt(options, "explicit_wetting_and_drying_mass", "plain")
+        self.wd_mass = wd_mass if wd_mass is not None else _opt(options, "explicit_wetting_and_drying_mass", None)
+        if self.wd_mass is None:
+            self.wd_mass = WD_MASS_DEFAULT
         if self.wd_mass not in ("plain", "displaced"):
             raise ValueError(f"wd_mass must be 'plain' or 'displaced', not {self.wd_mass!r}")
         self.equation = equation
