@@ -492,6 +492,9 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a, wd), "triangles": int(n_tri_global), "dofs": int(dpc * n_tri_global),
                        "dt": dt,
+                       "wetting_drying_step": ("plain-mass explicit extension (DESIGN.md section 6): the reference's depth "
+                                               "formulation, no reference code path for the step; `no_wd` is the leg "
+                                               "whose every term and step has one") if (a.config == 5 and wd) else None,
                        "l2": ("per-GPU working set %.0f MB vs L2 %.0f MB: " % (work_bytes / 1e6, l2_bytes / 1e6))
                              + ("L2 flushed between timed steps (2 x L2 buffer written, untimed), steps timed one by one"
                                 if flush else "inputs larger than L2, no flush"),
