@@ -234,3 +234,27 @@ def test_thacker_default_alpha_cap_defeats_both_explicit_steps():
     except RuntimeError:
         broke = True                                             # the Newton solve gave up on the way
     assert broke
+
+
+def test_plain_and_displaced_mass_agree_where_the_water_is_deep():
+    """Where the depth stays large against alpha (17 - 23 m vs 0.5 m: f' = (H / sqrt(H^2 + alpha^2) - 1) / 2 ~ 2e-4) the
+    two explicit wetting-drying steps and the step without wetting-drying are the same scheme to that order: the
+    plain-mass extension is legitimate there -- this is the regime DESIGN.md section 6 restricts it to."""
+    import reference_cases as RC
+    mesh = RC.build_mesh(RC.RECT)
+    b = RC.nodal_value(("p1", "bath_wavy"), mesh)
+    wd = O.SWEOracle(mesh, b, options=dict(use_wetting_and_drying=True, wetting_and_drying_alpha=0.5))
+    nowd = O.SWEOracle(mesh, b, options=dict(use_wetting_and_drying=False))
+    uv, eta = RC.state(mesh, 5)
+    out = {}
+    for name, cls, orc in (("plain", O.ShuOsherStepper, wd), ("displaced", O.DisplacedMassShuOsherStepper, wd),
+                           ("no_wd", O.ShuOsherStepper, nowd)):
+        u, e = uv.copy(), eta.copy()
+        st = cls(orc, [u, e], 4.0)
+        for i in range(25):
+            st.advance(4.0 * i)
+        out[name] = e
+    moved = np.abs(out["no_wd"] - eta).max()
+    assert moved > 0.5                                                     # the state really evolved (0.84 m)
+    assert np.abs(out["plain"] - out["displaced"]).max() < 5e-4 * moved    # 1.6e-4 m
+    assert np.abs(out["plain"] - out["no_wd"]).max() < 5e-4 * moved
