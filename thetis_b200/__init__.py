@@ -8,14 +8,20 @@ Importing the package does not need a GPU; constructing an integrator does
 __version__ = "0.1.0"
 
 
-def install(thetis_module=None, sync_policy="every_step"):
+def install(thetis_module=None, sync_policy="every_step", wd_mass=None):
     """
     Rebind `thetis.rungekutta.SSPRK33` (+ the Butcher-form ERK classes and `thetis.timeintegrator.ForwardEuler`
     where the module has them) and `thetis.limiter.VertexBasedP1DGLimiter` to the B200
     implementations so that FlowSolver2d.create_timestepper() picks them up (the `steppers` dict is built from
     module attributes at call time, thetis/solver2d.py:662-672).  See INTEGRATION.md.
+    ``wd_mass``: 'plain' | 'displaced' -- mass functional of the explicit wetting-drying step for every integrator built
+    afterwards (rungekutta.WD_MASS_DEFAULT); None leaves the current default.
     """
     from . import rungekutta as rk, limiter as lim
+    if wd_mass is not None:
+        if wd_mass not in ("plain", "displaced"):
+            raise ValueError(f"wd_mass must be 'plain' or 'displaced', not {wd_mass!r}")
+        rk.WD_MASS_DEFAULT = wd_mass
     if thetis_module is None:
         import thetis as thetis_module          # raises ImportError without a Thetis/Firedrake install
     policy = sync_policy
