@@ -40,7 +40,8 @@ here); tests/test_oracle_reference_residuals.py: every SWE term, all open-bounda
 depth, the three drag laws, SIPG viscosity, ModeSplit2DEquations, the tracer terms in both forms, and whole steps of
 SSPRK33 / ERKLSPUM2 / ERKLPUM2 / ERKMidpoint / ERKEuler / ForwardEuler are reproduced to <= 2e-15 (tolerance 1e-12).
 What that cannot pin is Firedrake's own assembly of those forms (quadrature rule choice for non-polynomial
-integrands) and the limiter, whose kernels live in Firedrake.
+integrands) and Firedrake's VertexBasedLimiter (Thetis' own exterior-facet kernel of the limiter,
+limiter.py:123-145, IS pinned: its C text is compiled and executed, tests/test_oracle_reference_limiter.py).
 (2) pinned against the reference's own known-answer criteria
 (tests/test_oracle_kat.py: Shu-Osher coefficients produced by executing
 rungekutta.py:13-87 itself, ODE convergence slope, eta-norm 6251.2574, standing
@@ -964,6 +965,22 @@ class TracerOracle:
         return (np.linalg.solve(self.mass, (dt * R)[..., None])[..., 0],)
 
 
+def limiter_boundary_bounds(mesh, q, qmax, qmin):
+    """Thetis' own addition to the vertex bounds (limiter.py:109-145, the `my_kernel` par_loop over the exterior
+    facets): the arithmetic mean of the two nodal values on every exterior facet enters the max / min of the facet's two
+    vertices.  In place on qmax / qmin (one value per topological vertex).  Pinned to the reference's kernel text,
+    compiled and executed: tests/golden/make_reference_limiter_golden.py."""
+    tv = mesh.topo[mesh.cells]
+    bc = mesh.bf_cell.astype(np.int64)
+    bl = mesh.bf_lf.astype(np.int64)
+    n0 = FACET_NODES[bl, 0]
+    n1 = FACET_NODES[bl, 1]
+    face_mean = (q[bc, n0] + q[bc, n1]) / 2
+    for nn in (n0, n1):
+        np.maximum.at(qmax, tv[bc, nn], face_mean)
+        np.minimum.at(qmin, tv[bc, nn], face_mean)
+
+
 def vertex_based_limiter(mesh, q):
     """
     `VertexBasedP1DGLimiter.apply` for a scalar P1DG field on a 2-D mesh
@@ -981,15 +998,7 @@ def vertex_based_limiter(mesh, q):
     for a in range(3):
         np.maximum.at(qmax, tv[:, a], qbar)
         np.minimum.at(qmin, tv[:, a], qbar)
-    # boundary facets: arithmetic mean of the facet's nodal values (limiter.py:123-145)
-    bc = mesh.bf_cell.astype(np.int64)
-    bl = mesh.bf_lf.astype(np.int64)
-    n0 = FACET_NODES[bl, 0]
-    n1 = FACET_NODES[bl, 1]
-    face_mean = (q[bc, n0] + q[bc, n1]) / 2
-    for nn in (n0, n1):
-        np.maximum.at(qmax, tv[bc, nn], face_mean)
-        np.minimum.at(qmin, tv[bc, nn], face_mean)
+    limiter_boundary_bounds(mesh, q, qmax, qmin)
     # limit
     alpha = np.ones(nt)
     for a in range(3):
