@@ -59,3 +59,35 @@ def test_committed_fixture_is_what_the_reference_kernel_produces(tmp_path):
     assert set(new.files) == set(GOLD.files)
     for k in GOLD.files:
         assert np.array_equal(new[k], GOLD[k]), k
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/thetis/utility.py"), reason="the reference tree only exists in the build container")
+def test_cell_widths_of_the_automatic_wetting_drying_alpha_equal_the_reference_kernel(tmp_path):
+    """`get_cell_widths_2d` (utility.py:716-739; feeds `use_automatic_wetting_and_drying_alpha`, solver2d.py:279-287, which
+    the Thacker set-up of tests/kat_setups.py restates as the coordinate ranges of a cell): the reference's kernel text,
+    compiled and run cell by cell with access MAX on a DG0 vector initialised to the smallest double, as the reference does"""
+    import ast
+    import ctypes as C
+    tree = ast.parse(open("/root/reference/thetis/utility.py").read())
+    src = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "get_cell_widths_2d":
+            for sub in ast.walk(node):
+                if isinstance(sub, ast.Constant) and isinstance(sub.value, str) and "cell_width_kernel" in sub.value:
+                    src = sub.value % {"nodes": 3}                # arity of the P1 coordinate cell_node_map
+    assert src is not None
+    (tmp_path / "k.c").write_text("#include <math.h>\n" + src + "\n")
+    subprocess.run(["gcc", "-O1", "-fPIC", "-shared", "-o", str(tmp_path / "k.so"), str(tmp_path / "k.c"), "-lm"], check=True)
+    lib = C.CDLL(str(tmp_path / "k.so"))
+    dp = C.POINTER(C.c_double)
+    lib.cell_width_kernel.argtypes = [dp, dp]
+    import kat_setups as K
+    p = K.thacker_problem(10)
+    mesh = p["mesh"]
+    xc = np.ascontiguousarray(mesh.coords[mesh.cells])               # (nt, 3, 2): the gathered coordinates of a cell
+    widths = np.full((mesh.n_cells, 2), np.finfo(0.0).min)
+    for c in range(mesh.n_cells):
+        w = widths[c].copy()
+        lib.cell_width_kernel(xc[c].ctypes.data_as(dp), w.ctypes.data_as(dp))
+        widths[c] = np.maximum(widths[c], w)
+    assert np.array_equal(widths, np.ptp(xc, axis=1))
