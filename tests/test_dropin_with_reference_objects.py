@@ -358,3 +358,37 @@ def test_displaced_mass_wetting_drying_step_on_reference_objects(ref, name):
         assert ref.engines[-1].opt[L.OPT_WD_DISPLACED_MASS] == 1.0
     finally:
         B.WD_MASS_DEFAULT = "plain"
+
+
+def test_reference_diagnostics_equal_the_closed_forms_the_device_reductions_are_checked_against(ref):
+    """`utility.comp_volume_2d` / `comp_tracer_mass_2d` (utility.py:422-443; behind VolumeConservation2DCallback and
+    TracerMassConservation2DCallback, callback.py:350-389) executed from the reference tree on the UFL stand-in, against
+    the closed P1 forms tests/test_gpu_tracer_terms.py holds the device reductions (tb_swe_integrals /
+    tb_tracer_integrals, fused print_state norms) to: int (eta + b) = sum A mean(eta + b), int H c = sum A H^T M c,
+    M = (I + 1 1^T) / 12, and the L2 norms of print_state (solver2d.py:955-956)."""
+    import reference_cases as RC
+    from oracle import swe_oracle as O
+    G = ref.G
+    case = RC.SWE_CASES["nonlinear_lf_closed"]
+    st = G.Setup(case)
+    depth, opts, o = st.depth_and_options()
+    sol, uv, eta = st.swe_solution(3)
+    m = st.m2
+    area = m.cell_area()
+    bn = RC.nodal_value(case["bath"], m)
+    vol_ref = G.util.comp_volume_2d(sol.subfunctions[1], depth.bathymetry_2d)
+    vol = (area * (eta + bn).mean(1)).sum()
+    assert abs(vol_ref - vol) <= 1e-13 * abs(vol)
+    rng = np.random.default_rng(5)
+    c = 1.0 + 0.3 * rng.standard_normal(eta.shape)
+    q = G.U.Function(st.H, name="tracer_2d")
+    q.dat.data[...] = c.reshape(-1)
+    mass_ref = G.util.comp_tracer_mass_2d(q, depth.get_total_depth(sol.subfunctions[1]))
+    mref = (np.ones((3, 3)) + np.eye(3)) / 12.0
+    mass = (area * np.einsum("ca,ab,cb->c", bn + eta, mref, c)).sum()
+    assert abs(mass_ref - mass) <= 1e-13 * abs(mass)
+    # print_state norms: firedrake.norm(f) = sqrt(assemble(inner(f, f) * dx))
+    U = G.U
+    n_h = np.sqrt(U.assemble(U.inner(sol.subfunctions[1], sol.subfunctions[1]) * U.dx))
+    n_u = np.sqrt(U.assemble(U.inner(sol.subfunctions[0], sol.subfunctions[0]) * U.dx))
+    assert abs(n_h - O.l2_norm(m, eta)) <= 1e-13 * n_h and abs(n_u - O.l2_norm(m, uv)) <= 1e-13 * n_u
