@@ -260,7 +260,7 @@ def test_install_rebinds_the_reference_modules_and_the_coupled_run_still_matches
         thetis_b200.install(thetis, sync_policy="every_step")
         assert issubclass(rk_mod.SSPRK33, B.SSPRK33) and issubclass(rk_mod.ERKLSPUM2, B.ERKLSPUM2)
         assert issubclass(ti_mod.ForwardEuler, B.ForwardEuler)
-        assert lim_mod.VertexBasedP1DGLimiter is BL.VertexBasedP1DGLimiter
+        assert issubclass(lim_mod.VertexBasedP1DGLimiter, BL.VertexBasedP1DGLimiter)
         steppers = {"SSPRK33": rk_mod.SSPRK33}                      # what solver2d.py:662-672 builds at call time
         name = "coupled_ssprk33_advection"
         spec = RC.COUPLED_CASES[name]
@@ -392,3 +392,76 @@ def test_reference_diagnostics_equal_the_closed_forms_the_device_reductions_are_
     n_h = np.sqrt(U.assemble(U.inner(sol.subfunctions[1], sol.subfunctions[1]) * U.dx))
     n_u = np.sqrt(U.assemble(U.inner(sol.subfunctions[0], sol.subfunctions[0]) * U.dx))
     assert abs(n_h - O.l2_norm(m, eta)) <= 1e-13 * n_h and abs(n_u - O.l2_norm(m, uv)) <= 1e-13 * n_u
+
+
+def test_install_falls_back_to_the_reference_class_outside_the_accelerated_path(ref):
+    """`steppers['SSPRK33']` also serves equations this library does not accelerate (solver2d.py:662-700: sediment,
+    Exner; boundary data it cannot take).  After install() such a construction returns an instance of the reference's
+    own class built from the same arguments (with a warning); a supported one returns the B200 class; with
+    fallback=False the NotImplementedError propagates; errors the reference raises too are never swallowed."""
+    import importlib
+    import warnings
+    import reference_cases as RC
+    import thetis_b200
+    from thetis_b200 import rungekutta as B
+    G = ref.G
+    thetis = sys.modules["thetis"]
+    importlib.import_module("thetis.limiter")
+    rk_mod, ti_mod, lim_mod = thetis.rungekutta, thetis.timeintegrator, thetis.limiter
+    names = [(rk_mod, "SSPRK33"), (rk_mod, "ERKLSPUM2"), (rk_mod, "ERKLPUM2"), (rk_mod, "ERKMidpoint"), (rk_mod, "ERKEuler"),
+             (ti_mod, "ForwardEuler"), (lim_mod, "VertexBasedP1DGLimiter")]
+    saved = {(m, n): getattr(m, n) for m, n in names}
+    ref_ssprk33 = saved[(rk_mod, "SSPRK33")]
+    topt = types.SimpleNamespace(ad_block_tag="", solver_parameters={})
+    try:
+        thetis_b200.install(thetis)
+        thetis_b200.install(thetis)                                  # twice: the reference class is not lost
+        assert rk_mod.SSPRK33._reference_class is ref_ssprk33
+        # 1. supported set-up: the B200 class
+        case = RC.SWE_CASES["nonlinear_lf_closed"]
+        st = G.Setup(case)
+        eq, fields, bnd, o = G.swe_equation(st)
+        sol, uv0, eta0 = st.swe_solution(1)
+        ti = rk_mod.SSPRK33(eq, sol, fields, 2.0, topt, bnd)
+        assert isinstance(ti, B.SSPRK33) and ti.sync_policy == "every_step"
+        # 2. a Function-valued boundary 'drag' is outside the accelerated path: the reference integrator takes over
+        case2 = dict(case, bnd={1: {"drag": ("p1", "lin_drag")}})
+        st2 = G.Setup(case2)
+        eq2, fields2, bnd2, _ = G.swe_equation(st2)
+        sol2, uv2, eta2 = st2.swe_solution(1)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            ti2 = rk_mod.SSPRK33(eq2, sol2, fields2, 2.0, topt, bnd2)
+        assert type(ti2) is ref_ssprk33 and not isinstance(ti2, B.SSPRK33)
+        assert any("falls back to the reference class" in str(x.message) for x in w)
+        eng = ref.engines[-1]
+        assert eng.swe_stepper is None                               # the half-built B200 stepper deregistered itself
+        ti2.advance(0.0)                                             # ... and the reference object works
+        assert np.abs(sol2.subfunctions[1].dat.data.reshape(eta2.shape) - eta2).max() > 1e-6
+        # 3. an equation class the library does not know at all
+        class SedimentEquation:                                      # noqa: N801 (stands for thetis.sediment_eq_2d's)
+            pass
+        made = {}
+
+        class RefStandIn:
+            def __init__(self, *a, **k):
+                made["args"] = a
+        rk_mod.SSPRK33._reference_class = RefStandIn                  # look at what the fallback is called with
+        thetis_b200.install(thetis)                                  # rebinding keeps the remembered class
+        out = rk_mod.SSPRK33(SedimentEquation(), sol, fields, 2.0, topt, {})
+        assert isinstance(out, RefStandIn) and made["args"][3] == 2.0
+        # 4. fallback off: the error propagates
+        for (m, n), v in saved.items():
+            setattr(m, n, v)
+        thetis_b200.install(thetis, fallback=False)
+        with pytest.raises(NotImplementedError, match="drag"):
+            rk_mod.SSPRK33(eq2, st2.swe_solution(1)[0], fields2, 2.0, topt, bnd2)
+        # 5. what the reference rejects too is never swallowed
+        for (m, n), v in saved.items():
+            setattr(m, n, v)
+        thetis_b200.install(thetis)
+        with pytest.raises(Exception, match="Invalid boundary tag"):
+            rk_mod.SSPRK33(eq, st.swe_solution(1)[0], fields, 2.0, topt, {1: {"elevation": G.U.Constant(0.0)}})
+    finally:
+        for (m, n), v in saved.items():
+            setattr(m, n, v)

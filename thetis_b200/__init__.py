@@ -8,7 +8,7 @@ Importing the package does not need a GPU; constructing an integrator does
 __version__ = "0.1.0"
 
 
-def install(thetis_module=None, sync_policy="every_step", wd_mass=None):
+def install(thetis_module=None, sync_policy="every_step", wd_mass=None, fallback=True):
     """
     Rebind `thetis.rungekutta.SSPRK33` (+ the Butcher-form ERK classes and `thetis.timeintegrator.ForwardEuler`
     where the module has them) and `thetis.limiter.VertexBasedP1DGLimiter` to the B200
@@ -16,7 +16,14 @@ def install(thetis_module=None, sync_policy="every_step", wd_mass=None):
     module attributes at call time, thetis/solver2d.py:662-672).  See INTEGRATION.md.
     ``wd_mass``: 'plain' | 'displaced' -- mass functional of the explicit wetting-drying step for every integrator built
     afterwards (rungekutta.WD_MASS_DEFAULT); None leaves the current default.
+    ``fallback``: the same `steppers` entries also serve equations this library does not accelerate (sediment, Exner,
+    the 3-D model's explicit parts, turbines, SUPG ...).  With fallback on, a construction that raises
+    NotImplementedError -- "outside the accelerated path" -- returns an instance of the REFERENCE class that was bound
+    to the name before install(), built from the same arguments, and warns once per class and reason; with
+    fallback off the NotImplementedError propagates.  Errors the reference raises too (invalid boundary tag, ...) always
+    propagate.  Nothing computes on the CPU inside this library either way.
     """
+    import warnings
     from . import rungekutta as rk, limiter as lim
     if wd_mass is not None:
         if wd_mass not in ("plain", "displaced"):
@@ -25,29 +32,69 @@ def install(thetis_module=None, sync_policy="every_step", wd_mass=None):
     if thetis_module is None:
         import thetis as thetis_module          # raises ImportError without a Thetis/Firedrake install
     policy = sync_policy
+    warned = set()
 
-    class SSPRK33(rk.SSPRK33):
-        def __init__(self, equation, solution, fields, dt, options=None, bnd_conditions=None, terms_to_add="all"):
-            super().__init__(equation, solution, fields, dt, options, bnd_conditions, terms_to_add,
-                             sync_policy=policy)
+    def _reference(orig, name, err, args, kwargs):
+        if not fallback or orig is None or orig is object or getattr(orig, "_thetis_b200_bound", False):
+            raise err
+        key = (name, str(err))
+        if key not in warned:
+            warned.add(key)
+            warnings.warn(f"thetis_b200: {name} falls back to the reference class ({err})", RuntimeWarning, stacklevel=3)
+        return orig(*args, **kwargs)
 
-    cls = SSPRK33
-    thetis_module.rungekutta.SSPRK33 = cls
-    thetis_module.limiter.VertexBasedP1DGLimiter = lim.VertexBasedP1DGLimiter
+    def _unwrap(orig):
+        # install() called twice: the reference class is the one remembered by the first binding
+        return getattr(orig, "_reference_class", None) if getattr(orig, "_thetis_b200_bound", False) else orig
 
-    def _bind(base):
+    def _bind(base, orig):
+        orig = _unwrap(orig)
+
         class _Bound(base):
-            def __init__(self, equation, solution, fields, dt, options=None, bnd_conditions=None, terms_to_add="all"):
-                super().__init__(equation, solution, fields, dt, options, bnd_conditions, terms_to_add,
-                                 sync_policy=policy)
+            _thetis_b200_bound = True
+            _reference_class = orig
+
+            def __new__(cls, *args, **kwargs):
+                obj = object.__new__(cls)
+                try:
+                    base.__init__(obj, *args, sync_policy=policy, **kwargs)
+                except NotImplementedError as err:
+                    return _reference(orig, base.__name__, err, args, kwargs)
+                return obj
+
+            def __init__(self, *args, **kwargs):
+                pass                              # constructed in __new__ (so that a fallback can replace the object)
         _Bound.__name__ = _Bound.__qualname__ = base.__name__
         return _Bound
+
+    cls = _bind(rk.SSPRK33, getattr(thetis_module.rungekutta, "SSPRK33", None))
+    thetis_module.rungekutta.SSPRK33 = cls
+
+    orig_lim = _unwrap(getattr(thetis_module.limiter, "VertexBasedP1DGLimiter", None))
+    if fallback and orig_lim is not None and orig_lim is not object and not getattr(orig_lim, "_thetis_b200_bound", False):
+        class VertexBasedP1DGLimiter(lim.VertexBasedP1DGLimiter):
+            _thetis_b200_bound = True
+            _reference_class = orig_lim
+
+            def __new__(cls, *args, **kwargs):
+                obj = object.__new__(cls)
+                try:
+                    lim.VertexBasedP1DGLimiter.__init__(obj, *args, **kwargs)
+                except NotImplementedError as err:      # vector fields, extruded meshes: the reference's 3-D path
+                    return _reference(orig_lim, "VertexBasedP1DGLimiter", err, args, kwargs)
+                return obj
+
+            def __init__(self, *args, **kwargs):
+                pass
+        thetis_module.limiter.VertexBasedP1DGLimiter = VertexBasedP1DGLimiter
+    else:
+        thetis_module.limiter.VertexBasedP1DGLimiter = lim.VertexBasedP1DGLimiter
 
     # the Butcher-form explicit schemes (rungekutta.py:959-980) and timeintegrator.ForwardEuler, where present
     for name in ("ERKLSPUM2", "ERKLPUM2", "ERKMidpoint", "ERKEuler"):
         if hasattr(thetis_module.rungekutta, name):
-            setattr(thetis_module.rungekutta, name, _bind(getattr(rk, name)))
+            setattr(thetis_module.rungekutta, name, _bind(getattr(rk, name), getattr(thetis_module.rungekutta, name)))
     ti_mod = getattr(thetis_module, "timeintegrator", None)
     if ti_mod is not None and hasattr(ti_mod, "ForwardEuler"):
-        ti_mod.ForwardEuler = _bind(rk.ForwardEuler)
+        ti_mod.ForwardEuler = _bind(rk.ForwardEuler, ti_mod.ForwardEuler)
     return cls

@@ -158,10 +158,14 @@ class ERKGenericShuOsher:
         self._field_versions = {}
         self._bc_versions = {}
         self._stamps = {}
-        self._setup_buffers()
-        self._check_supported()
-        self._push_static()
-        self.initialize(solution)
+        try:
+            self._setup_buffers()
+            self._check_supported()
+            self._push_static()
+            self.initialize(solution)
+        except Exception:
+            self._unregister()      # a caller may fall back to the reference class: leave no half-built stepper behind
+            raise
 
     # ------------------------------------------------------------------ set-up
     def _function_space(self):
@@ -209,6 +213,18 @@ class ERKGenericShuOsher:
                 eng.tracer_steppers = {}
             # keyed by id() for the lookup, validated through a weak reference (an id can be reused after GC)
             eng.tracer_steppers[id(self.solution)] = (weakref.ref(self.solution), self)
+
+    def _unregister(self):
+        """Remove this integrator from the registries of the shared device engine (failed construction)."""
+        eng = self.engine
+        if getattr(eng, "swe_stepper", None) is self:
+            eng.swe_stepper = None
+        reg = getattr(eng, "tracer_steppers", None)
+        if reg:
+            for k in [k for k, (_, st) in reg.items() if st is self]:
+                del reg[k]
+        if getattr(eng, "_tracer_cfg_owner", None) is self:
+            eng._tracer_cfg_owner = None
 
     def _check_supported(self):
         if self._kind == "swe":
