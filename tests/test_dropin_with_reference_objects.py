@@ -396,9 +396,9 @@ def test_reference_diagnostics_equal_the_closed_forms_the_device_reductions_are_
 
 def test_install_falls_back_to_the_reference_class_outside_the_accelerated_path(ref):
     """`steppers['SSPRK33']` also serves equations this library does not accelerate (solver2d.py:662-700: sediment,
-    Exner; boundary data it cannot take).  After install() such a construction returns an instance of the reference's
-    own class built from the same arguments (with a warning); a supported one returns the B200 class; with
-    fallback=False the NotImplementedError propagates; errors the reference raises too are never swallowed."""
+    Exner; boundary data it cannot take).  After install(fallback=True) such a construction returns an instance of the
+    reference's own class built from the same arguments (with a warning); a supported one returns the B200 class; by
+    default the NotImplementedError propagates; errors the reference raises too are never swallowed."""
     import importlib
     import warnings
     import reference_cases as RC
@@ -414,8 +414,8 @@ def test_install_falls_back_to_the_reference_class_outside_the_accelerated_path(
     ref_ssprk33 = saved[(rk_mod, "SSPRK33")]
     topt = types.SimpleNamespace(ad_block_tag="", solver_parameters={})
     try:
-        thetis_b200.install(thetis)
-        thetis_b200.install(thetis)                                  # twice: the reference class is not lost
+        thetis_b200.install(thetis, fallback=True)
+        thetis_b200.install(thetis, fallback=True)                   # twice: the reference class is not lost
         assert rk_mod.SSPRK33._reference_class is ref_ssprk33
         # 1. supported set-up: the B200 class
         case = RC.SWE_CASES["nonlinear_lf_closed"]
@@ -447,19 +447,19 @@ def test_install_falls_back_to_the_reference_class_outside_the_accelerated_path(
             def __init__(self, *a, **k):
                 made["args"] = a
         rk_mod.SSPRK33._reference_class = RefStandIn                  # look at what the fallback is called with
-        thetis_b200.install(thetis)                                  # rebinding keeps the remembered class
+        thetis_b200.install(thetis, fallback=True)                   # rebinding keeps the remembered class
         out = rk_mod.SSPRK33(SedimentEquation(), sol, fields, 2.0, topt, {})
         assert isinstance(out, RefStandIn) and made["args"][3] == 2.0
-        # 4. fallback off: the error propagates
+        # 4. the default (fallback off): the error propagates
         for (m, n), v in saved.items():
             setattr(m, n, v)
-        thetis_b200.install(thetis, fallback=False)
+        thetis_b200.install(thetis)
         with pytest.raises(NotImplementedError, match="drag"):
             rk_mod.SSPRK33(eq2, st2.swe_solution(1)[0], fields2, 2.0, topt, bnd2)
         # 5. what the reference rejects too is never swallowed
         for (m, n), v in saved.items():
             setattr(m, n, v)
-        thetis_b200.install(thetis)
+        thetis_b200.install(thetis, fallback=True)
         with pytest.raises(Exception, match="Invalid boundary tag"):
             rk_mod.SSPRK33(eq, st.swe_solution(1)[0], fields, 2.0, topt, {1: {"elevation": G.U.Constant(0.0)}})
     finally:

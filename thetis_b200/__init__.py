@@ -8,7 +8,7 @@ Importing the package does not need a GPU; constructing an integrator does
 __version__ = "0.1.0"
 
 
-def install(thetis_module=None, sync_policy="every_step", wd_mass=None, fallback=True):
+def install(thetis_module=None, sync_policy="every_step", wd_mass=None, fallback=False):
     """
     Rebind `thetis.rungekutta.SSPRK33` (+ the Butcher-form ERK classes and `thetis.timeintegrator.ForwardEuler`
     where the module has them) and `thetis.limiter.VertexBasedP1DGLimiter` to the B200
@@ -17,11 +17,13 @@ def install(thetis_module=None, sync_policy="every_step", wd_mass=None, fallback
     ``wd_mass``: 'plain' | 'displaced' -- mass functional of the explicit wetting-drying step for every integrator built
     afterwards (rungekutta.WD_MASS_DEFAULT); None leaves the current default.
     ``fallback``: the same `steppers` entries also serve equations this library does not accelerate (sediment, Exner,
-    the 3-D model's explicit parts, turbines, SUPG ...).  With fallback on, a construction that raises
-    NotImplementedError -- "outside the accelerated path" -- returns an instance of the REFERENCE class that was bound
-    to the name before install(), built from the same arguments, and warns once per class and reason; with
-    fallback off the NotImplementedError propagates.  Errors the reference raises too (invalid boundary tag, ...) always
-    propagate.  Nothing computes on the CPU inside this library either way.
+    the 3-D model's explicit parts, turbines, SUPG ...).  By default (fallback off) such a construction raises
+    NotImplementedError -- "outside the accelerated path" -- like everything else this library cannot do: it fails
+    loudly.  With ``fallback=True`` (opt-in) it instead returns an instance of the REFERENCE class that was bound to the
+    name before install(), i.e. the user's own Thetis / Firedrake object, built from the same arguments, and warns once
+    per class and reason.  Only NotImplementedError at construction is treated that way: a missing CUDA library, a
+    missing GPU, an error inside a kernel launch or an error the reference raises too (invalid boundary tag, ...) always
+    propagate, and nothing inside this library ever computes on the CPU.
     """
     import warnings
     from . import rungekutta as rk, limiter as lim
