@@ -13,6 +13,9 @@ What is restated (all paths relative to /root/reference):
 * thetis/shallowwater_eq.py:619-663   CoriolisTerm, WindStressTerm, AtmosphericPressureTerm
 * thetis/shallowwater_eq.py:666-701   QuadraticDragTerm (constant / Manning)
 * thetis/shallowwater_eq.py:728-740   LinearDragTerm
+* thetis/shallowwater_eq.py:704-726   BoundaryDragTerm ('drag' boundary tag)
+* thetis/shallowwater_eq.py:834-850,917-920  BathymetryDisplacementMassTerm / the wetting-drying mass functional
+                                      (displaced_mass, solve_displaced_mass, DisplacedMassShuOsherStepper)
 * thetis/shallowwater_eq.py:513-616   HorizontalViscosityTerm (SIPG; grad-div and grad-depth variants)
 * thetis/shallowwater_eq.py:794-831   MomentumSourceTerm, ContinuitySourceTerm
 * thetis/shallowwater_eq.py:232-296   get_bnd_functions / impose_dynamic_bnd
@@ -23,7 +26,8 @@ What is restated (all paths relative to /root/reference):
 * thetis/tracer_eq_2d.py:196-278              HorizontalDiffusionTerm (SIPG)
 * thetis/tracer_eq_2d.py:300-437              conservative tracer advection + source
 * thetis/rungekutta.py:762-867                ERKGeneric (Butcher form)
-* thetis/limiter.py:48-198 + firedrake.VertexBasedLimiter (recalled)
+* thetis/limiter.py:48-198 + firedrake.VertexBasedLimiter (recalled); the exterior-facet kernel :123-145 is pinned
+  by executing the reference's kernel text (limiter_boundary_bounds)
 
 The arithmetic itself lives in Firedrake/TSFC/PyOP2/PETSc, which is NOT under
 /root/reference and is unpinned upstream (CI image
