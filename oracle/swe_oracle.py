@@ -627,29 +627,77 @@ class SWEOracle:
             F = F + self.geom.area[:, None] * np.einsum("q,cq,qa->ca", qw, f, lam)
         return F
 
-    def solve_displaced_mass(self, target, guess, tol=1e-12, max_it=50):
-        """eta with displaced_mass(eta) = target: cell-local Newton iteration (the functional is convex in eta:
-        d/d eta (eta + f) = (1 + H / sqrt(H^2 + alpha^2)) / 2 in (0, 1))."""
+    def solve_displaced_mass(self, target, guess, tol=1e-12, max_it=60):
+        """eta with displaced_mass(eta) = target (the functional is the gradient of a strictly convex potential:
+        d/d eta (eta + f) = (1 + H / sqrt(H^2 + alpha^2)) / 2 in (0, 1), so the root is unique)."""
+        shift = np.einsum("cab,cb->ca", self.mass, self.bath)       # eta + f = Ht - b:  F = depth_mass - M b
+        return self.solve_depth_mass(target + shift, guess, tol, max_it)
+
+    def _depth_and_slope(self, H, al):
+        """total depth Ht = (sqrt(H^2 + alpha^2) + H) / 2 (utility.py:987-996) and dHt/dH, without cancellation on the
+        dry side (H < 0: Ht = alpha^2 / (2 (r - H)))"""
+        if not self.options["use_wetting_and_drying"]:
+            return H, np.ones_like(H)
+        aa = np.asarray(al, dtype=float) ** 2 + 0.0 * H
+        r = np.sqrt(H * H + aa)
+        wet = H >= 0.0
+        d = np.where(wet, 1.0, r - H)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ht = np.where(wet, 0.5 * (r + H), 0.5 * aa / d)
+            dht = np.where(wet, np.where(r > 0, 0.5 * (1.0 + H / np.where(r > 0, r, 1.0)), 0.5), 0.5 * aa / (d * np.where(r > 0, r, 1.0)))
+        return ht, dht
+
+    def depth_mass(self, eta):
+        """S(eta)_a = int Ht(b + eta) phi_a dx = displaced_mass(eta) + int b phi_a: the same functional up to a constant,
+        evaluated without the cancellation eta + f suffers from in almost dry cells"""
+        lam, qw = self.lam, self.qw
+        aln = self._alpha_nodal()
+        al = self.options["wetting_and_drying_alpha"] if aln is None else self._at_cell_q(aln, lam)
+        ht, _ = self._depth_and_slope(self._at_cell_q(self.bath, lam) + self._at_cell_q(eta, lam), al)
+        return self.geom.area[:, None] * np.einsum("q,cq,qa->ca", qw, ht, lam)
+
+    def solve_depth_mass(self, target, guess, tol=1e-12, max_it=60):
+        """eta with depth_mass(eta) = target: cell-local Newton iteration with step halving (a step that increases the
+        residual of its cell -- a jump across the kink of Ht from the flat, dry side -- is halved)."""
         lam, qw = self.lam, self.qw
         aln = self._alpha_nodal()
         al = self.options["wetting_and_drying_alpha"] if aln is None else self._at_cell_q(aln, lam)
         b_q = self._at_cell_q(self.bath, lam)
-        eta = np.array(guess, dtype=float, copy=True)
+        area = self.geom.area
+        e = np.array(guess, dtype=float, copy=True)
+        base, step = e.copy(), np.zeros_like(e)
+        gprev = np.full(e.shape[0], np.inf)
         prev = np.inf
         for _ in range(max_it):
-            G = self.displaced_mass(eta) - target
-            J = self.mass
-            if self.options["use_wetting_and_drying"]:
-                H = b_q + self._at_cell_q(eta, lam)
-                fp = 0.5 * (H / np.sqrt(H ** 2 + np.asarray(al) ** 2) - 1.0)
-                J = J + self.geom.area[:, None, None] * np.einsum("q,cq,qa,qb->cab", qw, fp, lam, lam)
-            d = np.linalg.solve(J, G[..., None])[..., 0]
-            eta -= d
-            dm, scale = np.abs(d).max(), max(1.0, np.abs(eta).max())
-            # converged, or stagnated at the rounding level of an ill-conditioned (almost dry) cell
-            if dm <= tol * scale or (dm >= 0.5 * prev and dm <= 1e-8 * scale):
-                return eta
-            prev = dm
+            ht, dht = self._depth_and_slope(b_q + self._at_cell_q(e, lam), al)
+            G = area[:, None] * np.einsum("q,cq,qa->ca", qw, ht, lam) - target
+            gn = np.abs(G).max(axis=1)
+            noise = 4e-15 * (np.abs(G + target).sum(axis=1) + np.abs(target).sum(axis=1))     # rounding level of S - T
+            if _ > 0 and (gn <= noise).all():
+                return e
+            rej = (gn > gprev) & (gn > noise)
+            if rej.any():
+                step[rej] *= 0.5
+                e[rej] = base[rej] - step[rej]
+                if rej.all():
+                    continue
+            acc = ~rej
+            J = area[:, None, None] * np.einsum("q,cq,qa,qb->cab", qw, dht, lam, lam)
+            try:
+                d = np.linalg.solve(J[acc], G[acc][..., None])[..., 0]
+            except np.linalg.LinAlgError as err:      # an iterate ran off (target no elevation can meet, non-finite state)
+                raise RuntimeError("displaced-mass Newton iteration: " + str(err))
+            gprev[acc] = gn[acc]
+            base[acc] = e[acc]
+            step[acc] = d
+            e[acc] = base[acc] - d
+            dm, scale = np.abs(d).max() if d.size else 0.0, max(1.0, np.abs(e).max())
+            if not np.isfinite(dm):
+                break
+            if not rej.any() and (dm <= tol * scale or (dm >= 0.5 * prev and dm <= 1e-8 * scale)):
+                return e
+            if not rej.any():
+                prev = dm
         raise RuntimeError("displaced-mass Newton iteration did not converge")
 
 
@@ -718,7 +766,7 @@ class DisplacedMassShuOsherStepper(ShuOsherStepper):
         if i == 0:
             self.stage_sol[0][0][...] = uv
             self.stage_sol[0][1][...] = eta
-            self._F = [orc.displaced_mass(eta)]
+            self._F = [orc.depth_mass(eta)]       # = displaced_mass + const: the constant cancels (sum alpha = 1)
         Ru, Re = orc.residual(uv, eta)
         ku = np.linalg.solve(orc.mass, self.dt * Ru)
         new_uv = self.beta[i + 1][i] * ku
@@ -727,12 +775,12 @@ class DisplacedMassShuOsherStepper(ShuOsherStepper):
             if self.alpha[i + 1][j] != 0.0:
                 new_uv = new_uv + self.alpha[i + 1][j] * self.stage_sol[j][0]
                 target = target + self.alpha[i + 1][j] * self._F[j]
-        eta[...] = orc.solve_displaced_mass(target, eta)
+        eta[...] = orc.solve_depth_mass(target, eta)
         uv[...] = new_uv
         if i < self.n_stages - 1:
             self.stage_sol[i + 1][0][...] = uv
             self.stage_sol[i + 1][1][...] = eta
-            self._F.append(orc.displaced_mass(eta))
+            self._F.append(orc.depth_mass(eta))
 
 
 class ButcherStepper:

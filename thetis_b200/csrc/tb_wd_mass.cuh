@@ -109,7 +109,14 @@ static TB_WDM_FN int tb_wd_displaced_update(double *eta_io, double a0, const dou
             J01 += dht * l0 * l1; J02 += dht * l0 * l2; J12 += dht * l1 * l2;
         }
         const double gn = fmax(fabs(G0), fmax(fabs(G1), fabs(G2)));
-        if (gn > gprev && halvings < 40) {
+        // rounding level of the residual: S(e) is a sum of positive terms, S = G + T
+        const double noise = 4.0e-15 * (fabs(G0 + T[0]) + fabs(G1 + T[1]) + fabs(G2 + T[2]) + fabs(T[0]) + fabs(T[1]) + fabs(T[2]));
+        if (gn <= noise && it > 0) {          // the residual cannot get any smaller
+            ok = 1;
+            ++it;
+            break;
+        }
+        if (gn > gprev && gn > noise && halvings < 40) {
             // reject: back to the last accepted iterate, half of the step that led here
             ++halvings;
             for (int a = 0; a < 3; ++a) {
