@@ -1,0 +1,29 @@
+"""
+Thacker basin (test/swe2d/test_thacker.py) with the reference test's OWN wetting-drying alpha (automatic, capped at the
+default 2 m) under the explicit displaced-mass SSPRK33 step of the oracle at dt = 2 s: 21 600 steps, ~6 minutes on the
+numpy oracle -- too slow for the test suite, run once for DESIGN.md section 6:
+
+    DONE err 0.2397 (thresholds of the reference on this mesh: 0.26 second-order implicit, 0.33 BackwardEuler)
+
+    python scripts/thacker_reference_alpha_oracle.py
+"""
+import sys; import os; ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,os.path.join(ROOT,'tests')); sys.path.insert(0,ROOT)
+import numpy as np, time, warnings
+warnings.filterwarnings("ignore")
+import kat_setups as K
+from oracle import swe_oracle as O
+p=K.thacker_problem(10, 2.0)
+orc=O.SWEOracle(p["mesh"],p["bath"],options=dict(use_wetting_and_drying=True,wetting_and_drying_alpha=p["alpha"]))
+dt=2.0; ns=int(43200/dt)
+eta=p["eta0"].copy(); uv=np.zeros(eta.shape+(2,))
+st=O.DisplacedMassShuOsherStepper(orc,[uv,eta],dt)
+xc=p["mesh"].coords[p["mesh"].cells].mean(1); ic=int(np.argmin(np.hypot(xc[:,0]-p["centre"][0],xc[:,1]-p["centre"][1])))
+t0=time.time(); c=[]
+try:
+    with np.errstate(all="ignore"):
+        for i in range(ns):
+            st.advance(i*dt)
+            if i%1800==0: c.append(round(float(eta[ic].mean()),3)); print(i, c[-1], round(eta.min(),2), round(time.time()-t0), flush=True)
+    print("DONE err", K.thacker_error(p,eta), "centre", c, "time", time.time()-t0)
+except Exception as e:
+    print("FAILED at", i, str(e)[:80], c)

@@ -70,4 +70,4 @@ def test_refuse_check_logic(monkeypatch):
 
 def test_thacker_check_logic(monkeypatch):
     _patched(monkeypatch)
-    W.check_thacker()
+    W.check_thacker(quick=True)          # the capped-alpha leg takes the numpy oracle 5 minutes: GPU only
