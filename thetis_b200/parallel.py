@@ -22,7 +22,8 @@ import numpy as np
 
 from .mesh import Mesh2D, FACET_NODES
 
-__all__ = ["LocalPart", "partition_mesh", "HaloPlan", "distribute_mesh", "exchange_halo"]
+__all__ = ["LocalPart", "PeerInfo", "partition_mesh", "HaloPlan", "distribute_mesh", "exchange_halo",
+           "mark_unknown_facets", "build_overlap_connectivity", "local_contribution", "part_from_gathered", "plan_from_local_mesh"]
 
 INT32_MIN = np.iinfo(np.int32).min
 
@@ -435,3 +436,164 @@ def distribute_mesh(mesh: Mesh2D, rank=None, world=None, halo="vertex", transpor
     sm.halo_plan = HaloPlan(parts, rank, transport=transport, overlap=overlap, fused=fused)
     sm.global_mesh = mesh
     return sm
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# A mesh that is ALREADY distributed (Firedrake under mpiexec: DMPlex has cut the mesh, every rank holds its owned
+# cells followed by an overlap of ghost cells, `firedrake/mesh.py` distribution_parameters["overlap_type"]).  The
+# plan is built from what a rank knows locally -- its cells, which of them it owns and a global cell numbering --
+# plus ONE all-gather of the id lists.  No rank ever sees the global mesh.
+# ---------------------------------------------------------------------------------------------------------------
+class PeerInfo:
+    """What `HaloPlan` needs to know about another rank: sizes and the owner-grouping of its ghost block."""
+
+    def __init__(self, rank, n_owned, n_ghost, ghost_owner):
+        self.rank, self.n_owned, self.n_ghost = rank, int(n_owned), int(n_ghost)
+        self.ghost_owner = np.asarray(ghost_owner, dtype=np.int32)
+
+
+def mark_unknown_facets(mesh: Mesh2D, unknown):
+    """
+    Turn the boundary facets flagged in `unknown` (bool over the mesh's boundary facets) into facets whose neighbour
+    is not on this rank (INT32_MIN in `nbr`, the convention of `partition_mesh`): the outer edge of the overlap of a
+    distributed mesh has one cell locally but is not part of the domain boundary.  In place; returns the mesh.
+    """
+    unknown = np.asarray(unknown, dtype=bool)
+    if not unknown.any():
+        return mesh
+    nbr = mesh.nbr.astype(np.int64)
+    nbr[mesh.bf_cell[unknown], mesh.bf_lf[unknown]] = INT32_MIN
+    keep = np.nonzero(~unknown)[0]
+    nbr[mesh.bf_cell[keep], mesh.bf_lf[keep]] = -(1 + np.arange(keep.shape[0], dtype=np.int64))
+    mesh.nbr = nbr.astype(np.int32)
+    mesh.bf_cell, mesh.bf_lf, mesh.bf_marker = mesh.bf_cell[keep], mesh.bf_lf[keep], mesh.bf_marker[keep]
+    return mesh
+
+
+def build_overlap_connectivity(mesh: Mesh2D, exterior_edges):
+    """
+    Connectivity of a rank-local mesh with an overlap: `exterior_edges` = {(topological vertex a, b): marker} of the
+    facets that lie on the DOMAIN boundary (Firedrake: `mesh.exterior_facets`, which carries the overlap cells' too);
+    every other one-sided facet is the outer edge of the overlap and gets an unknown neighbour.
+    """
+    sentinel = INT32_MIN + 1
+    mesh.build_connectivity(edge_markers={(min(a, b), max(a, b)): mk for (a, b), mk in exterior_edges.items()},
+                            default_marker=sentinel)
+    return mark_unknown_facets(mesh, mesh.bf_marker == sentinel)
+
+
+def _owned_boundary_length(mesh: Mesh2D, n_owned):
+    """Length of the exterior facets of the OWNED cells per marker (each facet counted on exactly one rank)."""
+    sel = mesh.bf_cell < n_owned
+    x = mesh.cell_coords()
+    p = x[mesh.bf_cell[sel], FACET_NODES[mesh.bf_lf[sel], 0]]
+    q = x[mesh.bf_cell[sel], FACET_NODES[mesh.bf_lf[sel], 1]]
+    ln = np.hypot(*(q - p).T)
+    return {int(mk): float(ln[mesh.bf_marker[sel] == mk].sum()) for mk in np.unique(mesh.bf_marker[sel])}
+
+
+def local_contribution(mesh: Mesh2D, n_owned, global_ids):
+    """This rank's entry of the all-gather behind `part_from_gathered` (small: two id lists and a dict)."""
+    gids = np.asarray(global_ids, dtype=np.int64)
+    if gids.shape[0] != mesh.n_cells:
+        raise ValueError("one global id per local cell (owned cells first, then the overlap)")
+    return dict(owned=gids[:n_owned].copy(), ghost=gids[n_owned:].copy(),
+                boundary_len=_owned_boundary_length(mesh, n_owned))
+
+
+def _owners_of(ids, gathered):
+    """Owner rank of every global cell id in `ids` (-1: owned by nobody)."""
+    allo = np.concatenate([g["owned"] for g in gathered])
+    allr = np.concatenate([np.full(g["owned"].shape[0], r, dtype=np.int32) for r, g in enumerate(gathered)])
+    so = np.argsort(allo, kind="stable")
+    allo, allr = allo[so], allr[so]
+    if np.any(allo[1:] == allo[:-1]):
+        raise ValueError("a cell is owned by two ranks")
+    if ids.size == 0:
+        return np.zeros(0, dtype=np.int32)
+    if allo.size == 0:
+        return np.full(ids.shape[0], -1, dtype=np.int32)
+    pos = np.minimum(np.searchsorted(allo, ids), allo.shape[0] - 1)
+    return np.where(allo[pos] == ids, allr[pos], -1).astype(np.int32)
+
+
+def part_from_gathered(mesh: Mesh2D, n_owned, global_ids, gathered, rank, halo="facet", renumber=True):
+    """
+    `LocalPart` of `rank` + the `PeerInfo` of the others from a local mesh (connectivity built, overlap edge marked
+    with `mark_unknown_facets`), the global cell ids and the gathered `local_contribution`s.
+
+    The device layout wants owned cells along a space-filling curve and the ghost block grouped by owner (a peer
+    writes ONE contiguous run of it, in ascending global id): the local cells are permuted accordingly;
+    `part.mesh.cell_perm[new] = old` local index.  Returns (parts, part) with parts[rank] is part.
+    """
+    from .mesh import hilbert_index, sfc_renumber
+    world = len(gathered)
+    gids = np.asarray(global_ids, dtype=np.int64)
+    n_owned = int(n_owned)
+    ghost_g = gids[n_owned:]
+    go = _owners_of(ghost_g, gathered)
+    if np.any(go < 0) or np.any(go == rank):
+        raise ValueError("overlap cell owned by no other rank: global ids and ownership are inconsistent")
+    own_nbr = mesh.nbr[:n_owned]
+    if np.any(own_nbr == INT32_MIN):
+        raise ValueError("a facet neighbour of an owned cell is not on this rank: the mesh needs an overlap of at "
+                         "least one cell (Firedrake's default)")
+    gorder = np.lexsort((ghost_g, go))
+    if renumber and n_owned:
+        oorder = np.argsort(hilbert_index(mesh.cell_centroids()[:n_owned]), kind="stable")
+    else:
+        oorder = np.arange(n_owned)
+    perm = np.concatenate([oorder, n_owned + gorder]).astype(np.int64)
+    lm = sfc_renumber(mesh, perm)
+    new_gids = gids[perm]
+    # what I send to peer q = q's ghosts that I own, in q's ghost order (= ascending global id inside my run)
+    so = np.argsort(new_gids[:n_owned], kind="stable")
+    sorted_owned = new_gids[:n_owned][so]
+    send, peers = {}, []
+    for q, g in enumerate(gathered):
+        qo = _owners_of(g["ghost"], gathered) if q != rank else go
+        peers.append(PeerInfo(q, g["owned"].shape[0], g["ghost"].shape[0], np.sort(qo)))
+        if q == rank:
+            continue
+        mine = np.sort(g["ghost"][qo == rank])
+        if mine.size:
+            pos = np.searchsorted(sorted_owned, mine)
+            assert np.array_equal(sorted_owned[pos], mine)
+            send[q] = so[pos].astype(np.int64)
+    blen = {}
+    for g in gathered:
+        for mk, ln in g["boundary_len"].items():
+            blen[mk] = blen.get(mk, 0.0) + ln
+    lm.meta.update(global_cells=new_gids, global_boundary_len=blen, n_owned=n_owned, halo=halo, sfc=True)
+    part = LocalPart(rank, world, lm, new_gids[:n_owned], new_gids[n_owned:], go[gorder], send)
+    peers[rank] = part
+    return peers, part
+
+
+def torch_allgather(obj):
+    """All-gather of a picklable object over torch.distributed's default group (gloo or NCCL)."""
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def plan_from_local_mesh(mesh: Mesh2D, n_owned, global_ids, rank=None, allgather=None, halo="facet",
+                         transport="auto", overlap=True, fused=True, renumber=True):
+    """
+    HaloPlan of a mesh that arrives already distributed: `mesh` = this rank's cells, the `n_owned` owned ones first
+    (connectivity built; facets on the outer edge of the overlap marked with `mark_unknown_facets`), `global_ids` =
+    a global number per local cell.  `allgather(obj) -> [obj of rank 0, ...]` defaults to torch.distributed's; an
+    mpi4py communicator's `comm.allgather` (Firedrake's `mesh.comm`) works as well, provided both number the ranks
+    alike.  `halo` says what the overlap holds ('facet' neighbours, or 'vertex': every cell around an owned cell's
+    vertices -- the limiter needs that, DistributedMeshOverlapType.VERTEX on the Firedrake side).
+    Returns (plan, part); part.mesh is the device-ordered local mesh, part.mesh.cell_perm[new] = old local cell.
+    """
+    if allgather is None:
+        allgather = torch_allgather
+    gathered = allgather(local_contribution(mesh, n_owned, global_ids))
+    if rank is None:
+        import torch.distributed as dist
+        rank = dist.get_rank()
+    parts, part = part_from_gathered(mesh, n_owned, global_ids, gathered, rank, halo=halo, renumber=renumber)
+    return HaloPlan(parts, rank, transport=transport, overlap=overlap, fused=fused), part
