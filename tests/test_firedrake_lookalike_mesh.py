@@ -142,6 +142,8 @@ def fake_firedrake(monkeypatch):
     mod = types.ModuleType("firedrake")
 
     def FunctionSpace(mesh, family, degree):
+        if (family, degree) == ("DG", 0):
+            return mesh.dg0_space()
         assert family == "CG" and degree == 1
         return mesh.p1_space()
     mod.FunctionSpace = FunctionSpace
@@ -218,3 +220,171 @@ def test_node_maps_of_the_adaptor_on_a_firedrake_shaped_mesh(fake_firedrake, per
             sel = m.bf_marker == marker
             want = dev[m.bf_cell, :, 0][np.arange(m.n_bfacets)[:, None], FACET_NODES[m.bf_lf]]
             assert np.allclose(np.asarray(vals)[sel], want[sel], atol=1e-12)
+
+
+# ---------------------------------------------------------------- a mesh Firedrake has distributed itself (mpiexec -n N)
+class _HaloMap:
+    """PyOP2 map of a distributed set: `values` stops at the owned entities, `values_with_halo` has them all."""
+
+    def __init__(self, values, n_owned):
+        self.values_with_halo = values
+        self.values = values[:n_owned]
+        self.arity = values.shape[1]
+
+
+class _HaloDat:
+    def __init__(self, data, n_owned_rows):
+        self._all, self._n = data, n_owned_rows
+        self.dat_version = 0
+
+    @property
+    def data_ro(self):
+        return self._all[:self._n]
+
+    data = data_ro
+
+    @property
+    def data_ro_with_halos(self):
+        return self._all
+
+    data_with_halos = data_ro_with_halos
+
+
+class _HaloSpace(_Space):
+    def __init__(self, mesh, family, values, n_owned, degree=1):
+        self._mesh, self._el, self._map = mesh, _Element(family, degree), _HaloMap(values, n_owned)
+
+
+class _DistributedLookalike:
+    """Rank `rank`'s view of `src` under the ownership `owner`, the way Firedrake presents a distributed mesh: owned
+    cells first, then a VERTEX overlap; private vertex numbering; DG0 dofs numbered globally through an lgmap;
+    exterior facets of owned cells first (`facet_cell`), those of overlap cells only behind the `_with_halo`
+    accessors; facets on the outer edge of the overlap in neither list."""
+
+    def __init__(self, src, owner, rank, world, seed=0):
+        rng = np.random.default_rng(100 * seed + rank)
+        owned = np.nonzero(owner == rank)[0]
+        ptr, idx = src.vertex_to_cell_csr()
+        tv = np.unique(src.topo[src.cells[owned]])
+        cand = np.unique(np.concatenate([idx[ptr[v]:ptr[v + 1]] for v in tv]))
+        ghost = cand[owner[cand] != rank]
+        self.gids = np.concatenate([rng.permutation(owned), rng.permutation(ghost)]).astype(np.int64)
+        self.n_owned, n_local = owned.shape[0], self.gids.shape[0]
+        cells_g = src.cells[self.gids].astype(np.int64)
+        self.flipped = rng.random(n_local) < 0.2
+        cells_g[self.flipped, 1], cells_g[self.flipped, 2] = cells_g[self.flipped, 2].copy(), cells_g[self.flipped, 1].copy()
+        vused = rng.permutation(np.unique(cells_g))
+        self.vused = vused
+        vloc = np.full(src.n_vertices, -1, dtype=np.int64)
+        vloc[vused] = np.arange(vused.shape[0])
+        self._cmap = vloc[cells_g]
+        self.local_cells_global_vertices = cells_g
+        self.cell_set = types.SimpleNamespace(size=self.n_owned, total_size=n_local)
+        self.coordinates = _Function(_HaloSpace(self, "Lagrange", self._cmap, self.n_owned), src.coords[vused].copy())
+        self.comm = types.SimpleNamespace(size=world, rank=rank, allgather=None)
+        self._distribution_parameters = {"overlap_type": (types.SimpleNamespace(name="VERTEX"), 1)}
+        # DG0: local dof = a permutation of the local cells (owned dofs first), global number through the lgmap
+        dof_of_cell = np.concatenate([rng.permutation(self.n_owned), self.n_owned + rng.permutation(n_local - self.n_owned)])
+        lg = np.empty(n_local, dtype=np.int64)
+        lg[dof_of_cell] = 7 * self.gids + 3                     # any injective global numbering will do
+        self._dg0 = _HaloSpace(self, "Discontinuous Lagrange", dof_of_cell.reshape(-1, 1), self.n_owned, degree=0)
+        self._dg0.dof_dset = types.SimpleNamespace(lgmap=types.SimpleNamespace(indices=lg))
+        # exterior facets (of the DOMAIN boundary): owned cells' first
+        rows = []
+        for c_loc, c in enumerate(self.gids):
+            for f in range(3):
+                if src.nbr[c, f] < 0:
+                    lf = f
+                    if self.flipped[c_loc] and f in (1, 2):
+                        lf = 3 - f
+                    rows.append((c_loc, lf, int(src.bf_marker[-(src.nbr[c, f] + 1)])))
+        rows = np.array(rows, dtype=np.int64).reshape(-1, 3)
+        own = rows[rows[:, 0] < self.n_owned]
+        gh = rows[rows[:, 0] >= self.n_owned]
+        rows = np.vstack([own[rng.permutation(own.shape[0])], gh[rng.permutation(gh.shape[0])]])
+        ef = _Facets()
+        ef.facet_cell_map = _HaloMap(rows[:, :1].copy(), own.shape[0])
+        ef.facet_cell = ef.facet_cell_map.values
+        ef.local_facet_dat = _HaloDat(rows[:, 1:2].copy(), own.shape[0])
+        ef.markers = rows[:, 2].copy()
+        self.exterior_facets = ef
+
+    def p1_space(self):
+        return _HaloSpace(self, "Lagrange", self._cmap, self.n_owned)
+
+    def dg0_space(self):
+        return self._dg0
+
+    def p1dg_function(self, nodal_of_global_vertex):
+        """P1DG Function (dofs 3c..3c+2 of local cell c, overlap rows after the owned ones) holding a vertex field."""
+        n_local = self.cell_set.total_size
+        fs = _HaloSpace(self, "Discontinuous Lagrange", np.arange(3 * n_local, dtype=np.int64).reshape(n_local, 3),
+                        self.n_owned)
+        f = _Function(fs, None)
+        f.dat = _HaloDat(nodal_of_global_vertex[self.local_cells_global_vertices].reshape(-1).copy(), 3 * self.n_owned)
+        return f
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_adaptor_on_a_distributed_firedrake_shaped_mesh(fake_firedrake, world):
+    """`MeshAdaptor` on a mesh that arrives distributed: it must take the overlap along, build the halo plan from the
+    owned / overlap split and the global DG0 numbering (one all-gather over the mesh's communicator), and its node
+    maps must reach the overlap rows of the caller's Functions (`data_ro_with_halos`)."""
+    from thetis_b200 import parallel as PA
+    src = rectangle_mesh(8, 6, 8.0, 6.0)
+    c = src.cell_centroids()
+    owner = (np.floor(c[:, 0] / 8.0 * world).astype(np.int32) + (c[:, 1] > 3.0) * 1) % world
+    fms = [_DistributedLookalike(src, owner, r, world, seed=2) for r in range(world)]
+    # the all-gather: every rank's contribution, computed the way the adaptor computes it
+    gathered = []
+    for fm in fms:
+        m, _ = AD._mesh2d_from_firedrake(fm, with_overlap=True)
+        gids = AD._global_cell_ids(fm, m.n_cells)
+        assert np.array_equal(gids, 7 * fm.gids + 3)
+        gathered.append(PA.local_contribution(m, fm.n_owned, gids))
+    blen = src.boundary_length()
+    ads = []
+    for r, fm in enumerate(fms):
+        fm.comm.allgather = lambda obj, _g=gathered: _g
+        ad = AD.MeshAdaptor(fm)
+        ads.append(ad)
+        assert ad.with_halos and ad.halo is not None and ad.halo.rank == r and ad.halo.world == world
+        part = ad.halo.part
+        assert ad.n_owned == fm.n_owned == part.n_owned and ad.mesh.n_cells == fm.cell_set.total_size
+        assert ad.mesh.meta["halo"] == "vertex"
+        assert np.all(ad.mesh.cell_area() > 0)
+        # owned cells first, ghosts grouped by owner; global ids survive the renumbering
+        glob = (ad.mesh.meta["global_cells"] - 3) // 7
+        assert np.array_equal(np.sort(glob[:ad.n_owned]), np.nonzero(owner == r)[0])
+        assert np.all(np.diff(owner[glob[ad.n_owned:]]) >= 0) and np.all(owner[glob[ad.n_owned:]] != r)
+        assert np.allclose(ad.mesh.cell_centroids(), src.cell_centroids()[glob], atol=1e-12)
+        # boundary lengths are global; the exterior facets of overlap cells were found, the overlap edge is unknown
+        assert set(ad.boundary_len) == set(blen)
+        assert all(abs(ad.boundary_len[k] - blen[k]) < 1e-12 for k in blen)
+        assert not np.any(ad.mesh.nbr[:ad.n_owned] == np.iinfo(np.int32).min)
+        nb_glob = src.nbr[glob]
+        assert np.array_equal(np.sort((ad.mesh.nbr < 0) & (ad.mesh.nbr != np.iinfo(np.int32).min), axis=1).sum(1),
+                              (nb_glob < 0).sum(1))
+        # node maps reach the overlap rows: a P1DG Function holding x is read back at the device mesh's nodes
+        fx = fm.p1dg_function(src.coords[:, 0])
+        dev = ad.mesh.coords[ad.mesh.cells]
+        assert np.allclose(ad.nodal_values(fx), dev[..., 0], atol=1e-12)
+        nm = ad.dg_node_map(fx.function_space())
+        assert np.array_equal(np.sort(nm.reshape(-1)), np.arange(3 * ad.mesh.n_cells))
+        assert nm[:ad.n_owned].max() < 3 * ad.n_owned <= nm[ad.n_owned:].min()
+        assert ad.dat_ro(fx).shape[0] == 3 * ad.mesh.n_cells and fx.dat.data_ro.shape[0] == 3 * ad.n_owned
+    # send lists mirror the peers' ghost runs across the adaptors
+    for r, ad in enumerate(ads):
+        for q, lst in ad.halo.part.send_lists.items():
+            peer = ads[q].halo.part
+            assert np.array_equal(ad.halo.part.owned_global[lst], peer.ghost_global[peer.ghost_owner == r])
+
+
+def test_distributed_mesh_without_overlap_is_rejected(fake_firedrake):
+    src = rectangle_mesh(4, 4, 4.0, 4.0)
+    owner = (src.cell_centroids()[:, 0] > 2.0).astype(np.int32)
+    fm = _DistributedLookalike(src, owner, 0, 2)
+    fm._distribution_parameters = {"overlap_type": (types.SimpleNamespace(name="NONE"), 0)}
+    fm.comm.allgather = lambda obj: [obj, obj]
+    with pytest.raises(NotImplementedError, match="overlap of at least one cell"):
+        AD.MeshAdaptor(fm)

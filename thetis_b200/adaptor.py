@@ -148,17 +148,61 @@ def _family_of_name(fam):
     return fam
 
 
-def _mesh2d_from_firedrake(mesh):
+def _comm_size(mesh):
+    """Number of ranks a Firedrake mesh is distributed over (1 for anything without an MPI communicator)."""
+    comm = getattr(mesh, "comm", None)
+    try:
+        return int(comm.size) if comm is not None else 1
+    except Exception:                                          # noqa: BLE001
+        return 1
+
+
+def _map_rows(pmap, n, with_overlap):
+    """First `n` rows of a PyOP2 map; `values` stops at the owned entities, `values_with_halo` carries the overlap."""
+    vals = getattr(pmap, "values_with_halo", None) if with_overlap else None
+    if vals is None:
+        vals = pmap.values
+    return np.asarray(vals[:n], dtype=np.int64)
+
+
+def _overlap_kind(mesh):
+    """'vertex' / 'facet': what the overlap of a distributed Firedrake mesh holds (firedrake/mesh.py
+    distribution_parameters['overlap_type'] = (DistributedMeshOverlapType.X, depth); Firedrake's default is FACET)."""
+    dp = getattr(mesh, "_distribution_parameters", None) or {}
+    ot = dp.get("overlap_type")
+    if ot is None:
+        return "facet"
+    kind, depth = ot[0], (ot[1] if len(ot) > 1 else 1)
+    name = str(getattr(kind, "name", kind)).lower()
+    if "none" in name or depth < 1:
+        raise NotImplementedError("a distributed mesh needs an overlap of at least one cell "
+                                  "(distribution_parameters={'overlap_type': (DistributedMeshOverlapType.VERTEX, 1)})")
+    return "vertex" if "vertex" in name else "facet"
+
+
+def _global_cell_ids(mesh, n_local):
+    """A global number per local cell (overlap included) of a distributed Firedrake mesh: the global DG0 dof numbers
+    (PETSc local-to-global map of the DG0 space: one dof per cell)."""
+    import firedrake as fd
+    dg0 = fd.FunctionSpace(mesh, "DG", 0)
+    cell_dof = _map_rows(dg0.cell_node_map(), n_local, True).reshape(-1)
+    lg = np.asarray(dg0.dof_dset.lgmap.indices, dtype=np.int64)
+    return lg[cell_dof]
+
+
+def _mesh2d_from_firedrake(mesh, with_overlap=False):
     """
     Build a `Mesh2D` from a real Firedrake mesh.  Written against the attribute names listed in SURVEY.md 8b;
     exercised against a Firedrake-shaped look-alike (tests/test_firedrake_lookalike_mesh.py), never against
-    Firedrake itself (not installable here).
+    Firedrake itself (not installable here).  ``with_overlap``: the mesh is distributed over MPI ranks -- the
+    overlap cells are taken along (after the owned ones) and one-sided facets that are not in
+    `mesh.exterior_facets` become facets with an unknown neighbour.
     """
     import firedrake as fd  # noqa: F401  (ImportError if absent, by design)
     coords_f = mesh.coordinates
     cfs = coords_f.function_space()
-    ncell = mesh.cell_set.size                                 # owned cells
-    cmap = np.asarray(cfs.cell_node_map().values[:ncell], dtype=np.int64)
+    ncell = mesh.cell_set.total_size if with_overlap else mesh.cell_set.size
+    cmap = _map_rows(cfs.cell_node_map(), ncell, with_overlap)
     xy = np.asarray(coords_f.dat.data_ro_with_halos, dtype=np.float64)
     used = np.unique(cmap)
     remap = np.full(xy.shape[0], -1, dtype=np.int64)
@@ -166,7 +210,7 @@ def _mesh2d_from_firedrake(mesh):
     coords = xy[used][:, :2]
     cells = remap[cmap].astype(np.int32)
     p1 = fd.FunctionSpace(mesh, "CG", 1)
-    tmap = np.asarray(p1.cell_node_map().values[:ncell], dtype=np.int64)
+    tmap = _map_rows(p1.cell_node_map(), ncell, with_overlap)
     topo = np.zeros(coords.shape[0], dtype=np.int64)
     topo[cells.reshape(-1)] = tmap.reshape(-1)
     _, topo = np.unique(topo, return_inverse=True)
@@ -177,8 +221,11 @@ def _mesh2d_from_firedrake(mesh):
     m.make_ccw()
     # exterior facet markers by topological edge
     ef = mesh.exterior_facets
-    fcell = np.asarray(ef.facet_cell).reshape(-1)
-    flocal = np.asarray(ef.local_facet_dat.data_ro).reshape(-1)
+    fcm = getattr(ef, "facet_cell_map", None) if with_overlap else None
+    fcell = (_map_rows(fcm, None, True) if fcm is not None else np.asarray(ef.facet_cell)).reshape(-1)
+    lfd = ef.local_facet_dat
+    flocal = np.asarray(lfd.data_ro_with_halos if with_overlap and hasattr(lfd, "data_ro_with_halos")
+                        else lfd.data_ro).reshape(-1)
     markers = np.asarray(ef.markers).reshape(-1)
     em = {}
     for c, lf, mk in zip(fcell, flocal, markers):
@@ -186,7 +233,11 @@ def _mesh2d_from_firedrake(mesh):
             continue
         ta, tb = int(topo[remap[cmap[c, FACET_NODES[lf, 0]]]]), int(topo[remap[cmap[c, FACET_NODES[lf, 1]]]])
         em[(min(ta, tb), max(ta, tb))] = int(mk)
-    m.build_connectivity(edge_markers=em)
+    if with_overlap:
+        from .parallel import build_overlap_connectivity
+        build_overlap_connectivity(m, em)
+    else:
+        m.build_connectivity(edge_markers=em)
     m.cell_perm = np.arange(m.n_cells, dtype=np.int64)
     return m, swap
 
@@ -199,16 +250,32 @@ class MeshAdaptor:
 
     def __init__(self, mesh_obj, renumber=True):
         tm = getattr(mesh_obj, "topology_mesh", None)
+        dist_fd = False
         if isinstance(mesh_obj, Mesh2D):
             base, swap = mesh_obj, np.zeros(mesh_obj.n_cells, dtype=bool)
         elif isinstance(tm, Mesh2D):
             base, swap = tm, np.zeros(tm.n_cells, dtype=bool)
         else:
-            base, swap = _mesh2d_from_firedrake(mesh_obj)
+            dist_fd = _comm_size(mesh_obj) > 1
+            base, swap = _mesh2d_from_firedrake(mesh_obj, with_overlap=dist_fd)
         self.mesh_obj_ref = weakref.ref(mesh_obj) if not isinstance(mesh_obj, Mesh2D) else (lambda: mesh_obj)
         self.base = base
         self.swap = swap
-        if renumber and not base.meta.get("sfc"):
+        # Functions on a mesh Firedrake distributed itself: overlap rows live behind the `_with_halos` accessors
+        self.with_halos = dist_fd
+        plan = None
+        if dist_fd:
+            # a mesh Firedrake has already distributed (mpiexec -n N): the halo plan comes from the local cells, the
+            # owned / overlap split and the global DG0 numbering; Firedrake's communicator does the one all-gather.
+            # torch.distributed must be initialised with the same ranks (the transport of the stage exchanges).
+            from .parallel import plan_from_local_mesh
+            comm = mesh_obj.comm
+            plan, part = plan_from_local_mesh(base, int(mesh_obj.cell_set.size), _global_cell_ids(mesh_obj, base.n_cells),
+                                              rank=int(comm.rank), allgather=comm.allgather,
+                                              halo=_overlap_kind(mesh_obj), renumber=renumber)
+            self.mesh = part.mesh
+            self.perm = np.asarray(part.mesh.cell_perm, dtype=np.int64)
+        elif renumber and not base.meta.get("sfc"):
             self.mesh = sfc_renumber(base)
             # cell_perm composes with earlier renumberings of `base`; we need new -> base order
             base_perm = base.cell_perm if base.cell_perm is not None else np.arange(base.n_cells)
@@ -220,9 +287,9 @@ class MeshAdaptor:
             self.perm = np.arange(base.n_cells, dtype=np.int64)
         self.engine = None
         # distributed run: the mesh object carries this rank's HaloPlan (thetis_b200.parallel.distribute_mesh)
-        self.halo = getattr(mesh_obj, "halo_plan", None)
+        self.halo = plan if plan is not None else getattr(mesh_obj, "halo_plan", None)
         self.n_owned = self.halo.part.n_owned if self.halo is not None else self.mesh.n_cells
-        bl = getattr(mesh_obj, "boundary_len", None)
+        bl = self.mesh.meta["global_boundary_len"] if plan is not None else getattr(mesh_obj, "boundary_len", None)
         self.boundary_len = dict(bl) if bl is not None else self.mesh.boundary_length()
 
     def get_engine(self):
@@ -237,8 +304,18 @@ class MeshAdaptor:
         return self.engine
 
     # ------------------------------------------------------------ node maps
+    def dat_ro(self, func):
+        """The Function's values as the node maps of this adaptor index them (overlap rows included)."""
+        d = func.dat
+        return np.asarray(d.data_ro_with_halos if self.with_halos else d.data_ro)
+
+    def dat_rw(self, func):
+        """Writable view of the same rows."""
+        d = func.dat
+        return d.data_with_halos if self.with_halos else d.data
+
     def _cell_nodes(self, fs):
-        cm = np.asarray(fs.cell_node_map().values)[: self.base.n_cells].astype(np.int64)
+        cm = _map_rows(fs.cell_node_map(), self.base.n_cells, self.with_halos)
         if cm.shape[1] != 3:
             raise NotImplementedError("only P1 / P1DG spaces are supported on the accelerated path")
         if self.swap.any():
@@ -255,8 +332,7 @@ class MeshAdaptor:
     def nodal_values(self, func):
         """(nt, 3[,k]) values of a P1/P1DG Function at the device cells' nodes."""
         fs = func.function_space()
-        data = np.asarray(func.dat.data_ro)
-        return data[self._cell_nodes(fs)]
+        return self.dat_ro(func)[self._cell_nodes(fs)]
 
     def evaluate(self, expr):
         """
@@ -384,7 +460,7 @@ class MeshAdaptor:
             idx = np.stack([cn[m.bf_cell, FACET_NODES[m.bf_lf, 0]], cn[m.bf_cell, FACET_NODES[m.bf_lf, 1]]], axis=1)
             cache[id(fs)] = idx
             self.__dict__.setdefault("_bf_keep", []).append(fs)     # keep the key object alive
-        data = np.asarray(func.dat.data_ro)
+        data = self.dat_ro(func)
         if marker is None:
             return data[idx]
         key = (id(fs), int(marker))

@@ -62,9 +62,9 @@ class VertexBasedP1DGLimiter:
             raise NotImplementedError("distributed limiter needs the field to be owned by a B200 tracer integrator")
         if self.node_map is None:
             self.node_map = torch.as_tensor(self.adaptor.dg_node_map(self.P1DG).reshape(-1)).to(eng.device)
-        q = torch.as_tensor(np.ascontiguousarray(np.asarray(field.dat.data_ro, dtype=np.float64))).to(eng.device)
+        q = torch.as_tensor(np.ascontiguousarray(np.asarray(self.adaptor.dat_ro(field), dtype=np.float64))).to(eng.device)
         c = eng.new_tracer()
         eng.tracer_from_field(q, self.node_map, c)
         eng.limiter_apply(c)
         eng.tracer_to_field(c, self.node_map, q)
-        field.dat.data[...] = q.cpu().numpy()
+        self.adaptor.dat_rw(field)[...] = q.cpu().numpy()

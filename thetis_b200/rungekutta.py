@@ -192,7 +192,7 @@ class ERKGenericShuOsher:
             if not np.array_equal(nm_u, nm_e):
                 raise NotImplementedError("velocity and elevation P1DG spaces must share their node numbering")
             self.node_map = torch.as_tensor(nm_u.reshape(-1)).to(dev)
-            n_nodes = int(np.asarray(eta_f.dat.data_ro).shape[0])
+            n_nodes = int(ad.dat_ro(eta_f).shape[0])
             nb = self.n_buffers
             self.buf = self.halo.alloc(9, nbuf=nb) if self.halo is not None else [eng.new_state() for _ in range(nb)]
             self._d_uv = torch.empty((n_nodes, 2), dtype=torch.float64, device=dev)
@@ -203,7 +203,7 @@ class ERKGenericShuOsher:
         else:
             nm = ad.dg_node_map(self.solution.function_space())
             self.node_map = torch.as_tensor(nm.reshape(-1)).to(dev)
-            n_nodes = int(np.asarray(self.solution.dat.data_ro).shape[0])
+            n_nodes = int(ad.dat_ro(self.solution).shape[0])
             nb = self.n_buffers
             self.buf = self.halo.alloc(3, nbuf=nb) if self.halo is not None else [eng.new_tracer() for _ in range(nb)]
             self._d_q = torch.empty(n_nodes, dtype=torch.float64, device=dev)
@@ -602,13 +602,13 @@ class ERKGenericShuOsher:
         eng = self.engine
         if self._kind == "swe":
             uv_f, eta_f = self.solution.subfunctions
-            self._h_uv.numpy()[...] = np.asarray(uv_f.dat.data_ro).reshape(-1, 2)
-            self._h_eta.numpy()[...] = np.asarray(eta_f.dat.data_ro)
+            self._h_uv.numpy()[...] = self.adaptor.dat_ro(uv_f).reshape(-1, 2)
+            self._h_eta.numpy()[...] = self.adaptor.dat_ro(eta_f)
             self._d_uv.copy_(self._h_uv, non_blocking=True)
             self._d_eta.copy_(self._h_eta, non_blocking=True)
             eng.state_from_fields(self._d_uv, self._d_eta, self.node_map, self.buf[0])
         else:
-            self._h_q.numpy()[...] = np.asarray(self.solution.dat.data_ro)
+            self._h_q.numpy()[...] = self.adaptor.dat_ro(self.solution)
             self._d_q.copy_(self._h_q, non_blocking=True)
             eng.tracer_from_field(self._d_q, self.node_map, self.buf[0])
         if self.halo is not None:
@@ -634,13 +634,14 @@ class ERKGenericShuOsher:
             self._h_eta.copy_(self._d_eta, non_blocking=True)
             torch.cuda.current_stream(eng.device).synchronize()
             uv_f, eta_f = self.solution.subfunctions
-            uv_f.dat.data[...] = self._h_uv.numpy().reshape(np.asarray(uv_f.dat.data_ro).shape)
-            eta_f.dat.data[...] = self._h_eta.numpy()
+            ad = self.adaptor
+            ad.dat_rw(uv_f)[...] = self._h_uv.numpy().reshape(ad.dat_ro(uv_f).shape)
+            ad.dat_rw(eta_f)[...] = self._h_eta.numpy()
         else:
             eng.tracer_to_field(src, self.node_map, self._d_q)
             self._h_q.copy_(self._d_q, non_blocking=True)
             torch.cuda.current_stream(eng.device).synchronize()
-            self.solution.dat.data[...] = self._h_q.numpy()
+            self.adaptor.dat_rw(self.solution)[...] = self._h_q.numpy()
         self._host_stale = False
         self._last_host_version = self._solution_version()
 
@@ -734,9 +735,9 @@ class ERKGenericShuOsher:
         if self._own_swe_state is None:
             self._own_swe_state = self.halo.alloc(9, nbuf=1)[0] if self.halo is not None else eng.new_state()
         el_f = self.fields.get("elev_2d")
-        uvd = torch.as_tensor(np.ascontiguousarray(np.asarray(uv_f.dat.data_ro).reshape(-1, 2))).to(eng.device)
+        uvd = torch.as_tensor(np.ascontiguousarray(self.adaptor.dat_ro(uv_f).reshape(-1, 2))).to(eng.device)
         if el_f is not None:
-            ed = torch.as_tensor(np.ascontiguousarray(np.asarray(el_f.dat.data_ro))).to(eng.device)
+            ed = torch.as_tensor(np.ascontiguousarray(self.adaptor.dat_ro(el_f))).to(eng.device)
         else:
             ed = torch.zeros(uvd.shape[0], dtype=torch.float64, device=eng.device)
         eng.state_from_fields(uvd, ed, self.node_map, self._own_swe_state)
