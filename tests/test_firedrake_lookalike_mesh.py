@@ -325,8 +325,18 @@ class _DistributedLookalike:
         return f
 
 
+@pytest.fixture
+def no_process_group(monkeypatch):
+    """The adaptor brings torch.distributed up from the mesh's communicator; one test process cannot be N ranks, so
+    the call is recorded instead (the real thing runs in tests/test_local_mesh_plan.py over two processes)."""
+    from thetis_b200 import parallel as PA
+    calls = []
+    monkeypatch.setattr(PA, "init_torch_distributed_from_comm", lambda comm, backend=None: calls.append(comm))
+    return calls
+
+
 @pytest.mark.parametrize("world", [2, 3])
-def test_adaptor_on_a_distributed_firedrake_shaped_mesh(fake_firedrake, world):
+def test_adaptor_on_a_distributed_firedrake_shaped_mesh(fake_firedrake, no_process_group, world):
     """`MeshAdaptor` on a mesh that arrives distributed: it must take the overlap along, build the halo plan from the
     owned / overlap split and the global DG0 numbering (one all-gather over the mesh's communicator), and its node
     maps must reach the overlap rows of the caller's Functions (`data_ro_with_halos`)."""
@@ -373,6 +383,7 @@ def test_adaptor_on_a_distributed_firedrake_shaped_mesh(fake_firedrake, world):
         assert np.array_equal(np.sort(nm.reshape(-1)), np.arange(3 * ad.mesh.n_cells))
         assert nm[:ad.n_owned].max() < 3 * ad.n_owned <= nm[ad.n_owned:].min()
         assert ad.dat_ro(fx).shape[0] == 3 * ad.mesh.n_cells and fx.dat.data_ro.shape[0] == 3 * ad.n_owned
+    assert [c.rank for c in no_process_group] == list(range(world))      # every adaptor asked for the process group
     # send lists mirror the peers' ghost runs across the adaptors
     for r, ad in enumerate(ads):
         for q, lst in ad.halo.part.send_lists.items():
@@ -380,7 +391,7 @@ def test_adaptor_on_a_distributed_firedrake_shaped_mesh(fake_firedrake, world):
             assert np.array_equal(ad.halo.part.owned_global[lst], peer.ghost_global[peer.ghost_owner == r])
 
 
-def test_distributed_mesh_without_overlap_is_rejected(fake_firedrake):
+def test_distributed_mesh_without_overlap_is_rejected(fake_firedrake, no_process_group):
     src = rectangle_mesh(4, 4, 4.0, 4.0)
     owner = (src.cell_centroids()[:, 0] > 2.0).astype(np.int32)
     fm = _DistributedLookalike(src, owner, 0, 2)

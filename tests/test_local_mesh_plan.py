@@ -243,3 +243,57 @@ def test_plan_from_local_mesh_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+# ---------------------------------------------------------------- torch.distributed from an MPI-shaped communicator
+class _BoardComm:
+    """mpi4py-shaped communicator (rank, size, bcast, allgather) over a multiprocessing manager: what a Thetis script
+    under `mpiexec` hands over through `mesh.comm`."""
+
+    def __init__(self, rank, size, board, barrier):
+        self.rank, self.size, self._board, self._barrier, self._n = rank, size, board, barrier, 0
+
+    def allgather(self, obj):
+        self._n += 1
+        self._board[(self._n, self.rank)] = obj
+        self._barrier.wait()
+        return [self._board[(self._n, r)] for r in range(self.size)]
+
+    def bcast(self, obj, root=0):
+        return self.allgather(obj)[root]
+
+
+def _worker_from_comm(rank, world, board, barrier, out):
+    for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):          # an mpiexec launch sets none of these
+        os.environ.pop(k, None)
+    comm = _BoardComm(rank, world, board, barrier)
+    try:
+        assert PA.init_torch_distributed_from_comm(comm) == (rank, world)
+        assert dist.get_rank() == rank and dist.get_world_size() == world and dist.get_backend() == "gloo"
+        assert PA.init_torch_distributed_from_comm(comm) == (rank, world)     # second call: only the check
+        mesh = _mesh("rect")
+        owner = _ownership(mesh, world, seed=4)
+        lm, n_owned, gids, _ = _local_view(mesh, owner, rank, "facet", seed=9)
+        plan, part = PA.plan_from_local_mesh(lm, n_owned, gids, rank=comm.rank, allgather=comm.allgather)
+        _, _, rec = _records(mesh)
+        send_idx = np.concatenate([part.send_lists[q] for q in range(world) if q in part.send_lists])
+        ghost = torch.zeros((part.n_ghost, 9), dtype=torch.float64)
+        PA.exchange_halo(part, torch.as_tensor(rec[part.owned_global][send_idx].copy()), ghost)
+        ok = bool(np.array_equal(ghost.numpy(), rec[part.ghost_global]))
+        wrong = _BoardComm((rank + 1) % world, world, board, barrier)
+        try:
+            PA.init_torch_distributed_from_comm(wrong)
+            ok = False
+        except RuntimeError as exc:
+            ok = ok and "number the processes alike" in str(exc)
+        out[rank] = ok
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_process_group_from_an_mpi_shaped_communicator():
+    mgr = mp.Manager()
+    out, board, barrier = mgr.dict(), mgr.dict(), mgr.Barrier(2)
+    mp.spawn(_worker_from_comm, args=(2, board, barrier, out), nprocs=2, join=True)
+    assert dict(out) == {0: True, 1: True}

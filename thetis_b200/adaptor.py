@@ -267,9 +267,10 @@ class MeshAdaptor:
         if dist_fd:
             # a mesh Firedrake has already distributed (mpiexec -n N): the halo plan comes from the local cells, the
             # owned / overlap split and the global DG0 numbering; Firedrake's communicator does the one all-gather.
-            # torch.distributed must be initialised with the same ranks (the transport of the stage exchanges).
-            from .parallel import plan_from_local_mesh
+            # torch.distributed (the transport of the stage exchanges) is brought up with the same rank numbering.
+            from .parallel import plan_from_local_mesh, init_torch_distributed_from_comm
             comm = mesh_obj.comm
+            init_torch_distributed_from_comm(comm)
             plan, part = plan_from_local_mesh(base, int(mesh_obj.cell_set.size), _global_cell_ids(mesh_obj, base.n_cells),
                                               rank=int(comm.rank), allgather=comm.allgather,
                                               halo=_overlap_kind(mesh_obj), renumber=renumber)

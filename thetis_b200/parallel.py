@@ -23,7 +23,7 @@ import numpy as np
 from .mesh import Mesh2D, FACET_NODES
 
 __all__ = ["LocalPart", "PeerInfo", "partition_mesh", "HaloPlan", "distribute_mesh", "exchange_halo",
-           "mark_unknown_facets", "build_overlap_connectivity", "local_contribution", "part_from_gathered", "plan_from_local_mesh"]
+           "mark_unknown_facets", "build_overlap_connectivity", "local_contribution", "part_from_gathered", "plan_from_local_mesh", "init_torch_distributed_from_comm"]
 
 INT32_MIN = np.iinfo(np.int32).min
 
@@ -597,3 +597,46 @@ def plan_from_local_mesh(mesh: Mesh2D, n_owned, global_ids, rank=None, allgather
         rank = dist.get_rank()
     parts, part = part_from_gathered(mesh, n_owned, global_ids, gathered, rank, halo=halo, renumber=renumber)
     return HaloPlan(parts, rank, transport=transport, overlap=overlap, fused=fused), part
+
+
+def init_torch_distributed_from_comm(comm, backend=None):
+    """
+    Bring torch.distributed up with the rank numbering of an MPI communicator (mpi4py's interface: `rank`, `size`,
+    `bcast`, `allgather`) -- the situation of a Thetis script started with `mpiexec -n N`, where nobody set
+    RANK / WORLD_SIZE / MASTER_ADDR.  Rank 0 picks a free TCP port and broadcasts its address; every rank binds the
+    GPU with the index of its position among the ranks of its host (one process per GPU).  A group that is already
+    initialised is only checked for the same numbering.  Returns (rank, world).
+    """
+    import socket
+    import torch
+    import torch.distributed as dist
+    rank, world = int(comm.rank), int(comm.size)
+    if dist.is_initialized():
+        if dist.get_rank() != rank or dist.get_world_size() != world:
+            raise RuntimeError(f"torch.distributed is rank {dist.get_rank()} of {dist.get_world_size()} but the mesh's "
+                               f"communicator is rank {rank} of {world}: both must number the processes alike")
+        return rank, world
+    host = socket.gethostname()
+    hosts = comm.allgather(host)
+    local_rank = sum(1 for h in hosts[:rank] if h == host)
+    one_node = all(h == hosts[0] for h in hosts)
+    addr_port = None
+    if rank == 0:
+        s = socket.socket()
+        s.bind(("127.0.0.1" if one_node else "", 0))
+        port = s.getsockname()[1]
+        s.close()
+        addr = "127.0.0.1"
+        if not one_node:
+            try:
+                addr = socket.gethostbyname(host)
+            except OSError:
+                addr = host
+        addr_port = (addr, port)
+    addr, port = comm.bcast(addr_port, root=0)
+    use_cuda = torch.cuda.is_available()
+    if use_cuda:
+        torch.cuda.set_device(local_rank % torch.cuda.device_count())
+    dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), init_method=f"tcp://{addr}:{port}",
+                            rank=rank, world_size=world)
+    return rank, world
