@@ -297,3 +297,53 @@ def test_process_group_from_an_mpi_shaped_communicator():
     out, board, barrier = mgr.dict(), mgr.dict(), mgr.Barrier(2)
     mp.spawn(_worker_from_comm, args=(2, board, barrier, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+# ---------------------------------------------------------------- the two routes agree
+@pytest.mark.parametrize("halo", ["facet", "vertex"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_local_route_reproduces_partition_mesh(halo, world):
+    """Fed with the parts `partition_mesh` cuts (the route every multi-GPU measurement went through), the local route
+    must arrive at the SAME device layout: cell order, ghost block, send lists, neighbour table, exterior facets and
+    boundary lengths -- so what the GPU tests established for one holds for the other."""
+    mesh = _mesh("gmsh")
+    ref = PA.partition_mesh(mesh, world, halo=halo)
+    gathered, inputs = [], []
+    for p in ref:
+        lm = p.mesh
+        bare = Mesh2D(coords=lm.coords, cells=lm.cells, topo=lm.topo, periodic=lm.periodic)
+        tv = lm.topo[lm.cells]
+        ext = {(int(tv[c, FACET_NODES[f, 0]]), int(tv[c, FACET_NODES[f, 1]])): int(mk)
+               for c, f, mk in zip(lm.bf_cell, lm.bf_lf, lm.bf_marker)}
+        PA.build_overlap_connectivity(bare, ext)
+        gids = np.concatenate([p.owned_global, p.ghost_global])
+        inputs.append((bare, p.n_owned, gids))
+        gathered.append(PA.local_contribution(bare, p.n_owned, gids))
+    for r, p in enumerate(ref):
+        bare, n_owned, gids = inputs[r]
+        peers, part = PA.part_from_gathered(bare, n_owned, gids, gathered, r, halo=halo, renumber=False)
+        assert np.array_equal(part.owned_global, p.owned_global)
+        assert np.array_equal(part.ghost_global, p.ghost_global)
+        assert np.array_equal(part.ghost_owner, p.ghost_owner)
+        assert set(part.send_lists) == set(p.send_lists)
+        for q in p.send_lists:
+            assert np.array_equal(part.send_lists[q], p.send_lists[q])
+        assert np.array_equal(part.send_counts, p.send_counts) and np.array_equal(part.recv_counts, p.recv_counts)
+        a, b = part.mesh, p.mesh
+        assert np.array_equal(a.coords[a.cells], b.coords[b.cells])              # same cells, same local vertex order
+        assert np.array_equal(a.nbr >= 0, b.nbr >= 0) and np.array_equal(a.nbr[a.nbr >= 0], b.nbr[b.nbr >= 0])
+        assert np.array_equal(a.nbr == INT32_MIN, b.nbr == INT32_MIN)
+        assert np.array_equal(a.nbr_lf[a.nbr >= 0], b.nbr_lf[b.nbr >= 0])
+        # exterior facets: same (cell, local facet, marker) set, and nbr points at the right row of each list
+        fa = sorted(zip(a.bf_cell.tolist(), a.bf_lf.tolist(), a.bf_marker.tolist()))
+        fb = sorted(zip(b.bf_cell.tolist(), b.bf_lf.tolist(), b.bf_marker.tolist()))
+        assert fa == fb
+        for m in (a, b):
+            i = np.arange(m.n_bfacets)
+            assert np.array_equal(m.nbr[m.bf_cell, m.bf_lf], -(1 + i))
+        gl, bl = a.meta["global_boundary_len"], b.meta["global_boundary_len"]
+        assert set(gl) == set(bl) and all(abs(gl[k] - bl[k]) < 1e-9 * max(1.0, bl[k]) for k in bl)
+        assert a.meta["n_owned"] == b.meta["n_owned"] and a.meta["halo"] == b.meta["halo"] == halo
+        for q in range(world):
+            assert (peers[q].n_owned, peers[q].n_ghost) == (ref[q].n_owned, ref[q].n_ghost)
+            assert np.array_equal(np.asarray(peers[q].ghost_owner), ref[q].ghost_owner)
