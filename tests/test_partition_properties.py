@@ -106,3 +106,103 @@ def test_partition_and_push_tables(kind, n, m, seed, world, halo, P):
                 arrays[q][slot] = arrays[r][cell]
     for r, p in enumerate(parts):
         assert np.array_equal(arrays[r][pads[r]:], p.ghost_global.astype(float))
+
+
+# ---------------------------------------------------------------- the route of a mesh that arrives distributed
+def _scrambled_view(mesh, owner, rank, halo, rng):
+    """Rank-local view with arbitrary cell / vertex numbering and no neighbour table (see tests/test_local_mesh_plan.py)."""
+    from thetis_b200.mesh import Mesh2D
+    from thetis_b200.parallel import build_overlap_connectivity
+    owned = np.nonzero(owner == rank)[0]
+    if halo == "facet":
+        nb = mesh.nbr[owned]
+        cand = np.unique(nb[nb >= 0])
+        ghost = cand[owner[cand] != rank]
+    else:
+        ghost = _vertex_neighbours(mesh, owned)
+    gids = np.concatenate([rng.permutation(owned), rng.permutation(ghost)]).astype(np.int64)
+    cells_g = mesh.cells[gids]
+    vused = rng.permutation(np.unique(cells_g))
+    vloc = np.full(mesh.n_vertices, -1, dtype=np.int64)
+    vloc[vused] = np.arange(vused.shape[0])
+    lm = Mesh2D(coords=mesh.coords[vused], cells=vloc[cells_g].astype(np.int32).reshape(-1, 3),
+                topo=np.unique(mesh.topo[vused], return_inverse=True)[1].astype(np.int32), periodic=mesh.periodic)
+    ext = {}
+    cl, fl = np.nonzero(mesh.nbr[gids] < 0)
+    for c_loc, f in zip(cl, fl):
+        a, b = lm.topo[lm.cells[c_loc, FACET_NODES[f]]]
+        ext[(int(a), int(b))] = int(mesh.bf_marker[-(mesh.nbr[gids[c_loc], f] + 1)])
+    build_overlap_connectivity(lm, ext)
+    return lm, owned.shape[0], gids
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(kind=st.sampled_from(["rect", "delaunay"]), n=st.integers(3, 8), m=st.integers(3, 6), seed=st.integers(0, 50),
+       world=st.integers(1, 6), halo=st.sampled_from(["facet", "vertex"]), P=st.sampled_from([4, 16, 128]))
+def test_plan_from_scrambled_local_views(kind, n, m, seed, world, halo, P):
+    """Random ownership (not contiguous, ranks may own scattered cells), random local numberings: the parts built from
+    local knowledge + one all-gather own every cell once, hold exactly the overlap they were given grouped by owner,
+    mirror each other's ghost runs, keep neighbours and markers, and the fused push built on them delivers every ghost."""
+    from thetis_b200.parallel import local_contribution, part_from_gathered
+    INT32_MIN = np.iinfo(np.int32).min
+    mesh = _mesh(kind, n, m, seed)
+    rng = np.random.default_rng(seed)
+    world = min(world, mesh.n_cells)
+    # blocks of the SFC order dealt to random ranks: scattered but not pathological; every rank owns something
+    nblk = max(world, min(mesh.n_cells, 3 * world))
+    blk = (np.arange(mesh.n_cells) * nblk) // mesh.n_cells
+    deal = np.concatenate([rng.permutation(world), rng.integers(0, world, nblk - world)])
+    owner = deal[blk].astype(np.int32)
+    views = [_scrambled_view(mesh, owner, r, halo, rng) for r in range(world)]
+    gathered = [local_contribution(lm, k, g) for lm, k, g in views]
+    built = [part_from_gathered(lm, k, g, gathered, r, halo=halo)[1] for r, (lm, k, g) in enumerate(views)]
+    assert np.array_equal(np.sort(np.concatenate([p.owned_global for p in built])), np.arange(mesh.n_cells))
+    cent = mesh.cell_centroids()
+    for r, p in enumerate(built):
+        lm, k, g = views[r]
+        assert np.array_equal(np.sort(p.ghost_global), np.sort(g[k:]))
+        assert np.array_equal(p.ghost_owner, owner[p.ghost_global]) and np.all(np.diff(p.ghost_owner) >= 0)
+        glob = np.concatenate([p.owned_global, p.ghost_global])
+        assert np.allclose(p.mesh.cell_centroids(), cent[glob], atol=1e-9)
+        # neighbours: local ids point at the right global cells; unknown only on ghosts; exterior markers kept
+        nb_l, nb_g = p.mesh.nbr, mesh.nbr[glob]
+        # the local cell may list its facets in the global cell's order only (vertex order is kept by the view)
+        loc = nb_l >= 0
+        assert np.array_equal(glob[nb_l[loc]], nb_g[loc])
+        unk = nb_l == INT32_MIN
+        assert not unk[:p.n_owned].any() and np.all(nb_g[unk] >= 0)
+        ext = (nb_l < 0) & ~unk
+        assert np.array_equal(ext, nb_g < 0)
+        assert np.array_equal(p.mesh.bf_marker[-(nb_l[ext] + 1)], mesh.bf_marker[-(nb_g[ext] + 1)])
+        for q in range(world):
+            if q == r:
+                continue
+            want = built[q].ghost_global[built[q].ghost_owner == r]
+            got = p.owned_global[p.send_lists[q]] if q in p.send_lists else np.zeros(0, np.int64)
+            assert np.array_equal(got, want)
+    # fused push emulation: every rank's ghost block is filled with the owners' records, nothing else is touched
+    rec = np.arange(mesh.n_cells, dtype=np.float64) + 0.5
+    pads = [((p.n_owned + P - 1) // P) * P for p in built]
+    state = [np.full(pads[r] + p.n_ghost, -1.0) for r, p in enumerate(built)]
+    for r, p in enumerate(built):
+        state[r][:p.n_owned] = rec[p.owned_global]
+    for r, p in enumerate(built):
+        if not p.send_lists:
+            continue
+        send_idx = np.concatenate([p.send_lists[q] for q in range(world) if q in p.send_lists])
+        n_patches = pads[r] // P
+        order, push_ptr, push_cell, perm = fused_push_tables(send_idx, n_patches, P)
+        dst = []
+        for q in range(world):
+            if q not in p.send_lists:
+                continue
+            first = int((built[q].ghost_owner < r).sum())
+            dst += [(q, pads[q] + first + i) for i in range(p.send_lists[q].shape[0])]
+        dst = [dst[e] for e in perm]
+        for b in range(push_ptr.shape[0] - 1):
+            for e in range(push_ptr[b], push_ptr[b + 1]):
+                q, slot = dst[e]
+                state[q][slot] = state[r][order[b] * P + push_cell[e]]
+    for r, p in enumerate(built):
+        assert np.array_equal(state[r][pads[r]:], rec[p.ghost_global])
+        assert np.array_equal(state[r][:p.n_owned], rec[p.owned_global])
