@@ -172,7 +172,7 @@ def thacker_run(n, dt, stepper_cls, alpha_max=None, n_steps=None):
     NB the alpha: the reference test keeps `wetting_and_drying_alpha_max` at its default of 2 m (options.py:897-902) and
     runs its implicit integrators.  With that alpha the plain-mass step breaks down whatever dt and the displaced-mass
     step needs dt = 2 s (21 600 steps: 0.2397, inside all the reference's thresholds for this mesh --
-    scripts/thacker_reference_alpha_oracle.py, too slow for this suite; last test below), so the two comparisons here
+    tests/thacker_reference_alpha_oracle.py, too slow for this suite; last test below), so the two comparisons here
     are made with the cap lifted (`wetting_and_drying_alpha_max = None`, alpha = 5 - 44 m on the 10 x 10 mesh)."""
     p = K.thacker_problem(n, alpha_max)
     orc = O.SWEOracle(p["mesh"], p["bath"], options=dict(use_wetting_and_drying=True, wetting_and_drying_alpha=p["alpha"]))
@@ -226,7 +226,7 @@ def test_thacker_default_alpha_cap_defeats_both_explicit_steps_at_ordinary_time_
     (1 + H / sqrt(H^2 + alpha^2)) / 2 of 1e-4 and a transport depth of centimetres: the plain-mass step runs into
     non-finite values at about half a period whatever the time step (2 s ... 300 s), and the displaced-mass step, stable
     at 100 s with the cap lifted, develops an odd-even instability of the dry-region elevation within 40 steps of 10 s;
-    it needs dt = 2 s there (scripts/thacker_reference_alpha_oracle.py: full period, error 0.2397 < 0.26).  The
+    it needs dt = 2 s there (tests/thacker_reference_alpha_oracle.py: full period, error 0.2397 < 0.26).  The
     reference runs this set-up with implicit integrators only."""
     p, orc, eta, centre, _ = thacker_run(10, 100.0, O.ShuOsherStepper, alpha_max=2.0)
     assert not np.isfinite(eta).all()

@@ -5,7 +5,7 @@ numpy oracle -- too slow for the test suite, run once for DESIGN.md section 6:
 
     DONE err 0.2397 (thresholds of the reference on this mesh: 0.26 second-order implicit, 0.33 BackwardEuler)
 
-    python scripts/thacker_reference_alpha_oracle.py
+    python tests/thacker_reference_alpha_oracle.py
 """
 import sys; import os; ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,os.path.join(ROOT,'tests')); sys.path.insert(0,ROOT)
 import numpy as np, time, warnings
