@@ -72,6 +72,17 @@ def test_product_package_never_imports_the_oracle():
                 assert "oracle" not in re.sub(r"#.*|//.*", "", src).replace("swe_oracle.py", ""), f
 
 
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """The oracle is test infrastructure: besides tests/, only `__graft_entry__` (build of the checker + smoke()) and
+    `bench.py` (cpu_baseline / reference arm) may import it -- not the harness the bench drives, not the dev scripts."""
+    for sub in ("harness", "scripts"):
+        for dp, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dp, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(sub, f)
+
+
 # ---------------------------------------------------------------- mesh toolkit
 def test_rectangle_mesh_conventions():
     m = M.rectangle_mesh(25, 2, 40e3, 2e3)
