@@ -217,3 +217,72 @@ class OracleEngine:
         if u0 is not None:
             new = new + a0 * self._rec(u0, 3)
         self._rec(dst, 3)[...] = new
+
+
+class DistributedOracleEngine(OracleEngine):
+    """
+    The same double for ONE RANK of a distributed run: `mesh` = owned cells followed by ghost cells whose outer facets
+    have no neighbour on this rank (INT32_MIN in `nbr`).  Patch size 1, so the ghost block follows the owned cells
+    directly (`n_owned_pad == n_owned`) and a state buffer is one contiguous array of cell records.  Every stage is
+    evaluated on ALL local cells with the unknown facets closed by a fake marker: the ghost results are meaningless
+    and must be overwritten by the halo exchange that follows each stage -- which is exactly what is under test
+    (`thetis_b200.parallel.HaloPlan` and the integrators' distributed code paths, on the CPU over gloo).
+    """
+    FAKE = 999
+
+    def __init__(self, mesh, n_owned, boundary_len):
+        from thetis_b200.mesh import Mesh2D
+        nbr = mesh.nbr.astype(np.int64)
+        unknown = nbr == np.iinfo(np.int32).min
+        assert not unknown[:n_owned].any()
+        nfake = int(unknown.sum())
+        nbr[unknown] = -(1 + mesh.n_bfacets + np.arange(nfake))
+        cu, fu = np.nonzero(unknown)
+        closed = Mesh2D(coords=mesh.coords, cells=mesh.cells, topo=mesh.topo, periodic=mesh.periodic)
+        closed.nbr, closed.nbr_lf = nbr.astype(np.int32), mesh.nbr_lf
+        closed.bf_cell = np.concatenate([mesh.bf_cell, cu]).astype(np.int32)
+        closed.bf_lf = np.concatenate([mesh.bf_lf, fu]).astype(np.int8)
+        closed.bf_marker = np.concatenate([mesh.bf_marker, np.full(nfake, self.FAKE)]).astype(np.int32)
+        super().__init__(closed)
+        self.n_real_bfacets = mesh.n_bfacets
+        self.n_owned = self.n_owned_pad = int(n_owned)
+        self.patch_size, self.n_patches = 1, int(n_owned)
+        self.state_len, self.tracer_len = mesh.n_cells * 9, mesh.n_cells * 3
+        self.boundary_len = {int(k): float(v) for k, v in boundary_len.items()}
+        self.n_gathers = 0
+
+    def set_boundary_length(self, marker, length):
+        self.boundary_len[int(marker)] = float(length)         # global lengths (flux boundary data divide by them)
+
+    def set_bc_array(self, eq, marker, tag, values):
+        v = np.array(values, dtype=float, copy=True)
+        pad = np.zeros((self.mesh.n_bfacets - v.shape[0],) + v.shape[1:])
+        super().set_bc_array(eq, marker, tag, np.concatenate([v, pad]))
+
+    def swe_oracle(self):
+        orc = super().swe_oracle()
+        orc.boundary_len = dict(self.boundary_len)
+        orc.boundary_len[self.FAKE] = 1.0
+        return orc
+
+    # the real kernels advance owned cells only and leave the ghost block of their output STALE: the double poisons
+    # it, so that one missing or misdirected exchange reaches an owned cell as NaN in the very next stage (without
+    # this, the redundancy of a vertex overlap hides a single dropped exchange)
+    def _poison_ghosts(self, buf, width):
+        buf.view(-1, width)[self.n_owned:] = float("nan")
+
+    def swe_stage(self, a0, a1, bdt, src, u0, dst):
+        super().swe_stage(a0, a1, bdt, src, u0, dst)
+        self._poison_ghosts(dst, 9)
+
+    def tracer_stage(self, a0, a1, bdt, src, u0, dst, swe_state):
+        super().tracer_stage(a0, a1, bdt, src, u0, dst, swe_state)
+        self._poison_ghosts(dst, 3)
+
+    def limiter_apply_to(self, c_in, c_out):
+        super().limiter_apply_to(c_in, c_out)
+        self._poison_ghosts(c_out, 3)
+
+    def gather_cells(self, state, idx, rec, out):
+        self.n_gathers += 1
+        out[: idx.numel()] = state.view(-1, rec)[idx.long()]
