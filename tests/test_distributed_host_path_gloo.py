@@ -59,7 +59,7 @@ def _install_double():
     adaptor.MeshAdaptor.get_engine = get_engine
 
 
-def _solver(mesh_obj):
+def _solver(mesh_obj, scheme="ssprk33"):
     """SWE (nonlinear, Lax-Friedrichs, Manning drag, open boundary with elev + flux data: the flux datum divides by
     the GLOBAL boundary length) -> tracer (inflow value) -> vertex-based limiter."""
     from thetis_b200 import solver2d
@@ -74,7 +74,16 @@ def _solver(mesh_obj):
     o.simulation_end_time = DT * NSTEPS
     o.simulation_export_time = DT * NSTEPS
     o.manning_drag_coefficient = Constant(0.02)
-    o.add_tracer_2d("tracer_2d", "Depth averaged tracer", "Tracer2d")
+    kw = {}
+    if scheme == "erk_viscous":
+        # Butcher-form ERK (tendency buffers + tb_lincomb: ghost blocks are read outside the Shu-Osher stage order),
+        # SIPG viscosity as a P1 field and tracer diffusion (neighbour gradients across the partition cut)
+        o.swe_timestepper_type = o.tracer_timestepper_type = "ERKLSPUM2"
+        o.horizontal_viscosity = Function(FunctionSpace(sm, "CG", 1)).interpolate(
+            lambda x, y: 20.0 * (1.0 + 0.3 * np.sin(y / 2e3)))
+        o.use_grad_div_viscosity_term = True
+        kw["diffusivity"] = Constant(12.0)
+    o.add_tracer_2d("tracer_2d", "Depth averaged tracer", "Tracer2d", **kw)
     o.use_limiter_for_tracers = True
     s.bnd_functions["shallow_water"] = {1: {"elev": Constant(0.2), "flux": Constant(-400.0)},
                                         2: {"elev": Constant(0.0), "uv": Constant((0.05, 0.0))}}
@@ -121,7 +130,7 @@ def _local_view(mesh, owner, rank, seed):
     return lm, owned.shape[0], gids
 
 
-def _worker(rank, world, port, route, out):
+def _worker(rank, world, port, route, scheme, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world, timeout=timedelta(seconds=120))
@@ -143,7 +152,7 @@ def _worker(rank, world, port, route, out):
             sm = ShimMesh(part.mesh)
             sm.boundary_len = dict(part.mesh.meta["global_boundary_len"])
             sm.halo_plan = plan
-        s = _solver(sm)
+        s = _solver(sm, scheme)
         uv, eta, q = _run(s)
         plan = sm.halo_plan
         eng = s.timestepper.timesteppers["swe2d"].engine
@@ -155,35 +164,43 @@ def _worker(rank, world, port, route, out):
         dist.destroy_process_group()
 
 
-@pytest.fixture(scope="module")
-def single_rank():
+_SINGLE = {}
+
+
+def _single_rank(scheme):
     """The same classes on the same double, one rank -- in a process of its own (the double is patched in globally)."""
     import subprocess
+    if scheme in _SINGLE:
+        return _SINGLE[scheme]
     ref = os.path.join(HERE, "_dist_ref_%d.npz" % os.getpid())
     code = ("import sys; sys.path.insert(0, %r); import numpy as np; import test_distributed_host_path_gloo as T; "
-            "T._install_double(); uv, eta, q = T._run(T._solver(T._mesh())); np.savez(%r, uv=uv, eta=eta, q=q)" % (HERE, ref))
+            "T._install_double(); uv, eta, q = T._run(T._solver(T._mesh(), %r)); np.savez(%r, uv=uv, eta=eta, q=q)"
+            % (HERE, scheme, ref))
     try:
         subprocess.run([sys.executable, "-c", code], check=True, cwd=os.path.dirname(HERE), timeout=600)
         g = np.load(ref)
-        return g["uv"], g["eta"], g["q"]
+        _SINGLE[scheme] = (g["uv"], g["eta"], g["q"])
+        return _SINGLE[scheme]
     finally:
         if os.path.exists(ref):
             os.remove(ref)
 
 
-@pytest.mark.parametrize("route,world", [("partition", 2), ("partition", 3), ("local", 2), ("local", 3)])
-def test_distributed_host_classes_reproduce_the_single_rank_run(single_rank, route, world):
+@pytest.mark.parametrize("route,world,scheme", [("partition", 2, "ssprk33"), ("partition", 3, "ssprk33"),
+                                                ("local", 2, "ssprk33"), ("local", 3, "ssprk33"),
+                                                ("partition", 2, "erk_viscous"), ("local", 3, "erk_viscous")])
+def test_distributed_host_classes_reproduce_the_single_rank_run(route, world, scheme):
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), route, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), route, scheme, out), nprocs=world, join=True)
     assert len(out) == world
-    uv1, eta1, q1 = single_rank
+    uv1, eta1, q1 = _single_rank(scheme)
     assert np.abs(q1 - 4.5).max() > 0.5 and np.abs(uv1).max() > 1e-3          # something happened
     seen = []
     for r in range(world):
         cells, uv, eta, q, n_stage, n_gather, n_ghost = out[r]
         seen.append(cells)
-        assert n_ghost > 0 and n_gather >= 6 * NSTEPS          # 3 SWE + 3 tracer stages + limiter, exchanged every time
+        assert n_ghost > 0 and n_gather >= 5 * NSTEPS          # every SWE / tracer stage and the limiter is exchanged
         for name, a, b in (("uv", uv, uv1[cells]), ("eta", eta, eta1[cells]), ("tracer", q, q1[cells])):
             err = np.abs(a - b).max() / np.abs(b).max()
             assert err < 1e-12, (route, r, name, err)                          # NaN (a stale ghost was read) fails too
