@@ -635,8 +635,12 @@ def init_torch_distributed_from_comm(comm, backend=None):
         addr_port = (addr, port)
     addr, port = comm.bcast(addr_port, root=0)
     use_cuda = torch.cuda.is_available()
+    kw = {}
     if use_cuda:
-        torch.cuda.set_device(local_rank % torch.cuda.device_count())
+        dev = local_rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        if (backend or "nccl") == "nccl":
+            kw["device_id"] = torch.device("cuda", dev)      # binds the communicator to this GPU (as bench.py does)
     dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), init_method=f"tcp://{addr}:{port}",
-                            rank=rank, world_size=world)
+                            rank=rank, world_size=world, **kw)
     return rank, world
