@@ -3,7 +3,8 @@ The DISTRIBUTED code paths of the host classes end to end on the CPU: `SSPRK33` 
 coupled integrator and `HaloPlan` (buffer allocation with the ghost block behind the owned cells, send lists,
 per-stage exchange over torch.distributed) run on 2 and 3 gloo ranks against the oracle-backed engine double
 (tests/oracle_engine.py: DistributedOracleEngine poisons the ghost block of every stage output like the real kernels
-leave it stale, so one missing or misdirected exchange reaches an owned cell as NaN in the next stage), and must reproduce the single-rank run of the same classes.
+leave it stale, so one missing or misdirected exchange reaches an owned cell as NaN in the next stage), and must
+reproduce the single-rank run of the same classes.
 
 Two ways to the halo plan: `distribute_mesh` (the library's own partitioner, the route of every multi-GPU
 measurement) and `plan_from_local_mesh` (a mesh that arrives distributed: scattered ownership, scrambled local

@@ -23,7 +23,8 @@ import numpy as np
 from .mesh import Mesh2D, FACET_NODES
 
 __all__ = ["LocalPart", "PeerInfo", "partition_mesh", "HaloPlan", "distribute_mesh", "exchange_halo",
-           "mark_unknown_facets", "build_overlap_connectivity", "local_contribution", "part_from_gathered", "plan_from_local_mesh", "init_torch_distributed_from_comm"]
+           "mark_unknown_facets", "build_overlap_connectivity", "local_contribution", "part_from_gathered",
+           "plan_from_local_mesh", "init_torch_distributed_from_comm"]
 
 INT32_MIN = np.iinfo(np.int32).min
 
