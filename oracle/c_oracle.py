@@ -16,8 +16,22 @@ SRC = os.path.join(HERE, "swe_oracle.c")
 LIB = os.path.join(HERE, "_build", "libswe_oracle.so")
 
 
+def _host_signature():
+    """Instruction-set flags of this host: the library is built with -march=native and travels with the repo to other
+    machines (gpurun snapshot), where a different CPU must trigger a rebuild instead of an illegal instruction."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha1(" ".join(sorted(flags.split(":")[-1].split())).encode()).hexdigest()
+
+
 def build(force=False):
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+    sig_file, sig = LIB + ".host", _host_signature()
+    same_host = os.path.exists(sig_file) and open(sig_file).read().strip() == sig
+    if not force and same_host and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", LIB, SRC, "-lm"]
@@ -28,6 +42,8 @@ def build(force=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("gcc failed building the C oracle:\n" + r.stderr)
+    with open(sig_file, "w") as f:
+        f.write(sig + "\n")
     return LIB
 
 
