@@ -34,14 +34,23 @@ def build(force=False):
     if not force and same_host and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", LIB, SRC, "-lm"]
+    tmp = f"{LIB}.tmp{os.getpid()}"              # built aside and renamed: concurrent processes never load a partial file
+    cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", tmp, SRC, "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         # -march=native may be unavailable on exotic hosts
         cmd.remove("-march=native")
         r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+            import warnings
+            warnings.warn("gcc could not rebuild the C oracle for this host; using the library built elsewhere:\n"
+                          + r.stderr[-500:], RuntimeWarning)
+            return LIB
         raise RuntimeError("gcc failed building the C oracle:\n" + r.stderr)
+    os.replace(tmp, LIB)
     with open(sig_file, "w") as f:
         f.write(sig + "\n")
     return LIB
