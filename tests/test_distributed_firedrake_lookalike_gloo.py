@@ -58,14 +58,20 @@ class _Mixed:
         return self._fs
 
 
-def _stepper(mesh_obj, mixed_space, uv_f, eta_f, bath_f):
+def _tide(x, y, t):
+    return 0.2 + 0.1 * np.sin(2 * np.pi * t / 600.0) * (1.0 + y / LY)
+
+
+def _stepper(mesh_obj, mixed_space, uv_f, eta_f, bath_f, tide_f):
     from thetis_b200 import rungekutta
     from thetis_b200.equations import ShallowWaterEquations, DepthExpression
     from thetis_b200.options import ModelOptions2d
     from thetis_b200.shim import Constant
     o = ModelOptions2d()
     eq = ShallowWaterEquations(mixed_space, DepthExpression(bath_f, True, False), o)
-    bnd = {1: {"elev": Constant(0.2), "flux": Constant(-300.0)}, 2: {"elev": Constant(0.0), "uv": Constant((0.05, 0.0))}}
+    # marker 1: a Function-valued tidal elevation re-assigned by update_forcings before every stage (the North-Sea
+    # pattern, examples/north_sea/model_config.py:188-192) + a flux datum (divides by the GLOBAL boundary length)
+    bnd = {1: {"elev": tide_f, "flux": Constant(-300.0)}, 2: {"elev": Constant(0.0), "uv": Constant((0.05, 0.0))}}
     fields = {"manning_drag_coefficient": Constant(0.02), "lax_friedrichs_velocity_scaling_factor": Constant(1.0)}
     return rungekutta.SSPRK33(eq, _Mixed(mixed_space, uv_f, eta_f), fields, DT, o.swe_timestepper_options, bnd,
                               sync_policy="every_step")
@@ -105,12 +111,19 @@ def _worker(rank, world, port, out):
         bath_f = func(_bath(xy[:, 0], xy[:, 1]))
         # the overlap rows of the host solution start out WRONG (a stale PyOP2 halo): the owners' values must win
         eta_f.dat.data_with_halos[3 * n_owned:] = 77.0
-        ti = _stepper(fm, mixed, uv_f, eta_f, bath_f)
+        tide_f = func(_tide(xy[:, 0], xy[:, 1], 0.0))
+
+        def update_forcings(t):
+            tide_f.dat.data_with_halos[...] = _tide(xy[:, 0], xy[:, 1], t)
+            tide_f.dat.dat_version += 1                       # PyOP2 bumps the version on write access
+        ti = _stepper(fm, mixed, uv_f, eta_f, bath_f, tide_f)
         assert ti.adaptor.with_halos and ti.halo is not None and ti.halo.world == world and ti.adaptor.n_owned == n_owned
         t = 0.0
         for _ in range(NSTEPS):
-            ti.advance(t)
+            ti.advance(t, update_forcings)
             t += DT
+        from thetis_b200 import _lib as L
+        assert (0, 1, L.BC_ELEV) in ti.engine.bc_arrays      # the tidal Function went out as a boundary array
         out[rank] = (fm.gids.copy(), n_owned, fm.local_cells_global_vertices.copy(),
                      uv_f.dat.data_ro_with_halos.reshape(n_local, 3, 2).copy(),
                      eta_f.dat.data_ro_with_halos.reshape(n_local, 3).copy(),
@@ -128,10 +141,11 @@ def _single_rank(path):
     uv_f = Function(FunctionSpace(sm, "DG", 1, value_size=2))
     eta_f = Function(dg).interpolate(_eta0)
     bath_f = Function(dg).interpolate(_bath)
-    ti = _stepper(sm, types.SimpleNamespace(mesh=lambda: sm), uv_f, eta_f, bath_f)
+    tide_f = Function(dg).interpolate(lambda x, y: _tide(x, y, 0.0))
+    ti = _stepper(sm, types.SimpleNamespace(mesh=lambda: sm), uv_f, eta_f, bath_f, tide_f)
     t = 0.0
     for _ in range(NSTEPS):
-        ti.advance(t)
+        ti.advance(t, lambda tt: tide_f.interpolate(lambda x, y: _tide(x, y, tt)))
         t += DT
     np.savez(path, uv=np.array(uv_f.dat.data_ro).reshape(-1, 3, 2), eta=np.array(eta_f.dat.data_ro).reshape(-1, 3))
 
