@@ -502,14 +502,20 @@ def local_contribution(mesh: Mesh2D, n_owned, global_ids):
                 boundary_len=_owned_boundary_length(mesh, n_owned))
 
 
-def _owners_of(ids, gathered):
-    """Owner rank of every global cell id in `ids` (-1: owned by nobody)."""
+def _owner_table(gathered):
+    """(sorted global ids of all owned cells, their owner ranks): the lookup table behind `_owners_of`."""
     allo = np.concatenate([g["owned"] for g in gathered])
     allr = np.concatenate([np.full(g["owned"].shape[0], r, dtype=np.int32) for r, g in enumerate(gathered)])
     so = np.argsort(allo, kind="stable")
     allo, allr = allo[so], allr[so]
     if np.any(allo[1:] == allo[:-1]):
         raise ValueError("a cell is owned by two ranks")
+    return allo, allr
+
+
+def _owners_of(ids, table):
+    """Owner rank of every global cell id in `ids` (-1: owned by nobody)."""
+    allo, allr = table
     if ids.size == 0:
         return np.zeros(0, dtype=np.int32)
     if allo.size == 0:
@@ -532,7 +538,8 @@ def part_from_gathered(mesh: Mesh2D, n_owned, global_ids, gathered, rank, halo="
     gids = np.asarray(global_ids, dtype=np.int64)
     n_owned = int(n_owned)
     ghost_g = gids[n_owned:]
-    go = _owners_of(ghost_g, gathered)
+    table = _owner_table(gathered)
+    go = _owners_of(ghost_g, table)
     if np.any(go < 0) or np.any(go == rank):
         raise ValueError("overlap cell owned by no other rank: global ids and ownership are inconsistent")
     own_nbr = mesh.nbr[:n_owned]
@@ -552,7 +559,7 @@ def part_from_gathered(mesh: Mesh2D, n_owned, global_ids, gathered, rank, halo="
     sorted_owned = new_gids[:n_owned][so]
     send, peers = {}, []
     for q, g in enumerate(gathered):
-        qo = _owners_of(g["ghost"], gathered) if q != rank else go
+        qo = _owners_of(g["ghost"], table) if q != rank else go
         peers.append(PeerInfo(q, g["owned"].shape[0], g["ghost"].shape[0], np.sort(qo)))
         if q == rank:
             continue
