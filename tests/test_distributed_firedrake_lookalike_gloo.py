@@ -80,7 +80,7 @@ def _stepper(mesh_obj, mixed_space, uv_f, eta_f, bath_f, tide_f):
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=timedelta(seconds=120))
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=timedelta(seconds=300))
     try:
         import test_firedrake_lookalike_mesh as LK
         from test_distributed_host_path_gloo import _install_double

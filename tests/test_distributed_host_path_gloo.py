@@ -137,7 +137,7 @@ SCHEMES = ("ssprk33", "erk_viscous")
 def _worker(rank, world, port, route, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=timedelta(seconds=120))
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=timedelta(seconds=300))
     try:
         _install_double()
         from thetis_b200 import parallel as PA
