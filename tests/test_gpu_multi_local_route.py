@@ -32,7 +32,7 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(0)
-    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=timedelta(seconds=120))
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=timedelta(seconds=240))
     try:
         import test_gpu_multi as TM
         from test_distributed_host_path_gloo import _local_view
