@@ -1,6 +1,6 @@
 """
-The drop-in on a mesh that Firedrake distributed itself, end to end on the CPU (2 gloo ranks): `SSPRK33` is
-constructed on Firedrake-SHAPED objects of one MPI rank -- a mesh with owned cells + a vertex overlap, clockwise
+The drop-in on a mesh that Firedrake distributed itself, end to end on the CPU (2 gloo ranks): `SSPRK33` (SWE, then
+tracer) and the vertex-based limiter are constructed on Firedrake-SHAPED objects of one MPI rank -- a mesh with owned cells + a vertex overlap, clockwise
 cells, private vertex numbering, `cell_set.size / total_size`, `cell_node_map().values / values_with_halo`, a global
 DG0 `lgmap`, `Function.dat.data(_ro) / data(_ro)_with_halos`, `mesh.comm` -- exactly as
 `thetis.solver2d.FlowSolver2d.get_swe_timestepper` would construct it under `mpiexec -n 2`
@@ -77,6 +77,26 @@ def _stepper(mesh_obj, mixed_space, uv_f, eta_f, bath_f, tide_f):
                               sync_policy="every_step")
 
 
+def _q0(x, y):
+    return 4.5 + 2.0 * ((np.abs(x - LX / 2) < 2.5e3) & (np.abs(y - LY / 2) < 2e3))
+
+
+def _tracer_stepper(space, uv_f, eta_f, q_f, bath_f):
+    """what FlowSolver2d.get_tracer_timestepper builds (solver2d.py:576-598) + the limiter of solver2d.py:535-539"""
+    from thetis_b200 import rungekutta
+    from thetis_b200.equations import TracerEquation2D, DepthExpression
+    from thetis_b200.limiter import VertexBasedP1DGLimiter
+    from thetis_b200.options import ModelOptions2d
+    from thetis_b200.shim import Constant
+    o = ModelOptions2d()
+    o.add_tracer_2d("tracer_2d", "Depth averaged tracer", "Tracer2d")
+    eq = TracerEquation2D("tracer_2d", space, DepthExpression(bath_f, True, False), o, uv_f)
+    fields = {"elev_2d": eta_f, "uv_2d": uv_f, "tracer_advective_velocity_factor": Constant(1.0)}
+    ti = rungekutta.SSPRK33(eq, q_f, fields, DT, o.tracer_timestepper_options, {1: {"value": Constant(4.0)}},
+                            sync_policy="every_step")
+    return ti, VertexBasedP1DGLimiter(space)
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -118,16 +138,21 @@ def _worker(rank, world, port, out):
             tide_f.dat.dat_version += 1                       # PyOP2 bumps the version on write access
         ti = _stepper(fm, mixed, uv_f, eta_f, bath_f, tide_f)
         assert ti.adaptor.with_halos and ti.halo is not None and ti.halo.world == world and ti.adaptor.n_owned == n_owned
+        q_f = func(_q0(xy[:, 0], xy[:, 1]))
+        tr, lim = _tracer_stepper(space, uv_f, eta_f, q_f, bath_f)
+        assert tr.adaptor is ti.adaptor and lim.halo is ti.halo            # one adaptor / plan / engine per mesh
         t = 0.0
         for _ in range(NSTEPS):
-            ti.advance(t, update_forcings)
+            ti.advance(t, update_forcings)                                  # coupled_timeintegrator_2d.py:94-105
+            tr.advance(t, update_forcings)
+            lim.apply(q_f)
             t += DT
         from thetis_b200 import _lib as L
         assert (0, 1, L.BC_ELEV) in ti.engine.bc_arrays      # the tidal Function went out as a boundary array
         out[rank] = (fm.gids.copy(), n_owned, fm.local_cells_global_vertices.copy(),
                      uv_f.dat.data_ro_with_halos.reshape(n_local, 3, 2).copy(),
                      eta_f.dat.data_ro_with_halos.reshape(n_local, 3).copy(),
-                     int(ti.engine.n_gathers))
+                     int(ti.engine.n_gathers), q_f.dat.data_ro_with_halos.reshape(n_local, 3).copy())
     finally:
         dist.destroy_process_group()
 
@@ -143,11 +168,17 @@ def _single_rank(path):
     bath_f = Function(dg).interpolate(_bath)
     tide_f = Function(dg).interpolate(lambda x, y: _tide(x, y, 0.0))
     ti = _stepper(sm, types.SimpleNamespace(mesh=lambda: sm), uv_f, eta_f, bath_f, tide_f)
+    q_f = Function(dg).interpolate(_q0)
+    tr, lim = _tracer_stepper(dg, uv_f, eta_f, q_f, bath_f)
+    uf = lambda tt: tide_f.interpolate(lambda x, y: _tide(x, y, tt))
     t = 0.0
     for _ in range(NSTEPS):
-        ti.advance(t, lambda tt: tide_f.interpolate(lambda x, y: _tide(x, y, tt)))
+        ti.advance(t, uf)
+        tr.advance(t, uf)
+        lim.apply(q_f)
         t += DT
-    np.savez(path, uv=np.array(uv_f.dat.data_ro).reshape(-1, 3, 2), eta=np.array(eta_f.dat.data_ro).reshape(-1, 3))
+    np.savez(path, uv=np.array(uv_f.dat.data_ro).reshape(-1, 3, 2), eta=np.array(eta_f.dat.data_ro).reshape(-1, 3),
+             q=np.array(q_f.dat.data_ro).reshape(-1, 3))
 
 
 def test_ssprk33_on_a_distributed_firedrake_shaped_mesh():
@@ -162,21 +193,21 @@ def test_ssprk33_on_a_distributed_firedrake_shaped_mesh():
                         "import test_distributed_firedrake_lookalike_gloo as T; T._single_rank(%r)" % (HERE, ref)],
                        check=True, cwd=os.path.dirname(HERE), timeout=600)
         g = np.load(ref)
-        uv1, eta1 = g["uv"], g["eta"]
+        uv1, eta1, q1 = g["uv"], g["eta"], g["q"]
     finally:
         if os.path.exists(ref):
             os.remove(ref)
     src = _src_mesh()
-    assert np.abs(uv1).max() > 1e-3
+    assert np.abs(uv1).max() > 1e-3 and np.abs(q1 - 4.5).max() > 0.5
     owned_all = []
     for r in range(world):
-        gids, n_owned, lcgv, uv, eta, n_gathers = out[r]
-        assert n_gathers >= 3 * NSTEPS + 1                     # the upload and every stage were exchanged
+        gids, n_owned, lcgv, uv, eta, n_gathers, q = out[r]
+        assert n_gathers >= 7 * NSTEPS + 2                     # uploads, every SWE / tracer stage and the limiter exchanged
         owned_all.append(gids[:n_owned])
         # local (cell, node a) sits at global vertex lcgv[c, a] = node j of the global cell gids[c]
         j = np.argmax(src.cells[gids][:, None, :] == lcgv[:, :, None], axis=2)
         idx = gids[:, None]
-        for name, a, b in (("uv", uv, uv1[idx, j]), ("eta", eta, eta1[idx, j])):
+        for name, a, b in (("uv", uv, uv1[idx, j]), ("eta", eta, eta1[idx, j]), ("tracer", q, q1[idx, j])):
             for what, sl in (("owned", slice(0, n_owned)), ("overlap", slice(n_owned, None))):
                 err = np.abs(a[sl] - b[sl]).max() / np.abs(b).max()
                 assert err < 1e-12, (r, name, what, err)         # overlap rows of the host Functions are current too
