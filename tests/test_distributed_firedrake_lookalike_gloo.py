@@ -1,7 +1,7 @@
 """
 The drop-in on a mesh that Firedrake distributed itself, end to end on the CPU (2 gloo ranks): `SSPRK33` (SWE, then
-tracer) and the vertex-based limiter are constructed on Firedrake-SHAPED objects of one MPI rank -- a mesh with owned cells + a vertex overlap, clockwise
-cells, private vertex numbering, `cell_set.size / total_size`, `cell_node_map().values / values_with_halo`, a global
+tracer) and the vertex-based limiter are constructed on Firedrake-SHAPED objects of one MPI rank -- a mesh with owned
+cells + a vertex overlap, clockwise cells, private vertex numbering, `cell_set.size / total_size`, `cell_node_map().values / values_with_halo`, a global
 DG0 `lgmap`, `Function.dat.data(_ro) / data(_ro)_with_halos`, `mesh.comm` -- exactly as
 `thetis.solver2d.FlowSolver2d.get_swe_timestepper` would construct it under `mpiexec -n 2`
 (solver2d.py:542-573).  The adaptor must build the halo plan from the communicator, the integrator must read the
